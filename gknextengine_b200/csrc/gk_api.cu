@@ -1,0 +1,473 @@
+// gk_api.cu — the C ABI of libgknext_cuda.so (include/gkcu.h). Thin: owns device memory, orders the passes of a frame
+// on one CUDA stream, converts failures into return codes + gkcu_last_error(). There is no CPU fallback anywhere: every
+// entry point either runs the sm_100a kernels or fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "gk_context.h"
+
+struct GkcuContext {
+    gkcu::Context c;
+};
+
+namespace gkcu {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+bool check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+bool DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap && p) return true;
+    if (bytes == 0) bytes = 16;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    if (!check(cudaMalloc(&p, want), "cudaMalloc")) { p = nullptr; return false; }
+    cap = want;
+    return true;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+static int alloc_zero(void** p, size_t bytes, cudaStream_t st) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    GK_CUDA(cudaMalloc(p, bytes));
+    GK_CUDA(cudaMemsetAsync(*p, 0, bytes, st));
+    return 0;
+}
+
+static void free_targets(RenderTargets& t) {
+    void** ptrs[] = {(void**)&t.accum_diffuse[0], (void**)&t.accum_diffuse[1], (void**)&t.accum_specular[0], (void**)&t.accum_specular[1],
+                     (void**)&t.accum_albedo[0], (void**)&t.accum_albedo[1], (void**)&t.single_diffuse, (void**)&t.single_specular,
+                     (void**)&t.albedo, (void**)&t.normal, (void**)&t.denoised, (void**)&t.objectid[0], (void**)&t.objectid[1],
+                     (void**)&t.primitiveid, (void**)&t.motion, (void**)&t.prev_depth, (void**)&t.moment};
+    for (void** p : ptrs) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    t.w = t.h = 0;
+}
+
+static int upload_tex_table(Context& c) {
+    struct TexDescHost { const float4* texels; uint32_t w, h, pad; };
+    std::vector<TexDescHost> tab(c.textures.size());
+    for (size_t i = 0; i < c.textures.size(); ++i) tab[i] = {c.textures[i].texels, c.textures[i].w, c.textures[i].h, 0};
+    if (!c.tex_table.reserve(std::max<size_t>(1, tab.size()) * sizeof(TexDescHost))) return 1;
+    if (!tab.empty()) GK_CUDA(cudaMemcpyAsync(c.tex_table.p, tab.data(), tab.size() * sizeof(TexDescHost), cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    c.tex_count = (uint32_t)tab.size();
+    return 0;
+}
+
+}  // namespace gkcu
+
+using namespace gkcu;
+
+#define CTX_OR_FAIL(ctx)                                   \
+    if (!(ctx)) { set_error("null context"); return 1; }   \
+    Context& c = (ctx)->c;                                 \
+    if (!check(cudaSetDevice(c.device), "cudaSetDevice")) return 1;
+
+extern "C" {
+
+const char* gkcu_last_error(void) { return g_error.c_str(); }
+
+int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
+    if (!out_ctx) { set_error("gkcu_create: out_ctx is null"); return 1; }
+    *out_ctx = nullptr;
+    int count = 0;
+    if (!check(cudaGetDeviceCount(&count), "cudaGetDeviceCount") || count == 0) {
+        if (g_error.empty()) set_error("no CUDA device visible: libgknext_cuda has no CPU fallback");
+        return 1;
+    }
+    if (device_ordinal < 0 || device_ordinal >= count) { set_error("gkcu_create: bad device ordinal"); return 1; }
+    GK_CUDA(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    GK_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major < 10) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device_ordinal, prop.major, prop.minor);
+        set_error(msg);
+        return 1;
+    }
+    GkcuContext* ctx = new GkcuContext();
+    Context& c = ctx->c;
+    c.device = device_ordinal;
+    c.sm_count = prop.multiProcessorCount;
+    if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
+    for (auto& e : c.ev) cudaEventCreate(&e);
+    if (!c.ubo.reserve(sizeof(GkUniformBufferObject))) { delete ctx; return 1; }
+    *out_ctx = ctx;
+    return 0;
+}
+
+int gkcu_destroy(GkcuContext* ctx) {
+    if (!ctx) return 0;
+    Context& c = ctx->c;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    path_release(c);
+    free_targets(c.rt);
+    for (auto& t : c.textures)
+        if (t.texels) cudaFree(t.texels);
+    DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
+                      &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
+                      &c.inst_hi, &c.tex_table, &c.cubes, &c.voxels, &c.ubo, &c.trace_rays, &c.trace_hits};
+    for (DevBuf* b : bufs) b->release();
+    BuildScratch& s = c.scratch;
+    DevBuf* sb[] = {&s.prim_lo, &s.prim_hi, &s.keys, &s.keys_sorted, &s.order, &s.order_tmp, &s.sort_tmp, &s.n2_lo, &s.n2_hi, &s.n2_left, &s.n2_right,
+                    &s.n2_parent, &s.n2_first, &s.n2_count, &s.n2_flag, &s.queue_a, &s.queue_b, &s.counters, &s.bounds, &s.bins, &s.pos_node,
+                    &s.pos_node_tmp, &s.active, &s.cursors};
+    for (DevBuf* b : sb) b->release();
+    for (auto& e : c.ev)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(c.stream);
+    delete ctx;
+    return 0;
+}
+
+int gkcu_resize(GkcuContext* ctx, uint32_t width, uint32_t height) {
+    CTX_OR_FAIL(ctx);
+    if (width == 0 || height == 0 || (uint64_t)width * height >= (1ull << 31)) { set_error("gkcu_resize: bad extent"); return 1; }
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    RenderTargets& t = c.rt;
+    free_targets(t);
+    size_t n = (size_t)width * height;
+    cudaStream_t st = c.stream;
+    for (int k = 0; k < 2; ++k) {
+        if (alloc_zero((void**)&t.accum_diffuse[k], n * 8, st) || alloc_zero((void**)&t.accum_specular[k], n * 8, st) ||
+            alloc_zero((void**)&t.accum_albedo[k], n * 8, st) || alloc_zero((void**)&t.objectid[k], n * 4, st))
+            return 1;
+    }
+    if (alloc_zero((void**)&t.single_diffuse, n * 8, st) || alloc_zero((void**)&t.single_specular, n * 8, st) || alloc_zero((void**)&t.albedo, n * 8, st) ||
+        alloc_zero((void**)&t.normal, n * 8, st) || alloc_zero((void**)&t.denoised, n * 8, st) || alloc_zero((void**)&t.primitiveid, n * 4, st) ||
+        alloc_zero((void**)&t.motion, n * 8, st) || alloc_zero((void**)&t.prev_depth, n * 4, st) || alloc_zero((void**)&t.moment, n * 2, st))
+        return 1;
+    t.w = width;
+    t.h = height;
+    t.cur = 0;
+    if (path_resize(c)) return 1;
+    GK_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gkcu_scene_upload(GkcuContext* ctx, const GkcuSceneDesc* d) {
+    CTX_OR_FAIL(ctx);
+    if (!d || !d->vertices || !d->simple_vertices || !d->indices || !d->offsets) { set_error("gkcu_scene_upload: null array"); return 1; }
+    if (d->offset_count != d->model_count * 10) { set_error("gkcu_scene_upload: offsets must hold 10 sections per model"); return 1; }
+    cudaStream_t st = c.stream;
+    if (!c.vertices.reserve((size_t)d->vertex_count * sizeof(GkGPUVertex)) || !c.simple.reserve((size_t)d->vertex_count * 8) ||
+        !c.indices.reserve((size_t)d->index_count * 4) || !c.offsets.reserve((size_t)d->offset_count * sizeof(GkModelData)))
+        return 1;
+    GK_CUDA(cudaMemcpyAsync(c.vertices.p, d->vertices, (size_t)d->vertex_count * sizeof(GkGPUVertex), cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(c.simple.p, d->simple_vertices, (size_t)d->vertex_count * 8, cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(c.indices.p, d->indices, (size_t)d->index_count * 4, cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(c.offsets.p, d->offsets, (size_t)d->offset_count * sizeof(GkModelData), cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    c.vertex_count = d->vertex_count;
+    c.index_count = d->index_count;
+    c.offset_count = d->offset_count;
+    c.model_count = d->model_count;
+    c.host_offsets.assign(d->offsets, d->offsets + d->offset_count);
+    for (uint32_t m = 0; m < c.model_count; ++m) {
+        const GkModelData& md = c.host_offsets[m * 10];
+        uint64_t idx = 0;
+        for (int s = 0; s < 10; ++s) idx += c.host_offsets[m * 10 + s].indexCount;
+        if ((uint64_t)md.indexOffset + idx > d->index_count || (uint64_t)md.vertexOffset + md.vertexCount > d->vertex_count) {
+            set_error("gkcu_scene_upload: ModelData ranges exceed the buffers");
+            return 1;
+        }
+    }
+    c.blas_built = false;
+    c.tlas_dirty = true;
+    c.tlas.node_count = 0;
+    return 0;
+}
+
+int gkcu_blas_build(GkcuContext* ctx) {
+    CTX_OR_FAIL(ctx);
+    if (c.model_count == 0) { set_error("gkcu_blas_build: no scene uploaded"); return 1; }
+    return build_all_blas(c);
+}
+
+int gkcu_blas_refit(GkcuContext* ctx, uint32_t model_index, const uint16_t* simple_vertices, uint32_t vertex_count) {
+    CTX_OR_FAIL(ctx);
+    if (!c.blas_built || model_index >= c.model_count) { set_error("gkcu_blas_refit: BLAS not built / bad model index"); return 1; }
+    const GkModelData& md = c.host_offsets[model_index * 10];
+    if (!simple_vertices || vertex_count != md.vertexCount) { set_error("gkcu_blas_refit: vertex_count must equal the model's vertex count"); return 1; }
+    GK_CUDA(cudaMemcpyAsync(c.simple.as<uint16_t>() + (size_t)md.vertexOffset * 4, simple_vertices, (size_t)vertex_count * 8, cudaMemcpyHostToDevice, c.stream));
+    return refit_blas(c, model_index);
+}
+
+int gkcu_update_nodes(GkcuContext* ctx, const GkNodeProxy* nodes, uint32_t count) {
+    CTX_OR_FAIL(ctx);
+    if (count && !nodes) { set_error("gkcu_update_nodes: null array"); return 1; }
+    if (!c.nodes.reserve(std::max<size_t>(1, count) * sizeof(GkNodeProxy))) return 1;
+    if (count) GK_CUDA(cudaMemcpyAsync(c.nodes.p, nodes, (size_t)count * sizeof(GkNodeProxy), cudaMemcpyHostToDevice, c.stream));
+    c.node_count = count;
+    // instances that make it into the TLAS (mask != 0, RayTraceBaseRenderer.cpp:178)
+    uint32_t active = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        uint32_t blas = nodes[i].modelId / 10;
+        bool a = nodes[i].visible && !nodes[i].nort && blas < c.model_count;
+        if (a) {
+            uint64_t idx = 0;
+            for (int s = 0; s < 10; ++s) idx += c.host_offsets[blas * 10 + s].indexCount;
+            if (idx / 3 == 0) a = false;
+        }
+        active += a ? 1 : 0;
+    }
+    c.tlas.prim_count = active;
+    c.tlas_dirty = true;
+    GK_CUDA(cudaStreamSynchronize(c.stream));  // the caller may reuse its array
+    return 0;
+}
+
+int gkcu_update_materials(GkcuContext* ctx, const GkMaterial* materials, uint32_t count) {
+    CTX_OR_FAIL(ctx);
+    if (count && !materials) { set_error("gkcu_update_materials: null array"); return 1; }
+    if (count > GK_MAX_MATERIALS) { set_error("gkcu_update_materials: more than MAX_MATERIALS"); return 1; }
+    if (!c.materials.reserve(std::max<size_t>(1, count) * sizeof(GkMaterial))) return 1;
+    if (count) GK_CUDA(cudaMemcpyAsync(c.materials.p, materials, (size_t)count * sizeof(GkMaterial), cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    c.material_count = count;
+    return 0;
+}
+
+int gkcu_tlas_build(GkcuContext* ctx) {
+    CTX_OR_FAIL(ctx);
+    if (!c.blas_built) { set_error("gkcu_tlas_build: call gkcu_blas_build first"); return 1; }
+    cudaEventRecord(c.ev[0], c.stream);
+    int r = build_tlas(c);
+    cudaEventRecord(c.ev[1], c.stream);
+    if (r) return r;
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    cudaEventElapsedTime(&c.timings.tlas_update_ms, c.ev[0], c.ev[1]);
+    return 0;
+}
+
+int gkcu_set_sky(GkcuContext* ctx, uint32_t id, const float* rgba, uint32_t width, uint32_t height) {
+    CTX_OR_FAIL(ctx);
+    if (!rgba || width == 0 || height == 0 || id > 4096) { set_error("gkcu_set_sky: bad arguments"); return 1; }
+    if (c.textures.size() <= id) c.textures.resize(id + 1);
+    Context::Tex& t = c.textures[id];
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    if (t.texels) cudaFree(t.texels);
+    t.texels = nullptr;
+    GK_CUDA(cudaMalloc(&t.texels, (size_t)width * height * 16));
+    GK_CUDA(cudaMemcpyAsync(t.texels, rgba, (size_t)width * height * 16, cudaMemcpyHostToDevice, c.stream));
+    t.w = width;
+    t.h = height;
+    return upload_tex_table(c);
+}
+
+int gkcu_set_probes(GkcuContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels) {
+    CTX_OR_FAIL(ctx);
+    if (!cubes || !voxels) { c.has_probes = false; return 0; }
+    size_t n = (size_t)GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z;
+    if (!c.cubes.reserve(n * sizeof(GkAmbientCube)) || !c.voxels.reserve(n * sizeof(GkVoxelData))) return 1;
+    GK_CUDA(cudaMemcpyAsync(c.cubes.p, cubes, n * sizeof(GkAmbientCube), cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaMemcpyAsync(c.voxels.p, voxels, n * sizeof(GkVoxelData), cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    c.has_probes = true;
+    return 0;
+}
+
+static int frame_prologue(Context& c, const GkUniformBufferObject* ubo, const GkcuFrameParams* params) {
+    if (!ubo || !params) { set_error("null ubo/params"); return 1; }
+    if (c.rt.w == 0) { set_error("call gkcu_resize first"); return 1; }
+    if (!c.blas_built) { set_error("call gkcu_scene_upload + gkcu_blas_build first"); return 1; }
+    if (params->spp_world > 1 && params->spp_rank >= params->spp_world) { set_error("spp_rank >= spp_world"); return 1; }
+    GK_CUDA(cudaMemcpyAsync(c.ubo.p, ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, c.stream));
+    return 0;
+}
+
+static void end_frame_swaps(Context& c) {
+    // copy pass (PathTracingRenderer.cpp:160-182) + object-id copy (VulkanBaseRenderer.cpp:1136-1152) as pointer swaps:
+    // next frame's PREV_* / OBJECTID_1 are this frame's ACCUM_* / OBJECTID_0.
+    c.rt.cur ^= 1;
+}
+
+int gkcu_render_frame(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params) {
+    CTX_OR_FAIL(ctx);
+    const uint64_t launches0 = c.launches;
+    if (frame_prologue(c, ubo, params)) return 1;
+    cudaStream_t st = c.stream;
+    cudaEventRecord(c.ev[0], st);
+    if (c.tlas_dirty && build_tlas(c)) return 1;  // RayTraceBaseRenderer::PreRender "TLAS Update"
+    cudaEventRecord(c.ev[1], st);
+    if (run_rt_pass(c, *ubo, *params)) return 1;
+    cudaEventRecord(c.ev[2], st);
+    if (!params->skip_post) {
+        if (run_reproject(c, *params)) return 1;
+        cudaEventRecord(c.ev[3], st);
+        if (run_denoise(c, *ubo)) return 1;
+        cudaEventRecord(c.ev[4], st);
+        end_frame_swaps(c);
+    } else {
+        cudaEventRecord(c.ev[3], st);
+        cudaEventRecord(c.ev[4], st);
+    }
+    cudaEventRecord(c.ev[5], st);
+    c.counters.kernel_launches = c.launches - launches0;
+    return 0;
+}
+
+int gkcu_radiance_buffer(GkcuContext* ctx, void** device_ptr, size_t* bytes) {
+    CTX_OR_FAIL(ctx);
+    if (!device_ptr || !bytes) { set_error("null out pointer"); return 1; }
+    return radiance_buffer(c, device_ptr, bytes);
+}
+
+int gkcu_render_resolve(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params) {
+    CTX_OR_FAIL(ctx);
+    const uint64_t launches0 = c.launches;
+    if (frame_prologue(c, ubo, params)) return 1;
+    cudaStream_t st = c.stream;
+    cudaEventRecord(c.ev[2], st);
+    if (run_resolve(c, *ubo, *params)) return 1;
+    if (run_reproject(c, *params)) return 1;
+    cudaEventRecord(c.ev[3], st);
+    if (run_denoise(c, *ubo)) return 1;
+    cudaEventRecord(c.ev[4], st);
+    end_frame_swaps(c);
+    cudaEventRecord(c.ev[5], st);
+    c.counters.kernel_launches += c.launches - launches0;
+    return 0;
+}
+
+int gkcu_synchronize(GkcuContext* ctx) {
+    CTX_OR_FAIL(ctx);
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int gkcu_readback(GkcuContext* ctx, uint32_t rt_index, void* dst, size_t dst_bytes) {
+    CTX_OR_FAIL(ctx);
+    RenderTargets& t = c.rt;
+    if (t.w == 0) { set_error("gkcu_readback: no images"); return 1; }
+    size_t n = (size_t)t.w * t.h;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    // after a frame the swap has happened: the newest ACCUM_* / OBJECTID_0 live in slot cur^1 (== PREV_* / OBJECTID_1,
+    // exactly as in the reference after its copy pass)
+    const int latest = t.cur ^ 1;
+    switch (rt_index) {
+        case GK_RT_ACCUMLATE_DIFFUSE: case GK_RT_SINGLE_PREV_DIFFUSE: src = t.accum_diffuse[latest]; bytes = n * 8; break;
+        case GK_RT_ACCUMLATE_SPECULAR: case GK_RT_SINGLE_PREV_SPECULAR: src = t.accum_specular[latest]; bytes = n * 8; break;
+        case GK_RT_ACCUMLATE_ALBEDO: case GK_RT_SINGLE_PREV_ALBEDO: src = t.accum_albedo[latest]; bytes = n * 8; break;
+        case GK_RT_OBJEDCTID_0: case GK_RT_OBJEDCTID_1: src = t.objectid[latest]; bytes = n * 4; break;
+        case GK_RT_SINGLE_DIFFUSE: src = t.single_diffuse; bytes = n * 8; break;
+        case GK_RT_SINGLE_SPECULAR: src = t.single_specular; bytes = n * 8; break;
+        case GK_RT_ALBEDO: src = t.albedo; bytes = n * 8; break;
+        case GK_RT_NORMAL: src = t.normal; bytes = n * 8; break;
+        case GK_RT_DENOISED: src = t.denoised; bytes = n * 8; break;
+        case GK_RT_MOTIONVECTOR: src = t.motion; bytes = n * 8; break;
+        case GK_RT_PREV_DEPTHBUFFER: src = t.prev_depth; bytes = n * 4; break;
+        case GK_RT_MOTIONMOMENT: src = t.moment; bytes = n * 2; break;
+        case GK_RT_EXT_PRIMITIVEID: src = t.primitiveid; bytes = n * 4; break;
+        default: set_error("gkcu_readback: unknown storage image index"); return 1;
+    }
+    if (!dst || dst_bytes < bytes) { set_error("gkcu_readback: destination too small"); return 1; }
+    GK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+// Test/bring-up hook: overwrite a storage image from host memory (same formats as gkcu_readback); the "latest" slot.
+int gkcu_upload_image(GkcuContext* ctx, uint32_t rt_index, const void* src, size_t src_bytes) {
+    CTX_OR_FAIL(ctx);
+    RenderTargets& t = c.rt;
+    if (t.w == 0 || !src) { set_error("gkcu_upload_image: no images"); return 1; }
+    size_t n = (size_t)t.w * t.h;
+    void* dst = nullptr;
+    size_t bytes = 0;
+    const int prev = t.cur ^ 1, cur = t.cur;
+    switch (rt_index) {
+        case GK_RT_SINGLE_PREV_DIFFUSE: dst = t.accum_diffuse[prev]; bytes = n * 8; break;
+        case GK_RT_SINGLE_PREV_SPECULAR: dst = t.accum_specular[prev]; bytes = n * 8; break;
+        case GK_RT_SINGLE_PREV_ALBEDO: dst = t.accum_albedo[prev]; bytes = n * 8; break;
+        case GK_RT_ACCUMLATE_DIFFUSE: dst = t.accum_diffuse[cur]; bytes = n * 8; break;
+        case GK_RT_ACCUMLATE_SPECULAR: dst = t.accum_specular[cur]; bytes = n * 8; break;
+        case GK_RT_ACCUMLATE_ALBEDO: dst = t.accum_albedo[cur]; bytes = n * 8; break;
+        case GK_RT_OBJEDCTID_0: dst = t.objectid[cur]; bytes = n * 4; break;
+        case GK_RT_OBJEDCTID_1: dst = t.objectid[prev]; bytes = n * 4; break;
+        case GK_RT_SINGLE_DIFFUSE: dst = t.single_diffuse; bytes = n * 8; break;
+        case GK_RT_SINGLE_SPECULAR: dst = t.single_specular; bytes = n * 8; break;
+        case GK_RT_ALBEDO: dst = t.albedo; bytes = n * 8; break;
+        case GK_RT_NORMAL: dst = t.normal; bytes = n * 8; break;
+        case GK_RT_MOTIONVECTOR: dst = t.motion; bytes = n * 8; break;
+        case GK_RT_MOTIONMOMENT: dst = t.moment; bytes = n * 2; break;
+        default: set_error("gkcu_upload_image: unsupported storage image index"); return 1;
+    }
+    if (src_bytes != bytes) { set_error("gkcu_upload_image: size mismatch"); return 1; }
+    GK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+// Test/bring-up hook: run only the post passes (reproject -> compose -> swaps) on the current images.
+int gkcu_run_post(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params) {
+    CTX_OR_FAIL(ctx);
+    if (!ubo || !params || c.rt.w == 0) { set_error("gkcu_run_post: bad arguments"); return 1; }
+    GK_CUDA(cudaMemcpyAsync(c.ubo.p, ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, c.stream));
+    cudaEventRecord(c.ev[2], c.stream);
+    if (run_reproject(c, *params)) return 1;
+    cudaEventRecord(c.ev[3], c.stream);
+    if (run_denoise(c, *ubo)) return 1;
+    cudaEventRecord(c.ev[4], c.stream);
+    end_frame_swaps(c);
+    cudaEventRecord(c.ev[5], c.stream);
+    return 0;
+}
+
+int gkcu_get_timings(GkcuContext* ctx, GkcuTimings* out) {
+    CTX_OR_FAIL(ctx);
+    if (!out) { set_error("null out"); return 1; }
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]) == cudaSuccess) c.timings.tlas_update_ms = ms;
+    if (cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]) == cudaSuccess) c.timings.rt_pass_ms = ms;
+    if (cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]) == cudaSuccess) c.timings.reproject_pass_ms = ms;
+    if (cudaEventElapsedTime(&ms, c.ev[3], c.ev[4]) == cudaSuccess) c.timings.compose_pass_ms = ms;
+    if (cudaEventElapsedTime(&ms, c.ev[4], c.ev[5]) == cudaSuccess) c.timings.copy_pass_ms = ms;
+    if (cudaEventElapsedTime(&ms, c.ev[0], c.ev[5]) == cudaSuccess) c.timings.frame_ms = ms;
+    cudaGetLastError();
+    *out = c.timings;
+    return 0;
+}
+
+int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out) {
+    CTX_OR_FAIL(ctx);
+    if (!out) { set_error("null out"); return 1; }
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    fetch_ray_counters(c);
+    *out = c.counters;
+    return 0;
+}
+
+uint64_t gkcu_stream(GkcuContext* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->c.stream : 0; }
+
+int gkcu_trace_rays(GkcuContext* ctx, const GkcuRay* rays, uint32_t count, GkcuHit* hits, uint32_t any_hit) {
+    CTX_OR_FAIL(ctx);
+    if (!rays || !hits) { set_error("gkcu_trace_rays: null array"); return 1; }
+    if (!c.blas_built) { set_error("gkcu_trace_rays: no acceleration structure"); return 1; }
+    if (count == 0) return 0;
+    if (c.tlas_dirty && build_tlas(c)) return 1;
+    if (!c.trace_rays.reserve((size_t)count * sizeof(GkcuRay)) || !c.trace_hits.reserve((size_t)count * sizeof(GkcuHit))) return 1;
+    GK_CUDA(cudaMemcpyAsync(c.trace_rays.p, rays, (size_t)count * sizeof(GkcuRay), cudaMemcpyHostToDevice, c.stream));
+    if (run_trace_rays(c, count, any_hit != 0)) return 1;
+    GK_CUDA(cudaMemcpyAsync(hits, c.trace_hits.p, (size_t)count * sizeof(GkcuHit), cudaMemcpyDeviceToHost, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+}  // extern "C"

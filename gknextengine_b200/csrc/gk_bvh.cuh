@@ -1,0 +1,251 @@
+// gk_bvh.cuh — acceleration-structure layouts and the stack traversal used by every tracing kernel.
+// Replaces what VK_KHR_ray_query + RT cores do for the reference (RayQuery.TraceRayInline/Proceed at
+// assets/shaders/common/Shading.slang:749-756, 794-801); B200 has no RT cores, so this is the hot loop.
+//
+// Layout (all 16-byte aligned, read with 128-bit loads):
+//   Node4       64 B   4-wide node, children boxes quantised to 8 bits on a per-node power-of-two grid
+//   leaf tris   48 B   3 x float4 (v0|prim id, v1, v2), stored in leaf order
+//   InstanceRec 64 B   world->object 3x4 + BLAS offsets; TLAS leaves reference one instance each
+// Semantics (shared with the CPU checker): a hit needs tmin < t < tmax, no face culling; the committed closest hit
+// is the minimum of (t, instance, primitive) over all such hits, which makes the result independent of traversal order.
+#pragma once
+#include "gk_device.cuh"
+
+namespace gkd {
+
+struct __align__(16) Node4 {
+    float ox, oy, oz;       // quantisation origin (node box min)
+    uint8_t ex, ey, ez, n;  // biased exponents: cell size = 2^(e-127); n = child count
+    uint32_t child[4];      // CHILD_EMPTY | leaf (bit31, count-1 in 30:28, first in 27:0) | node index
+    uint32_t qlo[3];        // qlo[axis] byte c = child c
+    uint32_t qhi[3];
+    uint32_t pad[2];
+};
+static_assert(sizeof(Node4) == 64, "Node4 must be 64 bytes");
+
+struct __align__(16) InstanceRec {
+    float w2o[12];       // world->object, 3 rows x 4
+    uint32_t node_base;  // BLAS root index in the BLAS node pool
+    uint32_t tri_base;   // first leaf-ordered triangle of the BLAS in the triangle pool
+    uint32_t active;     // visible && !nort && BLAS non-empty (VkAccelerationStructureInstanceKHR.mask)
+    uint32_t blas;
+};
+static_assert(sizeof(InstanceRec) == 64, "InstanceRec must be 64 bytes");
+
+#define GK_CHILD_EMPTY 0xFFFFFFFFu
+#define GK_LEAF_BIT 0x80000000u
+#define GK_STACK_SENTINEL 0xFFFFFFFEu
+#define GK_TRAV_STACK 64
+#define GK_NO_HIT 0xFFFFFFFFu
+
+struct TraceScene {
+    const Node4* tlas;
+    const Node4* blas;
+    const float4* tris;
+    const InstanceRec* inst;
+    uint32_t tlas_nodes;  // 0 -> empty scene
+};
+
+struct Hit {
+    float t, u, v;
+    uint32_t inst, prim;
+};
+
+GK_DEV float safe_rcp(float x) {
+    if (fabsf(x) < 1e-18f) return x < 0.0f ? -1e18f : 1e18f;
+    return 1.0f / x;
+}
+GK_DEV float sel3(int k, float3 v) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+struct RayShear {
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+GK_DEV RayShear make_shear(float3 d) {
+    RayShear r;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    r.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+    r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
+    r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
+    float dz = sel3(r.kz, d);
+    if (dz < 0.0f) { int t = r.kx; r.kx = r.ky; r.ky = t; }
+    r.Sx = sel3(r.kx, d) / dz;
+    r.Sy = sel3(r.ky, d) / dz;
+    r.Sz = 1.0f / dz;
+    return r;
+}
+
+// Watertight ray/triangle test (Woop, Benthin, Wald 2013), no culling; returns t and the weights of v1, v2.
+GK_DEV bool tri_test(float3 v0, float3 v1, float3 v2, float3 o, const RayShear& s, float& t, float& b1, float& b2) {
+    const float3 A = v0 - o, B = v1 - o, C = v2 - o;
+    const float Akz = sel3(s.kz, A), Bkz = sel3(s.kz, B), Ckz = sel3(s.kz, C);
+    const float Ax = sel3(s.kx, A) - s.Sx * Akz, Ay = sel3(s.ky, A) - s.Sy * Akz;
+    const float Bx = sel3(s.kx, B) - s.Sx * Bkz, By = sel3(s.ky, B) - s.Sy * Bkz;
+    const float Cx = sel3(s.kx, C) - s.Sx * Ckz, Cy = sel3(s.ky, C) - s.Sy * Ckz;
+    float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
+        V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
+        W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    const float Az = s.Sz * Akz, Bz = s.Sz * Bkz, Cz = s.Sz * Ckz;
+    const float T = U * Az + V * Bz + W * Cz;
+    const float inv = 1.0f / det;
+    t = T * inv;
+    b1 = V * inv;
+    b2 = W * inv;
+    return true;
+}
+
+GK_DEV float3 xform_point(const float* m, float3 p) {
+    return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+              m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+GK_DEV float3 xform_vec(const float* m, float3 p) {
+    return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z, m[4] * p.x + m[5] * p.y + m[6] * p.z, m[8] * p.x + m[9] * p.y + m[10] * p.z);
+}
+
+GK_DEV float byte_f(uint32_t w, int c) { return (float)((w >> (8 * c)) & 0xFFu); }
+
+// Tests the 4 quantised child boxes of a node. tn[c] = padded entry distance or +inf on a miss.
+GK_DEV void node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, float3 ro, float3 idir, float tmin, float tbest, float tn[4]) {
+    const float ox = __uint_as_float(n0.x), oy = __uint_as_float(n0.y), oz = __uint_as_float(n0.z);
+    const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
+                sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+    const float adjx = (ox - ro.x) * idir.x, adjy = (oy - ro.y) * idir.y, adjz = (oz - ro.z) * idir.z;
+    const float scx = sx * idir.x, scy = sy * idir.y, scz = sz * idir.z;
+    const uint32_t child[4] = {n1.x, n1.y, n1.z, n1.w};
+    const uint32_t qlx = n2.x, qly = n2.y, qlz = n2.z, qhx = n2.w, qhy = n3.x, qhz = n3.y;
+    const float tfcap = tbest * 1.000001f + 1e-7f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float x0 = __fmaf_rn(byte_f(qlx, c), scx, adjx), x1 = __fmaf_rn(byte_f(qhx, c), scx, adjx);
+        float y0 = __fmaf_rn(byte_f(qly, c), scy, adjy), y1 = __fmaf_rn(byte_f(qhy, c), scy, adjy);
+        float z0 = __fmaf_rn(byte_f(qlz, c), scz, adjz), z1 = __fmaf_rn(byte_f(qhz, c), scz, adjz);
+        float n = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+        float f = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+        float npad = n * 0.999999f - 1e-7f;
+        bool hit = (child[c] != GK_CHILD_EMPTY) && (npad <= f * 1.000001f + 1e-7f) && (npad <= tfcap);
+        tn[c] = hit ? npad : __int_as_float(0x7f800000);
+    }
+}
+
+#define GK_CSWAP(a, b)                                                     \
+    {                                                                      \
+        bool sw = tn[b] < tn[a];                                           \
+        float tt = sw ? tn[a] : tn[b];                                     \
+        tn[a] = sw ? tn[b] : tn[a];                                        \
+        tn[b] = tt;                                                        \
+        uint32_t rr = sw ? ref[a] : ref[b];                                \
+        ref[a] = sw ? ref[b] : ref[a];                                     \
+        ref[b] = rr;                                                       \
+    }
+
+// Closest hit (ANY = false) or first hit (ANY = true; best.inst != GK_NO_HIT means occluded).
+template <bool ANY>
+GK_DEV void trace_ray(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, Hit& best) {
+    best.t = tmax;
+    best.u = 0.0f;
+    best.v = 0.0f;
+    best.inst = GK_NO_HIT;
+    best.prim = 0;
+    if (S.tlas_nodes == 0) return;
+
+    uint2 stack[GK_TRAV_STACK];
+    int sp = 0;
+    float3 ro = o, rd = d;
+    float3 idir = f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z));
+    const uint4* nodes = reinterpret_cast<const uint4*>(S.tlas);
+    const float4* tris = S.tris;
+    uint32_t cur_inst = GK_NO_HIT;
+    RayShear sh;
+    sh.kx = sh.ky = sh.kz = 0;
+    sh.Sx = sh.Sy = sh.Sz = 0.0f;
+    uint32_t cur = 0;  // TLAS root
+
+    for (;;) {
+        if (!(cur & GK_LEAF_BIT)) {
+            const uint4* np = nodes + (size_t)cur * 4;
+            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            float tn[4];
+            node_test(n0, n1, n2, n3, ro, idir, tmin, best.t, tn);
+            uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
+            GK_CSWAP(0, 1) GK_CSWAP(2, 3) GK_CSWAP(0, 2) GK_CSWAP(1, 3) GK_CSWAP(1, 2)
+            const float inf = __int_as_float(0x7f800000);
+            if (tn[0] < inf) {
+                if (tn[3] < inf) stack[sp++] = make_uint2(ref[3], __float_as_uint(tn[3]));
+                if (tn[2] < inf) stack[sp++] = make_uint2(ref[2], __float_as_uint(tn[2]));
+                if (tn[1] < inf) stack[sp++] = make_uint2(ref[1], __float_as_uint(tn[1]));
+                cur = ref[0];
+                continue;
+            }
+        } else if (cur_inst == GK_NO_HIT) {
+            // TLAS leaf: one instance. Enter its BLAS in object space; t is preserved by the affine map.
+            const uint32_t ii = cur & 0x0FFFFFFFu;
+            const InstanceRec* ir = S.inst + ii;
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(ir)), r1 = __ldg(reinterpret_cast<const float4*>(ir) + 1),
+                         r2 = __ldg(reinterpret_cast<const float4*>(ir) + 2);
+            const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ir) + 3);
+            if (meta.z) {
+                const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                ro = xform_point(m, o);
+                rd = xform_vec(m, d);
+                idir = f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z));
+                sh = make_shear(rd);
+                stack[sp++] = make_uint2(GK_STACK_SENTINEL, 0u);
+                nodes = reinterpret_cast<const uint4*>(S.blas + meta.x);
+                tris = S.tris + (size_t)meta.y * 3;
+                cur_inst = ii;
+                cur = 0;
+                continue;
+            }
+        } else {
+            // BLAS leaf: triangles
+            const uint32_t first = cur & 0x0FFFFFFFu, count = ((cur >> 28) & 7u) + 1u;
+            for (uint32_t i = 0; i < count; ++i) {
+                const float4* tp = tris + (size_t)(first + i) * 3;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float t, b1, b2;
+                if (!tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), ro, sh, t, b1, b2)) continue;
+                if (!(t > tmin && t < tmax)) continue;
+                if (ANY) {
+                    best.t = t;
+                    best.inst = cur_inst;
+                    best.prim = __float_as_uint(a.w);
+                    return;
+                }
+                const uint32_t p = __float_as_uint(a.w);
+                const bool better = best.inst == GK_NO_HIT || t < best.t ||
+                                    (t == best.t && (cur_inst < best.inst || (cur_inst == best.inst && p < best.prim)));
+                if (better) {
+                    best.t = t;
+                    best.u = b1;
+                    best.v = b2;
+                    best.inst = cur_inst;
+                    best.prim = p;
+                }
+            }
+        }
+        // pop
+        for (;;) {
+            if (sp == 0) return;
+            const uint2 e = stack[--sp];
+            if (e.x == GK_STACK_SENTINEL) {
+                ro = o;
+                rd = d;
+                idir = f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z));
+                nodes = reinterpret_cast<const uint4*>(S.tlas);
+                cur_inst = GK_NO_HIT;
+                continue;
+            }
+            if (__uint_as_float(e.y) > best.t) continue;
+            cur = e.x;
+            break;
+        }
+    }
+}
+
+}  // namespace gkd

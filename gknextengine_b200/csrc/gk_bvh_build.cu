@@ -1,0 +1,878 @@
+// gk_bvh_build.cu — acceleration-structure builds on the GPU.
+//
+// Replaces the driver work behind vkCmdBuildAccelerationStructuresKHR in the reference:
+//   BLAS per model, built at scene load   src/Vulkan/RayTracing/BottomLevelAccelerationStructure.cpp:42-59,
+//                                         src/Rendering/RayTraceBaseRenderer.cpp:276-340
+//   TLAS over the NodeProxy array, fully rebuilt when nodes change
+//                                         src/Vulkan/RayTracing/TopLevelAccelerationStructure.cpp:50-81,
+//                                         src/Rendering/RayTraceBaseRenderer.cpp:165-218
+// plus a BLAS refit the reference does not have.
+//
+// Pipeline: primitive boxes -> binary BVH (Morton LBVH, Karras 2012; or level-synchronous SAH-binned build for BLAS)
+//           -> collapse to 4-wide nodes with 8-bit quantised child boxes (Node4, gk_bvh.cuh) in BFS order
+//           -> leaf-ordered triangle pool. The BFS level table makes the bottom-up refit a handful of launches.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "gk_context.h"
+
+using namespace gkd;
+
+namespace gkcu {
+
+namespace {
+
+constexpr int kBlasLeafMax = 4;
+constexpr int kSahBins = 16;
+
+__device__ __forceinline__ int f2o(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float o2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+// ------------------------------------------------------------------------------------------- primitive setup
+// Triangle boxes of one model from the BLAS inputs the reference hands to Vulkan: fp16x4 positions (stride 8 B) and
+// uint32 model-local indices (src/Vulkan/RayTracing/BottomLevelGeometry.cpp:9-38).
+__global__ void k_tri_boxes(const uint16_t* __restrict__ simple, const uint32_t* __restrict__ indices, uint32_t vertex_offset,
+                            uint32_t index_offset, uint32_t n, float4* __restrict__ lo, float4* __restrict__ hi) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float3 mn = f3(FLT_MAX, FLT_MAX, FLT_MAX), mx = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int k = 0; k < 3; ++k) {
+        uint32_t vi = vertex_offset + indices[index_offset + p * 3 + k];
+        float3 v = f3(h2f(simple[vi * 4]), h2f(simple[vi * 4 + 1]), h2f(simple[vi * 4 + 2]));
+        mn = f3(fminf(mn.x, v.x), fminf(mn.y, v.y), fminf(mn.z, v.z));
+        mx = f3(fmaxf(mx.x, v.x), fmaxf(mx.y, v.y), fmaxf(mx.z, v.z));
+    }
+    lo[p] = f4(mn.x, mn.y, mn.z, 0);
+    hi[p] = f4(mx.x, mx.y, mx.z, 0);
+}
+
+__global__ void k_init_bounds(int* b) {
+    if (threadIdx.x < 3) b[threadIdx.x] = 0x7FFFFFFF;
+    else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000;
+}
+
+__global__ void k_bounds(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, int* __restrict__ bounds) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 mn = f3(FLT_MAX, FLT_MAX, FLT_MAX), mx = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    if (i < n) {
+        float4 a = lo[i], b = hi[i];
+        if (a.x <= b.x) {  // inactive instances carry an inverted box
+            mn = f3(a.x, a.y, a.z);
+            mx = f3(b.x, b.y, b.z);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn.x = fminf(mn.x, __shfl_xor_sync(0xffffffffu, mn.x, o)); mn.y = fminf(mn.y, __shfl_xor_sync(0xffffffffu, mn.y, o));
+        mn.z = fminf(mn.z, __shfl_xor_sync(0xffffffffu, mn.z, o)); mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, o));
+        mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, o)); mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mn.x <= mx.x) {
+        atomicMin(&bounds[0], f2o(mn.x)); atomicMin(&bounds[1], f2o(mn.y)); atomicMin(&bounds[2], f2o(mn.z));
+        atomicMax(&bounds[3], f2o(mx.x)); atomicMax(&bounds[4], f2o(mx.y)); atomicMax(&bounds[5], f2o(mx.z));
+    }
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {
+    uint64_t x = v & 0x1FFFFFu;
+    x = (x | x << 32) & 0x1F00000000FFFFull;
+    x = (x | x << 16) & 0x1F0000FF0000FFull;
+    x = (x | x << 8) & 0x100F00F00F00F00Full;
+    x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, const int* __restrict__ bounds,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ order) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 bmn = f3(o2f(bounds[0]), o2f(bounds[1]), o2f(bounds[2])), bmx = f3(o2f(bounds[3]), o2f(bounds[4]), o2f(bounds[5]));
+    float4 a = lo[i], b = hi[i];
+    uint64_t key;
+    if (a.x > b.x) {
+        key = 0x7FFFFFFFFFFFFFFFull;  // inactive: sorted to the end
+    } else {
+        float3 c = f3((a.x + b.x) * 0.5f, (a.y + b.y) * 0.5f, (a.z + b.z) * 0.5f);
+        float3 e = f3(fmaxf(bmx.x - bmn.x, 1e-30f), fmaxf(bmx.y - bmn.y, 1e-30f), fmaxf(bmx.z - bmn.z, 1e-30f));
+        const float s = 2097151.0f;
+        uint32_t x = (uint32_t)fminf(fmaxf((c.x - bmn.x) / e.x * s, 0.0f), s);
+        uint32_t y = (uint32_t)fminf(fmaxf((c.y - bmn.y) / e.y * s, 0.0f), s);
+        uint32_t z = (uint32_t)fminf(fmaxf((c.z - bmn.z) / e.z * s, 0.0f), s);
+        key = (expand21(x) << 2) | (expand21(y) << 1) | expand21(z);
+    }
+    keys[i] = key;
+    order[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------- Karras 2012
+__device__ __forceinline__ int delta(const uint64_t* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+// internal node i in [0, n-1); leaf j is node (n-1)+j
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right, int* __restrict__ parent,
+                         int* __restrict__ first, int* __restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int l_idx = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    int r_idx = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    left[i] = l_idx;
+    right[i] = r_idx;
+    parent[l_idx] = i;
+    parent[r_idx] = i;
+    first[i] = lo;
+    count[i] = hi - lo + 1;
+    if (i == 0) parent[0] = -1;
+}
+
+__global__ void k_lbvh_leaves(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ order, int n,
+                              float4* __restrict__ nlo, float4* __restrict__ nhi, int* __restrict__ left, int* __restrict__ right,
+                              int* __restrict__ first, int* __restrict__ count, int* __restrict__ flag) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int node = n - 1 + j;
+    uint32_t p = order[j];
+    nlo[node] = plo[p];
+    nhi[node] = phi[p];
+    left[node] = -1;
+    right[node] = -1;
+    first[node] = j;
+    count[node] = 1;
+    if (j < n - 1) flag[j] = 0;
+}
+
+__global__ void k_lbvh_fit(int n, const int* __restrict__ parent, const int* __restrict__ left, const int* __restrict__ right,
+                           float4* __restrict__ nlo, float4* __restrict__ nhi, int* __restrict__ flag) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int node = parent[n - 1 + j];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&flag[node], 1) == 0) return;  // first arrival: the sibling subtree is not done yet
+        __threadfence();
+        int l = left[node], r = right[node];
+        float4 al = __ldcg(&nlo[l]), ah = __ldcg(&nhi[l]), bl = __ldcg(&nlo[r]), bh = __ldcg(&nhi[r]);
+        // inverted (inactive) boxes are ignored by min/max only if both are inverted; handle explicitly
+        bool av = al.x <= ah.x, bv = bl.x <= bh.x;
+        float4 lo4, hi4;
+        if (av && bv) {
+            lo4 = f4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0);
+            hi4 = f4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0);
+        } else if (av) { lo4 = al; hi4 = ah; }
+        else { lo4 = bl; hi4 = bh; }
+        nlo[node] = lo4;
+        nhi[node] = hi4;
+        node = parent[node];
+    }
+}
+
+// ------------------------------------------------------------------------------------------- wide-node writer
+struct ChildBox { float3 lo, hi; uint32_t ref; };
+
+__device__ void write_node4(Node4* out, float3 nlo, float3 nhi, int nchild, const ChildBox* ch) {
+    Node4 node;
+    node.ox = nlo.x; node.oy = nlo.y; node.oz = nlo.z;
+    float ext[3] = {nhi.x - nlo.x, nhi.y - nlo.y, nhi.z - nlo.z};
+    float org[3] = {nlo.x, nlo.y, nlo.z};
+    uint8_t eb[3];
+    float scale[3];
+    for (int a = 0; a < 3; ++a) {
+        int ex = -126;
+        if (ext[a] > 0.0f) {
+            frexpf(ext[a] * (1.0002f / 255.0f), &ex);  // 2^ex >= ext/255 with slack
+            ex = max(-126, min(ex, 126));
+        }
+        eb[a] = (uint8_t)(ex + 127);
+        scale[a] = __uint_as_float((uint32_t)eb[a] << 23);
+    }
+    node.ex = eb[0]; node.ey = eb[1]; node.ez = eb[2];
+    node.n = (uint8_t)nchild;
+    node.qlo[0] = node.qlo[1] = node.qlo[2] = 0;
+    node.qhi[0] = node.qhi[1] = node.qhi[2] = 0;
+    node.pad[0] = node.pad[1] = 0;
+    for (int c = 0; c < 4; ++c) {
+        if (c >= nchild) {
+            node.child[c] = GK_CHILD_EMPTY;
+            for (int a = 0; a < 3; ++a) { node.qlo[a] |= 255u << (8 * c); }
+            continue;
+        }
+        node.child[c] = ch[c].ref;
+        float clo[3] = {ch[c].lo.x, ch[c].lo.y, ch[c].lo.z}, chi[3] = {ch[c].hi.x, ch[c].hi.y, ch[c].hi.z};
+        for (int a = 0; a < 3; ++a) {
+            int ql = (int)floorf((clo[a] - org[a]) / scale[a]);
+            ql = max(0, min(255, ql));
+            while (ql > 0 && org[a] + (float)ql * scale[a] > clo[a]) --ql;
+            int qh = (int)ceilf((chi[a] - org[a]) / scale[a]);
+            qh = max(0, min(255, qh));
+            while (qh < 255 && org[a] + (float)qh * scale[a] < chi[a]) ++qh;
+            node.qlo[a] |= (uint32_t)ql << (8 * c);
+            node.qhi[a] |= (uint32_t)qh << (8 * c);
+        }
+    }
+    *out = node;
+}
+
+__device__ __forceinline__ float box_area(float4 lo, float4 hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// One BFS level of the BVH2 -> Node4 collapse. Entry = (bvh2 node, node4 slot). A bvh2 node with <= leaf_max primitives
+// becomes a leaf reference; otherwise the largest-area internal child is opened until there are 4 children.
+__global__ void k_collapse_level(const int2* __restrict__ qin, int nin, int2* __restrict__ qout, int* __restrict__ nout, int* __restrict__ node_counter,
+                                 const float4* __restrict__ nlo, const float4* __restrict__ nhi, const int* __restrict__ left,
+                                 const int* __restrict__ right, const int* __restrict__ first, const int* __restrict__ count, int leaf_max,
+                                 const uint32_t* __restrict__ order, int tlas_mode, Node4* __restrict__ out, float4* __restrict__ out_lo,
+                                 float4* __restrict__ out_hi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nin) return;
+    int2 e = qin[i];
+    int kids[4];
+    int nk;
+#define GK_IS_LEAF2(n2) (left[n2] < 0 || count[n2] <= leaf_max)
+    if (GK_IS_LEAF2(e.x)) {  // degenerate: the whole BVH is one leaf
+        kids[0] = e.x;
+        nk = 1;
+    } else {
+        kids[0] = left[e.x];
+        kids[1] = right[e.x];
+        nk = 2;
+        while (nk < 4) {
+            int best = -1;
+            float barea = -1.0f;
+            for (int k = 0; k < nk; ++k) {
+                if (GK_IS_LEAF2(kids[k])) continue;
+                float a = box_area(nlo[kids[k]], nhi[kids[k]]);
+                if (a > barea) { barea = a; best = k; }
+            }
+            if (best < 0) break;
+            int n2 = kids[best];
+            kids[best] = left[n2];
+            kids[nk++] = right[n2];
+        }
+    }
+    ChildBox ch[4];
+    for (int k = 0; k < nk; ++k) {
+        int n2 = kids[k];
+        float4 l = nlo[n2], h = nhi[n2];
+        ch[k].lo = f3(l.x, l.y, l.z);
+        ch[k].hi = f3(h.x, h.y, h.z);
+        if (GK_IS_LEAF2(n2)) {
+            uint32_t f = (uint32_t)first[n2];
+            if (tlas_mode) f = order[f];  // TLAS leaves carry the instance index itself
+            ch[k].ref = GK_LEAF_BIT | ((uint32_t)(count[n2] - 1) << 28) | f;
+        } else {
+            int slot = atomicAdd(node_counter, 1);
+            int q = atomicAdd(nout, 1);
+            qout[q] = make_int2(n2, slot);
+            ch[k].ref = (uint32_t)slot;
+        }
+    }
+    float4 l = nlo[e.x], h = nhi[e.x];
+    write_node4(out + e.y, f3(l.x, l.y, l.z), f3(h.x, h.y, h.z), nk, ch);
+    out_lo[e.y] = l;
+    out_hi[e.y] = h;
+}
+
+__global__ void k_write_tris(const uint16_t* __restrict__ simple, const uint32_t* __restrict__ indices, uint32_t vertex_offset,
+                             uint32_t index_offset, const uint32_t* __restrict__ order, uint32_t n, float4* __restrict__ tris,
+                             uint32_t* __restrict__ tri_prim) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = order ? order[i] : tri_prim[i];
+    float3 v[3];
+    for (int k = 0; k < 3; ++k) {
+        uint32_t vi = vertex_offset + indices[index_offset + p * 3 + k];
+        v[k] = f3(h2f(simple[vi * 4]), h2f(simple[vi * 4 + 1]), h2f(simple[vi * 4 + 2]));
+    }
+    tris[(size_t)i * 3 + 0] = f4(v[0].x, v[0].y, v[0].z, __uint_as_float(p));
+    tris[(size_t)i * 3 + 1] = f4(v[1].x, v[1].y, v[1].z, 0);
+    tris[(size_t)i * 3 + 2] = f4(v[2].x, v[2].y, v[2].z, 0);
+    if (order) tri_prim[i] = p;
+}
+
+// Bottom-up refit of one BFS level: child boxes from triangles (leaves) or from the already refitted deeper level.
+__global__ void k_refit_level(Node4* __restrict__ nodes, float4* __restrict__ node_lo, float4* __restrict__ node_hi, uint32_t begin, uint32_t end,
+                              const float4* __restrict__ tris) {
+    uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    Node4 nd = nodes[i];
+    ChildBox ch[4];
+    int nk = nd.n;
+    float3 nlo = f3(FLT_MAX, FLT_MAX, FLT_MAX), nhi = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int k = 0; k < nk; ++k) {
+        uint32_t ref = nd.child[k];
+        float3 lo, hi;
+        if (ref & GK_LEAF_BIT) {
+            uint32_t first = ref & 0x0FFFFFFFu, cnt = ((ref >> 28) & 7u) + 1u;
+            lo = f3(FLT_MAX, FLT_MAX, FLT_MAX);
+            hi = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+            for (uint32_t t = 0; t < cnt * 3; ++t) {
+                float4 v = tris[(size_t)first * 3 + t];
+                lo = f3(fminf(lo.x, v.x), fminf(lo.y, v.y), fminf(lo.z, v.z));
+                hi = f3(fmaxf(hi.x, v.x), fmaxf(hi.y, v.y), fmaxf(hi.z, v.z));
+            }
+        } else {
+            float4 l = node_lo[ref], h = node_hi[ref];
+            lo = f3(l.x, l.y, l.z);
+            hi = f3(h.x, h.y, h.z);
+        }
+        ch[k].lo = lo; ch[k].hi = hi; ch[k].ref = ref;
+        nlo = f3(fminf(nlo.x, lo.x), fminf(nlo.y, lo.y), fminf(nlo.z, lo.z));
+        nhi = f3(fmaxf(nhi.x, hi.x), fmaxf(nhi.y, hi.y), fmaxf(nhi.z, hi.z));
+    }
+    write_node4(nodes + i, nlo, nhi, nk, ch);
+    node_lo[i] = f4(nlo.x, nlo.y, nlo.z, 0);
+    node_hi[i] = f4(nhi.x, nhi.y, nhi.z, 0);
+}
+
+// ------------------------------------------------------------------------------------------- SAH-binned BVH2 (BLAS)
+// Level-synchronous top-down build: every level bins all primitives of the still-open nodes (16 bins x 3 axes, integer
+// atomics on order-encoded floats so the tree is deterministic), picks the SAH-best plane per node, and partitions.
+struct SahBin { int lo[3], hi[3], cnt, pad; };  // 32 B
+
+__global__ void k_sah_init(int n, const int* __restrict__ bounds, float4* nlo, float4* nhi, int* left, int* right, int* first, int* count,
+                           uint32_t* order, int* pos_node, int* active, int* counters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { order[i] = i; pos_node[i] = 0; }
+    if (i == 0) {
+        nlo[0] = f4(o2f(bounds[0]), o2f(bounds[1]), o2f(bounds[2]), 0);
+        nhi[0] = f4(o2f(bounds[3]), o2f(bounds[4]), o2f(bounds[5]), 0);
+        left[0] = right[0] = -1;
+        first[0] = 0;
+        count[0] = n;
+        active[0] = 0;      // active list: node ids; slot s <-> bins[s]
+        counters[0] = 1;    // node count
+        counters[1] = (n > kBlasLeafMax) ? 1 : 0;  // active count (this level)
+        counters[2] = 0;    // active count (next level)
+    }
+}
+
+__global__ void k_sah_clear_bins(SahBin* bins, int nslots) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots * 3 * kSahBins) return;
+    SahBin b;
+    b.lo[0] = b.lo[1] = b.lo[2] = 0x7FFFFFFF;
+    b.hi[0] = b.hi[1] = b.hi[2] = (int)0x80000000;
+    b.cnt = 0;
+    b.pad = 0;
+    bins[i] = b;
+}
+
+__device__ __forceinline__ int sah_bin_of(float c, float lo, float hi) {
+    float e = hi - lo;
+    if (!(e > 0.0f)) return 0;
+    int b = (int)((c - lo) / e * (float)kSahBins);
+    return max(0, min(kSahBins - 1, b));
+}
+
+// slot_of[node] = active slot or -1
+__global__ void k_sah_bin(int n, const uint32_t* __restrict__ order, const int* __restrict__ pos_node, const int* __restrict__ slot_of,
+                          const float4* __restrict__ plo, const float4* __restrict__ phi, const float4* __restrict__ nlo,
+                          const float4* __restrict__ nhi, SahBin* __restrict__ bins) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int node = pos_node[i];
+    int slot = slot_of[node];
+    if (slot < 0) return;
+    uint32_t p = order[i];
+    float4 a = plo[p], b = phi[p], l = nlo[node], h = nhi[node];
+    float c[3] = {(a.x + b.x) * 0.5f, (a.y + b.y) * 0.5f, (a.z + b.z) * 0.5f};
+    float nl[3] = {l.x, l.y, l.z}, nh[3] = {h.x, h.y, h.z};
+    int ia[3] = {f2o(a.x), f2o(a.y), f2o(a.z)}, ib[3] = {f2o(b.x), f2o(b.y), f2o(b.z)};
+    for (int ax = 0; ax < 3; ++ax) {
+        SahBin* bn = bins + ((size_t)slot * 3 + ax) * kSahBins + sah_bin_of(c[ax], nl[ax], nh[ax]);
+        atomicMin(&bn->lo[0], ia[0]); atomicMin(&bn->lo[1], ia[1]); atomicMin(&bn->lo[2], ia[2]);
+        atomicMax(&bn->hi[0], ib[0]); atomicMax(&bn->hi[1], ib[1]); atomicMax(&bn->hi[2], ib[2]);
+        atomicAdd(&bn->cnt, 1);
+    }
+}
+
+struct SahSplit { int axis, plane, nl, fallback; };
+
+__global__ void k_sah_split(int nactive, const int* __restrict__ active, const SahBin* __restrict__ bins, float4* nlo, float4* nhi, int* left,
+                            int* right, int* first, int* count, int* counters, int* next_active, SahSplit* splits, int* cursors) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nactive) return;
+    int node = active[s];
+    int cnt = count[node];
+    float bestCost = FLT_MAX;
+    int bestAxis = -1, bestPlane = 0, bestNl = 0;
+    for (int ax = 0; ax < 3; ++ax) {
+        const SahBin* b = bins + ((size_t)s * 3 + ax) * kSahBins;
+        // right-to-left suffix areas
+        float rarea[kSahBins];
+        int rcnt[kSahBins];
+        int lo[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+        int c = 0;
+        for (int k = kSahBins - 1; k >= 1; --k) {
+            if (b[k].cnt) {
+                for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], b[k].lo[a]); hi[a] = max(hi[a], b[k].hi[a]); }
+                c += b[k].cnt;
+            }
+            rcnt[k] = c;
+            rarea[k] = c ? box_area(f4(o2f(lo[0]), o2f(lo[1]), o2f(lo[2]), 0), f4(o2f(hi[0]), o2f(hi[1]), o2f(hi[2]), 0)) : 0.0f;
+        }
+        for (int a = 0; a < 3; ++a) { lo[a] = 0x7FFFFFFF; hi[a] = (int)0x80000000; }
+        c = 0;
+        for (int k = 0; k < kSahBins - 1; ++k) {
+            if (b[k].cnt) {
+                for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], b[k].lo[a]); hi[a] = max(hi[a], b[k].hi[a]); }
+                c += b[k].cnt;
+            }
+            if (c == 0 || rcnt[k + 1] == 0) continue;
+            float la = box_area(f4(o2f(lo[0]), o2f(lo[1]), o2f(lo[2]), 0), f4(o2f(hi[0]), o2f(hi[1]), o2f(hi[2]), 0));
+            float cost = la * (float)c + rarea[k + 1] * (float)rcnt[k + 1];
+            if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestPlane = k; bestNl = c; }
+        }
+    }
+    SahSplit sp;
+    sp.axis = bestAxis;
+    sp.plane = bestPlane;
+    sp.nl = bestNl;
+    sp.fallback = 0;
+    float4 l = nlo[node], h = nhi[node];
+    float4 llo = l, lhi = h, rlo = l, rhi = h;
+    if (bestAxis < 0) {
+        // every centroid fell into one bin on every axis: median split by position, children keep the parent box
+        if (cnt <= 8) { splits[s].axis = -2; return; }  // stays a leaf (<= 8 fits the leaf encoding)
+        sp.fallback = 1;
+        sp.nl = cnt / 2;
+    } else {
+        const SahBin* b = bins + ((size_t)s * 3 + bestAxis) * kSahBins;
+        int lo[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+        for (int k = 0; k <= bestPlane; ++k)
+            if (b[k].cnt) for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], b[k].lo[a]); hi[a] = max(hi[a], b[k].hi[a]); }
+        llo = f4(o2f(lo[0]), o2f(lo[1]), o2f(lo[2]), 0);
+        lhi = f4(o2f(hi[0]), o2f(hi[1]), o2f(hi[2]), 0);
+        for (int a = 0; a < 3; ++a) { lo[a] = 0x7FFFFFFF; hi[a] = (int)0x80000000; }
+        for (int k = bestPlane + 1; k < kSahBins; ++k)
+            if (b[k].cnt) for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], b[k].lo[a]); hi[a] = max(hi[a], b[k].hi[a]); }
+        rlo = f4(o2f(lo[0]), o2f(lo[1]), o2f(lo[2]), 0);
+        rhi = f4(o2f(hi[0]), o2f(hi[1]), o2f(hi[2]), 0);
+    }
+    int c0 = atomicAdd(&counters[0], 2);
+    int f = first[node];
+    left[node] = c0;
+    right[node] = c0 + 1;
+    nlo[c0] = llo; nhi[c0] = lhi; left[c0] = right[c0] = -1; first[c0] = f; count[c0] = sp.nl;
+    nlo[c0 + 1] = rlo; nhi[c0 + 1] = rhi; left[c0 + 1] = right[c0 + 1] = -1; first[c0 + 1] = f + sp.nl; count[c0 + 1] = cnt - sp.nl;
+    splits[s] = sp;
+    cursors[2 * s] = 0;
+    cursors[2 * s + 1] = 0;
+    if (sp.nl > kBlasLeafMax) next_active[atomicAdd(&counters[2], 1)] = c0;
+    if (cnt - sp.nl > kBlasLeafMax) next_active[atomicAdd(&counters[2], 1)] = c0 + 1;
+}
+
+__global__ void k_sah_partition(int n, const uint32_t* __restrict__ order, const int* __restrict__ pos_node, const int* __restrict__ slot_of,
+                                const float4* __restrict__ plo, const float4* __restrict__ phi, const float4* __restrict__ nlo,
+                                const float4* __restrict__ nhi, const int* __restrict__ left, const int* __restrict__ first,
+                                const SahSplit* __restrict__ splits, int* __restrict__ cursors, uint32_t* __restrict__ order_out,
+                                int* __restrict__ pos_node_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int node = pos_node[i];
+    int slot = slot_of[node];
+    uint32_t p = order[i];
+    if (slot < 0 || splits[slot].axis == -2) {
+        order_out[i] = p;
+        pos_node_out[i] = node;
+        return;
+    }
+    SahSplit sp = splits[slot];
+    int f = first[node];
+    bool goLeft;
+    if (sp.fallback) {
+        goLeft = (i - f) < sp.nl;
+    } else {
+        float4 a = plo[p], b = phi[p], l = nlo[node], h = nhi[node];
+        float c = sp.axis == 0 ? (a.x + b.x) * 0.5f : (sp.axis == 1 ? (a.y + b.y) * 0.5f : (a.z + b.z) * 0.5f);
+        float nl = sp.axis == 0 ? l.x : (sp.axis == 1 ? l.y : l.z), nh = sp.axis == 0 ? h.x : (sp.axis == 1 ? h.y : h.z);
+        goLeft = sah_bin_of(c, nl, nh) <= sp.plane;
+    }
+    int dst;
+    if (sp.fallback) dst = i;
+    else if (goLeft) dst = f + atomicAdd(&cursors[2 * slot], 1);
+    else dst = f + sp.nl + atomicAdd(&cursors[2 * slot + 1], 1);
+    order_out[dst] = p;
+    pos_node_out[dst] = left[node] + (goLeft ? 0 : 1);
+}
+
+__global__ void k_fill_int(int* p, int n, int v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_mark_slots(const int* active, int nactive, int* slot_of, int unmark) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nactive) slot_of[active[i]] = unmark ? -1 : i;
+}
+
+// ------------------------------------------------------------------------------------------- instances
+// VkAccelerationStructureInstanceKHR equivalent (TopLevelAccelerationStructure.cpp:83-111): instance i <-> Nodes[i],
+// BLAS = modelId / 10, mask = visible && !nort (RayTraceBaseRenderer.cpp:172-179). Also the world box for the TLAS.
+__global__ void k_instances(const GkNodeProxy* __restrict__ nodes, uint32_t n, const uint4* __restrict__ blas_table, uint32_t model_count,
+                            InstanceRec* __restrict__ inst, float4* __restrict__ lo, float4* __restrict__ hi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GkNodeProxy& nd = nodes[i];
+    InstanceRec r;
+    uint32_t blas = nd.modelId / 10;
+    bool active = nd.visible && !nd.nort && blas < model_count;
+    uint4 bt = make_uint4(0, 0, 0, 0);
+    if (active) {
+        bt = blas_table[blas * 3];
+        if (bt.z == 0) active = false;
+    }
+    // rows of object->world
+    float a[3][3], t[3];
+    for (int r_ = 0; r_ < 3; ++r_) {
+        for (int c = 0; c < 3; ++c) a[r_][c] = nd.worldTS.m[c][r_];
+        t[r_] = nd.worldTS.m[3][r_];
+    }
+    float c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+    float c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+    float c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+    float det = a[0][0] * c00 + a[0][1] * c01 + a[0][2] * c02;
+    float id = 1.0f / det;
+    float inv[3][3];
+    inv[0][0] = c00 * id;
+    inv[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id;
+    inv[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+    inv[1][0] = c01 * id;
+    inv[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id;
+    inv[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+    inv[2][0] = c02 * id;
+    inv[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id;
+    inv[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
+    for (int r_ = 0; r_ < 3; ++r_) {
+        for (int c = 0; c < 3; ++c) r.w2o[r_ * 4 + c] = inv[r_][c];
+        r.w2o[r_ * 4 + 3] = -(inv[r_][0] * t[0] + inv[r_][1] * t[1] + inv[r_][2] * t[2]);
+    }
+    r.node_base = bt.x;
+    r.tri_base = bt.y;
+    r.active = active ? 1u : 0u;
+    r.blas = blas;
+    inst[i] = r;
+    if (active) {
+        float4 bl = reinterpret_cast<const float4*>(blas_table)[blas * 3 + 1], bh = reinterpret_cast<const float4*>(blas_table)[blas * 3 + 2];
+        float3 mn = f3(FLT_MAX, FLT_MAX, FLT_MAX), mx = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+        for (int c = 0; c < 8; ++c) {
+            float3 p = f3(c & 1 ? bh.x : bl.x, c & 2 ? bh.y : bl.y, c & 4 ? bh.z : bl.z);
+            float3 w = f3(a[0][0] * p.x + a[0][1] * p.y + a[0][2] * p.z + t[0], a[1][0] * p.x + a[1][1] * p.y + a[1][2] * p.z + t[1],
+                          a[2][0] * p.x + a[2][1] * p.y + a[2][2] * p.z + t[2]);
+            mn = f3(fminf(mn.x, w.x), fminf(mn.y, w.y), fminf(mn.z, w.z));
+            mx = f3(fmaxf(mx.x, w.x), fmaxf(mx.y, w.y), fmaxf(mx.z, w.z));
+        }
+        float3 pad = (mx - mn) * 1e-6f + f3(1e-6f, 1e-6f, 1e-6f);
+        lo[i] = f4(mn.x - pad.x, mn.y - pad.y, mn.z - pad.z, 0);
+        hi[i] = f4(mx.x + pad.x, mx.y + pad.y, mx.z + pad.z, 0);
+    } else {
+        lo[i] = f4(1e30f, 1e30f, 1e30f, 0);
+        hi[i] = f4(-1e30f, -1e30f, -1e30f, 0);
+    }
+}
+
+inline dim3 grid_for(size_t n, int block = 256) { return dim3((unsigned)((n + block - 1) / block)); }
+
+struct Bvh2 {
+    float4 *lo, *hi;
+    int *left, *right, *first, *count;
+    uint32_t* order;
+    int root;
+};
+
+bool reserve_bvh2(BuildScratch& s, size_t n) {
+    size_t nn = 2 * n + 2;
+    return s.n2_lo.reserve(nn * 16) && s.n2_hi.reserve(nn * 16) && s.n2_left.reserve(nn * 4) && s.n2_right.reserve(nn * 4) &&
+           s.n2_parent.reserve(nn * 4) && s.n2_first.reserve(nn * 4) && s.n2_count.reserve(nn * 4) && s.n2_flag.reserve(nn * 4) &&
+           s.keys.reserve(n * 8) && s.keys_sorted.reserve(n * 8) && s.order.reserve(n * 4) && s.order_tmp.reserve(n * 4) &&
+           s.queue_a.reserve((n + 4) * 8) && s.queue_b.reserve((n + 4) * 8) && s.counters.reserve(64 * 4) && s.bounds.reserve(64);
+}
+
+// Morton LBVH over n boxes (prim_lo/prim_hi in scratch). Inactive (inverted) boxes sort to the end and are excluded.
+int build_lbvh(Context& c, uint32_t n_total, uint32_t n_active, Bvh2& out) {
+    BuildScratch& s = c.scratch;
+    cudaStream_t st = c.stream;
+    uint32_t n = n_total;
+    k_init_bounds<<<1, 32, 0, st>>>(s.bounds.as<int>());
+    k_bounds<<<grid_for(n), 256, 0, st>>>(s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), n, s.bounds.as<int>());
+    k_morton<<<grid_for(n), 256, 0, st>>>(s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), n, s.bounds.as<int>(), s.keys.as<uint64_t>(),
+                                          s.order_tmp.as<uint32_t>());
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s.keys.as<uint64_t>(), s.keys_sorted.as<uint64_t>(), s.order_tmp.as<uint32_t>(),
+                                    s.order.as<uint32_t>(), (int)n, 0, 64, st);
+    if (!s.sort_tmp.reserve(tmp_bytes)) return 1;
+    GK_CUDA(cub::DeviceRadixSort::SortPairs(s.sort_tmp.p, tmp_bytes, s.keys.as<uint64_t>(), s.keys_sorted.as<uint64_t>(),
+                                            s.order_tmp.as<uint32_t>(), s.order.as<uint32_t>(), (int)n, 0, 64, st));
+    c.launches += 4;
+    int m = (int)n_active;  // active primitives occupy sorted positions [0, m)
+    out.lo = s.n2_lo.as<float4>(); out.hi = s.n2_hi.as<float4>();
+    out.left = s.n2_left.as<int>(); out.right = s.n2_right.as<int>();
+    out.first = s.n2_first.as<int>(); out.count = s.n2_count.as<int>();
+    out.order = s.order.as<uint32_t>();
+    out.root = 0;
+    if (m == 0) return 0;
+    k_lbvh_leaves<<<grid_for(m), 256, 0, st>>>(s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), out.order, m, out.lo, out.hi, out.left, out.right,
+                                               out.first, out.count, s.n2_flag.as<int>());
+    if (m > 1) {
+        k_karras<<<grid_for(m - 1), 256, 0, st>>>(s.keys_sorted.as<uint64_t>(), m, out.left, out.right, s.n2_parent.as<int>(), out.first, out.count);
+        k_lbvh_fit<<<grid_for(m), 256, 0, st>>>(m, s.n2_parent.as<int>(), out.left, out.right, out.lo, out.hi, s.n2_flag.as<int>());
+        c.launches += 2;
+    }
+    c.launches += 1;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Level-synchronous SAH-binned build over n boxes (all active).
+int build_sah(Context& c, uint32_t n, Bvh2& out) {
+    BuildScratch& s = c.scratch;
+    cudaStream_t st = c.stream;
+    size_t max_slots = n / (kBlasLeafMax + 1) + 2;
+    if (!s.bins.reserve(max_slots * 3 * kSahBins * sizeof(SahBin)) || !s.pos_node.reserve((size_t)n * 4) || !s.pos_node_tmp.reserve((size_t)n * 4) ||
+        !s.active.reserve((max_slots * 2 + 4) * 4 * 2) || !s.cursors.reserve(max_slots * 2 * 4 + max_slots * sizeof(SahSplit) + 64))
+        return 1;
+    int* counters = s.counters.as<int>();
+    float4 *nlo = s.n2_lo.as<float4>(), *nhi = s.n2_hi.as<float4>();
+    int *left = s.n2_left.as<int>(), *right = s.n2_right.as<int>(), *first = s.n2_first.as<int>(), *count = s.n2_count.as<int>();
+    int* slot_of = s.n2_flag.as<int>();
+    uint32_t *ord_a = s.order.as<uint32_t>(), *ord_b = s.order_tmp.as<uint32_t>();
+    int *pn_a = s.pos_node.as<int>(), *pn_b = s.pos_node_tmp.as<int>();
+    int* act_a = s.active.as<int>();
+    int* act_b = act_a + (max_slots * 2 + 4);
+    int* cursors = s.cursors.as<int>();
+    SahSplit* splits = reinterpret_cast<SahSplit*>(cursors + max_slots * 2 + 16);
+
+    k_init_bounds<<<1, 32, 0, st>>>(s.bounds.as<int>());
+    k_bounds<<<grid_for(n), 256, 0, st>>>(s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), n, s.bounds.as<int>());
+    k_sah_init<<<grid_for(n), 256, 0, st>>>((int)n, s.bounds.as<int>(), nlo, nhi, left, right, first, count, ord_a, pn_a, act_a, counters);
+    k_fill_int<<<grid_for(2 * (size_t)n + 2), 256, 0, st>>>(slot_of, (int)(2 * n + 2), -1);
+    c.launches += 4;
+    int nactive = n > (uint32_t)kBlasLeafMax ? 1 : 0;
+    int guard = 0;
+    while (nactive > 0 && guard++ < 128) {
+        k_mark_slots<<<grid_for(nactive), 256, 0, st>>>(act_a, nactive, slot_of, 0);
+        k_sah_clear_bins<<<grid_for((size_t)nactive * 3 * kSahBins), 256, 0, st>>>(s.bins.as<SahBin>(), nactive);
+        k_sah_bin<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, s.bins.as<SahBin>());
+        k_sah_split<<<grid_for(nactive), 128, 0, st>>>(nactive, act_a, s.bins.as<SahBin>(), nlo, nhi, left, right, first, count, counters, act_b, splits,
+                                                      cursors);
+        k_sah_partition<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, left, first,
+                                                     splits, cursors, ord_b, pn_b);
+        k_mark_slots<<<grid_for(nactive), 256, 0, st>>>(act_a, nactive, slot_of, 1);
+        c.launches += 6;
+        int h[3];
+        GK_CUDA(cudaMemcpyAsync(h, counters, 12, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        nactive = h[2];
+        int zero = 0;
+        GK_CUDA(cudaMemcpyAsync(counters + 2, &zero, 4, cudaMemcpyHostToDevice, st));
+        std::swap(ord_a, ord_b);
+        std::swap(pn_a, pn_b);
+        std::swap(act_a, act_b);
+    }
+    out.lo = nlo; out.hi = nhi; out.left = left; out.right = right; out.first = first; out.count = count;
+    out.order = ord_a;
+    out.root = 0;
+    return 0;
+}
+
+// BVH2 -> Node4 (BFS), returns node count and the level table.
+int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, bool tlas_mode, Node4* out, float4* out_lo, float4* out_hi,
+             WideBvhInfo& info) {
+    BuildScratch& s = c.scratch;
+    cudaStream_t st = c.stream;
+    int* counters = s.counters.as<int>();  // [8] node counter, [9] out-queue count
+    int2 *qa = s.queue_a.as<int2>(), *qb = s.queue_b.as<int2>();
+    int2 root = make_int2(b.root, 0);
+    int init[2] = {1, 0};
+    GK_CUDA(cudaMemcpyAsync(qa, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(counters + 8, init, 8, cudaMemcpyHostToDevice, st));
+    info.level_start.clear();
+    info.level_start.push_back(0);
+    int nin = 1, total = 1;
+    (void)n_prims;
+    while (nin > 0) {
+        k_collapse_level<<<grid_for(nin, 128), 128, 0, st>>>(qa, nin, qb, counters + 9, counters + 8, b.lo, b.hi, b.left, b.right, b.first, b.count,
+                                                             leaf_max, b.order, tlas_mode ? 1 : 0, out, out_lo, out_hi);
+        c.launches += 1;
+        int h[2];
+        GK_CUDA(cudaMemcpyAsync(h, counters + 8, 8, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        int zero = 0;
+        GK_CUDA(cudaMemcpyAsync(counters + 9, &zero, 4, cudaMemcpyHostToDevice, st));
+        info.level_start.push_back((uint32_t)total);
+        nin = h[1];
+        total = h[0];
+        std::swap(qa, qb);
+    }
+    info.level_start.back() = (uint32_t)total;
+    info.node_count = (uint32_t)total;
+    return 0;
+}
+
+}  // namespace
+
+gkd::TraceScene make_trace_scene(const Context& c) {
+    gkd::TraceScene s;
+    s.tlas = c.tlas_nodes.as<Node4>();
+    s.blas = c.blas_nodes.as<Node4>();
+    s.tris = c.blas_tris.as<float4>();
+    s.inst = c.instances.as<InstanceRec>();
+    s.tlas_nodes = c.tlas.node_count;
+    return s;
+}
+
+int build_all_blas(Context& c) {
+    cudaStream_t st = c.stream;
+    const char* env = getenv("GKCU_BLAS_BUILDER");
+    if (env) c.blas_builder = (std::string(env) == "lbvh") ? 0 : 1;
+    c.blas.assign(c.model_count, WideBvhInfo());
+    size_t total_prims = 0;
+    for (uint32_t m = 0; m < c.model_count; ++m) {
+        uint32_t idx = 0;
+        for (int s = 0; s < 10; ++s) idx += c.host_offsets[m * 10 + s].indexCount;
+        c.blas[m].prim_count = idx / 3;
+        c.blas[m].vertex_offset = c.host_offsets[m * 10].vertexOffset;
+        c.blas[m].index_offset = c.host_offsets[m * 10].indexOffset;
+        total_prims += idx / 3;
+    }
+    size_t node_cap = total_prims + 2 * (size_t)c.model_count + 4;
+    if (!c.blas_nodes.reserve(node_cap * sizeof(Node4)) || !c.blas_node_lo.reserve(node_cap * 16) || !c.blas_node_hi.reserve(node_cap * 16) ||
+        !c.blas_tris.reserve((total_prims + 1) * 48) || !c.blas_tri_prim.reserve((total_prims + 1) * 4) ||
+        !c.blas_table.reserve((size_t)(c.model_count + 1) * 48))
+        return 1;
+    cudaEventRecord(c.ev[6], st);
+    uint32_t node_base = 0, tri_base = 0;
+    std::vector<float> table((size_t)c.model_count * 12, 0.0f);
+    for (uint32_t m = 0; m < c.model_count; ++m) {
+        WideBvhInfo& bi = c.blas[m];
+        bi.node_base = node_base;
+        bi.tri_base = tri_base;
+        uint32_t n = bi.prim_count;
+        uint32_t* tb = reinterpret_cast<uint32_t*>(&table[(size_t)m * 12]);
+        tb[0] = node_base; tb[1] = tri_base; tb[2] = n; tb[3] = 0;
+        if (n == 0) continue;
+        if (n >= (1u << 28)) { set_error("BLAS with >= 2^28 triangles"); return 1; }
+        BuildScratch& s = c.scratch;
+        if (!s.prim_lo.reserve((size_t)n * 16) || !s.prim_hi.reserve((size_t)n * 16) || !reserve_bvh2(s, n)) return 1;
+        k_tri_boxes<<<grid_for(n), 256, 0, st>>>(c.simple.as<uint16_t>(), c.indices.as<uint32_t>(), bi.vertex_offset, bi.index_offset, n,
+                                                 s.prim_lo.as<float4>(), s.prim_hi.as<float4>());
+        c.launches += 1;
+        Bvh2 b2;
+        if (c.blas_builder == 1) { if (build_sah(c, n, b2)) return 1; }
+        else { if (build_lbvh(c, n, n, b2)) return 1; }
+        Node4* out = c.blas_nodes.as<Node4>() + node_base;
+        if (collapse(c, b2, n, kBlasLeafMax, false, out, c.blas_node_lo.as<float4>() + node_base, c.blas_node_hi.as<float4>() + node_base, bi)) return 1;
+        k_write_tris<<<grid_for(n), 256, 0, st>>>(c.simple.as<uint16_t>(), c.indices.as<uint32_t>(), bi.vertex_offset, bi.index_offset, b2.order, n,
+                                                  c.blas_tris.as<float4>() + (size_t)tri_base * 3, c.blas_tri_prim.as<uint32_t>() + tri_base);
+        c.launches += 1;
+        float4 rl, rh;
+        GK_CUDA(cudaMemcpyAsync(&rl, c.blas_node_lo.as<float4>() + node_base, 16, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaMemcpyAsync(&rh, c.blas_node_hi.as<float4>() + node_base, 16, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        bi.root_lo[0] = rl.x; bi.root_lo[1] = rl.y; bi.root_lo[2] = rl.z;
+        bi.root_hi[0] = rh.x; bi.root_hi[1] = rh.y; bi.root_hi[2] = rh.z;
+        float* tf = &table[(size_t)m * 12];
+        tf[4] = rl.x; tf[5] = rl.y; tf[6] = rl.z; tf[7] = 0;
+        tf[8] = rh.x; tf[9] = rh.y; tf[10] = rh.z; tf[11] = 0;
+        node_base += bi.node_count;
+        tri_base += n;
+    }
+    GK_CUDA(cudaMemcpyAsync(c.blas_table.p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st));
+    cudaEventRecord(c.ev[7], st);
+    GK_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c.timings.blas_build_ms, c.ev[6], c.ev[7]);
+    c.blas_built = true;
+    c.tlas_dirty = true;
+    return 0;
+}
+
+int refit_blas(Context& c, uint32_t model) {
+    if (!c.blas_built || model >= c.model_count) { set_error("gkcu_blas_refit: no such BLAS"); return 1; }
+    cudaStream_t st = c.stream;
+    WideBvhInfo& bi = c.blas[model];
+    if (bi.prim_count == 0) return 0;
+    cudaEventRecord(c.ev[6], st);
+    k_write_tris<<<grid_for(bi.prim_count), 256, 0, st>>>(c.simple.as<uint16_t>(), c.indices.as<uint32_t>(), bi.vertex_offset, bi.index_offset, nullptr,
+                                                          bi.prim_count, c.blas_tris.as<float4>() + (size_t)bi.tri_base * 3,
+                                                          c.blas_tri_prim.as<uint32_t>() + bi.tri_base);
+    c.launches += 1;
+    Node4* nodes = c.blas_nodes.as<Node4>() + bi.node_base;
+    float4 *nlo = c.blas_node_lo.as<float4>() + bi.node_base, *nhi = c.blas_node_hi.as<float4>() + bi.node_base;
+    for (int L = (int)bi.level_start.size() - 2; L >= 0; --L) {
+        uint32_t b = bi.level_start[L], e = bi.level_start[L + 1];
+        if (e <= b) continue;
+        k_refit_level<<<grid_for(e - b, 128), 128, 0, st>>>(nodes, nlo, nhi, b, e, c.blas_tris.as<float4>() + (size_t)bi.tri_base * 3);
+        c.launches += 1;
+    }
+    // the root box feeds the instance boxes of the next TLAS build
+    GK_CUDA(cudaMemcpyAsync(reinterpret_cast<float4*>(c.blas_table.p) + model * 3 + 1, nlo, 16, cudaMemcpyDeviceToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(reinterpret_cast<float4*>(c.blas_table.p) + model * 3 + 2, nhi, 16, cudaMemcpyDeviceToDevice, st));
+    cudaEventRecord(c.ev[7], st);
+    GK_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c.timings.blas_refit_ms, c.ev[6], c.ev[7]);
+    c.tlas_dirty = true;
+    return 0;
+}
+
+int build_tlas(Context& c) {
+    cudaStream_t st = c.stream;
+    uint32_t n = c.node_count;
+    c.tlas.node_count = 0;
+    c.tlas_dirty = false;
+    if (n == 0 || !c.blas_built) return 0;
+    if (n >= (1u << 28)) { set_error("too many instances"); return 1; }
+    BuildScratch& s = c.scratch;
+    if (!c.instances.reserve((size_t)n * sizeof(InstanceRec)) || !s.prim_lo.reserve((size_t)n * 16) || !s.prim_hi.reserve((size_t)n * 16) ||
+        !reserve_bvh2(s, n) || !c.tlas_nodes.reserve(((size_t)n + 4) * sizeof(Node4)) || !c.tlas_node_lo.reserve(((size_t)n + 4) * 16) ||
+        !c.tlas_node_hi.reserve(((size_t)n + 4) * 16))
+        return 1;
+    k_instances<<<grid_for(n), 128, 0, st>>>(c.nodes.as<GkNodeProxy>(), n, c.blas_table.as<uint4>(), c.model_count, c.instances.as<InstanceRec>(),
+                                             s.prim_lo.as<float4>(), s.prim_hi.as<float4>());
+    c.launches += 1;
+    // count active instances: they sort in front of the inactive ones (key 0x7FFF...)
+    // cheap host-side count from the node proxies we were given
+    uint32_t n_active = c.tlas.prim_count;  // set by gkcu_update_nodes
+    Bvh2 b2;
+    if (build_lbvh(c, n, n_active, b2)) return 1;
+    if (n_active == 0) return 0;
+    if (collapse(c, b2, n_active, 1, true, c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+    // the traversal stack holds at most 3 entries per level plus one sentinel per instance entry
+    size_t blas_levels = 0;
+    for (auto& b : c.blas) blas_levels = std::max(blas_levels, b.level_start.size() > 0 ? b.level_start.size() - 1 : 0);
+    size_t need = 3 * (c.tlas.level_start.size() - 1) + 3 * blas_levels + 2;
+    if (need > GK_TRAV_STACK) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "acceleration structure too deep for the traversal stack (%zu TLAS + %zu BLAS levels need %zu entries, have %d)",
+                 c.tlas.level_start.size() - 1, blas_levels, need, GK_TRAV_STACK);
+        set_error(msg);
+        c.tlas.node_count = 0;
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace gkcu

@@ -1,0 +1,124 @@
+// gk_context.h — the renderer context behind the opaque GkcuContext handle, shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gkcu.h"
+#include "gk_bvh.cuh"
+
+namespace gkcu {
+
+void set_error(const std::string& msg);
+bool check(cudaError_t e, const char* what);
+#define GK_CUDA(expr)                                \
+    do {                                             \
+        if (!gkcu::check((expr), #expr)) return 1;   \
+    } while (0)
+
+// Growable device allocation (cudaMalloc is only hit when a buffer has to grow).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes);
+    void release();
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+// One built wide BVH (BLAS of one model, or the TLAS).
+struct WideBvhInfo {
+    uint32_t node_base = 0;     // first node in the owning node pool
+    uint32_t node_count = 0;
+    uint32_t tri_base = 0;      // BLAS only: first leaf-ordered triangle in the triangle pool
+    uint32_t prim_count = 0;
+    uint32_t vertex_offset = 0, index_offset = 0;
+    std::vector<uint32_t> level_start;  // node index (relative) of each BFS level, size levels+1
+    float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+};
+
+// Scratch + outputs of one BVH2 build, see gk_bvh_build.cu.
+struct BuildScratch {
+    DevBuf prim_lo, prim_hi, keys, keys_sorted, order, order_tmp, sort_tmp;
+    DevBuf n2_lo, n2_hi, n2_left, n2_right, n2_parent, n2_first, n2_count, n2_flag;
+    DevBuf queue_a, queue_b, counters, bounds;
+    DevBuf bins, pos_node, pos_node_tmp, active, cursors;
+};
+
+struct RenderTargets {
+    uint32_t w = 0, h = 0;
+    // fp16x4 images as uint2 per pixel
+    uint2 *accum_diffuse[2] = {nullptr, nullptr}, *accum_specular[2] = {nullptr, nullptr}, *accum_albedo[2] = {nullptr, nullptr};
+    uint2 *single_diffuse = nullptr, *single_specular = nullptr, *albedo = nullptr, *normal = nullptr, *denoised = nullptr;
+    uint32_t* objectid[2] = {nullptr, nullptr};
+    uint32_t* primitiveid = nullptr;
+    float2* motion = nullptr;
+    float* prev_depth = nullptr;
+    uint16_t* moment = nullptr;
+    int cur = 0;  // accum_*[cur] is this frame's ACCUM, [cur^1] is PREV; objectid[cur] is OBJECTID_0
+};
+
+struct PathBuffers;  // gk_pathtrace.cu
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+
+    // scene (GPUScene buffers, BasicTypes.slang:261-291)
+    DevBuf vertices, simple, indices, offsets, materials, nodes;
+    uint32_t vertex_count = 0, index_count = 0, offset_count = 0, model_count = 0, material_count = 0, node_count = 0;
+    std::vector<GkModelData> host_offsets;
+
+    // acceleration structures
+    DevBuf blas_nodes, blas_node_lo, blas_node_hi, blas_tris, blas_tri_prim;  // pools shared by all BLAS
+    std::vector<WideBvhInfo> blas;
+    DevBuf blas_table;  // per model: node_base, tri_base, prim_count, pad + root box (2 x float4)
+    DevBuf tlas_nodes, tlas_node_lo, tlas_node_hi, instances, inst_lo, inst_hi;
+    WideBvhInfo tlas;
+    bool tlas_dirty = true;
+    bool blas_built = false;
+    BuildScratch scratch;
+    int blas_builder = 1;  // 0 = LBVH, 1 = SAH-binned (GKCU_BLAS_BUILDER=lbvh|sah)
+
+    // textures / probes
+    struct Tex { float4* texels = nullptr; uint32_t w = 0, h = 0; };
+    std::vector<Tex> textures;
+    DevBuf tex_table;
+    uint32_t tex_count = 0;
+    DevBuf cubes, voxels;
+    bool has_probes = false;
+
+    DevBuf ubo;
+    RenderTargets rt;
+    PathBuffers* path = nullptr;
+
+    GkcuTimings timings{};
+    GkcuCounters counters{};
+    cudaEvent_t ev[8] = {};
+    uint64_t launches = 0;
+    DevBuf trace_rays, trace_hits;
+};
+
+gkd::TraceScene make_trace_scene(const Context& c);
+
+// gk_bvh_build.cu
+int build_all_blas(Context& c);
+int refit_blas(Context& c, uint32_t model);
+int build_tlas(Context& c);
+
+// gk_pathtrace.cu
+int path_resize(Context& c);
+void path_release(Context& c);
+int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p);
+int run_resolve(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p);
+int run_trace_rays(Context& c, uint32_t count, bool any_hit);
+void fetch_ray_counters(Context& c);
+int radiance_buffer(Context& c, void** ptr, size_t* bytes);
+
+// gk_post.cu
+int run_reproject(Context& c, const GkcuFrameParams& p);
+int run_denoise(Context& c, const GkUniformBufferObject& ubo);
+
+}  // namespace gkcu

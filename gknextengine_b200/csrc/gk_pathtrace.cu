@@ -1,0 +1,971 @@
+// gk_pathtrace.cu — the "rt pass": primary visibility + G-buffer + the path tracer.
+//
+// Restates the reference's megakernel (assets/shaders/Core.PathTracing.comp.slang:5-31 ->
+// FPathTracingRendererV2, assets/shaders/common/Shading.slang:995-1261) as a per-pixel state machine so the same
+// shading code runs in two drivers:
+//   * wavefront (default): k_primary -> { k_trace (persistent threads, dynamic ray fetch) -> k_shade (advance the
+//     state machine, warp-ballot compaction of the survivors) }* -> k_tail (finishes the thin tail in one launch)
+//   * megakernel (tracer = 1): k_primary -> k_tail over every pixel (one thread per pixel, traversal inlined).
+// The reference threads ONE pcg4d state per pixel through all samples and bounces (Shading.slang:1232, 1117, 1130,
+// 1135-1147, 1179); a pixel therefore has one path in flight at a time and samples run in order, which keeps the
+// random stream - and with it every ray - identical to the megakernel order.
+#include <algorithm>
+#include <cstdio>
+
+#include "gk_context.h"
+
+using namespace gkd;
+
+namespace gkcu {
+
+struct TexDesc { const float4* texels; uint32_t w, h; uint32_t pad; };
+
+struct SceneView {
+    TraceScene ts;
+    const uint2* vertices;  // GkGPUVertex as 3 x uint2
+    const uint32_t* indices;
+    const GkModelData* offsets;
+    const GkMaterial* materials;
+    uint32_t material_count;
+    const GkNodeProxy* nodes;
+    const TexDesc* textures;
+    uint32_t tex_count;
+    const GkAmbientCube* cubes;
+    const GkVoxelData* voxels;
+    const GkUniformBufferObject* cam;
+};
+
+struct RTView {
+    uint32_t w, h;
+    uint2 *single_diffuse, *single_specular, *albedo, *normal;
+    uint32_t *objectid0, *primitiveid;
+    float2* motion;
+    float* prev_depth;
+    uint16_t* moment;
+};
+
+// Per-pixel path state (SoA, 16-byte records) + per-slot ray/hit records of the wavefront queues.
+struct PathView {
+    uint4* rng;
+    float4 *pos_mat, *nrm_flags, *dir_cnt, *ray_color, *final_color, *final_refl;
+    float4 *prim_pos_mat, *prim_nrm_cnt, *prim_albedo;
+    float4 *ray_o, *ray_d;      // per slot: origin|tmin, dir|tmax
+    uint32_t* slot_pixel[2];    // per slot: pixel | any-hit flag in bit 31 (ping-pong)
+    float4* hit_tuv;            // per slot: t, u, v, inst
+    uint32_t* hit_prim;
+    uint32_t* counts;           // [0],[1] queue sizes (ping-pong), [2] trace cursor, [4..] ray counters
+    float4 *radiance, *direct;  // multi-GPU: un-normalised sums (2 planes) and rank 0's direct term
+};
+
+struct PathBuffers {
+    DevBuf rng, pos_mat, nrm_flags, dir_cnt, ray_color, final_color, final_refl, prim_pos_mat, prim_nrm_cnt, prim_albedo;
+    DevBuf ray_o, ray_d, slot_pixel[2], hit_tuv, hit_prim, counts, radiance, direct;
+    uint32_t* host_counts = nullptr;  // pinned
+    size_t pixels = 0;
+};
+
+struct FrameCfg {
+    uint32_t frame_seed;     // TotalFrames, or TotalFrames * world + rank
+    uint32_t rank, world;
+    uint32_t to_radiance;    // 1: leave un-normalised sums in the radiance buffer (multi-GPU)
+    uint32_t exit_after_first;
+};
+
+namespace {
+
+#define ST_FIRST 0u
+#define ST_BOUNCE 1u
+#define ST_SUN 2u
+#define ST_DIRECT 3u
+#define FL_HIT_REFLECT 1u
+#define FL_HIT_METAL 2u
+#define FL_CHANCE_REFLECT 4u
+#define FL_BACKFACE_ND 8u
+#define FL_STAGE_SHIFT 4
+#define FL_STAGE_MASK (3u << FL_STAGE_SHIFT)
+#define FL_PRIM_DIELECTRIC 64u
+
+#define REQ_DONE 0
+#define REQ_CLOSEST 1
+#define REQ_ANY 2
+
+struct PathRegs {
+    uint4 rng;
+    float3 pos, nrm;
+    uint32_t mat;
+    float3 dir;
+    float4 rayColor, finalColor, finalRefl;
+    uint32_t flags;
+    uint32_t sample, sampleEnd, sampleTotal, bounce, maxBounces;
+    float3 ppos, pnrm;
+    uint32_t pmat;
+    float4 palbedo;
+    float3 ro, rd;
+};
+
+GK_DEV GkMaterial get_material(const SceneView& S, uint32_t idx) {  // BasicTypes.slang:376-379
+    int i = min(GK_MAX_MATERIALS - 1, max(0, (int)idx));
+    if (i >= (int)S.material_count) {
+        GkMaterial z;
+        z.Diffuse = {0, 0, 0, 0}; z.DiffuseTextureId = 0; z.MRATextureId = 0; z.NormalTextureId = 0; z.Fuzziness = 0; z.RefractionIndex = 0;
+        z.MaterialModel = 0; z.Metalness = 0; z.RefractionIndex2 = 0; z.NormalTextureScale = 0; z.Reserverd2 = z.Reserverd3 = z.Reserverd4 = 0;
+        return z;
+    }
+    const float4* p = reinterpret_cast<const float4*>(S.materials + i);
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    GkMaterial m;
+    m.Diffuse = {a.x, a.y, a.z, a.w};
+    m.DiffuseTextureId = __float_as_int(b.x); m.MRATextureId = __float_as_int(b.y); m.NormalTextureId = __float_as_int(b.z); m.Fuzziness = b.w;
+    m.RefractionIndex = c.x; m.MaterialModel = __float_as_uint(c.y); m.Metalness = c.z; m.RefractionIndex2 = c.w;
+    m.NormalTextureScale = 0; m.Reserverd2 = m.Reserverd3 = m.Reserverd4 = 0;
+    return m;
+}
+
+struct VtxLite { float3 pos, nrm; float2 uv; float4 tan; uint32_t matSlot; };
+GK_DEV VtxLite unpack_vertex(const SceneView& S, uint32_t vi) {  // UnpackVertexV2, Const_Func.slang:356-368
+    const uint2* p = S.vertices + (size_t)vi * 3;
+    uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    VtxLite v;
+    v.pos = f3(h2f(a.x & 0xFFFF), h2f(a.x >> 16), h2f(a.y & 0xFFFF));
+    v.nrm = f3(h2f(b.x & 0xFFFF), h2f(b.x >> 16), h2f(b.y & 0xFFFF));
+    v.uv = make_float2(h2f(a.y >> 16), h2f(b.y >> 16));
+    uint32_t tw = c.y >> 16;
+    v.tan = f4(h2f(c.x & 0xFFFF), h2f(c.x >> 16), h2f(c.y & 0xFFFF), (float)((tw >> 8) & 0xFF));
+    v.matSlot = tw & 0xFF;
+    return v;
+}
+GK_DEV uint32_t fetch_material_id(const GkNodeProxy* node, uint32_t slot) { return slot < 16 ? node->matId[slot] : 0; }  // :370-424
+
+// Sampler2D.SampleLevel(uv, 0): linear, repeat (src/Vulkan/Sampler.hpp:9-26), full-precision weights
+GK_DEV float4 sample_texture(const SceneView& S, uint32_t id, float2 uv) {
+    if (id >= S.tex_count) return f4(0, 0, 0, 0);
+    TexDesc tx = S.textures[id];
+    if (tx.w == 0) return f4(0, 0, 0, 0);
+    float x = uv.x * (float)tx.w - 0.5f, y = uv.y * (float)tx.h - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    int x0 = (int)fx, y0 = (int)fy;
+    int xa = x0 % (int)tx.w; if (xa < 0) xa += tx.w;
+    int xb = (x0 + 1) % (int)tx.w; if (xb < 0) xb += tx.w;
+    int ya = y0 % (int)tx.h; if (ya < 0) ya += tx.h;
+    int yb = (y0 + 1) % (int)tx.h; if (yb < 0) yb += tx.h;
+    float4 t00 = __ldg(tx.texels + (size_t)ya * tx.w + xa), t10 = __ldg(tx.texels + (size_t)ya * tx.w + xb);
+    float4 t01 = __ldg(tx.texels + (size_t)yb * tx.w + xa), t11 = __ldg(tx.texels + (size_t)yb * tx.w + xb);
+    return lerp4(lerp4(t00, t10, ax), lerp4(t01, t11, ax), ay);
+}
+
+GK_DEV float4 SampleIBLV2(const SceneView& S, uint32_t skyIdx, float3 direction, float rotate) {  // Shading.slang:194-199
+    float3 d = normalize(direction);
+    float2 t = make_float2((atan2f(d.x, d.z) + GK_M_PI * rotate) * GK_M_1_OVER_TWO_PI, acosf(d.y) * GK_M_1_PI);
+    float4 s = sample_texture(S, skyIdx, t);
+    return f4(fminf(10.f, s.x), fminf(10.f, s.y), fminf(10.f, s.z), fminf(1.f, s.w));
+}
+GK_DEV float4 sky_color(const SceneView& S, float3 dir) {
+    const GkUniformBufferObject* C = S.cam;
+    return C->HasSky ? SampleIBLV2(S, C->SkyIdx, dir, C->SkyRotation) * C->SkyIntensity : f4(0, 0, 0, 0);
+}
+
+// AmbientCube.slang:71-78, 178-223, 290-382
+GK_DEV float4 unpackRGB10A2(uint32_t p) {
+    float r = float(p & 0x3FF) / 1023.0f, g = float((p >> 10) & 0x3FF) / 1023.0f, b = float((p >> 20) & 0x3FF) / 1023.0f;
+    return f4(r, g, b, 0.0f) * 512.f;
+}
+GK_DEV float4 sampleAmbientCubeHL2_Full(const GkAmbientCube& cube, float3 normal) {
+    float4 color = f4(0, 0, 0, 0);
+    float skyvis = 0.0f;
+    float wx = fmaxf(normal.x, 0.0f), wnx = fmaxf(-normal.x, 0.0f), wy = fmaxf(normal.y, 0.0f), wny = fmaxf(-normal.y, 0.0f),
+          wz = fmaxf(normal.z, 0.0f), wnz = fmaxf(-normal.z, 0.0f);
+    float sum = wx + wnx + wy + wny + wz + wnz;
+    uint32_t s0 = cube.skyVisibility_pznzpyny, s1 = cube.skyVisibility_pxnxs0s1;
+    skyvis += float(s0 & 0xFF) * wz;
+    skyvis += float((s0 >> 8) & 0xFF) * wnz;
+    skyvis += float((s0 >> 16) & 0xFF) * wy;
+    skyvis += float((s0 >> 24) & 0xFF) * wny;
+    skyvis += float(s1 & 0xFF) * wx;
+    skyvis += float((s1 >> 8) & 0xFF) * wnx;
+    color = color + unpackRGB10A2(cube.PosX_D) * wx; color = color + unpackRGB10A2(cube.NegX_D) * wnx;
+    color = color + unpackRGB10A2(cube.PosY_D) * wy; color = color + unpackRGB10A2(cube.NegY_D) * wny;
+    color = color + unpackRGB10A2(cube.PosZ_D) * wz; color = color + unpackRGB10A2(cube.NegZ_D) * wnz;
+    color = color + unpackRGB10A2(cube.PosX) * wx; color = color + unpackRGB10A2(cube.NegX) * wnx;
+    color = color + unpackRGB10A2(cube.PosY) * wy; color = color + unpackRGB10A2(cube.NegY) * wny;
+    color = color + unpackRGB10A2(cube.PosZ) * wz; color = color + unpackRGB10A2(cube.NegZ) * wnz;
+    float k = (sum > 0.0f) ? (1.0f / sum) : 1.0f;
+    color.x *= k; color.y *= k; color.z *= k;
+    skyvis *= k;
+    color.w = skyvis / 255.0f;
+    return color;
+}
+__device__ __noinline__ float4 interpolateAmbientCubesV2(const SceneView& S, float3 inPos, float3 normal) {
+    const float3 CUBE_OFFSET = f3(-GK_CUBE_SIZE_XY / 2, -1.375f, -GK_CUBE_SIZE_XY / 2) * 0.25f;
+    float3 nearpos = (inPos - CUBE_OFFSET) * (1.0f / 0.25f);
+    if (nearpos.x < 0 || nearpos.y < 0 || nearpos.z < 0 || nearpos.x > GK_CUBE_SIZE_XY - 2 || nearpos.y > GK_CUBE_SIZE_Z - 2 ||
+        nearpos.z > GK_CUBE_SIZE_XY - 2)
+        return f4(0, 0, 0, 1);
+    if (!S.cubes) return f4(0, 0, 0, 0);  // zero probe state: every probe is skipped at AmbientCube.slang:327
+    int bx = (int)floorf(nearpos.x), by = (int)floorf(nearpos.y), bz = (int)floorf(nearpos.z);
+    float3 fr = f3(nearpos.x - floorf(nearpos.x), nearpos.y - floorf(nearpos.y), nearpos.z - floorf(nearpos.z));
+    float totalWeight = 0.0f;
+    float4 result = f4(0, 0, 0, 0);
+    for (int i = 0; i < 8; i++) {
+        int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
+        int idx = (by + oy) * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + (bz + oz) * GK_CUBE_SIZE_XY + (bx + ox);
+        const GkVoxelData voxel = S.voxels[idx];
+        uint32_t u0 = voxel.distanceToSolid_gg_z01, u1 = voxel.distanceToSolid_x01_y01;
+        float d0y = float((u0 >> 8) & 0xFF) / 255.0f, distPZ = float((u0 >> 16) & 0xFF) / 255.0f, distNZ = float((u0 >> 24) & 0xFF) / 255.0f;
+        float distPX = float(u1 & 0xFF) / 255.0f, distNX = float((u1 >> 8) & 0xFF) / 255.0f, distPY = float((u1 >> 16) & 0xFF) / 255.0f,
+              distNY = float((u1 >> 24) & 0xFF) / 255.0f;
+        if (d0y < 0.01f) continue;
+        float3 probeToLocal = fr - f3((float)ox, (float)oy, (float)oz);
+        float distanceToProbe = length(probeToLocal);
+        float3 dir = normalize(probeToLocal);
+        float hitLength = sqrtf(fmaxf(dir.x, 0.0f)) * distPX + sqrtf(fmaxf(-dir.x, 0.0f)) * distNX + sqrtf(fmaxf(dir.y, 0.0f)) * distPY +
+                          sqrtf(fmaxf(-dir.y, 0.0f)) * distNY + sqrtf(fmaxf(dir.z, 0.0f)) * distPZ + sqrtf(fmaxf(-dir.z, 0.0f)) * distNZ;
+        if (distanceToProbe > hitLength + 0.05f) continue;
+        float wx = ox == 0 ? (1.0f - fr.x) : fr.x, wy = oy == 0 ? (1.0f - fr.y) : fr.y, wz = oz == 0 ? (1.0f - fr.z) : fr.z;
+        float weight = wx * wy * wz;
+        result = result + sampleAmbientCubeHL2_Full(S.cubes[idx], normal) * weight;
+        totalWeight += weight;
+    }
+    return totalWeight > 0.0f ? result / totalWeight : f4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ primary hit
+struct PrimVertex { float3 pos, nrm; float2 uv; uint32_t matSlot; };
+
+// Common.get_material_dataV2, GeneralFunc.slang:6-56 (tangent frames only feed normal maps: "next" row f4)
+GK_DEV PrimVertex get_material_dataV2(const SceneView& S, uint32_t nodeIdx, uint32_t prim, float3 ray_origin, float3 ray_direction) {
+    const GkNodeProxy* proxy = S.nodes + nodeIdx;
+    const GkModelData* model = S.offsets + proxy->modelId;
+    const uint32_t vo = model->vertexOffset, io = model->indexOffset;
+    float3 positions[3], normals[3];
+    float2 tex[3];
+    uint32_t matid = 0;
+    for (int i = 0; i != 3; ++i) {
+        VtxLite v = unpack_vertex(S, vo + __ldg(S.indices + io + prim * 3 + i));
+        positions[i] = xyz(mul(proxy->worldTS, f4(v.pos.x, v.pos.y, v.pos.z, 1)));
+        normals[i] = xyz(mul(proxy->worldTS, f4(v.nrm.x, v.nrm.y, v.nrm.z, 0)));
+        tex[i] = v.uv;
+        if (i == 0) matid = v.matSlot;
+    }
+    float3 e0 = positions[1] - positions[0], e1 = positions[2] - positions[0];
+    float3 ray_cross_edge_1 = cross(ray_direction, e1);
+    float rcp_det = 1.0f / dot(e0, ray_cross_edge_1);
+    float3 ray_to_0 = ray_origin - positions[0];
+    float by = rcp_det * dot(ray_to_0, ray_cross_edge_1);
+    float3 edge_0_cross_0 = cross(e0, ray_to_0);
+    float bz = -rcp_det * dot(ray_direction, edge_0_cross_0);
+    float bx = 1.0f - (by + bz);
+    PrimVertex r;
+    r.pos = positions[0] * bx + (positions[1] * by + positions[2] * bz);
+    r.nrm = normalize(normals[0] * bx + (normals[1] * by + normals[2] * bz));
+    r.uv = tex[0] * bx + (tex[1] * by + tex[2] * bz);
+    r.matSlot = matid;
+    return r;
+}
+
+GK_DEV float3 pixel_ray_dir(const GkUniformBufferObject* C, int x, int y, int w, int h) {  // Shading.slang:350-356
+    float2 uv = make_float2((float)x / (float)w * 2.0f - 1.0f, (float)y / (float)h * 2.0f - 1.0f);
+    float4 target = mul(C->ProjectionInverse, f4(uv.x, uv.y, 1, 1));
+    float3 tn = normalize(xyz(target));
+    float4 dir = mul(C->ModelViewInverse, f4(tn.x, tn.y, tn.z, 0));
+    return normalize(xyz(dir));
+}
+
+// ------------------------------------------------------------------------------------------------ state machine
+// GetRayColor up to the TraceRay call (Shading.slang:1005-1039)
+GK_DEV void gen_closest(const SceneView& S, PathRegs& P, bool first) {
+    GkMaterial mat = get_material(S, P.mat);
+    const float startPosOffset = mat.MaterialModel == GK_MATERIAL_DIELECTRIC ? 0.0f : 1.0f;
+    float roughness = mat.Fuzziness;
+    const float dotValue = dot(P.dir, P.nrm);
+    const bool BackFace = dotValue > 0;
+    const float3 outwardNormal = BackFace ? -P.nrm : P.nrm;
+    const float niOverNt = BackFace ? mat.RefractionIndex2 : (1 / mat.RefractionIndex2);
+    const float cosine = dotValue > 0 ? mat.RefractionIndex * dotValue : -dotValue;
+    const float reflectProb = Schlick(cosine, mat.RefractionIndex);
+    const float metalProb = mat.Metalness;
+    bool chanceReflect = (RandomFloat(P.rng) < reflectProb);
+    bool chanceMetal = (RandomFloat(P.rng) < metalProb);
+    bool chanceGGX = chanceReflect || chanceMetal;
+    const float3 trace_next = chanceGGX ? reflect3(P.dir, outwardNormal) : outwardNormal;
+    float3 trace_dir;
+    if (chanceGGX) trace_dir = ggxSampling(P.rng, sqrtf(roughness), trace_next);
+    else trace_dir = AlignWithNormal(RandomInHemiSphere1(P.rng), trace_next);
+    if (first) {
+        P.flags &= ~(FL_HIT_REFLECT | FL_HIT_METAL);
+        if (chanceGGX) P.flags |= FL_HIT_REFLECT;
+        if (chanceMetal) P.flags |= FL_HIT_METAL;
+    }
+    if (mat.MaterialModel == GK_MATERIAL_DIELECTRIC) {
+        if (!chanceReflect) trace_dir = refract3(P.dir, outwardNormal, niOverNt);
+    }
+    P.dir = trace_dir;
+    P.flags &= ~(FL_CHANCE_REFLECT | FL_BACKFACE_ND);
+    if (chanceReflect) P.flags |= FL_CHANCE_REFLECT;
+    if (BackFace && mat.MaterialModel != GK_MATERIAL_DIELECTRIC) P.flags |= FL_BACKFACE_ND;
+    P.ro = P.pos + P.nrm * 0.001f * startPosOffset;  // HitNormalOffset, Core.PathTracing.comp.slang:18
+    P.rd = trace_dir;
+}
+
+// FHardwareRayTracerV2::TraceRay after the query (Shading.slang:801-823) + the rest of GetRayColor (:1040-1081).
+GK_DEV bool on_closest(const SceneView& S, PathRegs& P, const Hit& h) {
+    if (h.inst != GK_NO_HIT) {
+        const GkNodeProxy* node = S.nodes + h.inst;
+        const GkModelData* off = S.offsets + node->modelId;
+        const uint32_t io = off->indexOffset + h.prim * 3, vo = off->vertexOffset;
+        const VtxLite v0 = unpack_vertex(S, vo + __ldg(S.indices + io)), v1 = unpack_vertex(S, vo + __ldg(S.indices + io + 1)),
+                      v2 = unpack_vertex(S, vo + __ldg(S.indices + io + 2));
+        P.mat = fetch_material_id(node, v0.matSlot);
+        float3 n = v0.nrm + (v1.nrm - v0.nrm) * h.u + (v2.nrm - v0.nrm) * h.v;  // Mix(), PreProcessor.slang:24
+        const float* m = S.ts.inst[h.inst].w2o;  // mul(WorldToObject4x3, n) = transpose(w2o 3x3) * n
+        float3 nw = f3(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z);
+        P.nrm = normalize(nw);
+        float2 uv = v0.uv + (v1.uv - v0.uv) * h.u + (v2.uv - v0.uv) * h.v;
+        P.pos = P.ro + P.rd * h.t;
+        GkMaterial hitMat = get_material(S, P.mat);
+        float4 outAlbedo = f4(hitMat.Diffuse.x, hitMat.Diffuse.y, hitMat.Diffuse.z, hitMat.Diffuse.w);
+        if (hitMat.DiffuseTextureId >= 0) outAlbedo = outAlbedo * sample_texture(S, (uint32_t)hitMat.DiffuseTextureId, uv);
+        if (hitMat.MaterialModel == GK_MATERIAL_DIFFUSE_LIGHT || !(P.flags & FL_CHANCE_REFLECT)) P.rayColor = P.rayColor * outAlbedo;
+        if (P.flags & FL_BACKFACE_ND) {
+            P.rayColor = f4(0.5f, 0.5f, 0.5f, 0);
+            return true;
+        }
+        if (hitMat.MaterialModel == GK_MATERIAL_DIFFUSE_LIGHT) return true;
+        return false;
+    }
+    P.rayColor = P.rayColor * sky_color(S, P.rd);
+    return true;
+}
+
+GK_DEV void set_stage(PathRegs& P, uint32_t st) { P.flags = (P.flags & ~FL_STAGE_MASK) | (st << FL_STAGE_SHIFT); }
+
+// Shading.slang:1105-1117: start sample i
+GK_DEV void start_sample(const SceneView& S, PathRegs& P) {
+    P.rayColor = f4(1, 1, 1, 1);
+    float4 eye = mul(S.cam->ModelViewInverse, f4(0, 0, 0, 1));
+    P.dir = normalize(P.ppos - xyz(eye));
+    P.pos = P.ppos;
+    P.nrm = P.pnrm;
+    P.mat = P.pmat;
+    P.bounce = 0;
+    set_stage(P, ST_FIRST);
+    gen_closest(S, P, true);
+}
+
+struct PixelOut {
+    RTView rt;
+    float4 *radiance, *direct;
+    size_t pixels;
+};
+
+GK_DEV void write_result(const PixelOut& O, const FrameCfg& cfg, uint32_t pixel, const PathRegs& P, float4 direct) {
+    if (cfg.to_radiance) {
+        O.radiance[pixel] = P.finalColor;
+        O.radiance[O.pixels + pixel] = P.finalRefl;
+        if (cfg.rank == 0) O.direct[pixel] = direct;
+        return;
+    }
+    float4 fc = P.finalColor / float(P.sampleTotal);   // Shading.slang:1175-1176
+    float4 fr = P.finalRefl / float(P.sampleTotal);
+    fc = fc + direct;                                  // :1180
+    store_h4(O.rt.single_diffuse, pixel, fc);
+    store_h4(O.rt.single_specular, pixel, fr);
+}
+
+// Consumes the result of the pending ray and runs the pixel's program up to its next ray (or to completion).
+GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, uint32_t pixel, PathRegs& P, const Hit& h) {
+    const GkUniformBufferObject* C = S.cam;
+    const uint32_t stage = (P.flags & FL_STAGE_MASK) >> FL_STAGE_SHIFT;
+    const bool primDielectric = (P.flags & FL_PRIM_DIELECTRIC) != 0;
+    bool end_sample = false;
+    bool after_sun = false;
+    if (stage == ST_FIRST) {
+        bool exitFirst = on_closest(S, P, h);
+        if (!exitFirst) {
+            if (cfg.exit_after_first && !primDielectric) {
+                P.rayColor = P.rayColor * interpolateAmbientCubesV2(S, P.pos, P.nrm);  // :1120-1123
+                end_sample = true;
+            } else {
+                P.bounce = 1;
+                if (1u < P.maxBounces) {
+                    set_stage(P, ST_BOUNCE);
+                    gen_closest(S, P, false);
+                    return REQ_CLOSEST;
+                }
+                end_sample = true;
+            }
+        } else end_sample = true;
+    } else if (stage == ST_BOUNCE) {
+        if (on_closest(S, P, h)) end_sample = true;  // :1130-1133
+        else if (C->HasSun && (RandomFloat(P.rng) < 0.5f)) {  // :1135-1144
+            const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
+            const float3 cone = AlignWithNormal(RandomInCone(P.rng, GK_COS_QUARTER_DEGREE), lightVector);
+            P.ro = P.pos + P.nrm * 0.0f;  // TRACE_CORRECTION_OFFSET
+            P.rd = cone;
+            set_stage(P, ST_SUN);
+            return REQ_ANY;
+        } else after_sun = true;
+    } else if (stage == ST_SUN) {
+        if (h.inst == GK_NO_HIT) {
+            P.rayColor = P.rayColor * f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w);
+            end_sample = true;
+        } else after_sun = true;
+    } else {  // ST_DIRECT: FHardwareDirectIlluminatorV2::DirectIlluminate, :886-908
+        const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
+        const float d = fmaxf(dot(lightVector, normalize(P.pnrm)), 0.0f) * GK_M_1_PI;
+        const float shadow = (h.inst == GK_NO_HIT) ? 1.0f : 0.0f;
+        write_result(O, cfg, pixel, P, f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w) * d * shadow);
+        return REQ_DONE;
+    }
+    if (after_sun) {  // :1146-1154
+        const bool earlyExit = !primDielectric && (RandomFloat(P.rng) < 0.5f);  // ExitProbability
+        if (P.bounce == P.maxBounces - 1u || earlyExit) {
+            P.rayColor = P.rayColor * interpolateAmbientCubesV2(S, P.pos, P.nrm);
+            end_sample = true;
+        } else {
+            P.bounce++;
+            gen_closest(S, P, false);
+            set_stage(P, ST_BOUNCE);
+            return REQ_CLOSEST;
+        }
+    }
+    // end of sample, :1159-1171
+    (void)end_sample;
+    if (P.flags & FL_HIT_METAL) P.rayColor = P.rayColor * P.palbedo;
+    if (P.flags & FL_HIT_REFLECT) P.finalRefl = P.finalRefl + P.rayColor;
+    else P.finalColor = P.finalColor + P.rayColor;
+    P.sample++;
+    if (P.sample < P.sampleEnd) {
+        start_sample(S, P);
+        return REQ_CLOSEST;
+    }
+    // all samples done, :1175-1183
+    if (cfg.rank != 0) {
+        write_result(O, cfg, pixel, P, f4(0, 0, 0, 0));
+        return REQ_DONE;
+    }
+    if (C->HasSun) {
+        const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
+        const float3 cone = AlignWithNormal(RandomInCone(P.rng, GK_COS_QUARTER_DEGREE), lightVector);
+        P.ro = P.ppos;
+        P.rd = cone;
+        set_stage(P, ST_DIRECT);
+        return REQ_ANY;
+    }
+    {
+        const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
+        const float d = fmaxf(dot(lightVector, normalize(P.pnrm)), 0.0f) * GK_M_1_PI;
+        write_result(O, cfg, pixel, P, f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w) * d * 0.0f);
+    }
+    return REQ_DONE;
+}
+
+// ------------------------------------------------------------------------------------------------ state I/O
+GK_DEV void store_hot(const PathView& V, uint32_t pixel, const PathRegs& P) {
+    V.rng[pixel] = P.rng;
+    V.pos_mat[pixel] = f4(P.pos.x, P.pos.y, P.pos.z, __uint_as_float(P.mat));
+    V.nrm_flags[pixel] = f4(P.nrm.x, P.nrm.y, P.nrm.z, __uint_as_float(P.flags));
+    V.dir_cnt[pixel] = f4(P.dir.x, P.dir.y, P.dir.z, __uint_as_float(P.sample | (P.bounce << 16)));
+    V.ray_color[pixel] = P.rayColor;
+}
+GK_DEV void store_cold(const PathView& V, uint32_t pixel, const PathRegs& P) {
+    V.final_color[pixel] = P.finalColor;
+    V.final_refl[pixel] = P.finalRefl;
+}
+GK_DEV void store_primary(const PathView& V, uint32_t pixel, const PathRegs& P) {
+    V.prim_pos_mat[pixel] = f4(P.ppos.x, P.ppos.y, P.ppos.z, __uint_as_float(P.pmat));
+    V.prim_nrm_cnt[pixel] = f4(P.pnrm.x, P.pnrm.y, P.pnrm.z, __uint_as_float(P.sampleEnd | (P.sampleTotal << 16)));
+    V.prim_albedo[pixel] = P.palbedo;
+}
+GK_DEV void load_state(const PathView& V, const SceneView& S, uint32_t pixel, PathRegs& P) {
+    P.rng = V.rng[pixel];
+    float4 a = V.pos_mat[pixel], b = V.nrm_flags[pixel], c = V.dir_cnt[pixel];
+    P.pos = f3(a.x, a.y, a.z); P.mat = __float_as_uint(a.w);
+    P.nrm = f3(b.x, b.y, b.z); P.flags = __float_as_uint(b.w);
+    P.dir = f3(c.x, c.y, c.z);
+    uint32_t cnt = __float_as_uint(c.w);
+    P.sample = cnt & 0xFFFF; P.bounce = cnt >> 16;
+    P.rayColor = V.ray_color[pixel];
+    P.finalColor = V.final_color[pixel];
+    P.finalRefl = V.final_refl[pixel];
+    float4 pa = V.prim_pos_mat[pixel], pb = V.prim_nrm_cnt[pixel];
+    P.ppos = f3(pa.x, pa.y, pa.z); P.pmat = __float_as_uint(pa.w);
+    P.pnrm = f3(pb.x, pb.y, pb.z);
+    uint32_t sc = __float_as_uint(pb.w);
+    P.sampleEnd = sc & 0xFFFF; P.sampleTotal = sc >> 16;
+    P.palbedo = V.prim_albedo[pixel];
+    P.maxBounces = (P.flags & FL_PRIM_DIELECTRIC) ? S.cam->MaxNumberOfBounces : S.cam->NumberOfBounces;
+}
+
+// Appends (pixel, ray) to a queue; one atomic per warp (ballot + popc + shuffle).
+GK_DEV void enqueue(uint32_t* count, uint32_t* slot_pixel, float4* ray_o, float4* ray_d, bool want, uint32_t pixel, int req, const PathRegs& P) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) {
+        uint32_t slot = base + __popc(mask & ((1u << lane) - 1u));
+        slot_pixel[slot] = pixel | (req == REQ_ANY ? 0x80000000u : 0u);
+        ray_o[slot] = f4(P.ro.x, P.ro.y, P.ro.z, GK_EPS);
+        ray_d[slot] = f4(P.rd.x, P.rd.y, P.rd.z, GK_PT_MAX_TRACE_DISTANCE);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+// Primary visibility + G-buffer (FPathTracingRendererV2::Init/PrimaryHit, Shading.slang:1187-1241, with the visibility
+// buffer lookup of FVisibilityBufferRayCasterV2::TracePrimaryRay, :338-494, replaced by a closest-hit cast of the same
+// pixel-corner ray), the buffer clear (Util.BufferClear.comp.slang:5-14), and the first ray of sample 0.
+__global__ void __launch_bounds__(128) k_primary(SceneView S, RTView R, PathView V, FrameCfg cfg, unsigned long long* ray_counters) {
+    const int x = blockIdx.x * 8 + (threadIdx.x & 7), y = blockIdx.y * 16 + (threadIdx.x >> 3);
+    const bool inside = x < (int)R.w && y < (int)R.h;
+    const uint32_t pixel = inside ? (uint32_t)y * R.w + (uint32_t)x : 0u;
+    const GkUniformBufferObject* C = S.cam;
+    PathRegs P;
+    bool want = false;
+    uint32_t nprimary = 0;
+    if (inside) {
+        const bool owner = cfg.rank == 0 || !cfg.to_radiance;  // rank 0 owns the G-buffer in a multi-GPU frame
+        P.rng = make_uint4((uint32_t)x, (uint32_t)y, cfg.frame_seed, 0u);  // InitRandomSeed, Const_Func.slang:237-240
+        float4 origin4 = mul(C->ModelViewInverse, f4(0, 0, 0, 1));
+        float3 origin = xyz(origin4);
+        float3 ray_dir = pixel_ray_dir(C, x, y, R.w, R.h);
+        Hit h;
+        trace_ray<false>(S.ts, origin, ray_dir, GK_EPS, GK_PRIMARY_T_MAX, h);
+        nprimary++;
+        float4 zero = f4(0, 0, 0, 0);
+        if (h.inst == GK_NO_HIT) {  // Shading.slang:1193-1201
+            float4 sky = sky_color(S, ray_dir);
+            if (cfg.to_radiance) {
+                V.radiance[pixel] = zero;
+                V.radiance[(size_t)R.w * R.h + pixel] = zero;
+                if (cfg.rank == 0) V.direct[pixel] = sky;
+            } else {
+                store_h4(R.single_diffuse, pixel, sky);
+                store_h4(R.single_specular, pixel, zero);
+            }
+            if (owner) {
+                R.motion[pixel] = make_float2(0, 0);
+                store_h4(R.albedo, pixel, f4(1, 1, 1, 1));
+                store_h4(R.normal, pixel, f4(0, 1, 0, 1));
+                R.objectid0[pixel] = GK_OBJECTID_MISS;
+                R.primitiveid[pixel] = 0xFFFFFFFFu;
+                R.prev_depth[pixel] = 100000.0f;
+            }
+        } else {
+            PrimVertex iv = get_material_dataV2(S, h.inst, h.prim, origin, ray_dir);
+            uint32_t node_idx = h.inst, prim = h.prim;
+            float3 out_dir = ray_dir;
+            PrimVertex fv = iv;
+            // depth of field, Shading.slang:368-489
+            float vertexDistance = length(iv.pos - origin);
+            float cocRadius = 0.0f;
+            if (fabsf(vertexDistance - C->FocusDistance) > 0.001f) cocRadius = (C->Aperture * fabsf(vertexDistance - C->FocusDistance)) / vertexDistance;
+            if (cocRadius > 0.001f) {
+                float2 diskSample = RandomInUnitDisk(P.rng);
+                float3 right = normalize(cross(ray_dir, f3(0, 1, 0)));
+                float3 circleEdge = iv.pos + right * cocRadius;
+                float4 cp = mul(C->ViewProjection, f4(iv.pos.x, iv.pos.y, iv.pos.z, 1.0f));
+                float4 ep = mul(C->ViewProjection, f4(circleEdge.x, circleEdge.y, circleEdge.z, 1.0f));
+                float2 c2 = make_float2(cp.x / cp.w, cp.y / cp.w), e2 = make_float2(ep.x / ep.w, ep.y / ep.w);
+                float screenSpaceRadius = length(e2 - c2);
+                float2 pixelOffset = make_float2(diskSample.x * screenSpaceRadius * (float)R.w * 0.5f, diskSample.y * screenSpaceRadius * (float)R.h * 0.5f);
+                int ox = min(max(x + (int)pixelOffset.x, 0), (int)R.w - 1), oy = min(max(y + (int)pixelOffset.y, 0), (int)R.h - 1);
+                if (ox != x || oy != y) {
+                    float3 fdir = pixel_ray_dir(C, ox, oy, R.w, R.h);
+                    Hit h2;
+                    trace_ray<false>(S.ts, origin, fdir, GK_EPS, GK_PRIMARY_T_MAX, h2);
+                    nprimary++;
+                    if (h2.inst != GK_NO_HIT) {
+                        PrimVertex cand = get_material_dataV2(S, h2.inst, h2.prim, origin, fdir);
+                        bool cancel = false;
+                        if (fabsf(vertexDistance - C->FocusDistance) < C->FocusDistance * 0.1f) {
+                            float depthDifference = vertexDistance - length(cand.pos - origin);
+                            if (depthDifference > C->FocusDistance * 0.05f) cancel = true;
+                        }
+                        if (!cancel) { fv = cand; node_idx = h2.inst; prim = h2.prim; out_dir = fdir; }
+                    }
+                }
+            }
+            const GkNodeProxy* node = S.nodes + node_idx;
+            float3 hpos = fv.pos;
+            float3 hnrm = normalize(fv.nrm);
+            uint32_t hmat = fetch_material_id(node, fv.matSlot);
+            GkMaterial material = get_material(S, hmat);
+            // FetchGBufferV2, Shading.slang:82-112
+            float4 albedo = f4(material.Diffuse.x, material.Diffuse.y, material.Diffuse.z, material.Diffuse.w);
+            if (material.DiffuseTextureId >= 0) albedo = albedo * sample_texture(S, (uint32_t)material.DiffuseTextureId, fv.uv);
+            float roughness = material.Fuzziness;
+            if (material.MRATextureId >= 0) roughness = roughness * sample_texture(S, (uint32_t)material.MRATextureId, fv.uv).y;
+            uint16_t moment = R.moment[pixel];
+            {   // CalculateMotionVectorV2, Shading.slang:50-72
+                float4 Pw = f4(hpos.x, hpos.y, hpos.z, 1);
+                float4 cur = mul(C->ViewProjectionUnJit, Pw);
+                float2 currfpos = make_float2(cur.x / cur.w * 0.5f, cur.y / cur.w * 0.5f);
+                float4 prevPos = mul(node->combinedPrevTS, Pw);
+                // mul(mul(PrevVP, combinedPrevTS), P): the matrix product first, like the shader
+                GkMat4 pm;
+                for (int c = 0; c < 4; ++c)
+                    for (int r = 0; r < 4; ++r)
+                        pm.m[c][r] = C->PrevViewProjectionUnJit.m[0][r] * node->combinedPrevTS.m[c][0] + C->PrevViewProjectionUnJit.m[1][r] * node->combinedPrevTS.m[c][1] +
+                                     C->PrevViewProjectionUnJit.m[2][r] * node->combinedPrevTS.m[c][2] + C->PrevViewProjectionUnJit.m[3][r] * node->combinedPrevTS.m[c][3];
+                float4 prev = mul(pm, Pw);
+                float2 prevfpos = make_float2(prev.x / prev.w * 0.5f, prev.y / prev.w * 0.5f);
+                if (length(hpos - xyz(prevPos)) > 0.02f) moment = (uint16_t)C->TemporalFrames;
+                else moment = moment > 0 ? moment - 1 : 0;
+                float2 motion = prevfpos - currfpos;
+                if (owner) {
+                    R.moment[pixel] = moment;
+                    R.motion[pixel] = make_float2(motion.x * (float)R.w, motion.y * (float)R.h);
+                }
+            }
+            if (owner) {
+                float4 clip = mul(C->ViewProjection, f4(hpos.x, hpos.y, hpos.z, 1.0f));
+                store_h4(R.albedo, pixel, albedo);
+                store_h4(R.normal, pixel, f4(hnrm.x, hnrm.y, hnrm.z, roughness));
+                R.objectid0[pixel] = node->instanceId;
+                R.primitiveid[pixel] = prim;
+                R.prev_depth[pixel] = clip.z / clip.w;
+            }
+            if (material.MaterialModel != GK_MATERIAL_DIELECTRIC) hpos = hpos - out_dir * 0.03f;  // :1217-1220
+            if (material.MaterialModel == GK_MATERIAL_DIFFUSE_LIGHT) {  // :1093-1099
+                float4 e = f4(material.Diffuse.x, material.Diffuse.y, material.Diffuse.z, material.Diffuse.w);
+                if (cfg.to_radiance) {
+                    V.radiance[pixel] = zero;
+                    V.radiance[(size_t)R.w * R.h + pixel] = zero;
+                    if (cfg.rank == 0) V.direct[pixel] = e;
+                } else {
+                    store_h4(R.single_diffuse, pixel, e);
+                    store_h4(R.single_specular, pixel, zero);
+                }
+            } else {
+                int sampleMultiplier = moment > 0 ? 4 : 1;  // Core.PathTracing.comp.slang:28
+                int sample = max(1, (int)C->NumberOfSamples * sampleMultiplier);  // SampleDownscale = 1
+                uint32_t s0 = (uint32_t)((uint64_t)cfg.rank * sample / cfg.world), s1 = (uint32_t)((uint64_t)(cfg.rank + 1) * sample / cfg.world);
+                P.ppos = hpos; P.pnrm = hnrm; P.pmat = hmat; P.palbedo = albedo;
+                P.finalColor = zero; P.finalRefl = zero;
+                P.flags = material.MaterialModel == GK_MATERIAL_DIELECTRIC ? FL_PRIM_DIELECTRIC : 0u;
+                P.maxBounces = (P.flags & FL_PRIM_DIELECTRIC) ? C->MaxNumberOfBounces : C->NumberOfBounces;
+                P.sample = s0; P.sampleEnd = s1; P.sampleTotal = (uint32_t)sample;
+                if (s0 < s1) {
+                    start_sample(S, P);
+                    want = true;
+                } else {  // this rank has no samples for the pixel (spp < world)
+                    if (cfg.to_radiance) {
+                        V.radiance[pixel] = zero;
+                        V.radiance[(size_t)R.w * R.h + pixel] = zero;
+                        if (cfg.rank == 0) V.direct[pixel] = zero;
+                    }
+                }
+            }
+        }
+        if (want) {
+            store_hot(V, pixel, P);
+            store_cold(V, pixel, P);
+            store_primary(V, pixel, P);
+        }
+    }
+    enqueue(V.counts + 0, V.slot_pixel[0], V.ray_o, V.ray_d, want, pixel, REQ_CLOSEST, P);
+    // ray statistics: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) nprimary += __shfl_xor_sync(0xffffffffu, nprimary, o);
+    if ((threadIdx.x & 31) == 0 && nprimary) atomicAdd(ray_counters + 0, (unsigned long long)nprimary);
+}
+
+// Persistent-thread traversal: lanes pull rays from the queue whenever they run dry, so a warp keeps tracing while any
+// work is left. (Per-ray traversal itself is the stack loop of trace_ray.)
+__global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi, size_t half) {
+    const uint32_t n = V.counts[qi];
+    const int lane = threadIdx.x & 31;
+    const float4* ray_o = V.ray_o + (size_t)qi * half;
+    const float4* ray_d = V.ray_d + (size_t)qi * half;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(V.counts + 2, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) return;
+        uint32_t slot = base + lane;
+        if (slot < n) {
+            float4 o = ray_o[slot], d = ray_d[slot];
+            Hit h;
+            if (V.slot_pixel[qi][slot] & 0x80000000u) trace_ray<true>(ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h);
+            else trace_ray<false>(ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h);
+            V.hit_tuv[slot] = f4(h.t, h.u, h.v, __uint_as_float(h.inst));
+            V.hit_prim[slot] = h.prim;
+        }
+    }
+}
+
+// Shade: consume hits, advance every path to its next ray, compact the survivors into the other queue.
+__global__ void __launch_bounds__(128) k_shade(SceneView S, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
+    const uint32_t n = V.counts[qi];
+    PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
+    uint32_t nclosest = 0, nany = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (n + stride - 1) / stride;
+    for (uint32_t k = 0; k < rounds; ++k) {
+        uint32_t slot = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool want = false;
+        int req = REQ_DONE;
+        uint32_t pixel = 0;
+        PathRegs P;
+        if (slot < n) {
+            uint32_t sp = V.slot_pixel[qi][slot];
+            pixel = sp & 0x7FFFFFFFu;
+            if (sp & 0x80000000u) nany++; else nclosest++;
+            float4 hv = V.hit_tuv[slot];
+            Hit h;
+            h.t = hv.x; h.u = hv.y; h.v = hv.z; h.inst = __float_as_uint(hv.w); h.prim = V.hit_prim[slot];
+            load_state(V, S, pixel, P);
+            float4 o = V.ray_o[(size_t)qi * ((size_t)R.w * R.h) + slot], d = V.ray_d[(size_t)qi * ((size_t)R.w * R.h) + slot];
+            P.ro = f3(o.x, o.y, o.z);
+            P.rd = f3(d.x, d.y, d.z);
+            req = advance(S, O, cfg, pixel, P, h);
+            want = req != REQ_DONE;
+            if (want) {
+                store_hot(V, pixel, P);
+                store_cold(V, pixel, P);
+            }
+        }
+        // rays of the next wave go to the other half of the ray arrays
+        const unsigned mask = __ballot_sync(0xffffffffu, want);
+        if (mask) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(mask) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(V.counts + (qi ^ 1), (uint32_t)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                uint32_t ns = base + __popc(mask & ((1u << lane) - 1u));
+                const size_t half = (size_t)R.w * R.h;
+                V.slot_pixel[qi ^ 1][ns] = pixel | (req == REQ_ANY ? 0x80000000u : 0u);
+                V.ray_o[(size_t)(qi ^ 1) * half + ns] = f4(P.ro.x, P.ro.y, P.ro.z, GK_EPS);
+                V.ray_d[(size_t)(qi ^ 1) * half + ns] = f4(P.rd.x, P.rd.y, P.rd.z, GK_PT_MAX_TRACE_DISTANCE);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nclosest += __shfl_xor_sync(0xffffffffu, nclosest, o);
+        nany += __shfl_xor_sync(0xffffffffu, nany, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nclosest) atomicAdd(ray_counters + 1, (unsigned long long)nclosest);
+        if (nany) atomicAdd(ray_counters + 2, (unsigned long long)nany);
+    }
+}
+
+// Tail / megakernel: every thread runs its pixel's program to completion with the traversal inlined.
+__global__ void __launch_bounds__(128) k_tail(SceneView S, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
+    const uint32_t n = V.counts[qi];
+    PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
+    const size_t half = (size_t)R.w * R.h;
+    uint32_t nclosest = 0, nany = 0;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        uint32_t sp = V.slot_pixel[qi][slot];
+        uint32_t pixel = sp & 0x7FFFFFFFu;
+        PathRegs P;
+        load_state(V, S, pixel, P);
+        float4 o = V.ray_o[(size_t)qi * half + slot], d = V.ray_d[(size_t)qi * half + slot];
+        P.ro = f3(o.x, o.y, o.z);
+        P.rd = f3(d.x, d.y, d.z);
+        int req = (sp & 0x80000000u) ? REQ_ANY : REQ_CLOSEST;
+        while (req != REQ_DONE) {
+            Hit h;
+            if (req == REQ_ANY) { trace_ray<true>(S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h); nany++; }
+            else { trace_ray<false>(S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h); nclosest++; }
+            req = advance(S, O, cfg, pixel, P, h);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nclosest += __shfl_xor_sync(0xffffffffu, nclosest, o);
+        nany += __shfl_xor_sync(0xffffffffu, nany, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nclosest) atomicAdd(ray_counters + 1, (unsigned long long)nclosest);
+        if (nany) atomicAdd(ray_counters + 2, (unsigned long long)nany);
+    }
+}
+
+// Multi-GPU resolve: SINGLE_* = sums / S + direct (Shading.slang:1175-1183) after the NCCL reduce.
+__global__ void k_resolve(RTView R, const float4* __restrict__ radiance, const float4* __restrict__ direct, const uint16_t* __restrict__ moment,
+                          const GkUniformBufferObject* __restrict__ C) {
+    uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = R.w * R.h;
+    if (pixel >= n) return;
+    int sampleMultiplier = moment[pixel] > 0 ? 4 : 1;
+    int sample = max(1, (int)C->NumberOfSamples * sampleMultiplier);
+    float4 fc = radiance[pixel] / float(sample), fr = radiance[(size_t)n + pixel] / float(sample);
+    fc = fc + direct[pixel];
+    store_h4(R.single_diffuse, pixel, fc);
+    store_h4(R.single_specular, pixel, fr);
+}
+
+__global__ void k_trace_rays(TraceScene ts, const GkcuRay* __restrict__ rays, uint32_t n, GkcuHit* __restrict__ hits, int any_hit) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GkcuRay r = rays[i];
+    Hit h;
+    if (any_hit) trace_ray<true>(ts, f3(r.ox, r.oy, r.oz), f3(r.dx, r.dy, r.dz), r.tmin, r.tmax, h);
+    else trace_ray<false>(ts, f3(r.ox, r.oy, r.oz), f3(r.dx, r.dy, r.dz), r.tmin, r.tmax, h);
+    GkcuHit o;
+    o.t = any_hit ? 0.0f : h.t; o.u = h.u; o.v = h.v; o.inst = any_hit ? (h.inst != GK_NO_HIT ? 0u : GK_NO_HIT) : h.inst; o.prim = any_hit ? 0u : h.prim;
+    if (!any_hit && h.inst == GK_NO_HIT) { o.t = 0; o.u = 0; o.v = 0; o.prim = 0; }
+    hits[i] = o;
+}
+
+SceneView make_scene_view(const Context& c) {
+    SceneView S;
+    S.ts = make_trace_scene(c);
+    S.vertices = c.vertices.as<uint2>();
+    S.indices = c.indices.as<uint32_t>();
+    S.offsets = c.offsets.as<GkModelData>();
+    S.materials = c.materials.as<GkMaterial>();
+    S.material_count = c.material_count;
+    S.nodes = c.nodes.as<GkNodeProxy>();
+    S.textures = c.tex_table.as<TexDesc>();
+    S.tex_count = c.tex_count;
+    S.cubes = c.has_probes ? c.cubes.as<GkAmbientCube>() : nullptr;
+    S.voxels = c.has_probes ? c.voxels.as<GkVoxelData>() : nullptr;
+    S.cam = c.ubo.as<GkUniformBufferObject>();
+    return S;
+}
+RTView make_rt_view(const Context& c) {
+    RTView R;
+    const RenderTargets& t = c.rt;
+    R.w = t.w; R.h = t.h;
+    R.single_diffuse = t.single_diffuse; R.single_specular = t.single_specular; R.albedo = t.albedo; R.normal = t.normal;
+    R.objectid0 = t.objectid[t.cur]; R.primitiveid = t.primitiveid; R.motion = t.motion; R.prev_depth = t.prev_depth; R.moment = t.moment;
+    return R;
+}
+PathView make_path_view(const Context& c) {
+    PathBuffers& b = *c.path;
+    PathView V;
+    V.rng = b.rng.as<uint4>();
+    V.pos_mat = b.pos_mat.as<float4>(); V.nrm_flags = b.nrm_flags.as<float4>(); V.dir_cnt = b.dir_cnt.as<float4>();
+    V.ray_color = b.ray_color.as<float4>(); V.final_color = b.final_color.as<float4>(); V.final_refl = b.final_refl.as<float4>();
+    V.prim_pos_mat = b.prim_pos_mat.as<float4>(); V.prim_nrm_cnt = b.prim_nrm_cnt.as<float4>(); V.prim_albedo = b.prim_albedo.as<float4>();
+    V.ray_o = b.ray_o.as<float4>(); V.ray_d = b.ray_d.as<float4>();
+    V.slot_pixel[0] = b.slot_pixel[0].as<uint32_t>(); V.slot_pixel[1] = b.slot_pixel[1].as<uint32_t>();
+    V.hit_tuv = b.hit_tuv.as<float4>(); V.hit_prim = b.hit_prim.as<uint32_t>();
+    V.counts = b.counts.as<uint32_t>();
+    V.radiance = b.radiance.as<float4>(); V.direct = b.direct.as<float4>();
+    return V;
+}
+
+}  // namespace
+
+int path_resize(Context& c) {
+    if (!c.path) c.path = new PathBuffers();
+    PathBuffers& b = *c.path;
+    size_t n = (size_t)c.rt.w * c.rt.h;
+    b.pixels = n;
+    bool ok = b.rng.reserve(n * 16) && b.pos_mat.reserve(n * 16) && b.nrm_flags.reserve(n * 16) && b.dir_cnt.reserve(n * 16) &&
+              b.ray_color.reserve(n * 16) && b.final_color.reserve(n * 16) && b.final_refl.reserve(n * 16) && b.prim_pos_mat.reserve(n * 16) &&
+              b.prim_nrm_cnt.reserve(n * 16) && b.prim_albedo.reserve(n * 16) && b.ray_o.reserve(2 * n * 16) && b.ray_d.reserve(2 * n * 16) &&
+              b.slot_pixel[0].reserve(n * 4) && b.slot_pixel[1].reserve(n * 4) && b.hit_tuv.reserve(n * 16) && b.hit_prim.reserve(n * 4) &&
+              b.counts.reserve(64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16);
+    if (!ok) return 1;
+    if (!b.host_counts) GK_CUDA(cudaMallocHost(&b.host_counts, 64 * 4));
+    return 0;
+}
+
+void path_release(Context& c) {
+    if (!c.path) return;
+    PathBuffers& b = *c.path;
+    for (DevBuf* d : {&b.rng, &b.pos_mat, &b.nrm_flags, &b.dir_cnt, &b.ray_color, &b.final_color, &b.final_refl, &b.prim_pos_mat, &b.prim_nrm_cnt,
+                      &b.prim_albedo, &b.ray_o, &b.ray_d, &b.slot_pixel[0], &b.slot_pixel[1], &b.hit_tuv, &b.hit_prim, &b.counts, &b.radiance, &b.direct})
+        d->release();
+    if (b.host_counts) cudaFreeHost(b.host_counts);
+    delete c.path;
+    c.path = nullptr;
+}
+
+int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {
+    cudaStream_t st = c.stream;
+    PathBuffers& b = *c.path;
+    SceneView S = make_scene_view(c);
+    RTView R = make_rt_view(c);
+    PathView V = make_path_view(c);
+    FrameCfg cfg;
+    cfg.world = std::max(1u, p.spp_world);
+    cfg.rank = std::min(p.spp_rank, cfg.world - 1);
+    cfg.frame_seed = cfg.world == 1 ? ubo.TotalFrames : ubo.TotalFrames * cfg.world + cfg.rank;
+    cfg.to_radiance = p.skip_post ? 1u : 0u;
+    cfg.exit_after_first = ubo.FastGather ? 1u : 0u;
+    uint32_t* counts = V.counts;
+    unsigned long long* ray_counters = reinterpret_cast<unsigned long long*>(counts + 4);
+    GK_CUDA(cudaMemsetAsync(counts, 0, 64 * 4, st));
+    dim3 grid((R.w + 7) / 8, (R.h + 15) / 16);
+    k_primary<<<grid, 128, 0, st>>>(S, R, V, cfg, ray_counters);
+    c.launches++;
+    const uint32_t pixels = R.w * R.h;
+    const size_t half = pixels;
+    const uint32_t persistent_blocks = (uint32_t)c.sm_count * 8u;
+    uint64_t iterations = 0;
+    int qi = 0;
+    if (p.tracer == 0) {
+        // wavefront loop while the wave is wide; k_tail finishes the thin tail in one launch
+        const uint32_t tail_threshold = std::max<uint32_t>(pixels / 64, (uint32_t)c.sm_count * 128u);
+        for (;;) {
+            GK_CUDA(cudaMemcpyAsync(b.host_counts, counts + qi, 4, cudaMemcpyDeviceToHost, st));
+            GK_CUDA(cudaStreamSynchronize(st));
+            const uint32_t n = b.host_counts[0];
+            if (n <= tail_threshold) break;
+            GK_CUDA(cudaMemsetAsync(counts + 2, 0, 4, st));
+            GK_CUDA(cudaMemsetAsync(counts + (qi ^ 1), 0, 4, st));
+            const uint32_t blocks = std::min<uint32_t>((n + 127) / 128, persistent_blocks);
+            k_trace<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
+            k_shade<<<blocks, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+            c.launches += 2;
+            qi ^= 1;
+            ++iterations;
+        }
+    }
+    {
+        const uint32_t blocks = std::min<uint32_t>((pixels + 127) / 128, (uint32_t)c.sm_count * 16u);
+        k_tail<<<blocks, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+        c.launches++;
+    }
+    GK_CUDA(cudaMemcpyAsync(b.host_counts + 8, ray_counters, 24, cudaMemcpyDeviceToHost, st));
+    c.counters.wavefront_iterations = iterations;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// valid after the stream has been synchronised
+void fetch_ray_counters(Context& c) {
+    if (!c.path || !c.path->host_counts) return;
+    const unsigned long long* h = reinterpret_cast<const unsigned long long*>(c.path->host_counts + 8);
+    c.counters.primary_rays = h[0];
+    c.counters.closest_hit_rays = h[1];
+    c.counters.any_hit_rays = h[2];
+}
+
+int run_resolve(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {
+    (void)ubo;
+    (void)p;
+    RTView R = make_rt_view(c);
+    PathView V = make_path_view(c);
+    uint32_t n = R.w * R.h;
+    k_resolve<<<(n + 255) / 256, 256, 0, c.stream>>>(R, V.radiance, V.direct, R.moment, c.ubo.as<GkUniformBufferObject>());
+    c.launches++;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int radiance_buffer(Context& c, void** ptr, size_t* bytes) {
+    if (!c.path) { set_error("gkcu_radiance_buffer: call gkcu_resize first"); return 1; }
+    *ptr = c.path->radiance.p;
+    *bytes = 2 * c.path->pixels * 16;
+    return 0;
+}
+
+int run_trace_rays(Context& c, uint32_t count, bool any_hit) {
+    k_trace_rays<<<(count + 127) / 128, 128, 0, c.stream>>>(make_trace_scene(c), c.trace_rays.as<GkcuRay>(), count, c.trace_hits.as<GkcuHit>(), any_hit ? 1 : 0);
+    c.launches++;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gkcu

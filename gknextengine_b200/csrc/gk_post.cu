@@ -1,0 +1,302 @@
+// gk_post.cu — the two stencil passes after the rt pass, as shared-memory-tiled kernels.
+//   k_reproject  = assets/shaders/Process.ReProject.comp.slang:71-223   ("reproject pass", PathTracingRenderer.cpp:126-136)
+//   k_denoise    = assets/shaders/Process.DenoiseJBF.comp.slang:75-182  ("compose pass",   PathTracingRenderer.cpp:138-157)
+// Storage images are fp16x4 / R32_UINT / RG32F exactly as in the reference (VulkanBaseRenderer.cpp:439-457); out-of-bounds
+// loads return 0 and out-of-bounds stores are dropped, like Vulkan robust image access.
+// The "copy pass" (ACCUM -> PREV x3, PathTracingRenderer.cpp:160-182) and the object-id copy (VulkanBaseRenderer.cpp:1136-1152)
+// are pointer swaps done by the caller; ReProject therefore writes ACCUM.a = PREV.a where the reference leaves alpha untouched.
+#include "gk_context.h"
+
+using namespace gkd;
+
+namespace gkcu {
+
+namespace {
+
+constexpr int RBX = 32, RBY = 8;            // reproject block
+constexpr int RH = 2;                       // 5x5 spatial filter halo
+constexpr int RTW = RBX + 2 * RH, RTH = RBY + 2 * RH;
+constexpr int RMH = 4;                      // motion-vector taps at 2 * offset
+constexpr int RMW = RBX + 2 * RMH, RMHH = RBY + 2 * RMH;
+
+struct ReprojArgs {
+    int w, h;
+    const uint2 *single_diffuse, *single_specular, *albedo, *normal;
+    const uint2 *prev_diffuse, *prev_specular, *prev_albedo;
+    uint2 *accum_diffuse, *accum_specular, *accum_albedo;
+    const uint32_t *objectid0, *objectid1;
+    const float2* motion;
+    const uint16_t* moment;
+    uint32_t progressive, fast_reproject;
+    int temporal_frames;
+};
+
+GK_DEV bool inb(int x, int y, int w, int h) { return x >= 0 && y >= 0 && x < w && y < h; }
+GK_DEV float4 ld4(const uint2* img, int x, int y, int w, int h) { return inb(x, y, w, h) ? load_h4(img, (size_t)y * w + x) : f4(0, 0, 0, 0); }
+GK_DEV uint32_t ldu(const uint32_t* img, int x, int y, int w, int h) { return inb(x, y, w, h) ? img[(size_t)y * w + x] : 0u; }
+
+GK_DEV float calculateWeight(float centerDist, bool sameObject, bool isCenter, float3 Normal, float3 CenterNormal) {  // :32-47
+    if (isCenter) return 0.4f;
+    if (!sameObject) return 0.0f;
+    float normalDot = clampf(dot(Normal, CenterNormal), 0.0f, 1.0f);
+    const float normalThreshold = 0.98f;
+    if (normalDot < normalThreshold) return 0.0f;
+    const float normalWeight = (normalDot - normalThreshold) / (1.0f - normalThreshold);
+    return normalWeight * 2.0f / (centerDist * 1.5f + 4.0f);
+}
+
+GK_DEV float3 FilterHistoryColor(const uint2* prev, int w, int h, float2 subpixel, int px, int py, uint32_t cur, uint32_t p0, uint32_t p1, uint32_t p2,
+                                 uint32_t p3, float4 currFrameSample) {  // :49-68
+    float3 c = xyz(currFrameSample);
+    float3 h0 = cur == p0 ? xyz(ld4(prev, px, py, w, h)) : c;
+    float3 h1 = cur == p1 ? xyz(ld4(prev, px + 1, py, w, h)) : c;
+    float3 h2 = cur == p2 ? xyz(ld4(prev, px, py + 1, w, h)) : c;
+    float3 h3 = cur == p3 ? xyz(ld4(prev, px + 1, py + 1, w, h)) : c;
+    float3 history = lerp3(lerp3(h0, h1, subpixel.x), lerp3(h2, h3, subpixel.x), subpixel.y);
+    return f3(clampf(history.x, 0.0f, 1600.0f), clampf(history.y, 0.0f, 1600.0f), clampf(history.z, 0.0f, 1600.0f));
+}
+
+__global__ void __launch_bounds__(RBX* RBY) k_reproject(ReprojArgs A) {
+    __shared__ uint2 s_diff[RTH][RTW];
+    __shared__ uint2 s_spec[RTH][RTW];
+    __shared__ uint2 s_norm[RTH][RTW];
+    __shared__ uint32_t s_id[RTH][RTW];
+    __shared__ float s_mlen[RMHH][RMW];
+    const int w = A.w, h = A.h;
+    const int bx0 = blockIdx.x * RBX, by0 = blockIdx.y * RBY;
+    const int tid = threadIdx.y * RBX + threadIdx.x;
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    const float k512 = clampf(1.0f / 512.0f, 0.0f, 1.0f);
+    if (A.progressive) {  // :95-101
+        if (x < w && y < h) {
+            size_t i = (size_t)y * w + x;
+            store_h4(A.accum_diffuse, i, lerp4(load_h4(A.prev_diffuse, i), load_h4(A.single_diffuse, i), k512));
+            store_h4(A.accum_specular, i, lerp4(load_h4(A.prev_specular, i), load_h4(A.single_specular, i), k512));
+            store_h4(A.accum_albedo, i, lerp4(load_h4(A.prev_albedo, i), load_h4(A.albedo, i), k512));
+        }
+        return;
+    }
+    // stage the tile + halo (raw fp16 bits; zero outside the image)
+    for (int i = tid; i < RTW * RTH; i += RBX * RBY) {
+        int ty = i / RTW, tx = i % RTW;
+        int gx = bx0 + tx - RH, gy = by0 + ty - RH;
+        bool in = inb(gx, gy, w, h);
+        size_t g = (size_t)gy * w + gx;
+        s_diff[ty][tx] = in ? A.single_diffuse[g] : make_uint2(0, 0);
+        s_spec[ty][tx] = in ? A.single_specular[g] : make_uint2(0, 0);
+        s_norm[ty][tx] = in ? A.normal[g] : make_uint2(0, 0);
+        s_id[ty][tx] = in ? A.objectid0[g] : 0u;
+    }
+    for (int i = tid; i < RMW * RMHH; i += RBX * RBY) {
+        int ty = i / RMW, tx = i % RMW;
+        int gx = bx0 + tx - RMH, gy = by0 + ty - RMH;
+        float2 m = inb(gx, gy, w, h) ? A.motion[(size_t)gy * w + gx] : make_float2(0, 0);
+        s_mlen[ty][tx] = length(m);
+    }
+    __syncthreads();
+    if (x >= w || y >= h) return;
+    const size_t idx = (size_t)y * w + x;
+    const int lx = threadIdx.x + RH, ly = threadIdx.y + RH;
+    auto h4 = [](uint2 v) {
+        __half2 a = *reinterpret_cast<__half2*>(&v.x), b = *reinterpret_cast<__half2*>(&v.y);
+        float2 fa = __half22float2(a), fb = __half22float2(b);
+        return f4(fa.x, fa.y, fb.x, fb.y);
+    };
+    float4 currDiffuseSample = h4(s_diff[ly][lx]), currSpecularSample = h4(s_spec[ly][lx]), currAlbedoSample = load_h4(A.albedo, idx);
+    bool useHistory = true;
+    float2 motion = A.motion[idx];
+    int pvx = (int)floorf((float)x + motion.x), pvy = (int)floorf((float)y + motion.y);
+    // all(previpos < isize) mixes int and uint: negative coordinates fail the test (C conversion rules)
+    const bool inside = ((uint32_t)pvx < (uint32_t)w) && ((uint32_t)pvy < (uint32_t)h) && pvx >= -1 && pvy >= -1;
+    uint32_t cur = s_id[ly][lx];
+    uint32_t prev0 = ldu(A.objectid1, pvx, pvy, w, h);
+    const bool miss = cur == 65535u;
+    uint32_t moment = A.moment[idx];
+    if (miss || !inside || moment > 0) useHistory = false;
+    if (useHistory) {
+        const int SAMPLE_RANGE = A.fast_reproject ? 0 : 2;
+        const float3 CenterNormal = xyz(h4(s_norm[ly][lx]));
+        float4 spatialDiffuseSample = f4(0, 0, 0, 0), spatialSpecularSample = f4(0, 0, 0, 0);
+        float totalWeight = 0.0f, motionInRange = 0;
+        for (int yy = -SAMPLE_RANGE; yy <= SAMPLE_RANGE; yy++) {
+            for (int xx = -SAMPLE_RANGE; xx <= SAMPLE_RANGE; xx++) {
+                const uint32_t primitiveIdx = s_id[ly + yy][lx + xx];
+                const float3 worldNormal = xyz(h4(s_norm[ly + yy][lx + xx]));
+                const bool isCenter = (xx == 0 && yy == 0);
+                const bool sameObject = (primitiveIdx == cur);
+                const float centerDist = length(make_float2((float)xx, (float)yy));
+                const float weight = calculateWeight(centerDist, sameObject, isCenter, worldNormal, CenterNormal);
+                spatialDiffuseSample = spatialDiffuseSample + h4(s_diff[ly + yy][lx + xx]) * weight;
+                spatialSpecularSample = spatialSpecularSample + h4(s_spec[ly + yy][lx + xx]) * weight;
+                totalWeight += weight;
+                motionInRange += s_mlen[threadIdx.y + RMH + yy * 2][threadIdx.x + RMH + xx * 2];
+            }
+        }
+        spatialDiffuseSample = spatialDiffuseSample / totalWeight;
+        spatialSpecularSample = spatialSpecularSample / totalWeight;
+        uint32_t prev1 = ldu(A.objectid1, pvx + 1, pvy, w, h), prev2 = ldu(A.objectid1, pvx, pvy + 1, w, h), prev3 = ldu(A.objectid1, pvx + 1, pvy + 1, w, h);
+        if (fabsf(motionInRange) < 0.1f) prev0 = prev1 = prev2 = prev3 = cur;
+        float2 pos = make_float2((float)x + motion.x, (float)y + motion.y);
+        float2 subpixel = make_float2(pos.x - floorf(pos.x), pos.y - floorf(pos.y));
+        float3 historyDiffuse = FilterHistoryColor(A.prev_diffuse, w, h, subpixel, pvx, pvy, cur, prev0, prev1, prev2, prev3, spatialDiffuseSample);
+        float3 historySpecular = FilterHistoryColor(A.prev_specular, w, h, subpixel, pvx, pvy, cur, prev0, prev1, prev2, prev3, spatialSpecularSample);
+        float3 historyAlbedo = FilterHistoryColor(A.prev_albedo, w, h, subpixel, pvx, pvy, cur, prev0, prev1, prev2, prev3, currAlbedoSample);
+        float currKeep = clampf(1.0f / (float)max(1, A.temporal_frames), 0.0f, 1.0f);
+        float3 d = lerp3(historyDiffuse, xyz(currDiffuseSample), currKeep);
+        float3 s = lerp3(historySpecular, xyz(currSpecularSample), currKeep);
+        float3 a = lerp3(historyAlbedo, xyz(currAlbedoSample), currKeep);
+        // ".rgb =" stores keep the texel's alpha, which after the copy pass equals PREV's alpha
+        store_h4(A.accum_diffuse, idx, f4(d.x, d.y, d.z, load_h4(A.prev_diffuse, idx).w));
+        store_h4(A.accum_specular, idx, f4(s.x, s.y, s.z, load_h4(A.prev_specular, idx).w));
+        store_h4(A.accum_albedo, idx, f4(a.x, a.y, a.z, load_h4(A.prev_albedo, idx).w));
+    } else {
+        store_h4(A.accum_diffuse, idx, currDiffuseSample);
+        store_h4(A.accum_specular, idx, currSpecularSample);
+        store_h4(A.accum_albedo, idx, currAlbedoSample);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ DenoiseJBF
+constexpr int DBX = 32, DBY = 8, DR = 5;
+constexpr int DTW = DBX + 2 * DR, DTH = DBY + 2 * DR;
+
+struct DenoiseArgs {
+    int w, h;
+    const uint2 *accum_diffuse, *accum_specular, *accum_albedo;
+    uint2* denoised;
+    const GkUniformBufferObject* cam;
+};
+
+// Const_Func.slang:51-68, 82-126
+GK_DEV float W_f(float x, float e0, float e1) {
+    if (x <= e0) return 0;
+    if (x >= e1) return 1;
+    float a = (x - e0) / (e1 - e0);
+    return a * a * (3 - 2 * a);
+}
+GK_DEV float H_f(float x, float e0, float e1) {
+    if (x <= e0) return 0;
+    if (x >= e1) return 1;
+    return (x - e0) / (e1 - e0);
+}
+GK_DEV float GranTurismoTonemapper(float x) {
+    const float e = 2.71828f;
+    float P = 1, a = 0.7f, m = 0.22f, l = 0.4f, c = 1.33f, b = 0;
+    float l0 = (P - m) * l / a;
+    float L_x = m + a * (x - m);
+    float T_x = m * powf(x / m, c) + b;
+    float S0 = m + l0;
+    float S1 = m + a * l0;
+    float C2 = a * P / (P - S1);
+    float S_x = P - (P - S1) * powf(e, -(C2 * (x - S0) / P));
+    float w0_x = 1 - W_f(x, 0, m);
+    float w2_x = H_f(x, m + l0, m + l0);
+    float w1_x = 1 - w0_x - w2_x;
+    return T_x * w0_x + L_x * w1_x + S_x * w2_x;
+}
+GK_DEV float3 GT_Tonemapping(float3 x) { return f3(GranTurismoTonemapper(x.x), GranTurismoTonemapper(x.y), GranTurismoTonemapper(x.z)); }
+GK_DEV float ST2084(float lin) {
+    const float m1 = 0.1593017578125f, m2 = 78.84375f, c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f, C = 10000.f;
+    float L = lin / C;
+    float Lm = powf(L, m1);
+    float N1 = (c1 + c2 * Lm), N2 = (1.0f + c3 * Lm);
+    float N = N1 * (1.0f / N2);
+    return powf(N, m2);
+}
+
+__global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
+    __shared__ float4 s_diff[DTH][DTW];  // rgb + 0.001 bias, luminance in w
+    const GkUniformBufferObject* C = A.cam;
+    const int w = A.w, h = A.h;
+    const int gx0 = (int)C->ViewportRect.x, gy0 = (int)C->ViewportRect.y;
+    const int bx0 = blockIdx.x * DBX + gx0, by0 = blockIdx.y * DBY + gy0;
+    const int tid = threadIdx.y * DBX + threadIdx.x;
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    const bool filter = C->BFSize > 0;
+    if (filter) {
+        for (int i = tid; i < DTW * DTH; i += DBX * DBY) {
+            int ty = i / DTW, tx = i % DTW;
+            float4 v = ld4(A.accum_diffuse, bx0 + tx - DR, by0 + ty - DR, w, h);
+            float3 c = xyz(v) + f3(0.001f, 0.001f, 0.001f);  // FetchDiffuse, :14-17
+            s_diff[ty][tx] = f4(c.x, c.y, c.z, dot(c, f3(0.212671f, 0.715160f, 0.072169f)));
+        }
+        __syncthreads();
+    }
+    if (!inb(x, y, w, h)) return;
+    const size_t idx = (size_t)y * w + x;
+    float3 Total = f3(0, 0, 0);
+    if (filter) {
+        const int ly = threadIdx.y + DR, lx = threadIdx.x + DR;
+        const float CenterLum = s_diff[ly][lx].w;
+        const float3 CenterSpec = xyz(load_h4(A.accum_specular, idx)) + f3(0.001f, 0.001f, 0.001f);
+        const float sigma = C->BFSigma, sigmaL = C->BFSigmaLum * 100.0f;
+        float Weight = 0;
+        // tap (i, j) = tile[row + i][col + j]; the centre pixel is not a tap (:133-141)
+        for (int i = -DR; i <= DR; i += 2) {
+            for (int j = -DR; j <= DR; j += 2) {
+                const float4 t = s_diff[ly + i][lx + j];
+                const float3 Ci = xyz(t);
+                const float lumi = t.w;
+                const float dist = clampf(float(i * i + j * j) / float(DR * DR), 0.0f, 1.0f);
+                const float dlum = (CenterLum - lumi) * (CenterLum - lumi);
+                const float Fi = expf(-dist * dist / (2.0f * sigma * sigma));
+                const float Li = expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
+                Total = Total + Ci * Fi * Li;
+                Weight += Fi * Li;
+            }
+        }
+        Total = f3(Total.x / Weight, Total.y / Weight, Total.z / Weight);
+        if (!C->DebugDraw_Lighting) Total = Total * xyz(load_h4(A.accum_albedo, idx)) + CenterSpec;
+    } else {
+        float3 d = xyz(load_h4(A.accum_diffuse, idx)), s = xyz(load_h4(A.accum_specular, idx));
+        if (C->DebugDraw_Lighting) Total = d * f3(0.5f, 0.5f, 0.5f) + s;
+        else Total = d * xyz(load_h4(A.accum_albedo, idx)) + s;
+    }
+    if (C->HDR) {
+        Total = f3(Total.x / 2000.0f, Total.y / 2000.0f, Total.z / 2000.0f);
+        Total = GT_Tonemapping(Total);
+        Total = Total * 2000.0f;
+        float3 pw = Total * C->PaperWhiteNit;
+        store_h4(A.denoised, idx, f4(ST2084(pw.x / 230.0f), ST2084(pw.y / 230.0f), ST2084(pw.z / 230.0f), 1.0f));
+    } else {
+        float3 pw = Total * C->PaperWhiteNit;
+        float3 t = GT_Tonemapping(f3(pw.x / 40000.0f, pw.y / 40000.0f, pw.z / 40000.0f));
+        store_h4(A.denoised, idx, f4(t.x, t.y, t.z, 1.0f));
+    }
+}
+
+}  // namespace
+
+int run_reproject(Context& c, const GkcuFrameParams& p) {
+    RenderTargets& t = c.rt;
+    ReprojArgs A;
+    A.w = (int)t.w; A.h = (int)t.h;
+    A.single_diffuse = t.single_diffuse; A.single_specular = t.single_specular; A.albedo = t.albedo; A.normal = t.normal;
+    A.prev_diffuse = t.accum_diffuse[t.cur ^ 1]; A.prev_specular = t.accum_specular[t.cur ^ 1]; A.prev_albedo = t.accum_albedo[t.cur ^ 1];
+    A.accum_diffuse = t.accum_diffuse[t.cur]; A.accum_specular = t.accum_specular[t.cur]; A.accum_albedo = t.accum_albedo[t.cur];
+    A.objectid0 = t.objectid[t.cur]; A.objectid1 = t.objectid[t.cur ^ 1];
+    A.motion = t.motion; A.moment = t.moment;
+    A.progressive = p.progressive; A.fast_reproject = p.fast_reproject; A.temporal_frames = p.temporal_frames;
+    dim3 grid((t.w + RBX - 1) / RBX, (t.h + RBY - 1) / RBY), block(RBX, RBY);
+    k_reproject<<<grid, block, 0, c.stream>>>(A);
+    c.launches++;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int run_denoise(Context& c, const GkUniformBufferObject& ubo) {
+    (void)ubo;
+    RenderTargets& t = c.rt;
+    DenoiseArgs A;
+    A.w = (int)t.w; A.h = (int)t.h;
+    A.accum_diffuse = t.accum_diffuse[t.cur]; A.accum_specular = t.accum_specular[t.cur]; A.accum_albedo = t.accum_albedo[t.cur];
+    A.denoised = t.denoised;
+    A.cam = c.ubo.as<GkUniformBufferObject>();
+    dim3 grid((t.w + DBX - 1) / DBX, (t.h + DBY - 1) / DBY), block(DBX, DBY);
+    k_denoise<<<grid, block, 0, c.stream>>>(A);
+    c.launches++;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gkcu

@@ -1,0 +1,122 @@
+"""Python view of the C++ host-side scene code (gknextengine_b200/host/, libgknext_host.so).
+
+Mirrors what the reference's Assets::Scene / NextEngine hand to a renderer each frame
+(src/Assets/Scene.cpp:102-289, 443-492; src/Runtime/Engine.cpp:736-849).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._abi import GkcuSceneDesc, GkMaterial, GkNodeProxy, GkUniformBufferObject
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "libgknext_host.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(path)
+        L.gkhost_scene_create.restype = C.c_void_p
+        L.gkhost_scene_create.argtypes = [C.c_char_p]
+        L.gkhost_scene_destroy.argtypes = [C.c_void_p]
+        L.gkhost_scene_desc.argtypes = [C.c_void_p, C.POINTER(GkcuSceneDesc)]
+        L.gkhost_scene_nodes.restype = C.POINTER(GkNodeProxy)
+        L.gkhost_scene_nodes.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.gkhost_scene_materials.restype = C.POINTER(GkMaterial)
+        L.gkhost_scene_materials.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.gkhost_scene_update_nodes.argtypes = [C.c_void_p]
+        L.gkhost_scene_settings.argtypes = [C.c_void_p] + [C.c_int] * 8
+        L.gkhost_scene_env.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.gkhost_scene_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+        L.gkhost_scene_ubo.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.POINTER(GkUniformBufferObject)]
+        L.gkhost_scene_reset_history.argtypes = [C.c_void_p]
+        L.gkhost_scene_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.gkhost_scene_jitter_instances.argtypes = [C.c_void_p, C.c_uint32, C.c_float]
+        L.gkhost_scene_perturb_model.restype = C.c_uint32
+        L.gkhost_scene_perturb_model.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.gkhost_make_sky.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+        L.gkhost_to_float16.restype = C.c_uint16
+        L.gkhost_to_float16.argtypes = [C.c_float]
+        L.gkhost_mat4_inverse.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class Scene:
+    """SceneList::LoadScene + Scene::RebuildMeshBuffer: 'CornellBox.proc', 'RTIO.proc', 'LegoBricks.synth[:N]'."""
+
+    def __init__(self, name, samples=8, bounces=5, max_bounces=10, taa=True, temporal_frames=16, denoiser=False, hdr=False,
+                 fast_gather=False):
+        self._h = lib().gkhost_scene_create(name.encode())
+        if not self._h:
+            raise ValueError(f"unknown scene {name!r}")
+        self.name = name
+        self.settings(samples, bounces, max_bounces, taa, temporal_frames, denoiser, hdr, fast_gather)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().gkhost_scene_destroy(self._h)
+            self._h = None
+
+    def settings(self, samples, bounces, max_bounces=10, taa=True, temporal_frames=16, denoiser=False, hdr=False, fast_gather=False):
+        self.temporal_frames = temporal_frames
+        lib().gkhost_scene_settings(self._h, samples, bounces, max_bounces, int(taa), temporal_frames, int(denoiser), int(hdr), int(fast_gather))
+
+    def env(self, has_sky, has_sun, sky_intensity=100.0, sun_intensity=500.0, sun_rotation=0.5, sky_rotation=0.0):
+        lib().gkhost_scene_env(self._h, int(has_sky), int(has_sun), sky_intensity, sun_intensity, sun_rotation, sky_rotation)
+
+    def camera(self, aperture=0.0, focal_distance=10.0, fov=0.0):
+        lib().gkhost_scene_camera(self._h, aperture, focal_distance, fov)
+
+    def desc(self):
+        d = GkcuSceneDesc()
+        lib().gkhost_scene_desc(self._h, C.byref(d))
+        return d
+
+    def nodes(self):
+        n = C.c_uint32()
+        p = lib().gkhost_scene_nodes(self._h, C.byref(n))
+        return p, n.value
+
+    def materials(self):
+        n = C.c_uint32()
+        p = lib().gkhost_scene_materials(self._h, C.byref(n))
+        return p, n.value
+
+    def update_nodes(self):
+        """Scene::UpdateNodes: recompute NodeProxy[] (velocity tick included)."""
+        return bool(lib().gkhost_scene_update_nodes(self._h))
+
+    def ubo(self, width, height, total_frames, progressive=False, model_rotation_deg=0.0):
+        u = GkUniformBufferObject()
+        lib().gkhost_scene_ubo(self._h, width, height, total_frames, int(progressive), model_rotation_deg, C.byref(u))
+        return u
+
+    def reset_history(self):
+        lib().gkhost_scene_reset_history(self._h)
+
+    def counts(self):
+        a, b, c, t = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        lib().gkhost_scene_counts(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(t))
+        return dict(nodes=a.value, models=b.value, materials=c.value, instanced_triangles=t.value)
+
+    def jitter_instances(self, step, fraction):
+        lib().gkhost_scene_jitter_instances(self._h, step, fraction)
+
+    def perturb_model(self, model, step):
+        n = lib().gkhost_scene_perturb_model(self._h, model, step, None)
+        out = np.zeros(n * 4, dtype=np.uint16)
+        lib().gkhost_scene_perturb_model(self._h, model, step, out.ctypes.data)
+        return out
+
+
+def make_sky(width=1024, height=512):
+    """Procedural stand-in for assets/textures/river_road_2.hdr (sky id 0, Engine.cpp:855): RGBA32F equirect."""
+    out = np.zeros((height, width, 4), dtype=np.float32)
+    lib().gkhost_make_sky(width, height, out.ctypes.data)
+    return out

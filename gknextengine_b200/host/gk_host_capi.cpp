@@ -1,0 +1,107 @@
+// C ABI over the C++ host-side scene code (gk_scene.hpp) so the Python tests / bench can obtain exactly the arrays the
+// reference's Scene hands to its renderer: libgknext_host.so. Pure CPU; no CUDA here.
+#include <cstring>
+#include <string>
+
+#include "gk_scene.hpp"
+
+extern "C" {
+
+void* gkhost_scene_create(const char* name) {
+    auto* s = new gk::Scene();
+    if (!s->Load(name)) { delete s; return nullptr; }
+    return s;
+}
+void gkhost_scene_destroy(void* h) { delete static_cast<gk::Scene*>(h); }
+
+void gkhost_scene_desc(void* h, GkcuSceneDesc* out) {
+    auto* s = static_cast<gk::Scene*>(h);
+    out->vertices = s->gpu_vertices.data();
+    out->vertex_count = (uint32_t)s->gpu_vertices.size();
+    out->simple_vertices = s->simple_vertices.data();
+    out->indices = s->prim_indices.data();
+    out->index_count = (uint32_t)s->prim_indices.size();
+    out->offsets = s->offsets.data();
+    out->offset_count = (uint32_t)s->offsets.size();
+    out->model_count = (uint32_t)s->models.size();
+}
+const GkNodeProxy* gkhost_scene_nodes(void* h, uint32_t* count) {
+    auto* s = static_cast<gk::Scene*>(h);
+    *count = (uint32_t)s->node_proxies.size();
+    return s->node_proxies.data();
+}
+const GkMaterial* gkhost_scene_materials(void* h, uint32_t* count) {
+    auto* s = static_cast<gk::Scene*>(h);
+    *count = (uint32_t)s->materials.size();
+    return s->materials.data();
+}
+// Scene::UpdateNodes: ticks node velocities (first call after load reports every node as moved, Node.cpp:154-171)
+int gkhost_scene_update_nodes(void* h) { return static_cast<gk::Scene*>(h)->UpdateNodes() ? 1 : 0; }
+
+void gkhost_scene_settings(void* h, int samples, int bounces, int max_bounces, int taa, int temporal_frames, int denoiser, int hdr,
+                           int fast_gather) {
+    auto* s = static_cast<gk::Scene*>(h);
+    s->settings.NumberOfSamples = samples;
+    s->settings.NumberOfBounces = bounces;
+    s->settings.MaxNumberOfBounces = max_bounces;
+    s->settings.TAA = taa != 0;
+    s->settings.TemporalFrames = temporal_frames;
+    s->settings.Denoiser = denoiser != 0;
+    s->settings.HDR = hdr != 0;
+    s->settings.FastGather = fast_gather != 0;
+}
+void gkhost_scene_env(void* h, int has_sky, int has_sun, float sky_intensity, float sun_intensity, float sun_rotation, float sky_rotation) {
+    auto* s = static_cast<gk::Scene*>(h);
+    s->env.HasSky = has_sky != 0;
+    s->env.HasSun = has_sun != 0;
+    s->env.SkyIntensity = sky_intensity;
+    s->env.SunIntensity = sun_intensity;
+    s->env.SunRotation = sun_rotation;
+    s->env.SkyRotation = sky_rotation;
+}
+void gkhost_scene_camera(void* h, float aperture, float focal_distance, float fov) {
+    auto* s = static_cast<gk::Scene*>(h);
+    s->camera.Aperture = aperture;
+    s->camera.FocalDistance = focal_distance;
+    if (fov > 0) s->camera.FieldOfView = fov;
+}
+void gkhost_scene_ubo(void* h, uint32_t width, uint32_t height, uint32_t total_frames, int progressive, float model_rotation_deg,
+                      GkUniformBufferObject* out) {
+    *out = static_cast<gk::Scene*>(h)->GetUniformBufferObject(width, height, total_frames, progressive != 0, model_rotation_deg);
+}
+void gkhost_scene_reset_history(void* h) { static_cast<gk::Scene*>(h)->ResetHistory(); }
+
+void gkhost_scene_counts(void* h, uint32_t* nodes, uint32_t* models, uint32_t* materials, uint64_t* instanced_triangles) {
+    auto* s = static_cast<gk::Scene*>(h);
+    *nodes = (uint32_t)s->nodes.size();
+    *models = (uint32_t)s->models.size();
+    *materials = (uint32_t)s->materials.size();
+    uint64_t t = 0;
+    for (auto& n : s->nodes) t += s->models[n.modelId].indices.size() / 3;
+    *instanced_triangles = t;
+}
+void gkhost_scene_jitter_instances(void* h, uint32_t step, float fraction) { static_cast<gk::Scene*>(h)->JitterInstances(step, fraction); }
+// returns the vertex count; out must hold 4 * vertex_count halfs (call with out = NULL to query)
+uint32_t gkhost_scene_perturb_model(void* h, uint32_t model, uint32_t step, uint16_t* out) {
+    auto* s = static_cast<gk::Scene*>(h);
+    uint32_t n = (uint32_t)s->models[model].vertices.size();
+    if (!out) return n;
+    std::vector<uint16_t> v;
+    s->PerturbModel(model, step, v);
+    std::memcpy(out, v.data(), v.size() * 2);
+    return n;
+}
+void gkhost_make_sky(uint32_t width, uint32_t height, float* rgba) {
+    std::vector<float> v;
+    gk::MakeProceduralSky(width, height, v);
+    std::memcpy(rgba, v.data(), v.size() * 4);
+}
+uint16_t gkhost_to_float16(float f) { return gk::to_float16(f); }
+void gkhost_mat4_inverse(const float* in, float* out) {
+    gk::mat4 m;
+    std::memcpy(m.m, in, 64);
+    gk::mat4 r = gk::inverse(m);
+    std::memcpy(out, r.m, 64);
+}
+
+}  // extern "C"

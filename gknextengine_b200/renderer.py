@@ -1,0 +1,218 @@
+"""Python mirror of the reference's renderer plug-in interface for the CUDA path tracer.
+
+Reference interface (src/Rendering/VulkanBaseRenderer.hpp:45-51, 213-243; .cpp:892-917):
+    enum ERendererType { ERT_PathTracing, ERT_ModernDeferred, ERT_LegacyDeferred, ERT_VoxelTracing }
+    class LogicRendererBase { OnDeviceSet(); CreateSwapChain(extent); DeleteSwapChain(); Render(cmd, imageIndex); BeforeNextFrame(); }
+    VulkanBaseRenderer::RegisterLogicRenderer(type) / SwitchLogicRenderer(type)
+and the acceleration-structure hooks of RayTraceBaseRenderer (src/Rendering/RayTraceBaseRenderer.cpp:165-218):
+    OnPreLoadScene / OnPostLoadScene / AfterUpdateScene / PreRender.
+
+Everything below calls the C ABI of libgknext_cuda.so (include/gkcu.h) through ctypes; there is no CPU fallback:
+constructing a renderer without the library or without a B200 raises.
+"""
+import ctypes as C
+import enum
+import os
+
+import numpy as np
+
+from ._abi import (HIT_DTYPE, RAY_DTYPE, RT, RT_FORMAT, GkcuCounters, GkcuFrameParams, GkcuSceneDesc, GkcuTimings, GkMaterial,
+                   GkNodeProxy, GkUniformBufferObject)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgknext_cuda.so")
+_lib = None
+
+
+class GkcuError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise GkcuError(f"{_LIB_PATH} is missing; build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        P = C.c_void_p
+        L.gkcu_last_error.restype = C.c_char_p
+        L.gkcu_create.argtypes = [C.c_int, C.POINTER(P)]
+        L.gkcu_destroy.argtypes = [P]
+        L.gkcu_resize.argtypes = [P, C.c_uint32, C.c_uint32]
+        L.gkcu_scene_upload.argtypes = [P, C.POINTER(GkcuSceneDesc)]
+        L.gkcu_blas_build.argtypes = [P]
+        L.gkcu_blas_refit.argtypes = [P, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.gkcu_update_nodes.argtypes = [P, C.POINTER(GkNodeProxy), C.c_uint32]
+        L.gkcu_update_materials.argtypes = [P, C.POINTER(GkMaterial), C.c_uint32]
+        L.gkcu_tlas_build.argtypes = [P]
+        L.gkcu_set_sky.argtypes = [P, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.gkcu_set_probes.argtypes = [P, C.c_void_p, C.c_void_p]
+        L.gkcu_render_frame.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
+        L.gkcu_radiance_buffer.argtypes = [P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.gkcu_render_resolve.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
+        L.gkcu_readback.argtypes = [P, C.c_uint32, C.c_void_p, C.c_size_t]
+        L.gkcu_upload_image.argtypes = [P, C.c_uint32, C.c_void_p, C.c_size_t]
+        L.gkcu_run_post.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
+        L.gkcu_synchronize.argtypes = [P]
+        L.gkcu_get_timings.argtypes = [P, C.POINTER(GkcuTimings)]
+        L.gkcu_get_counters.argtypes = [P, C.POINTER(GkcuCounters)]
+        L.gkcu_stream.restype = C.c_uint64
+        L.gkcu_stream.argtypes = [P]
+        L.gkcu_trace_rays.argtypes = [P, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise GkcuError(lib().gkcu_last_error().decode(errors="replace"))
+
+
+class ERendererType(enum.IntEnum):
+    """VulkanBaseRenderer.hpp:45-51 plus the new entry the CUDA renderer registers under."""
+    ERT_PathTracing = 0
+    ERT_ModernDeferred = 1
+    ERT_LegacyDeferred = 2
+    ERT_VoxelTracing = 3
+    ERT_CudaPathTracing = 4
+
+
+class CudaPathTracingRenderer:
+    """LogicRendererBase implementation backed by libgknext_cuda.so (the drop-in for RayTracing::PathTracingRenderer)."""
+
+    def __init__(self, device=0):
+        self.device = device
+        self._ctx = C.c_void_p()
+        self.extent = None
+        self.OnDeviceSet()
+
+    # ---- LogicRendererBase
+    def OnDeviceSet(self):
+        if not self._ctx:
+            _ck(lib().gkcu_create(self.device, C.byref(self._ctx)))
+
+    def CreateSwapChain(self, extent):
+        w, h = extent
+        _ck(lib().gkcu_resize(self._ctx, w, h))
+        self.extent = (w, h)
+
+    def DeleteSwapChain(self):
+        self.extent = None
+
+    def Render(self, ubo, params=None):
+        """PathTracingRenderer::Render: rt pass -> reproject pass -> compose pass -> copy pass (asynchronous)."""
+        params = params or GkcuFrameParams(temporal_frames=16, spp_world=1)
+        _ck(lib().gkcu_render_frame(self._ctx, C.byref(ubo), C.byref(params)))
+
+    def BeforeNextFrame(self):
+        _ck(lib().gkcu_synchronize(self._ctx))
+
+    # ---- RayTraceBaseRenderer hooks
+    def OnPostLoadScene(self, scene, sky=None):
+        """Scene::RebuildMeshBuffer uploads + CreateAccelerationStructures."""
+        d = scene.desc()
+        _ck(lib().gkcu_scene_upload(self._ctx, C.byref(d)))
+        mats, nm = scene.materials()
+        _ck(lib().gkcu_update_materials(self._ctx, mats, nm))
+        _ck(lib().gkcu_blas_build(self._ctx))
+        self.AfterUpdateScene(scene)
+        if sky is not None:
+            self.set_sky(0, sky)
+
+    def AfterUpdateScene(self, scene):
+        nodes, nn = scene.nodes()
+        _ck(lib().gkcu_update_nodes(self._ctx, nodes, nn))
+
+    def PreRender(self):
+        _ck(lib().gkcu_tlas_build(self._ctx))
+
+    def update_materials(self, scene):
+        mats, nm = scene.materials()
+        _ck(lib().gkcu_update_materials(self._ctx, mats, nm))
+
+    def refit_model(self, model, simple_vertices):
+        sv = np.ascontiguousarray(simple_vertices, dtype=np.uint16)
+        _ck(lib().gkcu_blas_refit(self._ctx, model, sv.ctypes.data, len(sv) // 4))
+
+    def set_sky(self, idx, rgba):
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        _ck(lib().gkcu_set_sky(self._ctx, idx, rgba.ctypes.data, rgba.shape[1], rgba.shape[0]))
+
+    # ---- multi-GPU split
+    def radiance_buffer(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _ck(lib().gkcu_radiance_buffer(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def Resolve(self, ubo, params):
+        _ck(lib().gkcu_render_resolve(self._ctx, C.byref(ubo), C.byref(params)))
+
+    # ---- results
+    def readback(self, rt, out=None):
+        w, h = self.extent
+        dtype, ch = RT_FORMAT[rt]
+        shape = (h, w, ch) if ch > 1 else (h, w)
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        _ck(lib().gkcu_readback(self._ctx, rt, out.ctypes.data, out.nbytes))
+        return out
+
+    def upload_image(self, rt, arr):
+        arr = np.ascontiguousarray(arr)
+        _ck(lib().gkcu_upload_image(self._ctx, rt, arr.ctypes.data, arr.nbytes))
+
+    def run_post(self, ubo, params):
+        _ck(lib().gkcu_run_post(self._ctx, C.byref(ubo), C.byref(params)))
+
+    def timings(self):
+        t = GkcuTimings()
+        _ck(lib().gkcu_get_timings(self._ctx, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in GkcuTimings._fields_}
+
+    def counters(self):
+        c = GkcuCounters()
+        _ck(lib().gkcu_get_counters(self._ctx, C.byref(c)))
+        return {n: getattr(c, n) for n, _ in GkcuCounters._fields_}
+
+    def stream(self):
+        return lib().gkcu_stream(self._ctx)
+
+    def trace(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        _ck(lib().gkcu_trace_rays(self._ctx, rays.ctypes.data, len(rays), hits.ctypes.data, int(any_hit)))
+        return hits
+
+    def close(self):
+        if self._ctx:
+            lib().gkcu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RendererRegistry:
+    """VulkanBaseRenderer::RegisterLogicRenderer / SwitchLogicRenderer (VulkanBaseRenderer.cpp:892-917) for the headless host."""
+
+    def __init__(self, device=0):
+        self.device = device
+        self.logicRenderers_ = {}
+        self.currentLogicRenderer_ = None
+
+    def RegisterLogicRenderer(self, rtype):
+        rtype = ERendererType(rtype)
+        if rtype != ERendererType.ERT_CudaPathTracing:
+            raise GkcuError(f"{rtype.name} is a Vulkan renderer of the reference and is not part of this build")
+        self.logicRenderers_[rtype] = CudaPathTracingRenderer(self.device)
+        self.currentLogicRenderer_ = rtype
+
+    def SwitchLogicRenderer(self, rtype):
+        self.currentLogicRenderer_ = ERendererType(rtype)
+
+    def current(self):
+        return self.logicRenderers_[self.currentLogicRenderer_]

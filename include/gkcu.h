@@ -1,0 +1,367 @@
+/*
+ * gkcu.h — C ABI of libgknext_cuda.so, the B200-native (sm_100a) CUDA path-tracing
+ * renderer that stands in for gkNextEngine's Vulkan RayTracing renderer.
+ *
+ * Everything here is plain C: POD structs, raw host pointers, sizes and int return
+ * codes (0 = ok, anything else = error; text via gkcu_last_error()). No exceptions,
+ * no torch/CUDA types cross this boundary. One render thread per context.
+ *
+ * The POD structs are byte-exact mirrors of the reference's shared C++/Slang header
+ * (reference: assets/shaders/common/BasicTypes.slang:22-291, included into C++ by
+ * src/Assets/UniformBuffer.hpp:30-48 with bool -> uint32_t, half4 -> uint16). The
+ * static_asserts at the bottom pin sizeof/offsetof to the values measured from the
+ * reference header; oracle/ref_layout_check.cpp re-checks them
+ * against the reference header itself when /root/reference is mounted.
+ *
+ * Each entry point cites the reference interface it replaces.
+ */
+#ifndef GKCU_H
+#define GKCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ POD types */
+
+typedef struct GkVec4 { float x, y, z, w; } GkVec4;
+/* glm column-major: m[col][row]; shaders use mul(M, v) == M * v. */
+typedef struct GkMat4 { float m[4][4]; } GkMat4;
+
+/* BasicTypes.slang:22-84 */
+typedef struct GkUniformBufferObject {
+    GkMat4 ModelView;
+    GkMat4 Projection;
+    GkMat4 ModelViewInverse;
+    GkMat4 ProjectionInverse;
+    GkMat4 ViewProjection;
+    GkMat4 PrevViewProjection;
+    GkMat4 ViewProjectionUnJit;
+    GkMat4 PrevViewProjectionUnJit;
+
+    GkVec4 ViewportRect;
+    GkVec4 SunDirection;
+    GkVec4 SunColor;
+    GkVec4 BackGroundColor;
+
+    GkMat4 SunViewProjection;
+
+    float Aperture;
+    float FocusDistance;
+    float SkyRotation;
+    float HeatmapScale;
+
+    float PaperWhiteNit;
+    float SkyIntensity;
+    uint32_t SkyIdx;
+    uint32_t TotalFrames;
+
+    uint32_t MaxNumberOfBounces;
+    uint32_t NumberOfSamples;
+    uint32_t NumberOfBounces;
+    uint32_t RandomSeed;
+
+    uint32_t LightCount;
+    uint32_t HasSky;
+    uint32_t ShowHeatmap;
+    uint32_t UseCheckerBoard;
+
+    uint32_t TemporalFrames;
+    uint32_t HasSun;
+    uint32_t HDR;
+    uint32_t AdaptiveSample;
+
+    float AdaptiveVariance;
+    uint32_t AdaptiveSteps;
+    uint32_t TAA;
+    uint32_t SelectedId;
+
+    uint32_t ShowEdge;
+    uint32_t ProgressiveRender;
+    float BFSigma;
+    float BFSigmaLum;
+
+    float BFSigmaNormal;
+    uint32_t BFSize;
+
+    uint32_t FastGather;
+
+    uint32_t FastInterpole;
+    uint32_t DebugDraw_Lighting;
+    uint32_t DisableSpatialReuse;
+    uint32_t SuperResolution;
+    uint32_t _pad0;
+} GkUniformBufferObject;
+
+/* BasicTypes.slang:86-95 */
+typedef struct GkNodeProxy {
+    uint32_t instanceId;
+    uint32_t modelId;   /* model * 10 + section (Scene.cpp:470) */
+    uint32_t visible;
+    uint32_t nort;      /* section > 0 -> not in the TLAS (RayTraceBaseRenderer.cpp:178) */
+    GkMat4 worldTS;
+    GkMat4 combinedPrevTS;
+    uint32_t matId[16];
+} GkNodeProxy;
+
+/* BasicTypes.slang:97-111 */
+typedef struct GkModelData {
+    uint32_t indexOffset;
+    uint32_t indexCount;
+    uint32_t vertexOffset;
+    uint32_t vertexCount;
+    GkVec4 localAabbMin;
+    GkVec4 localAabbMax;
+    uint32_t modelType;
+    uint32_t voxelDataIdx;
+    uint32_t reorderOffset;
+    uint32_t reserved2;
+} GkModelData;
+
+/* BasicTypes.slang:116-138 */
+typedef struct GkAmbientCube {
+    uint32_t PosZ, NegZ, PosY, NegY, PosX, NegX;
+    uint32_t PosZ_D, NegZ_D, PosY_D, NegY_D, PosX_D, NegX_D;
+    uint32_t skyVisibility_pznzpyny;
+    uint32_t skyVisibility_pxnxs0s1;
+} GkAmbientCube;
+
+/* BasicTypes.slang:145-151 */
+typedef struct GkVoxelData {
+    uint32_t matId;
+    uint32_t age;
+    uint32_t distanceToSolid_gg_z01;
+    uint32_t distanceToSolid_x01_y01;
+} GkVoxelData;
+
+/* BasicTypes.slang:218-236 / src/Assets/Material.hpp:8-74 */
+typedef struct GkMaterial {
+    GkVec4 Diffuse;
+    int32_t DiffuseTextureId;
+    int32_t MRATextureId;
+    int32_t NormalTextureId;
+    float Fuzziness;
+    float RefractionIndex;
+    uint32_t MaterialModel;
+    float Metalness;
+    float RefractionIndex2;
+    float NormalTextureScale;
+    float Reserverd2;
+    float Reserverd3;
+    float Reserverd4;
+} GkMaterial;
+
+enum { /* BasicTypes.slang:183-188 */
+    GK_MATERIAL_LAMBERTIAN = 0,
+    GK_MATERIAL_METALLIC = 1,
+    GK_MATERIAL_DIELECTRIC = 2,
+    GK_MATERIAL_ISOTROPIC = 3,
+    GK_MATERIAL_DIFFUSE_LIGHT = 4,
+    GK_MATERIAL_MIXTURE = 5
+};
+
+/* BasicTypes.slang:249-254 / src/Assets/Vertex.hpp:32-47: 12 x 16-bit.
+ * pos.xyz, u, nrm.xyz, v, tan.xyz as IEEE half bits (glm::detail::toFloat16 rounding),
+ * tangentw = (tanSign > 0 ? 2 : 0) << 8 | materialSlot (Vertex.hpp:97). */
+typedef struct GkGPUVertex {
+    uint16_t posx, posy, posz, texcoordx;
+    uint16_t normalx, normaly, normalz, texcoordy;
+    uint16_t tangentx, tangenty, tangentz, tangentw;
+} GkGPUVertex;
+
+/* Storage-image indices: assets/shaders/common/BindlessTexture.slang:8-40. */
+enum {
+    GK_RT_ACCUMLATE_DIFFUSE = 0,
+    GK_RT_SINGLE_DIFFUSE = 1,
+    GK_RT_MINIGBUFFER = 2,
+    GK_RT_OBJEDCTID_0 = 3,
+    GK_RT_OBJEDCTID_1 = 4,
+    GK_RT_MOTIONVECTOR = 5,
+    GK_RT_ALBEDO = 6,
+    GK_RT_NORMAL = 7,
+    GK_RT_SHADER_TIMER = 8,
+    GK_RT_DENOISED = 9,
+    GK_RT_PREV_DEPTHBUFFER = 10,
+    GK_RT_ACCUMLATE_SPECULAR = 11,
+    GK_RT_SINGLE_SPECULAR = 12,
+    GK_RT_ACCUMLATE_ALBEDO = 13,
+    GK_RT_MOTIONMOMENT = 14,
+    GK_RT_SINGLE_PREV_DIFFUSE = 20,
+    GK_RT_SINGLE_PREV_SPECULAR = 21,
+    GK_RT_SINGLE_PREV_ALBEDO = 22,
+    /* CUDA-side extension (no reference counterpart): per-pixel primitive index of the
+     * primary hit (R32_UINT, 0xFFFFFFFF on miss), used for the id-parity check. */
+    GK_RT_EXT_PRIMITIVEID = 64
+};
+
+#define GK_OBJECTID_MISS 65535u      /* Shading.slang:1199 */
+#define GK_MAX_MATERIALS 8192        /* BasicTypes.slang:11 */
+
+/* Probe grid: assets/shaders/common/AmbientCube.slang:11-15. */
+#define GK_CUBE_SIZE_XY 192
+#define GK_CUBE_SIZE_Z 48
+
+/* ------------------------------------------------------------- scene contract */
+
+/* Outputs of Scene::RebuildMeshBuffer (reference: src/Assets/Scene.cpp:102-289):
+ * the global vertex/index/offset arrays the shaders read through GPUScene
+ * (BasicTypes.slang:261-291). All pointers are HOST memory; the call copies. */
+typedef struct GkcuSceneDesc {
+    const GkGPUVertex* vertices;      /* GPUScene.Vertices */
+    uint32_t vertex_count;
+    const uint16_t* simple_vertices;  /* GPUScene.VerticesSimple: half4 (x,y,z,x) per vertex, the BLAS positions
+                                         (BottomLevelGeometry.cpp:21-24) */
+    const uint32_t* indices;          /* GPUScene.Indices (= PrimAddress: model-local vertex ids) */
+    uint32_t index_count;
+    const GkModelData* offsets;       /* GPUScene.Offsets: 10 sections per model */
+    uint32_t offset_count;            /* = 10 * model_count */
+    uint32_t model_count;
+} GkcuSceneDesc;
+
+typedef struct GkcuFrameParams {
+    uint32_t progressive;       /* ReProject push constant ProgressiveRender (PathTracingRenderer.cpp:127) */
+    int32_t temporal_frames;    /* ReProject push constant TemporalFrames (user setting, not ubo.TemporalFrames) */
+    uint32_t fast_reproject;    /* push constant FastReproject (always 0 in the reference) */
+    /* Multi-GPU sample split (no reference counterpart). world = 1 reproduces the reference.
+     * Rank r of `spp_world` traces samples [r*S/world, (r+1)*S/world) with frame seed TotalFrames*world + r. */
+    uint32_t spp_rank;
+    uint32_t spp_world;
+    uint32_t tracer;            /* 0 = wavefront (default), 1 = megakernel (one thread per pixel) */
+    uint32_t skip_post;         /* 1 = stop after the rt pass (radiance sums left un-normalised for a reduce) */
+    uint32_t reserved;
+} GkcuFrameParams;
+
+typedef struct GkcuTimings {   /* names follow the reference's GPU timer scopes (PathTracingRenderer.cpp:111,126,138,160) */
+    float tlas_update_ms;      /* "TLAS Update" (RayTraceBaseRenderer.cpp:209) */
+    float rt_pass_ms;          /* "rt pass" */
+    float reproject_pass_ms;   /* "reproject pass" */
+    float compose_pass_ms;     /* "compose pass" */
+    float copy_pass_ms;        /* "copy pass": pointer swaps here, ~0 */
+    float frame_ms;
+    float blas_build_ms;       /* last gkcu_blas_build */
+    float blas_refit_ms;       /* last gkcu_blas_refit */
+} GkcuTimings;
+
+typedef struct GkcuCounters {  /* exact ray counts of the last frame */
+    uint64_t primary_rays;
+    uint64_t closest_hit_rays;
+    uint64_t any_hit_rays;
+    uint64_t wavefront_iterations;
+    uint64_t kernel_launches;  /* kernels launched by this library during the last frame */
+} GkcuCounters;
+
+typedef struct GkcuRay { float ox, oy, oz, tmin, dx, dy, dz, tmax; } GkcuRay;
+typedef struct GkcuHit { float t, u, v; uint32_t inst; uint32_t prim; } GkcuHit; /* inst = 0xFFFFFFFF on miss */
+
+typedef struct GkcuContext GkcuContext;
+
+/* ------------------------------------------------------------------ lifecycle */
+
+const char* gkcu_last_error(void);
+
+/* Replaces NextRenderer::CreateRenderer + LogicRendererBase::OnDeviceSet
+ * (src/Runtime/Engine.cpp:57-90, src/Rendering/VulkanBaseRenderer.hpp:213-243). */
+int gkcu_create(int device_ordinal, GkcuContext** out_ctx);
+int gkcu_destroy(GkcuContext* ctx);
+
+/* Replaces VulkanBaseRenderer::CreateRenderImages + LogicRendererBase::CreateSwapChain/DeleteSwapChain
+ * (src/Rendering/VulkanBaseRenderer.cpp:429-463, PathTracingRenderer.cpp:66-102): (re)allocates the
+ * storage images, zero-filled, and the wavefront path state. */
+int gkcu_resize(GkcuContext* ctx, uint32_t width, uint32_t height);
+
+/* ---------------------------------------------------------------------- scene */
+
+/* Replaces the device uploads at the end of Scene::RebuildMeshBuffer (src/Assets/Scene.cpp:262-277). */
+int gkcu_scene_upload(GkcuContext* ctx, const GkcuSceneDesc* desc);
+
+/* Replaces RayTraceBaseRenderer::CreateBottomLevelStructures (src/Rendering/RayTraceBaseRenderer.cpp:276-340,
+ * src/Vulkan/RayTracing/BottomLevelAccelerationStructure.cpp:7-59): one BLAS per model. */
+int gkcu_blas_build(GkcuContext* ctx);
+
+/* New capability (the reference never updates a BLAS): replace the positions of one model
+ * (half4 per vertex, vertex_count entries, host memory) and refit its BLAS bottom-up. */
+int gkcu_blas_refit(GkcuContext* ctx, uint32_t model_index, const uint16_t* simple_vertices, uint32_t vertex_count);
+
+/* Replaces Scene::UpdateNodesGpuDriven's memcpy into the Nodes buffer + RayTraceBaseRenderer::AfterUpdateScene
+ * (src/Assets/Scene.cpp:443-492, src/Rendering/RayTraceBaseRenderer.cpp:165-191): instance i <-> nodes[i]. */
+int gkcu_update_nodes(GkcuContext* ctx, const GkNodeProxy* nodes, uint32_t count);
+
+/* Replaces Scene::UpdateAllMaterials (src/Assets/Scene.cpp:393-408). */
+int gkcu_update_materials(GkcuContext* ctx, const GkMaterial* materials, uint32_t count);
+
+/* Replaces RayTraceBaseRenderer::PreRender "TLAS Update" = TopLevelAccelerationStructure::Update, a full rebuild
+ * (src/Rendering/RayTraceBaseRenderer.cpp:205-218, TopLevelAccelerationStructure.cpp:73-81). Also run implicitly
+ * by gkcu_render_frame when the nodes changed since the last build. */
+int gkcu_tlas_build(GkcuContext* ctx);
+
+/* Sampled texture `id` of the bindless array (sky HDRs are ids 0-10, Engine.cpp:855): RGBA32F, row-major,
+ * sampled bilinear + repeat at mip 0 (Shading.slang:194-199, src/Vulkan/Sampler.hpp:9-26). */
+int gkcu_set_sky(GkcuContext* ctx, uint32_t id, const float* rgba, uint32_t width, uint32_t height);
+
+/* GPUScene.Cubes / GPUScene.Voxels (192*48*192 entries each) or NULL,NULL for the zero probe state
+ * (AmbientCube.slang:290-382). */
+int gkcu_set_probes(GkcuContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels);
+
+/* ---------------------------------------------------------------------- frame */
+
+/* Replaces PathTracingRenderer::Render (src/Rendering/PathTracing/PathTracingRenderer.cpp:104-218):
+ * clear -> rt pass -> reproject pass -> compose pass -> copy pass (+ the object-id copy of
+ * VulkanBaseRenderer::PostRender, VulkanBaseRenderer.cpp:1136-1152). Asynchronous on the context stream. */
+int gkcu_render_frame(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params);
+
+/* Multi-GPU split of the frame: gkcu_render_frame(skip_post=1) leaves the un-normalised
+ * FinalColor/FinalReflection sums in the radiance buffer (2 x W x H x float4, device memory) for an NCCL
+ * reduce; gkcu_render_resolve divides by the total sample count, adds the direct term, and runs the post passes. */
+int gkcu_radiance_buffer(GkcuContext* ctx, void** device_ptr, size_t* bytes);
+int gkcu_render_resolve(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params);
+
+/* Blocking device->host copy of one storage image in its reference format
+ * (fp16x4 / R32_UINT / RG32F / R32F / R16_UINT, VulkanBaseRenderer.cpp:439-457). */
+int gkcu_readback(GkcuContext* ctx, uint32_t rt_index, void* dst, size_t dst_bytes);
+/* Stencil-pass bring-up hooks used by the parity tests: overwrite one storage image from host memory (formats as in
+ * gkcu_readback; PREV_* and OBJECTID_1 address the history slots), and run only reproject -> compose -> copy pass. */
+int gkcu_upload_image(GkcuContext* ctx, uint32_t rt_index, const void* src, size_t src_bytes);
+int gkcu_run_post(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params);
+int gkcu_synchronize(GkcuContext* ctx);
+int gkcu_get_timings(GkcuContext* ctx, GkcuTimings* out);
+int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out);
+/* cudaStream_t of the context as an integer handle, for callers that time with events or enqueue collectives. */
+uint64_t gkcu_stream(GkcuContext* ctx);
+
+/* Closest-hit / any-hit queries against the current TLAS; the CUDA counterpart of
+ * FCPUAccelerationStructure::RayCastInCPU (src/Assets/CPUAccelerationStructure.cpp:286-313). Host arrays. */
+int gkcu_trace_rays(GkcuContext* ctx, const GkcuRay* rays, uint32_t count, GkcuHit* hits, uint32_t any_hit);
+
+#ifdef __cplusplus
+}
+
+static_assert(sizeof(GkUniformBufferObject) == 784, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, ViewportRect) == 512, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, SunViewProjection) == 576, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, Aperture) == 640, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, TotalFrames) == 668, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, NumberOfBounces) == 680, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, HasSky) == 692, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, TemporalFrames) == 704, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, HasSun) == 708, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, TAA) == 728, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, ProgressiveRender) == 740, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, BFSigma) == 744, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, BFSize) == 756, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, FastGather) == 760, "UBO layout");
+static_assert(offsetof(GkUniformBufferObject, SuperResolution) == 776, "UBO layout");
+static_assert(sizeof(GkNodeProxy) == 208 && offsetof(GkNodeProxy, worldTS) == 16 &&
+              offsetof(GkNodeProxy, combinedPrevTS) == 80 && offsetof(GkNodeProxy, matId) == 144, "NodeProxy layout");
+static_assert(sizeof(GkModelData) == 64 && offsetof(GkModelData, localAabbMin) == 16 &&
+              offsetof(GkModelData, modelType) == 48 && offsetof(GkModelData, reorderOffset) == 56, "ModelData layout");
+static_assert(sizeof(GkMaterial) == 64 && offsetof(GkMaterial, Fuzziness) == 28 &&
+              offsetof(GkMaterial, MaterialModel) == 36 && offsetof(GkMaterial, NormalTextureScale) == 48, "Material layout");
+static_assert(sizeof(GkGPUVertex) == 24, "GPUVertex layout");
+static_assert(sizeof(GkAmbientCube) == 56, "AmbientCube layout");
+static_assert(sizeof(GkVoxelData) == 16, "VoxelData layout");
+#endif
+
+#endif /* GKCU_H */

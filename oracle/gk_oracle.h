@@ -1,0 +1,70 @@
+/*
+ * gk_oracle.h — CPU oracle for the gkNextEngine path-tracing frame. TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library; the product (libgknext_cuda.so, gknextengine_b200/) never links, imports or calls it.
+ *
+ * PARITY STATUS: "parity unpinned" for the shading chain. The reference has no tests, golden images or
+ * known-answer vectors for this path and its implementation is Slang shader code behind
+ * Vulkan ray queries, which cannot be compiled or run in this container (no slangc, no Vulkan). What IS pinned:
+ *   - struct layouts, against the reference's own dual-language header compiled as C++ (oracle/ref_layout_check.cpp)
+ *   - the ray/BVH intersector, against the reference's vendored tinybvh v1.3.8 compiled from
+ *     /root/reference/src/ThirdParty/tinybvh/tiny_bvh.h into oracle/_ref/ (same oracle source, -DGKO_TINYBVH)
+ *   - fixture known-answers generated here with libstdc++, in tests/golden/.
+ */
+#ifndef GK_ORACLE_H
+#define GK_ORACLE_H
+
+#include "../include/gkcu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct GkoScene GkoScene;
+typedef struct GkoFrame GkoFrame;
+
+GkoScene* gko_scene_create(const GkcuSceneDesc* desc);
+void gko_scene_destroy(GkoScene* s);
+void gko_update_nodes(GkoScene* s, const GkNodeProxy* nodes, uint32_t count);      /* also rebuilds the TLAS */
+void gko_update_materials(GkoScene* s, const GkMaterial* materials, uint32_t count);
+void gko_refit_model(GkoScene* s, uint32_t model, const uint16_t* simple_vertices, uint32_t vertex_count);
+void gko_set_sky(GkoScene* s, uint32_t id, const float* rgba, uint32_t w, uint32_t h);
+void gko_set_probes(GkoScene* s, const GkAmbientCube* cubes, const GkVoxelData* voxels);
+const char* gko_intersector_name(void); /* "native-watertight" or "tinybvh-1.3.8" */
+
+GkoFrame* gko_frame_create(uint32_t width, uint32_t height);
+void gko_frame_destroy(GkoFrame* f);
+
+/* One frame = clear + rt pass + reproject + compose + copies, like PathTracingRenderer::Render.
+ * rows [y0, y1) bound the rt pass for timing samples (post passes then only make sense on full frames:
+ * pass run_post = 0). threads <= 0 -> hardware_concurrency. */
+int gko_render_frame(GkoScene* s, GkoFrame* f, const GkUniformBufferObject* ubo, const GkcuFrameParams* params,
+                     int threads, uint32_t y0, uint32_t y1, int run_post);
+
+/* Post passes alone on caller-filled images (stencil parity tests). */
+int gko_reproject(GkoFrame* f, const GkcuFrameParams* params);
+int gko_denoise(GkoFrame* f, const GkUniformBufferObject* ubo);
+void gko_end_frame_copies(GkoFrame* f); /* ACCUM -> PREV x3, OBJECTID_0 -> OBJECTID_1 */
+
+/* Raw storage image (reference formats), writable so tests can seed inputs. */
+void* gko_image(GkoFrame* f, uint32_t rt_index, size_t* bytes);
+void gko_get_counters(GkoFrame* f, GkcuCounters* out);
+double gko_last_rt_seconds(GkoFrame* f);
+
+void gko_trace_rays(GkoScene* s, const GkcuRay* rays, uint32_t count, GkcuHit* hits, uint32_t any_hit);
+
+/* Known-answer helpers for the small pure functions (tests/test_oracle_kat.py). */
+void gko_pcg4d(uint32_t v[4]);
+float gko_uint_to_float(uint32_t x);
+uint16_t gko_float_to_half(float f);
+float gko_half_to_float(uint16_t h);
+void gko_gt_tonemap(const float in[3], float out[3]);
+void gko_ggx_sampling(uint32_t seed[4], float roughness, const float normal[3], float out[3]);
+void gko_random_in_hemisphere1(uint32_t seed[4], float out[3]);
+float gko_schlick(float cosine, float ior);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
