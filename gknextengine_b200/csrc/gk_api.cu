@@ -454,6 +454,44 @@ int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out) {
     return 0;
 }
 
+// Debug/validation hook (tests/test_gpu_bvh.py): raw device->host copies of the acceleration-structure pools.
+// what: 0 TLAS nodes, 1 BLAS nodes, 2 BLAS triangles, 3 instances, 4/5 TLAS node boxes lo/hi, 6 BLAS table.
+int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, size_t bytes) {
+    CTX_OR_FAIL(ctx);
+    const DevBuf* b = nullptr;
+    switch (what) {
+        case 0: b = &c.tlas_nodes; break;
+        case 1: b = &c.blas_nodes; break;
+        case 2: b = &c.blas_tris; break;
+        case 3: b = &c.instances; break;
+        case 4: b = &c.tlas_node_lo; break;
+        case 5: b = &c.tlas_node_hi; break;
+        case 6: b = &c.blas_table; break;
+        default: set_error("gkcu_debug_read: bad selector"); return 1;
+    }
+    if (!b->p || offset + bytes > b->cap) { set_error("gkcu_debug_read: out of range"); return 1; }
+    GK_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(b->p) + offset, bytes, cudaMemcpyDeviceToHost, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+// out[0] TLAS node count, [1] TLAS levels, [2] instance count, [3] model count, [4 + 4m ..] per model: node_base, node_count, tri_base, prim_count
+int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity) {
+    CTX_OR_FAIL(ctx);
+    if (capacity < 4 + 4 * c.model_count) { set_error("gkcu_debug_info: capacity"); return 1; }
+    if (c.tlas_dirty && c.blas_built && build_tlas(c)) return 1;
+    out[0] = c.tlas.node_count;
+    out[1] = c.tlas.level_start.empty() ? 0 : (uint32_t)c.tlas.level_start.size() - 1;
+    out[2] = c.node_count;
+    out[3] = c.model_count;
+    for (uint32_t m = 0; m < c.model_count && m < c.blas.size(); ++m) {
+        out[4 + 4 * m] = c.blas[m].node_base;
+        out[5 + 4 * m] = c.blas[m].node_count;
+        out[6 + 4 * m] = c.blas[m].tri_base;
+        out[7 + 4 * m] = c.blas[m].prim_count;
+    }
+    return 0;
+}
+
 uint64_t gkcu_stream(GkcuContext* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->c.stream : 0; }
 
 int gkcu_trace_rays(GkcuContext* ctx, const GkcuRay* rays, uint32_t count, GkcuHit* hits, uint32_t any_hit) {

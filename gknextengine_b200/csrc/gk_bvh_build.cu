@@ -677,7 +677,7 @@ int build_sah(Context& c, uint32_t n, Bvh2& out) {
         k_mark_slots<<<grid_for(nactive), 256, 0, st>>>(act_a, nactive, slot_of, 0);
         k_sah_clear_bins<<<grid_for((size_t)nactive * 3 * kSahBins), 256, 0, st>>>(s.bins.as<SahBin>(), nactive);
         k_sah_bin<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, s.bins.as<SahBin>());
-        k_sah_split<<<grid_for(nactive), 128, 0, st>>>(nactive, act_a, s.bins.as<SahBin>(), nlo, nhi, left, right, first, count, counters, act_b, splits,
+        k_sah_split<<<grid_for(nactive, 128), 128, 0, st>>>(nactive, act_a, s.bins.as<SahBin>(), nlo, nhi, left, right, first, count, counters, act_b, splits,
                                                       cursors);
         k_sah_partition<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, left, first,
                                                      splits, cursors, ord_b, pn_b);
@@ -850,7 +850,7 @@ int build_tlas(Context& c) {
         !reserve_bvh2(s, n) || !c.tlas_nodes.reserve(((size_t)n + 4) * sizeof(Node4)) || !c.tlas_node_lo.reserve(((size_t)n + 4) * 16) ||
         !c.tlas_node_hi.reserve(((size_t)n + 4) * 16))
         return 1;
-    k_instances<<<grid_for(n), 128, 0, st>>>(c.nodes.as<GkNodeProxy>(), n, c.blas_table.as<uint4>(), c.model_count, c.instances.as<InstanceRec>(),
+    k_instances<<<grid_for(n, 128), 128, 0, st>>>(c.nodes.as<GkNodeProxy>(), n, c.blas_table.as<uint4>(), c.model_count, c.instances.as<InstanceRec>(),
                                              s.prim_lo.as<float4>(), s.prim_hi.as<float4>());
     c.launches += 1;
     // count active instances: they sort in front of the inactive ones (key 0x7FFF...)

@@ -54,6 +54,8 @@ def lib():
         L.gkcu_readback.argtypes = [P, C.c_uint32, C.c_void_p, C.c_size_t]
         L.gkcu_upload_image.argtypes = [P, C.c_uint32, C.c_void_p, C.c_size_t]
         L.gkcu_run_post.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
+        L.gkcu_debug_read.argtypes = [P, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.gkcu_debug_info.argtypes = [P, C.POINTER(C.c_uint32), C.c_uint32]
         L.gkcu_synchronize.argtypes = [P]
         L.gkcu_get_timings.argtypes = [P, C.POINTER(GkcuTimings)]
         L.gkcu_get_counters.argtypes = [P, C.POINTER(GkcuCounters)]
@@ -183,6 +185,20 @@ class CudaPathTracingRenderer:
         hits = np.zeros(len(rays), dtype=HIT_DTYPE)
         _ck(lib().gkcu_trace_rays(self._ctx, rays.ctypes.data, len(rays), hits.ctypes.data, int(any_hit)))
         return hits
+
+    # ---- validation hooks
+    def debug_info(self):
+        cap = 4 + 4 * 4096
+        out = (C.c_uint32 * cap)()
+        _ck(lib().gkcu_debug_info(self._ctx, out, cap))
+        models = [dict(node_base=out[4 + 4 * m], node_count=out[5 + 4 * m], tri_base=out[6 + 4 * m], prim_count=out[7 + 4 * m])
+                  for m in range(out[3])]
+        return dict(tlas_nodes=out[0], tlas_levels=out[1], instances=out[2], models=models)
+
+    def debug_read(self, what, offset, count, dtype):
+        arr = np.zeros(count, dtype=dtype)
+        _ck(lib().gkcu_debug_read(self._ctx, what, offset, arr.ctypes.data, arr.nbytes))
+        return arr
 
     def close(self):
         if self._ctx:

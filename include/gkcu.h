@@ -325,6 +325,9 @@ int gkcu_readback(GkcuContext* ctx, uint32_t rt_index, void* dst, size_t dst_byt
  * gkcu_readback; PREV_* and OBJECTID_1 address the history slots), and run only reproject -> compose -> copy pass. */
 int gkcu_upload_image(GkcuContext* ctx, uint32_t rt_index, const void* src, size_t src_bytes);
 int gkcu_run_post(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params);
+/* Validation hooks (tests only): raw copies of the acceleration-structure pools and their bookkeeping. */
+int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, size_t bytes);
+int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity);
 int gkcu_synchronize(GkcuContext* ctx);
 int gkcu_get_timings(GkcuContext* ctx, GkcuTimings* out);
 int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out);
