@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and ms/frame of the path-tracing frame on N B200s (BASELINE.json metric), one JSON line.
+
+Workload (config.workload): BASELINE.json configs[1] — the RayTracingInOneWeekend procedural scene (RTIO.proc,
+src/Runtime/SceneList.cpp:117-178), 1920x1080, 16 spp, 8 bounces, sky, steady state (no node motion). A "step" is one
+frame through PathTracingRenderer::Render's pass sequence: TLAS rebuild -> rt pass -> reproject pass -> compose pass.
+With N > 1 every rank holds a scene replica and traces 16 spp of a 16*N-spp frame (weak scaling over samples per pixel,
+SURVEY 8e); the un-normalised radiance sums are reduced to rank 0 with NCCL and rank 0 resolves + runs the post passes.
+
+  value          rays/s of the whole job, inputs resident in HBM, CUDA-event timed on the renderer's stream, max over ranks
+  e2e            the same through the public API with HOST buffers: NodeProxy[] + UBO H2D from pinned memory and the
+                 RT_DENOISED D2H read every step, wall-clock between synchronisations
+  roofline       dominant kernel (k_trace) against the measured HBM peak, see DESIGN.md for the byte accounting
+  cpu_baseline   the CPU oracle (scalar port of the reference shaders) on the host cores, bounded sample of the same frame
+
+--impl reference times that CPU port alone (the reference's Slang/Vulkan path cannot run without slangc/Vulkan).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, SPP, BOUNCES = 1920, 1080, 16, 8
+SCENE = "RTIO.proc"
+# algorithmic bytes (DESIGN.md "Byte accounting"): per closest-hit ray 436 B, per any-hit ray 100 B for the
+# trace+shade pair; the share k_trace itself moves is the ray record it reads and the hit record it writes.
+TRACE_BYTES_PER_RAY = 32 + 4 + 16 + 4
+PAIR_BYTES_CLOSEST, PAIR_BYTES_ANY = 436, 100
+PRIMARY_BYTES_PER_PIXEL, REPROJECT_BYTES_PER_PIXEL, DENOISE_BYTES_PER_PIXEL = 36 + 2, 98, 44
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_sample(scene, sky, ubo, params, bands, band_rows, threads=0):
+    """Times the CPU oracle (reference-semantics port) on `bands` evenly spaced bands of `band_rows` rows of the frame."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+
+    osc = O.OracleScene(scene, sky)
+    ofr = O.OracleFrame(WIDTH, HEIGHT)
+    rays, secs = 0, 0.0
+    for b in range(bands):
+        y0 = int((b + 0.5) * HEIGHT / bands) - band_rows // 2
+        ofr.render(osc, ubo, params, threads=threads, rows=(y0, y0 + band_rows), run_post=False)
+        c = ofr.counters()
+        rays += c["primary"] + c["closest"] + c["any"]
+        secs += ofr.rt_seconds()
+    return rays, secs
+
+
+def reference_arm(args):
+    """--impl reference: the reference-semantics CPU port on all host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gknextengine_b200 import GkcuFrameParams, host
+
+    scene = host.Scene(SCENE, samples=SPP * args.gpus, bounces=BOUNCES, taa=True, temporal_frames=16, denoiser=True)
+    scene.update_nodes()
+    sky = host.make_sky(1024, 512)
+    params = GkcuFrameParams(temporal_frames=16, spp_world=1)
+    cores = os.cpu_count() or 1
+    bands, band_rows = 8, 8  # 64 of 1080 rows per step
+    total_rays, total_s = 0, 0.0
+    for step in range(args.warmup + args.steps):
+        ubo = scene.ubo(WIDTH, HEIGHT, step + 1)
+        rays, secs = cpu_port_sample(scene, sky, ubo, params, bands, band_rows)
+        if step >= args.warmup:
+            total_rays += rays
+            total_s += secs
+    value = total_rays / total_s / 1e6
+    sample = f"{bands} bands x {band_rows} rows of the {WIDTH}x{HEIGHT} frame per step, rt pass only"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n):
+    return {"workload": f"BASELINE configs[1]: RayTracingInOneWeekend procedural scene (RTIO.proc), {WIDTH}x{HEIGHT}, {SPP} spp per GPU "
+                        f"({SPP * n} spp/frame), {BOUNCES} bounces, procedural sky stand-in, steady state, temporal reproject + bilateral denoise",
+            "scene": SCENE, "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_per_frame": SPP * n, "bounces": BOUNCES,
+            "parallelism": f"spp-split x{n}, scene replica per GPU" if n > 1 else "single GPU",
+            "l2": "working set (path state 160 B/px + storage images 122 B/px = 585 MB) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--tracer", type=int, default=0, help="0 wavefront (default), 1 megakernel")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from gknextengine_b200 import RT, CudaPathTracingRenderer, GkcuFrameParams, host
+    from gknextengine_b200._abi import GkNodeProxy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene = host.Scene(SCENE, samples=SPP * world, bounces=BOUNCES, taa=True, temporal_frames=16, denoiser=True)
+    scene.update_nodes()  # steady state: combinedPrevTS = identity, MOTIONMOMENT stays 0
+    sky = host.make_sky(1024, 512)
+    r = CudaPathTracingRenderer(local_rank)
+    r.CreateSwapChain((WIDTH, HEIGHT))
+    r.OnPostLoadScene(scene, sky)
+    ext = torch.cuda.ExternalStream(r.stream(), device=local_rank)
+    params = GkcuFrameParams(temporal_frames=16, spp_world=world, spp_rank=rank, tracer=args.tracer, skip_post=1 if world > 1 else 0)
+
+    radiance = None
+    if world > 1:
+        ptr, nbytes = r.radiance_buffer()
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+        radiance = torch.as_tensor(_Buf(), device=f"cuda:{local_rank}")
+
+    def frame(total_frames):
+        ubo = scene.ubo(WIDTH, HEIGHT, total_frames)
+        r.PreRender()  # "TLAS Update": the reference rebuilds the TLAS every frame (RayTraceBaseRenderer.cpp:205-218)
+        r.Render(ubo, params)
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.reduce(radiance, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                r.Resolve(ubo, params)
+        return ubo
+
+    def sync_all():
+        r.BeforeNextFrame()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident timing (value)
+    tf = 1
+    for _ in range(args.warmup):
+        frame(tf)
+        tf += 1
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    rays = 0
+    launches = 0
+    kstats = {"trace_ms": 0.0, "shade_ms": 0.0, "tail_ms": 0.0, "primary_ms": 0.0, "trace_launches": 0, "trace_rays": 0, "tail_rays": 0}
+    pass_ms = {"tlas_update_ms": 0.0, "rt_pass_ms": 0.0, "reproject_pass_ms": 0.0, "compose_pass_ms": 0.0}
+    any_rays = closest_rays = primary_rays = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        frame(tf)
+        tf += 1
+        c = r.counters()  # synchronises the stream: the frame is complete
+        k = r.kernel_stats()
+        t = r.timings()
+        rays += c["primary_rays"] + c["closest_hit_rays"] + c["any_hit_rays"]
+        primary_rays += c["primary_rays"]
+        closest_rays += c["closest_hit_rays"]
+        any_rays += c["any_hit_rays"]
+        launches += c["kernel_launches"]
+        for key in kstats:
+            kstats[key] += k[key]
+        for key in pass_ms:
+            pass_ms[key] += t[key]
+    e1.record(ext)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    stats = torch.tensor([ms, float(rays), float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, rays, launches = float(mx[0]), float(sm[1]), float(sm[2])
+    value = rays / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the public API with host buffers (e2e)
+    nodes_ptr, nn = scene.nodes()
+    node_bytes = nn * C.sizeof(GkNodeProxy)
+    pinned_nodes = torch.empty(node_bytes, dtype=torch.uint8, pin_memory=True)
+    pinned_out = torch.empty(WIDTH * HEIGHT * 8, dtype=torch.uint8, pin_memory=True)
+    e2e_rays = 0
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        scene.update_nodes()  # Scene::UpdateNodes on the host (Scene.cpp:410-492)
+        nodes_ptr, nn = scene.nodes()
+        C.memmove(pinned_nodes.data_ptr(), nodes_ptr, node_bytes)
+        r.update_nodes_ptr(pinned_nodes.data_ptr(), nn)  # H2D NodeProxy[]
+        frame(tf)  # H2D UBO inside
+        tf += 1
+        if rank == 0:
+            r.readback_into(RT["DENOISED"], pinned_out.data_ptr(), pinned_out.numel())  # D2H result
+        c = r.counters()
+        e2e_rays += c["primary_rays"] + c["closest_hit_rays"] + c["any_hit_rays"]
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    est = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        mx = est.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = est.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_rays = float(mx[0]), float(sm[1])
+    e2e_value = e2e_rays / e2e_s / 1e6
+
+    if rank == 0:
+        peak, peak_kind = load_peaks()
+        out = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": node_bytes + 784,
+                    "d2h_bytes_per_step": WIDTH * HEIGHT * 8},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "tracer": "wavefront" if args.tracer == 0 else "megakernel",
+            "rays_per_frame": {"primary": primary_rays / args.steps, "closest_hit": closest_rays / args.steps, "any_hit": any_rays / args.steps},
+            "passes_ms_per_frame_rank0": {k: v / args.steps for k, v in pass_ms.items()},
+        }
+        # roofline of the dominant kernel: k_trace in the wavefront tracer, k_tail in the megakernel
+        if args.tracer == 0 and kstats["trace_launches"] > 0:
+            per_launch_ms = kstats["trace_ms"] / kstats["trace_launches"]
+            per_launch_bytes = TRACE_BYTES_PER_RAY * kstats["trace_rays"] / kstats["trace_launches"]
+            kernel, kms, share = "k_trace", kstats["trace_ms"], kstats["trace_ms"] / (ms if world == 1 else max(ms, 1e-9))
+        else:
+            per_launch_ms = kstats["tail_ms"] / args.steps
+            per_launch_bytes = (PAIR_BYTES_CLOSEST * closest_rays + PAIR_BYTES_ANY * any_rays) / args.steps
+            kernel, kms, share = "k_tail", kstats["tail_ms"], kstats["tail_ms"] / ms
+        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(kernel)
+        except Exception:
+            pass
+        out["roofline"] = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": traffic, "launches": kstats["trace_launches"] if kernel == "k_trace" else args.steps,
+                           "avg_launch_ms": per_launch_ms, "share_of_step": share,
+                           "kernels_ms_per_frame_rank0": {k: kstats[k] / args.steps for k in ("primary_ms", "trace_ms", "shade_ms", "tail_ms")}}
+        rt_bytes = (PAIR_BYTES_CLOSEST * closest_rays + PAIR_BYTES_ANY * any_rays + PRIMARY_BYTES_PER_PIXEL * WIDTH * HEIGHT * args.steps * world) / world
+        out["roofline_rt_pass"] = {"achieved": rt_bytes / (pass_ms["rt_pass_ms"] * 1e-3) / 1e9 if pass_ms["rt_pass_ms"] else 0.0, "unit": "GB/s",
+                                   "note": "SURVEY 8d bytes (436 B/closest-hit ray, 100 B/any-hit ray, 38 B/pixel) over the whole rt pass, rank 0"}
+        px = WIDTH * HEIGHT
+        out["roofline_stencils"] = {
+            "reproject": {"achieved": REPROJECT_BYTES_PER_PIXEL * px * args.steps / (pass_ms["reproject_pass_ms"] * 1e-3) / 1e9 if pass_ms["reproject_pass_ms"] else 0.0,
+                          "bytes_per_pixel": REPROJECT_BYTES_PER_PIXEL},
+            "denoise": {"achieved": DENOISE_BYTES_PER_PIXEL * px * args.steps / (pass_ms["compose_pass_ms"] * 1e-3) / 1e9 if pass_ms["compose_pass_ms"] else 0.0,
+                        "bytes_per_pixel": DENOISE_BYTES_PER_PIXEL},
+            "unit": "GB/s", "peak": peak}
+        if world == 1 and not args.no_cpu_baseline:
+            ubo = scene.ubo(WIDTH, HEIGHT, 1)
+            p1 = GkcuFrameParams(temporal_frames=16, spp_world=1)
+            bands, band_rows = 8, 16
+            crays, csecs = cpu_port_sample(scene, sky, ubo, p1, bands, band_rows)
+            out["cpu_baseline"] = {"value": crays / csecs / 1e6, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": f"{bands} bands x {band_rows} rows of the {WIDTH}x{HEIGHT} frame (rt pass), {csecs:.1f} s of CPU work",
+                                   "ms_per_frame_extrapolated": 1e3 * csecs * HEIGHT / (bands * band_rows)}
+        print(json.dumps(out))
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

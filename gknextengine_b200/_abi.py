@@ -73,6 +73,11 @@ class GkcuCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("primary_rays", "closest_hit_rays", "any_hit_rays", "wavefront_iterations", "kernel_launches")]
 
 
+class GkcuKernelStats(C.Structure):
+    _fields_ = [("primary_ms", C.c_float), ("trace_ms", C.c_float), ("shade_ms", C.c_float), ("tail_ms", C.c_float),
+                ("trace_launches", C.c_uint32), ("shade_launches", C.c_uint32), ("trace_rays", C.c_uint64), ("tail_rays", C.c_uint64)]
+
+
 class GkcuRay(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ox", "oy", "oz", "tmin", "dx", "dy", "dz", "tmax")]
 

@@ -104,6 +104,7 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     c.sm_count = prop.multiProcessorCount;
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
     for (auto& e : c.ev) cudaEventCreate(&e);
+    for (auto& e : c.kev) cudaEventCreate(&e);
     if (!c.ubo.reserve(sizeof(GkUniformBufferObject))) { delete ctx; return 1; }
     *out_ctx = ctx;
     return 0;
@@ -128,6 +129,8 @@ int gkcu_destroy(GkcuContext* ctx) {
                     &s.pos_node_tmp, &s.active, &s.cursors};
     for (DevBuf* b : sb) b->release();
     for (auto& e : c.ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c.kev)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
     delete ctx;
@@ -489,6 +492,15 @@ int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity) {
         out[6 + 4 * m] = c.blas[m].tri_base;
         out[7 + 4 * m] = c.blas[m].prim_count;
     }
+    return 0;
+}
+
+int gkcu_get_kernel_stats(GkcuContext* ctx, GkcuKernelStats* out) {
+    CTX_OR_FAIL(ctx);
+    if (!out) { set_error("null out"); return 1; }
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    fetch_ray_counters(c);
+    *out = c.kstats;
     return 0;
 }
 

@@ -96,6 +96,8 @@ struct Context {
 
     GkcuTimings timings{};
     GkcuCounters counters{};
+    GkcuKernelStats kstats{};
+    cudaEvent_t kev[8] = {};
     cudaEvent_t ev[8] = {};
     uint64_t launches = 0;
     DevBuf trace_rays, trace_hits;

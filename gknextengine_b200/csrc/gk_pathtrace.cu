@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S, RTView R, PathView
     bool want = false;
     uint32_t nprimary = 0;
     if (inside) {
-        const bool owner = cfg.rank == 0 || !cfg.to_radiance;  // rank 0 owns the G-buffer in a multi-GPU frame
+        const bool owner = true;  // every rank keeps its own (identical) G-buffer and MOTIONMOMENT in a multi-GPU frame
         P.rng = make_uint4((uint32_t)x, (uint32_t)y, cfg.frame_seed, 0u);  // InitRandomSeed, Const_Func.slang:237-240
         float4 origin4 = mul(C->ModelViewInverse, f4(0, 0, 0, 1));
         float3 origin = xyz(origin4);
@@ -896,27 +896,48 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     uint32_t* counts = V.counts;
     unsigned long long* ray_counters = reinterpret_cast<unsigned long long*>(counts + 4);
     GK_CUDA(cudaMemsetAsync(counts, 0, 64 * 4, st));
+    GkcuKernelStats ks{};
     dim3 grid((R.w + 7) / 8, (R.h + 15) / 16);
+    cudaEventRecord(c.kev[0], st);
     k_primary<<<grid, 128, 0, st>>>(S, R, V, cfg, ray_counters);
+    cudaEventRecord(c.kev[1], st);
     c.launches++;
     const uint32_t pixels = R.w * R.h;
     const size_t half = pixels;
     const uint32_t persistent_blocks = (uint32_t)c.sm_count * 8u;
     uint64_t iterations = 0;
     int qi = 0;
+    bool pending = false;  // kev[2..4] hold the previous wave's trace/shade brackets
+    auto collect = [&]() {
+        if (!pending) return;
+        float a = 0, bms = 0;
+        cudaEventElapsedTime(&a, c.kev[2], c.kev[3]);
+        cudaEventElapsedTime(&bms, c.kev[3], c.kev[4]);
+        ks.trace_ms += a;
+        ks.shade_ms += bms;
+        pending = false;
+    };
     if (p.tracer == 0) {
         // wavefront loop while the wave is wide; k_tail finishes the thin tail in one launch
         const uint32_t tail_threshold = std::max<uint32_t>(pixels / 64, (uint32_t)c.sm_count * 128u);
         for (;;) {
             GK_CUDA(cudaMemcpyAsync(b.host_counts, counts + qi, 4, cudaMemcpyDeviceToHost, st));
             GK_CUDA(cudaStreamSynchronize(st));
+            collect();
             const uint32_t n = b.host_counts[0];
             if (n <= tail_threshold) break;
             GK_CUDA(cudaMemsetAsync(counts + 2, 0, 4, st));
             GK_CUDA(cudaMemsetAsync(counts + (qi ^ 1), 0, 4, st));
             const uint32_t blocks = std::min<uint32_t>((n + 127) / 128, persistent_blocks);
+            cudaEventRecord(c.kev[2], st);
             k_trace<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
+            cudaEventRecord(c.kev[3], st);
             k_shade<<<blocks, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+            cudaEventRecord(c.kev[4], st);
+            pending = true;
+            ks.trace_launches++;
+            ks.shade_launches++;
+            ks.trace_rays += n;
             c.launches += 2;
             qi ^= 1;
             ++iterations;
@@ -924,9 +945,12 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     }
     {
         const uint32_t blocks = std::min<uint32_t>((pixels + 127) / 128, (uint32_t)c.sm_count * 16u);
+        cudaEventRecord(c.kev[5], st);
         k_tail<<<blocks, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+        cudaEventRecord(c.kev[6], st);
         c.launches++;
     }
+    c.kstats = ks;
     GK_CUDA(cudaMemcpyAsync(b.host_counts + 8, ray_counters, 24, cudaMemcpyDeviceToHost, st));
     c.counters.wavefront_iterations = iterations;
     GK_CUDA(cudaGetLastError());
@@ -940,6 +964,11 @@ void fetch_ray_counters(Context& c) {
     c.counters.primary_rays = h[0];
     c.counters.closest_hit_rays = h[1];
     c.counters.any_hit_rays = h[2];
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.kev[0], c.kev[1]) == cudaSuccess) c.kstats.primary_ms = ms;
+    if (cudaEventElapsedTime(&ms, c.kev[5], c.kev[6]) == cudaSuccess) c.kstats.tail_ms = ms;
+    cudaGetLastError();
+    c.kstats.tail_rays = h[1] + h[2] - c.kstats.trace_rays;
 }
 
 int run_resolve(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {

@@ -16,7 +16,7 @@ import os
 
 import numpy as np
 
-from ._abi import (HIT_DTYPE, RAY_DTYPE, RT, RT_FORMAT, GkcuCounters, GkcuFrameParams, GkcuSceneDesc, GkcuTimings, GkMaterial,
+from ._abi import (HIT_DTYPE, RAY_DTYPE, RT, RT_FORMAT, GkcuCounters, GkcuKernelStats, GkcuFrameParams, GkcuSceneDesc, GkcuTimings, GkMaterial,
                    GkNodeProxy, GkUniformBufferObject)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -59,6 +59,7 @@ def lib():
         L.gkcu_synchronize.argtypes = [P]
         L.gkcu_get_timings.argtypes = [P, C.POINTER(GkcuTimings)]
         L.gkcu_get_counters.argtypes = [P, C.POINTER(GkcuCounters)]
+        L.gkcu_get_kernel_stats.argtypes = [P, C.POINTER(GkcuKernelStats)]
         L.gkcu_stream.restype = C.c_uint64
         L.gkcu_stream.argtypes = [P]
         L.gkcu_trace_rays.argtypes = [P, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
@@ -176,6 +177,18 @@ class CudaPathTracingRenderer:
         c = GkcuCounters()
         _ck(lib().gkcu_get_counters(self._ctx, C.byref(c)))
         return {n: getattr(c, n) for n, _ in GkcuCounters._fields_}
+
+    def kernel_stats(self):
+        k = GkcuKernelStats()
+        _ck(lib().gkcu_get_kernel_stats(self._ctx, C.byref(k)))
+        return {n: getattr(k, n) for n, _ in GkcuKernelStats._fields_}
+
+    def readback_into(self, rt, ptr, nbytes):
+        """Blocking device->host copy into caller-owned (e.g. pinned) host memory."""
+        _ck(lib().gkcu_readback(self._ctx, rt, ptr, nbytes))
+
+    def update_nodes_ptr(self, ptr, count):
+        _ck(lib().gkcu_update_nodes(self._ctx, C.cast(ptr, C.POINTER(GkNodeProxy)), count))
 
     def stream(self):
         return lib().gkcu_stream(self._ctx)

@@ -245,6 +245,17 @@ typedef struct GkcuTimings {   /* names follow the reference's GPU timer scopes 
     float blas_refit_ms;       /* last gkcu_blas_refit */
 } GkcuTimings;
 
+typedef struct GkcuKernelStats { /* device time of the rt-pass kernels of the last frame, CUDA events on the context stream */
+    float primary_ms;          /* k_primary: primary visibility + G-buffer */
+    float trace_ms;            /* sum over k_trace launches (persistent-thread BVH traversal) */
+    float shade_ms;            /* sum over k_shade launches */
+    float tail_ms;             /* k_tail */
+    uint32_t trace_launches;
+    uint32_t shade_launches;
+    uint64_t trace_rays;       /* rays traversed by the k_trace launches (closest + any) */
+    uint64_t tail_rays;
+} GkcuKernelStats;
+
 typedef struct GkcuCounters {  /* exact ray counts of the last frame */
     uint64_t primary_rays;
     uint64_t closest_hit_rays;
@@ -331,6 +342,7 @@ int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity);
 int gkcu_synchronize(GkcuContext* ctx);
 int gkcu_get_timings(GkcuContext* ctx, GkcuTimings* out);
 int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out);
+int gkcu_get_kernel_stats(GkcuContext* ctx, GkcuKernelStats* out);
 /* cudaStream_t of the context as an integer handle, for callers that time with events or enqueue collectives. */
 uint64_t gkcu_stream(GkcuContext* ctx);
 

@@ -779,6 +779,7 @@ struct GkoFrame {
     std::vector<float> motion;  // RG32F
     std::vector<float> prev_depth;
     std::vector<uint16_t> moment;
+    std::vector<float> radiance;  // multi-GPU split: FinalColor | FinalReflection | direct planes (float4 per pixel)
     std::atomic<uint64_t> primary_rays{0}, closest_rays{0}, any_rays{0};
     double rt_seconds = 0;
 
@@ -1174,6 +1175,7 @@ struct Renderer {  // FPathTracingRendererV2, Shading.slang:995-1261, configured
 void RenderPixel(const GkoScene& S, GkoFrame& F, const GkUniformBufferObject& ubo, const GkcuFrameParams& P, int x, int y) {
     const uint32_t world = std::max(1u, P.spp_world);
     size_t o = (size_t)y * F.w + x;
+    const bool single_rank = P.skip_post != 0;  // trace only rank P.spp_rank and leave sums in F.radiance
     // Util.BufferClear.comp.slang:5-14
     F.store4(F.single_diffuse, x, y, F4(0, 0, 0, 0));
     F.store4(F.single_specular, x, y, F4(0, 0, 0, 0));
@@ -1182,15 +1184,17 @@ void RenderPixel(const GkoScene& S, GkoFrame& F, const GkUniformBufferObject& ub
     int sample = 1;
     bool sampled = false, hit = false;
     for (uint32_t r = 0; r < world; ++r) {
+        if (single_rank && r != P.spp_rank) continue;
         Renderer R(S, F, ubo);
         R.Init(x, y, world == 1 ? ubo.TotalFrames : ubo.TotalFrames * world + r);
-        bool rhit = R.PrimaryHit(r == 0);  // rank 0 owns the G-buffer and the direct term
-        if (r == 0) { hit = rhit; direct = R.direct_; }
+        bool rhit = R.PrimaryHit(r == 0 || single_rank);  // every rank keeps its own (identical) G-buffer; rank 0 owns the direct term
+        if (r == 0 || single_rank) { hit = rhit; direct = R.direct_; }
         if (rhit) {
             int sampleMultiplier = F.moment[o] > 0 ? 4 : 1;  // Core.PathTracing.comp.slang:28
             sample = std::max(1, (int)ubo.NumberOfSamples / R.SampleDownscale * sampleMultiplier);
             int s0 = (int)((uint64_t)r * sample / world), s1 = (int)((uint64_t)(r + 1) * sample / world);
             bool rsampled = R.RenderSamples(s0, s1, FinalColor, FinalReflection);
+            if (single_rank && r != 0) sampled = rsampled;
             if (r == 0) {
                 sampled = rsampled;
                 // world == 1: exactly Shading.slang:1178-1180 (the RNG has consumed all samples by now)
@@ -1200,6 +1204,18 @@ void RenderPixel(const GkoScene& S, GkoFrame& F, const GkUniformBufferObject& ub
         F.primary_rays += R.n_primary;
         F.closest_rays += R.n_closest;
         F.any_rays += R.n_any;
+    }
+    if (single_rank) {
+        const size_t n = (size_t)F.w * F.h;
+        float* rc = &F.radiance[o * 4];
+        float* rr = &F.radiance[(n + o) * 4];
+        float* rd = &F.radiance[(2 * n + o) * 4];
+        f4 z = F4(0, 0, 0, 0);
+        f4 c = (hit && sampled) ? FinalColor : z, rf = (hit && sampled) ? FinalReflection : z, d = P.spp_rank == 0 ? direct : z;
+        rc[0] = c.x; rc[1] = c.y; rc[2] = c.z; rc[3] = c.w;
+        rr[0] = rf.x; rr[1] = rf.y; rr[2] = rf.z; rr[3] = rf.w;
+        rd[0] = d.x; rd[1] = d.y; rd[2] = d.z; rd[3] = d.w;
+        return;
     }
     if (!hit) {  // Shading.slang:1195 writes only SINGLE_DIFFUSE
         F.store4(F.single_diffuse, x, y, direct);
@@ -1344,15 +1360,20 @@ void DenoisePixel(GkoFrame& F, const GkUniformBufferObject& Camera, int dx, int 
     }
 }
 
+// Work items are 64-pixel row segments handed out by an atomic counter, so even a 1-row band uses every core.
 template <class Fn>
-void parallel_rows(uint32_t y0, uint32_t y1, int threads, Fn fn) {
+void parallel_pixels(uint32_t y0, uint32_t y1, uint32_t width, int threads, Fn fn) {
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    std::atomic<uint32_t> next{y0};
+    const uint32_t seg = 64, segs_per_row = (width + seg - 1) / seg;
+    const uint64_t total = (uint64_t)(y1 > y0 ? y1 - y0 : 0) * segs_per_row;
+    std::atomic<uint64_t> next{0};
     auto worker = [&]() {
         for (;;) {
-            uint32_t y = next.fetch_add(4);
-            if (y >= y1) break;
-            for (uint32_t yy = y; yy < std::min(y + 4, y1); ++yy) fn((int)yy);
+            uint64_t i = next.fetch_add(1);
+            if (i >= total) break;
+            int y = (int)(y0 + i / segs_per_row);
+            uint32_t x0 = (uint32_t)(i % segs_per_row) * seg;
+            for (uint32_t x = x0; x < std::min(x0 + seg, width); ++x) fn((int)x, y);
         }
     };
     std::vector<std::thread> pool;
@@ -1426,16 +1447,17 @@ GkoFrame* gko_frame_create(uint32_t w, uint32_t h) {
     f->motion.assign(n * 2, 0.f);
     f->prev_depth.assign(n, 0.f);
     f->moment.assign(n, 0);
+    f->radiance.assign(n * 12, 0.f);
     return f;
 }
 void gko_frame_destroy(GkoFrame* f) { delete f; }
 
 int gko_reproject(GkoFrame* f, const GkcuFrameParams* params) {
-    parallel_rows(0, f->h, 0, [&](int y) { for (int x = 0; x < (int)f->w; ++x) ReProjectPixel(*f, *params, x, y); });
+    parallel_pixels(0, f->h, f->w, 0, [&](int x, int y) { ReProjectPixel(*f, *params, x, y); });
     return 0;
 }
 int gko_denoise(GkoFrame* f, const GkUniformBufferObject* ubo) {
-    parallel_rows(0, f->h, 0, [&](int y) { for (int x = 0; x < (int)f->w; ++x) DenoisePixel(*f, *ubo, x, y); });
+    parallel_pixels(0, f->h, f->w, 0, [&](int x, int y) { DenoisePixel(*f, *ubo, x, y); });
     return 0;
 }
 void gko_end_frame_copies(GkoFrame* f) {  // PathTracingRenderer.cpp:160-182, VulkanBaseRenderer.cpp:1136-1152
@@ -1452,11 +1474,11 @@ int gko_render_frame(GkoScene* s, GkoFrame* f, const GkUniformBufferObject* ubo,
     f->closest_rays = 0;
     f->any_rays = 0;
     auto t0 = std::chrono::steady_clock::now();
-    parallel_rows(y0, y1, threads, [&](int y) { for (int x = 0; x < (int)f->w; ++x) RenderPixel(*s, *f, *ubo, *params, x, y); });
+    parallel_pixels(y0, y1, f->w, threads, [&](int x, int y) { RenderPixel(*s, *f, *ubo, *params, x, y); });
     f->rt_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (run_post) {
-        parallel_rows(0, f->h, threads, [&](int y) { for (int x = 0; x < (int)f->w; ++x) ReProjectPixel(*f, *params, x, y); });
-        parallel_rows(0, f->h, threads, [&](int y) { for (int x = 0; x < (int)f->w; ++x) DenoisePixel(*f, *ubo, x, y); });
+        parallel_pixels(0, f->h, f->w, threads, [&](int x, int y) { ReProjectPixel(*f, *params, x, y); });
+        parallel_pixels(0, f->h, f->w, threads, [&](int x, int y) { DenoisePixel(*f, *ubo, x, y); });
         gko_end_frame_copies(f);
     }
     return 0;
@@ -1496,8 +1518,9 @@ void gko_get_counters(GkoFrame* f, GkcuCounters* out) {
 double gko_last_rt_seconds(GkoFrame* f) { return f->rt_seconds; }
 
 void gko_trace_rays(GkoScene* s, const GkcuRay* rays, uint32_t count, GkcuHit* hits, uint32_t any_hit) {
-    parallel_rows(0, (count + 255) / 256, 0, [&](int blk) {
-        for (uint32_t i = blk * 256u; i < std::min(count, blk * 256u + 256u); ++i) {
+    parallel_pixels(0, 1, count, 0, [&](int xi, int) {
+        {
+            const uint32_t i = (uint32_t)xi;
             const GkcuRay& r = rays[i];
             if (any_hit) {
                 bool occ = s->occluded(F3(r.ox, r.oy, r.oz), F3(r.dx, r.dy, r.dz), r.tmin, r.tmax);
@@ -1528,5 +1551,21 @@ void gko_random_in_hemisphere1(uint32_t seed[4], float out[3]) {
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 float gko_schlick(float cosine, float ior) { return Schlick(cosine, ior); }
+void gko_det_sincos(float x, float* s, float* c) { gk_det_sincosf(x, s, c); }
+float* gko_radiance(GkoFrame* f, size_t* floats) { if (floats) *floats = f->radiance.size(); return f->radiance.data(); }
+void gko_resolve(GkoFrame* f, const GkUniformBufferObject* ubo) {
+    const size_t n = (size_t)f->w * f->h;
+    for (size_t o = 0; o < n; ++o) {
+        int x = (int)(o % f->w), y = (int)(o / f->w);
+        int sample = std::max(1, (int)ubo->NumberOfSamples * (f->moment[o] > 0 ? 4 : 1));
+        const float* rc = &f->radiance[o * 4];
+        const float* rr = &f->radiance[(n + o) * 4];
+        const float* rd = &f->radiance[(2 * n + o) * 4];
+        f4 fc = F4(rc[0], rc[1], rc[2], rc[3]) / float(sample), fr = F4(rr[0], rr[1], rr[2], rr[3]) / float(sample);
+        fc = fc + F4(rd[0], rd[1], rd[2], rd[3]);
+        f->store4(f->single_diffuse, x, y, fc);
+        f->store4(f->single_specular, x, y, fr);
+    }
+}
 
 }  // extern "C"

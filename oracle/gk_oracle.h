@@ -63,6 +63,13 @@ void gko_gt_tonemap(const float in[3], float out[3]);
 void gko_ggx_sampling(uint32_t seed[4], float roughness, const float normal[3], float out[3]);
 void gko_random_in_hemisphere1(uint32_t seed[4], float out[3]);
 float gko_schlick(float cosine, float ior);
+void gko_det_sincos(float x, float* s, float* c);
+
+/* Multi-GPU sample split: with params.skip_post = 1 gko_render_frame traces only rank params.spp_rank's samples and
+ * leaves the un-normalised sums in the radiance buffer: 2 planes of W*H float4 (FinalColor, FinalReflection) followed by the
+ * direct-term plane (rank 0 only, zero elsewhere). gko_resolve turns (summed) planes into SINGLE_DIFFUSE / SINGLE_SPECULAR. */
+float* gko_radiance(GkoFrame* f, size_t* floats);
+void gko_resolve(GkoFrame* f, const GkUniformBufferObject* ubo);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,45 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def _ensure_built():
+    pkg = os.path.join(ROOT, "gknextengine_b200")
+    need = [os.path.join(pkg, "libgknext_cuda.so"), os.path.join(pkg, "libgknext_host.so"), os.path.join(ROOT, "oracle", "liboracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+_ensure_built()
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def sky():
+    from gknextengine_b200 import host
+    return host.make_sky(256, 128)
+
+
+@pytest.fixture()
+def renderer():
+    from gknextengine_b200 import CudaPathTracingRenderer
+    r = CudaPathTracingRenderer(0)
+    yield r
+    r.close()

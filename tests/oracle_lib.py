@@ -53,6 +53,10 @@ def load(path=NATIVE):
     L.gko_gt_tonemap.argtypes = [C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3)]
     L.gko_ggx_sampling.argtypes = [C.POINTER(C.c_uint32 * 4), C.c_float, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3)]
     L.gko_random_in_hemisphere1.argtypes = [C.POINTER(C.c_uint32 * 4), C.POINTER(C.c_float * 3)]
+    L.gko_det_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.gko_radiance.restype = C.POINTER(C.c_float)
+    L.gko_radiance.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    L.gko_resolve.argtypes = [C.c_void_p, C.POINTER(GkUniformBufferObject)]
     L.gko_schlick.restype = C.c_float
     L.gko_schlick.argtypes = [C.c_float, C.c_float]
     _libs[path] = L
@@ -125,6 +129,15 @@ class OracleFrame:
         buf = (C.c_char * n.value).from_address(p)
         a = np.frombuffer(buf, dtype=dtype)
         return a.reshape(self.h, self.w, ch) if ch > 1 else a.reshape(self.h, self.w)
+
+    def radiance(self):
+        """Writable view of the multi-GPU radiance planes: (3, H, W, 4) float32 = FinalColor sums, FinalReflection sums, direct."""
+        n = C.c_size_t()
+        p = self.L.gko_radiance(self._h, C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).reshape(3, self.h, self.w, 4)
+
+    def resolve(self, ubo):
+        self.L.gko_resolve(self._h, C.byref(ubo))
 
     def counters(self):
         c = GkcuCounters()

@@ -1,0 +1,388 @@
+"""GPU parity: libgknext_cuda.so (through its C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact ids / G-buffer; radiance images bit-exact except where the sky lookup's atan2/acos (libm vs CUDA) flips an
+fp16 rounding (stated per test); RT_DENOISED within 2 fp16 ulps (pow/exp differ between libms)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from gknextengine_b200 import RT, CudaPathTracingRenderer, GkcuError, GkcuFrameParams, host
+from gknextengine_b200.bvh_check import validate
+from helpers import check_frame, half_ulp_diff, mismatch_fraction, random_rays, rel_rmse, setup_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def params(**kw):
+    d = dict(temporal_frames=16, spp_world=1)
+    d.update(kw)
+    return GkcuFrameParams(**d)
+
+
+@pytest.mark.parametrize("tracer", [0, 1])
+def test_config1_cornell_box_ids_and_radiance(renderer, tracer):
+    """BASELINE config 1: Cornell box 640x360, 1 spp, 4 bounces, fixed seed. Ids bit-exact (budget 1e-4), radiance relative
+    RMSE <= 2 % after N accumulated frames (it is in fact bit-exact frame by frame)."""
+    W, H = 640, 360
+    scene = host.Scene("CornellBox.proc", samples=1, bounces=4, taa=False)
+    scene.update_nodes()
+    osc, ofr = setup_pair(renderer, scene, W, H)
+    p = params(tracer=tracer)
+    acc_g, acc_c = np.zeros((H, W, 3)), np.zeros((H, W, 3))
+    for f in range(1, 9):
+        ubo = scene.ubo(W, H, f)
+        renderer.Render(ubo, p)
+        renderer.BeforeNextFrame()
+        ofr.render(osc, ubo, p)
+        rep = check_frame(renderer, ofr, exact_fraction=1e-4, radiance_fraction=1e-4)
+        gc, oc = renderer.counters(), ofr.counters()
+        assert (gc["primary_rays"], gc["closest_hit_rays"], gc["any_hit_rays"]) == (oc["primary"], oc["closest"], oc["any"])
+        acc_g += renderer.readback(RT["SINGLE_DIFFUSE"]).astype(np.float64)[..., :3]
+        acc_c += ofr.image(RT["SINGLE_DIFFUSE"]).astype(np.float64)[..., :3]
+    assert rel_rmse(acc_g, acc_c) <= 0.02
+    assert rep["OBJEDCTID_0"] == 0.0
+
+
+@pytest.mark.parametrize("builder", ["lbvh", "sah"])
+def test_rtiow_sky_multi_bounce(monkeypatch, sky, builder):
+    """RTIOW (1939 instances, dielectric / metallic / lambertian spheres, sky): both BLAS builders."""
+    monkeypatch.setenv("GKCU_BLAS_BUILDER", builder)
+    r = CudaPathTracingRenderer(0)
+    try:
+        W, H = 480, 270
+        scene = host.Scene("RTIO.proc", samples=4, bounces=8, taa=True, denoiser=True)
+        scene.update_nodes()
+        osc, ofr = setup_pair(r, scene, W, H, sky)
+        p = params()
+        for f in (1, 2):
+            ubo = scene.ubo(W, H, f)
+            r.Render(ubo, p)
+            r.BeforeNextFrame()
+            ofr.render(osc, ubo, p)
+            check_frame(r, ofr, exact_fraction=0.0, radiance_fraction=2e-3)
+            gc, oc = r.counters(), ofr.counters()
+            assert (gc["closest_hit_rays"], gc["any_hit_rays"]) == (oc["closest"], oc["any"])
+        rep = validate(r)
+        assert rep["tlas"]["all_instances_once"] and rep["tlas"]["violations"] == 0
+        assert all(v["violations"] == 0 and v["all_tris_once"] and v["prim_ids_are_permutation"] for k, v in rep.items() if k.startswith("blas"))
+    finally:
+        r.close()
+
+
+def test_sun_shadow_rays_and_wavefront_equals_megakernel(sky):
+    """Sun on: the bounce-loop NEE ray and DirectIlluminate's shadow ray (Shading.slang:1135-1144, 886-908) are any-hit
+    queries. The wavefront and megakernel drivers must agree bit for bit."""
+    W, H = 320, 180
+    scene = host.Scene("RTIO.proc", samples=3, bounces=5, taa=False)
+    scene.env(True, True)
+    scene.update_nodes()
+    imgs = []
+    for tracer in (0, 1):
+        r = CudaPathTracingRenderer(0)
+        osc, ofr = setup_pair(r, scene, W, H, sky)
+        ubo = scene.ubo(W, H, 5)
+        r.Render(ubo, params(tracer=tracer))
+        r.BeforeNextFrame()
+        ofr.render(osc, ubo, params())
+        check_frame(r, ofr, radiance_fraction=2e-3)
+        gc, oc = r.counters(), ofr.counters()
+        assert gc["any_hit_rays"] == oc["any"] > W * H // 2
+        imgs.append((r.readback(RT["SINGLE_DIFFUSE"]), r.readback(RT["SINGLE_SPECULAR"])))
+        r.close()
+    assert np.array_equal(imgs[0][0], imgs[1][0]) and np.array_equal(imgs[0][1], imgs[1][1])
+
+
+def test_first_frame_motion_moment_quadruples_samples(renderer):
+    """Right after a scene load every node reports motion (Node.cpp:154-171): MOTIONMOMENT = TemporalFrames and the sample
+    count is multiplied by 4 (Core.PathTracing.comp.slang:28); history is rejected by ReProject."""
+    W, H = 200, 120
+    scene = host.Scene("CornellBox.proc", samples=1, bounces=4, taa=False)  # no update_nodes(): first-frame proxies
+    osc, ofr = setup_pair(renderer, scene, W, H)
+    ubo = scene.ubo(W, H, 1)
+    renderer.Render(ubo, params())
+    renderer.BeforeNextFrame()
+    ofr.render(osc, ubo, params())
+    check_frame(renderer, ofr)
+    mm = renderer.readback(RT["MOTIONMOMENT"])
+    ids = renderer.readback(RT["OBJEDCTID_0"])
+    assert (mm[ids != 65535] == 16).all() and (mm[ids == 65535] == 0).all()
+    one = host.Scene("CornellBox.proc", samples=1, bounces=4, taa=False)
+    one.update_nodes()
+    r2 = CudaPathTracingRenderer(0)
+    r2.CreateSwapChain((W, H))
+    r2.OnPostLoadScene(one)
+    r2.Render(one.ubo(W, H, 1), params())
+    assert renderer.counters()["closest_hit_rays"] > 3 * r2.counters()["closest_hit_rays"]
+    r2.close()
+
+
+def test_temporal_sequence_with_camera_orbit(renderer, sky):
+    """BASELINE config 3 shape (1 spp/frame, TAA jitter, TemporalFrames 16, bilateral denoise, orbiting camera) on the RTIOW
+    stand-in: every frame's history / accumulation / denoised output against the oracle."""
+    W, H = 320, 180
+    scene = host.Scene("RTIO.proc", samples=1, bounces=4, taa=True, temporal_frames=16, denoiser=True)
+    scene.update_nodes()
+    osc, ofr = setup_pair(renderer, scene, W, H, sky)
+    p = params()
+    for f in range(1, 7):
+        ubo = scene.ubo(W, H, f, model_rotation_deg=(f / 60.0) * 20.0)  # gkNextMotionBenchmark: SetModelRotation(t * 20)
+        renderer.Render(ubo, p)
+        renderer.BeforeNextFrame()
+        ofr.render(osc, ubo, p)
+        check_frame(renderer, ofr, radiance_fraction=5e-3)
+    mv = renderer.readback(RT["MOTIONVECTOR"])
+    assert np.abs(mv).max() > 0.05  # the orbit produces real motion vectors
+
+
+def test_progressive_mode(renderer):
+    W, H = 160, 90
+    scene = host.Scene("CornellBox.proc", samples=1, bounces=4, taa=False)
+    scene.update_nodes()
+    osc, ofr = setup_pair(renderer, scene, W, H)
+    p = params(progressive=1)
+    for f in (1, 2, 3):
+        ubo = scene.ubo(W, H, f, progressive=True)
+        renderer.Render(ubo, p)
+        renderer.BeforeNextFrame()
+        ofr.render(osc, ubo, p)
+        check_frame(renderer, ofr)
+
+
+def test_depth_of_field_and_fast_gather_with_probes(renderer):
+    """Aperture > 0 exercises the CoC re-cast of the primary ray (Shading.slang:368-489); FastGather exercises the ambient-cube
+    path termination (:1120-1123, AmbientCube.slang:290-382) with synthetic probe data."""
+    import ctypes as C
+    from gknextengine_b200._abi import GkUniformBufferObject
+    from gknextengine_b200.renderer import _ck, lib
+    W, H = 240, 136
+    scene = host.Scene("CornellBox.proc", samples=2, bounces=4, taa=False, fast_gather=True)
+    scene.camera(aperture=0.3, focal_distance=9.0)
+    scene.update_nodes()
+    osc, ofr = setup_pair(renderer, scene, W, H)
+    n = 192 * 192 * 48
+    rng = np.random.default_rng(3)
+    cubes = rng.integers(0, 2 ** 32, size=(n, 14), dtype=np.uint32)
+    voxels = rng.integers(0, 2 ** 32, size=(n, 4), dtype=np.uint32)
+    _ck(lib().gkcu_set_probes(renderer._ctx, cubes.ctypes.data, voxels.ctypes.data))
+    osc.L.gko_set_probes(osc._h, cubes.ctypes.data, voxels.ctypes.data)
+    ubo = scene.ubo(W, H, 3)
+    renderer.Render(ubo, params())
+    renderer.BeforeNextFrame()
+    ofr.render(osc, ubo, params())
+    rep = check_frame(renderer, ofr, exact_fraction=1e-4, radiance_fraction=1e-3)
+    assert renderer.counters()["primary_rays"] > W * H  # CoC re-casts happened
+    sd = renderer.readback(RT["SINGLE_DIFFUSE"]).astype(np.float32)
+    assert sd[..., :3].max() > 0
+
+
+def test_stencil_passes_on_random_inputs(renderer):
+    """ReProject + DenoiseJBF alone on random storage-image contents (incl. out-of-bounds history fetches, id mismatches,
+    non-zero moments): ACCUM_* bit-exact, RT_DENOISED within 2 fp16 ulps."""
+    W, H = 203, 117  # not a multiple of the tile sizes
+    scene = host.Scene("CornellBox.proc", denoiser=True)
+    renderer.CreateSwapChain((W, H))
+    ofr = O.OracleFrame(W, H)
+    rng = np.random.default_rng(11)
+
+    def rnd16(hi=4.0):
+        return rng.uniform(0, hi, (H, W, 4)).astype(np.float16)
+
+    ids0 = rng.integers(0, 4, (H, W)).astype(np.uint32)
+    ids0[rng.uniform(size=(H, W)) < 0.05] = 65535
+    ids1 = np.where(rng.uniform(size=(H, W)) < 0.8, ids0, rng.integers(0, 4, (H, W))).astype(np.uint32)
+    nrm = rng.normal(size=(H, W, 4)).astype(np.float32)
+    nrm[..., :3] /= np.linalg.norm(nrm[..., :3], axis=2, keepdims=True)
+    nrm[::2] = np.float32([0, 1, 0, 0.3])  # coherent rows so that the 5x5 filter finds neighbours
+    images = {
+        "SINGLE_DIFFUSE": rnd16(), "SINGLE_SPECULAR": rnd16(), "ALBEDO": rnd16(1.0), "NORMAL": nrm.astype(np.float16),
+        "SINGLE_PREV_DIFFUSE": rnd16(), "SINGLE_PREV_SPECULAR": rnd16(), "SINGLE_PREV_ALBEDO": rnd16(1.0),
+        "OBJEDCTID_0": ids0, "OBJEDCTID_1": ids1,
+        "MOTIONVECTOR": np.where(rng.uniform(size=(H, W, 1)) < 0.5, 0, rng.uniform(-6, 6, (H, W, 2))).astype(np.float32),
+        "MOTIONMOMENT": (rng.uniform(size=(H, W)) < 0.1).astype(np.uint16) * 3,
+    }
+    for mode in (dict(progressive=0, temporal_frames=16), dict(progressive=0, temporal_frames=1), dict(progressive=1, temporal_frames=16),
+                 dict(progressive=0, temporal_frames=8, fast_reproject=1)):
+        for name, arr in images.items():
+            renderer.upload_image(RT[name], arr)
+            ofr.image(RT[name])[...] = arr
+        p = params(**mode)
+        for hdr in (False, True):
+            s2 = host.Scene("CornellBox.proc", denoiser=True, hdr=hdr)
+            ubo = s2.ubo(W, H, 1)
+            for name, arr in images.items():
+                renderer.upload_image(RT[name], arr)
+                ofr.image(RT[name])[...] = arr
+            renderer.run_post(ubo, p)
+            renderer.BeforeNextFrame()
+            ofr.reproject(p)
+            ofr.denoise(ubo)
+            ofr.end_frame_copies()
+            for name in ("ACCUMLATE_DIFFUSE", "ACCUMLATE_SPECULAR", "ACCUMLATE_ALBEDO"):
+                g, c = renderer.readback(RT[name]), ofr.image(RT[name])
+                assert np.array_equal(g.view(np.uint16), c.view(np.uint16)), (name, mode)
+            ulps = half_ulp_diff(renderer.readback(RT["DENOISED"]), ofr.image(RT["DENOISED"]))
+            assert ulps.max() <= 2, (mode, hdr, int(ulps.max()))
+            # the swap: next frame's history is this frame's accumulation
+            renderer.upload_image(RT["SINGLE_DIFFUSE"], images["SINGLE_DIFFUSE"])
+
+
+def test_trace_rays_edge_cases(renderer):
+    scene = host.Scene("CornellBox.proc")
+    scene.update_nodes()
+    osc, _ = setup_pair(renderer, scene, 64, 64)
+    assert len(renderer.trace(random_rays(0))) == 0  # empty
+    rays = random_rays(50000, seed=9, center=(0, 2.7, 0))
+    # axis-parallel and degenerate directions, rays starting on surfaces, tiny and huge intervals
+    rays["dx"][:1000], rays["dy"][:1000], rays["dz"][:1000] = 0, -1, 0
+    rays["dx"][1000:2000], rays["dy"][1000:2000], rays["dz"][1000:2000] = 1, 0, 0
+    rays["oy"][2000:3000] = 0.0
+    rays["tmax"][3000:4000] = 0.5
+    rays["tmin"][4000:5000] = 2.0
+    rays["dx"][5000:5100], rays["dy"][5000:5100], rays["dz"][5000:5100] = 0, 0, 0  # zero direction (refract() can return it)
+    hg, hc = renderer.trace(rays), osc.trace(rays)
+    for k in ("inst", "prim"):
+        assert np.array_equal(hg[k], hc[k]), k
+    assert np.array_equal(hg["t"].view(np.uint32), hc["t"].view(np.uint32))
+    assert np.array_equal(hg["u"].view(np.uint32), hc["u"].view(np.uint32))
+    ag, ac = renderer.trace(rays, any_hit=True), osc.trace(rays, any_hit=True)
+    assert np.array_equal(ag["inst"], ac["inst"])
+
+
+def test_blas_refit_and_dynamic_tlas(renderer):
+    """BASELINE config 4 shape at test size: instances move every frame (full TLAS rebuild) and one brick model is deformed
+    (BLAS refit). Hits must equal the oracle's (which rebuilds from scratch) and a refit must equal a rebuild."""
+    scene = host.Scene("LegoBricks.synth:4000")
+    scene.update_nodes()
+    osc, _ = setup_pair(renderer, scene, 64, 64)
+    rays = random_rays(40000, seed=4, center=(0, 1.5, 0), spread=8.0)
+    rays["dy"] = -np.abs(rays["dy"])
+    for step in range(1, 4):
+        scene.jitter_instances(step, 0.01)
+        scene.update_nodes()
+        renderer.AfterUpdateScene(scene)
+        osc.update_nodes(scene)
+        model = 1 + step
+        sv = scene.perturb_model(model, step)
+        renderer.refit_model(model, sv)
+        osc.refit_model(model, sv)
+        renderer.PreRender()
+        hg, hc = renderer.trace(rays), osc.trace(rays)
+        assert np.array_equal(hg["inst"], hc["inst"]) and np.array_equal(hg["prim"], hc["prim"])
+        assert np.array_equal(hg["t"].view(np.uint32), hc["t"].view(np.uint32))
+        rep = validate(renderer)
+        assert rep[f"blas{model}"]["violations"] == 0 and rep["tlas"]["all_instances_once"]
+    t = renderer.timings()
+    assert t["blas_refit_ms"] > 0 and t["tlas_update_ms"] > 0
+
+
+def test_invisible_and_nort_nodes_are_masked(renderer):
+    scene = host.Scene("CornellBox.proc")
+    scene.update_nodes()
+    osc, _ = setup_pair(renderer, scene, 64, 64)
+    import ctypes as C
+    from gknextengine_b200._abi import GkNodeProxy
+    nodes, n = scene.nodes()
+    arr = (GkNodeProxy * n)(*[nodes[i] for i in range(n)])
+    arr[1].visible = 0  # the sphere disappears
+    arr[2].nort = 1     # the box is a non-zero section: not in the TLAS
+    renderer.update_nodes_ptr(C.addressof(arr), n)
+    osc.L.gko_update_nodes(osc._h, arr, n)
+    rays = random_rays(20000, seed=2, center=(0, 2.7, 0))
+    hg, hc = renderer.trace(rays), osc.trace(rays)
+    assert np.array_equal(hg["inst"], hc["inst"])
+    assert set(np.unique(hg["inst"])) <= {0, 0xFFFFFFFF}
+
+
+def test_spp_split_across_two_contexts_matches_oracle(sky):
+    """The multi-GPU sample split emulated with two contexts on one GPU: each rank traces its half of the samples
+    (skip_post), the radiance buffers are summed, rank 0 resolves. Must equal the oracle's simulation of both ranks."""
+    import torch
+    W, H, world = 256, 144, 2
+    scene = host.Scene("RTIO.proc", samples=6, bounces=5, taa=False)
+    scene.update_nodes()
+    ubo = scene.ubo(W, H, 9)
+    rs, bufs = [], []
+    for rank in range(world):
+        r = CudaPathTracingRenderer(0)
+        r.CreateSwapChain((W, H))
+        r.OnPostLoadScene(scene, sky)
+        r.Render(ubo, params(spp_world=world, spp_rank=rank, skip_post=1))
+        r.BeforeNextFrame()
+        ptr, nbytes = r.radiance_buffer()
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+        rs.append(r)
+        bufs.append(torch.as_tensor(_Buf(), device="cuda:0"))
+    bufs[0] += bufs[1]
+    torch.cuda.synchronize()
+    rs[0].Resolve(ubo, params(spp_world=world, spp_rank=0))
+    rs[0].BeforeNextFrame()
+    osc, ofr = O.OracleScene(scene, sky), O.OracleFrame(W, H)
+    ofr.render(osc, ubo, params(spp_world=world))
+    for name in ("SINGLE_DIFFUSE", "SINGLE_SPECULAR", "OBJEDCTID_0", "ALBEDO"):
+        assert mismatch_fraction(rs[0].readback(RT[name]), ofr.image(RT[name])) <= 2e-3, name
+    ulps = half_ulp_diff(rs[0].readback(RT["DENOISED"]), ofr.image(RT["DENOISED"]))
+    assert float((ulps > 2).any(axis=2).mean()) <= 2e-3
+    for r in rs:
+        r.close()
+
+
+def test_full_size_properties_1080p(sky):
+    """BASELINE config 2 at full size (1920x1080, 16 spp, 8 bounces): size-independent properties — determinism, exact ray
+    accounting, wavefront == megakernel, finite output — plus oracle parity on sampled rows."""
+    W, H = 1920, 1080
+    scene = host.Scene("RTIO.proc", samples=16, bounces=8, taa=True, denoiser=True)
+    scene.update_nodes()
+    ubo = scene.ubo(W, H, 1)
+    out = []
+    for tracer in (0, 0, 1):
+        r = CudaPathTracingRenderer(0)
+        r.CreateSwapChain((W, H))
+        r.OnPostLoadScene(scene, sky)
+        r.Render(ubo, params(tracer=tracer))
+        r.BeforeNextFrame()
+        c = r.counters()
+        assert c["primary_rays"] == W * H
+        out.append((r.readback(RT["SINGLE_DIFFUSE"]), r.readback(RT["DENOISED"]), c["closest_hit_rays"], r.readback(RT["OBJEDCTID_0"])))
+        r.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])  # deterministic
+    assert np.array_equal(out[0][0], out[2][0]) and out[0][2] == out[2][2]                # wavefront == megakernel
+    assert np.isfinite(out[0][1].astype(np.float32)).all()
+    hit = out[0][3] != 65535
+    assert 16 * hit.sum() <= out[0][2] <= 16 * 8 * hit.sum()
+    # oracle parity on 3 bands of 4 rows
+    osc, ofr = O.OracleScene(scene, sky), O.OracleFrame(W, H)
+    for y0 in (200, 600, 1000):
+        ofr.render(osc, ubo, params(), rows=(y0, y0 + 4), run_post=False)
+        g, c = out[0][0][y0:y0 + 4], ofr.image(RT["SINGLE_DIFFUSE"])[y0:y0 + 4]
+        assert mismatch_fraction(g, c) <= 5e-3
+        assert np.array_equal(out[0][3][y0:y0 + 4], ofr.image(RT["OBJEDCTID_0"])[y0:y0 + 4])
+
+
+def test_error_handling(renderer):
+    """Errors come back as return codes + messages (no exceptions across the C ABI)."""
+    import ctypes as C
+    from gknextengine_b200.renderer import lib
+    L = lib()
+    scene = host.Scene("CornellBox.proc")
+    ubo = scene.ubo(64, 64, 1)
+    p = params()
+    assert L.gkcu_render_frame(renderer._ctx, C.byref(ubo), C.byref(p)) != 0 and b"gkcu_resize" in L.gkcu_last_error()
+    renderer.CreateSwapChain((64, 64))
+    assert L.gkcu_render_frame(renderer._ctx, C.byref(ubo), C.byref(p)) != 0 and b"blas" in L.gkcu_last_error().lower()
+    with pytest.raises(GkcuError):
+        renderer.PreRender()
+    renderer.OnPostLoadScene(scene)
+    buf = np.zeros(16, dtype=np.uint8)
+    assert L.gkcu_readback(renderer._ctx, RT["DENOISED"], buf.ctypes.data, buf.nbytes) != 0
+    assert L.gkcu_readback(renderer._ctx, 99, buf.ctypes.data, buf.nbytes) != 0
+    with pytest.raises(GkcuError):
+        renderer.refit_model(1, np.zeros(8, dtype=np.uint16))  # wrong vertex count
+    with pytest.raises(GkcuError):
+        renderer.Render(ubo, params(spp_world=2, spp_rank=5))
+    assert L.gkcu_resize(renderer._ctx, 0, 10) != 0
+    renderer.Render(ubo, p)  # still usable after errors
+    renderer.BeforeNextFrame()
+    assert renderer.counters()["primary_rays"] == 64 * 64

@@ -1,0 +1,132 @@
+"""Pins the oracle's intersector against the reference's own vendored tinybvh (compiled from /root/reference into
+oracle/_ref/liboracle_tinybvh.so, same oracle source with -DGKO_TINYBVH) and checks frame-level invariants of the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from gknextengine_b200 import RT, GkcuFrameParams, host
+from helpers import random_rays
+
+need_ref = pytest.mark.skipif(not os.path.exists(O.TINYBVH), reason="oracle/_ref not built (reference not mounted)")
+
+
+@need_ref
+@pytest.mark.parametrize("name,center", [("CornellBox.proc", (0, 2.7, 0)), ("RTIO.proc", (0, 3, 0))])
+def test_native_intersector_matches_tinybvh(name, center):
+    s = host.Scene(name)
+    s.update_nodes()
+    a, b = O.OracleScene(s), O.OracleScene(s, lib_path=O.TINYBVH)
+    assert O.load(O.TINYBVH).gko_intersector_name() == b"tinybvh-1.3.8"
+    rays = random_rays(20000, seed=3, center=center)
+    ha, hb = a.trace(rays), b.trace(rays)
+    # coplanar surfaces of different instances (the Cornell tall box stands on the floor) are genuine ties: the oracle commits
+    # the lower instance id, tinybvh whichever it meets first. Anything that is not a tie must agree.
+    differ = ha["inst"] != hb["inst"]
+    tie = differ & (ha["inst"] != 0xFFFFFFFF) & (hb["inst"] != 0xFFFFFFFF) & (np.abs(ha["t"] - hb["t"]) <= 1e-4 * np.maximum(1.0, ha["t"]))
+    assert (differ & ~tie).mean() <= 1e-4
+    same = ha["inst"] == hb["inst"]
+    hit = same & (ha["inst"] != 0xFFFFFFFF)
+    assert (ha["prim"][hit] != hb["prim"][hit]).mean() <= 2e-3  # shared edges: Moeller-Trumbore vs watertight pick either side
+    assert np.abs(ha["t"][hit] - hb["t"][hit]).max() < 2e-3
+    oa, ob = a.trace(rays, any_hit=True), b.trace(rays, any_hit=True)
+    assert (oa["inst"] != ob["inst"]).mean() <= 1e-4
+
+
+@need_ref
+def test_primary_ids_match_tinybvh_on_config1():
+    """BASELINE config 1 (Cornell box 640x360): primary-hit instance ids, <= 1e-4 mismatching (triangle edges)."""
+    s = host.Scene("CornellBox.proc", samples=1, bounces=4, taa=False)
+    s.update_nodes()
+    p = GkcuFrameParams(temporal_frames=16, spp_world=1)
+    ubo = s.ubo(640, 360, 1)
+    imgs = []
+    for path in (O.NATIVE, O.TINYBVH):
+        sc, fr = O.OracleScene(s, lib_path=path), O.OracleFrame(640, 360, lib_path=path)
+        fr.render(sc, ubo, p, run_post=False)
+        imgs.append((fr.image(RT["OBJEDCTID_0"]).copy(), fr.image(RT["EXT_PRIMITIVEID"]).copy()))
+    assert (imgs[0][0] != imgs[1][0]).mean() <= 1e-4
+    assert (imgs[0][1] != imgs[1][1]).mean() <= 1e-3
+
+
+def test_oracle_frame_invariants():
+    s = host.Scene("CornellBox.proc", samples=2, bounces=4, taa=False)
+    s.update_nodes()
+    W, H = 160, 90
+    sc, fr = O.OracleScene(s), O.OracleFrame(W, H)
+    p = GkcuFrameParams(temporal_frames=16, spp_world=1)
+    ubo = s.ubo(W, H, 1)
+    fr.render(sc, ubo, p)
+    ids = fr.image(RT["OBJEDCTID_0"]).copy()
+    sd = fr.image(RT["SINGLE_DIFFUSE"]).astype(np.float32)
+    c = fr.counters()
+    assert c["primary"] == W * H and c["any"] == 0 and c["closest"] >= 2 * (ids != 65535).sum() * 0.9
+    assert set(np.unique(ids)) <= {0, 1, 2, 65535}
+    assert (sd[ids == 65535] == 0).all()  # no sky in the Cornell box
+    prim = fr.image(RT["EXT_PRIMITIVEID"])
+    light = (ids == 0) & (prim >= 10) & (prim < 12)  # the two light triangles
+    assert light.sum() > 50 and (sd[light][:, :3] == 2000.0).all()
+    # determinism and frame seeding
+    fr2 = O.OracleFrame(W, H)
+    fr2.render(sc, ubo, p)
+    assert np.array_equal(fr2.image(RT["SINGLE_DIFFUSE"]), fr.image(RT["SINGLE_DIFFUSE"]))
+    fr2.render(sc, s.ubo(W, H, 2), p)
+    assert not np.array_equal(fr2.image(RT["SINGLE_DIFFUSE"]), fr.image(RT["SINGLE_DIFFUSE"]))
+    # after the copy pass PREV == ACCUM and OBJECTID_1 == OBJECTID_0
+    assert np.array_equal(fr.image(RT["SINGLE_PREV_DIFFUSE"]), fr.image(RT["ACCUMLATE_DIFFUSE"]))
+    assert np.array_equal(fr.image(RT["OBJEDCTID_1"]), fr.image(RT["OBJEDCTID_0"]))
+
+
+def test_reproject_properties():
+    W, H = 48, 32
+    fr = O.OracleFrame(W, H)
+    rng = np.random.default_rng(5)
+    cur = rng.uniform(0, 4, (H, W, 4)).astype(np.float16)
+    prev = rng.uniform(0, 4, (H, W, 4)).astype(np.float16)
+    fr.image(RT["SINGLE_DIFFUSE"])[:] = cur
+    fr.image(RT["SINGLE_PREV_DIFFUSE"])[:] = prev
+    # progressive: exact lerp(prev, cur, 1/512) on all four channels (Process.ReProject.comp.slang:95-101)
+    fr.reproject(GkcuFrameParams(progressive=1, temporal_frames=16))
+    expect = (prev.astype(np.float32) + (cur.astype(np.float32) - prev.astype(np.float32)) * np.float32(1 / 512)).astype(np.float16)
+    assert np.array_equal(fr.image(RT["ACCUMLATE_DIFFUSE"]), expect)
+    # a miss (object id 65535) never uses history: ACCUM = current
+    fr.image(RT["OBJEDCTID_0"])[:] = 65535
+    fr.reproject(GkcuFrameParams(progressive=0, temporal_frames=16))
+    assert np.array_equal(fr.image(RT["ACCUMLATE_DIFFUSE"]), cur)
+    # static uniform scene: history valid, constant colour stays constant
+    fr.image(RT["OBJEDCTID_0"])[:] = 3
+    fr.image(RT["OBJEDCTID_1"])[:] = 3
+    fr.image(RT["NORMAL"])[:] = np.float16([0, 1, 0, 0.5])
+    fr.image(RT["SINGLE_DIFFUSE"])[:] = np.float16([0.5, 0.25, 0.125, 1])
+    fr.image(RT["SINGLE_PREV_DIFFUSE"])[:] = np.float16([0.5, 0.25, 0.125, 1])
+    fr.reproject(GkcuFrameParams(progressive=0, temporal_frames=16))
+    inner = fr.image(RT["ACCUMLATE_DIFFUSE"])[4:-4, 4:-4, :3].astype(np.float32)
+    assert np.abs(inner - np.float32([0.5, 0.25, 0.125])).max() < 1e-3
+    # MOTIONMOMENT > 0 disables history
+    fr.image(RT["MOTIONMOMENT"])[:] = 2
+    fr.image(RT["SINGLE_PREV_DIFFUSE"])[:] = 0
+    fr.reproject(GkcuFrameParams(progressive=0, temporal_frames=16))
+    assert np.array_equal(fr.image(RT["ACCUMLATE_DIFFUSE"]), fr.image(RT["SINGLE_DIFFUSE"]))
+
+
+def test_denoise_properties():
+    W, H = 40, 24
+    s = host.Scene("CornellBox.proc", denoiser=True)
+    ubo = s.ubo(W, H, 1)
+    fr = O.OracleFrame(W, H)
+    fr.image(RT["ACCUMLATE_DIFFUSE"])[:] = np.float16([0.5, 0.5, 0.5, 1])
+    fr.image(RT["ACCUMLATE_ALBEDO"])[:] = np.float16([0.5, 1.0, 0.25, 1])
+    fr.image(RT["ACCUMLATE_SPECULAR"])[:] = np.float16([0.125, 0, 0, 1])
+    fr.denoise(ubo)
+    out = fr.image(RT["DENOISED"]).astype(np.float32)
+    assert (out[..., 3] == 1).all()
+    inner = out[6:-6, 6:-6, :3]
+    assert np.ptp(inner.reshape(-1, 3), axis=0).max() == 0  # uniform input -> uniform output away from the border
+    # filter off: plain modulate + tonemap, identical everywhere including the border
+    s2 = host.Scene("CornellBox.proc", denoiser=False)
+    fr.denoise(s2.ubo(W, H, 1))
+    out2 = fr.image(RT["DENOISED"]).astype(np.float32)
+    assert np.ptp(out2.reshape(-1, 4), axis=0).max() == 0
+    # the 0.001 fetch bias of the filtered path makes it slightly brighter than the unfiltered one
+    assert (inner[0, 0] >= out2[0, 0, :3]).all()
