@@ -212,6 +212,10 @@ def test_stencil_passes_on_random_inputs(renderer):
             for name, arr in images.items():
                 renderer.upload_image(RT[name], arr)
                 ofr.image(RT[name])[...] = arr
+            # invariant of a real frame sequence: after the copy pass ACCUM_* == PREV_* (the ".rgb =" stores keep ACCUM's alpha)
+            for acc, prev in (("ACCUMLATE_DIFFUSE", "SINGLE_PREV_DIFFUSE"), ("ACCUMLATE_SPECULAR", "SINGLE_PREV_SPECULAR"),
+                              ("ACCUMLATE_ALBEDO", "SINGLE_PREV_ALBEDO")):
+                ofr.image(RT[acc])[...] = images[prev]
             renderer.run_post(ubo, p)
             renderer.BeforeNextFrame()
             ofr.reproject(p)
@@ -347,9 +351,12 @@ def test_full_size_properties_1080p(sky):
         assert c["primary_rays"] == W * H
         out.append((r.readback(RT["SINGLE_DIFFUSE"]), r.readback(RT["DENOISED"]), c["closest_hit_rays"], r.readback(RT["OBJEDCTID_0"])))
         r.close()
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])  # deterministic
-    assert np.array_equal(out[0][0], out[2][0]) and out[0][2] == out[2][2]                # wavefront == megakernel
-    assert np.isfinite(out[0][1].astype(np.float32)).all()
+    bits = lambda a: a.view(np.uint16)  # compare bit patterns: NaN == NaN
+    assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and np.array_equal(bits(out[0][1]), bits(out[1][1]))  # deterministic
+    assert np.array_equal(bits(out[0][0]), bits(out[2][0])) and out[0][2] == out[2][2]                          # wavefront == megakernel
+    # total internal reflection makes refract() return the zero vector, which the reference then traces and looks up in the
+    # sky (Shading.slang:1031-1039, 1077): normalize(0) is NaN. Reproduced, not fixed; it touches a handful of pixels.
+    assert (~np.isfinite(out[0][1].astype(np.float32))).any(axis=2).mean() < 1e-4
     hit = out[0][3] != 65535
     assert 16 * hit.sum() <= out[0][2] <= 16 * 8 * hit.sum()
     # oracle parity on 3 bands of 4 rows
