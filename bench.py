@@ -327,7 +327,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             ubo = scene.ubo(WIDTH, HEIGHT, 1)
             p1 = GkcuFrameParams(temporal_frames=16, spp_world=1)
-            bands, band_rows = 8, 16
+            bands, band_rows = 27, 40  # the whole frame: ~10 s of CPU work on a 16-core host
             crays, csecs = cpu_port_sample(scene, sky, ubo, p1, bands, band_rows)
             out["cpu_baseline"] = {"value": crays / csecs / 1e6, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
                                    "sample": f"{bands} bands x {band_rows} rows of the {WIDTH}x{HEIGHT} frame (rt pass), {csecs:.1f} s of CPU work",

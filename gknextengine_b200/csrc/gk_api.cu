@@ -3,6 +3,7 @@
 // entry point either runs the sm_100a kernels or fails.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -102,6 +103,8 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     Context& c = ctx->c;
     c.device = device_ordinal;
     c.sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("GKCU_TRACE_VARIANT")) c.trace_variant = atoi(e);
+    if (const char* e = getenv("GKCU_REFILL")) c.refill_below = std::max(1, std::min(32, atoi(e)));
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
     for (auto& e : c.ev) cudaEventCreate(&e);
     for (auto& e : c.kev) cudaEventCreate(&e);
@@ -121,7 +124,7 @@ int gkcu_destroy(GkcuContext* ctx) {
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
                       &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
-                      &c.inst_hi, &c.tex_table, &c.cubes, &c.voxels, &c.ubo, &c.trace_rays, &c.trace_hits};
+                      &c.inst_hi, &c.tlas_active_ids, &c.tex_table, &c.cubes, &c.voxels, &c.ubo, &c.trace_rays, &c.trace_hits};
     for (DevBuf* b : bufs) b->release();
     BuildScratch& s = c.scratch;
     DevBuf* sb[] = {&s.prim_lo, &s.prim_hi, &s.keys, &s.keys_sorted, &s.order, &s.order_tmp, &s.sort_tmp, &s.n2_lo, &s.n2_hi, &s.n2_left, &s.n2_right,
@@ -217,7 +220,8 @@ int gkcu_update_nodes(GkcuContext* ctx, const GkNodeProxy* nodes, uint32_t count
     if (count) GK_CUDA(cudaMemcpyAsync(c.nodes.p, nodes, (size_t)count * sizeof(GkNodeProxy), cudaMemcpyHostToDevice, c.stream));
     c.node_count = count;
     // instances that make it into the TLAS (mask != 0, RayTraceBaseRenderer.cpp:178)
-    uint32_t active = 0;
+    std::vector<uint32_t> ids;
+    ids.reserve(count);
     for (uint32_t i = 0; i < count; ++i) {
         uint32_t blas = nodes[i].modelId / 10;
         bool a = nodes[i].visible && !nodes[i].nort && blas < c.model_count;
@@ -226,8 +230,11 @@ int gkcu_update_nodes(GkcuContext* ctx, const GkNodeProxy* nodes, uint32_t count
             for (int s = 0; s < 10; ++s) idx += c.host_offsets[blas * 10 + s].indexCount;
             if (idx / 3 == 0) a = false;
         }
-        active += a ? 1 : 0;
+        if (a) ids.push_back(i);
     }
+    const uint32_t active = (uint32_t)ids.size();
+    if (!c.tlas_active_ids.reserve(std::max<size_t>(1, ids.size()) * 4)) return 1;
+    if (active) GK_CUDA(cudaMemcpyAsync(c.tlas_active_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c.stream));
     c.tlas.prim_count = active;
     c.tlas_dirty = true;
     GK_CUDA(cudaStreamSynchronize(c.stream));  // the caller may reuse its array
@@ -248,12 +255,13 @@ int gkcu_update_materials(GkcuContext* ctx, const GkMaterial* materials, uint32_
 int gkcu_tlas_build(GkcuContext* ctx) {
     CTX_OR_FAIL(ctx);
     if (!c.blas_built) { set_error("gkcu_tlas_build: call gkcu_blas_build first"); return 1; }
-    cudaEventRecord(c.ev[0], c.stream);
+    cudaEventRecord(c.kev[7], c.stream);
     int r = build_tlas(c);
-    cudaEventRecord(c.ev[1], c.stream);
+    cudaEventRecord(c.ev[7], c.stream);
     if (r) return r;
     GK_CUDA(cudaStreamSynchronize(c.stream));
-    cudaEventElapsedTime(&c.timings.tlas_update_ms, c.ev[0], c.ev[1]);
+    cudaEventElapsedTime(&c.timings.tlas_update_ms, c.kev[7], c.ev[7]);
+    c.frame_built_tlas = false;
     return 0;
 }
 
@@ -305,6 +313,7 @@ int gkcu_render_frame(GkcuContext* ctx, const GkUniformBufferObject* ubo, const 
     if (frame_prologue(c, ubo, params)) return 1;
     cudaStream_t st = c.stream;
     cudaEventRecord(c.ev[0], st);
+    c.frame_built_tlas = c.tlas_dirty;
     if (c.tlas_dirty && build_tlas(c)) return 1;  // RayTraceBaseRenderer::PreRender "TLAS Update"
     cudaEventRecord(c.ev[1], st);
     if (run_rt_pass(c, *ubo, *params)) return 1;
@@ -437,7 +446,7 @@ int gkcu_get_timings(GkcuContext* ctx, GkcuTimings* out) {
     if (!out) { set_error("null out"); return 1; }
     GK_CUDA(cudaStreamSynchronize(c.stream));
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]) == cudaSuccess) c.timings.tlas_update_ms = ms;
+    if (c.frame_built_tlas && cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]) == cudaSuccess) c.timings.tlas_update_ms = ms;
     if (cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]) == cudaSuccess) c.timings.rt_pass_ms = ms;
     if (cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]) == cudaSuccess) c.timings.reproject_pass_ms = ms;
     if (cudaEventElapsedTime(&ms, c.ev[3], c.ev[4]) == cudaSuccess) c.timings.compose_pass_ms = ms;

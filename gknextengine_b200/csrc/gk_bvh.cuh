@@ -133,119 +133,152 @@ GK_DEV void node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint
     }
 }
 
-#define GK_CSWAP(a, b)                                                     \
-    {                                                                      \
-        bool sw = tn[b] < tn[a];                                           \
-        float tt = sw ? tn[a] : tn[b];                                     \
-        tn[a] = sw ? tn[b] : tn[a];                                        \
-        tn[b] = tt;                                                        \
-        uint32_t rr = sw ? ref[a] : ref[b];                                \
-        ref[a] = sw ? ref[b] : ref[a];                                     \
-        ref[b] = rr;                                                       \
-    }
+// ---------------------------------------------------------------------------------------------------------------------
+// Traversal state machine. One ray per lane; the same three steps serve the simple per-ray loop (trace_ray) and the
+// persistent-thread kernel (k_trace), which interleaves them "while-while" style so that a warp runs node steps together
+// and leaf steps together, and refills finished lanes with new rays.
+struct Trav {
+    float3 o, d;       // world-space ray
+    float3 ro, rd;     // current-space ray (world or object)
+    float3 idir;
+    float tmin, tmax;
+    Hit best;
+    RayShear sh;
+    const uint4* nodes;
+    const float4* tris;
+    uint32_t cur;      // current node reference
+    uint32_t cur_inst; // GK_NO_HIT while in the TLAS
+    int sp;
+    bool any;          // first-hit query
+    bool done;
+};
 
-// Closest hit (ANY = false) or first hit (ANY = true; best.inst != GK_NO_HIT means occluded).
+GK_DEV void trav_init(Trav& T, const TraceScene& S, float3 o, float3 d, float tmin, float tmax, bool any) {
+    T.o = o; T.d = d; T.ro = o; T.rd = d;
+    T.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+    T.tmin = tmin; T.tmax = tmax;
+    T.best.t = tmax; T.best.u = 0.0f; T.best.v = 0.0f; T.best.inst = GK_NO_HIT; T.best.prim = 0;
+    T.sh.kx = T.sh.ky = T.sh.kz = 0;
+    T.sh.Sx = T.sh.Sy = T.sh.Sz = 0.0f;
+    T.nodes = reinterpret_cast<const uint4*>(S.tlas);
+    T.tris = S.tris;
+    T.cur = 0;
+    T.cur_inst = GK_NO_HIT;
+    T.sp = 0;
+    T.any = any;
+    T.done = S.tlas_nodes == 0;
+}
+
+// Pops the next node to visit (culling entries that are already farther than the best hit); leaves instances on sentinels.
+GK_DEV void trav_pop(Trav& T, const TraceScene& S, uint2* stack) {
+    for (;;) {
+        if (T.sp == 0) { T.done = true; return; }
+        const uint2 e = stack[--T.sp];
+        if (e.x == GK_STACK_SENTINEL) {
+            T.ro = T.o;
+            T.rd = T.d;
+            T.idir = f3(safe_rcp(T.rd.x), safe_rcp(T.rd.y), safe_rcp(T.rd.z));
+            T.nodes = reinterpret_cast<const uint4*>(S.tlas);
+            T.cur_inst = GK_NO_HIT;
+            continue;
+        }
+        if (__uint_as_float(e.y) > T.best.t) continue;
+        T.cur = e.x;
+        return;
+    }
+}
+
+// Internal node: test the 4 children, continue with the nearest, push the others (second nearest on top).
+GK_DEV void trav_node_step(Trav& T, const TraceScene& S, uint2* stack) {
+    const uint4* np = T.nodes + (size_t)T.cur * 4;
+    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+    float tn[4];
+    node_test(n0, n1, n2, n3, T.ro, T.idir, T.tmin, T.best.t, tn);
+    const uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
+    const float inf = __int_as_float(0x7f800000);
+    // nearest child
+    int i0 = 0;
+    float t0 = tn[0];
+    if (tn[1] < t0) { t0 = tn[1]; i0 = 1; }
+    if (tn[2] < t0) { t0 = tn[2]; i0 = 2; }
+    if (tn[3] < t0) { t0 = tn[3]; i0 = 3; }
+    if (!(t0 < inf)) { trav_pop(T, S, stack); return; }
+    // second nearest goes on top of the stack, the rest below it in index order
+    int i1 = -1;
+    float t1 = inf;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c != i0 && tn[c] < t1) { t1 = tn[c]; i1 = c; }
+    if (i1 >= 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c != i0 && c != i1 && tn[c] < inf) stack[T.sp++] = make_uint2(ref[c], __float_as_uint(tn[c]));
+        stack[T.sp++] = make_uint2(ref[i1], __float_as_uint(t1));
+    }
+    T.cur = ref[i0];
+}
+
+// Leaf: a TLAS leaf enters the instance's BLAS in object space (t is preserved by the affine map); a BLAS leaf tests triangles.
+GK_DEV void trav_leaf_step(Trav& T, const TraceScene& S, uint2* stack) {
+    if (T.cur_inst == GK_NO_HIT) {
+        const uint32_t ii = T.cur & 0x0FFFFFFFu;
+        const float4* ir = reinterpret_cast<const float4*>(S.inst + ii);
+        const float4 r0 = __ldg(ir), r1 = __ldg(ir + 1), r2 = __ldg(ir + 2);
+        const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ir) + 3);
+        if (meta.z) {
+            const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+            T.ro = xform_point(m, T.o);
+            T.rd = xform_vec(m, T.d);
+            T.idir = f3(safe_rcp(T.rd.x), safe_rcp(T.rd.y), safe_rcp(T.rd.z));
+            T.sh = make_shear(T.rd);
+            stack[T.sp++] = make_uint2(GK_STACK_SENTINEL, 0u);
+            T.nodes = reinterpret_cast<const uint4*>(S.blas + meta.x);
+            T.tris = S.tris + (size_t)meta.y * 3;
+            T.cur_inst = ii;
+            T.cur = 0;
+            return;
+        }
+    } else {
+        const uint32_t first = T.cur & 0x0FFFFFFFu, count = ((T.cur >> 28) & 7u) + 1u;
+        for (uint32_t i = 0; i < count; ++i) {
+            const float4* tp = T.tris + (size_t)(first + i) * 3;
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            float t, b1, b2;
+            if (!tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), T.ro, T.sh, t, b1, b2)) continue;
+            if (!(t > T.tmin && t < T.tmax)) continue;
+            const uint32_t p = __float_as_uint(a.w);
+            if (T.any) {
+                T.best.t = t;
+                T.best.inst = T.cur_inst;
+                T.best.prim = p;
+                T.done = true;
+                return;
+            }
+            const bool better = T.best.inst == GK_NO_HIT || t < T.best.t ||
+                                (t == T.best.t && (T.cur_inst < T.best.inst || (T.cur_inst == T.best.inst && p < T.best.prim)));
+            if (better) {
+                T.best.t = t;
+                T.best.u = b1;
+                T.best.v = b2;
+                T.best.inst = T.cur_inst;
+                T.best.prim = p;
+            }
+        }
+    }
+    trav_pop(T, S, stack);
+}
+
+// Closest hit (ANY = false) or first hit (ANY = true; best.inst != GK_NO_HIT means occluded): the simple per-ray loop.
 template <bool ANY>
 GK_DEV void trace_ray(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, Hit& best) {
-    best.t = tmax;
-    best.u = 0.0f;
-    best.v = 0.0f;
-    best.inst = GK_NO_HIT;
-    best.prim = 0;
-    if (S.tlas_nodes == 0) return;
-
     uint2 stack[GK_TRAV_STACK];
-    int sp = 0;
-    float3 ro = o, rd = d;
-    float3 idir = f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z));
-    const uint4* nodes = reinterpret_cast<const uint4*>(S.tlas);
-    const float4* tris = S.tris;
-    uint32_t cur_inst = GK_NO_HIT;
-    RayShear sh;
-    sh.kx = sh.ky = sh.kz = 0;
-    sh.Sx = sh.Sy = sh.Sz = 0.0f;
-    uint32_t cur = 0;  // TLAS root
-
-    for (;;) {
-        if (!(cur & GK_LEAF_BIT)) {
-            const uint4* np = nodes + (size_t)cur * 4;
-            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-            float tn[4];
-            node_test(n0, n1, n2, n3, ro, idir, tmin, best.t, tn);
-            uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
-            GK_CSWAP(0, 1) GK_CSWAP(2, 3) GK_CSWAP(0, 2) GK_CSWAP(1, 3) GK_CSWAP(1, 2)
-            const float inf = __int_as_float(0x7f800000);
-            if (tn[0] < inf) {
-                if (tn[3] < inf) stack[sp++] = make_uint2(ref[3], __float_as_uint(tn[3]));
-                if (tn[2] < inf) stack[sp++] = make_uint2(ref[2], __float_as_uint(tn[2]));
-                if (tn[1] < inf) stack[sp++] = make_uint2(ref[1], __float_as_uint(tn[1]));
-                cur = ref[0];
-                continue;
-            }
-        } else if (cur_inst == GK_NO_HIT) {
-            // TLAS leaf: one instance. Enter its BLAS in object space; t is preserved by the affine map.
-            const uint32_t ii = cur & 0x0FFFFFFFu;
-            const InstanceRec* ir = S.inst + ii;
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(ir)), r1 = __ldg(reinterpret_cast<const float4*>(ir) + 1),
-                         r2 = __ldg(reinterpret_cast<const float4*>(ir) + 2);
-            const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ir) + 3);
-            if (meta.z) {
-                const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-                ro = xform_point(m, o);
-                rd = xform_vec(m, d);
-                idir = f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z));
-                sh = make_shear(rd);
-                stack[sp++] = make_uint2(GK_STACK_SENTINEL, 0u);
-                nodes = reinterpret_cast<const uint4*>(S.blas + meta.x);
-                tris = S.tris + (size_t)meta.y * 3;
-                cur_inst = ii;
-                cur = 0;
-                continue;
-            }
-        } else {
-            // BLAS leaf: triangles
-            const uint32_t first = cur & 0x0FFFFFFFu, count = ((cur >> 28) & 7u) + 1u;
-            for (uint32_t i = 0; i < count; ++i) {
-                const float4* tp = tris + (size_t)(first + i) * 3;
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                float t, b1, b2;
-                if (!tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), ro, sh, t, b1, b2)) continue;
-                if (!(t > tmin && t < tmax)) continue;
-                if (ANY) {
-                    best.t = t;
-                    best.inst = cur_inst;
-                    best.prim = __float_as_uint(a.w);
-                    return;
-                }
-                const uint32_t p = __float_as_uint(a.w);
-                const bool better = best.inst == GK_NO_HIT || t < best.t ||
-                                    (t == best.t && (cur_inst < best.inst || (cur_inst == best.inst && p < best.prim)));
-                if (better) {
-                    best.t = t;
-                    best.u = b1;
-                    best.v = b2;
-                    best.inst = cur_inst;
-                    best.prim = p;
-                }
-            }
-        }
-        // pop
-        for (;;) {
-            if (sp == 0) return;
-            const uint2 e = stack[--sp];
-            if (e.x == GK_STACK_SENTINEL) {
-                ro = o;
-                rd = d;
-                idir = f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z));
-                nodes = reinterpret_cast<const uint4*>(S.tlas);
-                cur_inst = GK_NO_HIT;
-                continue;
-            }
-            if (__uint_as_float(e.y) > best.t) continue;
-            cur = e.x;
-            break;
-        }
+    Trav T;
+    trav_init(T, S, o, d, tmin, tmax, ANY);
+    while (!T.done) {
+        if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, S, stack);
+        else trav_leaf_step(T, S, stack);
     }
+    best = T.best;
 }
 
 }  // namespace gkd

@@ -25,7 +25,7 @@ namespace gkcu {
 
 namespace {
 
-constexpr int kBlasLeafMax = 4;
+static int kBlasLeafMax = 2;  // GKCU_LEAF_MAX (1..8); 2 measured best on the sphere/brick meshes (profiles/r01_experiments.md)
 constexpr int kSahBins = 16;
 
 __device__ __forceinline__ int f2o(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
@@ -245,7 +245,7 @@ __device__ __forceinline__ float box_area(float4 lo, float4 hi) {
 __global__ void k_collapse_level(const int2* __restrict__ qin, int nin, int2* __restrict__ qout, int* __restrict__ nout, int* __restrict__ node_counter,
                                  const float4* __restrict__ nlo, const float4* __restrict__ nhi, const int* __restrict__ left,
                                  const int* __restrict__ right, const int* __restrict__ first, const int* __restrict__ count, int leaf_max,
-                                 const uint32_t* __restrict__ order, int tlas_mode, Node4* __restrict__ out, float4* __restrict__ out_lo,
+                                 const uint32_t* __restrict__ order, const uint32_t* __restrict__ remap, int tlas_mode, Node4* __restrict__ out, float4* __restrict__ out_lo,
                                  float4* __restrict__ out_hi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nin) return;
@@ -282,7 +282,7 @@ __global__ void k_collapse_level(const int2* __restrict__ qin, int nin, int2* __
         ch[k].hi = f3(h.x, h.y, h.z);
         if (GK_IS_LEAF2(n2)) {
             uint32_t f = (uint32_t)first[n2];
-            if (tlas_mode) f = order[f];  // TLAS leaves carry the instance index itself
+            if (tlas_mode) f = remap[order[f]];  // TLAS leaves carry the instance index itself
             ch[k].ref = GK_LEAF_BIT | ((uint32_t)(count[n2] - 1) << 28) | f;
         } else {
             int slot = atomicAdd(node_counter, 1);
@@ -354,7 +354,7 @@ __global__ void k_refit_level(Node4* __restrict__ nodes, float4* __restrict__ no
 // atomics on order-encoded floats so the tree is deterministic), picks the SAH-best plane per node, and partitions.
 struct SahBin { int lo[3], hi[3], cnt, pad; };  // 32 B
 
-__global__ void k_sah_init(int n, const int* __restrict__ bounds, float4* nlo, float4* nhi, int* left, int* right, int* first, int* count,
+__global__ void k_sah_init(int leaf_max, int n, const int* __restrict__ bounds, float4* nlo, float4* nhi, int* left, int* right, int* first, int* count,
                            uint32_t* order, int* pos_node, int* active, int* counters) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { order[i] = i; pos_node[i] = 0; }
@@ -366,7 +366,7 @@ __global__ void k_sah_init(int n, const int* __restrict__ bounds, float4* nlo, f
         count[0] = n;
         active[0] = 0;      // active list: node ids; slot s <-> bins[s]
         counters[0] = 1;    // node count
-        counters[1] = (n > kBlasLeafMax) ? 1 : 0;  // active count (this level)
+        counters[1] = (n > leaf_max) ? 1 : 0;  // active count (this level)
         counters[2] = 0;    // active count (next level)
     }
 }
@@ -413,7 +413,7 @@ __global__ void k_sah_bin(int n, const uint32_t* __restrict__ order, const int* 
 
 struct SahSplit { int axis, plane, nl, fallback; };
 
-__global__ void k_sah_split(int nactive, const int* __restrict__ active, const SahBin* __restrict__ bins, float4* nlo, float4* nhi, int* left,
+__global__ void k_sah_split(int leaf_max, int nactive, const int* __restrict__ active, const SahBin* __restrict__ bins, float4* nlo, float4* nhi, int* left,
                             int* right, int* first, int* count, int* counters, int* next_active, SahSplit* splits, int* cursors) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nactive) return;
@@ -483,8 +483,8 @@ __global__ void k_sah_split(int nactive, const int* __restrict__ active, const S
     splits[s] = sp;
     cursors[2 * s] = 0;
     cursors[2 * s + 1] = 0;
-    if (sp.nl > kBlasLeafMax) next_active[atomicAdd(&counters[2], 1)] = c0;
-    if (cnt - sp.nl > kBlasLeafMax) next_active[atomicAdd(&counters[2], 1)] = c0 + 1;
+    if (sp.nl > leaf_max) next_active[atomicAdd(&counters[2], 1)] = c0;
+    if (cnt - sp.nl > leaf_max) next_active[atomicAdd(&counters[2], 1)] = c0 + 1;
 }
 
 __global__ void k_sah_partition(int n, const uint32_t* __restrict__ order, const int* __restrict__ pos_node, const int* __restrict__ slot_of,
@@ -595,6 +595,14 @@ __global__ void k_instances(const GkNodeProxy* __restrict__ nodes, uint32_t n, c
     }
 }
 
+__global__ void k_gather_boxes(const uint32_t* __restrict__ ids, uint32_t m, const float4* __restrict__ lo, const float4* __restrict__ hi,
+                               float4* __restrict__ out_lo, float4* __restrict__ out_hi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    out_lo[i] = lo[ids[i]];
+    out_hi[i] = hi[ids[i]];
+}
+
 inline dim3 grid_for(size_t n, int block = 256) { return dim3((unsigned)((n + block - 1) / block)); }
 
 struct Bvh2 {
@@ -648,10 +656,10 @@ int build_lbvh(Context& c, uint32_t n_total, uint32_t n_active, Bvh2& out) {
 }
 
 // Level-synchronous SAH-binned build over n boxes (all active).
-int build_sah(Context& c, uint32_t n, Bvh2& out) {
+int build_sah(Context& c, uint32_t n, int leaf_max, Bvh2& out) {
     BuildScratch& s = c.scratch;
     cudaStream_t st = c.stream;
-    size_t max_slots = n / (kBlasLeafMax + 1) + 2;
+    size_t max_slots = n / (leaf_max + 1) + 2;
     if (!s.bins.reserve(max_slots * 3 * kSahBins * sizeof(SahBin)) || !s.pos_node.reserve((size_t)n * 4) || !s.pos_node_tmp.reserve((size_t)n * 4) ||
         !s.active.reserve((max_slots * 2 + 4) * 4 * 2) || !s.cursors.reserve(max_slots * 2 * 4 + max_slots * sizeof(SahSplit) + 64))
         return 1;
@@ -668,16 +676,16 @@ int build_sah(Context& c, uint32_t n, Bvh2& out) {
 
     k_init_bounds<<<1, 32, 0, st>>>(s.bounds.as<int>());
     k_bounds<<<grid_for(n), 256, 0, st>>>(s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), n, s.bounds.as<int>());
-    k_sah_init<<<grid_for(n), 256, 0, st>>>((int)n, s.bounds.as<int>(), nlo, nhi, left, right, first, count, ord_a, pn_a, act_a, counters);
+    k_sah_init<<<grid_for(n), 256, 0, st>>>(leaf_max, (int)n, s.bounds.as<int>(), nlo, nhi, left, right, first, count, ord_a, pn_a, act_a, counters);
     k_fill_int<<<grid_for(2 * (size_t)n + 2), 256, 0, st>>>(slot_of, (int)(2 * n + 2), -1);
     c.launches += 4;
-    int nactive = n > (uint32_t)kBlasLeafMax ? 1 : 0;
+    int nactive = n > (uint32_t)leaf_max ? 1 : 0;
     int guard = 0;
     while (nactive > 0 && guard++ < 128) {
         k_mark_slots<<<grid_for(nactive), 256, 0, st>>>(act_a, nactive, slot_of, 0);
         k_sah_clear_bins<<<grid_for((size_t)nactive * 3 * kSahBins), 256, 0, st>>>(s.bins.as<SahBin>(), nactive);
         k_sah_bin<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, s.bins.as<SahBin>());
-        k_sah_split<<<grid_for(nactive, 128), 128, 0, st>>>(nactive, act_a, s.bins.as<SahBin>(), nlo, nhi, left, right, first, count, counters, act_b, splits,
+        k_sah_split<<<grid_for(nactive, 128), 128, 0, st>>>(leaf_max, nactive, act_a, s.bins.as<SahBin>(), nlo, nhi, left, right, first, count, counters, act_b, splits,
                                                       cursors);
         k_sah_partition<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, left, first,
                                                      splits, cursors, ord_b, pn_b);
@@ -700,7 +708,7 @@ int build_sah(Context& c, uint32_t n, Bvh2& out) {
 }
 
 // BVH2 -> Node4 (BFS), returns node count and the level table.
-int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, bool tlas_mode, Node4* out, float4* out_lo, float4* out_hi,
+int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, const uint32_t* remap, Node4* out, float4* out_lo, float4* out_hi,
              WideBvhInfo& info) {
     BuildScratch& s = c.scratch;
     cudaStream_t st = c.stream;
@@ -716,7 +724,7 @@ int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, bool tla
     (void)n_prims;
     while (nin > 0) {
         k_collapse_level<<<grid_for(nin, 128), 128, 0, st>>>(qa, nin, qb, counters + 9, counters + 8, b.lo, b.hi, b.left, b.right, b.first, b.count,
-                                                             leaf_max, b.order, tlas_mode ? 1 : 0, out, out_lo, out_hi);
+                                                             leaf_max, b.order, remap, remap ? 1 : 0, out, out_lo, out_hi);
         c.launches += 1;
         int h[2];
         GK_CUDA(cudaMemcpyAsync(h, counters + 8, 8, cudaMemcpyDeviceToHost, st));
@@ -749,6 +757,7 @@ int build_all_blas(Context& c) {
     cudaStream_t st = c.stream;
     const char* env = getenv("GKCU_BLAS_BUILDER");
     if (env) c.blas_builder = (std::string(env) == "lbvh") ? 0 : 1;
+    if (const char* e = getenv("GKCU_LEAF_MAX")) kBlasLeafMax = std::max(1, std::min(8, atoi(e)));
     c.blas.assign(c.model_count, WideBvhInfo());
     size_t total_prims = 0;
     for (uint32_t m = 0; m < c.model_count; ++m) {
@@ -782,10 +791,10 @@ int build_all_blas(Context& c) {
                                                  s.prim_lo.as<float4>(), s.prim_hi.as<float4>());
         c.launches += 1;
         Bvh2 b2;
-        if (c.blas_builder == 1) { if (build_sah(c, n, b2)) return 1; }
+        if (c.blas_builder == 1) { if (build_sah(c, n, kBlasLeafMax, b2)) return 1; }
         else { if (build_lbvh(c, n, n, b2)) return 1; }
         Node4* out = c.blas_nodes.as<Node4>() + node_base;
-        if (collapse(c, b2, n, kBlasLeafMax, false, out, c.blas_node_lo.as<float4>() + node_base, c.blas_node_hi.as<float4>() + node_base, bi)) return 1;
+        if (collapse(c, b2, n, kBlasLeafMax, nullptr, out, c.blas_node_lo.as<float4>() + node_base, c.blas_node_hi.as<float4>() + node_base, bi)) return 1;
         k_write_tris<<<grid_for(n), 256, 0, st>>>(c.simple.as<uint16_t>(), c.indices.as<uint32_t>(), bi.vertex_offset, bi.index_offset, b2.order, n,
                                                   c.blas_tris.as<float4>() + (size_t)tri_base * 3, c.blas_tri_prim.as<uint32_t>() + tri_base);
         c.launches += 1;
@@ -850,16 +859,23 @@ int build_tlas(Context& c) {
         !reserve_bvh2(s, n) || !c.tlas_nodes.reserve(((size_t)n + 4) * sizeof(Node4)) || !c.tlas_node_lo.reserve(((size_t)n + 4) * 16) ||
         !c.tlas_node_hi.reserve(((size_t)n + 4) * 16))
         return 1;
+    if (!c.inst_lo.reserve((size_t)n * 16) || !c.inst_hi.reserve((size_t)n * 16)) return 1;
     k_instances<<<grid_for(n, 128), 128, 0, st>>>(c.nodes.as<GkNodeProxy>(), n, c.blas_table.as<uint4>(), c.model_count, c.instances.as<InstanceRec>(),
-                                             s.prim_lo.as<float4>(), s.prim_hi.as<float4>());
+                                             c.inst_lo.as<float4>(), c.inst_hi.as<float4>());
     c.launches += 1;
-    // count active instances: they sort in front of the inactive ones (key 0x7FFF...)
-    // cheap host-side count from the node proxies we were given
-    uint32_t n_active = c.tlas.prim_count;  // set by gkcu_update_nodes
+    // only instances with a non-zero mask enter the TLAS (RayTraceBaseRenderer.cpp:178); their indices were listed by
+    // gkcu_update_nodes. The TLAS is built with the SAH-binned builder by default: on RTIO.proc it halves the traversal time
+    // compared with the Morton LBVH (the floor's 2 km box degrades the Morton order); GKCU_TLAS_BUILDER=lbvh selects the LBVH.
+    const uint32_t m = c.tlas.prim_count;
+    if (m == 0) return 0;
+    k_gather_boxes<<<grid_for(m), 256, 0, st>>>(c.tlas_active_ids.as<uint32_t>(), m, c.inst_lo.as<float4>(), c.inst_hi.as<float4>(),
+                                               s.prim_lo.as<float4>(), s.prim_hi.as<float4>());
+    c.launches += 1;
     Bvh2 b2;
-    if (build_lbvh(c, n, n_active, b2)) return 1;
-    if (n_active == 0) return 0;
-    if (collapse(c, b2, n_active, 1, true, c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+    const char* tb = getenv("GKCU_TLAS_BUILDER");
+    if (tb && std::string(tb) == "lbvh") { if (build_lbvh(c, m, m, b2)) return 1; }
+    else if (build_sah(c, m, 1, b2)) return 1;
+    if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
     // the traversal stack holds at most 3 entries per level plus one sentinel per instance entry
     size_t blas_levels = 0;
     for (auto& b : c.blas) blas_levels = std::max(blas_levels, b.level_start.size() > 0 ? b.level_start.size() - 1 : 0);

@@ -75,11 +75,14 @@ struct Context {
     DevBuf blas_nodes, blas_node_lo, blas_node_hi, blas_tris, blas_tri_prim;  // pools shared by all BLAS
     std::vector<WideBvhInfo> blas;
     DevBuf blas_table;  // per model: node_base, tri_base, prim_count, pad + root box (2 x float4)
-    DevBuf tlas_nodes, tlas_node_lo, tlas_node_hi, instances, inst_lo, inst_hi;
+    DevBuf tlas_nodes, tlas_node_lo, tlas_node_hi, instances, inst_lo, inst_hi, tlas_active_ids;
     WideBvhInfo tlas;
     bool tlas_dirty = true;
+    bool frame_built_tlas = false;
     bool blas_built = false;
     BuildScratch scratch;
+    int trace_variant = 0;  // GKCU_TRACE_VARIANT: 0 persistent lanes, one step per iteration; 1 while-while; 2 warp-granular batches
+    int refill_below = 20;  // k_trace: refill idle lanes when fewer than this many lanes are busy (GKCU_REFILL)
     int blas_builder = 1;  // 0 = LBVH, 1 = SAH-binned (GKCU_BLAS_BUILDER=lbvh|sah)
 
     // textures / probes

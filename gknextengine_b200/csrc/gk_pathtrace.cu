@@ -673,9 +673,74 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S, RTView R, PathView
     if ((threadIdx.x & 31) == 0 && nprimary) atomicAdd(ray_counters + 0, (unsigned long long)nprimary);
 }
 
-// Persistent-thread traversal: lanes pull rays from the queue whenever they run dry, so a warp keeps tracing while any
-// work is left. (Per-ray traversal itself is the stack loop of trace_ray.)
-__global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi, size_t half) {
+// Persistent-thread traversal (Aila & Laine style "while-while"): every lane owns one ray; the warp alternates between a
+// phase where all lanes walk internal nodes and a phase where all lanes process their leaf, which keeps the two code paths
+// from serialising against each other, and lanes whose ray has terminated pull the next ray from the queue (one atomic per
+// warp) as soon as the number of busy lanes drops below `refill_below`.
+template <int VARIANT>
+__global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below) {
+    const uint32_t n = V.counts[qi];
+    const int lane = threadIdx.x & 31;
+    const float4* ray_o = V.ray_o + (size_t)qi * half;
+    const float4* ray_d = V.ray_d + (size_t)qi * half;
+    const uint32_t* slot_pixel = V.slot_pixel[qi];
+    uint2 stack[GK_TRAV_STACK];
+    Trav T;
+    T.done = true;
+    uint32_t slot = 0;
+    bool busy = false;
+    bool drained = false;  // the queue has no more rays
+    for (;;) {
+        if (!drained) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+            if (idle) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(V.counts + 2, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!busy) {
+                    slot = base + __popc(idle & ((1u << lane) - 1u));
+                    if (slot < n) {
+                        const float4 o = ray_o[slot], d = ray_d[slot];
+                        trav_init(T, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, (slot_pixel[slot] & 0x80000000u) != 0);
+                        busy = true;
+                    }
+                }
+                if (base + (uint32_t)__popc(idle) >= n) drained = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy)) return;
+        if (VARIANT == 0) {
+            // every lane advances one step (node or leaf) per iteration
+            do {
+                if (busy && !T.done) {
+                    if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, ts, stack);
+                    else trav_leaf_step(T, ts, stack);
+                }
+                if (busy && T.done) {
+                    V.hit_tuv[slot] = f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst));
+                    V.hit_prim[slot] = T.best.prim;
+                    busy = false;
+                }
+            } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
+        } else {
+            do {
+                // phase 1: internal nodes until every busy lane holds a leaf (or has finished)
+                while (busy && !T.done && !(T.cur & GK_LEAF_BIT)) trav_node_step(T, ts, stack);
+                // phase 2: one leaf per lane
+                if (busy && !T.done) trav_leaf_step(T, ts, stack);
+                if (busy && T.done) {
+                    V.hit_tuv[slot] = f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst));
+                    V.hit_prim[slot] = T.best.prim;
+                    busy = false;
+                }
+            } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
+        }
+    }
+}
+
+// The first version: a warp takes 32 rays, every lane runs the simple per-ray loop, the warp refills when all are done.
+__global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V, int qi, size_t half) {
     const uint32_t n = V.counts[qi];
     const int lane = threadIdx.x & 31;
     const float4* ray_o = V.ray_o + (size_t)qi * half;
@@ -930,7 +995,9 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
             GK_CUDA(cudaMemsetAsync(counts + (qi ^ 1), 0, 4, st));
             const uint32_t blocks = std::min<uint32_t>((n + 127) / 128, persistent_blocks);
             cudaEventRecord(c.kev[2], st);
-            k_trace<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
+            if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
+            else if (c.trace_variant == 1) k_trace<1><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+            else k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
             cudaEventRecord(c.kev[3], st);
             k_shade<<<blocks, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
             cudaEventRecord(c.kev[4], st);
