@@ -45,10 +45,15 @@ struct RTView {
 };
 
 // Per-pixel path state (SoA, 16-byte records) + per-slot ray/hit records of the wavefront queues.
+// "Hot" state (read and written on every path segment) lives per queue SLOT, double-buffered with the ray records, so k_shade
+// reads and writes it coalesced without a pixel indirection. "Cold" state (per-pixel accumulators and the primary-hit record)
+// is touched only at sample boundaries.
 struct PathView {
-    uint4* rng;
-    float4 *pos_mat, *nrm_flags, *dir_cnt, *ray_color, *final_color, *final_refl;
-    float4 *prim_pos_mat, *prim_nrm_cnt, *prim_albedo;
+    uint4* rng;                                          // hot, [2][pixels]
+    float4 *pos_mat, *nrm_flags, *dir_cnt, *ray_color;   // hot, [2][pixels]
+    float4 *final_color, *final_refl;                    // cold, per pixel: running sums of the finished samples
+    float4 *prim_pos_mat, *prim_nrm_cnt, *prim_albedo;   // cold, per pixel: primary hit (position|material, normal|sample range, albedo)
+    size_t pixels;
     float4 *ray_o, *ray_d;      // per slot: origin|tmin, dir|tmax
     uint32_t* slot_pixel[2];    // per slot: pixel | any-hit flag in bit 31 (ping-pong)
     float4* hit_tuv;            // per slot: t, u, v, inst
@@ -91,16 +96,13 @@ namespace {
 
 struct PathRegs {
     uint4 rng;
-    float3 pos, nrm;
-    uint32_t mat;
-    float3 dir;
-    float4 rayColor, finalColor, finalRefl;
+    float3 pos, nrm;   // vertexStart.Position / Normal
+    uint32_t mat;      // vertexStart.MaterialIndex
+    float3 dir;        // direction
+    float4 rayColor;
     uint32_t flags;
-    uint32_t sample, sampleEnd, sampleTotal, bounce, maxBounces;
-    float3 ppos, pnrm;
-    uint32_t pmat;
-    float4 palbedo;
-    float3 ro, rd;
+    uint32_t sample, bounce, maxBounces;
+    float3 ro, rd;     // pending ray
 };
 
 GK_DEV GkMaterial get_material(const SceneView& S, uint32_t idx) {  // BasicTypes.slang:376-379
@@ -339,14 +341,15 @@ GK_DEV bool on_closest(const SceneView& S, PathRegs& P, const Hit& h) {
 
 GK_DEV void set_stage(PathRegs& P, uint32_t st) { P.flags = (P.flags & ~FL_STAGE_MASK) | (st << FL_STAGE_SHIFT); }
 
-// Shading.slang:1105-1117: start sample i
-GK_DEV void start_sample(const SceneView& S, PathRegs& P) {
+// Shading.slang:1105-1117: start sample i from the primary-hit record
+GK_DEV void start_sample(const SceneView& S, const PathView& V, uint32_t pixel, PathRegs& P) {
+    const float4 pa = V.prim_pos_mat[pixel], pb = V.prim_nrm_cnt[pixel];
     P.rayColor = f4(1, 1, 1, 1);
     float4 eye = mul(S.cam->ModelViewInverse, f4(0, 0, 0, 1));
-    P.dir = normalize(P.ppos - xyz(eye));
-    P.pos = P.ppos;
-    P.nrm = P.pnrm;
-    P.mat = P.pmat;
+    P.pos = f3(pa.x, pa.y, pa.z);
+    P.dir = normalize(P.pos - xyz(eye));
+    P.nrm = f3(pb.x, pb.y, pb.z);
+    P.mat = __float_as_uint(pa.w);
     P.bounce = 0;
     set_stage(P, ST_FIRST);
     gen_closest(S, P, true);
@@ -358,33 +361,33 @@ struct PixelOut {
     size_t pixels;
 };
 
-GK_DEV void write_result(const PixelOut& O, const FrameCfg& cfg, uint32_t pixel, const PathRegs& P, float4 direct) {
+GK_DEV void write_result(const PixelOut& O, const FrameCfg& cfg, const PathView& V, uint32_t pixel, float4 direct) {
+    const float4 finalColor = V.final_color[pixel], finalRefl = V.final_refl[pixel];
     if (cfg.to_radiance) {
-        O.radiance[pixel] = P.finalColor;
-        O.radiance[O.pixels + pixel] = P.finalRefl;
+        O.radiance[pixel] = finalColor;
+        O.radiance[O.pixels + pixel] = finalRefl;
         if (cfg.rank == 0) O.direct[pixel] = direct;
         return;
     }
-    float4 fc = P.finalColor / float(P.sampleTotal);   // Shading.slang:1175-1176
-    float4 fr = P.finalRefl / float(P.sampleTotal);
-    fc = fc + direct;                                  // :1180
+    const uint32_t sampleTotal = __float_as_uint(V.prim_nrm_cnt[pixel].w) >> 16;
+    float4 fc = finalColor / float(sampleTotal);   // Shading.slang:1175-1176
+    float4 fr = finalRefl / float(sampleTotal);
+    fc = fc + direct;                              // :1180
     store_h4(O.rt.single_diffuse, pixel, fc);
     store_h4(O.rt.single_specular, pixel, fr);
 }
 
 // Consumes the result of the pending ray and runs the pixel's program up to its next ray (or to completion).
-GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, uint32_t pixel, PathRegs& P, const Hit& h) {
+GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, const PathView& V, uint32_t pixel, PathRegs& P, const Hit& h) {
     const GkUniformBufferObject* C = S.cam;
     const uint32_t stage = (P.flags & FL_STAGE_MASK) >> FL_STAGE_SHIFT;
     const bool primDielectric = (P.flags & FL_PRIM_DIELECTRIC) != 0;
-    bool end_sample = false;
     bool after_sun = false;
     if (stage == ST_FIRST) {
         bool exitFirst = on_closest(S, P, h);
         if (!exitFirst) {
             if (cfg.exit_after_first && !primDielectric) {
                 P.rayColor = P.rayColor * interpolateAmbientCubesV2(S, P.pos, P.nrm);  // :1120-1123
-                end_sample = true;
             } else {
                 P.bounce = 1;
                 if (1u < P.maxBounces) {
@@ -392,12 +395,12 @@ GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, u
                     gen_closest(S, P, false);
                     return REQ_CLOSEST;
                 }
-                end_sample = true;
             }
-        } else end_sample = true;
+        }
     } else if (stage == ST_BOUNCE) {
-        if (on_closest(S, P, h)) end_sample = true;  // :1130-1133
-        else if (C->HasSun && (RandomFloat(P.rng) < 0.5f)) {  // :1135-1144
+        if (on_closest(S, P, h)) {
+            // :1130-1133 break
+        } else if (C->HasSun && (RandomFloat(P.rng) < 0.5f)) {  // :1135-1144
             const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
             const float3 cone = AlignWithNormal(RandomInCone(P.rng, GK_COS_QUARTER_DEGREE), lightVector);
             P.ro = P.pos + P.nrm * 0.0f;  // TRACE_CORRECTION_OFFSET
@@ -406,22 +409,20 @@ GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, u
             return REQ_ANY;
         } else after_sun = true;
     } else if (stage == ST_SUN) {
-        if (h.inst == GK_NO_HIT) {
-            P.rayColor = P.rayColor * f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w);
-            end_sample = true;
-        } else after_sun = true;
+        if (h.inst == GK_NO_HIT) P.rayColor = P.rayColor * f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w);
+        else after_sun = true;
     } else {  // ST_DIRECT: FHardwareDirectIlluminatorV2::DirectIlluminate, :886-908
+        const float4 pb = V.prim_nrm_cnt[pixel];
         const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
-        const float d = fmaxf(dot(lightVector, normalize(P.pnrm)), 0.0f) * GK_M_1_PI;
+        const float d = fmaxf(dot(lightVector, normalize(f3(pb.x, pb.y, pb.z))), 0.0f) * GK_M_1_PI;
         const float shadow = (h.inst == GK_NO_HIT) ? 1.0f : 0.0f;
-        write_result(O, cfg, pixel, P, f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w) * d * shadow);
+        write_result(O, cfg, V, pixel, f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w) * d * shadow);
         return REQ_DONE;
     }
     if (after_sun) {  // :1146-1154
         const bool earlyExit = !primDielectric && (RandomFloat(P.rng) < 0.5f);  // ExitProbability
         if (P.bounce == P.maxBounces - 1u || earlyExit) {
             P.rayColor = P.rayColor * interpolateAmbientCubesV2(S, P.pos, P.nrm);
-            end_sample = true;
         } else {
             P.bounce++;
             gen_closest(S, P, false);
@@ -429,88 +430,77 @@ GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, u
             return REQ_CLOSEST;
         }
     }
-    // end of sample, :1159-1171
-    (void)end_sample;
-    if (P.flags & FL_HIT_METAL) P.rayColor = P.rayColor * P.palbedo;
-    if (P.flags & FL_HIT_REFLECT) P.finalRefl = P.finalRefl + P.rayColor;
-    else P.finalColor = P.finalColor + P.rayColor;
+    // end of sample, :1159-1171: fold the path into the pixel's running sums
+    if (P.flags & FL_HIT_METAL) P.rayColor = P.rayColor * V.prim_albedo[pixel];
+    {
+        float4* acc = (P.flags & FL_HIT_REFLECT) ? V.final_refl + pixel : V.final_color + pixel;
+        *acc = *acc + P.rayColor;
+    }
+    const float4 pb = V.prim_nrm_cnt[pixel];
+    const uint32_t sampleEnd = __float_as_uint(pb.w) & 0xFFFFu;
     P.sample++;
-    if (P.sample < P.sampleEnd) {
-        start_sample(S, P);
+    if (P.sample < sampleEnd) {
+        start_sample(S, V, pixel, P);
         return REQ_CLOSEST;
     }
     // all samples done, :1175-1183
     if (cfg.rank != 0) {
-        write_result(O, cfg, pixel, P, f4(0, 0, 0, 0));
+        write_result(O, cfg, V, pixel, f4(0, 0, 0, 0));
         return REQ_DONE;
     }
+    const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
     if (C->HasSun) {
-        const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
         const float3 cone = AlignWithNormal(RandomInCone(P.rng, GK_COS_QUARTER_DEGREE), lightVector);
-        P.ro = P.ppos;
+        const float4 pa = V.prim_pos_mat[pixel];
+        P.ro = f3(pa.x, pa.y, pa.z);
         P.rd = cone;
         set_stage(P, ST_DIRECT);
         return REQ_ANY;
     }
-    {
-        const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
-        const float d = fmaxf(dot(lightVector, normalize(P.pnrm)), 0.0f) * GK_M_1_PI;
-        write_result(O, cfg, pixel, P, f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w) * d * 0.0f);
-    }
+    const float d = fmaxf(dot(lightVector, normalize(f3(pb.x, pb.y, pb.z))), 0.0f) * GK_M_1_PI;
+    write_result(O, cfg, V, pixel, f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w) * d * 0.0f);
     return REQ_DONE;
 }
 
 // ------------------------------------------------------------------------------------------------ state I/O
-GK_DEV void store_hot(const PathView& V, uint32_t pixel, const PathRegs& P) {
-    V.rng[pixel] = P.rng;
-    V.pos_mat[pixel] = f4(P.pos.x, P.pos.y, P.pos.z, __uint_as_float(P.mat));
-    V.nrm_flags[pixel] = f4(P.nrm.x, P.nrm.y, P.nrm.z, __uint_as_float(P.flags));
-    V.dir_cnt[pixel] = f4(P.dir.x, P.dir.y, P.dir.z, __uint_as_float(P.sample | (P.bounce << 16)));
-    V.ray_color[pixel] = P.rayColor;
+GK_DEV void store_hot(const PathView& V, int qi, uint32_t slot, const PathRegs& P) {
+    const size_t i = (size_t)qi * V.pixels + slot;
+    V.rng[i] = P.rng;
+    V.pos_mat[i] = f4(P.pos.x, P.pos.y, P.pos.z, __uint_as_float(P.mat));
+    V.nrm_flags[i] = f4(P.nrm.x, P.nrm.y, P.nrm.z, __uint_as_float(P.flags));
+    V.dir_cnt[i] = f4(P.dir.x, P.dir.y, P.dir.z, __uint_as_float(P.sample | (P.bounce << 16)));
+    V.ray_color[i] = P.rayColor;
 }
-GK_DEV void store_cold(const PathView& V, uint32_t pixel, const PathRegs& P) {
-    V.final_color[pixel] = P.finalColor;
-    V.final_refl[pixel] = P.finalRefl;
-}
-GK_DEV void store_primary(const PathView& V, uint32_t pixel, const PathRegs& P) {
-    V.prim_pos_mat[pixel] = f4(P.ppos.x, P.ppos.y, P.ppos.z, __uint_as_float(P.pmat));
-    V.prim_nrm_cnt[pixel] = f4(P.pnrm.x, P.pnrm.y, P.pnrm.z, __uint_as_float(P.sampleEnd | (P.sampleTotal << 16)));
-    V.prim_albedo[pixel] = P.palbedo;
-}
-GK_DEV void load_state(const PathView& V, const SceneView& S, uint32_t pixel, PathRegs& P) {
-    P.rng = V.rng[pixel];
-    float4 a = V.pos_mat[pixel], b = V.nrm_flags[pixel], c = V.dir_cnt[pixel];
+GK_DEV void load_hot(const PathView& V, const SceneView& S, int qi, uint32_t slot, PathRegs& P) {
+    const size_t i = (size_t)qi * V.pixels + slot;
+    P.rng = V.rng[i];
+    float4 a = V.pos_mat[i], b = V.nrm_flags[i], c = V.dir_cnt[i];
     P.pos = f3(a.x, a.y, a.z); P.mat = __float_as_uint(a.w);
     P.nrm = f3(b.x, b.y, b.z); P.flags = __float_as_uint(b.w);
     P.dir = f3(c.x, c.y, c.z);
     uint32_t cnt = __float_as_uint(c.w);
     P.sample = cnt & 0xFFFF; P.bounce = cnt >> 16;
-    P.rayColor = V.ray_color[pixel];
-    P.finalColor = V.final_color[pixel];
-    P.finalRefl = V.final_refl[pixel];
-    float4 pa = V.prim_pos_mat[pixel], pb = V.prim_nrm_cnt[pixel];
-    P.ppos = f3(pa.x, pa.y, pa.z); P.pmat = __float_as_uint(pa.w);
-    P.pnrm = f3(pb.x, pb.y, pb.z);
-    uint32_t sc = __float_as_uint(pb.w);
-    P.sampleEnd = sc & 0xFFFF; P.sampleTotal = sc >> 16;
-    P.palbedo = V.prim_albedo[pixel];
+    P.rayColor = V.ray_color[i];
     P.maxBounces = (P.flags & FL_PRIM_DIELECTRIC) ? S.cam->MaxNumberOfBounces : S.cam->NumberOfBounces;
 }
 
-// Appends (pixel, ray) to a queue; one atomic per warp (ballot + popc + shuffle).
-GK_DEV void enqueue(uint32_t* count, uint32_t* slot_pixel, float4* ray_o, float4* ray_d, bool want, uint32_t pixel, int req, const PathRegs& P) {
+// Appends one entry to queue `qi` (one atomic per warp: ballot + popc + shuffle) and writes the hot state, the ray and the
+// pixel tag at the new slot.
+GK_DEV void enqueue(const PathView& V, int qi, bool want, uint32_t pixel, int req, const PathRegs& P) {
     const unsigned mask = __ballot_sync(0xffffffffu, want);
     if (!mask) return;
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(mask) - 1;
     uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+    if (lane == leader) base = atomicAdd(V.counts + qi, (uint32_t)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (want) {
-        uint32_t slot = base + __popc(mask & ((1u << lane) - 1u));
-        slot_pixel[slot] = pixel | (req == REQ_ANY ? 0x80000000u : 0u);
-        ray_o[slot] = f4(P.ro.x, P.ro.y, P.ro.z, GK_EPS);
-        ray_d[slot] = f4(P.rd.x, P.rd.y, P.rd.z, GK_PT_MAX_TRACE_DISTANCE);
+        const uint32_t slot = base + __popc(mask & ((1u << lane) - 1u));
+        const size_t i = (size_t)qi * V.pixels + slot;
+        V.slot_pixel[qi][slot] = pixel | (req == REQ_ANY ? 0x80000000u : 0u);
+        V.ray_o[i] = f4(P.ro.x, P.ro.y, P.ro.z, GK_EPS);
+        V.ray_d[i] = f4(P.rd.x, P.rd.y, P.rd.z, GK_PT_MAX_TRACE_DISTANCE);
+        store_hot(V, qi, slot, P);
     }
 }
 
@@ -644,13 +634,16 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S, RTView R, PathView
                 int sampleMultiplier = moment > 0 ? 4 : 1;  // Core.PathTracing.comp.slang:28
                 int sample = max(1, (int)C->NumberOfSamples * sampleMultiplier);  // SampleDownscale = 1
                 uint32_t s0 = (uint32_t)((uint64_t)cfg.rank * sample / cfg.world), s1 = (uint32_t)((uint64_t)(cfg.rank + 1) * sample / cfg.world);
-                P.ppos = hpos; P.pnrm = hnrm; P.pmat = hmat; P.palbedo = albedo;
-                P.finalColor = zero; P.finalRefl = zero;
+                V.prim_pos_mat[pixel] = f4(hpos.x, hpos.y, hpos.z, __uint_as_float(hmat));
+                V.prim_nrm_cnt[pixel] = f4(hnrm.x, hnrm.y, hnrm.z, __uint_as_float(s1 | ((uint32_t)sample << 16)));
+                V.prim_albedo[pixel] = albedo;
+                V.final_color[pixel] = zero;
+                V.final_refl[pixel] = zero;
                 P.flags = material.MaterialModel == GK_MATERIAL_DIELECTRIC ? FL_PRIM_DIELECTRIC : 0u;
                 P.maxBounces = (P.flags & FL_PRIM_DIELECTRIC) ? C->MaxNumberOfBounces : C->NumberOfBounces;
-                P.sample = s0; P.sampleEnd = s1; P.sampleTotal = (uint32_t)sample;
+                P.sample = s0;
                 if (s0 < s1) {
-                    start_sample(S, P);
+                    start_sample(S, V, pixel, P);
                     want = true;
                 } else {  // this rank has no samples for the pixel (spp < world)
                     if (cfg.to_radiance) {
@@ -661,13 +654,8 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S, RTView R, PathView
                 }
             }
         }
-        if (want) {
-            store_hot(V, pixel, P);
-            store_cold(V, pixel, P);
-            store_primary(V, pixel, P);
-        }
     }
-    enqueue(V.counts + 0, V.slot_pixel[0], V.ray_o, V.ray_d, want, pixel, REQ_CLOSEST, P);
+    enqueue(V, 0, want, pixel, REQ_CLOSEST, P);
     // ray statistics: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) nprimary += __shfl_xor_sync(0xffffffffu, nprimary, o);
     if ((threadIdx.x & 31) == 0 && nprimary) atomicAdd(ray_counters + 0, (unsigned long long)nprimary);
@@ -762,54 +750,32 @@ __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V,
     }
 }
 
-// Shade: consume hits, advance every path to its next ray, compact the survivors into the other queue.
+// Shade: one thread per queue slot: consume the hit, advance the path to its next ray, compact the survivors into the other queue.
 __global__ void __launch_bounds__(128) k_shade(SceneView S, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
     const uint32_t n = V.counts[qi];
     PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
     uint32_t nclosest = 0, nany = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounds = (n + stride - 1) / stride;
-    for (uint32_t k = 0; k < rounds; ++k) {
-        uint32_t slot = k * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        bool want = false;
-        int req = REQ_DONE;
-        uint32_t pixel = 0;
-        PathRegs P;
-        if (slot < n) {
-            uint32_t sp = V.slot_pixel[qi][slot];
-            pixel = sp & 0x7FFFFFFFu;
-            if (sp & 0x80000000u) nany++; else nclosest++;
-            float4 hv = V.hit_tuv[slot];
-            Hit h;
-            h.t = hv.x; h.u = hv.y; h.v = hv.z; h.inst = __float_as_uint(hv.w); h.prim = V.hit_prim[slot];
-            load_state(V, S, pixel, P);
-            float4 o = V.ray_o[(size_t)qi * ((size_t)R.w * R.h) + slot], d = V.ray_d[(size_t)qi * ((size_t)R.w * R.h) + slot];
-            P.ro = f3(o.x, o.y, o.z);
-            P.rd = f3(d.x, d.y, d.z);
-            req = advance(S, O, cfg, pixel, P, h);
-            want = req != REQ_DONE;
-            if (want) {
-                store_hot(V, pixel, P);
-                store_cold(V, pixel, P);
-            }
-        }
-        // rays of the next wave go to the other half of the ray arrays
-        const unsigned mask = __ballot_sync(0xffffffffu, want);
-        if (mask) {
-            const int lane = threadIdx.x & 31;
-            const int leader = __ffs(mask) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(V.counts + (qi ^ 1), (uint32_t)__popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (want) {
-                uint32_t ns = base + __popc(mask & ((1u << lane) - 1u));
-                const size_t half = (size_t)R.w * R.h;
-                V.slot_pixel[qi ^ 1][ns] = pixel | (req == REQ_ANY ? 0x80000000u : 0u);
-                V.ray_o[(size_t)(qi ^ 1) * half + ns] = f4(P.ro.x, P.ro.y, P.ro.z, GK_EPS);
-                V.ray_d[(size_t)(qi ^ 1) * half + ns] = f4(P.rd.x, P.rd.y, P.rd.z, GK_PT_MAX_TRACE_DISTANCE);
-            }
-        }
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool want = false;
+    int req = REQ_DONE;
+    uint32_t pixel = 0;
+    PathRegs P;
+    if (slot < n) {
+        const size_t i = (size_t)qi * V.pixels + slot;
+        const uint32_t sp = V.slot_pixel[qi][slot];
+        const float4 hv = V.hit_tuv[slot];
+        const float4 o = V.ray_o[i], d = V.ray_d[i];
+        Hit h;
+        h.t = hv.x; h.u = hv.y; h.v = hv.z; h.inst = __float_as_uint(hv.w); h.prim = V.hit_prim[slot];
+        load_hot(V, S, qi, slot, P);
+        pixel = sp & 0x7FFFFFFFu;
+        if (sp & 0x80000000u) nany++; else nclosest++;
+        P.ro = f3(o.x, o.y, o.z);
+        P.rd = f3(d.x, d.y, d.z);
+        req = advance(S, O, cfg, V, pixel, P, h);
+        want = req != REQ_DONE;
     }
+    enqueue(V, qi ^ 1, want, pixel, req, P);
     for (int o = 16; o > 0; o >>= 1) {
         nclosest += __shfl_xor_sync(0xffffffffu, nclosest, o);
         nany += __shfl_xor_sync(0xffffffffu, nany, o);
@@ -830,7 +796,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneView S, RTView R, PathView V,
         uint32_t sp = V.slot_pixel[qi][slot];
         uint32_t pixel = sp & 0x7FFFFFFFu;
         PathRegs P;
-        load_state(V, S, pixel, P);
+        load_hot(V, S, qi, slot, P);
         float4 o = V.ray_o[(size_t)qi * half + slot], d = V.ray_d[(size_t)qi * half + slot];
         P.ro = f3(o.x, o.y, o.z);
         P.rd = f3(d.x, d.y, d.z);
@@ -839,7 +805,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneView S, RTView R, PathView V,
             Hit h;
             if (req == REQ_ANY) { trace_ray<true>(S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h); nany++; }
             else { trace_ray<false>(S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h); nclosest++; }
-            req = advance(S, O, cfg, pixel, P, h);
+            req = advance(S, O, cfg, V, pixel, P, h);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -907,6 +873,7 @@ PathView make_path_view(const Context& c) {
     PathBuffers& b = *c.path;
     PathView V;
     V.rng = b.rng.as<uint4>();
+    V.pixels = b.pixels;
     V.pos_mat = b.pos_mat.as<float4>(); V.nrm_flags = b.nrm_flags.as<float4>(); V.dir_cnt = b.dir_cnt.as<float4>();
     V.ray_color = b.ray_color.as<float4>(); V.final_color = b.final_color.as<float4>(); V.final_refl = b.final_refl.as<float4>();
     V.prim_pos_mat = b.prim_pos_mat.as<float4>(); V.prim_nrm_cnt = b.prim_nrm_cnt.as<float4>(); V.prim_albedo = b.prim_albedo.as<float4>();
@@ -925,8 +892,8 @@ int path_resize(Context& c) {
     PathBuffers& b = *c.path;
     size_t n = (size_t)c.rt.w * c.rt.h;
     b.pixels = n;
-    bool ok = b.rng.reserve(n * 16) && b.pos_mat.reserve(n * 16) && b.nrm_flags.reserve(n * 16) && b.dir_cnt.reserve(n * 16) &&
-              b.ray_color.reserve(n * 16) && b.final_color.reserve(n * 16) && b.final_refl.reserve(n * 16) && b.prim_pos_mat.reserve(n * 16) &&
+    bool ok = b.rng.reserve(2 * n * 16) && b.pos_mat.reserve(2 * n * 16) && b.nrm_flags.reserve(2 * n * 16) && b.dir_cnt.reserve(2 * n * 16) &&
+              b.ray_color.reserve(2 * n * 16) && b.final_color.reserve(n * 16) && b.final_refl.reserve(n * 16) && b.prim_pos_mat.reserve(n * 16) &&
               b.prim_nrm_cnt.reserve(n * 16) && b.prim_albedo.reserve(n * 16) && b.ray_o.reserve(2 * n * 16) && b.ray_d.reserve(2 * n * 16) &&
               b.slot_pixel[0].reserve(n * 4) && b.slot_pixel[1].reserve(n * 4) && b.hit_tuv.reserve(n * 16) && b.hit_prim.reserve(n * 4) &&
               b.counts.reserve(64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16);
@@ -999,7 +966,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
             else if (c.trace_variant == 1) k_trace<1><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
             else k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
             cudaEventRecord(c.kev[3], st);
-            k_shade<<<blocks, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+            k_shade<<<(n + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
             cudaEventRecord(c.kev[4], st);
             pending = true;
             ks.trace_launches++;
