@@ -111,6 +111,9 @@ GK_DEV float3 xform_vec(const float* m, float3 p) {
 GK_DEV float byte_f(uint32_t w, int c) { return (float)((w >> (8 * c)) & 0xFFu); }
 
 // Tests the 4 quantised child boxes of a node. tn[c] = padded entry distance or +inf on a miss.
+// Planes are dequantised relative to the node origin: t = q * (scale * idir) + (origin - o) * idir, one FMA per plane; the
+// near/far plane words are picked per axis from the sign of the ray direction, so no per-plane min/max is needed. The
+// interval is padded by a few ulps on both ends (the quantised boxes are conservative, the slab arithmetic is not).
 GK_DEV void node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, float3 ro, float3 idir, float tmin, float tbest, float tn[4]) {
     const float ox = __uint_as_float(n0.x), oy = __uint_as_float(n0.y), oz = __uint_as_float(n0.z);
     const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
@@ -118,18 +121,22 @@ GK_DEV void node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint
     const float adjx = (ox - ro.x) * idir.x, adjy = (oy - ro.y) * idir.y, adjz = (oz - ro.z) * idir.z;
     const float scx = sx * idir.x, scy = sy * idir.y, scz = sz * idir.z;
     const uint32_t child[4] = {n1.x, n1.y, n1.z, n1.w};
-    const uint32_t qlx = n2.x, qly = n2.y, qlz = n2.z, qhx = n2.w, qhy = n3.x, qhz = n3.y;
-    const float tfcap = tbest * 1.000001f + 1e-7f;
+    const bool px = idir.x >= 0.0f, py = idir.y >= 0.0f, pz = idir.z >= 0.0f;
+    const uint32_t nx = px ? n2.x : n2.w, fx = px ? n2.w : n2.x;  // qlo.x / qhi.x
+    const uint32_t ny = py ? n2.y : n3.x, fy = py ? n3.x : n2.y;
+    const uint32_t nz = pz ? n2.z : n3.y, fz = pz ? n3.y : n2.z;
+    const float tfcap = __fmaf_rn(tbest, 1.000001f, 1e-7f);
+    const float inf = __int_as_float(0x7f800000);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        float x0 = __fmaf_rn(byte_f(qlx, c), scx, adjx), x1 = __fmaf_rn(byte_f(qhx, c), scx, adjx);
-        float y0 = __fmaf_rn(byte_f(qly, c), scy, adjy), y1 = __fmaf_rn(byte_f(qhy, c), scy, adjy);
-        float z0 = __fmaf_rn(byte_f(qlz, c), scz, adjz), z1 = __fmaf_rn(byte_f(qhz, c), scz, adjz);
-        float n = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-        float f = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-        float npad = n * 0.999999f - 1e-7f;
-        bool hit = (child[c] != GK_CHILD_EMPTY) && (npad <= f * 1.000001f + 1e-7f) && (npad <= tfcap);
-        tn[c] = hit ? npad : __int_as_float(0x7f800000);
+        const float x0 = __fmaf_rn(byte_f(nx, c), scx, adjx), x1 = __fmaf_rn(byte_f(fx, c), scx, adjx);
+        const float y0 = __fmaf_rn(byte_f(ny, c), scy, adjy), y1 = __fmaf_rn(byte_f(fy, c), scy, adjy);
+        const float z0 = __fmaf_rn(byte_f(nz, c), scz, adjz), z1 = __fmaf_rn(byte_f(fz, c), scz, adjz);
+        const float n = fmaxf(fmaxf(x0, y0), fmaxf(z0, tmin));
+        const float f = fminf(fminf(x1, y1), z1);
+        const float npad = __fmaf_rn(n, 0.999999f, -1e-7f);
+        const bool hit = (child[c] != GK_CHILD_EMPTY) && (npad <= __fmaf_rn(f, 1.000001f, 1e-7f)) && (npad <= tfcap);
+        tn[c] = hit ? npad : inf;
     }
 }
 

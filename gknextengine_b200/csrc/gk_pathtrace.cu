@@ -711,6 +711,30 @@ __global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi
                     busy = false;
                 }
             } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
+        } else if (VARIANT == 3) {
+            // vote: each iteration the warp executes only the step kind most lanes are waiting for (node walk, instance entry
+            // or triangle leaf); lanes in another state sit the iteration out instead of serialising a second code path.
+            do {
+                const bool live = busy && !T.done;
+                const bool leaf = (T.cur & GK_LEAF_BIT) != 0;
+                const bool wN = live && !leaf;
+                const bool wI = live && leaf && T.cur_inst == GK_NO_HIT;
+                const bool wT = live && leaf && T.cur_inst != GK_NO_HIT;
+                const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nI = __popc(__ballot_sync(0xffffffffu, wI)),
+                          nT = __popc(__ballot_sync(0xffffffffu, wT));
+                if (nN >= nT && nN >= nI) {
+                    if (wN) trav_node_step(T, ts, stack);
+                } else if (nT >= nI) {
+                    if (wT) trav_leaf_step(T, ts, stack);
+                } else {
+                    if (wI) trav_leaf_step(T, ts, stack);
+                }
+                if (busy && T.done) {
+                    V.hit_tuv[slot] = f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst));
+                    V.hit_prim[slot] = T.best.prim;
+                    busy = false;
+                }
+            } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
         } else {
             do {
                 // phase 1: internal nodes until every busy lane holds a leaf (or has finished)
@@ -964,6 +988,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
             cudaEventRecord(c.kev[2], st);
             if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
             else if (c.trace_variant == 1) k_trace<1><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+            else if (c.trace_variant == 3) k_trace<3><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
             else k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
             cudaEventRecord(c.kev[3], st);
             k_shade<<<(n + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
