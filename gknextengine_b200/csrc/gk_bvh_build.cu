@@ -458,7 +458,9 @@ __global__ void k_sah_split(int leaf_max, int nactive, const int* __restrict__ a
     float4 llo = l, lhi = h, rlo = l, rhi = h;
     if (bestAxis < 0) {
         // every centroid fell into one bin on every axis: median split by position, children keep the parent box
-        if (cnt <= 8) { splits[s].axis = -2; return; }  // stays a leaf (<= 8 fits the leaf encoding)
+        // a BLAS leaf may hold up to 8 triangles (leaf encoding); a TLAS leaf holds exactly one instance, so coincident
+        // instances are always separated by the median split
+        if (leaf_max > 1 && cnt <= 8) { splits[s].axis = -2; return; }
         sp.fallback = 1;
         sp.nl = cnt / 2;
     } else {

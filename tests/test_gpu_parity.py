@@ -279,6 +279,29 @@ def test_blas_refit_and_dynamic_tlas(renderer):
     assert t["blas_refit_ms"] > 0 and t["tlas_update_ms"] > 0
 
 
+def test_coincident_instances_are_all_reachable(renderer):
+    """Instances with identical boxes (bricks moved onto each other) cannot be separated by any split plane; every one of
+    them must still be a TLAS leaf of its own."""
+    import ctypes as C
+    from gknextengine_b200._abi import GkNodeProxy
+    scene = host.Scene("LegoBricks.synth:600")
+    scene.update_nodes()
+    osc, _ = setup_pair(renderer, scene, 64, 64)
+    nodes, n = scene.nodes()
+    arr = (GkNodeProxy * n)(*[nodes[i] for i in range(n)])
+    for i in range(2, 40):  # pile 38 bricks exactly onto brick 1 (same model so that the boxes coincide)
+        arr[i].worldTS = arr[1].worldTS
+        arr[i].modelId = arr[1].modelId
+    renderer.update_nodes_ptr(C.addressof(arr), n)
+    osc.L.gko_update_nodes(osc._h, arr, n)
+    rep = validate(renderer)
+    assert rep["tlas"]["all_instances_once"] and rep["tlas"]["leaves"] == n
+    rays = random_rays(30000, seed=8, center=(0, 1.0, 0), spread=6.0)
+    rays["dy"] = -np.abs(rays["dy"])
+    hg, hc = renderer.trace(rays), osc.trace(rays)
+    assert np.array_equal(hg["inst"], hc["inst"]) and np.array_equal(hg["t"].view(np.uint32), hc["t"].view(np.uint32))
+
+
 def test_invisible_and_nort_nodes_are_masked(renderer):
     scene = host.Scene("CornellBox.proc")
     scene.update_nodes()
