@@ -242,13 +242,13 @@ __device__ __forceinline__ float box_area(float4 lo, float4 hi) {
 
 // One BFS level of the BVH2 -> Node4 collapse. Entry = (bvh2 node, node4 slot). A bvh2 node with <= leaf_max primitives
 // becomes a leaf reference; otherwise the largest-area internal child is opened until there are 4 children.
-__global__ void k_collapse_level(const int2* __restrict__ qin, int nin, int2* __restrict__ qout, int* __restrict__ nout, int* __restrict__ node_counter,
+__global__ void k_collapse_level(const int2* __restrict__ qin, const int* __restrict__ nin_ptr, int2* __restrict__ qout, int* __restrict__ nout, int* __restrict__ node_counter,
                                  const float4* __restrict__ nlo, const float4* __restrict__ nhi, const int* __restrict__ left,
                                  const int* __restrict__ right, const int* __restrict__ first, const int* __restrict__ count, int leaf_max,
                                  const uint32_t* __restrict__ order, const uint32_t* __restrict__ remap, int tlas_mode, Node4* __restrict__ out, float4* __restrict__ out_lo,
                                  float4* __restrict__ out_hi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nin) return;
+    if (i >= *nin_ptr) return;
     int2 e = qin[i];
     int kids[4];
     int nk;
@@ -371,9 +371,9 @@ __global__ void k_sah_init(int leaf_max, int n, const int* __restrict__ bounds, 
     }
 }
 
-__global__ void k_sah_clear_bins(SahBin* bins, int nslots) {
+__global__ void k_sah_clear_bins(SahBin* bins, const int* __restrict__ nslots_ptr) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nslots * 3 * kSahBins) return;
+    if (i >= *nslots_ptr * 3 * kSahBins) return;
     SahBin b;
     b.lo[0] = b.lo[1] = b.lo[2] = 0x7FFFFFFF;
     b.hi[0] = b.hi[1] = b.hi[2] = (int)0x80000000;
@@ -413,10 +413,10 @@ __global__ void k_sah_bin(int n, const uint32_t* __restrict__ order, const int* 
 
 struct SahSplit { int axis, plane, nl, fallback; };
 
-__global__ void k_sah_split(int leaf_max, int nactive, const int* __restrict__ active, const SahBin* __restrict__ bins, float4* nlo, float4* nhi, int* left,
+__global__ void k_sah_split(int leaf_max, const int* __restrict__ nactive_ptr, const int* __restrict__ active, const SahBin* __restrict__ bins, float4* nlo, float4* nhi, int* left,
                             int* right, int* first, int* count, int* counters, int* next_active, SahSplit* splits, int* cursors) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nactive) return;
+    if (s >= *nactive_ptr) return;
     int node = active[s];
     int cnt = count[node];
     float bestCost = FLT_MAX;
@@ -527,9 +527,19 @@ __global__ void k_fill_int(int* p, int n, int v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-__global__ void k_mark_slots(const int* active, int nactive, int* slot_of, int unmark) {
+__global__ void k_mark_slots(const int* active, const int* __restrict__ nactive_ptr, int* slot_of, int unmark) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nactive) slot_of[active[i]] = unmark ? -1 : i;
+    if (i < *nactive_ptr) slot_of[active[i]] = unmark ? -1 : i;
+}
+// level bookkeeping on the device, so the host only synchronises every few levels
+__global__ void k_sah_next(int* counters) {
+    counters[1] = counters[2];
+    counters[2] = 0;
+}
+__global__ void k_collapse_next(int* counters, int level) {
+    counters[16 + level + 2] = counters[8];  // nodes allocated so far = first node of level + 2
+    counters[10] = counters[9];
+    counters[9] = 0;
 }
 
 // ------------------------------------------------------------------------------------------- instances
@@ -619,7 +629,7 @@ bool reserve_bvh2(BuildScratch& s, size_t n) {
     return s.n2_lo.reserve(nn * 16) && s.n2_hi.reserve(nn * 16) && s.n2_left.reserve(nn * 4) && s.n2_right.reserve(nn * 4) &&
            s.n2_parent.reserve(nn * 4) && s.n2_first.reserve(nn * 4) && s.n2_count.reserve(nn * 4) && s.n2_flag.reserve(nn * 4) &&
            s.keys.reserve(n * 8) && s.keys_sorted.reserve(n * 8) && s.order.reserve(n * 4) && s.order_tmp.reserve(n * 4) &&
-           s.queue_a.reserve((n + 4) * 8) && s.queue_b.reserve((n + 4) * 8) && s.counters.reserve(64 * 4) && s.bounds.reserve(64);
+           s.queue_a.reserve((n + 4) * 8) && s.queue_b.reserve((n + 4) * 8) && s.counters.reserve(128 * 4) && s.bounds.reserve(64);
 }
 
 // Morton LBVH over n boxes (prim_lo/prim_hi in scratch). Inactive (inverted) boxes sort to the end and are excluded.
@@ -681,27 +691,31 @@ int build_sah(Context& c, uint32_t n, int leaf_max, Bvh2& out) {
     k_sah_init<<<grid_for(n), 256, 0, st>>>(leaf_max, (int)n, s.bounds.as<int>(), nlo, nhi, left, right, first, count, ord_a, pn_a, act_a, counters);
     k_fill_int<<<grid_for(2 * (size_t)n + 2), 256, 0, st>>>(slot_of, (int)(2 * n + 2), -1);
     c.launches += 4;
-    int nactive = n > (uint32_t)leaf_max ? 1 : 0;
-    int guard = 0;
-    while (nactive > 0 && guard++ < 128) {
-        k_mark_slots<<<grid_for(nactive), 256, 0, st>>>(act_a, nactive, slot_of, 0);
-        k_sah_clear_bins<<<grid_for((size_t)nactive * 3 * kSahBins), 256, 0, st>>>(s.bins.as<SahBin>(), nactive);
-        k_sah_bin<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, s.bins.as<SahBin>());
-        k_sah_split<<<grid_for(nactive, 128), 128, 0, st>>>(leaf_max, nactive, act_a, s.bins.as<SahBin>(), nlo, nhi, left, right, first, count, counters, act_b, splits,
-                                                      cursors);
-        k_sah_partition<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, left, first,
-                                                     splits, cursors, ord_b, pn_b);
-        k_mark_slots<<<grid_for(nactive), 256, 0, st>>>(act_a, nactive, slot_of, 1);
-        c.launches += 6;
-        int h[3];
-        GK_CUDA(cudaMemcpyAsync(h, counters, 12, cudaMemcpyDeviceToHost, st));
-        GK_CUDA(cudaStreamSynchronize(st));
-        nactive = h[2];
-        int zero = 0;
-        GK_CUDA(cudaMemcpyAsync(counters + 2, &zero, 4, cudaMemcpyHostToDevice, st));
-        std::swap(ord_a, ord_b);
-        std::swap(pn_a, pn_b);
-        std::swap(act_a, act_b);
+    // One level = mark, clear, bin, split, partition, unmark, next. Kernels take the number of open nodes from device memory;
+    // the host only bounds the grids (a level has at most min(2^level, max_slots) open nodes) and polls every 8 levels.
+    if (n > (uint32_t)leaf_max) {
+        for (int level = 0; level < 512; ++level) {
+            const size_t ub = std::min<size_t>(max_slots, level < 30 ? (size_t)1 << level : max_slots);
+            k_mark_slots<<<grid_for(ub), 256, 0, st>>>(act_a, counters + 1, slot_of, 0);
+            k_sah_clear_bins<<<grid_for(ub * 3 * kSahBins), 256, 0, st>>>(s.bins.as<SahBin>(), counters + 1);
+            k_sah_bin<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, s.bins.as<SahBin>());
+            k_sah_split<<<grid_for(ub, 128), 128, 0, st>>>(leaf_max, counters + 1, act_a, s.bins.as<SahBin>(), nlo, nhi, left, right, first, count, counters,
+                                                         act_b, splits, cursors);
+            k_sah_partition<<<grid_for(n), 256, 0, st>>>((int)n, ord_a, pn_a, slot_of, s.prim_lo.as<float4>(), s.prim_hi.as<float4>(), nlo, nhi, left, first,
+                                                         splits, cursors, ord_b, pn_b);
+            k_mark_slots<<<grid_for(ub), 256, 0, st>>>(act_a, counters + 1, slot_of, 1);
+            k_sah_next<<<1, 1, 0, st>>>(counters);
+            c.launches += 7;
+            std::swap(ord_a, ord_b);
+            std::swap(pn_a, pn_b);
+            std::swap(act_a, act_b);
+            if ((level & 7) == 7) {
+                int h = 0;
+                GK_CUDA(cudaMemcpyAsync(&h, counters + 1, 4, cudaMemcpyDeviceToHost, st));
+                GK_CUDA(cudaStreamSynchronize(st));
+                if (h == 0) break;
+            }
+        }
     }
     out.lo = nlo; out.hi = nhi; out.left = left; out.right = right; out.first = first; out.count = count;
     out.order = ord_a;
@@ -717,29 +731,45 @@ int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, const ui
     int* counters = s.counters.as<int>();  // [8] node counter, [9] out-queue count
     int2 *qa = s.queue_a.as<int2>(), *qb = s.queue_b.as<int2>();
     int2 root = make_int2(b.root, 0);
-    int init[2] = {1, 0};
+    int init[3] = {1, 0, 1};  // [8] node4 counter, [9] next-level queue size, [10] this level's queue size
     GK_CUDA(cudaMemcpyAsync(qa, &root, sizeof(root), cudaMemcpyHostToDevice, st));
-    GK_CUDA(cudaMemcpyAsync(counters + 8, init, 8, cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(counters + 8, init, 12, cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemsetAsync(counters + 16, 0, 48 * 4, st));
+    (void)n_prims;
+    int levels_run = 0;
+    for (int level = 0; level < 46; ++level) {
+        const size_t ub = level < 15 ? std::min<size_t>((size_t)n_prims + 1, (size_t)1 << (2 * level)) : (size_t)n_prims + 1;
+        k_collapse_level<<<grid_for(ub, 128), 128, 0, st>>>(qa, counters + 10, qb, counters + 9, counters + 8, b.lo, b.hi, b.left, b.right, b.first, b.count,
+                                                            leaf_max, b.order, remap, remap ? 1 : 0, out, out_lo, out_hi);
+        k_collapse_next<<<1, 1, 0, st>>>(counters, level);
+        c.launches += 2;
+        std::swap(qa, qb);
+        levels_run = level + 1;
+        if ((level & 7) == 7) {
+            int h = 0;
+            GK_CUDA(cudaMemcpyAsync(&h, counters + 10, 4, cudaMemcpyDeviceToHost, st));
+            GK_CUDA(cudaStreamSynchronize(st));
+            if (h == 0) break;
+        }
+    }
+    // level table: counters[16 + L] = first node of level L (level 0 starts at 0, level 1 at 1)
+    int table[48];
+    GK_CUDA(cudaMemcpyAsync(table, counters + 16, 48 * 4, cudaMemcpyDeviceToHost, st));
+    int last[3];
+    GK_CUDA(cudaMemcpyAsync(last, counters + 8, 12, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    if (last[2] != 0) { set_error("BVH collapse did not terminate (tree deeper than 46 wide levels)"); return 1; }
+    // level table: table[L] = first node of BFS level L; table[L + 2] was written after level L had been processed
     info.level_start.clear();
     info.level_start.push_back(0);
-    int nin = 1, total = 1;
-    (void)n_prims;
-    while (nin > 0) {
-        k_collapse_level<<<grid_for(nin, 128), 128, 0, st>>>(qa, nin, qb, counters + 9, counters + 8, b.lo, b.hi, b.left, b.right, b.first, b.count,
-                                                             leaf_max, b.order, remap, remap ? 1 : 0, out, out_lo, out_hi);
-        c.launches += 1;
-        int h[2];
-        GK_CUDA(cudaMemcpyAsync(h, counters + 8, 8, cudaMemcpyDeviceToHost, st));
-        GK_CUDA(cudaStreamSynchronize(st));
-        int zero = 0;
-        GK_CUDA(cudaMemcpyAsync(counters + 9, &zero, 4, cudaMemcpyHostToDevice, st));
-        info.level_start.push_back((uint32_t)total);
-        nin = h[1];
-        total = h[0];
-        std::swap(qa, qb);
+    table[0] = 0;
+    table[1] = 1;
+    for (int L = 1; L <= levels_run + 1 && L < 48; ++L) {
+        if (L > 1 && (uint32_t)table[L] == info.level_start.back()) break;  // no new nodes: the tree ended one level earlier
+        info.level_start.push_back((uint32_t)table[L]);
     }
-    info.level_start.back() = (uint32_t)total;
-    info.node_count = (uint32_t)total;
+    if (info.level_start.back() != (uint32_t)last[0]) { set_error("BVH collapse: inconsistent level table"); return 1; }
+    info.node_count = (uint32_t)last[0];
     return 0;
 }
 

@@ -735,6 +735,28 @@ __global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi
                     busy = false;
                 }
             } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
+        } else if (VARIANT == 4) {
+            // two classes: {node walk, instance entry} vs {triangle leaf}
+            do {
+                const bool live = busy && !T.done;
+                const bool leaf = (T.cur & GK_LEAF_BIT) != 0;
+                const bool wT = live && leaf && T.cur_inst != GK_NO_HIT;
+                const bool wN = live && !wT;
+                const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nT = __popc(__ballot_sync(0xffffffffu, wT));
+                if (nN >= nT) {
+                    if (wN) {
+                        if (!leaf) trav_node_step(T, ts, stack);
+                        else trav_leaf_step(T, ts, stack);
+                    }
+                } else {
+                    if (wT) trav_leaf_step(T, ts, stack);
+                }
+                if (busy && T.done) {
+                    V.hit_tuv[slot] = f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst));
+                    V.hit_prim[slot] = T.best.prim;
+                    busy = false;
+                }
+            } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
         } else {
             do {
                 // phase 1: internal nodes until every busy lane holds a leaf (or has finished)
@@ -989,6 +1011,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
             if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
             else if (c.trace_variant == 1) k_trace<1><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
             else if (c.trace_variant == 3) k_trace<3><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+            else if (c.trace_variant == 4) k_trace<4><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
             else k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
             cudaEventRecord(c.kev[3], st);
             k_shade<<<(n + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
