@@ -108,6 +108,8 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
     for (auto& e : c.ev) cudaEventCreate(&e);
     for (auto& e : c.kev) cudaEventCreate(&e);
+    for (auto& e : c.wev) cudaEventCreate(&e);
+    if (const char* e = getenv("GKCU_WAVE_CHUNK")) c.wave_chunk = std::max(1, std::min(8, atoi(e)));
     if (!c.ubo.reserve(sizeof(GkUniformBufferObject))) { delete ctx; return 1; }
     *out_ctx = ctx;
     return 0;
@@ -134,6 +136,8 @@ int gkcu_destroy(GkcuContext* ctx) {
     for (auto& e : c.ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : c.kev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c.wev)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
     delete ctx;

@@ -37,6 +37,9 @@ static_assert(sizeof(InstanceRec) == 64, "InstanceRec must be 64 bytes");
 #define GK_STACK_SENTINEL 0xFFFFFFFEu
 #define GK_TRAV_STACK 64
 #define GK_NO_HIT 0xFFFFFFFFu
+#ifndef GK_PUSH_ORDERED
+#define GK_PUSH_ORDERED 1
+#endif
 
 struct TraceScene {
     const Node4* tlas;
@@ -53,7 +56,7 @@ struct Hit {
 
 GK_DEV float safe_rcp(float x) {
     if (fabsf(x) < 1e-18f) return x < 0.0f ? -1e18f : 1e18f;
-    return 1.0f / x;
+    return __frcp_rn(x);  // correctly rounded, == 1.0f / x
 }
 GK_DEV float sel3(int k, float3 v) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
 
@@ -148,6 +151,7 @@ struct Trav {
     float3 o, d;       // world-space ray
     float3 ro, rd;     // current-space ray (world or object)
     float3 idir;
+    float3 widir;      // reciprocal world-space direction (restored when an instance is left)
     float tmin, tmax;
     Hit best;
     RayShear sh;
@@ -163,6 +167,7 @@ struct Trav {
 GK_DEV void trav_init(Trav& T, const TraceScene& S, float3 o, float3 d, float tmin, float tmax, bool any) {
     T.o = o; T.d = d; T.ro = o; T.rd = d;
     T.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+    T.widir = T.idir;
     T.tmin = tmin; T.tmax = tmax;
     T.best.t = tmax; T.best.u = 0.0f; T.best.v = 0.0f; T.best.inst = GK_NO_HIT; T.best.prim = 0;
     T.sh.kx = T.sh.ky = T.sh.kz = 0;
@@ -184,7 +189,7 @@ GK_DEV void trav_pop(Trav& T, const TraceScene& S, uint2* stack) {
         if (e.x == GK_STACK_SENTINEL) {
             T.ro = T.o;
             T.rd = T.d;
-            T.idir = f3(safe_rcp(T.rd.x), safe_rcp(T.rd.y), safe_rcp(T.rd.z));
+            T.idir = T.widir;
             T.nodes = reinterpret_cast<const uint4*>(S.tlas);
             T.cur_inst = GK_NO_HIT;
             continue;
@@ -203,24 +208,30 @@ GK_DEV void trav_node_step(Trav& T, const TraceScene& S, uint2* stack) {
     node_test(n0, n1, n2, n3, T.ro, T.idir, T.tmin, T.best.t, tn);
     const uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
     const float inf = __int_as_float(0x7f800000);
-    // nearest child
+    // continue with the nearest child; the second nearest goes on top of the stack, the rest below it in slot order
+    // (entries carry their entry distance, so a far one is culled when it is popped)
     int i0 = 0;
     float t0 = tn[0];
     if (tn[1] < t0) { t0 = tn[1]; i0 = 1; }
     if (tn[2] < t0) { t0 = tn[2]; i0 = 2; }
     if (tn[3] < t0) { t0 = tn[3]; i0 = 3; }
     if (!(t0 < inf)) { trav_pop(T, S, stack); return; }
-    // second nearest goes on top of the stack, the rest below it in index order
-    int i1 = -1;
-    float t1 = inf;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-        if (c != i0 && tn[c] < t1) { t1 = tn[c]; i1 = c; }
-    if (i1 >= 0) {
+    if (GK_PUSH_ORDERED) {
+        int i1 = -1;
+        float t1 = inf;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            if (c != i0 && c != i1 && tn[c] < inf) stack[T.sp++] = make_uint2(ref[c], __float_as_uint(tn[c]));
-        stack[T.sp++] = make_uint2(ref[i1], __float_as_uint(t1));
+            if (c != i0 && tn[c] < t1) { t1 = tn[c]; i1 = c; }
+        if (i1 >= 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c != i0 && c != i1 && tn[c] < inf) stack[T.sp++] = make_uint2(ref[c], __float_as_uint(tn[c]));
+            stack[T.sp++] = make_uint2(ref[i1], __float_as_uint(t1));
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c != i0 && tn[c] < inf) stack[T.sp++] = make_uint2(ref[c], __float_as_uint(tn[c]));
     }
     T.cur = ref[i0];
 }

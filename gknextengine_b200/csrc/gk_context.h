@@ -101,6 +101,8 @@ struct Context {
     GkcuCounters counters{};
     GkcuKernelStats kstats{};
     cudaEvent_t kev[8] = {};
+    cudaEvent_t wev[24] = {};  // trace/shade brackets of the waves of one chunk
+    int wave_chunk = 4;        // waves launched between two host polls of the queue size (GKCU_WAVE_CHUNK)
     cudaEvent_t ev[8] = {};
     uint64_t launches = 0;
     DevBuf trace_rays, trace_hits;

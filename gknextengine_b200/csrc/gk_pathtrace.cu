@@ -714,14 +714,15 @@ __global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi
         } else if (VARIANT == 3) {
             // vote: each iteration the warp executes only the step kind most lanes are waiting for (node walk, instance entry
             // or triangle leaf); lanes in another state sit the iteration out instead of serialising a second code path.
-            do {
+            for (;;) {
                 const bool live = busy && !T.done;
                 const bool leaf = (T.cur & GK_LEAF_BIT) != 0;
                 const bool wN = live && !leaf;
                 const bool wI = live && leaf && T.cur_inst == GK_NO_HIT;
                 const bool wT = live && leaf && T.cur_inst != GK_NO_HIT;
-                const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nI = __popc(__ballot_sync(0xffffffffu, wI)),
-                          nT = __popc(__ballot_sync(0xffffffffu, wT));
+                const unsigned bN = __ballot_sync(0xffffffffu, wN), bI = __ballot_sync(0xffffffffu, wI), bT = __ballot_sync(0xffffffffu, wT);
+                const int nN = __popc(bN), nI = __popc(bI), nT = __popc(bT);
+                if (nN + nI + nT < (drained ? 1 : refill_below)) break;  // too few lanes left: refill (or finish)
                 if (nN >= nT && nN >= nI) {
                     if (wN) trav_node_step(T, ts, stack);
                 } else if (nT >= nI) {
@@ -734,7 +735,7 @@ __global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi
                     V.hit_prim[slot] = T.best.prim;
                     busy = false;
                 }
-            } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
+            }
         } else if (VARIANT == 4) {
             // two classes: {node walk, instance entry} vs {triangle leaf}
             do {
@@ -985,44 +986,51 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     const uint32_t persistent_blocks = (uint32_t)c.sm_count * 8u;
     uint64_t iterations = 0;
     int qi = 0;
-    bool pending = false;  // kev[2..4] hold the previous wave's trace/shade brackets
-    auto collect = [&]() {
-        if (!pending) return;
-        float a = 0, bms = 0;
-        cudaEventElapsedTime(&a, c.kev[2], c.kev[3]);
-        cudaEventElapsedTime(&bms, c.kev[3], c.kev[4]);
-        ks.trace_ms += a;
-        ks.shade_ms += bms;
-        pending = false;
-    };
     if (p.tracer == 0) {
-        // wavefront loop while the wave is wide; k_tail finishes the thin tail in one launch
+        // Wavefront loop while the wave is wide; k_tail finishes the thin tail in one launch. The queue can only shrink (every
+        // path has at most one successor), so the last size the host has seen bounds the grids of the following waves: the
+        // host polls the size only every `wave_chunk` waves and the kernels read the exact size from device memory.
         const uint32_t tail_threshold = std::max<uint32_t>(pixels / 64, (uint32_t)c.sm_count * 128u);
-        for (;;) {
+        const int chunk = std::max(1, std::min(c.wave_chunk, 8));
+        uint32_t bound = pixels;
+        GK_CUDA(cudaMemcpyAsync(b.host_counts, counts + qi, 4, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        bound = b.host_counts[0];
+        while (bound > tail_threshold) {
+            for (int w = 0; w < chunk; ++w) {
+                GK_CUDA(cudaMemsetAsync(counts + 2, 0, 4, st));
+                GK_CUDA(cudaMemsetAsync(counts + (qi ^ 1), 0, 4, st));
+                const uint32_t blocks = std::min<uint32_t>((bound + 127) / 128, persistent_blocks);
+                cudaEventRecord(c.wev[3 * w], st);
+                if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
+                else if (c.trace_variant == 1) k_trace<1><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+                else if (c.trace_variant == 0) k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+                else if (c.trace_variant == 4) k_trace<4><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+                else k_trace<3><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+                cudaEventRecord(c.wev[3 * w + 1], st);
+                k_shade<<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+                cudaEventRecord(c.wev[3 * w + 2], st);
+                // exact size of this wave, for the statistics (read after the chunk's synchronisation)
+                GK_CUDA(cudaMemcpyAsync(b.host_counts + 16 + w, counts + qi, 4, cudaMemcpyDeviceToHost, st));
+                c.launches += 2;
+                qi ^= 1;
+                ++iterations;
+            }
             GK_CUDA(cudaMemcpyAsync(b.host_counts, counts + qi, 4, cudaMemcpyDeviceToHost, st));
             GK_CUDA(cudaStreamSynchronize(st));
-            collect();
-            const uint32_t n = b.host_counts[0];
-            if (n <= tail_threshold) break;
-            GK_CUDA(cudaMemsetAsync(counts + 2, 0, 4, st));
-            GK_CUDA(cudaMemsetAsync(counts + (qi ^ 1), 0, 4, st));
-            const uint32_t blocks = std::min<uint32_t>((n + 127) / 128, persistent_blocks);
-            cudaEventRecord(c.kev[2], st);
-            if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
-            else if (c.trace_variant == 1) k_trace<1><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-            else if (c.trace_variant == 3) k_trace<3><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-            else if (c.trace_variant == 4) k_trace<4><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-            else k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-            cudaEventRecord(c.kev[3], st);
-            k_shade<<<(n + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
-            cudaEventRecord(c.kev[4], st);
-            pending = true;
-            ks.trace_launches++;
-            ks.shade_launches++;
-            ks.trace_rays += n;
-            c.launches += 2;
-            qi ^= 1;
-            ++iterations;
+            for (int w = 0; w < chunk; ++w) {
+                float a = 0, bms = 0;
+                cudaEventElapsedTime(&a, c.wev[3 * w], c.wev[3 * w + 1]);
+                cudaEventElapsedTime(&bms, c.wev[3 * w + 1], c.wev[3 * w + 2]);
+                ks.trace_ms += a;
+                ks.shade_ms += bms;
+                if (b.host_counts[16 + w] > 0) {
+                    ks.trace_launches++;
+                    ks.shade_launches++;
+                    ks.trace_rays += b.host_counts[16 + w];
+                }
+            }
+            bound = b.host_counts[0];
         }
     }
     {
