@@ -125,7 +125,7 @@ int gkcu_destroy(GkcuContext* ctx) {
     for (auto& t : c.textures)
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
-                      &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
+                      &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
                       &c.inst_hi, &c.tlas_active_ids, &c.tex_table, &c.cubes, &c.voxels, &c.ubo, &c.trace_rays, &c.trace_hits};
     for (DevBuf* b : bufs) b->release();
     BuildScratch& s = c.scratch;

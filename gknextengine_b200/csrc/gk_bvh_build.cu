@@ -314,6 +314,32 @@ __global__ void k_write_tris(const uint16_t* __restrict__ simple, const uint32_t
     if (order) tri_prim[i] = p;
 }
 
+// Compact shading record of one primitive (primitive order): what FHardwareRayTracerV2::TraceRay fetches after a hit
+// (assets/shaders/common/Shading.slang:812-820: three indices + three 24-byte vertices) gathered into one 32-byte record:
+// normals 3 x half3, texcoords 3 x half2, material slot of vertex 0. Values are the same fp16 bits the vertex buffer holds.
+__global__ void k_shade_tris(const uint2* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vertex_offset, uint32_t index_offset,
+                             uint32_t n, uint4* __restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint16_t nrm[3][3], uv[3][2];
+    uint32_t slot = 0;
+    for (int k = 0; k < 3; ++k) {
+        uint32_t vi = vertex_offset + indices[index_offset + p * 3 + k];
+        const uint2* v = vertices + (size_t)vi * 3;
+        uint2 a = v[0], b = v[1], c = v[2];
+        nrm[k][0] = (uint16_t)(b.x & 0xFFFF); nrm[k][1] = (uint16_t)(b.x >> 16); nrm[k][2] = (uint16_t)(b.y & 0xFFFF);
+        uv[k][0] = (uint16_t)(a.y >> 16); uv[k][1] = (uint16_t)(b.y >> 16);
+        if (k == 0) slot = (c.y >> 16) & 0xFF;
+    }
+    uint4 r0, r1;
+    r0.x = nrm[0][0] | ((uint32_t)nrm[0][1] << 16); r0.y = nrm[0][2] | ((uint32_t)nrm[1][0] << 16);
+    r0.z = nrm[1][1] | ((uint32_t)nrm[1][2] << 16); r0.w = nrm[2][0] | ((uint32_t)nrm[2][1] << 16);
+    r1.x = nrm[2][2] | ((uint32_t)uv[0][0] << 16); r1.y = uv[0][1] | ((uint32_t)uv[1][0] << 16);
+    r1.z = uv[1][1] | ((uint32_t)uv[2][0] << 16); r1.w = uv[2][1] | (slot << 16);
+    out[(size_t)p * 2] = r0;
+    out[(size_t)p * 2 + 1] = r1;
+}
+
 // Bottom-up refit of one BFS level: child boxes from triangles (leaves) or from the already refitted deeper level.
 __global__ void k_refit_level(Node4* __restrict__ nodes, float4* __restrict__ node_lo, float4* __restrict__ node_hi, uint32_t begin, uint32_t end,
                               const float4* __restrict__ tris) {
@@ -546,7 +572,7 @@ __global__ void k_collapse_next(int* counters, int level) {
 // VkAccelerationStructureInstanceKHR equivalent (TopLevelAccelerationStructure.cpp:83-111): instance i <-> Nodes[i],
 // BLAS = modelId / 10, mask = visible && !nort (RayTraceBaseRenderer.cpp:172-179). Also the world box for the TLAS.
 __global__ void k_instances(const GkNodeProxy* __restrict__ nodes, uint32_t n, const uint4* __restrict__ blas_table, uint32_t model_count,
-                            InstanceRec* __restrict__ inst, float4* __restrict__ lo, float4* __restrict__ hi) {
+                            InstanceRec* __restrict__ inst, float4* __restrict__ lo, float4* __restrict__ hi, uint4* __restrict__ shade_inst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const GkNodeProxy& nd = nodes[i];
@@ -588,6 +614,9 @@ __global__ void k_instances(const GkNodeProxy* __restrict__ nodes, uint32_t n, c
     r.active = active ? 1u : 0u;
     r.blas = blas;
     inst[i] = r;
+    // shading record: where the instance's primitives start in the shade-triangle pool + the node's first material ids
+    shade_inst[(size_t)i * 2] = make_uint4(bt.w, nd.matId[0], nd.matId[1], nd.matId[2]);
+    shade_inst[(size_t)i * 2 + 1] = make_uint4(nd.matId[3], nd.matId[4], nd.matId[5], nd.matId[6]);
     if (active) {
         float4 bl = reinterpret_cast<const float4*>(blas_table)[blas * 3 + 1], bh = reinterpret_cast<const float4*>(blas_table)[blas * 3 + 2];
         float3 mn = f3(FLT_MAX, FLT_MAX, FLT_MAX), mx = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
@@ -803,7 +832,7 @@ int build_all_blas(Context& c) {
     size_t node_cap = total_prims + 2 * (size_t)c.model_count + 4;
     if (!c.blas_nodes.reserve(node_cap * sizeof(Node4)) || !c.blas_node_lo.reserve(node_cap * 16) || !c.blas_node_hi.reserve(node_cap * 16) ||
         !c.blas_tris.reserve((total_prims + 1) * 48) || !c.blas_tri_prim.reserve((total_prims + 1) * 4) ||
-        !c.blas_table.reserve((size_t)(c.model_count + 1) * 48))
+        !c.blas_table.reserve((size_t)(c.model_count + 1) * 48) || !c.shade_tris.reserve((total_prims + 1) * 32))
         return 1;
     cudaEventRecord(c.ev[6], st);
     uint32_t node_base = 0, tri_base = 0;
@@ -814,7 +843,7 @@ int build_all_blas(Context& c) {
         bi.tri_base = tri_base;
         uint32_t n = bi.prim_count;
         uint32_t* tb = reinterpret_cast<uint32_t*>(&table[(size_t)m * 12]);
-        tb[0] = node_base; tb[1] = tri_base; tb[2] = n; tb[3] = 0;
+        tb[0] = node_base; tb[1] = tri_base; tb[2] = n; tb[3] = tri_base;  // shade triangles use the same per-model base, primitive order
         if (n == 0) continue;
         if (n >= (1u << 28)) { set_error("BLAS with >= 2^28 triangles"); return 1; }
         BuildScratch& s = c.scratch;
@@ -829,7 +858,9 @@ int build_all_blas(Context& c) {
         if (collapse(c, b2, n, kBlasLeafMax, nullptr, out, c.blas_node_lo.as<float4>() + node_base, c.blas_node_hi.as<float4>() + node_base, bi)) return 1;
         k_write_tris<<<grid_for(n), 256, 0, st>>>(c.simple.as<uint16_t>(), c.indices.as<uint32_t>(), bi.vertex_offset, bi.index_offset, b2.order, n,
                                                   c.blas_tris.as<float4>() + (size_t)tri_base * 3, c.blas_tri_prim.as<uint32_t>() + tri_base);
-        c.launches += 1;
+        k_shade_tris<<<grid_for(n), 256, 0, st>>>(c.vertices.as<uint2>(), c.indices.as<uint32_t>(), bi.vertex_offset, bi.index_offset, n,
+                                                  c.shade_tris.as<uint4>() + (size_t)tri_base * 2);
+        c.launches += 2;
         float4 rl, rh;
         GK_CUDA(cudaMemcpyAsync(&rl, c.blas_node_lo.as<float4>() + node_base, 16, cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaMemcpyAsync(&rh, c.blas_node_hi.as<float4>() + node_base, 16, cudaMemcpyDeviceToHost, st));
@@ -891,9 +922,9 @@ int build_tlas(Context& c) {
         !reserve_bvh2(s, n) || !c.tlas_nodes.reserve(((size_t)n + 4) * sizeof(Node4)) || !c.tlas_node_lo.reserve(((size_t)n + 4) * 16) ||
         !c.tlas_node_hi.reserve(((size_t)n + 4) * 16))
         return 1;
-    if (!c.inst_lo.reserve((size_t)n * 16) || !c.inst_hi.reserve((size_t)n * 16)) return 1;
+    if (!c.inst_lo.reserve((size_t)n * 16) || !c.inst_hi.reserve((size_t)n * 16) || !c.shade_inst.reserve((size_t)n * 32)) return 1;
     k_instances<<<grid_for(n, 128), 128, 0, st>>>(c.nodes.as<GkNodeProxy>(), n, c.blas_table.as<uint4>(), c.model_count, c.instances.as<InstanceRec>(),
-                                             c.inst_lo.as<float4>(), c.inst_hi.as<float4>());
+                                             c.inst_lo.as<float4>(), c.inst_hi.as<float4>(), c.shade_inst.as<uint4>());
     c.launches += 1;
     // only instances with a non-zero mask enter the TLAS (RayTraceBaseRenderer.cpp:178); their indices were listed by
     // gkcu_update_nodes. The TLAS is built with the SAH-binned builder by default: on RTIO.proc it halves the traversal time

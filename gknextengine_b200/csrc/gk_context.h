@@ -74,7 +74,9 @@ struct Context {
     // acceleration structures
     DevBuf blas_nodes, blas_node_lo, blas_node_hi, blas_tris, blas_tri_prim;  // pools shared by all BLAS
     std::vector<WideBvhInfo> blas;
-    DevBuf blas_table;  // per model: node_base, tri_base, prim_count, pad + root box (2 x float4)
+    DevBuf blas_table;  // per model: node_base, tri_base, prim_count, shade-triangle base + root box (2 x float4)
+    DevBuf shade_tris;  // 32 B per primitive (primitive order): 3 normals + 3 uvs as fp16 + material slot, see gk_pathtrace.cu
+    DevBuf shade_inst;  // 32 B per instance: shade-triangle base + the first 7 material ids of the node
     DevBuf tlas_nodes, tlas_node_lo, tlas_node_hi, instances, inst_lo, inst_hi, tlas_active_ids;
     WideBvhInfo tlas;
     bool tlas_dirty = true;

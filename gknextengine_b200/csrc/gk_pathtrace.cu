@@ -28,6 +28,8 @@ struct SceneView {
     const GkMaterial* materials;
     uint32_t material_count;
     const GkNodeProxy* nodes;
+    const uint4* shade_tris;  // 2 x uint4 per primitive
+    const uint4* shade_inst;  // 2 x uint4 per instance
     const TexDesc* textures;
     uint32_t tex_count;
     const GkAmbientCube* cubes;
@@ -312,17 +314,28 @@ GK_DEV void gen_closest(const SceneView& S, PathRegs& P, bool first) {
 // FHardwareRayTracerV2::TraceRay after the query (Shading.slang:801-823) + the rest of GetRayColor (:1040-1081).
 GK_DEV bool on_closest(const SceneView& S, PathRegs& P, const Hit& h) {
     if (h.inst != GK_NO_HIT) {
-        const GkNodeProxy* node = S.nodes + h.inst;
-        const GkModelData* off = S.offsets + node->modelId;
-        const uint32_t io = off->indexOffset + h.prim * 3, vo = off->vertexOffset;
-        const VtxLite v0 = unpack_vertex(S, vo + __ldg(S.indices + io)), v1 = unpack_vertex(S, vo + __ldg(S.indices + io + 1)),
-                      v2 = unpack_vertex(S, vo + __ldg(S.indices + io + 2));
-        P.mat = fetch_material_id(node, v0.matSlot);
-        float3 n = v0.nrm + (v1.nrm - v0.nrm) * h.u + (v2.nrm - v0.nrm) * h.v;  // Mix(), PreProcessor.slang:24
-        const float* m = S.ts.inst[h.inst].w2o;  // mul(WorldToObject4x3, n) = transpose(w2o 3x3) * n
-        float3 nw = f3(m[0] * n.x + m[4] * n.y + m[8] * n.z, m[1] * n.x + m[5] * n.y + m[9] * n.z, m[2] * n.x + m[6] * n.y + m[10] * n.z);
+        // hit attributes from the compact records (same fp16 bits as Vertices[...] of Shading.slang:812-820)
+        const uint4 si0 = __ldg(S.shade_inst + (size_t)h.inst * 2);
+        const float4* wm = reinterpret_cast<const float4*>(S.ts.inst + h.inst);
+        const float4 m0 = __ldg(wm), m1 = __ldg(wm + 1), m2 = __ldg(wm + 2);
+        const uint4* tp = S.shade_tris + ((size_t)si0.x + h.prim) * 2;
+        const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+        const float3 n0 = f3(h2f(t0.x & 0xFFFF), h2f(t0.x >> 16), h2f(t0.y & 0xFFFF));
+        const float3 n1 = f3(h2f(t0.y >> 16), h2f(t0.z & 0xFFFF), h2f(t0.z >> 16));
+        const float3 n2 = f3(h2f(t0.w & 0xFFFF), h2f(t0.w >> 16), h2f(t1.x & 0xFFFF));
+        const float2 uv0 = make_float2(h2f(t1.x >> 16), h2f(t1.y & 0xFFFF)), uv1 = make_float2(h2f(t1.y >> 16), h2f(t1.z & 0xFFFF)),
+                     uv2 = make_float2(h2f(t1.z >> 16), h2f(t1.w & 0xFFFF));
+        const uint32_t slot = (t1.w >> 16) & 0xFF;
+        if (slot < 3) P.mat = slot == 0 ? si0.y : (slot == 1 ? si0.z : si0.w);
+        else if (slot < 7) {
+            const uint4 si1 = __ldg(S.shade_inst + (size_t)h.inst * 2 + 1);
+            P.mat = slot == 3 ? si1.x : (slot == 4 ? si1.y : (slot == 5 ? si1.z : si1.w));
+        } else P.mat = fetch_material_id(S.nodes + h.inst, slot);
+        float3 n = n0 + (n1 - n0) * h.u + (n2 - n0) * h.v;  // Mix(), PreProcessor.slang:24
+        // mul(WorldToObject4x3, n) = transpose(w2o 3x3) * n
+        float3 nw = f3(m0.x * n.x + m1.x * n.y + m2.x * n.z, m0.y * n.x + m1.y * n.y + m2.y * n.z, m0.z * n.x + m1.z * n.y + m2.z * n.z);
         P.nrm = normalize(nw);
-        float2 uv = v0.uv + (v1.uv - v0.uv) * h.u + (v2.uv - v0.uv) * h.v;
+        float2 uv = uv0 + (uv1 - uv0) * h.u + (uv2 - uv0) * h.v;
         P.pos = P.ro + P.rd * h.t;
         GkMaterial hitMat = get_material(S, P.mat);
         float4 outAlbedo = f4(hitMat.Diffuse.x, hitMat.Diffuse.y, hitMat.Diffuse.z, hitMat.Diffuse.w);
@@ -341,8 +354,8 @@ GK_DEV bool on_closest(const SceneView& S, PathRegs& P, const Hit& h) {
 
 GK_DEV void set_stage(PathRegs& P, uint32_t st) { P.flags = (P.flags & ~FL_STAGE_MASK) | (st << FL_STAGE_SHIFT); }
 
-// Shading.slang:1105-1117: start sample i from the primary-hit record
-GK_DEV void start_sample(const SceneView& S, const PathView& V, uint32_t pixel, PathRegs& P) {
+// Shading.slang:1105-1117: reset the path to the primary hit for sample i (the first GetRayColor follows)
+GK_DEV void begin_sample(const SceneView& S, const PathView& V, uint32_t pixel, PathRegs& P) {
     const float4 pa = V.prim_pos_mat[pixel], pb = V.prim_nrm_cnt[pixel];
     P.rayColor = f4(1, 1, 1, 1);
     float4 eye = mul(S.cam->ModelViewInverse, f4(0, 0, 0, 1));
@@ -351,6 +364,9 @@ GK_DEV void start_sample(const SceneView& S, const PathView& V, uint32_t pixel, 
     P.nrm = f3(pb.x, pb.y, pb.z);
     P.mat = __float_as_uint(pa.w);
     P.bounce = 0;
+}
+GK_DEV void start_sample(const SceneView& S, const PathView& V, uint32_t pixel, PathRegs& P) {
+    begin_sample(S, V, pixel, P);
     set_stage(P, ST_FIRST);
     gen_closest(S, P, true);
 }
@@ -378,88 +394,98 @@ GK_DEV void write_result(const PixelOut& O, const FrameCfg& cfg, const PathView&
 }
 
 // Consumes the result of the pending ray and runs the pixel's program up to its next ray (or to completion).
+// Written so that every heavy piece (hit resolve, direction sampling, sun cone, probe lookup, result write) has exactly one
+// call site: the shade kernel's code must stay inside the instruction cache (ncu: 49 % "no instruction" stalls at 96 KB).
 GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, const PathView& V, uint32_t pixel, PathRegs& P, const Hit& h) {
+    enum { A_END_SAMPLE, A_AFTER_SUN, A_GEN_BOUNCE, A_SUN_RAY, A_DIRECT_RESULT, A_PROBE_END };
     const GkUniformBufferObject* C = S.cam;
     const uint32_t stage = (P.flags & FL_STAGE_MASK) >> FL_STAGE_SHIFT;
     const bool primDielectric = (P.flags & FL_PRIM_DIELECTRIC) != 0;
-    bool after_sun = false;
-    if (stage == ST_FIRST) {
-        bool exitFirst = on_closest(S, P, h);
-        if (!exitFirst) {
-            if (cfg.exit_after_first && !primDielectric) {
-                P.rayColor = P.rayColor * interpolateAmbientCubesV2(S, P.pos, P.nrm);  // :1120-1123
-            } else {
-                P.bounce = 1;
-                if (1u < P.maxBounces) {
-                    set_stage(P, ST_BOUNCE);
-                    gen_closest(S, P, false);
-                    return REQ_CLOSEST;
+    const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
+    const float4 sunColor = f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w);
+    int action = A_END_SAMPLE;
+    float shadow = 0.0f;
+    bool direct_stage = false;
+    if (stage == ST_DIRECT) {  // FHardwareDirectIlluminatorV2::DirectIlluminate, :886-908
+        shadow = (h.inst == GK_NO_HIT) ? 1.0f : 0.0f;
+        action = A_DIRECT_RESULT;
+    } else if (stage == ST_SUN) {  // :1139-1143
+        if (h.inst == GK_NO_HIT) P.rayColor = P.rayColor * sunColor;
+        else action = A_AFTER_SUN;
+    } else {
+        const bool exited = on_closest(S, P, h);
+        if (stage == ST_FIRST) {
+            if (!exited) {
+                if (cfg.exit_after_first && !primDielectric) action = A_PROBE_END;  // :1120-1123
+                else {
+                    P.bounce = 1;
+                    if (1u < P.maxBounces) action = A_GEN_BOUNCE;
                 }
             }
+        } else if (!exited) {  // :1130-1144
+            if (C->HasSun && (RandomFloat(P.rng) < 0.5f)) action = A_SUN_RAY;
+            else action = A_AFTER_SUN;
         }
-    } else if (stage == ST_BOUNCE) {
-        if (on_closest(S, P, h)) {
-            // :1130-1133 break
-        } else if (C->HasSun && (RandomFloat(P.rng) < 0.5f)) {  // :1135-1144
-            const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
-            const float3 cone = AlignWithNormal(RandomInCone(P.rng, GK_COS_QUARTER_DEGREE), lightVector);
-            P.ro = P.pos + P.nrm * 0.0f;  // TRACE_CORRECTION_OFFSET
-            P.rd = cone;
-            set_stage(P, ST_SUN);
-            return REQ_ANY;
-        } else after_sun = true;
-    } else if (stage == ST_SUN) {
-        if (h.inst == GK_NO_HIT) P.rayColor = P.rayColor * f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w);
-        else after_sun = true;
-    } else {  // ST_DIRECT: FHardwareDirectIlluminatorV2::DirectIlluminate, :886-908
-        const float4 pb = V.prim_nrm_cnt[pixel];
-        const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
-        const float d = fmaxf(dot(lightVector, normalize(f3(pb.x, pb.y, pb.z))), 0.0f) * GK_M_1_PI;
-        const float shadow = (h.inst == GK_NO_HIT) ? 1.0f : 0.0f;
-        write_result(O, cfg, V, pixel, f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w) * d * shadow);
-        return REQ_DONE;
     }
-    if (after_sun) {  // :1146-1154
+    if (action == A_AFTER_SUN) {  // :1146-1154
         const bool earlyExit = !primDielectric && (RandomFloat(P.rng) < 0.5f);  // ExitProbability
-        if (P.bounce == P.maxBounces - 1u || earlyExit) {
-            P.rayColor = P.rayColor * interpolateAmbientCubesV2(S, P.pos, P.nrm);
-        } else {
+        if (P.bounce == P.maxBounces - 1u || earlyExit) action = A_PROBE_END;
+        else {
             P.bounce++;
-            gen_closest(S, P, false);
-            set_stage(P, ST_BOUNCE);
-            return REQ_CLOSEST;
+            action = A_GEN_BOUNCE;
         }
     }
-    // end of sample, :1159-1171: fold the path into the pixel's running sums
-    if (P.flags & FL_HIT_METAL) P.rayColor = P.rayColor * V.prim_albedo[pixel];
-    {
+    if (action == A_PROBE_END) {
+        P.rayColor = P.rayColor * interpolateAmbientCubesV2(S, P.pos, P.nrm);
+        action = A_END_SAMPLE;
+    }
+    bool first = false;
+    if (action == A_END_SAMPLE) {  // :1159-1171: fold the path into the pixel's running sums
+        if (P.flags & FL_HIT_METAL) P.rayColor = P.rayColor * V.prim_albedo[pixel];
         float4* acc = (P.flags & FL_HIT_REFLECT) ? V.final_refl + pixel : V.final_color + pixel;
         *acc = *acc + P.rayColor;
+        const uint32_t sampleEnd = __float_as_uint(V.prim_nrm_cnt[pixel].w) & 0xFFFFu;
+        P.sample++;
+        if (P.sample < sampleEnd) {
+            begin_sample(S, V, pixel, P);
+            first = true;
+            action = A_GEN_BOUNCE;
+        } else if (cfg.rank != 0) {  // all samples done, :1175-1183; only rank 0 owns the direct term
+            shadow = 0.0f;
+            action = A_DIRECT_RESULT;
+            direct_stage = true;
+        } else if (C->HasSun) {
+            direct_stage = true;
+            action = A_SUN_RAY;
+        } else {
+            shadow = 0.0f;
+            action = A_DIRECT_RESULT;
+        }
     }
-    const float4 pb = V.prim_nrm_cnt[pixel];
-    const uint32_t sampleEnd = __float_as_uint(pb.w) & 0xFFFFu;
-    P.sample++;
-    if (P.sample < sampleEnd) {
-        start_sample(S, V, pixel, P);
-        return REQ_CLOSEST;
-    }
-    // all samples done, :1175-1183
-    if (cfg.rank != 0) {
-        write_result(O, cfg, V, pixel, f4(0, 0, 0, 0));
-        return REQ_DONE;
-    }
-    const float3 lightVector = f3(C->SunDirection.x, C->SunDirection.y, C->SunDirection.z);
-    if (C->HasSun) {
+    if (action == A_SUN_RAY) {  // cone-jittered shadow ray towards the sun: the bounce-loop NEE (:1137-1139) or DirectIlluminate (:897-899)
         const float3 cone = AlignWithNormal(RandomInCone(P.rng, GK_COS_QUARTER_DEGREE), lightVector);
-        const float4 pa = V.prim_pos_mat[pixel];
-        P.ro = f3(pa.x, pa.y, pa.z);
+        if (direct_stage) {
+            const float4 pa = V.prim_pos_mat[pixel];
+            P.ro = f3(pa.x, pa.y, pa.z);
+            set_stage(P, ST_DIRECT);
+        } else {
+            P.ro = P.pos + P.nrm * 0.0f;  // TRACE_CORRECTION_OFFSET
+            set_stage(P, ST_SUN);
+        }
         P.rd = cone;
-        set_stage(P, ST_DIRECT);
         return REQ_ANY;
     }
-    const float d = fmaxf(dot(lightVector, normalize(f3(pb.x, pb.y, pb.z))), 0.0f) * GK_M_1_PI;
-    write_result(O, cfg, V, pixel, f4(C->SunColor.x, C->SunColor.y, C->SunColor.z, C->SunColor.w) * d * 0.0f);
-    return REQ_DONE;
+    if (action == A_DIRECT_RESULT) {
+        const float4 pb = V.prim_nrm_cnt[pixel];
+        const float d = fmaxf(dot(lightVector, normalize(f3(pb.x, pb.y, pb.z))), 0.0f) * GK_M_1_PI;
+        const bool zero = cfg.rank != 0 && direct_stage;
+        write_result(O, cfg, V, pixel, zero ? f4(0, 0, 0, 0) : sunColor * d * shadow);
+        return REQ_DONE;
+    }
+    // A_GEN_BOUNCE: the next GetRayColor (first of a sample or a bounce), single call site
+    set_stage(P, first ? ST_FIRST : ST_BOUNCE);
+    gen_closest(S, P, first);
+    return REQ_CLOSEST;
 }
 
 // ------------------------------------------------------------------------------------------------ state I/O
@@ -901,6 +927,8 @@ SceneView make_scene_view(const Context& c) {
     S.materials = c.materials.as<GkMaterial>();
     S.material_count = c.material_count;
     S.nodes = c.nodes.as<GkNodeProxy>();
+    S.shade_tris = c.shade_tris.as<uint4>();
+    S.shade_inst = c.shade_inst.as<uint4>();
     S.textures = c.tex_table.as<TexDesc>();
     S.tex_count = c.tex_count;
     S.cubes = c.has_probes ? c.cubes.as<GkAmbientCube>() : nullptr;
