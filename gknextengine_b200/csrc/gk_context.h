@@ -83,7 +83,7 @@ struct Context {
     bool frame_built_tlas = false;
     bool blas_built = false;
     BuildScratch scratch;
-    int trace_variant = 3;  // GKCU_TRACE_VARIANT: 3 vote-selected step kind (default); 0 one step per iteration; 1 while-while; 2 warp-granular batches
+    int trace_variant = 5;  // GKCU_TRACE_VARIANT: 5 vote-selected step kind at <= 64 registers, 8 blocks/SM (default); 3 same at 72 registers; 0 one step per iteration; 1 while-while; 2 warp-granular batches
     int refill_below = 24;  // k_trace: refill idle lanes when fewer than this many lanes are busy (GKCU_REFILL)
     int blas_builder = 1;  // 0 = LBVH, 1 = SAH-binned (GKCU_BLAS_BUILDER=lbvh|sah)
 

@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S, RTView R, PathView
 // from serialising against each other, and lanes whose ray has terminated pull the next ray from the queue (one atomic per
 // warp) as soon as the number of busy lanes drops below `refill_below`.
 template <int VARIANT>
-__global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below) {
+__global__ void __launch_bounds__(128, VARIANT == 5 ? 8 : 1) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below) {
     const uint32_t n = V.counts[qi];
     const int lane = threadIdx.x & 31;
     const float4* ray_o = V.ray_o + (size_t)qi * half;
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(128) k_trace(TraceScene ts, PathView V, int qi
                     busy = false;
                 }
             } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
-        } else if (VARIANT == 3) {
+        } else if (VARIANT == 3 || VARIANT == 5) {
             // vote: each iteration the warp executes only the step kind most lanes are waiting for (node walk, instance entry
             // or triangle leaf); lanes in another state sit the iteration out instead of serialising a second code path.
             for (;;) {
@@ -1034,6 +1034,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 else if (c.trace_variant == 1) k_trace<1><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 else if (c.trace_variant == 0) k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 else if (c.trace_variant == 4) k_trace<4><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+                else if (c.trace_variant == 5) k_trace<5><<<std::min<uint32_t>((bound + 127) / 128, (uint32_t)c.sm_count * 16u), 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 else k_trace<3><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 cudaEventRecord(c.wev[3 * w + 1], st);
                 k_shade<<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
