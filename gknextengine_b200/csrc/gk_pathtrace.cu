@@ -824,7 +824,8 @@ __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V,
 }
 
 // Shade: one thread per queue slot: consume the hit, advance the path to its next ray, compact the survivors into the other queue.
-__global__ void __launch_bounds__(128) k_shade(SceneView S, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_shade(SceneView S, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
     const uint32_t n = V.counts[qi];
     PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
     uint32_t nclosest = 0, nany = 0;
@@ -1037,7 +1038,11 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 else if (c.trace_variant == 5) k_trace<5><<<std::min<uint32_t>((bound + 127) / 128, (uint32_t)c.sm_count * 16u), 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 else k_trace<3><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 cudaEventRecord(c.wev[3 * w + 1], st);
-                k_shade<<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+                if (c.shade_minb == 8) k_shade<8><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+                else if (c.shade_minb == 7) k_shade<7><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+                else if (c.shade_minb == 6) k_shade<6><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+                else if (c.shade_minb == 10) k_shade<10><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+                else k_shade<1><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
                 cudaEventRecord(c.wev[3 * w + 2], st);
                 // exact size of this wave, for the statistics (read after the chunk's synchronisation)
                 GK_CUDA(cudaMemcpyAsync(b.host_counts + 16 + w, counts + qi, 4, cudaMemcpyDeviceToHost, st));
