@@ -104,6 +104,7 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     c.device = device_ordinal;
     c.sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("GKCU_TRACE_VARIANT")) c.trace_variant = atoi(e);
+    if (const char* e = getenv("GKCU_TMA")) c.use_tma = atoi(e);
     if (const char* e = getenv("GKCU_SHADE_MINB")) c.shade_minb = atoi(e);
     if (const char* e = getenv("GKCU_REFILL")) c.refill_below = std::max(1, std::min(32, atoi(e)));
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }

@@ -84,6 +84,7 @@ struct Context {
     bool blas_built = false;
     BuildScratch scratch;
     int trace_variant = 5;  // GKCU_TRACE_VARIANT: 5 vote-selected step kind at <= 64 registers, 8 blocks/SM (default); 3 same at 72 registers; 0 one step per iteration; 1 while-while; 2 warp-granular batches
+    int use_tma = 1;        // GKCU_TMA=0 falls back to plain-load staging of the stencil tiles (2 / 3: only reproject / only denoise)
     int shade_minb = 7;     // GKCU_SHADE_MINB: 8 compiles k_shade for 8 blocks/SM (<= 64 registers)
     int refill_below = 24;  // k_trace: refill idle lanes when fewer than this many lanes are busy (GKCU_REFILL)
     int blas_builder = 1;  // 0 = LBVH, 1 = SAH-binned (GKCU_BLAS_BUILDER=lbvh|sah)

@@ -6,6 +6,7 @@
 // The "copy pass" (ACCUM -> PREV x3, PathTracingRenderer.cpp:160-182) and the object-id copy (VulkanBaseRenderer.cpp:1136-1152)
 // are pointer swaps done by the caller; ReProject therefore writes ACCUM.a = PREV.a where the reference leaves alpha untouched.
 #include "gk_context.h"
+#include "gk_tma.cuh"
 
 using namespace gkd;
 
@@ -18,6 +19,10 @@ constexpr int RH = 2;                       // 5x5 spatial filter halo
 constexpr int RTW = RBX + 2 * RH, RTH = RBY + 2 * RH;
 constexpr int RMH = 4;                      // motion-vector taps at 2 * offset
 constexpr int RMW = RBX + 2 * RMH, RMHH = RBY + 2 * RMH;
+// TMA: the first column of a box must start on a 16-byte boundary in global memory (measured on sm_100a: a box starting at
+// column -2 of a 4-byte image, or column -5 of an 8-byte image, raises "illegal instruction"; scripts/tma_test3.cu), so the
+// object-id tile is loaded with a 4-column halo and the denoise tile with a 6-column halo.
+constexpr int RIH = 4, RIW = RBX + 2 * RIH;
 
 struct ReprojArgs {
     int w, h;
@@ -156,9 +161,117 @@ __global__ void __launch_bounds__(RBX* RBY) k_reproject(ReprojArgs A) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ ReProject, TMA-staged
+// Same arithmetic as k_reproject, different staging: one elected thread issues five cp.async.bulk.tensor copies (tile + halo of
+// SINGLE_DIFFUSE, SINGLE_SPECULAR, NORMAL, OBJECTID_0 and the wider motion-vector tile) onto one mbarrier; the hardware
+// zero-fills everything outside the image. The raw fp16 tiles are converted to float once (every texel is read by up to 25
+// threads), and the tap loops are unrolled at compile time (RANGE = 2, or 0 for FastReproject).
+struct ReprojMaps { CUtensorMap diff, spec, norm, ids, motion; };
+
+template <int RANGE>
+__global__ void __launch_bounds__(RBX* RBY) k_reproject_tma(const __grid_constant__ ReprojMaps M, ReprojArgs A) {
+    __shared__ alignas(128) uint2 r_diff[RTH][RTW];
+    __shared__ alignas(128) uint2 r_spec[RTH][RTW];
+    __shared__ alignas(128) uint2 r_norm[RTH][RTW];
+    __shared__ alignas(128) uint32_t s_id[RTH][RIW];
+    __shared__ alignas(128) float2 r_motion[RMHH][RMW];
+    __shared__ float4 s_diff[RTH][RTW];
+    __shared__ float4 s_spec[RTH][RTW];
+    __shared__ float4 s_norm[RTH][RTW];
+    __shared__ float s_mlen[RMHH][RMW];
+    __shared__ uint64_t bar;
+    const int w = A.w, h = A.h;
+    const int bx0 = blockIdx.x * RBX, by0 = blockIdx.y * RBY;
+    const int tid = threadIdx.y * RBX + threadIdx.x;
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    if (tid == 0) gktma::mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        gktma::mbar_expect_tx(&bar, (uint32_t)(sizeof(r_diff) + sizeof(r_spec) + sizeof(r_norm) + sizeof(s_id) + sizeof(r_motion)));
+        gktma::tma_load_2d(r_diff, &M.diff, bx0 - RH, by0 - RH, &bar);
+        gktma::tma_load_2d(r_spec, &M.spec, bx0 - RH, by0 - RH, &bar);
+        gktma::tma_load_2d(r_norm, &M.norm, bx0 - RH, by0 - RH, &bar);
+        gktma::tma_load_2d(s_id, &M.ids, bx0 - RIH, by0 - RH, &bar);
+        gktma::tma_load_2d(r_motion, &M.motion, bx0 - RMH, by0 - RMH, &bar);
+    }
+    gktma::mbar_wait(&bar, 0);
+    auto h4 = [](uint2 v) {
+        __half2 a = *reinterpret_cast<__half2*>(&v.x), b = *reinterpret_cast<__half2*>(&v.y);
+        float2 fa = __half22float2(a), fb = __half22float2(b);
+        return f4(fa.x, fa.y, fb.x, fb.y);
+    };
+    for (int i = tid; i < RTW * RTH; i += RBX * RBY) {
+        int ty = i / RTW, tx = i % RTW;
+        s_diff[ty][tx] = h4(r_diff[ty][tx]);
+        s_spec[ty][tx] = h4(r_spec[ty][tx]);
+        s_norm[ty][tx] = h4(r_norm[ty][tx]);
+    }
+    for (int i = tid; i < RMW * RMHH; i += RBX * RBY) {
+        int ty = i / RMW, tx = i % RMW;
+        s_mlen[ty][tx] = length(r_motion[ty][tx]);
+    }
+    __syncthreads();
+    if (x >= w || y >= h) return;
+    const size_t idx = (size_t)y * w + x;
+    const int lx = threadIdx.x + RH, ly = threadIdx.y + RH;
+    float4 currDiffuseSample = s_diff[ly][lx], currSpecularSample = s_spec[ly][lx], currAlbedoSample = load_h4(A.albedo, idx);
+    bool useHistory = true;
+    float2 motion = r_motion[threadIdx.y + RMH][threadIdx.x + RMH];
+    int pvx = (int)floorf((float)x + motion.x), pvy = (int)floorf((float)y + motion.y);
+    const bool inside = ((uint32_t)pvx < (uint32_t)w) && ((uint32_t)pvy < (uint32_t)h) && pvx >= -1 && pvy >= -1;
+    uint32_t cur = s_id[ly][lx + (RIH - RH)];
+    uint32_t prev0 = ldu(A.objectid1, pvx, pvy, w, h);
+    const bool miss = cur == 65535u;
+    uint32_t moment = A.moment[idx];
+    if (miss || !inside || moment > 0) useHistory = false;
+    if (useHistory) {
+        const float3 CenterNormal = xyz(s_norm[ly][lx]);
+        float4 spatialDiffuseSample = f4(0, 0, 0, 0), spatialSpecularSample = f4(0, 0, 0, 0);
+        float totalWeight = 0.0f, motionInRange = 0;
+#pragma unroll
+        for (int yy = -RANGE; yy <= RANGE; yy++) {
+#pragma unroll
+            for (int xx = -RANGE; xx <= RANGE; xx++) {
+                const uint32_t primitiveIdx = s_id[ly + yy][lx + xx + (RIH - RH)];
+                const float3 worldNormal = xyz(s_norm[ly + yy][lx + xx]);
+                const bool isCenter = (xx == 0 && yy == 0);
+                const bool sameObject = (primitiveIdx == cur);
+                const float centerDist = sqrtf((float)(xx * xx + yy * yy));  // length(float2(x, y)), folded at compile time
+                const float weight = calculateWeight(centerDist, sameObject, isCenter, worldNormal, CenterNormal);
+                spatialDiffuseSample = spatialDiffuseSample + s_diff[ly + yy][lx + xx] * weight;
+                spatialSpecularSample = spatialSpecularSample + s_spec[ly + yy][lx + xx] * weight;
+                totalWeight += weight;
+                motionInRange += s_mlen[threadIdx.y + RMH + yy * 2][threadIdx.x + RMH + xx * 2];
+            }
+        }
+        spatialDiffuseSample = spatialDiffuseSample / totalWeight;
+        spatialSpecularSample = spatialSpecularSample / totalWeight;
+        uint32_t prev1 = ldu(A.objectid1, pvx + 1, pvy, w, h), prev2 = ldu(A.objectid1, pvx, pvy + 1, w, h), prev3 = ldu(A.objectid1, pvx + 1, pvy + 1, w, h);
+        if (fabsf(motionInRange) < 0.1f) prev0 = prev1 = prev2 = prev3 = cur;
+        float2 pos = make_float2((float)x + motion.x, (float)y + motion.y);
+        float2 subpixel = make_float2(pos.x - floorf(pos.x), pos.y - floorf(pos.y));
+        float3 historyDiffuse = FilterHistoryColor(A.prev_diffuse, w, h, subpixel, pvx, pvy, cur, prev0, prev1, prev2, prev3, spatialDiffuseSample);
+        float3 historySpecular = FilterHistoryColor(A.prev_specular, w, h, subpixel, pvx, pvy, cur, prev0, prev1, prev2, prev3, spatialSpecularSample);
+        float3 historyAlbedo = FilterHistoryColor(A.prev_albedo, w, h, subpixel, pvx, pvy, cur, prev0, prev1, prev2, prev3, currAlbedoSample);
+        float currKeep = clampf(1.0f / (float)max(1, A.temporal_frames), 0.0f, 1.0f);
+        float3 d = lerp3(historyDiffuse, xyz(currDiffuseSample), currKeep);
+        float3 s = lerp3(historySpecular, xyz(currSpecularSample), currKeep);
+        float3 a = lerp3(historyAlbedo, xyz(currAlbedoSample), currKeep);
+        store_h4(A.accum_diffuse, idx, f4(d.x, d.y, d.z, load_h4(A.prev_diffuse, idx).w));
+        store_h4(A.accum_specular, idx, f4(s.x, s.y, s.z, load_h4(A.prev_specular, idx).w));
+        store_h4(A.accum_albedo, idx, f4(a.x, a.y, a.z, load_h4(A.prev_albedo, idx).w));
+    } else {
+        store_h4(A.accum_diffuse, idx, currDiffuseSample);
+        store_h4(A.accum_specular, idx, currSpecularSample);
+        store_h4(A.accum_albedo, idx, currAlbedoSample);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ DenoiseJBF
 constexpr int DBX = 32, DBY = 8, DR = 5;
 constexpr int DTW = DBX + 2 * DR, DTH = DBY + 2 * DR;
+constexpr int DRP = 6, DTWP = DBX + 2 * DRP;  // TMA box: 6-column halo so that the box starts 16-byte aligned
 
 struct DenoiseArgs {
     int w, h;
@@ -265,6 +378,72 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
     }
 }
 
+
+// DenoiseJBF with the 42x18 ACCUM_DIFFUSE tile staged by one TMA copy (zero fill outside the image).
+__global__ void __launch_bounds__(DBX* DBY) k_denoise_tma(const __grid_constant__ CUtensorMap map_diffuse, DenoiseArgs A) {
+    __shared__ alignas(128) uint2 raw[DTH][DTWP];
+    __shared__ float4 s_diff[DTH][DTW];  // rgb + 0.001 bias, luminance in w
+    __shared__ uint64_t bar;
+    const GkUniformBufferObject* C = A.cam;
+    const int w = A.w, h = A.h;
+    const int gx0 = (int)C->ViewportRect.x, gy0 = (int)C->ViewportRect.y;
+    const int bx0 = blockIdx.x * DBX + gx0, by0 = blockIdx.y * DBY + gy0;
+    const int tid = threadIdx.y * DBX + threadIdx.x;
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    if (tid == 0) gktma::mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        gktma::mbar_expect_tx(&bar, (uint32_t)sizeof(raw));
+        gktma::tma_load_2d(raw, &map_diffuse, bx0 - DRP, by0 - DR, &bar);
+    }
+    gktma::mbar_wait(&bar, 0);
+    for (int i = tid; i < DTW * DTH; i += DBX * DBY) {
+        int ty = i / DTW, tx = i % DTW;
+        uint2 v = raw[ty][tx + (DRP - DR)];
+        __half2 a = *reinterpret_cast<__half2*>(&v.x), b = *reinterpret_cast<__half2*>(&v.y);
+        float2 fa = __half22float2(a), fb = __half22float2(b);
+        float3 c = f3(fa.x, fa.y, fb.x) + f3(0.001f, 0.001f, 0.001f);  // FetchDiffuse, :14-17
+        s_diff[ty][tx] = f4(c.x, c.y, c.z, dot(c, f3(0.212671f, 0.715160f, 0.072169f)));
+    }
+    __syncthreads();
+    if (!inb(x, y, w, h)) return;
+    const size_t idx = (size_t)y * w + x;
+    const int ly = threadIdx.y + DR, lx = threadIdx.x + DR;
+    const float CenterLum = s_diff[ly][lx].w;
+    const float3 CenterSpec = xyz(load_h4(A.accum_specular, idx)) + f3(0.001f, 0.001f, 0.001f);
+    const float sigma = C->BFSigma, sigmaL = C->BFSigmaLum * 100.0f;
+    float3 Total = f3(0, 0, 0);
+    float Weight = 0;
+#pragma unroll
+    for (int i = -DR; i <= DR; i += 2) {
+#pragma unroll
+        for (int j = -DR; j <= DR; j += 2) {
+            const float4 t = s_diff[ly + i][lx + j];
+            const float3 Ci = xyz(t);
+            const float lumi = t.w;
+            const float dist = clampf(float(i * i + j * j) / float(DR * DR), 0.0f, 1.0f);
+            const float dlum = (CenterLum - lumi) * (CenterLum - lumi);
+            const float Fi = expf(-dist * dist / (2.0f * sigma * sigma));
+            const float Li = expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
+            Total = Total + Ci * Fi * Li;
+            Weight += Fi * Li;
+        }
+    }
+    Total = f3(Total.x / Weight, Total.y / Weight, Total.z / Weight);
+    if (!C->DebugDraw_Lighting) Total = Total * xyz(load_h4(A.accum_albedo, idx)) + CenterSpec;
+    if (C->HDR) {
+        Total = f3(Total.x / 2000.0f, Total.y / 2000.0f, Total.z / 2000.0f);
+        Total = GT_Tonemapping(Total);
+        Total = Total * 2000.0f;
+        float3 pw = Total * C->PaperWhiteNit;
+        store_h4(A.denoised, idx, f4(ST2084(pw.x / 230.0f), ST2084(pw.y / 230.0f), ST2084(pw.z / 230.0f), 1.0f));
+    } else {
+        float3 pw = Total * C->PaperWhiteNit;
+        float3 t = GT_Tonemapping(f3(pw.x / 40000.0f, pw.y / 40000.0f, pw.z / 40000.0f));
+        store_h4(A.denoised, idx, f4(t.x, t.y, t.z, 1.0f));
+    }
+}
+
 }  // namespace
 
 int run_reproject(Context& c, const GkcuFrameParams& p) {
@@ -278,14 +457,26 @@ int run_reproject(Context& c, const GkcuFrameParams& p) {
     A.motion = t.motion; A.moment = t.moment;
     A.progressive = p.progressive; A.fast_reproject = p.fast_reproject; A.temporal_frames = p.temporal_frames;
     dim3 grid((t.w + RBX - 1) / RBX, (t.h + RBY - 1) / RBY), block(RBX, RBY);
-    k_reproject<<<grid, block, 0, c.stream>>>(A);
+    // TMA staging needs 16-byte aligned rows (even width for the 8-byte pixels, width % 4 == 0 for the 4-byte ids)
+    ReprojMaps M;
+    const bool tma = (c.use_tma == 1 || c.use_tma == 2) && !p.progressive && (t.w % 4 == 0) &&
+                     gktma::encode_2d(&M.diff, t.single_diffuse, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, t.w, t.h, RTW, RTH) &&
+                     gktma::encode_2d(&M.spec, t.single_specular, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, t.w, t.h, RTW, RTH) &&
+                     gktma::encode_2d(&M.norm, t.normal, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, t.w, t.h, RTW, RTH) &&
+                     gktma::encode_2d(&M.ids, t.objectid[t.cur], CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, t.w, t.h, RIW, RTH) &&
+                     gktma::encode_2d(&M.motion, t.motion, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, t.w, t.h, RMW, RMHH);
+    if (tma) {
+        if (p.fast_reproject) k_reproject_tma<0><<<grid, block, 0, c.stream>>>(M, A);
+        else k_reproject_tma<2><<<grid, block, 0, c.stream>>>(M, A);
+    } else {
+        k_reproject<<<grid, block, 0, c.stream>>>(A);
+    }
     c.launches++;
     GK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int run_denoise(Context& c, const GkUniformBufferObject& ubo) {
-    (void)ubo;
     RenderTargets& t = c.rt;
     DenoiseArgs A;
     A.w = (int)t.w; A.h = (int)t.h;
@@ -293,7 +484,11 @@ int run_denoise(Context& c, const GkUniformBufferObject& ubo) {
     A.denoised = t.denoised;
     A.cam = c.ubo.as<GkUniformBufferObject>();
     dim3 grid((t.w + DBX - 1) / DBX, (t.h + DBY - 1) / DBY), block(DBX, DBY);
-    k_denoise<<<grid, block, 0, c.stream>>>(A);
+    CUtensorMap map;
+    if ((c.use_tma == 1 || c.use_tma == 3) && ubo.BFSize > 0 && (t.w % 2 == 0) && ((int)ubo.ViewportRect.x % 2 == 0) && gktma::encode_2d(&map, t.accum_diffuse[t.cur], CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, t.w, t.h, DTWP, DTH))
+        k_denoise_tma<<<grid, block, 0, c.stream>>>(map, A);
+    else
+        k_denoise<<<grid, block, 0, c.stream>>>(A);
     c.launches++;
     GK_CUDA(cudaGetLastError());
     return 0;

@@ -175,10 +175,10 @@ def test_depth_of_field_and_fast_gather_with_probes(renderer):
     assert sd[..., :3].max() > 0
 
 
-def test_stencil_passes_on_random_inputs(renderer):
+@pytest.mark.parametrize("W,H", [(203, 117), (204, 118), (512, 64)])  # odd width: plain-load staging; width % 4 == 0: TMA staging
+def test_stencil_passes_on_random_inputs(renderer, W, H):
     """ReProject + DenoiseJBF alone on random storage-image contents (incl. out-of-bounds history fetches, id mismatches,
-    non-zero moments): ACCUM_* bit-exact, RT_DENOISED within 2 fp16 ulps."""
-    W, H = 203, 117  # not a multiple of the tile sizes
+    non-zero moments): ACCUM_* bit-exact, RT_DENOISED within 2 fp16 ulps. Sizes are not multiples of the tile sizes."""
     scene = host.Scene("CornellBox.proc", denoiser=True)
     renderer.CreateSwapChain((W, H))
     ofr = O.OracleFrame(W, H)
