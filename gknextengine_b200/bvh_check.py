@@ -1,22 +1,21 @@
 """Host-side structural validation of the GPU-built acceleration structures (used by tests/ and bring-up scripts).
 
 Node4 layout: gknextengine_b200/csrc/gk_bvh.cuh. Checks: every primitive / instance is referenced exactly once, and every
-quantised child box contains what lies below it.
+child box contains what lies below it.
 """
 import numpy as np
 
-NODE_DTYPE = np.dtype([("o", "<f4", 3), ("e", "u1", 4), ("child", "<u4", 4), ("qlo", "u1", (3, 4)), ("qhi", "u1", (3, 4)), ("pad", "<u4", 2)])
+NODE_DTYPE = np.dtype([("planes", "<f4", (3, 2, 4)), ("child", "<u4", 4), ("n", "<u4"), ("pad", "<u4", 3)])  # planes[axis][lo|hi][child]
+NODE_BYTES = NODE_DTYPE.itemsize
+assert NODE_BYTES == 128
 INST_DTYPE = np.dtype([("w2o", "<f4", (3, 4)), ("node_base", "<u4"), ("tri_base", "<u4"), ("active", "<u4"), ("blas", "<u4")])
 LEAF = 0x80000000
 EMPTY = 0xFFFFFFFF
 
 
 def child_boxes(node):
-    scale = np.ldexp(1.0, node["e"][:3].astype(np.int32) - 127).astype(np.float64)
-    o = node["o"].astype(np.float64)
-    lo = o[:, None] + node["qlo"].astype(np.float64) * scale[:, None]
-    hi = o[:, None] + node["qhi"].astype(np.float64) * scale[:, None]
-    return lo.T, hi.T  # [child][axis]
+    pl = node["planes"].astype(np.float64)
+    return pl[:, 0, :].T, pl[:, 1, :].T  # [child][axis]
 
 
 def walk(nodes, leaf_box_fn, tol=1e-5):
@@ -43,10 +42,12 @@ def walk(nodes, leaf_box_fn, tol=1e-5):
                     viol += 1
                 leaves.append((first, count))
             else:
-                # the child node's own grid starts at its float box min, which must lie inside the box its parent stores for it
-                co = nodes[ref]["o"].astype(np.float64)
-                pad = tol * (1 + np.abs(co))
-                if (co < lo[c] - pad).any() or (co > hi[c] + pad).any():
+                # the union of the child node's own child boxes must lie inside the box its parent stores for it
+                clo, chi = child_boxes(nodes[ref])
+                used = nodes[ref]["child"] != EMPTY
+                ulo, uhi = clo[used].min(0), chi[used].max(0)
+                pad = tol * (1 + np.abs(ulo) + np.abs(uhi))
+                if (ulo < lo[c] - pad).any() or (uhi > hi[c] + pad).any():
                     viol += 1
                 stack.append((ref, lo[c], hi[c], depth + 1))
     return leaves, maxdepth, viol
@@ -61,7 +62,7 @@ def validate(renderer):
         if bm["prim_count"] == 0:
             blas_boxes.append(None)
             continue
-        nodes = renderer.debug_read(1, bm["node_base"] * 64, bm["node_count"], NODE_DTYPE)
+        nodes = renderer.debug_read(1, bm["node_base"] * NODE_BYTES, bm["node_count"], NODE_DTYPE)
         tris = renderer.debug_read(2, bm["tri_base"] * 48, bm["prim_count"] * 12, np.float32).reshape(-1, 3, 4)
 
         def leaf_box(first, count, tris=tris):

@@ -106,6 +106,7 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     if (const char* e = getenv("GKCU_TRACE_VARIANT")) c.trace_variant = atoi(e);
     if (const char* e = getenv("GKCU_TMA")) c.use_tma = atoi(e);
     if (const char* e = getenv("GKCU_SHADE_MINB")) c.shade_minb = atoi(e);
+    if (const char* e = getenv("GKCU_TRACE_CARVEOUT")) c.trace_carveout = std::max(-1, std::min(100, atoi(e)));
     if (const char* e = getenv("GKCU_REFILL")) c.refill_below = std::max(1, std::min(32, atoi(e)));
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
     for (auto& e : c.ev) cudaEventCreate(&e);

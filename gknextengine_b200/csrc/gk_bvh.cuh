@@ -3,7 +3,7 @@
 // assets/shaders/common/Shading.slang:749-756, 794-801); B200 has no RT cores, so this is the hot loop.
 //
 // Layout (all 16-byte aligned, read with 128-bit loads):
-//   Node4       64 B   4-wide node, children boxes quantised to 8 bits on a per-node power-of-two grid
+//   Node4      128 B   4-wide node, fp32 child boxes in plane-major order (one cache line)
 //   leaf tris   48 B   3 x float4 (v0|prim id, v1, v2), stored in leaf order
 //   InstanceRec 64 B   world->object 3x4 + BLAS offsets; TLAS leaves reference one instance each
 // Semantics (shared with the CPU checker): a hit needs tmin < t < tmax, no face culling; the committed closest hit
@@ -14,14 +14,13 @@
 namespace gkd {
 
 struct __align__(16) Node4 {
-    float ox, oy, oz;       // quantisation origin (node box min)
-    uint8_t ex, ey, ez, n;  // biased exponents: cell size = 2^(e-127); n = child count
-    uint32_t child[4];      // CHILD_EMPTY | leaf (bit31, count-1 in 30:28, first in 27:0) | node index
-    uint32_t qlo[3];        // qlo[axis] byte c = child c
-    uint32_t qhi[3];
-    uint32_t pad[2];
+    float lo_x[4], hi_x[4];  // child boxes, one float4 per plane set; an empty slot has lo = +inf, hi = -inf
+    float lo_y[4], hi_y[4];
+    float lo_z[4], hi_z[4];
+    uint32_t child[4];       // CHILD_EMPTY | leaf (bit31, count-1 in 30:28, first in 27:0) | node index
+    uint32_t n, pad[3];      // child count
 };
-static_assert(sizeof(Node4) == 64, "Node4 must be 64 bytes");
+static_assert(sizeof(Node4) == 128, "Node4 must be 128 bytes (one cache line)");
 
 struct __align__(16) InstanceRec {
     float w2o[12];       // world->object, 3 rows x 4
@@ -34,7 +33,6 @@ static_assert(sizeof(InstanceRec) == 64, "InstanceRec must be 64 bytes");
 
 #define GK_CHILD_EMPTY 0xFFFFFFFFu
 #define GK_LEAF_BIT 0x80000000u
-#define GK_STACK_SENTINEL 0xFFFFFFFEu
 #define GK_TRAV_STACK 64
 #define GK_NO_HIT 0xFFFFFFFFu
 #ifndef GK_PUSH_ORDERED
@@ -111,47 +109,46 @@ GK_DEV float3 xform_vec(const float* m, float3 p) {
     return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z, m[4] * p.x + m[5] * p.y + m[6] * p.z, m[8] * p.x + m[9] * p.y + m[10] * p.z);
 }
 
-GK_DEV float byte_f(uint32_t w, int c) { return (float)((w >> (8 * c)) & 0xFFu); }
-
-// Tests the 4 quantised child boxes of a node. tn[c] = padded entry distance or +inf on a miss.
-// Planes are dequantised relative to the node origin: t = q * (scale * idir) + (origin - o) * idir, one FMA per plane; the
-// near/far plane words are picked per axis from the sign of the ray direction, so no per-plane min/max is needed. The
-// interval is padded by a few ulps on both ends (the quantised boxes are conservative, the slab arithmetic is not).
-GK_DEV void node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, float3 ro, float3 idir, float tmin, float tbest, float tn[4]) {
-    const float ox = __uint_as_float(n0.x), oy = __uint_as_float(n0.y), oz = __uint_as_float(n0.z);
-    const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
-                sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
-    const float adjx = (ox - ro.x) * idir.x, adjy = (oy - ro.y) * idir.y, adjz = (oz - ro.z) * idir.z;
-    const float scx = sx * idir.x, scy = sy * idir.y, scz = sz * idir.z;
-    const uint32_t child[4] = {n1.x, n1.y, n1.z, n1.w};
-    const bool px = idir.x >= 0.0f, py = idir.y >= 0.0f, pz = idir.z >= 0.0f;
-    const uint32_t nx = px ? n2.x : n2.w, fx = px ? n2.w : n2.x;  // qlo.x / qhi.x
-    const uint32_t ny = py ? n2.y : n3.x, fy = py ? n3.x : n2.y;
-    const uint32_t nz = pz ? n2.z : n3.y, fz = pz ? n3.y : n2.z;
-    const float tfcap = __fmaf_rn(tbest, 1.000001f, 1e-7f);
-    const float inf = __int_as_float(0x7f800000);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float x0 = __fmaf_rn(byte_f(nx, c), scx, adjx), x1 = __fmaf_rn(byte_f(fx, c), scx, adjx);
-        const float y0 = __fmaf_rn(byte_f(ny, c), scy, adjy), y1 = __fmaf_rn(byte_f(fy, c), scy, adjy);
-        const float z0 = __fmaf_rn(byte_f(nz, c), scz, adjz), z1 = __fmaf_rn(byte_f(fz, c), scz, adjz);
-        const float n = fmaxf(fmaxf(x0, y0), fmaxf(z0, tmin));
-        const float f = fminf(fminf(x1, y1), z1);
-        const float npad = __fmaf_rn(n, 0.999999f, -1e-7f);
-        const bool hit = (child[c] != GK_CHILD_EMPTY) && (npad <= __fmaf_rn(f, 1.000001f, 1e-7f)) && (npad <= tfcap);
-        tn[c] = hit ? npad : inf;
+// Where a traversal keeps its world-space ray while it is inside an instance: registers for the simple per-ray loop,
+// shared memory for k_trace (nine registers fewer per lane; the values are only touched when an instance is entered or left).
+struct WorldRegs {
+    float3 o_, d_, widir_;
+    GK_DEV void set(float3 o, float3 d, float3 widir) { o_ = o; d_ = d; widir_ = widir; }
+    GK_DEV float3 o() const { return o_; }
+    GK_DEV float3 d() const { return d_; }
+    GK_DEV float3 widir() const { return widir_; }
+};
+template <int STRIDE>
+struct WorldSmem {
+    float* p;  // p[k * STRIDE], k = 0..8, one column per thread
+    GK_DEV void set(float3 o, float3 d, float3 widir) {
+        p[0] = o.x; p[STRIDE] = o.y; p[2 * STRIDE] = o.z;
+        p[3 * STRIDE] = d.x; p[4 * STRIDE] = d.y; p[5 * STRIDE] = d.z;
+        p[6 * STRIDE] = widir.x; p[7 * STRIDE] = widir.y; p[8 * STRIDE] = widir.z;
     }
-}
+    GK_DEV float3 o() const { return f3(p[0], p[STRIDE], p[2 * STRIDE]); }
+    GK_DEV float3 d() const { return f3(p[3 * STRIDE], p[4 * STRIDE], p[5 * STRIDE]); }
+    GK_DEV float3 widir() const { return f3(p[6 * STRIDE], p[7 * STRIDE], p[8 * STRIDE]); }
+};
+
+// Traversal stack: a per-thread array in local memory, entries are (node reference, entry distance). Keeping the top levels
+// in shared memory instead was measured and is slower (k_trace is sensitive to L1 capacity and the carve-out costs more than
+// the faster pops gain, profiles/r01_experiments.md).
+struct LocalStack {
+    uint2 e[GK_TRAV_STACK];
+    GK_DEV void push(int& sp, uint2 v) { e[sp++] = v; }
+    GK_DEV uint2 pop(int& sp) { return e[--sp]; }
+};
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Traversal state machine. One ray per lane; the same three steps serve the simple per-ray loop (trace_ray) and the
-// persistent-thread kernel (k_trace), which interleaves them "while-while" style so that a warp runs node steps together
-// and leaf steps together, and refills finished lanes with new rays.
+// persistent-thread kernel (k_trace), which lets a warp run node steps together and leaf steps together and refills
+// finished lanes with new rays.
 struct Trav {
-    float3 o, d;       // world-space ray
-    float3 ro, rd;     // current-space ray (world or object)
-    float3 idir;
-    float3 widir;      // reciprocal world-space direction (restored when an instance is left)
+    float3 ro;         // current-space origin (world or object)
+    float3 idir;       // current-space reciprocal direction
+    float3 adjn, adjf; // slab offsets -ro * idir, lowered / raised by their own rounding error (see set_space)
+    uint32_t sgn;      // bit a: idir[a] < 0, i.e. the near plane of axis a is the child's upper plane
     float tmin, tmax;
     Hit best;
     RayShear sh;
@@ -160,14 +157,31 @@ struct Trav {
     uint32_t cur;      // current node reference
     uint32_t cur_inst; // GK_NO_HIT while in the TLAS
     int sp;
+    int sp_inst;       // stack height when the current instance was entered: popping down to it leaves the instance
     bool any;          // first-hit query
     bool done;
 };
 
-GK_DEV void trav_init(Trav& T, const TraceScene& S, float3 o, float3 d, float tmin, float tmax, bool any) {
-    T.o = o; T.d = d; T.ro = o; T.rd = d;
-    T.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-    T.widir = T.idir;
+// Slab distances are evaluated as t = plane * idir + adj with adj = -(ro * idir): one FMA per plane. adj carries a rounding
+// error of half an ulp (|adj| * 2^-24) which the cancellation in plane * idir + adj can make large relative to t, so the
+// near-plane offset is lowered and the far-plane offset raised by 4 ulps of |adj|; the remaining error (one rounding of the
+// FMA result) is relative to t and covered by the relative padding in node_test. The slabs therefore never reject a box
+// that the exact ray enters, which is what makes the closest hit independent of the tree.
+GK_DEV void set_space(Trav& T, float3 ro, float3 idir) {
+    T.ro = ro;
+    T.idir = idir;
+    const float ax = -(ro.x * idir.x), ay = -(ro.y * idir.y), az = -(ro.z * idir.z);
+    const float ex = fabsf(ax) * 2.4e-7f, ey = fabsf(ay) * 2.4e-7f, ez = fabsf(az) * 2.4e-7f;
+    T.adjn = f3(ax - ex, ay - ey, az - ez);
+    T.adjf = f3(ax + ex, ay + ey, az + ez);
+    T.sgn = (idir.x < 0.0f ? 1u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 4u : 0u);
+}
+
+template <class W>
+GK_DEV void trav_init(Trav& T, W& world, const TraceScene& S, float3 o, float3 d, float tmin, float tmax, bool any) {
+    const float3 idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+    world.set(o, d, idir);
+    set_space(T, o, idir);
     T.tmin = tmin; T.tmax = tmax;
     T.best.t = tmax; T.best.u = 0.0f; T.best.v = 0.0f; T.best.inst = GK_NO_HIT; T.best.prim = 0;
     T.sh.kx = T.sh.ky = T.sh.kz = 0;
@@ -177,37 +191,64 @@ GK_DEV void trav_init(Trav& T, const TraceScene& S, float3 o, float3 d, float tm
     T.cur = 0;
     T.cur_inst = GK_NO_HIT;
     T.sp = 0;
+    T.sp_inst = 0;
     T.any = any;
     T.done = S.tlas_nodes == 0;
 }
 
-// Pops the next node to visit (culling entries that are already farther than the best hit); leaves instances on sentinels.
-GK_DEV void trav_pop(Trav& T, const TraceScene& S, uint2* stack) {
+// Pops the next node to visit (culling entries that are already farther than the best hit); once every node the current
+// instance pushed has been consumed the ray goes back to world space and the TLAS.
+template <class W, class St>
+GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
     for (;;) {
-        if (T.sp == 0) { T.done = true; return; }
-        const uint2 e = stack[--T.sp];
-        if (e.x == GK_STACK_SENTINEL) {
-            T.ro = T.o;
-            T.rd = T.d;
-            T.idir = T.widir;
+        if (T.cur_inst != GK_NO_HIT && T.sp == T.sp_inst) {
+            set_space(T, world.o(), world.widir());
             T.nodes = reinterpret_cast<const uint4*>(S.tlas);
             T.cur_inst = GK_NO_HIT;
-            continue;
         }
+        if (T.sp == 0) { T.done = true; return; }
+        const uint2 e = stack.pop(T.sp);
         if (__uint_as_float(e.y) > T.best.t) continue;
         T.cur = e.x;
         return;
     }
 }
 
-// Internal node: test the 4 children, continue with the nearest, push the others (second nearest on top).
-GK_DEV void trav_node_step(Trav& T, const TraceScene& S, uint2* stack) {
-    const uint4* np = T.nodes + (size_t)T.cur * 4;
-    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-    float tn[4];
-    node_test(n0, n1, n2, n3, T.ro, T.idir, T.tmin, T.best.t, tn);
-    const uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
+// Internal node: test the 4 child boxes, continue with the nearest, push the others (second nearest on top).
+// Node4 keeps the planes as fp32 in structure-of-arrays order, so the near and far planes of an axis are two 16-byte loads
+// picked by the sign of the ray direction and every plane costs exactly one FMA: the kernel is bound by instruction issue,
+// not by bytes (profiles/r01_experiments.md), and the 8-bit quantised nodes it replaces spent 12 of their 31 instructions
+// per child on unpacking. The interval is padded by a few ulps on both ends (see set_space).
+template <class W, class St>
+GK_DEV void trav_node_step(Trav& T, const W& world, const TraceScene& S, St& stack) {
+    const uint4* np = T.nodes + (size_t)T.cur * 8;
+    const uint32_t ix = T.sgn & 1u, iy = (T.sgn >> 1) & 1u, iz = T.sgn >> 2;
+    const uint4 nx = __ldg(np + ix), fx = __ldg(np + (ix ^ 1u));
+    const uint4 ny = __ldg(np + 2 + iy), fy = __ldg(np + 2 + (iy ^ 1u));
+    const uint4 nz = __ldg(np + 4 + iz), fz = __ldg(np + 4 + (iz ^ 1u));
+    const uint4 n1 = __ldg(np + 6);
+    const float pnx[4] = {__uint_as_float(nx.x), __uint_as_float(nx.y), __uint_as_float(nx.z), __uint_as_float(nx.w)};
+    const float pfx[4] = {__uint_as_float(fx.x), __uint_as_float(fx.y), __uint_as_float(fx.z), __uint_as_float(fx.w)};
+    const float pny[4] = {__uint_as_float(ny.x), __uint_as_float(ny.y), __uint_as_float(ny.z), __uint_as_float(ny.w)};
+    const float pfy[4] = {__uint_as_float(fy.x), __uint_as_float(fy.y), __uint_as_float(fy.z), __uint_as_float(fy.w)};
+    const float pnz[4] = {__uint_as_float(nz.x), __uint_as_float(nz.y), __uint_as_float(nz.z), __uint_as_float(nz.w)};
+    const float pfz[4] = {__uint_as_float(fz.x), __uint_as_float(fz.y), __uint_as_float(fz.z), __uint_as_float(fz.w)};
+    const float tfcap = __fmaf_rn(T.best.t, 1.000001f, 1e-7f);
     const float inf = __int_as_float(0x7f800000);
+    float tn[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float x0 = __fmaf_rn(pnx[c], T.idir.x, T.adjn.x), x1 = __fmaf_rn(pfx[c], T.idir.x, T.adjf.x);
+        const float y0 = __fmaf_rn(pny[c], T.idir.y, T.adjn.y), y1 = __fmaf_rn(pfy[c], T.idir.y, T.adjf.y);
+        const float z0 = __fmaf_rn(pnz[c], T.idir.z, T.adjn.z), z1 = __fmaf_rn(pfz[c], T.idir.z, T.adjf.z);
+        const float n = fmaxf(fmaxf(x0, y0), fmaxf(z0, T.tmin));
+        const float f = fminf(fminf(x1, y1), z1);
+        const float npad = __fmaf_rn(n, 0.999999f, -1e-7f);
+        // an empty slot has lo = +inf, hi = -inf: n = +inf, f = -inf, never a hit
+        const bool hit = (npad <= __fmaf_rn(f, 1.000001f, 1e-7f)) && (npad <= tfcap);
+        tn[c] = hit ? npad : inf;
+    }
+    const uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
     // continue with the nearest child; the second nearest goes on top of the stack, the rest below it in slot order
     // (entries carry their entry distance, so a far one is culled when it is popped)
     int i0 = 0;
@@ -215,7 +256,7 @@ GK_DEV void trav_node_step(Trav& T, const TraceScene& S, uint2* stack) {
     if (tn[1] < t0) { t0 = tn[1]; i0 = 1; }
     if (tn[2] < t0) { t0 = tn[2]; i0 = 2; }
     if (tn[3] < t0) { t0 = tn[3]; i0 = 3; }
-    if (!(t0 < inf)) { trav_pop(T, S, stack); return; }
+    if (!(t0 < inf)) { trav_pop(T, world, S, stack); return; }
     if (GK_PUSH_ORDERED) {
         int i1 = -1;
         float t1 = inf;
@@ -225,19 +266,20 @@ GK_DEV void trav_node_step(Trav& T, const TraceScene& S, uint2* stack) {
         if (i1 >= 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                if (c != i0 && c != i1 && tn[c] < inf) stack[T.sp++] = make_uint2(ref[c], __float_as_uint(tn[c]));
-            stack[T.sp++] = make_uint2(ref[i1], __float_as_uint(t1));
+                if (c != i0 && c != i1 && tn[c] < inf) stack.push(T.sp, make_uint2(ref[c], __float_as_uint(tn[c])));
+            stack.push(T.sp, make_uint2(ref[i1], __float_as_uint(t1)));
         }
     } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            if (c != i0 && tn[c] < inf) stack[T.sp++] = make_uint2(ref[c], __float_as_uint(tn[c]));
+            if (c != i0 && tn[c] < inf) stack.push(T.sp, make_uint2(ref[c], __float_as_uint(tn[c])));
     }
     T.cur = ref[i0];
 }
 
 // Leaf: a TLAS leaf enters the instance's BLAS in object space (t is preserved by the affine map); a BLAS leaf tests triangles.
-GK_DEV void trav_leaf_step(Trav& T, const TraceScene& S, uint2* stack) {
+template <class W, class St>
+GK_DEV void trav_leaf_step(Trav& T, const W& world, const TraceScene& S, St& stack) {
     if (T.cur_inst == GK_NO_HIT) {
         const uint32_t ii = T.cur & 0x0FFFFFFFu;
         const float4* ir = reinterpret_cast<const float4*>(S.inst + ii);
@@ -245,11 +287,10 @@ GK_DEV void trav_leaf_step(Trav& T, const TraceScene& S, uint2* stack) {
         const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ir) + 3);
         if (meta.z) {
             const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-            T.ro = xform_point(m, T.o);
-            T.rd = xform_vec(m, T.d);
-            T.idir = f3(safe_rcp(T.rd.x), safe_rcp(T.rd.y), safe_rcp(T.rd.z));
-            T.sh = make_shear(T.rd);
-            stack[T.sp++] = make_uint2(GK_STACK_SENTINEL, 0u);
+            const float3 rd = xform_vec(m, world.d());
+            set_space(T, xform_point(m, world.o()), f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z)));
+            T.sh = make_shear(rd);
+            T.sp_inst = T.sp;
             T.nodes = reinterpret_cast<const uint4*>(S.blas + meta.x);
             T.tris = S.tris + (size_t)meta.y * 3;
             T.cur_inst = ii;
@@ -283,18 +324,19 @@ GK_DEV void trav_leaf_step(Trav& T, const TraceScene& S, uint2* stack) {
             }
         }
     }
-    trav_pop(T, S, stack);
+    trav_pop(T, world, S, stack);
 }
 
 // Closest hit (ANY = false) or first hit (ANY = true; best.inst != GK_NO_HIT means occluded): the simple per-ray loop.
 template <bool ANY>
 GK_DEV void trace_ray(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, Hit& best) {
-    uint2 stack[GK_TRAV_STACK];
+    LocalStack stack;
     Trav T;
-    trav_init(T, S, o, d, tmin, tmax, ANY);
+    WorldRegs world;
+    trav_init(T, world, S, o, d, tmin, tmax, ANY);
     while (!T.done) {
-        if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, S, stack);
-        else trav_leaf_step(T, S, stack);
+        if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, world, S, stack);
+        else trav_leaf_step(T, world, S, stack);
     }
     best = T.best;
 }

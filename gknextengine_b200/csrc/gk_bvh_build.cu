@@ -9,7 +9,7 @@
 // plus a BLAS refit the reference does not have.
 //
 // Pipeline: primitive boxes -> binary BVH (Morton LBVH, Karras 2012; or level-synchronous SAH-binned build for BLAS)
-//           -> collapse to 4-wide nodes with 8-bit quantised child boxes (Node4, gk_bvh.cuh) in BFS order
+//           -> collapse to 4-wide nodes with fp32 child boxes (Node4, gk_bvh.cuh) in BFS order
 //           -> leaf-ordered triangle pool. The BFS level table makes the bottom-up refit a handful of launches.
 #include <algorithm>
 #include <cfloat>
@@ -192,46 +192,18 @@ __global__ void k_lbvh_fit(int n, const int* __restrict__ parent, const int* __r
 // ------------------------------------------------------------------------------------------- wide-node writer
 struct ChildBox { float3 lo, hi; uint32_t ref; };
 
-__device__ void write_node4(Node4* out, float3 nlo, float3 nhi, int nchild, const ChildBox* ch) {
+__device__ void write_node4(Node4* out, int nchild, const ChildBox* ch) {
     Node4 node;
-    node.ox = nlo.x; node.oy = nlo.y; node.oz = nlo.z;
-    float ext[3] = {nhi.x - nlo.x, nhi.y - nlo.y, nhi.z - nlo.z};
-    float org[3] = {nlo.x, nlo.y, nlo.z};
-    uint8_t eb[3];
-    float scale[3];
-    for (int a = 0; a < 3; ++a) {
-        int ex = -126;
-        if (ext[a] > 0.0f) {
-            frexpf(ext[a] * (1.0002f / 255.0f), &ex);  // 2^ex >= ext/255 with slack
-            ex = max(-126, min(ex, 126));
-        }
-        eb[a] = (uint8_t)(ex + 127);
-        scale[a] = __uint_as_float((uint32_t)eb[a] << 23);
-    }
-    node.ex = eb[0]; node.ey = eb[1]; node.ez = eb[2];
-    node.n = (uint8_t)nchild;
-    node.qlo[0] = node.qlo[1] = node.qlo[2] = 0;
-    node.qhi[0] = node.qhi[1] = node.qhi[2] = 0;
-    node.pad[0] = node.pad[1] = 0;
+    const float inf = __int_as_float(0x7f800000);
     for (int c = 0; c < 4; ++c) {
-        if (c >= nchild) {
-            node.child[c] = GK_CHILD_EMPTY;
-            for (int a = 0; a < 3; ++a) { node.qlo[a] |= 255u << (8 * c); }
-            continue;
-        }
-        node.child[c] = ch[c].ref;
-        float clo[3] = {ch[c].lo.x, ch[c].lo.y, ch[c].lo.z}, chi[3] = {ch[c].hi.x, ch[c].hi.y, ch[c].hi.z};
-        for (int a = 0; a < 3; ++a) {
-            int ql = (int)floorf((clo[a] - org[a]) / scale[a]);
-            ql = max(0, min(255, ql));
-            while (ql > 0 && org[a] + (float)ql * scale[a] > clo[a]) --ql;
-            int qh = (int)ceilf((chi[a] - org[a]) / scale[a]);
-            qh = max(0, min(255, qh));
-            while (qh < 255 && org[a] + (float)qh * scale[a] < chi[a]) ++qh;
-            node.qlo[a] |= (uint32_t)ql << (8 * c);
-            node.qhi[a] |= (uint32_t)qh << (8 * c);
-        }
+        const bool v = c < nchild;
+        node.lo_x[c] = v ? ch[c].lo.x : inf; node.hi_x[c] = v ? ch[c].hi.x : -inf;
+        node.lo_y[c] = v ? ch[c].lo.y : inf; node.hi_y[c] = v ? ch[c].hi.y : -inf;
+        node.lo_z[c] = v ? ch[c].lo.z : inf; node.hi_z[c] = v ? ch[c].hi.z : -inf;
+        node.child[c] = v ? ch[c].ref : GK_CHILD_EMPTY;
     }
+    node.n = (uint32_t)nchild;
+    node.pad[0] = node.pad[1] = node.pad[2] = 0;
     *out = node;
 }
 
@@ -292,7 +264,7 @@ __global__ void k_collapse_level(const int2* __restrict__ qin, const int* __rest
         }
     }
     float4 l = nlo[e.x], h = nhi[e.x];
-    write_node4(out + e.y, f3(l.x, l.y, l.z), f3(h.x, h.y, h.z), nk, ch);
+    write_node4(out + e.y, nk, ch);
     out_lo[e.y] = l;
     out_hi[e.y] = h;
 }
@@ -345,12 +317,13 @@ __global__ void k_refit_level(Node4* __restrict__ nodes, float4* __restrict__ no
                               const float4* __restrict__ tris) {
     uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= end) return;
-    Node4 nd = nodes[i];
+    const uint4 refs = *(reinterpret_cast<const uint4*>(nodes + i) + 6);
+    const uint32_t child[4] = {refs.x, refs.y, refs.z, refs.w};
     ChildBox ch[4];
-    int nk = nd.n;
+    int nk = (int)nodes[i].n;
     float3 nlo = f3(FLT_MAX, FLT_MAX, FLT_MAX), nhi = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
     for (int k = 0; k < nk; ++k) {
-        uint32_t ref = nd.child[k];
+        uint32_t ref = child[k];
         float3 lo, hi;
         if (ref & GK_LEAF_BIT) {
             uint32_t first = ref & 0x0FFFFFFFu, cnt = ((ref >> 28) & 7u) + 1u;
@@ -370,7 +343,7 @@ __global__ void k_refit_level(Node4* __restrict__ nodes, float4* __restrict__ no
         nlo = f3(fminf(nlo.x, lo.x), fminf(nlo.y, lo.y), fminf(nlo.z, lo.z));
         nhi = f3(fmaxf(nhi.x, hi.x), fmaxf(nhi.y, hi.y), fmaxf(nhi.z, hi.z));
     }
-    write_node4(nodes + i, nlo, nhi, nk, ch);
+    write_node4(nodes + i, nk, ch);
     node_lo[i] = f4(nlo.x, nlo.y, nlo.z, 0);
     node_hi[i] = f4(nhi.x, nhi.y, nhi.z, 0);
 }
@@ -619,15 +592,21 @@ __global__ void k_instances(const GkNodeProxy* __restrict__ nodes, uint32_t n, c
     shade_inst[(size_t)i * 2 + 1] = make_uint4(nd.matId[3], nd.matId[4], nd.matId[5], nd.matId[6]);
     if (active) {
         float4 bl = reinterpret_cast<const float4*>(blas_table)[blas * 3 + 1], bh = reinterpret_cast<const float4*>(blas_table)[blas * 3 + 2];
-        float3 mn = f3(FLT_MAX, FLT_MAX, FLT_MAX), mx = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+        float3 mn = f3(FLT_MAX, FLT_MAX, FLT_MAX), mx = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX), mag = f3(0, 0, 0);
         for (int c = 0; c < 8; ++c) {
             float3 p = f3(c & 1 ? bh.x : bl.x, c & 2 ? bh.y : bl.y, c & 4 ? bh.z : bl.z);
             float3 w = f3(a[0][0] * p.x + a[0][1] * p.y + a[0][2] * p.z + t[0], a[1][0] * p.x + a[1][1] * p.y + a[1][2] * p.z + t[1],
                           a[2][0] * p.x + a[2][1] * p.y + a[2][2] * p.z + t[2]);
             mn = f3(fminf(mn.x, w.x), fminf(mn.y, w.y), fminf(mn.z, w.z));
             mx = f3(fmaxf(mx.x, w.x), fmaxf(mx.y, w.y), fmaxf(mx.z, w.z));
+            mag = f3(fmaxf(mag.x, fabsf(a[0][0] * p.x) + fabsf(a[0][1] * p.y) + fabsf(a[0][2] * p.z) + fabsf(t[0])),
+                     fmaxf(mag.y, fabsf(a[1][0] * p.x) + fabsf(a[1][1] * p.y) + fabsf(a[1][2] * p.z) + fabsf(t[1])),
+                     fmaxf(mag.z, fabsf(a[2][0] * p.x) + fabsf(a[2][1] * p.y) + fabsf(a[2][2] * p.z) + fabsf(t[2])));
         }
-        float3 pad = (mx - mn) * 1e-6f + f3(1e-6f, 1e-6f, 1e-6f);
+        // The ray is intersected in object space through the fp32 inverse; the world box has to contain the image of the
+        // BLAS box under that map's exact inverse, which differs from worldTS * corner by rounding in the order of
+        // 1e-7 x (the magnitude of the terms summed), so the pad scales with that magnitude and not just with the extent.
+        float3 pad = (mx - mn) * 1e-6f + mag * 1e-6f + f3(1e-6f, 1e-6f, 1e-6f);
         lo[i] = f4(mn.x - pad.x, mn.y - pad.y, mn.z - pad.z, 0);
         hi[i] = f4(mx.x + pad.x, mx.y + pad.y, mx.z + pad.z, 0);
     } else {

@@ -83,10 +83,11 @@ struct Context {
     bool frame_built_tlas = false;
     bool blas_built = false;
     BuildScratch scratch;
-    int trace_variant = 5;  // GKCU_TRACE_VARIANT: 5 vote-selected step kind at <= 64 registers, 8 blocks/SM (default); 3 same at 72 registers; 0 one step per iteration; 1 while-while; 2 warp-granular batches
+    int trace_variant = 5;  // GKCU_TRACE_VARIANT: 5 vote-selected step kind, 6 blocks/SM (default); 0 one step of any kind per iteration; 2 warp-granular batches, no refill
     int use_tma = 1;        // GKCU_TMA=0 falls back to plain-load staging of the stencil tiles (2 / 3: only reproject / only denoise)
     int shade_minb = 7;     // GKCU_SHADE_MINB: 8 compiles k_shade for 8 blocks/SM (<= 64 registers)
-    int refill_below = 24;  // k_trace: refill idle lanes when fewer than this many lanes are busy (GKCU_REFILL)
+    int trace_carveout = -1;  // k_trace shared-memory carve-out in percent (GKCU_TRACE_CARVEOUT), -1 = driver default
+    int refill_below = 16;  // k_trace: refill idle lanes when fewer than this many lanes are busy (GKCU_REFILL)
     int blas_builder = 1;  // 0 = LBVH, 1 = SAH-binned (GKCU_BLAS_BUILDER=lbvh|sah)
 
     // textures / probes

@@ -11,7 +11,11 @@
 // random stream - and with it every ray - identical to the megakernel order.
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
 
+#ifndef GK_TRACE_MINB
+#define GK_TRACE_MINB 6  // resident blocks per SM k_trace<5> is compiled for (6 -> 80 registers; 8 -> 64 is 6% slower since the fp32 nodes)
+#endif
 #include "gk_context.h"
 
 using namespace gkd;
@@ -687,18 +691,23 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S, RTView R, PathView
     if ((threadIdx.x & 31) == 0 && nprimary) atomicAdd(ray_counters + 0, (unsigned long long)nprimary);
 }
 
-// Persistent-thread traversal (Aila & Laine style "while-while"): every lane owns one ray; the warp alternates between a
-// phase where all lanes walk internal nodes and a phase where all lanes process their leaf, which keeps the two code paths
-// from serialising against each other, and lanes whose ray has terminated pull the next ray from the queue (one atomic per
-// warp) as soon as the number of busy lanes drops below `refill_below`.
+// Persistent-thread traversal: every lane owns one ray, and lanes whose ray has terminated pull the next ray from the queue
+// (one atomic per warp) as soon as the number of busy lanes drops below `refill_below`. VARIANT 5 (default): each iteration
+// the warp votes and executes only the step kind most lanes are waiting for (node walk, instance entry or triangle leaf);
+// lanes in another state sit the iteration out instead of serialising a second code path; compiled for GK_TRACE_MINB
+// blocks/SM with the world-space ray parked in shared memory. VARIANT 0: every lane advances one step of whatever kind
+// per iteration (the baseline the vote is measured against, profiles/r01_experiments.md).
 template <int VARIANT>
-__global__ void __launch_bounds__(128, VARIANT == 5 ? 8 : 1) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below) {
+__global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below) {
     const uint32_t n = V.counts[qi];
     const int lane = threadIdx.x & 31;
     const float4* ray_o = V.ray_o + (size_t)qi * half;
     const float4* ray_d = V.ray_d + (size_t)qi * half;
     const uint32_t* slot_pixel = V.slot_pixel[qi];
-    uint2 stack[GK_TRAV_STACK];
+    __shared__ float s_world[VARIANT == 5 ? 9 * 128 : 1];
+    typename std::conditional<VARIANT == 5, WorldSmem<128>, WorldRegs>::type world;
+    if constexpr (VARIANT == 5) world.p = s_world + threadIdx.x;
+    LocalStack stack;
     Trav T;
     T.done = true;
     uint32_t slot = 0;
@@ -715,8 +724,8 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? 8 : 1) k_trace(TraceScene 
                 if (!busy) {
                     slot = base + __popc(idle & ((1u << lane) - 1u));
                     if (slot < n) {
-                        const float4 o = ray_o[slot], d = ray_d[slot];
-                        trav_init(T, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, (slot_pixel[slot] & 0x80000000u) != 0);
+                        const float4 o = __ldcs(ray_o + slot), d = __ldcs(ray_d + slot);  // streamed: keep L1 for nodes and stacks
+                        trav_init(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, (__ldcs(slot_pixel + slot) & 0x80000000u) != 0);
                         busy = true;
                     }
                 }
@@ -725,21 +734,18 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? 8 : 1) k_trace(TraceScene 
         }
         if (!__any_sync(0xffffffffu, busy)) return;
         if (VARIANT == 0) {
-            // every lane advances one step (node or leaf) per iteration
             do {
                 if (busy && !T.done) {
-                    if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, ts, stack);
-                    else trav_leaf_step(T, ts, stack);
+                    if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, world, ts, stack);
+                    else trav_leaf_step(T, world, ts, stack);
                 }
                 if (busy && T.done) {
-                    V.hit_tuv[slot] = f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst));
-                    V.hit_prim[slot] = T.best.prim;
+                    __stcs(V.hit_tuv + slot, f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst)));
+                    __stcs(V.hit_prim + slot, T.best.prim);
                     busy = false;
                 }
             } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
-        } else if (VARIANT == 3 || VARIANT == 5) {
-            // vote: each iteration the warp executes only the step kind most lanes are waiting for (node walk, instance entry
-            // or triangle leaf); lanes in another state sit the iteration out instead of serialising a second code path.
+        } else {
             for (;;) {
                 const bool live = busy && !T.done;
                 const bool leaf = (T.cur & GK_LEAF_BIT) != 0;
@@ -750,52 +756,18 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? 8 : 1) k_trace(TraceScene 
                 const int nN = __popc(bN), nI = __popc(bI), nT = __popc(bT);
                 if (nN + nI + nT < (drained ? 1 : refill_below)) break;  // too few lanes left: refill (or finish)
                 if (nN >= nT && nN >= nI) {
-                    if (wN) trav_node_step(T, ts, stack);
+                    if (wN) trav_node_step(T, world, ts, stack);
                 } else if (nT >= nI) {
-                    if (wT) trav_leaf_step(T, ts, stack);
+                    if (wT) trav_leaf_step(T, world, ts, stack);
                 } else {
-                    if (wI) trav_leaf_step(T, ts, stack);
+                    if (wI) trav_leaf_step(T, world, ts, stack);
                 }
                 if (busy && T.done) {
-                    V.hit_tuv[slot] = f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst));
-                    V.hit_prim[slot] = T.best.prim;
+                    __stcs(V.hit_tuv + slot, f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst)));
+                    __stcs(V.hit_prim + slot, T.best.prim);
                     busy = false;
                 }
             }
-        } else if (VARIANT == 4) {
-            // two classes: {node walk, instance entry} vs {triangle leaf}
-            do {
-                const bool live = busy && !T.done;
-                const bool leaf = (T.cur & GK_LEAF_BIT) != 0;
-                const bool wT = live && leaf && T.cur_inst != GK_NO_HIT;
-                const bool wN = live && !wT;
-                const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nT = __popc(__ballot_sync(0xffffffffu, wT));
-                if (nN >= nT) {
-                    if (wN) {
-                        if (!leaf) trav_node_step(T, ts, stack);
-                        else trav_leaf_step(T, ts, stack);
-                    }
-                } else {
-                    if (wT) trav_leaf_step(T, ts, stack);
-                }
-                if (busy && T.done) {
-                    V.hit_tuv[slot] = f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst));
-                    V.hit_prim[slot] = T.best.prim;
-                    busy = false;
-                }
-            } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
-        } else {
-            do {
-                // phase 1: internal nodes until every busy lane holds a leaf (or has finished)
-                while (busy && !T.done && !(T.cur & GK_LEAF_BIT)) trav_node_step(T, ts, stack);
-                // phase 2: one leaf per lane
-                if (busy && !T.done) trav_leaf_step(T, ts, stack);
-                if (busy && T.done) {
-                    V.hit_tuv[slot] = f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst));
-                    V.hit_prim[slot] = T.best.prim;
-                    busy = false;
-                }
-            } while (__popc(__ballot_sync(0xffffffffu, busy)) >= (drained ? 1 : refill_below));
         }
     }
 }
@@ -990,6 +962,21 @@ void path_release(Context& c) {
 }
 
 int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {
+    // k_trace<5> is sensitive to L1 capacity (nodes, triangles and the spilled part of the stacks live there): ask for exactly the
+    // shared memory its 8 resident blocks need and leave the rest of the 256 KB array to L1.
+    static int carveout_set = -2;
+    if (carveout_set != c.trace_carveout) {
+        int pct = c.trace_carveout;
+        if (pct < 0) {
+            cudaFuncAttributes fa;
+            int smem_sm = 0;
+            if (cudaFuncGetAttributes(&fa, k_trace<5>) == cudaSuccess &&
+                cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c.device) == cudaSuccess && smem_sm > 0)
+                pct = std::min(100, (int)((GK_TRACE_MINB * (fa.sharedSizeBytes + 1024) * 100 + smem_sm - 1) / smem_sm));
+        }
+        if (pct >= 0) cudaFuncSetAttribute(k_trace<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        carveout_set = c.trace_carveout;
+    }
     cudaStream_t st = c.stream;
     PathBuffers& b = *c.path;
     SceneView S = make_scene_view(c);
@@ -1032,11 +1019,8 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 const uint32_t blocks = std::min<uint32_t>((bound + 127) / 128, persistent_blocks);
                 cudaEventRecord(c.wev[3 * w], st);
                 if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
-                else if (c.trace_variant == 1) k_trace<1><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 else if (c.trace_variant == 0) k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-                else if (c.trace_variant == 4) k_trace<4><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-                else if (c.trace_variant == 5) k_trace<5><<<std::min<uint32_t>((bound + 127) / 128, (uint32_t)c.sm_count * 16u), 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-                else k_trace<3><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
+                else k_trace<5><<<std::min<uint32_t>((bound + 127) / 128, (uint32_t)c.sm_count * 16u), 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 cudaEventRecord(c.wev[3 * w + 1], st);
                 if (c.shade_minb == 8) k_shade<8><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
                 else if (c.shade_minb == 7) k_shade<7><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);

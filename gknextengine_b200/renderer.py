@@ -20,7 +20,7 @@ from ._abi import (HIT_DTYPE, RAY_DTYPE, RT, RT_FORMAT, GkcuCounters, GkcuKernel
                    GkNodeProxy, GkUniformBufferObject)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libgknext_cuda.so")
+_LIB_PATH = os.environ.get("GKCU_LIB") or os.path.join(_HERE, "libgknext_cuda.so")  # GKCU_LIB: A/B runs of two builds
 _lib = None
 
 

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Run on the GPU box (one GPU): bench line, ncu launch list and --set full captures of the hot kernels.
+#   gpurun --timeout 1200 -- 'bash scripts/capture_profiles.sh r01'
+# Outputs land in gpurun_out/; scripts/refresh_profiles.py turns them into profiles/<tag>_*.
+TAG=${1:-r01}
+O=gpurun_out
+mkdir -p $O
+python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench.err
+tail -c 2500 $O/${TAG}_bench_n1.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches.csv \
+    python scripts/profile_frame.py 2 > $O/${TAG}_launches.log 2>&1
+for k in k_trace k_shade; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 10 -c 2 -o $O/${TAG}_prof_$k -f \
+      python scripts/profile_frame.py 1 > $O/${TAG}_prof_$k.log 2>&1
+done
+ncu --set full --clock-control none --import-source on -k 'regex:k_reproject|k_denoise|k_primary|k_tail' -c 6 -o $O/${TAG}_prof_misc -f \
+    python scripts/profile_frame.py 1 > $O/${TAG}_prof_misc.log 2>&1
+ls -la $O | tail -12
