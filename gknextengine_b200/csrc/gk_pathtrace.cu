@@ -56,7 +56,7 @@ struct RTView {
 // is touched only at sample boundaries.
 struct PathView {
     uint4* rng;                                          // hot, [2][pixels]
-    float4 *pos_mat, *nrm_flags, *dir_cnt, *ray_color;   // hot, [2][pixels]
+    float4 *pos_mat, *nrm, *dir, *ray_color;   // queue slots, [2][pixels]; pos_mat / nrm / dir only for any-hit slots
     float4 *final_color, *final_refl;                    // cold, per pixel: running sums of the finished samples
     float4 *prim_pos_mat, *prim_nrm_cnt, *prim_albedo;   // cold, per pixel: primary hit (position|material, normal|sample range, albedo)
     size_t pixels;
@@ -493,29 +493,48 @@ GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, c
 }
 
 // ------------------------------------------------------------------------------------------------ state I/O
-GK_DEV void store_hot(const PathView& V, int qi, uint32_t slot, const PathRegs& P) {
+// Queue slot layout. A closest-hit request needs little of the path state back: the pending ray (its direction IS the path
+// direction, and position / normal / material are overwritten by the hit or unused on a miss), the RNG, the throughput and
+// two packed words, which ride in the .w lanes of the ray record (tmin / tmax of queue rays are constants):
+//   slot_pixel 4 B | ray_o = (origin, flags) 16 B | ray_d = (direction, sample | bounce << 16) 16 B | rng 16 B | ray_color 16 B
+// = 68 B per slot. A shadow ray (any-hit request) resumes the path at its current vertex, so only those slots also carry
+// pos_mat / nrm / dir (48 B). This is what k_shade streams from and to HBM every wave.
+GK_DEV void store_slot(const PathView& V, int qi, uint32_t slot, uint32_t pixel, int req, const PathRegs& P) {
     const size_t i = (size_t)qi * V.pixels + slot;
+    V.slot_pixel[qi][slot] = pixel | (req == REQ_ANY ? 0x80000000u : 0u);
+    V.ray_o[i] = f4(P.ro.x, P.ro.y, P.ro.z, __uint_as_float(P.flags));
+    V.ray_d[i] = f4(P.rd.x, P.rd.y, P.rd.z, __uint_as_float(P.sample | (P.bounce << 16)));
     V.rng[i] = P.rng;
-    V.pos_mat[i] = f4(P.pos.x, P.pos.y, P.pos.z, __uint_as_float(P.mat));
-    V.nrm_flags[i] = f4(P.nrm.x, P.nrm.y, P.nrm.z, __uint_as_float(P.flags));
-    V.dir_cnt[i] = f4(P.dir.x, P.dir.y, P.dir.z, __uint_as_float(P.sample | (P.bounce << 16)));
     V.ray_color[i] = P.rayColor;
+    if (req == REQ_ANY) {
+        V.pos_mat[i] = f4(P.pos.x, P.pos.y, P.pos.z, __uint_as_float(P.mat));
+        V.nrm[i] = f4(P.nrm.x, P.nrm.y, P.nrm.z, 0.0f);
+        V.dir[i] = f4(P.dir.x, P.dir.y, P.dir.z, 0.0f);
+    }
 }
-GK_DEV void load_hot(const PathView& V, const SceneView& S, int qi, uint32_t slot, PathRegs& P) {
+GK_DEV void load_slot(const PathView& V, const SceneView& S, int qi, uint32_t slot, bool any, PathRegs& P) {
     const size_t i = (size_t)qi * V.pixels + slot;
-    P.rng = V.rng[i];
-    float4 a = V.pos_mat[i], b = V.nrm_flags[i], c = V.dir_cnt[i];
-    P.pos = f3(a.x, a.y, a.z); P.mat = __float_as_uint(a.w);
-    P.nrm = f3(b.x, b.y, b.z); P.flags = __float_as_uint(b.w);
-    P.dir = f3(c.x, c.y, c.z);
-    uint32_t cnt = __float_as_uint(c.w);
+    const float4 o = V.ray_o[i], d = V.ray_d[i];
+    P.ro = f3(o.x, o.y, o.z); P.flags = __float_as_uint(o.w);
+    P.rd = f3(d.x, d.y, d.z);
+    const uint32_t cnt = __float_as_uint(d.w);
     P.sample = cnt & 0xFFFF; P.bounce = cnt >> 16;
+    P.rng = V.rng[i];
     P.rayColor = V.ray_color[i];
+    if (any) {
+        const float4 a = V.pos_mat[i], b = V.nrm[i], c = V.dir[i];
+        P.pos = f3(a.x, a.y, a.z); P.mat = __float_as_uint(a.w);
+        P.nrm = f3(b.x, b.y, b.z);
+        P.dir = f3(c.x, c.y, c.z);
+    } else {
+        P.pos = f3(0, 0, 0); P.mat = 0u;
+        P.nrm = f3(0, 0, 0);
+        P.dir = P.rd;
+    }
     P.maxBounces = (P.flags & FL_PRIM_DIELECTRIC) ? S.cam->MaxNumberOfBounces : S.cam->NumberOfBounces;
 }
 
-// Appends one entry to queue `qi` (one atomic per warp: ballot + popc + shuffle) and writes the hot state, the ray and the
-// pixel tag at the new slot.
+// Appends one entry to queue `qi` (one atomic per warp: ballot + popc + shuffle) and writes the slot.
 GK_DEV void enqueue(const PathView& V, int qi, bool want, uint32_t pixel, int req, const PathRegs& P) {
     const unsigned mask = __ballot_sync(0xffffffffu, want);
     if (!mask) return;
@@ -524,14 +543,7 @@ GK_DEV void enqueue(const PathView& V, int qi, bool want, uint32_t pixel, int re
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(V.counts + qi, (uint32_t)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (want) {
-        const uint32_t slot = base + __popc(mask & ((1u << lane) - 1u));
-        const size_t i = (size_t)qi * V.pixels + slot;
-        V.slot_pixel[qi][slot] = pixel | (req == REQ_ANY ? 0x80000000u : 0u);
-        V.ray_o[i] = f4(P.ro.x, P.ro.y, P.ro.z, GK_EPS);
-        V.ray_d[i] = f4(P.rd.x, P.rd.y, P.rd.z, GK_PT_MAX_TRACE_DISTANCE);
-        store_hot(V, qi, slot, P);
-    }
+    if (want) store_slot(V, qi, base + __popc(mask & ((1u << lane) - 1u)), pixel, req, P);
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -725,7 +737,7 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
                     slot = base + __popc(idle & ((1u << lane) - 1u));
                     if (slot < n) {
                         const float4 o = __ldcs(ray_o + slot), d = __ldcs(ray_d + slot);  // streamed: keep L1 for nodes and stacks
-                        trav_init(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, (__ldcs(slot_pixel + slot) & 0x80000000u) != 0);
+                        trav_init(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, (__ldcs(slot_pixel + slot) & 0x80000000u) != 0);
                         busy = true;
                     }
                 }
@@ -787,8 +799,8 @@ __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V,
         if (slot < n) {
             float4 o = ray_o[slot], d = ray_d[slot];
             Hit h;
-            if (V.slot_pixel[qi][slot] & 0x80000000u) trace_ray<true>(ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h);
-            else trace_ray<false>(ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h);
+            if (V.slot_pixel[qi][slot] & 0x80000000u) trace_ray<true>(ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h);
+            else trace_ray<false>(ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h);
             V.hit_tuv[slot] = f4(h.t, h.u, h.v, __uint_as_float(h.inst));
             V.hit_prim[slot] = h.prim;
         }
@@ -810,14 +822,11 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S, RTView R, Path
         const size_t i = (size_t)qi * V.pixels + slot;
         const uint32_t sp = V.slot_pixel[qi][slot];
         const float4 hv = V.hit_tuv[slot];
-        const float4 o = V.ray_o[i], d = V.ray_d[i];
         Hit h;
         h.t = hv.x; h.u = hv.y; h.v = hv.z; h.inst = __float_as_uint(hv.w); h.prim = V.hit_prim[slot];
-        load_hot(V, S, qi, slot, P);
+        load_slot(V, S, qi, slot, (sp & 0x80000000u) != 0, P);
         pixel = sp & 0x7FFFFFFFu;
         if (sp & 0x80000000u) nany++; else nclosest++;
-        P.ro = f3(o.x, o.y, o.z);
-        P.rd = f3(d.x, d.y, d.z);
         req = advance(S, O, cfg, V, pixel, P, h);
         want = req != REQ_DONE;
     }
@@ -842,10 +851,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneView S, RTView R, PathView V,
         uint32_t sp = V.slot_pixel[qi][slot];
         uint32_t pixel = sp & 0x7FFFFFFFu;
         PathRegs P;
-        load_hot(V, S, qi, slot, P);
-        float4 o = V.ray_o[(size_t)qi * half + slot], d = V.ray_d[(size_t)qi * half + slot];
-        P.ro = f3(o.x, o.y, o.z);
-        P.rd = f3(d.x, d.y, d.z);
+        load_slot(V, S, qi, slot, (sp & 0x80000000u) != 0, P);
         int req = (sp & 0x80000000u) ? REQ_ANY : REQ_CLOSEST;
         while (req != REQ_DONE) {
             Hit h;
@@ -922,7 +928,7 @@ PathView make_path_view(const Context& c) {
     PathView V;
     V.rng = b.rng.as<uint4>();
     V.pixels = b.pixels;
-    V.pos_mat = b.pos_mat.as<float4>(); V.nrm_flags = b.nrm_flags.as<float4>(); V.dir_cnt = b.dir_cnt.as<float4>();
+    V.pos_mat = b.pos_mat.as<float4>(); V.nrm = b.nrm_flags.as<float4>(); V.dir = b.dir_cnt.as<float4>();
     V.ray_color = b.ray_color.as<float4>(); V.final_color = b.final_color.as<float4>(); V.final_refl = b.final_refl.as<float4>();
     V.prim_pos_mat = b.prim_pos_mat.as<float4>(); V.prim_nrm_cnt = b.prim_nrm_cnt.as<float4>(); V.prim_albedo = b.prim_albedo.as<float4>();
     V.ray_o = b.ray_o.as<float4>(); V.ray_d = b.ray_d.as<float4>();
