@@ -550,7 +550,9 @@ GK_DEV void enqueue(const PathView& V, int qi, bool want, uint32_t pixel, int re
 // Primary visibility + G-buffer (FPathTracingRendererV2::Init/PrimaryHit, Shading.slang:1187-1241, with the visibility
 // buffer lookup of FVisibilityBufferRayCasterV2::TracePrimaryRay, :338-494, replaced by a closest-hit cast of the same
 // pixel-corner ray), the buffer clear (Util.BufferClear.comp.slang:5-14), and the first ray of sample 0.
-__global__ void __launch_bounds__(128) k_primary(SceneView S, RTView R, PathView V, FrameCfg cfg, unsigned long long* ray_counters) {
+__global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, unsigned long long* ray_counters) {
+    SceneView S = S_;
+    S.cam = &cam;  // the camera block is read through the constant bank (uniform loads), not through L1
     const int x = blockIdx.x * 8 + (threadIdx.x & 7), y = blockIdx.y * 16 + (threadIdx.x >> 3);
     const bool inside = x < (int)R.w && y < (int)R.h;
     const uint32_t pixel = inside ? (uint32_t)y * R.w + (uint32_t)x : 0u;
@@ -809,7 +811,9 @@ __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V,
 
 // Shade: one thread per queue slot: consume the hit, advance the path to its next ray, compact the survivors into the other queue.
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_shade(SceneView S, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
+__global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
+    SceneView S = S_;
+    S.cam = &cam;
     const uint32_t n = V.counts[qi];
     PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
     uint32_t nclosest = 0, nany = 0;
@@ -842,7 +846,9 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S, RTView R, Path
 }
 
 // Tail / megakernel: every thread runs its pixel's program to completion with the traversal inlined.
-__global__ void __launch_bounds__(128) k_tail(SceneView S, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
+__global__ void __launch_bounds__(128) k_tail(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
+    SceneView S = S_;
+    S.cam = &cam;
     const uint32_t n = V.counts[qi];
     PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
     const size_t half = (size_t)R.w * R.h;
@@ -1000,7 +1006,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     GkcuKernelStats ks{};
     dim3 grid((R.w + 7) / 8, (R.h + 15) / 16);
     cudaEventRecord(c.kev[0], st);
-    k_primary<<<grid, 128, 0, st>>>(S, R, V, cfg, ray_counters);
+    k_primary<<<grid, 128, 0, st>>>(S, ubo, R, V, cfg, ray_counters);
     cudaEventRecord(c.kev[1], st);
     c.launches++;
     const uint32_t pixels = R.w * R.h;
@@ -1028,11 +1034,11 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 else if (c.trace_variant == 0) k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 else k_trace<5><<<std::min<uint32_t>((bound + 127) / 128, (uint32_t)c.sm_count * 16u), 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
                 cudaEventRecord(c.wev[3 * w + 1], st);
-                if (c.shade_minb == 8) k_shade<8><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
-                else if (c.shade_minb == 7) k_shade<7><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
-                else if (c.shade_minb == 6) k_shade<6><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
-                else if (c.shade_minb == 10) k_shade<10><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
-                else k_shade<1><<<(bound + 127) / 128, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+                if (c.shade_minb == 8) k_shade<8><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
+                else if (c.shade_minb == 7) k_shade<7><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
+                else if (c.shade_minb == 6) k_shade<6><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
+                else if (c.shade_minb == 10) k_shade<10><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
+                else k_shade<1><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
                 cudaEventRecord(c.wev[3 * w + 2], st);
                 // exact size of this wave, for the statistics (read after the chunk's synchronisation)
                 GK_CUDA(cudaMemcpyAsync(b.host_counts + 16 + w, counts + qi, 4, cudaMemcpyDeviceToHost, st));
@@ -1060,7 +1066,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     {
         const uint32_t blocks = std::min<uint32_t>((pixels + 127) / 128, (uint32_t)c.sm_count * 16u);
         cudaEventRecord(c.kev[5], st);
-        k_tail<<<blocks, 128, 0, st>>>(S, R, V, cfg, qi, ray_counters);
+        k_tail<<<blocks, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
         cudaEventRecord(c.kev[6], st);
         c.launches++;
     }
