@@ -102,3 +102,16 @@ RT_FORMAT = {
     14: (np.uint16, 1), 20: (np.float16, 4), 21: (np.float16, 4), 22: (np.float16, 4), 64: (np.uint32, 1),
 }
 OBJECTID_MISS = 65535
+
+
+class GkLightObject(C.Structure):  # BasicTypes.slang:171-183
+    _fields_ = [("p0", GkVec4), ("p1", GkVec4), ("p3", GkVec4), ("normal_area", GkVec4), ("lightMatIdx", C.c_uint32), ("reserved1", C.c_uint32),
+                ("reserved2", C.c_uint32), ("reserved3", C.c_uint32)]
+
+
+class GkSphericalHarmonics(C.Structure):  # BasicTypes.slang:164-169
+    _fields_ = [("coefficients", (C.c_float * 9) * 3), ("padding", C.c_float)]
+
+
+GK_CUBE_SIZE_XY, GK_CUBE_SIZE_Z, GK_PAGE_COUNT = 192, 48, 64
+GK_CUBE_COUNT = GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z

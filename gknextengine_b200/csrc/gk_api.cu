@@ -129,7 +129,7 @@ int gkcu_destroy(GkcuContext* ctx) {
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
                       &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
-                      &c.inst_hi, &c.tlas_active_ids, &c.tex_table, &c.cubes, &c.voxels, &c.ubo, &c.trace_rays, &c.trace_hits};
+                      &c.inst_hi, &c.tlas_active_ids, &c.tex_table, &c.cubes, &c.voxels, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits};
     for (DevBuf* b : bufs) b->release();
     BuildScratch& s = c.scratch;
     DevBuf* sb[] = {&s.prim_lo, &s.prim_hi, &s.keys, &s.keys_sorted, &s.order, &s.order_tmp, &s.sort_tmp, &s.n2_lo, &s.n2_hi, &s.n2_left, &s.n2_right,
@@ -296,6 +296,64 @@ int gkcu_set_probes(GkcuContext* ctx, const GkAmbientCube* cubes, const GkVoxelD
     GK_CUDA(cudaMemcpyAsync(c.voxels.p, voxels, n * sizeof(GkVoxelData), cudaMemcpyHostToDevice, c.stream));
     GK_CUDA(cudaStreamSynchronize(c.stream));
     c.has_probes = true;
+    return 0;
+}
+
+int gkcu_set_lights(GkcuContext* ctx, const GkLightObject* lights, uint32_t count) {
+    CTX_OR_FAIL(ctx);
+    if (count && !lights) { set_error("gkcu_set_lights: null lights"); return 1; }
+    if (count) {
+        if (!c.lights.reserve((size_t)count * sizeof(GkLightObject))) return 1;
+        GK_CUDA(cudaMemcpyAsync(c.lights.p, lights, (size_t)count * sizeof(GkLightObject), cudaMemcpyHostToDevice, c.stream));
+        GK_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    c.light_count = count;
+    return 0;
+}
+
+int gkcu_set_sky_sh(GkcuContext* ctx, uint32_t id, const GkSphericalHarmonics* sh) {
+    CTX_OR_FAIL(ctx);
+    if (!sh || id >= 100) { set_error("gkcu_set_sky_sh: null coefficients or id >= 100 (Scene.cpp:38)"); return 1; }
+    if (!c.sky_sh.p) {
+        if (!c.sky_sh.reserve(100 * sizeof(GkSphericalHarmonics))) return 1;
+        GK_CUDA(cudaMemsetAsync(c.sky_sh.p, 0, 100 * sizeof(GkSphericalHarmonics), c.stream));
+    }
+    GK_CUDA(cudaMemcpyAsync(c.sky_sh.as<GkSphericalHarmonics>() + id, sh, sizeof(GkSphericalHarmonics), cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    c.sky_sh_count = std::max(c.sky_sh_count, id + 1);
+    return 0;
+}
+
+static int ensure_tlas(Context& c) {
+    if (!c.blas_built) { set_error("call gkcu_scene_upload + gkcu_blas_build first"); return 1; }
+    if (c.tlas_dirty) return build_tlas(c);
+    return 0;
+}
+
+int gkcu_probes_voxelize(GkcuContext* ctx) {
+    CTX_OR_FAIL(ctx);
+    if (ensure_tlas(c)) return 1;
+    return probes_voxelize(c);
+}
+
+int gkcu_probes_bake(GkcuContext* ctx, const GkUniformBufferObject* ubo, uint32_t first_cube, uint32_t cube_count) {
+    CTX_OR_FAIL(ctx);
+    if (!ubo) { set_error("gkcu_probes_bake: null ubo"); return 1; }
+    if (ensure_tlas(c)) return 1;
+    return probes_bake(c, *ubo, first_cube, cube_count);
+}
+
+int gkcu_probes_read(GkcuContext* ctx, GkAmbientCube* cubes, GkVoxelData* voxels, GkPageIndex* pages) {
+    CTX_OR_FAIL(ctx);
+    if (!c.has_probes) { set_error("gkcu_probes_read: no probe state"); return 1; }
+    const size_t n = (size_t)GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z;
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    if (cubes) GK_CUDA(cudaMemcpy(cubes, c.cubes.p, n * sizeof(GkAmbientCube), cudaMemcpyDeviceToHost));
+    if (voxels) GK_CUDA(cudaMemcpy(voxels, c.voxels.p, n * sizeof(GkVoxelData), cudaMemcpyDeviceToHost));
+    if (pages) {
+        if (!c.pages.p) { set_error("gkcu_probes_read: no page index (probes were set with gkcu_set_probes)"); return 1; }
+        GK_CUDA(cudaMemcpy(pages, c.pages.p, (size_t)GK_PAGE_COUNT * GK_PAGE_COUNT * sizeof(GkPageIndex), cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 

@@ -97,6 +97,8 @@ struct Context {
     uint32_t tex_count = 0;
     DevBuf cubes, voxels;
     bool has_probes = false;
+    DevBuf pages, cube_snapshot, lights, sky_sh;  // probe bake: page index, snapshot of the range being baked, GPUScene.Lights / HDRSHs
+    uint32_t light_count = 0, sky_sh_count = 0;
 
     DevBuf ubo;
     RenderTargets rt;
@@ -128,6 +130,10 @@ int run_resolve(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
 int run_trace_rays(Context& c, uint32_t count, bool any_hit);
 void fetch_ray_counters(Context& c);
 int radiance_buffer(Context& c, void** ptr, size_t* bytes);
+
+// gk_probes.cu
+int probes_voxelize(Context& c);
+int probes_bake(Context& c, const GkUniformBufferObject& ubo, uint32_t first, uint32_t count);
 
 // gk_post.cu
 int run_reproject(Context& c, const GkcuFrameParams& p);

@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from ._abi import GkcuSceneDesc, GkMaterial, GkNodeProxy, GkUniformBufferObject
+from ._abi import GkcuSceneDesc, GkLightObject, GkMaterial, GkNodeProxy, GkSphericalHarmonics, GkUniformBufferObject
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
@@ -29,6 +29,9 @@ def lib():
         L.gkhost_scene_nodes.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
         L.gkhost_scene_materials.restype = C.POINTER(GkMaterial)
         L.gkhost_scene_materials.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.gkhost_scene_lights.restype = C.POINTER(GkLightObject)
+        L.gkhost_scene_lights.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.gkhost_project_sh.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(GkSphericalHarmonics)]
         L.gkhost_scene_update_nodes.argtypes = [C.c_void_p]
         L.gkhost_scene_settings.argtypes = [C.c_void_p] + [C.c_int] * 8
         L.gkhost_scene_env.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
@@ -88,6 +91,11 @@ class Scene:
         p = lib().gkhost_scene_materials(self._h, C.byref(n))
         return p, n.value
 
+    def lights(self):
+        n = C.c_uint32()
+        p = lib().gkhost_scene_lights(self._h, C.byref(n))
+        return p, n.value
+
     def update_nodes(self):
         """Scene::UpdateNodes: recompute NodeProxy[] (velocity tick included)."""
         return bool(lib().gkhost_scene_update_nodes(self._h))
@@ -119,4 +127,12 @@ def make_sky(width=1024, height=512):
     """Procedural stand-in for assets/textures/river_road_2.hdr (sky id 0, Engine.cpp:855): RGBA32F equirect."""
     out = np.zeros((height, width, 4), dtype=np.float32)
     lib().gkhost_make_sky(width, height, out.ctypes.data)
+    return out
+
+
+def project_sh(rgba):
+    """GlobalTexturePool's ProjectHdrToSh (src/Assets/Texture.cpp:180-262) of an equirect RGBA32F image -> GkSphericalHarmonics."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+    out = GkSphericalHarmonics()
+    lib().gkhost_project_sh(rgba.ctypes.data, rgba.shape[1], rgba.shape[0], C.byref(out))
     return out

@@ -35,6 +35,14 @@ const GkMaterial* gkhost_scene_materials(void* h, uint32_t* count) {
     *count = (uint32_t)s->materials.size();
     return s->materials.data();
 }
+const GkLightObject* gkhost_scene_lights(void* h, uint32_t* count) {
+    auto* s = static_cast<gk::Scene*>(h);
+    *count = (uint32_t)s->lights.size();
+    return s->lights.data();
+}
+void gkhost_project_sh(const float* rgba, uint32_t width, uint32_t height, GkSphericalHarmonics* out) {
+    *out = gk::ProjectHdrToSh(rgba, (int)width, (int)height);
+}
 // Scene::UpdateNodes: ticks node velocities (first call after load reports every node as moved, Node.cpp:154-171)
 int gkhost_scene_update_nodes(void* h) { return static_cast<gk::Scene*>(h)->UpdateNodes() ? 1 : 0; }
 

@@ -86,7 +86,8 @@ static void Quad(Model& m, const Vertex& a, const Vertex& b, const Vertex& c, co
 }
 
 // FProcModel::CreateCornellBox (FProcModel.cpp:16-128): pushes 4 materials, returns the model.
-static Model CreateCornellBox(float s, std::vector<GkMaterial>& materials) {
+static Model CreateCornellBox(float s, std::vector<GkMaterial>& materials, std::vector<GkLightObject>& lights) {
+    const uint32_t prevMatId = (uint32_t)materials.size();
     materials.push_back(MaterialLambertian(vec3(0.65f, 0.05f, 0.05f)));  // red
     materials.push_back(MaterialLambertian(vec3(0.12f, 0.45f, 0.15f)));  // green
     materials.push_back(MaterialLambertian(vec3(0.73f, 0.73f, 0.73f)));  // white
@@ -114,6 +115,14 @@ static Model CreateCornellBox(float s, std::vector<GkMaterial>& materials) {
         const float y1 = s * 0.999f;
         Quad(m, V(vec3(x0, y1, z1) - offset, n, 0, 1, 3), V(vec3(x1, y1, z1) - offset, n, 1, 1, 3),
              V(vec3(x1, y1, z0) - offset, n, 1, 0, 3), V(vec3(x0, y1, z0) - offset, n, 0, 0, 3), fwd);
+        GkLightObject light{};  // FProcModel.cpp:110-118
+        const vec3 p0 = vec3(x0, y1, z1) - offset, p1 = vec3(x0, y1, z0) - offset, p3 = vec3(x1, y1, z1) - offset;
+        light.p0 = {p0.x, p0.y, p0.z, 1};
+        light.p1 = {p1.x, p1.y, p1.z, 1};
+        light.p3 = {p3.x, p3.y, p3.z, 1};
+        light.normal_area = {0, -1, 0, (x1 - x0) * (z0 - z1)};
+        light.lightMatIdx = prevMatId + 3;
+        lights.push_back(light);
     }
     FinishModel(m);
     return m;
@@ -230,7 +239,7 @@ static void LoadCornellBox(Scene& s) {  // SceneList.cpp:180-226
     s.camera.FocalDistance = 10;
     s.env.HasSky = false;
     s.env.HasSun = false;
-    s.models.push_back(CreateCornellBox(5.55f, s.materials));
+    s.models.push_back(CreateCornellBox(5.55f, s.materials, s.lights));
     uint32_t cboxModel = (uint32_t)s.models.size() - 1;
     AddNode(s, CreateNode("cbox", vec3(0, 0, 0), quat{1, 0, 0, 0}, vec3(1, 1, 1), cboxModel, (uint32_t)s.nodes.size(), false),
             {prevMatId + 0, prevMatId + 1, prevMatId + 2, prevMatId + 3});
@@ -497,7 +506,7 @@ GkUniformBufferObject Scene::GetUniformBufferObject(uint32_t width, uint32_t hei
     ubo.TemporalFrames = progressive ? 256 : settings.TemporalFrames;
     ubo.HDR = settings.HDR;
     ubo.PaperWhiteNit = settings.PaperWhiteNit;
-    ubo.LightCount = 0;
+    ubo.LightCount = (uint32_t)lights.size();  // Engine.cpp:830
     ubo.BFSigma = settings.DenoiseSigma;
     ubo.BFSigmaLum = settings.DenoiseSigmaLum;
     ubo.BFSigmaNormal = settings.DenoiseSigmaNormal;
@@ -540,6 +549,40 @@ void Scene::PerturbModel(uint32_t model, uint32_t step, std::vector<uint16_t>& o
 }
 
 // ---------------------------------------------------------------- procedural sky
+GkSphericalHarmonics ProjectHdrToSh(const float* hdrPixels, int width, int height) {
+    GkSphericalHarmonics result{};
+    const float pi = 3.14159265358979323846f;
+    const float shC0 = 0.282095f, shC1 = 0.488603f, shC2 = 1.092548f, shC3 = 0.315392f, shC4 = 0.546274f;
+    for (int y = 0; y < height; ++y) {
+        const float v = (y + 0.5f) / height;
+        const float theta = v * pi;
+        const float sinTheta = std::sin(theta), cosTheta = std::cos(theta);
+        const float weight = sinTheta * (pi / height) * (2.0f * pi / width);  // solid angle of the texel
+        for (int x = 0; x < width; ++x) {
+            const float u = (x + 0.5f) / width;
+            const float phi = u * 2.0f * pi;
+            const float dx = sinTheta * std::cos(phi), dy = cosTheta, dz = sinTheta * std::sin(phi);
+            float basis[9];
+            basis[0] = shC0;
+            basis[1] = -shC1 * dy;
+            basis[2] = shC1 * dz;
+            basis[3] = -shC1 * dx;
+            basis[4] = shC2 * dx * dy;
+            basis[5] = -shC2 * dy * dz;
+            basis[6] = shC3 * (3.0f * dy * dy - 1.0f);
+            basis[7] = -shC2 * dx * dz;
+            basis[8] = shC4 * (dx * dx - dz * dz);
+            const float* px = hdrPixels + ((size_t)y * width + x) * 4;
+            for (int i = 0; i < 9; ++i) {
+                result.coefficients[0][i] += px[0] * basis[i] * weight;
+                result.coefficients[1][i] += px[1] * basis[i] * weight;
+                result.coefficients[2][i] += px[2] * basis[i] * weight;
+            }
+        }
+    }
+    return result;
+}
+
 void MakeProceduralSky(uint32_t width, uint32_t height, std::vector<float>& rgba) {
     rgba.resize((size_t)width * height * 4);
     const float pi = 3.14159265358979323846f;

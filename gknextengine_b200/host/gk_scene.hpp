@@ -102,6 +102,7 @@ public:
     std::vector<Node> nodes;
     std::vector<Model> models;
     std::vector<GkMaterial> materials;
+    std::vector<GkLightObject> lights;  // Scene::Lights(), filled by the procedural models (FProcModel.cpp:110-118)
     Camera camera;
     EnvironmentSetting env;
     UserSettings settings;
@@ -124,6 +125,8 @@ GkMaterial MaterialMetallic(vec3 diffuse, float fuzziness);
 GkMaterial MaterialMixture(vec3 diffuse, float fuzziness);
 GkMaterial MaterialDielectric(float refractionIndex, float fuzziness);
 GkMaterial MaterialDiffuseLight(vec3 diffuse);
+// GlobalTexturePool's ProjectHdrToSh (src/Assets/Texture.cpp:180-262): 9 SH coefficients per channel of an equirect RGBA32F image.
+GkSphericalHarmonics ProjectHdrToSh(const float* rgba, int width, int height);
 
 // Procedural stand-in for the sky HDR (assets/textures/river_road_2.hdr is data that cannot travel with this
 // repo): a deterministic analytic equirect RGBA32F image, rows top (+Y) to bottom.

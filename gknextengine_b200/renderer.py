@@ -16,7 +16,7 @@ import os
 
 import numpy as np
 
-from ._abi import (HIT_DTYPE, RAY_DTYPE, RT, RT_FORMAT, GkcuCounters, GkcuKernelStats, GkcuFrameParams, GkcuSceneDesc, GkcuTimings, GkMaterial,
+from ._abi import (GK_CUBE_COUNT, GK_PAGE_COUNT, GkLightObject, GkSphericalHarmonics, HIT_DTYPE, RAY_DTYPE, RT, RT_FORMAT, GkcuCounters, GkcuKernelStats, GkcuFrameParams, GkcuSceneDesc, GkcuTimings, GkMaterial,
                    GkNodeProxy, GkUniformBufferObject)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -48,6 +48,11 @@ def lib():
         L.gkcu_tlas_build.argtypes = [P]
         L.gkcu_set_sky.argtypes = [P, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
         L.gkcu_set_probes.argtypes = [P, C.c_void_p, C.c_void_p]
+        L.gkcu_set_lights.argtypes = [P, C.c_void_p, C.c_uint32]
+        L.gkcu_set_sky_sh.argtypes = [P, C.c_uint32, C.POINTER(GkSphericalHarmonics)]
+        L.gkcu_probes_voxelize.argtypes = [P]
+        L.gkcu_probes_bake.argtypes = [P, C.POINTER(GkUniformBufferObject), C.c_uint32, C.c_uint32]
+        L.gkcu_probes_read.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gkcu_render_frame.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
         L.gkcu_radiance_buffer.argtypes = [P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.gkcu_render_resolve.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
@@ -141,6 +146,47 @@ class CudaPathTracingRenderer:
     def set_sky(self, idx, rgba):
         rgba = np.ascontiguousarray(rgba, dtype=np.float32)
         _ck(lib().gkcu_set_sky(self._ctx, idx, rgba.ctypes.data, rgba.shape[1], rgba.shape[0]))
+
+    # ---- ambient-cube probe grid
+    CUBE_DTYPE = np.dtype([(n, "<u4") for n in ("PosZ", "NegZ", "PosY", "NegY", "PosX", "NegX", "PosZ_D", "NegZ_D", "PosY_D", "NegY_D", "PosX_D", "NegX_D",
+                                                "skyVisibility_pznzpyny", "skyVisibility_pxnxs0s1")])
+    VOXEL_DTYPE = np.dtype([(n, "<u4") for n in ("matId", "age", "distanceToSolid_gg_z01", "distanceToSolid_x01_y01")])
+    PAGE_DTYPE = np.dtype([(n, "<u4") for n in ("pageId", "voxelCount", "voxelDataIdx", "probeDataIdx")])
+
+    def set_lights(self, scene):
+        """GPUScene.Lights of the loaded scene."""
+        p, n = scene.lights()
+        _ck(lib().gkcu_set_lights(self._ctx, C.cast(p, C.c_void_p), n))
+
+    def set_sky_sh(self, idx, sh):
+        """GPUScene.HDRSHs[idx] (host.project_sh of the sky image)."""
+        _ck(lib().gkcu_set_sky_sh(self._ctx, idx, C.byref(sh)))
+
+    def probes_voxelize(self):
+        """FCPUAccelerationStructure::AsyncProcessFull + FCPUPageIndex::UpdateData over the whole grid, on the GPU."""
+        _ck(lib().gkcu_probes_voxelize(self._ctx))
+
+    def probes_bake(self, ubo, first_cube, cube_count):
+        """One Bake.HwAmbientCube dispatch over probes [first_cube, first_cube + cube_count)."""
+        _ck(lib().gkcu_probes_bake(self._ctx, C.byref(ubo), first_cube, cube_count))
+
+    BAKE_TEMPORAL_FRAMES = {0: 30, 1: 120}  # UserSettings.BakeSpeedLevel, RayTraceBaseRenderer.cpp:237-251 (level 2 = off)
+
+    def PostRender(self, ubo, frame_count, bake_speed_level=1):
+        """RayTraceBaseRenderer::PostRender (RayTraceBaseRenderer.cpp:225-274): bake 1/temporalFrames of the grid per frame."""
+        tf = self.BAKE_TEMPORAL_FRAMES.get(bake_speed_level)
+        if tf is None:
+            return
+        group = GK_CUBE_COUNT // 64
+        group_per_frame = group // tf
+        self.probes_bake(ubo, (frame_count % tf) * group_per_frame * 64, group_per_frame * 64)
+
+    def probes_read(self, cubes=True, voxels=True, pages=False):
+        c = np.zeros(GK_CUBE_COUNT, dtype=self.CUBE_DTYPE) if cubes else None
+        v = np.zeros(GK_CUBE_COUNT, dtype=self.VOXEL_DTYPE) if voxels else None
+        pg = np.zeros(GK_PAGE_COUNT * GK_PAGE_COUNT, dtype=self.PAGE_DTYPE) if pages else None
+        _ck(lib().gkcu_probes_read(self._ctx, c.ctypes.data if cubes else None, v.ctypes.data if voxels else None, pg.ctypes.data if pages else None))
+        return c, v, pg
 
     # ---- multi-GPU split (SURVEY 8e)
     def radiance_buffer(self):

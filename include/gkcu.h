@@ -137,6 +137,26 @@ typedef struct GkVoxelData {
     uint32_t distanceToSolid_x01_y01;
 } GkVoxelData;
 
+/* BasicTypes.slang:156-162: one entry of the 64 x 64 page index over the probe grid */
+typedef struct GkPageIndex {
+    uint32_t pageId;
+    uint32_t voxelCount;
+    uint32_t voxelDataIdx;
+    uint32_t probeDataIdx;
+} GkPageIndex;
+
+/* BasicTypes.slang:164-169: 9-coefficient SH of a sky HDR, one row per colour channel */
+typedef struct GkSphericalHarmonics {
+    float coefficients[3][9];
+    float padding;
+} GkSphericalHarmonics;
+
+/* BasicTypes.slang:171-183: quad light (corners p0, p1, p3; area in normal_area.w) */
+typedef struct GkLightObject {
+    GkVec4 p0, p1, p3, normal_area;
+    uint32_t lightMatIdx, reserved1, reserved2, reserved3;
+} GkLightObject;
+
 /* BasicTypes.slang:218-236 / src/Assets/Material.hpp:8-74 */
 typedef struct GkMaterial {
     GkVec4 Diffuse;
@@ -203,6 +223,7 @@ enum {
 /* Probe grid: assets/shaders/common/AmbientCube.slang:11-15. */
 #define GK_CUBE_SIZE_XY 192
 #define GK_CUBE_SIZE_Z 48
+#define GK_PAGE_COUNT 64 /* ACGI_PAGE_COUNT, src/Assets/UniformBuffer.hpp:19-21: 64 x 64 pages of 16 m from (-512, 0, -512) */
 
 /* ------------------------------------------------------------- scene contract */
 
@@ -316,6 +337,24 @@ int gkcu_set_sky(GkcuContext* ctx, uint32_t id, const float* rgba, uint32_t widt
  * (AmbientCube.slang:290-382). */
 int gkcu_set_probes(GkcuContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels);
 
+/* ---------------------------------------------------------------------- probe bake
+ * GPUScene.Lights (Scene::Reload, src/Assets/Scene.cpp:92; FProcModel.cpp:110-118) and GPUScene.HDRSHs[id]
+ * (GlobalTexturePool::GetHDRSphericalHarmonics, src/Assets/Texture.cpp:180-262, uploaded by Scene::UpdateHDRSH, Scene.cpp:432-441). */
+int gkcu_set_lights(GkcuContext* ctx, const GkLightObject* lights, uint32_t count);
+int gkcu_set_sky_sh(GkcuContext* ctx, uint32_t id, const GkSphericalHarmonics* sh);
+/* Replaces FCPUAccelerationStructure::AsyncProcessFull(incremental = false) -> FCPUProbeBaker::ProcessCube(ECPT_Voxelize) over the
+ * whole 192 x 48 x 192 grid and FCPUPageIndex::UpdateData (src/Assets/CPUAccelerationStructure.cpp:85-159, 313-328, 340-389,
+ * 499-528): clears voxels and cubes, casts the 6 axis rays (+ 8 diagonal rays in open space) of every voxel against the current
+ * TLAS, rebuilds the page index. Needs gkcu_update_nodes; builds the TLAS if it is stale. Asynchronous. */
+int gkcu_probes_voxelize(GkcuContext* ctx);
+/* Replaces one Bake.HwAmbientCube dispatch (assets/shaders/Bake.HwAmbientCube.comp.slang:1-20 ->
+ * FGpuProbeGenerator::RenderAmbientCubeOnly, AmbientCube.slang:673-692) as recorded by RayTraceBaseRenderer::PostRender
+ * (src/Rendering/RayTraceBaseRenderer.cpp:225-274): probes [first_cube, first_cube + cube_count), first_cube =
+ * GPUScene.custom_data_0. The range being baked is sampled from a snapshot taken at launch (the reference races). */
+int gkcu_probes_bake(GkcuContext* ctx, const GkUniformBufferObject* ubo, uint32_t first_cube, uint32_t cube_count);
+/* Blocking readback of the probe state; any pointer may be NULL. pages: GK_PAGE_COUNT * GK_PAGE_COUNT entries. */
+int gkcu_probes_read(GkcuContext* ctx, GkAmbientCube* cubes, GkVoxelData* voxels, GkPageIndex* pages);
+
 /* ---------------------------------------------------------------------- frame */
 
 /* Replaces PathTracingRenderer::Render (src/Rendering/PathTracing/PathTracingRenderer.cpp:104-218):
@@ -377,6 +416,7 @@ static_assert(sizeof(GkMaterial) == 64 && offsetof(GkMaterial, Fuzziness) == 28 
 static_assert(sizeof(GkGPUVertex) == 24, "GPUVertex layout");
 static_assert(sizeof(GkAmbientCube) == 56, "AmbientCube layout");
 static_assert(sizeof(GkVoxelData) == 16, "VoxelData layout");
+static_assert(sizeof(GkPageIndex) == 16 && sizeof(GkSphericalHarmonics) == 112 && sizeof(GkLightObject) == 80, "probe-bake layouts");
 #endif
 
 #endif /* GKCU_H */

@@ -459,6 +459,9 @@ struct GkoScene {
     std::vector<Texture> textures;
     std::vector<GkAmbientCube> cubes;
     std::vector<GkVoxelData> voxels;
+    std::vector<GkPageIndex> pages;
+    std::vector<GkLightObject> lights;
+    std::vector<GkSphericalHarmonics> sky_sh;
 #ifdef GKO_TINYBVH
     tinybvh::BVH ttlas;
     std::vector<tinybvh::BLASInstance> tinst;
@@ -734,7 +737,240 @@ struct GkoScene {
         color.w = skyvis / 255.0f;
         return color;
     }
+    static f4 sampleAmbientCubeHL2_DI(const GkAmbientCube& cube, f3 normal) {  // AmbientCube.slang:128-151
+        f4 color = F4(0, 0, 0, 0);
+        float wx = fmaxf(normal.x, 0.0f), wnx = fmaxf(-normal.x, 0.0f), wy = fmaxf(normal.y, 0.0f), wny = fmaxf(-normal.y, 0.0f),
+              wz = fmaxf(normal.z, 0.0f), wnz = fmaxf(-normal.z, 0.0f);
+        float sum = wx + wnx + wy + wny + wz + wnz;
+        color = color + unpackRGB10A2(cube.PosX_D) * wx; color = color + unpackRGB10A2(cube.NegX_D) * wnx;
+        color = color + unpackRGB10A2(cube.PosY_D) * wy; color = color + unpackRGB10A2(cube.NegY_D) * wny;
+        color = color + unpackRGB10A2(cube.PosZ_D) * wz; color = color + unpackRGB10A2(cube.NegZ_D) * wnz;
+        return color * ((sum > 0.0f) ? (1.0f / sum) : 1.0f);
+    }
+    static uint32_t packRGB10A2(f4 color) {  // AmbientCube.slang:58-69
+        f4 c = F4(clampf(color.x / 512.f, 0.0f, 1.0f), clampf(color.y / 512.f, 0.0f, 1.0f), clampf(color.z / 512.f, 0.0f, 1.0f),
+                  clampf(color.w / 512.f, 0.0f, 1.0f));
+        uint32_t r = (uint32_t)(c.x * 1023.0f), g = (uint32_t)(c.y * 1023.0f), b = (uint32_t)(c.z * 1023.0f), a = (uint32_t)(c.w * 3.0f);
+        return r | (g << 10) | (b << 20) | (a << 30);
+    }
+    static uint32_t LerpPackedColorAlt(uint32_t c0, f4 c1, float t) { return packRGB10A2(lerp4(unpackRGB10A2(c0), c1, t)); }  // :112-119
+
+    // Shading.slang:146-192: EvaluateSH + SampleIBLRough
+    f4 SampleIBLRough(uint32_t skyIdx, f3 normal, float rotate) const {
+        if (skyIdx >= sky_sh.size()) return F4(0, 0, 0, 1);
+        const float angle = (1.0f - rotate) * 3.14159265358979323846f;
+        float sinAngle, cosAngle;
+        gk_det_sincosf(angle, &sinAngle, &cosAngle);
+        const f3 n = F3(normal.x * cosAngle + normal.z * sinAngle, normal.y, -normal.x * sinAngle + normal.z * cosAngle);
+        const float SH_C0 = 0.282095f, SH_C1 = 0.488603f, SH_C2 = 1.092548f, SH_C3 = 0.315392f, SH_C4 = 0.546274f;
+        float basis[9];
+        basis[0] = SH_C0;
+        basis[1] = -SH_C1 * n.y;
+        basis[2] = SH_C1 * n.z;
+        basis[3] = -SH_C1 * n.x;
+        basis[4] = SH_C2 * n.x * n.y;
+        basis[5] = -SH_C2 * n.y * n.z;
+        basis[6] = SH_C3 * (3.f * n.y * n.y - 1.0f);
+        basis[7] = -SH_C2 * n.x * n.z;
+        basis[8] = SH_C4 * (n.x * n.x - n.z * n.z);
+        const GkSphericalHarmonics& sh = sky_sh[skyIdx];
+        f3 color = F3(0, 0, 0);
+        for (int i = 0; i < 9; ++i) {
+            color.x += sh.coefficients[0][i] * basis[i];
+            color.y += sh.coefficients[1][i] * basis[i];
+            color.z += sh.coefficients[2][i] * basis[i];
+        }
+        return F4(color.x, color.y, color.z, 1.0f);
+    }
+
+    bool TraceRayVertex(f3 rayOrigin, f3 rayDir, float maxDistance, Vertex& outVertex, GkNodeProxy& outNode) const {
+        Hit h = closest(rayOrigin, rayDir, EPS, maxDistance);
+        if (h.inst == 0xFFFFFFFFu) return false;
+        f3 Bary = F3(1.0f - h.u - h.v, h.u, h.v);
+        outNode = nodes[h.inst];
+        const GkModelData& model = offsets[outNode.modelId];
+        const uint32_t indexOffset = model.indexOffset + h.prim * 3;
+        const uint32_t vertexOffset = model.vertexOffset;
+        const Vertex v0 = UnpackVertexV2(vertices[vertexOffset + indices[indexOffset]]);
+        const Vertex v1 = UnpackVertexV2(vertices[vertexOffset + indices[indexOffset + 1]]);
+        const Vertex v2 = UnpackVertexV2(vertices[vertexOffset + indices[indexOffset + 2]]);
+        outVertex.MaterialIndex = FetchMaterialId(outNode, v0.MaterialIndex);
+        // Mix(a,b,c,bary) = a + (b-a)*bary.y + (c-a)*bary.z (PreProcessor.slang:24)
+        f3 n = v0.Normal + (v1.Normal - v0.Normal) * Bary.y + (v2.Normal - v0.Normal) * Bary.z;
+        // mul(WorldToObject4x3, n).xyz = transpose(world-to-object 3x3) * n
+        const Instance& in = instances[h.inst];
+        f3 nw = F3(in.w2o[0][0] * n.x + in.w2o[1][0] * n.y + in.w2o[2][0] * n.z, in.w2o[0][1] * n.x + in.w2o[1][1] * n.y + in.w2o[2][1] * n.z,
+                   in.w2o[0][2] * n.x + in.w2o[1][2] * n.y + in.w2o[2][2] * n.z);
+        outVertex.Normal = normalize(nw);
+        outVertex.TexCoord = v0.TexCoord + (v1.TexCoord - v0.TexCoord) * Bary.y + (v2.TexCoord - v0.TexCoord) * Bary.z;
+        outVertex.Position = rayOrigin + rayDir * h.t;
+        return true;
+    }
+
+    // ------------------------------------------------------------------------------------------ probe grid
+    static f3 probe_origin(uint32_t gIdx) {  // Bake.HwAmbientCube.comp.slang:12-17
+        const uint32_t y = gIdx / (GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY);
+        const uint32_t z = (gIdx - y * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY) / GK_CUBE_SIZE_XY;
+        const uint32_t x = gIdx - y * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY - z * GK_CUBE_SIZE_XY;
+        const f3 CUBE_OFFSET = F3(-GK_CUBE_SIZE_XY / 2, -1.375f, -GK_CUBE_SIZE_XY / 2) * 0.25f;
+        return F3((float)x, (float)y, (float)z) * 0.25f + CUBE_OFFSET;
+    }
+    // TraceRay of the CPU baker, src/Assets/CPUAccelerationStructure.cpp:42-66 (normalised direction, no tmin, face normal
+    // through the world matrix, material of vertex 0), on the fp16 geometry.
+    bool VoxTrace(f3 origin, f3 dir, float dist, float& outT, f3& outNormal, uint32_t& outMat) const {
+        const f3 d = normalize(dir);
+        Hit h = closest(origin, d, 0.0f, dist);
+        if (h.inst == 0xFFFFFFFFu) return false;
+        const GkNodeProxy& node = nodes[h.inst];
+        const GkModelData& off = offsets[node.modelId];
+        const Vertex v0 = UnpackVertexV2(vertices[off.vertexOffset + indices[off.indexOffset + h.prim * 3]]);
+        const Vertex v1 = UnpackVertexV2(vertices[off.vertexOffset + indices[off.indexOffset + h.prim * 3 + 1]]);
+        const Vertex v2 = UnpackVertexV2(vertices[off.vertexOffset + indices[off.indexOffset + h.prim * 3 + 2]]);
+        const f3 n = normalize(cross(v1.Position - v0.Position, v2.Position - v1.Position));
+        const GkMat4& M = node.worldTS;
+        outNormal = F3(M.m[0][0] * n.x + M.m[1][0] * n.y + M.m[2][0] * n.z, M.m[0][1] * n.x + M.m[1][1] * n.y + M.m[2][1] * n.z,
+                       M.m[0][2] * n.x + M.m[1][2] * n.y + M.m[2][2] * n.z);
+        outT = h.t;
+        outMat = FetchMaterialId(node, v0.MaterialIndex);
+        return true;
+    }
+    void InsideGeometry(f3 origin, f3 rayDir, uint32_t& matId, float& distance) const {  // :85-110
+        float t; f3 nrm; uint32_t mat;
+        if (VoxTrace(origin, rayDir, 0.25f * 64, t, nrm, mat)) {
+            distance = t;
+            if (distance <= 0.25f) {
+                matId = mat;
+                if (dot(nrm, rayDir) > 0.0f || GetMaterial((int)mat).MaterialModel == GK_MATERIAL_DIFFUSE_LIGHT) distance = 0.0f;
+            }
+        }
+    }
+    float DetectDistance(f3 origin, f3 rayDir) const {  // :72-83
+        float t; f3 nrm; uint32_t mat;
+        return VoxTrace(origin, rayDir, 0.25f * 64, t, nrm, mat) ? t : 255.0f;
+    }
+    void VoxelizeCube(uint32_t gIdx) {  // :112-159
+        const f3 origin = probe_origin(gIdx);
+        GkVoxelData cube{};
+        float distPY = 255.0f, distNY = 255.0f, distPX = 255.0f, distNX = 255.0f, distPZ = 255.0f, distNZ = 255.0f;
+        const bool have = !instances.empty();
+        if (have) {
+            InsideGeometry(origin, F3(0, 1, 0), cube.matId, distPY);
+            InsideGeometry(origin, F3(0, -1, 0), cube.matId, distNY);
+            InsideGeometry(origin, F3(1, 0, 0), cube.matId, distPX);
+            InsideGeometry(origin, F3(-1, 0, 0), cube.matId, distNX);
+            InsideGeometry(origin, F3(0, 0, 1), cube.matId, distPZ);
+            InsideGeometry(origin, F3(0, 0, -1), cube.matId, distNZ);
+        }
+        float minDist = fminf(fminf(fminf(distPY, distNY), fminf(distPX, distNX)), fminf(distPZ, distNZ));
+        if (minDist > 254.0f && have) {
+            const f3 dirs[8] = {F3(1, 1, 1), F3(-1, 1, 1), F3(-1, -1, 1), F3(-1, 1, 1), F3(1, 1, -1), F3(-1, 1, -1), F3(-1, -1, -1), F3(-1, 1, -1)};
+            for (const f3& d : dirs) minDist = fminf(minDist, DetectDistance(origin, d));
+        }
+        distPY = clampf(distPY / 0.25f, 0.0f, 1.0f); distNY = clampf(distNY / 0.25f, 0.0f, 1.0f);
+        distPX = clampf(distPX / 0.25f, 0.0f, 1.0f); distNX = clampf(distNX / 0.25f, 0.0f, 1.0f);
+        distPZ = clampf(distPZ / 0.25f, 0.0f, 1.0f); distNZ = clampf(distNZ / 0.25f, 0.0f, 1.0f);
+        const float inside = distPY * distNY * distPX * distNX * distPZ * distNZ;
+        cube.distanceToSolid_gg_z01 = ((uint32_t)(minDist / 0.25f) & 0xFF) | (((uint32_t)(inside * 255.0f) & 0xFF) << 8) |
+                                      (((uint32_t)(distPZ * 255.0f) & 0xFF) << 16) | (((uint32_t)(distNZ * 255.0f) & 0xFF) << 24);
+        cube.distanceToSolid_x01_y01 = ((uint32_t)(distPX * 255.0f) & 0xFF) | (((uint32_t)(distNX * 255.0f) & 0xFF) << 8) |
+                                       (((uint32_t)(distPY * 255.0f) & 0xFF) << 16) | (((uint32_t)(distNY * 255.0f) & 0xFF) << 24);
+        voxels[gIdx] = cube;
+    }
+    void UpdatePageIndex() {  // FCPUPageIndex::UpdateData / GetPage, :499-545
+        pages.assign((size_t)GK_PAGE_COUNT * GK_PAGE_COUNT, GkPageIndex{});
+        for (uint32_t gIdx = 0; gIdx < voxels.size(); ++gIdx) {
+            if (voxels[gIdx].matId == 0) continue;
+            const f3 rel = probe_origin(gIdx) - F3(-512.0f, 0.0f, -512.0f);
+            const int px = std::min(std::max((int)(rel.x / 16.0f), 0), GK_PAGE_COUNT - 1), pz = std::min(std::max((int)(rel.z / 16.0f), 0), GK_PAGE_COUNT - 1);
+            pages[pz * GK_PAGE_COUNT + px].voxelCount += 1;
+        }
+    }
+    // FGpuProbeGenerator::FaceTask, AmbientCube.slang:479-553
+    void FaceTask(const GkUniformBufferObject& Camera, f3 origin, f3 basis, uint32_t iterate, uint32_t& DirectLight, uint32_t& IndirectLight, uint32_t& SkyVisOut,
+                  uint32_t& SunVisOut, const GkAmbientCube* snapshot, uint32_t first, uint32_t count) const {
+        static const f2 grid3x3[9] = {{-0.667f, -0.667f}, {0.0f, -0.667f}, {0.667f, -0.667f}, {-0.667f, 0.0f}, {0.0f, 0.0f},
+                                      {0.667f, 0.0f},     {-0.667f, 0.667f}, {0.0f, 0.667f},  {0.667f, 0.667f}};
+        static const f2 grid4x4[16] = {{-0.75f, -0.75f}, {-0.25f, -0.75f}, {0.25f, -0.75f}, {0.75f, -0.75f}, {-0.75f, -0.25f}, {-0.25f, -0.25f},
+                                       {0.25f, -0.25f},  {0.75f, -0.25f},  {-0.75f, 0.25f}, {-0.25f, 0.25f}, {0.25f, 0.25f},   {0.75f, 0.25f},
+                                       {-0.75f, 0.75f},  {-0.25f, 0.75f},  {0.25f, 0.75f},  {0.75f, 0.75f}};
+        origin = origin + basis * 0.25f * 0.25f;
+        f4 directColor = F4(0, 0, 0, 0), bounceColor = F4(0, 0, 0, 0);
+        float skyVisibility = 0.0f;
+        const f2 offset = grid3x3[iterate % 9u] * 0.25f;
+        for (uint32_t i = 0; i < 16; i++) {
+            const f2 g = grid4x4[i] + offset;
+            f3 hemiVec = normalize(F3(g.x, g.y, 1.0f));
+            f3 rayDir = AlignWithNormal(hemiVec, basis);
+            Vertex hitVertex;
+            GkNodeProxy hitNode;
+            if (TraceRayVertex(origin, rayDir, 20.0f /* FAST_MAX_TRACE_DISTANCE */, hitVertex, hitNode)) {
+                GkMaterial hitMaterial = GetMaterial((int)hitVertex.MaterialIndex);
+                f4 outAlbedo = F4(hitMaterial.Diffuse.x, hitMaterial.Diffuse.y, hitMaterial.Diffuse.z, hitMaterial.Diffuse.w);
+                if (hitMaterial.DiffuseTextureId >= 0) outAlbedo = outAlbedo * sample_texture((uint32_t)hitMaterial.DiffuseTextureId, hitVertex.TexCoord);
+                bounceColor = bounceColor + outAlbedo * interpolateAmbientCubesT(hitVertex.Position, hitVertex.Normal, true, snapshot, first, count) * 1.25f;
+            } else {
+                directColor = directColor + SampleIBLRough(Camera.SkyIdx, rayDir, Camera.SkyRotation) * (Camera.HasSky ? Camera.SkyIntensity : 0.0f);
+                skyVisibility += 1.0f;
+            }
+        }
+        directColor = directColor / 16.0f;
+        bounceColor = bounceColor / 16.0f;
+        if (Camera.LightCount > 0 && !lights.empty()) {
+            const GkLightObject& light = lights[0];
+            const GkMaterial lm = GetMaterial((int)light.lightMatIdx);
+            const f4 lightPower = F4(lm.Diffuse.x, lm.Diffuse.y, lm.Diffuse.z, lm.Diffuse.w);
+            const f3 lightPos = lerp3(F3(light.p1.x, light.p1.y, light.p1.z), F3(light.p3.x, light.p3.y, light.p3.z), 0.5f);
+            // TraceSegment(origin, lightPos, CUBE_UNIT * 0.5), Shading.slang:759-783
+            const f3 dir = lightPos - origin;
+            const float len = length(dir);
+            const float lightAtten = occluded(origin, F3(dir.x / len, dir.y / len, dir.z / len), 0.25f * 0.5f, len - 0.25f * 0.5f) ? 0.0f : 1.0f;
+            const f3 lightDir = normalize(lightPos - origin);
+            const float ndotl = clampf(dot(basis, lightDir), 0.0f, 1.0f);
+            const float distance = length(lightPos - origin);
+            const float attenuation = ndotl * light.normal_area.w / (distance * distance * 3.14159f);
+            directColor = directColor + lightPower * attenuation * lightAtten;
+        }
+        if (Camera.HasSun) {
+            const f3 sunDir = F3(Camera.SunDirection.x, Camera.SunDirection.y, Camera.SunDirection.z);
+            const float sunAtten = occluded(origin, sunDir, EPS, PT_MAX_TRACE_DISTANCE) ? 0.0f : 1.0f;
+            const float ndotl = clampf(dot(basis, sunDir), 0.0f, 1.0f);
+            SunVisOut = sunAtten > 0.0f ? 1 : 0;
+            const f4 sunColor = F4(Camera.SunColor.x, Camera.SunColor.y, Camera.SunColor.z, Camera.SunColor.w);
+            directColor = directColor + sunColor * sunAtten * ndotl * 1.0f * 0.25f;
+        }
+        const float currWeight = 0.125f;
+        const float a = (float)SkyVisOut, b = 255.0f * skyVisibility / 16.0f;
+        SkyVisOut = (uint32_t)(a + (b - a) * currWeight);
+        DirectLight = LerpPackedColorAlt(DirectLight, directColor, currWeight);
+        IndirectLight = LerpPackedColorAlt(IndirectLight, bounceColor, currWeight);
+    }
+    // FGpuProbeGenerator::RenderAmbientCubeOnly, AmbientCube.slang:673-692
+    void BakeCube(const GkUniformBufferObject& Camera, uint32_t CubeIdx, const GkAmbientCube* snapshot, uint32_t first, uint32_t count) {
+        if ((voxels[CubeIdx].distanceToSolid_gg_z01 & 0xFFu) >= 8u) return;
+        const f3 origin = probe_origin(CubeIdx);
+        const uint32_t iterate = voxels[CubeIdx].age;
+        voxels[CubeIdx].age = iterate + 1;
+        GkAmbientCube c = snapshot[CubeIdx - first];
+        uint32_t s0[4] = {c.skyVisibility_pznzpyny & 0xFF, (c.skyVisibility_pznzpyny >> 8) & 0xFF, (c.skyVisibility_pznzpyny >> 16) & 0xFF, c.skyVisibility_pznzpyny >> 24};
+        uint32_t s1[4] = {c.skyVisibility_pxnxs0s1 & 0xFF, (c.skyVisibility_pxnxs0s1 >> 8) & 0xFF, (c.skyVisibility_pxnxs0s1 >> 16) & 0xFF, c.skyVisibility_pxnxs0s1 >> 24};
+        uint32_t sunvis = 0;
+        FaceTask(Camera, origin, F3(0, 1, 0), iterate, c.PosY_D, c.PosY, s0[2], s1[2], snapshot, first, count);
+        FaceTask(Camera, origin, F3(0, -1, 0), iterate, c.NegY_D, c.NegY, s0[3], sunvis, snapshot, first, count);
+        FaceTask(Camera, origin, F3(1, 0, 0), iterate, c.PosX_D, c.PosX, s1[0], sunvis, snapshot, first, count);
+        FaceTask(Camera, origin, F3(-1, 0, 0), iterate, c.NegX_D, c.NegX, s1[1], sunvis, snapshot, first, count);
+        FaceTask(Camera, origin, F3(0, 0, 1), iterate, c.PosZ_D, c.PosZ, s0[0], sunvis, snapshot, first, count);
+        FaceTask(Camera, origin, F3(0, 0, -1), iterate, c.NegZ_D, c.NegZ, s0[1], sunvis, snapshot, first, count);
+        c.skyVisibility_pznzpyny = (s0[0] & 0xFF) | ((s0[1] & 0xFF) << 8) | ((s0[2] & 0xFF) << 16) | ((s0[3] & 0xFF) << 24);
+        c.skyVisibility_pxnxs0s1 = (s1[0] & 0xFF) | ((s1[1] & 0xFF) << 8) | ((s1[2] & 0xFF) << 16) | ((s1[3] & 0xFF) << 24);
+        cubes[CubeIdx] = c;
+    }
+
     f4 interpolateAmbientCubesV2(f3 inPos, f3 normal) const {
+        return interpolateAmbientCubesT(inPos, normal, false, nullptr, 0, 0);
+    }
+    // di: DIAmbientCubeSampler instead of FullAmbientCubeSampler; snapshot: pre-dispatch copies of cubes[first .. first + count)
+    // (the bake reads the range it is updating from there, see gk_shading.cuh SnapshotCubes).
+    f4 interpolateAmbientCubesT(f3 inPos, f3 normal, bool di, const GkAmbientCube* snapshot, uint32_t first, uint32_t count) const {
         const f3 CUBE_OFFSET = F3(-GK_CUBE_SIZE_XY / 2, -1.375f, -GK_CUBE_SIZE_XY / 2) * 0.25f;
         f3 nearpos = (inPos - CUBE_OFFSET) * (1.0f / 0.25f);
         if (nearpos.x < 0 || nearpos.y < 0 || nearpos.z < 0 || nearpos.x > GK_CUBE_SIZE_XY - 2 || nearpos.y > GK_CUBE_SIZE_Z - 2 ||
@@ -748,7 +984,8 @@ struct GkoScene {
         for (int i = 0; i < 8; i++) {
             int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
             int idx = (by + oy) * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + (bz + oz) * GK_CUBE_SIZE_XY + (bx + ox);
-            const GkAmbientCube& cube = cubes[idx];
+            const uint32_t rel = (uint32_t)idx - first;
+            const GkAmbientCube& cube = (snapshot && rel < count) ? snapshot[rel] : cubes[idx];
             const GkVoxelData& voxel = voxels[idx];
             uint32_t u0 = voxel.distanceToSolid_gg_z01, u1 = voxel.distanceToSolid_x01_y01;
             float d0y = float((u0 >> 8) & 0xFF) / 255.0f, distPZ = float((u0 >> 16) & 0xFF) / 255.0f, distNZ = float((u0 >> 24) & 0xFF) / 255.0f;
@@ -763,7 +1000,7 @@ struct GkoScene {
             if (distanceToProbe > hitLength + 0.05f) continue;
             float wx = ox == 0 ? (1.0f - fr.x) : fr.x, wy = oy == 0 ? (1.0f - fr.y) : fr.y, wz = oz == 0 ? (1.0f - fr.z) : fr.z;
             float weight = wx * wy * wz;
-            result = result + sampleAmbientCubeHL2_Full(cube, normal) * weight;
+            result = result + (di ? sampleAmbientCubeHL2_DI(cube, normal) : sampleAmbientCubeHL2_Full(cube, normal)) * weight;
             totalWeight += weight;
         }
         return totalWeight > 0.0f ? result / totalWeight : F4(0, 0, 0, 0);
@@ -873,27 +1110,7 @@ struct Renderer {  // FPathTracingRendererV2, Shading.slang:995-1261, configured
     // FHardwareRayTracerV2::TraceRay, Shading.slang:784-826
     bool TraceRay(f3 rayOrigin, f3 rayDir, float maxDistance, Vertex& outVertex, GkNodeProxy& outNode) {
         n_closest++;
-        Hit h = S.closest(rayOrigin, rayDir, EPS, maxDistance);
-        if (h.inst == 0xFFFFFFFFu) return false;
-        f3 Bary = F3(1.0f - h.u - h.v, h.u, h.v);
-        outNode = S.nodes[h.inst];
-        const GkModelData& offsets = S.offsets[outNode.modelId];
-        const uint32_t indexOffset = offsets.indexOffset + h.prim * 3;
-        const uint32_t vertexOffset = offsets.vertexOffset;
-        const Vertex v0 = UnpackVertexV2(S.vertices[vertexOffset + S.indices[indexOffset]]);
-        const Vertex v1 = UnpackVertexV2(S.vertices[vertexOffset + S.indices[indexOffset + 1]]);
-        const Vertex v2 = UnpackVertexV2(S.vertices[vertexOffset + S.indices[indexOffset + 2]]);
-        outVertex.MaterialIndex = FetchMaterialId(outNode, v0.MaterialIndex);
-        // Mix(a,b,c,bary) = a + (b-a)*bary.y + (c-a)*bary.z (PreProcessor.slang:24)
-        f3 n = v0.Normal + (v1.Normal - v0.Normal) * Bary.y + (v2.Normal - v0.Normal) * Bary.z;
-        // mul(WorldToObject4x3, n).xyz = transpose(world-to-object 3x3) * n
-        const Instance& in = S.instances[h.inst];
-        f3 nw = F3(in.w2o[0][0] * n.x + in.w2o[1][0] * n.y + in.w2o[2][0] * n.z, in.w2o[0][1] * n.x + in.w2o[1][1] * n.y + in.w2o[2][1] * n.z,
-                   in.w2o[0][2] * n.x + in.w2o[1][2] * n.y + in.w2o[2][2] * n.z);
-        outVertex.Normal = normalize(nw);
-        outVertex.TexCoord = v0.TexCoord + (v1.TexCoord - v0.TexCoord) * Bary.y + (v2.TexCoord - v0.TexCoord) * Bary.z;
-        outVertex.Position = rayOrigin + rayDir * h.t;
-        return true;
+        return S.TraceRayVertex(rayOrigin, rayDir, maxDistance, outVertex, outNode);
     }
     bool TraceOcclusion(f3 rayOrigin, f3 rayDir) {  // Shading.slang:737-757
         n_any++;
@@ -1385,6 +1602,23 @@ void parallel_pixels(uint32_t y0, uint32_t y1, uint32_t width, int threads, Fn f
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------- C API
+template <class Fn>
+static void parallel_range(uint32_t n, int threads, Fn fn) {
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<uint32_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            uint32_t i0 = next.fetch_add(256);
+            if (i0 >= n) break;
+            for (uint32_t i = i0; i < std::min(i0 + 256u, n); ++i) fn(i);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+}
+
 extern "C" {
 
 const char* gko_intersector_name(void) {
@@ -1431,6 +1665,32 @@ void gko_set_probes(GkoScene* s, const GkAmbientCube* cubes, const GkVoxelData* 
     if (!cubes || !voxels) { s->cubes.clear(); s->voxels.clear(); return; }
     s->cubes.assign(cubes, cubes + n);
     s->voxels.assign(voxels, voxels + n);
+}
+
+void gko_set_lights(GkoScene* s, const GkLightObject* lights, uint32_t count) { s->lights.assign(lights, lights + count); }
+void gko_set_sky_sh(GkoScene* s, uint32_t id, const GkSphericalHarmonics* sh) {
+    if (s->sky_sh.size() <= id) s->sky_sh.resize(id + 1, GkSphericalHarmonics{});
+    s->sky_sh[id] = *sh;
+}
+void gko_probes_voxelize(GkoScene* s, int threads) {
+    const uint32_t n = GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z;
+    s->voxels.assign(n, GkVoxelData{});
+    s->cubes.assign(n, GkAmbientCube{});
+    parallel_range(n, threads, [&](uint32_t i) { s->VoxelizeCube(i); });
+    s->UpdatePageIndex();
+}
+void gko_probes_bake(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t first, uint32_t count, int threads) {
+    if (s->cubes.empty() || count == 0) return;
+    const std::vector<GkAmbientCube> snapshot(s->cubes.begin() + first, s->cubes.begin() + first + count);
+    parallel_range(count, threads, [&](uint32_t i) { s->BakeCube(*ubo, first + i, snapshot.data(), first, count); });
+}
+const GkAmbientCube* gko_probes_cubes(GkoScene* s) { return s->cubes.data(); }
+const GkVoxelData* gko_probes_voxels(GkoScene* s) { return s->voxels.data(); }
+const GkPageIndex* gko_probes_pages(GkoScene* s) { return s->pages.data(); }
+uint32_t gko_pack_rgb10a2(const float c[4]) { return GkoScene::packRGB10A2(F4(c[0], c[1], c[2], c[3])); }
+void gko_unpack_rgb10a2(uint32_t p, float out[4]) { f4 c = GkoScene::unpackRGB10A2(p); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w; }
+void gko_sample_ibl_rough(GkoScene* s, uint32_t id, const float dir[3], float rotate, float out[4]) {
+    f4 c = s->SampleIBLRough(id, F3(dir[0], dir[1], dir[2]), rotate); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
 }
 
 GkoFrame* gko_frame_create(uint32_t w, uint32_t h) {

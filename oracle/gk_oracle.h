@@ -33,6 +33,19 @@ void gko_set_sky(GkoScene* s, uint32_t id, const float* rgba, uint32_t w, uint32
 void gko_set_probes(GkoScene* s, const GkAmbientCube* cubes, const GkVoxelData* voxels);
 const char* gko_intersector_name(void); /* "native-watertight" or "tinybvh-1.3.8" */
 
+/* Probe grid: voxelisation + page index (src/Assets/CPUAccelerationStructure.cpp:85-159, 499-545) and one bake
+ * dispatch over probes [first, first + count) (AmbientCube.slang:479-553, 673-692) with the snapshot rule of gk_shading.cuh. */
+void gko_set_lights(GkoScene* s, const GkLightObject* lights, uint32_t count);
+void gko_set_sky_sh(GkoScene* s, uint32_t id, const GkSphericalHarmonics* sh);
+void gko_probes_voxelize(GkoScene* s, int threads);
+void gko_probes_bake(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t first, uint32_t count, int threads);
+const GkAmbientCube* gko_probes_cubes(GkoScene* s);
+const GkVoxelData* gko_probes_voxels(GkoScene* s);
+const GkPageIndex* gko_probes_pages(GkoScene* s);
+uint32_t gko_pack_rgb10a2(const float c[4]);
+void gko_unpack_rgb10a2(uint32_t packed, float out[4]);
+void gko_sample_ibl_rough(GkoScene* s, uint32_t id, const float dir[3], float rotate, float out[4]);
+
 GkoFrame* gko_frame_create(uint32_t width, uint32_t height);
 void gko_frame_destroy(GkoFrame* f);
 

@@ -28,6 +28,17 @@ def load(path=NATIVE):
     L.gko_refit_model.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     L.gko_set_sky.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
     L.gko_set_probes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gko_set_lights.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.gko_set_sky_sh.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.gko_probes_voxelize.argtypes = [C.c_void_p, C.c_int]
+    L.gko_probes_bake.argtypes = [C.c_void_p, C.POINTER(GkUniformBufferObject), C.c_uint32, C.c_uint32, C.c_int]
+    for fn in ('gko_probes_cubes', 'gko_probes_voxels', 'gko_probes_pages'):
+        getattr(L, fn).restype = C.c_void_p
+        getattr(L, fn).argtypes = [C.c_void_p]
+    L.gko_pack_rgb10a2.restype = C.c_uint32
+    L.gko_pack_rgb10a2.argtypes = [C.POINTER(C.c_float * 4)]
+    L.gko_unpack_rgb10a2.argtypes = [C.c_uint32, C.POINTER(C.c_float * 4)]
+    L.gko_sample_ibl_rough.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float * 3), C.c_float, C.POINTER(C.c_float * 4)]
     L.gko_intersector_name.restype = C.c_char_p
     L.gko_frame_create.restype = C.c_void_p
     L.gko_frame_create.argtypes = [C.c_uint32, C.c_uint32]
@@ -86,6 +97,33 @@ class OracleScene:
     def set_sky(self, idx, rgba):
         rgba = np.ascontiguousarray(rgba, dtype=np.float32)
         self.L.gko_set_sky(self._h, idx, rgba.ctypes.data, rgba.shape[1], rgba.shape[0])
+
+    # ---- probe grid
+    def set_lights(self, scene):
+        p, n = scene.lights()
+        self.L.gko_set_lights(self._h, C.cast(p, C.c_void_p), n)
+
+    def set_sky_sh(self, idx, sh):
+        self.L.gko_set_sky_sh(self._h, idx, C.byref(sh))
+
+    def set_probes(self, cubes, voxels):
+        self.L.gko_set_probes(self._h, cubes.ctypes.data, voxels.ctypes.data)
+
+    def probes_voxelize(self, threads=0):
+        self.L.gko_probes_voxelize(self._h, threads)
+
+    def probes_bake(self, ubo, first, count, threads=0):
+        self.L.gko_probes_bake(self._h, C.byref(ubo), first, count, threads)
+
+    def probes_read(self, pages=False):
+        from gknextengine_b200._abi import GK_CUBE_COUNT, GK_PAGE_COUNT
+        from gknextengine_b200.renderer import CudaPathTracingRenderer as R
+        def view(ptr, n, dt):
+            return np.frombuffer((C.c_uint8 * (n * dt.itemsize)).from_address(ptr), dtype=dt).copy()
+        c = view(self.L.gko_probes_cubes(self._h), GK_CUBE_COUNT, R.CUBE_DTYPE)
+        v = view(self.L.gko_probes_voxels(self._h), GK_CUBE_COUNT, R.VOXEL_DTYPE)
+        pg = view(self.L.gko_probes_pages(self._h), GK_PAGE_COUNT * GK_PAGE_COUNT, R.PAGE_DTYPE) if pages else None
+        return c, v, pg
 
     def refit_model(self, model, simple_vertices):
         self.L.gko_refit_model(self._h, model, simple_vertices.ctypes.data, len(simple_vertices) // 4)
