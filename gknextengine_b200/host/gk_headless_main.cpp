@@ -1,5 +1,5 @@
 // Headless C++ harness: plays the role of the engine (NextEngine::Tick -> renderer->DrawFrame) for the CUDA renderer.
-//   gk_headless <scene> <width> <height> <frames> [spp] [bounces]
+//   gk_headless <scene> <width> <height> <frames> [spp] [bounces] [bake]     bake = 1: voxelise the probe grid at load, bake 1/120 per frame
 // Prints per-pass GPU times, exact ray counts and writes RT_DENOISED of the last frame as a PPM.
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +30,7 @@ int main(int argc, char** argv) {
         gk::MakeProceduralSky(1024, 512, base.sky_);
         base.skyW_ = 1024;
         base.skyH_ = 512;
+        base.bakeProbes_ = argc > 7 && atoi(argv[7]) != 0;
         base.RegisterLogicRenderer(gk::ERT_CudaPathTracing);  // the renderer switch: Engine.cpp:57-90 / gkNextRenderer.cpp:316-321
         base.SwitchLogicRenderer(gk::ERT_CudaPathTracing);
         base.CreateSwapChain({w, h});

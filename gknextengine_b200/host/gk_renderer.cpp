@@ -48,6 +48,8 @@ void HeadlessBaseRenderer::DrawFrame() {  // VulkanBaseRenderer.cpp:727-869, wit
     if (auto* c = dynamic_cast<CudaPathTracingRenderer*>(it->second.get())) c->PreRender();
     GkUniformBufferObject ubo = scene_->GetUniformBufferObject(extent_.width, extent_.height, frameCount_, progressiveRendering_);
     it->second->Render(ubo, 0);
+    if (bakeProbes_)
+        if (auto* c = dynamic_cast<CudaPathTracingRenderer*>(it->second.get())) c->PostRender(ubo, frameCount_);
     ++frameCount_;
 }
 
@@ -82,9 +84,15 @@ void CudaPathTracingRenderer::OnPostLoadScene(Scene& scene, const float* sky, ui
     Check(gkcu_scene_upload(ctx_, &d), "upload the mesh buffers");
     Check(gkcu_update_materials(ctx_, scene.materials.data(), (uint32_t)scene.materials.size()), "upload the materials");
     Check(gkcu_blas_build(ctx_), "build the bottom level acceleration structures");
-    if (sky) Check(gkcu_set_sky(ctx_, 0, sky, skyW, skyH), "upload the sky");
+    if (sky) {
+        Check(gkcu_set_sky(ctx_, 0, sky, skyW, skyH), "upload the sky");
+        const GkSphericalHarmonics sh = ProjectHdrToSh(sky, (int)skyW, (int)skyH);  // Texture.cpp:448-449
+        Check(gkcu_set_sky_sh(ctx_, 0, &sh), "upload the sky SH");
+    }
+    Check(gkcu_set_lights(ctx_, scene.lights.data(), (uint32_t)scene.lights.size()), "upload the lights");
     AfterUpdateScene(scene);
     sceneLoaded_ = true;
+    if (baseRender_.bakeProbes_) VoxelizeProbes();
 }
 
 void CudaPathTracingRenderer::AfterUpdateScene(Scene& scene) {
@@ -100,6 +108,22 @@ void CudaPathTracingRenderer::Render(const GkUniformBufferObject& ubo, uint32_t)
     p.spp_world = 1;
     Check(gkcu_render_frame(ctx_, &ubo, &p), "render the frame");
 }
+
+void CudaPathTracingRenderer::PostRender(const GkUniformBufferObject& ubo, uint32_t frameCount) {
+    int temporalFrames;
+    switch (baseRender_.bakeSpeedLevel_) {
+        case 0: temporalFrames = 30; break;
+        case 2: return;  // BakeSpeedLevel 2 records no dispatch
+        default: temporalFrames = 120; break;
+    }
+    const int cubesPerGroup = 64;
+    const int group = GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z / cubesPerGroup;
+    const int groupPerFrame = group / temporalFrames;
+    const int offsetInCubes = (int)(frameCount % temporalFrames) * groupPerFrame * cubesPerGroup;
+    Check(gkcu_probes_bake(ctx_, &ubo, (uint32_t)offsetInCubes, (uint32_t)(groupPerFrame * cubesPerGroup)), "bake the ambient cubes");
+}
+
+void CudaPathTracingRenderer::VoxelizeProbes() { Check(gkcu_probes_voxelize(ctx_), "voxelize the probe grid"); }
 
 void CudaPathTracingRenderer::BeforeNextFrame() { Check(gkcu_synchronize(ctx_), "wait for the previous frame"); }
 

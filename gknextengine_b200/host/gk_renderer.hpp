@@ -9,6 +9,7 @@
 //   RayTracing::PathTracingRenderer    PathTracingRenderer.hpp:30-71  gk::CudaPathTracingRenderer
 //   RegisterLogicRenderer / Switch...  VulkanBaseRenderer.cpp:892-917 gk::HeadlessBaseRenderer
 //   RayTraceBaseRenderer AS hooks      RayTraceBaseRenderer.cpp:165-218 OnPreLoadScene / OnPostLoadScene / AfterUpdateScene / PreRender
+//   RayTraceBaseRenderer::PostRender   RayTraceBaseRenderer.cpp:225-274 CudaPathTracingRenderer::PostRender (probe light bake)
 //   Throw(std::runtime_error)          src/Utilities/Exception.hpp:9-15  gk::Check() throws std::runtime_error with gkcu_last_error()
 //
 // The Vulkan-typed parameters of the reference (VkExtent2D, VkCommandBuffer, imageIndex) become plain values: the CUDA
@@ -78,6 +79,8 @@ public:
     void DrawFrame();         // UpdateNodes -> AfterUpdateScene -> PreRender -> Render of the current logic renderer
 
     bool progressiveRendering_ = false;
+    bool bakeProbes_ = false;   // run the probe voxelisation at scene load and the light bake every frame
+    int bakeSpeedLevel_ = 1;    // UserSettings.BakeSpeedLevel: 0 -> 30 frames per sweep, 1 -> 120, 2 -> off
     std::vector<float> sky_;  // RGBA32F equirect for sky id 0
     uint32_t skyW_ = 0, skyH_ = 0;
 
@@ -106,6 +109,10 @@ public:
     void OnPostLoadScene(Scene& scene, const float* sky, uint32_t skyW, uint32_t skyH);
     void AfterUpdateScene(Scene& scene);
     void PreRender();
+    // RayTraceBaseRenderer::PostRender (RayTraceBaseRenderer.cpp:225-274): the "hw-lightbake" dispatch over 1/temporalFrames of the grid
+    void PostRender(const GkUniformBufferObject& ubo, uint32_t frameCount);
+    // FCPUAccelerationStructure::AsyncProcessFull(incremental = false) + Tick upload, done in one call on the GPU
+    void VoxelizeProbes();
 
     void Readback(uint32_t rtIndex, void* dst, size_t bytes);  // RT_DENOISED is what the base renderer blits to the swap chain
     GkcuTimings Timings();
