@@ -133,7 +133,8 @@ def reference_arm(args):
 
 
 def workload_config(n):
-    return {"workload": f"BASELINE configs[1]: RayTracingInOneWeekend procedural scene (RTIO.proc), {WIDTH}x{HEIGHT}, {SPP} spp per GPU "
+    name = "BASELINE configs[1]" if (WIDTH, HEIGHT) == (1920, 1080) else "SURVEY 8d config 5 (qx50.glb absent: declared stand-in scene)"
+    return {"workload": f"{name}: RayTracingInOneWeekend procedural scene (RTIO.proc), {WIDTH}x{HEIGHT}, {SPP} spp per GPU "
                         f"({SPP * n} spp/frame), {BOUNCES} bounces, procedural sky stand-in, steady state, temporal reproject + bilateral denoise",
             "scene": SCENE, "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_per_frame": SPP * n, "bounces": BOUNCES,
             "parallelism": f"spp-split x{n}, scene replica per GPU" if n > 1 else "single GPU",
@@ -148,7 +149,16 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--tracer", type=int, default=0, help="0 wavefront (default), 1 megakernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "peer-hostbarrier", "nccl"],
+                    help="multi-GPU: peer = fused reduce + resolve kernel over NVLink peer memory with device-side barriers (default); "
+                         "peer-hostbarrier = same kernel bracketed by two 4-byte NCCL all-reduces; nccl = ncclReduce to rank 0, resolve there")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2: BASELINE configs[1], 1080p, 16 spp per GPU (weak scaling). config5: SURVEY 8d config 5, 3840x2160, 64 spp per frame "
+                         "split over the GPUs (strong scaling)")
     args = ap.parse_args()
+    global WIDTH, HEIGHT, SPP
+    if args.workload == "config5":
+        WIDTH, HEIGHT = 3840, 2160
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return reference_arm(args)
@@ -171,6 +181,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if args.workload == "config5":
+        if 64 % world:
+            raise SystemExit("config5 splits 64 spp: --gpus must divide 64")
+        SPP = 64 // world
     scene = host.Scene(SCENE, samples=SPP * world, bounces=BOUNCES, taa=True, temporal_frames=16, denoiser=True)
     scene.update_nodes()  # steady state: combinedPrevTS = identity, MOTIONMOMENT stays 0
     sky = host.make_sky(1024, 512)
@@ -188,16 +202,54 @@ def main():
             __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 3}
 
         radiance = torch.as_tensor(_Buf(), device=f"cuda:{local_rank}")
+        if args.reduce != "nccl":
+            # ship every rank's buffers as cudaIpcMemHandles; each rank opens its peers' (NVLink peer access)
+            mine = {what: r.peer_export(what)[0] for what in range(5)}
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            for pr in range(world):
+                if pr == rank:
+                    r.peer_import(pr, r.PEER_RADIANCE, ptr=r.peer_export(r.PEER_RADIANCE)[1])
+                else:
+                    r.peer_import(pr, r.PEER_RADIANCE, handle=everyone[pr][r.PEER_RADIANCE])
+                if args.reduce == "peer":
+                    if pr == rank:
+                        r.peer_import(pr, r.PEER_FLAGS, ptr=r.peer_export(r.PEER_FLAGS)[1])
+                    else:
+                        r.peer_import(pr, r.PEER_FLAGS, handle=everyone[pr][r.PEER_FLAGS])
+            for what in (r.PEER_DIRECT, r.PEER_SINGLE_DIFFUSE, r.PEER_SINGLE_SPECULAR):
+                if rank == 0:
+                    r.peer_import(0, what, ptr=r.peer_export(what)[1])
+                else:
+                    r.peer_import(0, what, handle=everyone[0][what])
+        flag = torch.zeros(1, device=f"cuda:{local_rank}")
+    reduce_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    reduce_ms = [0.0]
 
     def frame(total_frames):
         ubo = scene.ubo(WIDTH, HEIGHT, total_frames)
         r.PreRender()  # "TLAS Update": the reference rebuilds the TLAS every frame (RayTraceBaseRenderer.cpp:205-218)
         r.Render(ubo, params)
         if world > 1:
-            with torch.cuda.stream(ext):
-                dist.reduce(radiance, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                r.Resolve(ubo, params)
+            reduce_ev[0].record(ext)
+            if args.reduce == "nccl":
+                with torch.cuda.stream(ext):
+                    dist.reduce(radiance, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    r.Resolve(ubo, params)
+            elif args.reduce == "peer":
+                r.ResolveStrip(ubo, params)    # device-side barrier, peer loads of my strip from every rank, peer stores into rank 0's SINGLE_*, barrier
+                if rank == 0:
+                    r.run_post(ubo, params)
+            else:
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(flag)      # stream-ordered barrier: every rank's sums are complete
+                r.ResolveStrip(ubo, params)
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(flag)      # every strip has landed (and nobody still reads my radiance buffer)
+                if rank == 0:
+                    r.run_post(ubo, params)
+            reduce_ev[1].record(ext)
         return ubo
 
     def sync_all():
@@ -228,6 +280,8 @@ def main():
         c = r.counters()  # synchronises the stream: the frame is complete
         k = r.kernel_stats()
         t = r.timings()
+        if world > 1:
+            reduce_ms[0] += reduce_ev[0].elapsed_time(reduce_ev[1])
         rays += c["primary_rays"] + c["closest_hit_rays"] + c["any_hit_rays"]
         primary_rays += c["primary_rays"]
         closest_rays += c["closest_hit_rays"]
@@ -284,7 +338,7 @@ def main():
         peak, peak_kind = load_peaks()
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "config2" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": node_bytes + 784,
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 8},
@@ -294,6 +348,12 @@ def main():
             "rays_per_frame": {"primary": primary_rays / args.steps, "closest_hit": closest_rays / args.steps, "any_hit": any_rays / args.steps},
             "passes_ms_per_frame_rank0": {k: v / args.steps for k, v in pass_ms.items()},
         }
+        if world > 1:
+            out["multi_gpu"] = {"exchange": {"peer": "fused reduce+resolve kernel over NVLink peer memory (strips), device-side flag barriers, no collective call",
+                                             "peer-hostbarrier": "fused reduce+resolve kernel over NVLink peer memory (strips) between two 4-byte NCCL all-reduces",
+                                             "nccl": "ncclReduce(sum, fp32) to rank 0 + resolve on rank 0"}[args.reduce],
+                                "exchange_resolve_post_ms_per_frame_rank0": reduce_ms[0] / args.steps,
+                                "radiance_bytes_per_rank": 2 * WIDTH * HEIGHT * 16}
         # roofline of the dominant kernel: k_trace in the wavefront tracer, k_tail in the megakernel
         if args.tracer == 0 and kstats["trace_launches"] > 0:
             per_launch_ms = kstats["trace_ms"] / kstats["trace_launches"]

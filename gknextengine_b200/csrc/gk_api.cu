@@ -118,18 +118,22 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     return 0;
 }
 
+static void drop_peers(Context& c);
+
 int gkcu_destroy(GkcuContext* ctx) {
     if (!ctx) return 0;
     Context& c = ctx->c;
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
+    drop_peers(c);
     path_release(c);
     free_targets(c.rt);
     for (auto& t : c.textures)
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
                       &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
-                      &c.inst_hi, &c.tlas_active_ids, &c.tex_table, &c.cubes, &c.voxels, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits};
+                      &c.inst_hi, &c.tlas_active_ids, &c.tex_table, &c.cubes, &c.voxels, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
+                      &c.peer_flags};
     for (DevBuf* b : bufs) b->release();
     BuildScratch& s = c.scratch;
     DevBuf* sb[] = {&s.prim_lo, &s.prim_hi, &s.keys, &s.keys_sorted, &s.order, &s.order_tmp, &s.sort_tmp, &s.n2_lo, &s.n2_hi, &s.n2_left, &s.n2_right,
@@ -151,6 +155,7 @@ int gkcu_resize(GkcuContext* ctx, uint32_t width, uint32_t height) {
     CTX_OR_FAIL(ctx);
     if (width == 0 || height == 0 || (uint64_t)width * height >= (1ull << 31)) { set_error("gkcu_resize: bad extent"); return 1; }
     GK_CUDA(cudaStreamSynchronize(c.stream));
+    drop_peers(c);
     RenderTargets& t = c.rt;
     free_targets(t);
     size_t n = (size_t)width * height;
@@ -421,9 +426,64 @@ int gkcu_render_resolve(GkcuContext* ctx, const GkUniformBufferObject* ubo, cons
     return 0;
 }
 
+static void drop_peers(Context& c) {
+    for (void* p : c.ipc_opened) cudaIpcCloseMemHandle(p);
+    c.ipc_opened.clear();
+    memset(c.peer, 0, sizeof(c.peer));
+    c.peer_epoch = 0;
+    if (c.peer_flags.p) cudaMemset(c.peer_flags.p, 0, 32 * 8);
+}
+
+int gkcu_peer_export(GkcuContext* ctx, uint32_t what, void* handle, void** device_ptr) {
+    CTX_OR_FAIL(ctx);
+    void* p = peer_local_buffer(c, what);
+    if (!p) { set_error("gkcu_peer_export: unknown buffer or gkcu_resize not called"); return 1; }
+    if (handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == GKCU_IPC_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        GK_CUDA(cudaIpcGetMemHandle(&h, p));
+        memcpy(handle, &h, sizeof(h));
+    }
+    if (device_ptr) *device_ptr = p;
+    return 0;
+}
+
+int gkcu_peer_import(GkcuContext* ctx, uint32_t rank, uint32_t what, const void* handle, void* device_ptr) {
+    CTX_OR_FAIL(ctx);
+    if (rank >= GKCU_MAX_PEERS || what > GKCU_PEER_FLAGS) { set_error("gkcu_peer_import: rank >= 8 or unknown buffer"); return 1; }
+    void* p = device_ptr;
+    if (handle) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof(h));
+        GK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c.ipc_opened.push_back(p);
+    }
+    if (!p) { set_error("gkcu_peer_import: neither a handle nor a device pointer"); return 1; }
+    c.peer[rank][what] = p;
+    return 0;
+}
+
+int gkcu_render_resolve_strip(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params) {
+    CTX_OR_FAIL(ctx);
+    if (frame_prologue(c, ubo, params)) return 1;
+    const uint64_t launches0 = c.launches;
+    if (run_resolve_strip(c, *ubo, *params)) return 1;
+    c.counters.kernel_launches += c.launches - launches0;
+    return 0;
+}
+
 int gkcu_synchronize(GkcuContext* ctx) {
     CTX_OR_FAIL(ctx);
     GK_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.peer_flags.p && c.peer_epoch) {  // a device-side barrier that gave up means a peer never arrived
+        unsigned long long timeouts = 0;
+        GK_CUDA(cudaMemcpy(&timeouts, static_cast<unsigned long long*>(c.peer_flags.p) + 16, 8, cudaMemcpyDeviceToHost));
+        if (timeouts) {
+            cudaMemset(static_cast<unsigned long long*>(c.peer_flags.p) + 16, 0, 8);
+            set_error("multi-GPU barrier timed out: a peer did not reach gkcu_render_resolve_strip");
+            return 1;
+        }
+    }
     return 0;
 }
 

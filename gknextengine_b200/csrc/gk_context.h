@@ -113,6 +113,12 @@ struct Context {
     cudaEvent_t ev[8] = {};
     uint64_t launches = 0;
     DevBuf trace_rays, trace_hits;
+
+    // multi-GPU peer resolve: peer[rank][what] device pointers (local, same-process, or opened from an IPC handle)
+    void* peer[GKCU_MAX_PEERS][5] = {};
+    DevBuf peer_flags;          // this rank's flag block: ready[8], done[8], timeouts (uint64 each), written by the peers
+    uint64_t peer_epoch = 0;
+    std::vector<void*> ipc_opened;
 };
 
 gkd::TraceScene make_trace_scene(const Context& c);
@@ -130,6 +136,8 @@ int run_resolve(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
 int run_trace_rays(Context& c, uint32_t count, bool any_hit);
 void fetch_ray_counters(Context& c);
 int radiance_buffer(Context& c, void** ptr, size_t* bytes);
+int run_resolve_strip(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p);
+void* peer_local_buffer(Context& c, uint32_t what);
 
 // gk_probes.cu
 int probes_voxelize(Context& c);

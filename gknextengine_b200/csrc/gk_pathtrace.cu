@@ -728,6 +728,57 @@ __global__ void k_resolve(RTView R, const float4* __restrict__ radiance, const f
     store_h4(R.single_specular, pixel, fr);
 }
 
+// Fused multi-GPU reduce + resolve of one strip of rows: peer loads of every rank's un-normalised sums, rank-ordered sum,
+// Shading.slang:1175-1183, peer stores of the fp16 results into rank 0's SINGLE_* images. 80 B in per rank-pixel, 16 B out.
+struct PeerRadiance { const float4* rad[GKCU_MAX_PEERS]; };
+__global__ void __launch_bounds__(256) k_resolve_strip(uint2* __restrict__ out_diffuse, uint2* __restrict__ out_specular, PeerRadiance P, int world,
+                                                       const float4* __restrict__ direct0, const uint16_t* __restrict__ moment,
+                                                       const __grid_constant__ GkUniformBufferObject cam, uint32_t n, uint32_t first, uint32_t last) {
+    const uint32_t pixel = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= last) return;
+    float4 fc = __ldcs(P.rad[0] + pixel), fr = __ldcs(P.rad[0] + (size_t)n + pixel);
+    for (int r = 1; r < world; ++r) {
+        fc = fc + __ldcs(P.rad[r] + pixel);
+        fr = fr + __ldcs(P.rad[r] + (size_t)n + pixel);
+    }
+    const int sampleMultiplier = moment[pixel] > 0 ? 4 : 1;
+    const int sample = max(1, (int)cam.NumberOfSamples * sampleMultiplier);
+    fc = fc / float(sample);
+    fr = fr / float(sample);
+    fc = fc + __ldcs(direct0 + pixel);
+    store_h4(out_diffuse, pixel, fc);
+    store_h4(out_specular, pixel, fr);
+}
+
+// Device-side cross-GPU barrier for the strip resolve. Each rank owns a flag block {ready[8], done[8], timeouts}; rank r stores its
+// frame counter into slot r of EVERY rank's block (peer stores, release at system scope: by cumulativity everything this
+// stream wrote before - the radiance sums, or the resolved strip - is visible to whoever acquires the flag), and waits until
+// all slots of its own block have reached the counter.
+struct PeerFlags { unsigned long long* block[GKCU_MAX_PEERS]; };
+__global__ void k_peer_signal(PeerFlags F, int world, int rank, int slot0, unsigned long long epoch) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    unsigned long long* p = F.block[r] + slot0 + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(epoch) : "memory");
+}
+__global__ void k_peer_wait(unsigned long long* mine, int world, int slot0, unsigned long long epoch) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const unsigned long long* p = mine + slot0 + r;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; do not hang the GPU
+            atomicAdd(mine + 16, 1ull);
+            break;
+        }
+        __nanosleep(100);
+    }
+}
+
 __global__ void k_trace_rays(TraceScene ts, const GkcuRay* __restrict__ rays, uint32_t n, GkcuHit* __restrict__ hits, int any_hit) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -943,6 +994,63 @@ int run_resolve(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     PathView V = make_path_view(c);
     uint32_t n = R.w * R.h;
     k_resolve<<<(n + 255) / 256, 256, 0, c.stream>>>(R, V.radiance, V.direct, R.moment, c.ubo.as<GkUniformBufferObject>());
+    c.launches++;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+void* peer_local_buffer(Context& c, uint32_t what) {
+    if (!c.path) return nullptr;
+    switch (what) {
+        case GKCU_PEER_RADIANCE: return c.path->radiance.p;
+        case GKCU_PEER_DIRECT: return c.path->direct.p;
+        case GKCU_PEER_SINGLE_DIFFUSE: return c.rt.single_diffuse;
+        case GKCU_PEER_SINGLE_SPECULAR: return c.rt.single_specular;
+        case GKCU_PEER_FLAGS:
+            if (!c.peer_flags.p) {
+                if (!c.peer_flags.reserve(32 * 8)) return nullptr;
+                cudaMemset(c.peer_flags.p, 0, 32 * 8);
+            }
+            return c.peer_flags.p;
+        default: return nullptr;
+    }
+}
+
+int run_resolve_strip(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {
+    const int world = (int)std::max(1u, p.spp_world);
+    if (world > GKCU_MAX_PEERS) { set_error("gkcu_render_resolve_strip: spp_world > 8"); return 1; }
+    PeerRadiance P{};
+    for (int r = 0; r < world; ++r) {
+        P.rad[r] = static_cast<const float4*>(c.peer[r][GKCU_PEER_RADIANCE]);
+        if (!P.rad[r]) { set_error("gkcu_render_resolve_strip: radiance buffer of rank " + std::to_string(r) + " not imported"); return 1; }
+    }
+    void *d0 = c.peer[0][GKCU_PEER_DIRECT], *sd = c.peer[0][GKCU_PEER_SINGLE_DIFFUSE], *ss = c.peer[0][GKCU_PEER_SINGLE_SPECULAR];
+    if (!d0 || !sd || !ss) { set_error("gkcu_render_resolve_strip: rank 0's direct / SINGLE_* buffers not imported"); return 1; }
+    const uint32_t n = c.rt.w * c.rt.h;
+    const uint32_t y0 = (uint32_t)((uint64_t)p.spp_rank * c.rt.h / world), y1 = (uint32_t)((uint64_t)(p.spp_rank + 1) * c.rt.h / world);
+    const uint32_t first = y0 * c.rt.w, last = y1 * c.rt.w;
+    // device-side barriers when every rank's flag block is known, otherwise the host brackets this call with its own
+    bool flags = true;
+    PeerFlags F{};
+    for (int r = 0; r < world; ++r) {
+        F.block[r] = static_cast<unsigned long long*>(c.peer[r][GKCU_PEER_FLAGS]);
+        flags = flags && F.block[r];
+    }
+    unsigned long long* mine = flags ? F.block[p.spp_rank] : nullptr;
+    if (flags) {
+        ++c.peer_epoch;
+        k_peer_signal<<<1, 32, 0, c.stream>>>(F, world, (int)p.spp_rank, 0, c.peer_epoch);   // my sums are complete
+        k_peer_wait<<<1, 32, 0, c.stream>>>(mine, world, 0, c.peer_epoch);                    // ... and so are everybody's
+        c.launches += 2;
+    }
+    if (last > first)
+        k_resolve_strip<<<(last - first + 255) / 256, 256, 0, c.stream>>>(static_cast<uint2*>(sd), static_cast<uint2*>(ss), P, world, static_cast<const float4*>(d0),
+                                                                       c.rt.moment, ubo, n, first, last);
+    if (flags) {
+        k_peer_signal<<<1, 32, 0, c.stream>>>(F, world, (int)p.spp_rank, 8, c.peer_epoch);   // my strip has landed; I no longer read anyone's sums
+        k_peer_wait<<<1, 32, 0, c.stream>>>(mine, world, 8, c.peer_epoch);                    // all strips landed: rank 0 may post-process, everyone may start the next frame
+        c.launches += 2;
+    }
     c.launches++;
     GK_CUDA(cudaGetLastError());
     return 0;

@@ -53,6 +53,9 @@ def lib():
         L.gkcu_probes_voxelize.argtypes = [P]
         L.gkcu_probes_bake.argtypes = [P, C.POINTER(GkUniformBufferObject), C.c_uint32, C.c_uint32]
         L.gkcu_probes_read.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gkcu_peer_export.argtypes = [P, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.gkcu_peer_import.argtypes = [P, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.gkcu_render_resolve_strip.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
         L.gkcu_render_frame.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
         L.gkcu_radiance_buffer.argtypes = [P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.gkcu_render_resolve.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
@@ -193,6 +196,25 @@ class CudaPathTracingRenderer:
         p, n = C.c_void_p(), C.c_size_t()
         _ck(lib().gkcu_radiance_buffer(self._ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    PEER_RADIANCE, PEER_DIRECT, PEER_SINGLE_DIFFUSE, PEER_SINGLE_SPECULAR, PEER_FLAGS = 0, 1, 2, 3, 4
+
+    def peer_export(self, what):
+        """(64-byte cudaIpcMemHandle, raw device pointer) of one of this rank's buffers."""
+        h = (C.c_uint8 * 64)()
+        p = C.c_void_p()
+        _ck(lib().gkcu_peer_export(self._ctx, what, h, C.byref(p)))
+        return bytes(h), p.value
+
+    def peer_import(self, rank, what, handle=None, ptr=None):
+        """Registers rank `rank`'s buffer: `handle` from another process, or `ptr` from a context of this process."""
+        hb = (C.c_uint8 * 64).from_buffer_copy(handle) if handle is not None else None
+        _ck(lib().gkcu_peer_import(self._ctx, rank, what, hb, C.c_void_p(ptr) if ptr else None))
+
+    def ResolveStrip(self, ubo, params):
+        """Fused reduce + resolve of this rank's strip over peer memory. With every rank's PEER_FLAGS imported the two cross-rank
+        barriers run on the device; otherwise the caller brackets this call with its own stream-ordered barriers."""
+        _ck(lib().gkcu_render_resolve_strip(self._ctx, C.byref(ubo), C.byref(params)))
 
     def Resolve(self, ubo, params):
         _ck(lib().gkcu_render_resolve(self._ctx, C.byref(ubo), C.byref(params)))

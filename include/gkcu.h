@@ -368,6 +368,28 @@ int gkcu_render_frame(GkcuContext* ctx, const GkUniformBufferObject* ubo, const 
 int gkcu_radiance_buffer(GkcuContext* ctx, void** device_ptr, size_t* bytes);
 int gkcu_render_resolve(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params);
 
+/* Fused reduce + resolve over peer memory (the strip variant): instead of an NCCL reduce to rank 0 followed by
+ * gkcu_render_resolve there, every rank resolves its own strip of rows [rank * H / N, (rank + 1) * H / N): one kernel loads
+ * that strip of every rank's radiance buffer over NVLink (peer loads), sums it in rank order, divides by the sample count,
+ * adds rank 0's direct term and stores the fp16 SINGLE_DIFFUSE / SINGLE_SPECULAR strip straight into rank 0's images (peer
+ * stores). Rank 0 then runs gkcu_run_post. The host orders it with two stream-ordered barriers (any tiny collective on
+ * gkcu_stream): after gkcu_render_frame(skip_post = 1) and after gkcu_render_resolve_strip.
+ *   gkcu_peer_export: the caller's buffer `what` as a 64-byte cudaIpcMemHandle (to ship to other processes) and as a raw
+ *                     device pointer (for contexts of the same process).
+ *   gkcu_peer_import: registers rank `rank`'s buffer `what`; pass the handle from another process, or handle = NULL and the
+ *                     raw pointer for a context of this process. Needed: RADIANCE of every rank; DIRECT, SINGLE_DIFFUSE and
+ *                     SINGLE_SPECULAR of rank 0. Imports are dropped by gkcu_resize.
+ * If FLAGS of every rank is imported as well, gkcu_render_resolve_strip does both barriers itself on the device: each rank
+ * stores a frame counter into every peer's flag block when its sums are complete / its strip has landed, and a one-warp
+ * kernel polls the local block (acquire, system scope; gives up after ~2 s and reports it at gkcu_synchronize). The host then
+ * issues no collective at all. */
+#define GKCU_IPC_HANDLE_BYTES 64
+#define GKCU_MAX_PEERS 8
+enum { GKCU_PEER_RADIANCE = 0, GKCU_PEER_DIRECT = 1, GKCU_PEER_SINGLE_DIFFUSE = 2, GKCU_PEER_SINGLE_SPECULAR = 3, GKCU_PEER_FLAGS = 4 };
+int gkcu_peer_export(GkcuContext* ctx, uint32_t what, void* handle, void** device_ptr);
+int gkcu_peer_import(GkcuContext* ctx, uint32_t rank, uint32_t what, const void* handle, void* device_ptr);
+int gkcu_render_resolve_strip(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params);
+
 /* Blocking device->host copy of one storage image in its reference format
  * (fp16x4 / R32_UINT / RG32F / R32F / R16_UINT, VulkanBaseRenderer.cpp:439-457). */
 int gkcu_readback(GkcuContext* ctx, uint32_t rt_index, void* dst, size_t dst_bytes);

@@ -446,6 +446,64 @@ def test_spp_split_across_two_contexts_matches_oracle(sky):
         r.close()
 
 
+@pytest.mark.parametrize("world,device_barrier", [(2, False), (3, False), (2, True), (3, True)])
+def test_peer_memory_strip_resolve_matches_oracle(sky, world, device_barrier):
+    """The fused reduce + resolve over peer memory (gkcu_render_resolve_strip) with `world` contexts on one GPU standing in for
+    `world` GPUs (same kernel, same pointers-to-other-ranks' buffers; across processes the pointers come from IPC handles,
+    bench.py --gpus N). Every rank resolves its strip of rows into rank 0's images; the result must equal the oracle's
+    simulation of all ranks - bit for bit for two ranks (a two-term sum has one order), within one fp16 rounding for three."""
+    W, H = 256, 146  # H not divisible by 3: uneven strips
+    scene = host.Scene("RTIO.proc", samples=6, bounces=5, taa=False)
+    scene.update_nodes()
+    ubo = scene.ubo(W, H, 9)
+    rs = []
+    for rank in range(world):
+        r = CudaPathTracingRenderer(0)
+        r.CreateSwapChain((W, H))
+        r.OnPostLoadScene(scene, sky)
+        rs.append(r)
+    exports = [{what: r.peer_export(what)[1] for what in range(5)} for r in rs]
+    for r in rs:
+        for rank in range(world):
+            r.peer_import(rank, r.PEER_RADIANCE, ptr=exports[rank][r.PEER_RADIANCE])
+            if device_barrier:  # flag blocks known: gkcu_render_resolve_strip synchronises the ranks on the device
+                r.peer_import(rank, r.PEER_FLAGS, ptr=exports[rank][r.PEER_FLAGS])
+        for what in (r.PEER_DIRECT, r.PEER_SINGLE_DIFFUSE, r.PEER_SINGLE_SPECULAR):
+            r.peer_import(0, what, ptr=exports[0][what])
+    for rank, r in enumerate(rs):
+        r.Render(ubo, params(spp_world=world, spp_rank=rank, skip_post=1))
+    if not device_barrier:
+        for r in rs:
+            r.BeforeNextFrame()  # barrier 1: every rank's sums are complete
+    for rank, r in enumerate(rs):
+        r.ResolveStrip(ubo, params(spp_world=world, spp_rank=rank, skip_post=1))
+    if not device_barrier:
+        for r in rs:
+            r.BeforeNextFrame()  # barrier 2: every strip has landed in rank 0's images
+    rs[0].run_post(ubo, params(spp_world=world, spp_rank=0))
+    rs[0].BeforeNextFrame()
+    osc, ofr = O.OracleScene(scene, sky), O.OracleFrame(W, H)
+    ofr.render(osc, ubo, params(spp_world=world))
+    limit = 2e-3
+    for name in ("SINGLE_DIFFUSE", "SINGLE_SPECULAR", "OBJEDCTID_0", "ALBEDO"):
+        assert mismatch_fraction(rs[0].readback(RT[name]), ofr.image(RT[name])) <= limit, name
+    # every strip was written (rows of the last rank included), none twice with different data
+    sd = rs[0].readback(RT["SINGLE_DIFFUSE"]).astype(np.float32)
+    for rank in range(world):
+        y0, y1 = rank * H // world, (rank + 1) * H // world
+        assert sd[y0:y1, :, :3].max() > 0
+    ulps = half_ulp_diff(rs[0].readback(RT["DENOISED"]), ofr.image(RT["DENOISED"]))
+    assert float((ulps > 2).any(axis=2).mean()) <= limit
+    with pytest.raises(GkcuError):
+        rs[0].ResolveStrip(ubo, params(spp_world=world + 1, spp_rank=0, skip_post=1))  # rank `world` never imported
+    if device_barrier:  # a rank that never arrives: the barrier gives up after ~2 s instead of hanging the GPU, and says so
+        rs[0].ResolveStrip(ubo, params(spp_world=world, spp_rank=0, skip_post=1))
+        with pytest.raises(GkcuError, match="barrier timed out"):
+            rs[0].BeforeNextFrame()
+    for r in rs:
+        r.close()
+
+
 def test_full_size_properties_1080p(sky):
     """BASELINE config 2 at full size (1920x1080, 16 spp, 8 bounces): size-independent properties — determinism, exact ray
     accounting, wavefront == megakernel, finite output — plus oracle parity on sampled rows."""
