@@ -112,6 +112,7 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     for (auto& e : c.ev) cudaEventCreate(&e);
     for (auto& e : c.kev) cudaEventCreate(&e);
     for (auto& e : c.wev) cudaEventCreate(&e);
+    if (const char* e = getenv("GKCU_TAIL_DIV")) c.tail_div = std::max(1, std::min(65536, atoi(e)));
     if (const char* e = getenv("GKCU_WAVE_CHUNK")) c.wave_chunk = std::max(1, std::min(8, atoi(e)));
     if (!c.ubo.reserve(sizeof(GkUniformBufferObject))) { delete ctx; return 1; }
     *out_ctx = ctx;

@@ -109,6 +109,7 @@ struct Context {
     GkcuKernelStats kstats{};
     cudaEvent_t kev[8] = {};
     cudaEvent_t wev[24] = {};  // trace/shade brackets of the waves of one chunk
+    int tail_div = 64;         // the wavefront hands over to k_tail once the wave is narrower than pixels / tail_div (GKCU_TAIL_DIV)
     int wave_chunk = 4;        // waves launched between two host polls of the queue size (GKCU_WAVE_CHUNK)
     cudaEvent_t ev[8] = {};
     uint64_t launches = 0;

@@ -552,6 +552,9 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
 template <int VARIANT>
 __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below) {
     const uint32_t n = V.counts[qi];
+    // the other queue (this wave's output, last wave's input) is idle while this kernel runs: clear its size here instead of
+    // with a memset between the kernels
+    if (blockIdx.x == 0 && threadIdx.x == 0) V.counts[qi ^ 1] = 0;
     const int lane = threadIdx.x & 31;
     const float4* ray_o = V.ray_o + (size_t)qi * half;
     const float4* ray_d = V.ray_d + (size_t)qi * half;
@@ -627,6 +630,7 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
 // The first version: a warp takes 32 rays, every lane runs the simple per-ray loop, the warp refills when all are done.
 __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V, int qi, size_t half) {
     const uint32_t n = V.counts[qi];
+    if (blockIdx.x == 0 && threadIdx.x == 0) V.counts[qi ^ 1] = 0;
     const int lane = threadIdx.x & 31;
     const float4* ray_o = V.ray_o + (size_t)qi * half;
     const float4* ray_d = V.ray_d + (size_t)qi * half;
@@ -653,6 +657,10 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
     SceneView S = S_;
     S.cam = &cam;
     const uint32_t n = V.counts[qi];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        V.counts[2] = 0;  // trace cursor of the next wave (this wave's k_trace is done)
+        if (n) { V.counts[12] += n; V.counts[13] += 1; }  // rays and launches of the wavefront part, for the statistics
+    }
     PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
     uint32_t nclosest = 0, nany = 0;
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -914,7 +922,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
         // Wavefront loop while the wave is wide; k_tail finishes the thin tail in one launch. The queue can only shrink (every
         // path has at most one successor), so the last size the host has seen bounds the grids of the following waves: the
         // host polls the size only every `wave_chunk` waves and the kernels read the exact size from device memory.
-        const uint32_t tail_threshold = std::max<uint32_t>(pixels / 64, (uint32_t)c.sm_count * 128u);
+        const uint32_t tail_threshold = std::max<uint32_t>(pixels / (uint32_t)std::max(1, c.tail_div), (uint32_t)c.sm_count * 128u);
         const int chunk = std::max(1, std::min(c.wave_chunk, 8));
         uint32_t bound = pixels;
         GK_CUDA(cudaMemcpyAsync(b.host_counts, counts + qi, 4, cudaMemcpyDeviceToHost, st));
@@ -922,8 +930,6 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
         bound = b.host_counts[0];
         while (bound > tail_threshold) {
             for (int w = 0; w < chunk; ++w) {
-                GK_CUDA(cudaMemsetAsync(counts + 2, 0, 4, st));
-                GK_CUDA(cudaMemsetAsync(counts + (qi ^ 1), 0, 4, st));
                 const uint32_t blocks = std::min<uint32_t>((bound + 127) / 128, persistent_blocks);
                 cudaEventRecord(c.wev[3 * w], st);
                 if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
@@ -936,8 +942,6 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 else if (c.shade_minb == 10) k_shade<10><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
                 else k_shade<1><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
                 cudaEventRecord(c.wev[3 * w + 2], st);
-                // exact size of this wave, for the statistics (read after the chunk's synchronisation)
-                GK_CUDA(cudaMemcpyAsync(b.host_counts + 16 + w, counts + qi, 4, cudaMemcpyDeviceToHost, st));
                 c.launches += 2;
                 qi ^= 1;
                 ++iterations;
@@ -950,11 +954,6 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 cudaEventElapsedTime(&bms, c.wev[3 * w + 1], c.wev[3 * w + 2]);
                 ks.trace_ms += a;
                 ks.shade_ms += bms;
-                if (b.host_counts[16 + w] > 0) {
-                    ks.trace_launches++;
-                    ks.shade_launches++;
-                    ks.trace_rays += b.host_counts[16 + w];
-                }
             }
             bound = b.host_counts[0];
         }
@@ -968,6 +967,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     }
     c.kstats = ks;
     GK_CUDA(cudaMemcpyAsync(b.host_counts + 8, ray_counters, 24, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaMemcpyAsync(b.host_counts + 16, counts + 12, 8, cudaMemcpyDeviceToHost, st));
     c.counters.wavefront_iterations = iterations;
     GK_CUDA(cudaGetLastError());
     return 0;
@@ -984,6 +984,8 @@ void fetch_ray_counters(Context& c) {
     if (cudaEventElapsedTime(&ms, c.kev[0], c.kev[1]) == cudaSuccess) c.kstats.primary_ms = ms;
     if (cudaEventElapsedTime(&ms, c.kev[5], c.kev[6]) == cudaSuccess) c.kstats.tail_ms = ms;
     cudaGetLastError();
+    c.kstats.trace_rays = c.path->host_counts[16];
+    c.kstats.trace_launches = c.kstats.shade_launches = c.path->host_counts[17];
     c.kstats.tail_rays = h[1] + h[2] - c.kstats.trace_rays;
 }
 
