@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cooperative_groups.h>
+
 #include "gk_context.h"
 
 using namespace gkd;
@@ -214,13 +216,11 @@ __device__ __forceinline__ float box_area(float4 lo, float4 hi) {
 
 // One BFS level of the BVH2 -> Node4 collapse. Entry = (bvh2 node, node4 slot). A bvh2 node with <= leaf_max primitives
 // becomes a leaf reference; otherwise the largest-area internal child is opened until there are 4 children.
-__global__ void k_collapse_level(const int2* __restrict__ qin, const int* __restrict__ nin_ptr, int2* __restrict__ qout, int* __restrict__ nout, int* __restrict__ node_counter,
-                                 const float4* __restrict__ nlo, const float4* __restrict__ nhi, const int* __restrict__ left,
-                                 const int* __restrict__ right, const int* __restrict__ first, const int* __restrict__ count, int leaf_max,
-                                 const uint32_t* __restrict__ order, const uint32_t* __restrict__ remap, int tlas_mode, Node4* __restrict__ out, float4* __restrict__ out_lo,
-                                 float4* __restrict__ out_hi) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *nin_ptr) return;
+__device__ __forceinline__ void collapse_item(int i, const int2* qin, const int* nin_ptr, int2* qout, int* nout, int* node_counter,
+                                 const float4* nlo, const float4* nhi, const int* left,
+                                 const int* right, const int* first, const int* count, int leaf_max,
+                                 const uint32_t* order, const uint32_t* remap, int tlas_mode, Node4* out, float4* out_lo,
+                                 float4* out_hi) {
     int2 e = qin[i];
     int kids[4];
     int nk;
@@ -267,6 +267,15 @@ __global__ void k_collapse_level(const int2* __restrict__ qin, const int* __rest
     write_node4(out + e.y, nk, ch);
     out_lo[e.y] = l;
     out_hi[e.y] = h;
+}
+__global__ void k_collapse_level(const int2* __restrict__ qin, const int* __restrict__ nin_ptr, int2* __restrict__ qout, int* __restrict__ nout, int* __restrict__ node_counter,
+                                 const float4* __restrict__ nlo, const float4* __restrict__ nhi, const int* __restrict__ left,
+                                 const int* __restrict__ right, const int* __restrict__ first, const int* __restrict__ count, int leaf_max,
+                                 const uint32_t* __restrict__ order, const uint32_t* __restrict__ remap, int tlas_mode, Node4* __restrict__ out, float4* __restrict__ out_lo,
+                                 float4* __restrict__ out_hi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nin_ptr) return;
+    collapse_item(i, qin, nin_ptr, qout, nout, node_counter, nlo, nhi, left, right, first, count, leaf_max, order, remap, tlas_mode, out, out_lo, out_hi);
 }
 
 __global__ void k_write_tris(const uint16_t* __restrict__ simple, const uint32_t* __restrict__ indices, uint32_t vertex_offset,
@@ -389,11 +398,9 @@ __device__ __forceinline__ int sah_bin_of(float c, float lo, float hi) {
 }
 
 // slot_of[node] = active slot or -1
-__global__ void k_sah_bin(int n, const uint32_t* __restrict__ order, const int* __restrict__ pos_node, const int* __restrict__ slot_of,
-                          const float4* __restrict__ plo, const float4* __restrict__ phi, const float4* __restrict__ nlo,
-                          const float4* __restrict__ nhi, SahBin* __restrict__ bins) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void sah_bin_item(int i, int n, const uint32_t* order, const int* pos_node, const int* slot_of,
+                          const float4* plo, const float4* phi, const float4* nlo,
+                          const float4* nhi, SahBin* bins) {
     int node = pos_node[i];
     int slot = slot_of[node];
     if (slot < 0) return;
@@ -409,13 +416,18 @@ __global__ void k_sah_bin(int n, const uint32_t* __restrict__ order, const int* 
         atomicAdd(&bn->cnt, 1);
     }
 }
+__global__ void k_sah_bin(int n, const uint32_t* __restrict__ order, const int* __restrict__ pos_node, const int* __restrict__ slot_of,
+                          const float4* __restrict__ plo, const float4* __restrict__ phi, const float4* __restrict__ nlo,
+                          const float4* __restrict__ nhi, SahBin* __restrict__ bins) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sah_bin_item(i, n, order, pos_node, slot_of, plo, phi, nlo, nhi, bins);
+}
 
 struct SahSplit { int axis, plane, nl, fallback; };
 
-__global__ void k_sah_split(int leaf_max, const int* __restrict__ nactive_ptr, const int* __restrict__ active, const SahBin* __restrict__ bins, float4* nlo, float4* nhi, int* left,
+__device__ __forceinline__ void sah_split_item(int s, int leaf_max, const int* nactive_ptr, const int* active, const SahBin* bins, float4* nlo, float4* nhi, int* left,
                             int* right, int* first, int* count, int* counters, int* next_active, SahSplit* splits, int* cursors) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= *nactive_ptr) return;
     int node = active[s];
     int cnt = count[node];
     float bestCost = FLT_MAX;
@@ -487,14 +499,18 @@ __global__ void k_sah_split(int leaf_max, const int* __restrict__ nactive_ptr, c
     if (sp.nl > leaf_max) next_active[atomicAdd(&counters[2], 1)] = c0;
     if (cnt - sp.nl > leaf_max) next_active[atomicAdd(&counters[2], 1)] = c0 + 1;
 }
+__global__ void k_sah_split(int leaf_max, const int* __restrict__ nactive_ptr, const int* __restrict__ active, const SahBin* __restrict__ bins, float4* nlo, float4* nhi, int* left,
+                            int* right, int* first, int* count, int* counters, int* next_active, SahSplit* splits, int* cursors) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *nactive_ptr) return;
+    sah_split_item(s, leaf_max, nactive_ptr, active, bins, nlo, nhi, left, right, first, count, counters, next_active, splits, cursors);
+}
 
-__global__ void k_sah_partition(int n, const uint32_t* __restrict__ order, const int* __restrict__ pos_node, const int* __restrict__ slot_of,
-                                const float4* __restrict__ plo, const float4* __restrict__ phi, const float4* __restrict__ nlo,
-                                const float4* __restrict__ nhi, const int* __restrict__ left, const int* __restrict__ first,
-                                const SahSplit* __restrict__ splits, int* __restrict__ cursors, uint32_t* __restrict__ order_out,
-                                int* __restrict__ pos_node_out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void sah_partition_item(int i, int n, const uint32_t* order, const int* pos_node, const int* slot_of,
+                                const float4* plo, const float4* phi, const float4* nlo,
+                                const float4* nhi, const int* left, const int* first,
+                                const SahSplit* splits, int* cursors, uint32_t* order_out,
+                                int* pos_node_out) {
     int node = pos_node[i];
     int slot = slot_of[node];
     uint32_t p = order[i];
@@ -521,6 +537,15 @@ __global__ void k_sah_partition(int n, const uint32_t* __restrict__ order, const
     order_out[dst] = p;
     pos_node_out[dst] = left[node] + (goLeft ? 0 : 1);
 }
+__global__ void k_sah_partition(int n, const uint32_t* __restrict__ order, const int* __restrict__ pos_node, const int* __restrict__ slot_of,
+                                const float4* __restrict__ plo, const float4* __restrict__ phi, const float4* __restrict__ nlo,
+                                const float4* __restrict__ nhi, const int* __restrict__ left, const int* __restrict__ first,
+                                const SahSplit* __restrict__ splits, int* __restrict__ cursors, uint32_t* __restrict__ order_out,
+                                int* __restrict__ pos_node_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sah_partition_item(i, n, order, pos_node, slot_of, plo, phi, nlo, nhi, left, first, splits, cursors, order_out, pos_node_out);
+}
 
 __global__ void k_fill_int(int* p, int n, int v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -539,6 +564,128 @@ __global__ void k_collapse_next(int* counters, int level) {
     counters[16 + level + 2] = counters[8];  // nodes allocated so far = first node of level + 2
     counters[10] = counters[9];
     counters[9] = 0;
+}
+
+
+// ------------------------------------------------------------------------------------------- fused small build
+// The whole SAH build + wide collapse of a small input (the per-frame TLAS of a few thousand instances) in ONE block: the
+// level-synchronous phases above run back to back with __syncthreads() between them instead of ~130 tiny launches and three
+// host round trips (0.93 ms -> see profiles/r01_experiments.md for 1.9 k instances). Same per-item code, same tree.
+struct FusedBuild {
+    int n, leaf_max, max_slots;
+    const float4 *plo, *phi;
+    int* bounds;
+    float4 *nlo, *nhi;
+    int *left, *right, *first, *count, *slot_of;
+    uint32_t *ord_a, *ord_b;
+    int *pn_a, *pn_b, *act_a, *act_b, *cursors, *counters;
+    SahSplit* splits;
+    SahBin* bins;
+    int2 *qa, *qb;
+    const uint32_t* remap;
+    Node4* out;
+    float4 *out_lo, *out_hi;
+};
+template <bool GRID>
+__global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B) {
+    // GRID: a cooperative launch of a few blocks, phases separated by grid-wide barriers; otherwise one block and __syncthreads()
+    const int T = blockDim.x * gridDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    auto sync = [&]() {
+        if (GRID) cooperative_groups::this_grid().sync();
+        else __syncthreads();
+    };
+    const int n = B.n;
+    // bounds of the active boxes
+    if (t < 3) B.bounds[t] = 0x7FFFFFFF;
+    else if (t < 6) B.bounds[t] = (int)0x80000000;
+    sync();
+    {
+        float3 mn = f3(FLT_MAX, FLT_MAX, FLT_MAX), mx = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+        for (int i = t; i < n; i += T) {
+            const float4 a = B.plo[i], b = B.phi[i];
+            if (a.x <= b.x) {
+                mn = f3(fminf(mn.x, a.x), fminf(mn.y, a.y), fminf(mn.z, a.z));
+                mx = f3(fmaxf(mx.x, b.x), fmaxf(mx.y, b.y), fmaxf(mx.z, b.z));
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn.x = fminf(mn.x, __shfl_xor_sync(0xffffffffu, mn.x, o)); mn.y = fminf(mn.y, __shfl_xor_sync(0xffffffffu, mn.y, o));
+            mn.z = fminf(mn.z, __shfl_xor_sync(0xffffffffu, mn.z, o)); mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, o));
+            mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, o)); mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, o));
+        }
+        if ((t & 31) == 0 && mn.x <= mx.x) {
+            atomicMin(&B.bounds[0], f2o(mn.x)); atomicMin(&B.bounds[1], f2o(mn.y)); atomicMin(&B.bounds[2], f2o(mn.z));
+            atomicMax(&B.bounds[3], f2o(mx.x)); atomicMax(&B.bounds[4], f2o(mx.y)); atomicMax(&B.bounds[5], f2o(mx.z));
+        }
+    }
+    sync();
+    uint32_t *ord_a = B.ord_a, *ord_b = B.ord_b;
+    int *pn_a = B.pn_a, *pn_b = B.pn_b, *act_a = B.act_a, *act_b = B.act_b;
+    int* counters = B.counters;
+    for (int i = t; i < n; i += T) { ord_a[i] = i; pn_a[i] = 0; }
+    for (int i = t; i < 2 * n + 2; i += T) B.slot_of[i] = -1;
+    if (t == 0) {  // k_sah_init
+        B.nlo[0] = f4(o2f(B.bounds[0]), o2f(B.bounds[1]), o2f(B.bounds[2]), 0);
+        B.nhi[0] = f4(o2f(B.bounds[3]), o2f(B.bounds[4]), o2f(B.bounds[5]), 0);
+        B.left[0] = B.right[0] = -1;
+        B.first[0] = 0;
+        B.count[0] = n;
+        act_a[0] = 0;
+        counters[0] = 1;
+        counters[1] = (n > B.leaf_max) ? 1 : 0;
+        counters[2] = 0;
+    }
+    sync();
+    for (int level = 0; level < 512; ++level) {
+        const int nactive = counters[1];
+        if (nactive == 0) break;
+        for (int i = t; i < nactive; i += T) B.slot_of[act_a[i]] = i;
+        for (int i = t; i < nactive * 3 * kSahBins; i += T) {
+            SahBin b;
+            b.lo[0] = b.lo[1] = b.lo[2] = 0x7FFFFFFF;
+            b.hi[0] = b.hi[1] = b.hi[2] = (int)0x80000000;
+            b.cnt = 0;
+            b.pad = 0;
+            B.bins[i] = b;
+        }
+        sync();
+        for (int i = t; i < n; i += T) sah_bin_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, B.bins);
+        sync();
+        for (int sl = t; sl < nactive; sl += T)
+            sah_split_item(sl, B.leaf_max, counters + 1, act_a, B.bins, B.nlo, B.nhi, B.left, B.right, B.first, B.count, counters, act_b, B.splits, B.cursors);
+        sync();
+        for (int i = t; i < n; i += T)
+            sah_partition_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, B.left, B.first, B.splits, B.cursors, ord_b, pn_b);
+        sync();
+        for (int i = t; i < nactive; i += T) B.slot_of[act_a[i]] = -1;
+        sync();
+        if (t == 0) { counters[1] = counters[2]; counters[2] = 0; }
+        sync();
+        uint32_t* to = ord_a; ord_a = ord_b; ord_b = to;
+        int* tp = pn_a; pn_a = pn_b; pn_b = tp;
+        int* ta = act_a; act_a = act_b; act_b = ta;
+    }
+    // collapse to Node4, BFS; counters[8] node4 counter, [9] next-level queue size, [10] this level's queue size, [16 + L] level table
+    int2 *qa = B.qa, *qb = B.qb;
+    if (t == 0) { qa[0] = make_int2(0, 0); counters[8] = 1; counters[9] = 0; counters[10] = 1; }
+    for (int i = t; i < 48; i += T) counters[16 + i] = 0;
+    sync();
+    for (int level = 0; level < 46; ++level) {
+        const int nin = counters[10];
+        if (nin == 0) break;
+        for (int i = t; i < nin; i += T)
+            collapse_item(i, qa, counters + 10, qb, counters + 9, counters + 8, B.nlo, B.nhi, B.left, B.right, B.first, B.count, B.leaf_max, ord_a, B.remap,
+                          B.remap ? 1 : 0, B.out, B.out_lo, B.out_hi);
+        sync();
+        if (t == 0) {
+            counters[16 + level + 2] = counters[8];
+            counters[10] = counters[9];
+            counters[9] = 0;
+            counters[11] = level + 1;  // levels run
+        }
+        sync();
+        int2* tq = qa; qa = qb; qb = tq;
+    }
 }
 
 // ------------------------------------------------------------------------------------------- instances
@@ -781,6 +928,60 @@ int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, const ui
     return 0;
 }
 
+// Small inputs: bounds + SAH build + collapse in one single-block launch, one host read at the end.
+int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Node4* out, float4* out_lo, float4* out_hi, WideBvhInfo& info) {
+    BuildScratch& s = c.scratch;
+    cudaStream_t st = c.stream;
+    size_t max_slots = n / (leaf_max + 1) + 2;
+    if (!s.bins.reserve(max_slots * 3 * kSahBins * sizeof(SahBin)) || !s.pos_node.reserve((size_t)n * 4) || !s.pos_node_tmp.reserve((size_t)n * 4) ||
+        !s.active.reserve((max_slots * 2 + 4) * 4 * 2) || !s.cursors.reserve(max_slots * 2 * 4 + max_slots * sizeof(SahSplit) + 64))
+        return 1;
+    FusedBuild B;
+    B.n = (int)n; B.leaf_max = leaf_max; B.max_slots = (int)max_slots;
+    B.plo = s.prim_lo.as<float4>(); B.phi = s.prim_hi.as<float4>();
+    B.bounds = s.bounds.as<int>();
+    B.nlo = s.n2_lo.as<float4>(); B.nhi = s.n2_hi.as<float4>();
+    B.left = s.n2_left.as<int>(); B.right = s.n2_right.as<int>(); B.first = s.n2_first.as<int>(); B.count = s.n2_count.as<int>();
+    B.slot_of = s.n2_flag.as<int>();
+    B.ord_a = s.order.as<uint32_t>(); B.ord_b = s.order_tmp.as<uint32_t>();
+    B.pn_a = s.pos_node.as<int>(); B.pn_b = s.pos_node_tmp.as<int>();
+    B.act_a = s.active.as<int>(); B.act_b = B.act_a + (max_slots * 2 + 4);
+    B.cursors = s.cursors.as<int>();
+    B.splits = reinterpret_cast<SahSplit*>(B.cursors + max_slots * 2 + 16);
+    B.counters = s.counters.as<int>();
+    B.bins = s.bins.as<SahBin>();
+    B.qa = s.queue_a.as<int2>(); B.qb = s.queue_b.as<int2>();
+    B.remap = remap; B.out = out; B.out_lo = out_lo; B.out_hi = out_hi;
+    // one item per thread up to 64 blocks; a single block for tiny inputs (no cooperative launch needed)
+    const int blocks = (int)std::min<size_t>(64, ((size_t)n + 255) / 256);
+    if (blocks <= 1) {
+        k_build_fused<false><<<1, n <= 256 ? 256 : 1024, 0, st>>>(B);
+    } else {
+        void* args[] = {&B};
+        GK_CUDA(cudaLaunchCooperativeKernel((void*)k_build_fused<true>, dim3(blocks), dim3(256), args, 0, st));
+    }
+    c.launches += 1;
+    int table[48];
+    int last[4];
+    GK_CUDA(cudaMemcpyAsync(table, B.counters + 16, 48 * 4, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaMemcpyAsync(last, B.counters + 8, 16, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    GK_CUDA(cudaGetLastError());
+    if (last[2] != 0) { set_error("BVH collapse did not terminate (tree deeper than 46 wide levels)"); return 1; }
+    const int levels_run = last[3];
+    info.level_start.clear();
+    info.level_start.push_back(0);
+    table[0] = 0;
+    table[1] = 1;
+    for (int L = 1; L <= levels_run + 1 && L < 48; ++L) {
+        if (L > 1 && (uint32_t)table[L] == info.level_start.back()) break;
+        info.level_start.push_back((uint32_t)table[L]);
+    }
+    if (info.level_start.back() != (uint32_t)last[0]) { set_error("BVH collapse: inconsistent level table"); return 1; }
+    info.node_count = (uint32_t)last[0];
+    return 0;
+}
+
 }  // namespace
 
 gkd::TraceScene make_trace_scene(const Context& c) {
@@ -915,9 +1116,16 @@ int build_tlas(Context& c) {
     c.launches += 1;
     Bvh2 b2;
     const char* tb = getenv("GKCU_TLAS_BUILDER");
-    if (tb && std::string(tb) == "lbvh") { if (build_lbvh(c, m, m, b2)) return 1; }
-    else if (build_sah(c, m, 1, b2)) return 1;
-    if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+    static const uint32_t fused_max = getenv("GKCU_TLAS_FUSED_MAX") ? (uint32_t)atoi(getenv("GKCU_TLAS_FUSED_MAX")) : 8192u;
+    if (tb && std::string(tb) == "lbvh") {
+        if (build_lbvh(c, m, m, b2)) return 1;
+        if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+    } else if (m <= fused_max) {
+        if (build_fused(c, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+    } else {
+        if (build_sah(c, m, 1, b2)) return 1;
+        if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+    }
     // the traversal stack holds at most 3 entries per level plus one sentinel per instance entry
     size_t blas_levels = 0;
     for (auto& b : c.blas) blas_levels = std::max(blas_levels, b.level_start.size() > 0 ? b.level_start.size() - 1 : 0);
