@@ -111,7 +111,12 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
     for (auto& e : c.ev) cudaEventCreate(&e);
     for (auto& e : c.kev) cudaEventCreate(&e);
-    for (auto& e : c.wev) cudaEventCreate(&e);
+    for (auto& l : c.wev)
+        for (auto& e : l) cudaEventCreate(&e);
+    for (auto& l : c.lane_ev)
+        for (auto& e : l) cudaEventCreate(&e);
+    for (auto& st : c.lane_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (const char* e = getenv("GKCU_LANES")) c.lanes = std::max(1, std::min(4, atoi(e)));
     if (const char* e = getenv("GKCU_TAIL_DIV")) c.tail_div = std::max(1, std::min(65536, atoi(e)));
     if (const char* e = getenv("GKCU_WAVE_CHUNK")) c.wave_chunk = std::max(1, std::min(8, atoi(e)));
     if (!c.ubo.reserve(sizeof(GkUniformBufferObject))) { delete ctx; return 1; }
@@ -145,8 +150,14 @@ int gkcu_destroy(GkcuContext* ctx) {
         if (e) cudaEventDestroy(e);
     for (auto& e : c.kev)
         if (e) cudaEventDestroy(e);
-    for (auto& e : c.wev)
-        if (e) cudaEventDestroy(e);
+    for (auto& l : c.wev)
+        for (auto& e : l)
+            if (e) cudaEventDestroy(e);
+    for (auto& l : c.lane_ev)
+        for (auto& e : l)
+            if (e) cudaEventDestroy(e);
+    for (auto& st : c.lane_stream)
+        if (st) cudaStreamDestroy(st);
     cudaStreamDestroy(c.stream);
     delete ctx;
     return 0;

@@ -50,11 +50,15 @@ struct PathView {
     float4 *radiance, *direct;  // multi-GPU: un-normalised sums (2 planes) and rank 0's direct term
 };
 
+struct PathLanes { PathView v[4]; uint32_t n; };
+
 struct PathBuffers {
     DevBuf rng, pos_mat, nrm_flags, dir_cnt, ray_color, final_color, final_refl, prim_pos_mat, prim_nrm_cnt, prim_albedo;
     DevBuf ray_o, ray_d, slot_pixel[2], hit_tuv, hit_prim, counts, radiance, direct;
-    uint32_t* host_counts = nullptr;  // pinned
+    uint32_t* host_counts = nullptr;  // pinned, 64 words per lane
     size_t pixels = 0;
+    size_t lane_cap = 0;  // queue capacity of one lane
+    int lanes = 1;
 };
 
 struct FrameCfg {
@@ -388,7 +392,8 @@ GK_DEV void enqueue(const PathView& V, int qi, bool want, uint32_t pixel, int re
 // Primary visibility + G-buffer (FPathTracingRendererV2::Init/PrimaryHit, Shading.slang:1187-1241, with the visibility
 // buffer lookup of FVisibilityBufferRayCasterV2::TracePrimaryRay, :338-494, replaced by a closest-hit cast of the same
 // pixel-corner ray), the buffer clear (Util.BufferClear.comp.slang:5-14), and the first ray of sample 0.
-__global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, unsigned long long* ray_counters) {
+__global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, const __grid_constant__ PathLanes L, FrameCfg cfg, unsigned long long* ray_counters) {
+    const PathView& V = L.v[(blockIdx.x + blockIdx.y) % L.n];  // checkerboard of tiles over the lanes
     SceneView S = S_;
     S.cam = &cam;  // the camera block is read through the constant bank (uniform loads), not through L1
     const int x = blockIdx.x * 8 + (threadIdx.x & 7), y = blockIdx.y * 16 + (threadIdx.x >> 3);
@@ -833,18 +838,20 @@ RTView make_rt_view(const Context& c) {
     R.objectid0 = t.objectid[t.cur]; R.primitiveid = t.primitiveid; R.motion = t.motion; R.prev_depth = t.prev_depth; R.moment = t.moment;
     return R;
 }
-PathView make_path_view(const Context& c) {
+// Lane `lane` of the frame: its own pair of queues (capacity lane_cap each) and counters; the per-pixel state is shared.
+PathView make_path_view(const Context& c, int lane = 0) {
     PathBuffers& b = *c.path;
     PathView V;
-    V.rng = b.rng.as<uint4>();
-    V.pixels = b.pixels;
-    V.pos_mat = b.pos_mat.as<float4>(); V.nrm = b.nrm_flags.as<float4>(); V.dir = b.dir_cnt.as<float4>();
-    V.ray_color = b.ray_color.as<float4>(); V.final_color = b.final_color.as<float4>(); V.final_refl = b.final_refl.as<float4>();
+    const size_t cap = b.lane_cap, q = (size_t)lane * 2 * cap, h = (size_t)lane * cap;
+    V.rng = b.rng.as<uint4>() + q;
+    V.pixels = cap;
+    V.pos_mat = b.pos_mat.as<float4>() + q; V.nrm = b.nrm_flags.as<float4>() + q; V.dir = b.dir_cnt.as<float4>() + q;
+    V.ray_color = b.ray_color.as<float4>() + q; V.final_color = b.final_color.as<float4>(); V.final_refl = b.final_refl.as<float4>();
     V.prim_pos_mat = b.prim_pos_mat.as<float4>(); V.prim_nrm_cnt = b.prim_nrm_cnt.as<float4>(); V.prim_albedo = b.prim_albedo.as<float4>();
-    V.ray_o = b.ray_o.as<float4>(); V.ray_d = b.ray_d.as<float4>();
-    V.slot_pixel[0] = b.slot_pixel[0].as<uint32_t>(); V.slot_pixel[1] = b.slot_pixel[1].as<uint32_t>();
-    V.hit_tuv = b.hit_tuv.as<float4>(); V.hit_prim = b.hit_prim.as<uint32_t>();
-    V.counts = b.counts.as<uint32_t>();
+    V.ray_o = b.ray_o.as<float4>() + q; V.ray_d = b.ray_d.as<float4>() + q;
+    V.slot_pixel[0] = b.slot_pixel[0].as<uint32_t>() + h; V.slot_pixel[1] = b.slot_pixel[1].as<uint32_t>() + h;
+    V.hit_tuv = b.hit_tuv.as<float4>() + h; V.hit_prim = b.hit_prim.as<uint32_t>() + h;
+    V.counts = b.counts.as<uint32_t>() + (size_t)lane * 64;
     V.radiance = b.radiance.as<float4>(); V.direct = b.direct.as<float4>();
     return V;
 }
@@ -856,13 +863,18 @@ int path_resize(Context& c) {
     PathBuffers& b = *c.path;
     size_t n = (size_t)c.rt.w * c.rt.h;
     b.pixels = n;
-    bool ok = b.rng.reserve(2 * n * 16) && b.pos_mat.reserve(2 * n * 16) && b.nrm_flags.reserve(2 * n * 16) && b.dir_cnt.reserve(2 * n * 16) &&
-              b.ray_color.reserve(2 * n * 16) && b.final_color.reserve(n * 16) && b.final_refl.reserve(n * 16) && b.prim_pos_mat.reserve(n * 16) &&
-              b.prim_nrm_cnt.reserve(n * 16) && b.prim_albedo.reserve(n * 16) && b.ray_o.reserve(2 * n * 16) && b.ray_d.reserve(2 * n * 16) &&
-              b.slot_pixel[0].reserve(n * 4) && b.slot_pixel[1].reserve(n * 4) && b.hit_tuv.reserve(n * 16) && b.hit_prim.reserve(n * 4) &&
-              b.counts.reserve(64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16);
+    // k_primary deals its 8 x 16 pixel tiles to the lanes as a checkerboard: a lane gets at most one tile more per tile row than its share
+    b.lanes = std::max(1, std::min(4, c.lanes));
+    const size_t tiles_x = (c.rt.w + 7) / 8, tiles_y = (c.rt.h + 15) / 16;
+    b.lane_cap = b.lanes == 1 ? n : ((tiles_x * tiles_y + b.lanes - 1) / b.lanes + tiles_y + 8) * 128;
+    const size_t m = b.lane_cap * b.lanes;  // slots over all lanes (>= n)
+    bool ok = b.rng.reserve(2 * m * 16) && b.pos_mat.reserve(2 * m * 16) && b.nrm_flags.reserve(2 * m * 16) && b.dir_cnt.reserve(2 * m * 16) &&
+              b.ray_color.reserve(2 * m * 16) && b.final_color.reserve(n * 16) && b.final_refl.reserve(n * 16) && b.prim_pos_mat.reserve(n * 16) &&
+              b.prim_nrm_cnt.reserve(n * 16) && b.prim_albedo.reserve(n * 16) && b.ray_o.reserve(2 * m * 16) && b.ray_d.reserve(2 * m * 16) &&
+              b.slot_pixel[0].reserve(m * 4) && b.slot_pixel[1].reserve(m * 4) && b.hit_tuv.reserve(m * 16) && b.hit_prim.reserve(m * 4) &&
+              b.counts.reserve(4 * 64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16);
     if (!ok) return 1;
-    if (!b.host_counts) GK_CUDA(cudaMallocHost(&b.host_counts, 64 * 4));
+    if (!b.host_counts) GK_CUDA(cudaMallocHost(&b.host_counts, 4 * 64 * 4));
     return 0;
 }
 
@@ -897,77 +909,110 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     PathBuffers& b = *c.path;
     SceneView S = make_scene_view(c);
     RTView R = make_rt_view(c);
-    PathView V = make_path_view(c);
+    const int lanes = b.lanes;
+    PathLanes L{};
+    L.n = (uint32_t)lanes;
+    for (int l = 0; l < lanes; ++l) L.v[l] = make_path_view(c, l);
     FrameCfg cfg;
     cfg.world = std::max(1u, p.spp_world);
     cfg.rank = std::min(p.spp_rank, cfg.world - 1);
     cfg.frame_seed = cfg.world == 1 ? ubo.TotalFrames : ubo.TotalFrames * cfg.world + cfg.rank;
     cfg.to_radiance = p.skip_post ? 1u : 0u;
     cfg.exit_after_first = ubo.FastGather ? 1u : 0u;
-    uint32_t* counts = V.counts;
-    unsigned long long* ray_counters = reinterpret_cast<unsigned long long*>(counts + 4);
-    GK_CUDA(cudaMemsetAsync(counts, 0, 64 * 4, st));
+    GK_CUDA(cudaMemsetAsync(b.counts.p, 0, 4 * 64 * 4, st));
+    auto ray_counters_of = [&](int l) { return reinterpret_cast<unsigned long long*>(L.v[l].counts + 4); };
     GkcuKernelStats ks{};
     dim3 grid((R.w + 7) / 8, (R.h + 15) / 16);
     cudaEventRecord(c.kev[0], st);
-    k_primary<<<grid, 128, 0, st>>>(S, ubo, R, V, cfg, ray_counters);
+    k_primary<<<grid, 128, 0, st>>>(S, ubo, R, L, cfg, ray_counters_of(0));
     cudaEventRecord(c.kev[1], st);
     c.launches++;
     const uint32_t pixels = R.w * R.h;
-    const size_t half = pixels;
-    const uint32_t persistent_blocks = (uint32_t)c.sm_count * 8u;
     uint64_t iterations = 0;
-    int qi = 0;
+    // Lane l runs on its own stream (lane 0 of a single-lane frame stays on the context stream): waves are stream-ordered inside a
+    // lane and independent across lanes, so the hardware overlaps one lane's k_shade and the draining end of its k_trace with
+    // the other lanes' kernels.
+    cudaStream_t ls[4];
+    for (int l = 0; l < lanes; ++l) ls[l] = lanes == 1 ? st : c.lane_stream[l];
+    if (lanes > 1) {
+        cudaEventRecord(c.lane_ev[0][3], st);
+        for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls[l], c.lane_ev[0][3], 0);
+    }
+    int qi[4] = {0, 0, 0, 0};
+    uint32_t bound[4] = {0, 0, 0, 0};
+    bool active[4] = {false, false, false, false};
     if (p.tracer == 0) {
         // Wavefront loop while the wave is wide; k_tail finishes the thin tail in one launch. The queue can only shrink (every
         // path has at most one successor), so the last size the host has seen bounds the grids of the following waves: the
         // host polls the size only every `wave_chunk` waves and the kernels read the exact size from device memory.
-        const uint32_t tail_threshold = std::max<uint32_t>(pixels / (uint32_t)std::max(1, c.tail_div), (uint32_t)c.sm_count * 128u);
+        const uint32_t tail_threshold = std::max<uint32_t>(pixels / (uint32_t)std::max(1, c.tail_div), (uint32_t)c.sm_count * 128u) / (uint32_t)lanes;
         const int chunk = std::max(1, std::min(c.wave_chunk, 8));
-        uint32_t bound = pixels;
-        GK_CUDA(cudaMemcpyAsync(b.host_counts, counts + qi, 4, cudaMemcpyDeviceToHost, st));
-        GK_CUDA(cudaStreamSynchronize(st));
-        bound = b.host_counts[0];
-        while (bound > tail_threshold) {
-            for (int w = 0; w < chunk; ++w) {
-                const uint32_t blocks = std::min<uint32_t>((bound + 127) / 128, persistent_blocks);
-                cudaEventRecord(c.wev[3 * w], st);
-                if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, st>>>(S.ts, V, qi, half);
-                else if (c.trace_variant == 0) k_trace<0><<<blocks, 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-                else k_trace<5><<<std::min<uint32_t>((bound + 127) / 128, (uint32_t)c.sm_count * 16u), 128, 0, st>>>(S.ts, V, qi, half, c.refill_below);
-                cudaEventRecord(c.wev[3 * w + 1], st);
-                if (c.shade_minb == 8) k_shade<8><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
-                else if (c.shade_minb == 7) k_shade<7><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
-                else if (c.shade_minb == 6) k_shade<6><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
-                else if (c.shade_minb == 10) k_shade<10><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
-                else k_shade<1><<<(bound + 127) / 128, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
-                cudaEventRecord(c.wev[3 * w + 2], st);
-                c.launches += 2;
-                qi ^= 1;
-                ++iterations;
+        for (int l = 0; l < lanes; ++l) GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l, L.v[l].counts + 0, 4, cudaMemcpyDeviceToHost, ls[l]));
+        bool any = false;
+        for (int l = 0; l < lanes; ++l) {
+            GK_CUDA(cudaStreamSynchronize(ls[l]));
+            bound[l] = b.host_counts[64 * l];
+            active[l] = bound[l] > tail_threshold;
+            any = any || active[l];
+        }
+        while (any) {
+            for (int l = 0; l < lanes; ++l) {
+                if (!active[l]) continue;
+                const PathView& V = L.v[l];
+                const size_t half = V.pixels;
+                cudaStream_t s2 = ls[l];
+                for (int w = 0; w < chunk; ++w) {
+                    const uint32_t blocks = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 8u);
+                    cudaEventRecord(c.wev[l][3 * w], s2);
+                    if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half);
+                    else if (c.trace_variant == 0) k_trace<0><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                    else k_trace<5><<<std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u), 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                    cudaEventRecord(c.wev[l][3 * w + 1], s2);
+                    const uint32_t sb = (bound[l] + 127) / 128;
+                    if (c.shade_minb == 8) k_shade<8><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
+                    else if (c.shade_minb == 7) k_shade<7><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
+                    else if (c.shade_minb == 6) k_shade<6><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
+                    else if (c.shade_minb == 10) k_shade<10><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
+                    else k_shade<1><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
+                    cudaEventRecord(c.wev[l][3 * w + 2], s2);
+                    c.launches += 2;
+                    qi[l] ^= 1;
+                    ++iterations;
+                }
+                GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l, V.counts + qi[l], 4, cudaMemcpyDeviceToHost, s2));
             }
-            GK_CUDA(cudaMemcpyAsync(b.host_counts, counts + qi, 4, cudaMemcpyDeviceToHost, st));
-            GK_CUDA(cudaStreamSynchronize(st));
-            for (int w = 0; w < chunk; ++w) {
-                float a = 0, bms = 0;
-                cudaEventElapsedTime(&a, c.wev[3 * w], c.wev[3 * w + 1]);
-                cudaEventElapsedTime(&bms, c.wev[3 * w + 1], c.wev[3 * w + 2]);
-                ks.trace_ms += a;
-                ks.shade_ms += bms;
+            any = false;
+            for (int l = 0; l < lanes; ++l) {
+                if (!active[l]) continue;
+                GK_CUDA(cudaStreamSynchronize(ls[l]));
+                for (int w = 0; w < chunk; ++w) {
+                    float a = 0, bms = 0;
+                    cudaEventElapsedTime(&a, c.wev[l][3 * w], c.wev[l][3 * w + 1]);
+                    cudaEventElapsedTime(&bms, c.wev[l][3 * w + 1], c.wev[l][3 * w + 2]);
+                    ks.trace_ms += a;
+                    ks.shade_ms += bms;
+                }
+                bound[l] = b.host_counts[64 * l];
+                active[l] = bound[l] > tail_threshold;
+                any = any || active[l];
             }
-            bound = b.host_counts[0];
         }
     }
-    {
-        const uint32_t blocks = std::min<uint32_t>((pixels + 127) / 128, (uint32_t)c.sm_count * 16u);
-        cudaEventRecord(c.kev[5], st);
-        k_tail<<<blocks, 128, 0, st>>>(S, ubo, R, V, cfg, qi, ray_counters);
-        cudaEventRecord(c.kev[6], st);
+    for (int l = 0; l < lanes; ++l) {
+        const uint32_t blocks = std::min<uint32_t>((pixels / lanes + 127) / 128, (uint32_t)c.sm_count * 16u);
+        cudaEventRecord(c.lane_ev[l][0], ls[l]);
+        k_tail<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l));
+        cudaEventRecord(c.lane_ev[l][1], ls[l]);
         c.launches++;
+        // per lane: primary / closest / any ray counters (3 x u64) and the wavefront statistics (rays, launches)
+        GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 8, ray_counters_of(l), 24, cudaMemcpyDeviceToHost, ls[l]));
+        GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 16, L.v[l].counts + 12, 8, cudaMemcpyDeviceToHost, ls[l]));
+        if (lanes > 1) {
+            cudaEventRecord(c.lane_ev[l][2], ls[l]);
+            cudaStreamWaitEvent(st, c.lane_ev[l][2], 0);  // the post passes on the context stream follow every lane
+        }
     }
     c.kstats = ks;
-    GK_CUDA(cudaMemcpyAsync(b.host_counts + 8, ray_counters, 24, cudaMemcpyDeviceToHost, st));
-    GK_CUDA(cudaMemcpyAsync(b.host_counts + 16, counts + 12, 8, cudaMemcpyDeviceToHost, st));
     c.counters.wavefront_iterations = iterations;
     GK_CUDA(cudaGetLastError());
     return 0;
@@ -976,17 +1021,26 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
 // valid after the stream has been synchronised
 void fetch_ray_counters(Context& c) {
     if (!c.path || !c.path->host_counts) return;
-    const unsigned long long* h = reinterpret_cast<const unsigned long long*>(c.path->host_counts + 8);
-    c.counters.primary_rays = h[0];
-    c.counters.closest_hit_rays = h[1];
-    c.counters.any_hit_rays = h[2];
+    c.counters.primary_rays = c.counters.closest_hit_rays = c.counters.any_hit_rays = 0;
+    c.kstats.trace_rays = 0;
+    c.kstats.trace_launches = 0;
+    c.kstats.tail_ms = 0;
+    for (int l = 0; l < c.path->lanes; ++l) {
+        const uint32_t* hc = c.path->host_counts + 64 * l;
+        const unsigned long long* h = reinterpret_cast<const unsigned long long*>(hc + 8);
+        c.counters.primary_rays += h[0];
+        c.counters.closest_hit_rays += h[1];
+        c.counters.any_hit_rays += h[2];
+        c.kstats.trace_rays += hc[16];
+        c.kstats.trace_launches += hc[17];
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c.lane_ev[l][0], c.lane_ev[l][1]) == cudaSuccess) c.kstats.tail_ms += ms;
+    }
+    c.kstats.shade_launches = c.kstats.trace_launches;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c.kev[0], c.kev[1]) == cudaSuccess) c.kstats.primary_ms = ms;
-    if (cudaEventElapsedTime(&ms, c.kev[5], c.kev[6]) == cudaSuccess) c.kstats.tail_ms = ms;
     cudaGetLastError();
-    c.kstats.trace_rays = c.path->host_counts[16];
-    c.kstats.trace_launches = c.kstats.shade_launches = c.path->host_counts[17];
-    c.kstats.tail_rays = h[1] + h[2] - c.kstats.trace_rays;
+    c.kstats.tail_rays = c.counters.closest_hit_rays + c.counters.any_hit_rays - c.kstats.trace_rays;
 }
 
 int run_resolve(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {
