@@ -98,20 +98,23 @@ struct PathRegs {
 };
 
 // ------------------------------------------------------------------------------------------------ primary hit
-struct PrimVertex { float3 pos, nrm; float2 uv; uint32_t matSlot; };
+struct PrimVertex { float3 pos, nrm; float2 uv; uint32_t matSlot; float3 lnrm; float4 ltan; };
 
-// Common.get_material_dataV2, GeneralFunc.slang:6-56 (tangent frames only feed normal maps: "next" row f4)
+// Common.get_material_dataV2, GeneralFunc.slang:6-56 (the world-space tangent is not used on this path; the local normal and tangent feed the normal map)
 GK_DEV PrimVertex get_material_dataV2(const SceneView& S, uint32_t nodeIdx, uint32_t prim, float3 ray_origin, float3 ray_direction) {
     const GkNodeProxy* proxy = S.nodes + nodeIdx;
     const GkModelData* model = S.offsets + proxy->modelId;
     const uint32_t vo = model->vertexOffset, io = model->indexOffset;
-    float3 positions[3], normals[3];
+    float3 positions[3], normals[3], lnrm[3];
+    float4 ltan[3];
     float2 tex[3];
     uint32_t matid = 0;
     for (int i = 0; i != 3; ++i) {
         VtxLite v = unpack_vertex(S, vo + __ldg(S.indices + io + prim * 3 + i));
         positions[i] = xyz(mul(proxy->worldTS, f4(v.pos.x, v.pos.y, v.pos.z, 1)));
         normals[i] = xyz(mul(proxy->worldTS, f4(v.nrm.x, v.nrm.y, v.nrm.z, 0)));
+        lnrm[i] = v.nrm;
+        ltan[i] = v.tan;
         tex[i] = v.uv;
         if (i == 0) matid = v.matSlot;
     }
@@ -127,6 +130,8 @@ GK_DEV PrimVertex get_material_dataV2(const SceneView& S, uint32_t nodeIdx, uint
     r.pos = positions[0] * bx + (positions[1] * by + positions[2] * bz);
     r.nrm = normalize(normals[0] * bx + (normals[1] * by + normals[2] * bz));
     r.uv = tex[0] * bx + (tex[1] * by + tex[2] * bz);
+    r.lnrm = lnrm[0] * bx + (lnrm[1] * by + lnrm[2] * bz);
+    r.ltan = ltan[0] * bx + (ltan[1] * by + ltan[2] * bz);
     r.matSlot = matid;
     return r;
 }
@@ -476,6 +481,14 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
             if (material.DiffuseTextureId >= 0) albedo = albedo * sample_texture(S, (uint32_t)material.DiffuseTextureId, fv.uv);
             float roughness = material.Fuzziness;
             if (material.MRATextureId >= 0) roughness = roughness * sample_texture(S, (uint32_t)material.MRATextureId, fv.uv).y;
+            if (material.NormalTextureId >= 0) {  // mikkTSpace in the local frame, then to world space (:74-80, 100-107)
+                const float4 t = sample_texture(S, (uint32_t)material.NormalTextureId, fv.uv);
+                const float3 vNt = f3(t.x, t.y, t.z) * 2.0f - f3(1.0f, 1.0f, 1.0f);
+                const float3 tg = f3(fv.ltan.x, fv.ltan.y, fv.ltan.z);
+                const float3 vB = cross(fv.lnrm, tg) * fv.ltan.w;
+                const float3 nl = normalize(tg * vNt.x + vB * vNt.y + fv.lnrm * vNt.z);
+                hnrm = normalize(xyz(mul(node->worldTS, f4(nl.x, nl.y, nl.z, 0.0f))));
+            }
             uint16_t moment = R.moment[pixel];
             {   // CalculateMotionVectorV2, Shading.slang:50-72
                 float4 Pw = f4(hpos.x, hpos.y, hpos.z, 1);

@@ -1230,13 +1230,27 @@ struct Renderer {  // FPathTracingRendererV2, Shading.slang:995-1261, configured
         return prevfpos - currfpos;
     }
 
-    // Common.FetchGBufferV2, Shading.slang:82-112 (material textures: "next" row f4; ids < 0 in every fixture)
-    void FetchGBufferV2(Vertex& inVertex, const GkMaterial& m, f4& outAlbedo, f4& outNormal) {
+    // Shading.slang:74-80
+    static f3 mikkTSpace(f3 vNt, f3 normal, f4 tangent) {
+        vNt = vNt * 2.0f - F3(1.0f, 1.0f, 1.0f);
+        f3 vB = cross(normal, xyz(tangent)) * tangent.w;
+        return normalize(xyz(tangent) * vNt.x + vB * vNt.y + normal * vNt.z);
+    }
+    // Common.FetchGBufferV2, Shading.slang:82-112
+    void FetchGBufferV2(Vertex& inVertex, const GkMaterial& m, const GkNodeProxy& proxy, f4& outAlbedo, f4& outNormal) {
         outAlbedo = F4(m.Diffuse.x, m.Diffuse.y, m.Diffuse.z, m.Diffuse.w);
         if (m.DiffuseTextureId >= 0) outAlbedo = outAlbedo * S.sample_texture((uint32_t)m.DiffuseTextureId, inVertex.TexCoord);
         float roughness = m.Fuzziness;
         if (m.MRATextureId >= 0) roughness = roughness * S.sample_texture((uint32_t)m.MRATextureId, inVertex.TexCoord).y;
-        outNormal = F4(inVertex.Normal.x, inVertex.Normal.y, inVertex.Normal.z, roughness);
+        if (m.NormalTextureId >= 0) {  // normal map in the local frame, then to world space through the node matrix
+            f4 t = S.sample_texture((uint32_t)m.NormalTextureId, inVertex.TexCoord);
+            f3 nl = mikkTSpace(F3(t.x, t.y, t.z), inVertex.LocalNormal, inVertex.LocalTangent);
+            f3 nw = normalize(xyz(mul(proxy.worldTS, F4(nl.x, nl.y, nl.z, 0.0f))));
+            outNormal = F4(nw.x, nw.y, nw.z, roughness);
+            inVertex.Normal = nw;
+        } else {
+            outNormal = F4(inVertex.Normal.x, inVertex.Normal.y, inVertex.Normal.z, roughness);
+        }
     }
 
     void Init(int x, int y, uint32_t frameSeed) {  // Shading.slang:1226-1241
@@ -1267,7 +1281,7 @@ struct Renderer {  // FPathTracingRendererV2, Shading.slang:995-1261, configured
         f4 gbuffer = F4(0, 0, 0, 0);
         if (write_gbuffer) {
             f2 motion = CalculateMotionVectorV2(hitPrimaryNode_, hitPrimaryVertex_);
-            FetchGBufferV2(hitPrimaryVertex_, material, primaryAlbedo_, gbuffer);
+            FetchGBufferV2(hitPrimaryVertex_, material, hitPrimaryNode_, primaryAlbedo_, gbuffer);
             size_t o = (size_t)py * F.w + px;
             F.store4(F.albedo, px, py, primaryAlbedo_);
             F.store4(F.normal, px, py, gbuffer);
@@ -1277,7 +1291,7 @@ struct Renderer {  // FPathTracingRendererV2, Shading.slang:995-1261, configured
             F.motion[o * 2 + 1] = motion.y * (float)F.h;
             F.prev_depth[o] = ndcDepth;
         } else {
-            FetchGBufferV2(hitPrimaryVertex_, material, primaryAlbedo_, gbuffer);
+            FetchGBufferV2(hitPrimaryVertex_, material, hitPrimaryNode_, primaryAlbedo_, gbuffer);
         }
         if (material.MaterialModel != GK_MATERIAL_DIELECTRIC) hitPrimaryVertex_.Position = hitPrimaryVertex_.Position - primaryRayDir_ * 0.03f;
         return true;

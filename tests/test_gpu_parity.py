@@ -175,6 +175,45 @@ def test_depth_of_field_and_fast_gather_with_probes(renderer):
     assert sd[..., :3].max() > 0
 
 
+def test_material_textures_albedo_roughness_and_normal_maps(renderer):
+    """FetchGBufferV2 with all three texture slots bound (Shading.slang:82-112, mikkTSpace :74-80): albedo x texture, roughness x MRA.g,
+    tangent-space normal map taken through the local frame and the node matrix. The Cornell box quads carry uv and tangents;
+    the textures are small random images (ids 1-3 of the bindless array), so every texel boundary and wrap is exercised."""
+    W, H = 320, 180
+    scene = host.Scene("CornellBox.proc", samples=2, bounces=4, taa=False)
+    scene.update_nodes()
+    osc, ofr = setup_pair(renderer, scene, W, H)
+    rng = np.random.default_rng(11)
+    albedo_tex = rng.uniform(0.2, 1.0, (16, 16, 4)).astype(np.float32)
+    mra_tex = rng.uniform(0.0, 1.0, (8, 32, 4)).astype(np.float32)
+    nrm = rng.normal(size=(32, 32, 3)) * 0.35 + np.array([0, 0, 1.0])
+    nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+    nrm_tex = np.concatenate([nrm * 0.5 + 0.5, np.ones((32, 32, 1))], axis=2).astype(np.float32)
+    for idx, tex in ((1, albedo_tex), (2, mra_tex), (3, nrm_tex)):
+        renderer.set_sky(idx, tex)
+        osc.set_sky(idx, tex)
+    mats, nm = scene.materials()
+    for i in range(nm):
+        if mats[i].MaterialModel != 4:  # everything but the light
+            mats[i].DiffuseTextureId, mats[i].MRATextureId, mats[i].NormalTextureId = 1, 2, 3
+            mats[i].Fuzziness = 0.8
+            mats[i].Metalness = 0.5 if i % 2 else 0.0
+    renderer.update_materials(scene)
+    osc.L.gko_update_materials(osc._h, mats, nm)
+    ubo = scene.ubo(W, H, 5)
+    flat = renderer.readback(RT["NORMAL"]).copy()
+    renderer.Render(ubo, params())
+    renderer.BeforeNextFrame()
+    ofr.render(osc, ubo, params())
+    check_frame(renderer, ofr, exact_fraction=1e-4, radiance_fraction=1e-3)
+    n = renderer.readback(RT["NORMAL"]).astype(np.float32)
+    a = renderer.readback(RT["ALBEDO"]).astype(np.float32)
+    # the maps did something: normals are perturbed (not axis aligned any more) and stay unit length, roughness and albedo vary
+    back_wall = n[H // 2 - 20:H // 2 + 20, W // 2 - 20:W // 2 + 20]
+    assert np.abs(back_wall[..., :2]).max() > 0.05 and np.allclose(np.linalg.norm(back_wall[..., :3], axis=2), 1.0, atol=2e-3)
+    assert back_wall[..., 3].std() > 0.02 and a[H // 2 - 20:H // 2 + 20, W // 2 - 20:W // 2 + 20, 0].std() > 0.02
+
+
 def _probe_setup(renderer, scene_name, sky=None, sun=False):
     scene = host.Scene(scene_name, samples=2, bounces=4, taa=False)
     if sky is not None:
