@@ -887,6 +887,8 @@ int path_resize(Context& c) {
               b.slot_pixel[0].reserve(m * 4) && b.slot_pixel[1].reserve(m * 4) && b.hit_tuv.reserve(m * 16) && b.hit_prim.reserve(m * 4) &&
               b.counts.reserve(4 * 64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16);
     if (!ok) return 1;
+    // ranks other than 0 never write the direct-term plane; keep it defined for a host that resolves on such a context
+    GK_CUDA(cudaMemsetAsync(b.direct.p, 0, n * 16, c.stream));
     if (!b.host_counts) GK_CUDA(cudaMallocHost(&b.host_counts, 4 * 64 * 4));
     return 0;
 }

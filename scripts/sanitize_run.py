@@ -1,0 +1,42 @@
+"""Small end-to-end exercise of every kernel family for compute-sanitizer:
+   compute-sanitizer --tool memcheck|racecheck|initcheck|synccheck python scripts/sanitize_run.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from gknextengine_b200 import CudaPathTracingRenderer, GkcuFrameParams, host
+from helpers import random_rays
+
+for (W, H) in ((96, 56), (101, 57)):          # TMA stencils / plain-load stencils
+    for name, sky_on in (("CornellBox.proc", False), ("RTIO.proc", True)):
+        scene = host.Scene(name, samples=2, bounces=4, taa=True, denoiser=True)
+        if sky_on: scene.env(has_sky=True, has_sun=True)
+        scene.update_nodes()
+        sky = host.make_sky(64, 32) if sky_on else None
+        r = CudaPathTracingRenderer(0)
+        r.CreateSwapChain((W, H))
+        r.OnPostLoadScene(scene, sky)
+        r.set_lights(scene)
+        if sky_on: r.set_sky_sh(0, host.project_sh(sky))
+        p = GkcuFrameParams(temporal_frames=16, spp_world=1)
+        for f in range(1, 4):
+            r.PreRender()
+            r.Render(scene.ubo(W, H, f), p)
+            r.BeforeNextFrame()
+        r.Render(scene.ubo(W, H, 4), GkcuFrameParams(temporal_frames=16, spp_world=1, tracer=1))   # megakernel
+        r.Render(scene.ubo(W, H, 5), GkcuFrameParams(temporal_frames=16, spp_world=2, spp_rank=0, skip_post=1))
+        r.Resolve(scene.ubo(W, H, 5), GkcuFrameParams(temporal_frames=16, spp_world=2, spp_rank=0))
+        r.BeforeNextFrame()
+        r.trace(random_rays(2000, seed=3))
+        r.trace(random_rays(2000, seed=4), any_hit=True)
+        if name.startswith("Cornell") and W == 96:
+            r.probes_voxelize()
+            _, v, _ = r.probes_read()
+            act = np.nonzero((v["distanceToSolid_gg_z01"] & 0xFF) < 8)[0]
+            r.probes_bake(scene.ubo(W, H, 1), int(act.min()), 4096)
+            r.probes_bake(scene.ubo(W, H, 1), int(act.min()), 4096)
+            r.refit_model(0, scene.perturb_model(0, 1))
+            r.PreRender(); r.Render(scene.ubo(W, H, 6), p); r.BeforeNextFrame()
+        print(name, W, H, r.counters())
+        r.close()
+print("sanitize run finished")
