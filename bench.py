@@ -138,7 +138,8 @@ def workload_config(n):
                         f"({SPP * n} spp/frame), {BOUNCES} bounces, procedural sky stand-in, steady state, temporal reproject + bilateral denoise",
             "scene": SCENE, "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_per_frame": SPP * n, "bounces": BOUNCES,
             "parallelism": f"spp-split x{n}, scene replica per GPU" if n > 1 else "single GPU",
-            "l2": "working set (path state 160 B/px + storage images 122 B/px = 585 MB) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "working set (queue slots + hit records + per-pixel path state ~240 B/px, storage images 122 B/px: ~750 MB at 1080p) exceeds the 126 MB L2; "
+                  "no explicit flush"}
 
 
 def main():
@@ -149,6 +150,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--tracer", type=int, default=0, help="0 wavefront (default), 1 megakernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--present", default="async", choices=["async", "blocking"],
+                    help="e2e leg: async = double-buffered gkcu_readback_denoised_async overlapping the next frame; blocking = gkcu_readback")
     ap.add_argument("--reduce", default="peer", choices=["peer", "peer-hostbarrier", "nccl"],
                     help="multi-GPU: peer = fused reduce + resolve kernel over NVLink peer memory with device-side barriers (default); "
                          "peer-hostbarrier = same kernel bracketed by two 4-byte NCCL all-reduces; nccl = ncclReduce to rank 0, resolve there")
@@ -308,11 +311,11 @@ def main():
     nodes_ptr, nn = scene.nodes()
     node_bytes = nn * C.sizeof(GkNodeProxy)
     pinned_nodes = torch.empty(node_bytes, dtype=torch.uint8, pin_memory=True)
-    pinned_out = torch.empty(WIDTH * HEIGHT * 8, dtype=torch.uint8, pin_memory=True)
+    pinned_out = [torch.empty(WIDTH * HEIGHT * 8, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     e2e_rays = 0
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _step in range(args.steps):
         scene.update_nodes()  # Scene::UpdateNodes on the host (Scene.cpp:410-492)
         nodes_ptr, nn = scene.nodes()
         C.memmove(pinned_nodes.data_ptr(), nodes_ptr, node_bytes)
@@ -320,9 +323,18 @@ def main():
         frame(tf)  # H2D UBO inside
         tf += 1
         if rank == 0:
-            r.readback_into(RT["DENOISED"], pinned_out.data_ptr(), pinned_out.numel())  # D2H result
+            # D2H of the frame's RT_DENOISED every step, double-buffered: the copy runs on the renderer's copy stream and overlaps
+            # the next frame's rt pass; the copy of the previous step is complete before its buffer is reused
+            out_buf = pinned_out[_step & 1]
+            if args.present == "async":
+                r.present_wait()
+                r.present_async(out_buf.data_ptr(), out_buf.numel())
+            else:
+                r.readback_into(RT["DENOISED"], out_buf.data_ptr(), out_buf.numel())
         c = r.counters()
         e2e_rays += c["primary_rays"] + c["closest_hit_rays"] + c["any_hit_rays"]
+    if rank == 0:
+        r.present_wait()
     sync_all()
     e2e_s = time.perf_counter() - t0
     est = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device=f"cuda:{local_rank}")

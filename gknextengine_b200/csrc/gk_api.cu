@@ -158,6 +158,7 @@ int gkcu_destroy(GkcuContext* ctx) {
             if (e) cudaEventDestroy(e);
     for (auto& st : c.lane_stream)
         if (st) cudaStreamDestroy(st);
+    if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); cudaEventDestroy(c.copy_ready); cudaEventDestroy(c.copy_done); }
     cudaStreamDestroy(c.stream);
     delete ctx;
     return 0;
@@ -167,6 +168,8 @@ int gkcu_resize(GkcuContext* ctx, uint32_t width, uint32_t height) {
     CTX_OR_FAIL(ctx);
     if (width == 0 || height == 0 || (uint64_t)width * height >= (1ull << 31)) { set_error("gkcu_resize: bad extent"); return 1; }
     GK_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.copy_stream) GK_CUDA(cudaStreamSynchronize(c.copy_stream));
+    c.copy_pending = false;
     drop_peers(c);
     RenderTargets& t = c.rt;
     free_targets(t);
@@ -528,6 +531,31 @@ int gkcu_readback(GkcuContext* ctx, uint32_t rt_index, void* dst, size_t dst_byt
     if (!dst || dst_bytes < bytes) { set_error("gkcu_readback: destination too small"); return 1; }
     GK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
     GK_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int gkcu_readback_denoised_async(GkcuContext* ctx, void* dst, size_t dst_bytes) {
+    CTX_OR_FAIL(ctx);
+    RenderTargets& t = c.rt;
+    const size_t bytes = (size_t)t.w * t.h * 8;
+    if (t.w == 0) { set_error("gkcu_readback_denoised_async: no images"); return 1; }
+    if (!dst || dst_bytes < bytes) { set_error("gkcu_readback_denoised_async: destination too small"); return 1; }
+    if (!c.copy_stream) {
+        GK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        GK_CUDA(cudaEventCreateWithFlags(&c.copy_ready, cudaEventDisableTiming));
+        GK_CUDA(cudaEventCreateWithFlags(&c.copy_done, cudaEventDisableTiming));
+    }
+    GK_CUDA(cudaEventRecord(c.copy_ready, c.stream));           // the frame that produced the image
+    GK_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_ready, 0));
+    GK_CUDA(cudaMemcpyAsync(dst, t.denoised, bytes, cudaMemcpyDeviceToHost, c.copy_stream));
+    GK_CUDA(cudaEventRecord(c.copy_done, c.copy_stream));       // run_denoise waits for this before it overwrites the image
+    c.copy_pending = true;
+    return 0;
+}
+
+int gkcu_readback_wait(GkcuContext* ctx) {
+    CTX_OR_FAIL(ctx);
+    if (c.copy_stream) GK_CUDA(cudaStreamSynchronize(c.copy_stream));
     return 0;
 }
 

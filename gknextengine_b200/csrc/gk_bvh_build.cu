@@ -1116,7 +1116,7 @@ int build_tlas(Context& c) {
     c.launches += 1;
     Bvh2 b2;
     const char* tb = getenv("GKCU_TLAS_BUILDER");
-    static const uint32_t fused_max = getenv("GKCU_TLAS_FUSED_MAX") ? (uint32_t)atoi(getenv("GKCU_TLAS_FUSED_MAX")) : 8192u;
+    const uint32_t fused_max = getenv("GKCU_TLAS_FUSED_MAX") ? (uint32_t)atoi(getenv("GKCU_TLAS_FUSED_MAX")) : 8192u;
     if (tb && std::string(tb) == "lbvh") {
         if (build_lbvh(c, m, m, b2)) return 1;
         if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;

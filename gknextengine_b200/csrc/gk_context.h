@@ -120,6 +120,9 @@ struct Context {
     cudaEvent_t ev[8] = {};
     uint64_t launches = 0;
     DevBuf trace_rays, trace_hits;
+    cudaStream_t copy_stream = nullptr;  // gkcu_readback_denoised_async
+    cudaEvent_t copy_ready = nullptr, copy_done = nullptr;
+    bool copy_pending = false;
 
     // multi-GPU peer resolve: peer[rank][what] device pointers (local, same-process, or opened from an IPC handle)
     void* peer[GKCU_MAX_PEERS][5] = {};

@@ -477,6 +477,10 @@ int run_reproject(Context& c, const GkcuFrameParams& p) {
 }
 
 int run_denoise(Context& c, const GkUniformBufferObject& ubo) {
+    if (c.copy_pending) {  // an asynchronous present of the previous frame still reads RT_DENOISED
+        cudaStreamWaitEvent(c.stream, c.copy_done, 0);
+        c.copy_pending = false;
+    }
     RenderTargets& t = c.rt;
     DenoiseArgs A;
     A.w = (int)t.w; A.h = (int)t.h;

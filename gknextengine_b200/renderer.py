@@ -60,6 +60,8 @@ def lib():
         L.gkcu_radiance_buffer.argtypes = [P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.gkcu_render_resolve.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
         L.gkcu_readback.argtypes = [P, C.c_uint32, C.c_void_p, C.c_size_t]
+        L.gkcu_readback_denoised_async.argtypes = [P, C.c_void_p, C.c_size_t]
+        L.gkcu_readback_wait.argtypes = [P]
         L.gkcu_upload_image.argtypes = [P, C.c_uint32, C.c_void_p, C.c_size_t]
         L.gkcu_run_post.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
         L.gkcu_debug_read.argtypes = [P, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -254,6 +256,13 @@ class CudaPathTracingRenderer:
     def readback_into(self, rt, ptr, nbytes):
         """Blocking device->host copy into caller-owned (e.g. pinned) host memory."""
         _ck(lib().gkcu_readback(self._ctx, rt, ptr, nbytes))
+
+    def present_async(self, ptr, nbytes):
+        """Copy of RT_DENOISED into (pinned) host memory behind the last frame, overlapping the next frame (gkcu_readback_denoised_async)."""
+        _ck(lib().gkcu_readback_denoised_async(self._ctx, ptr, nbytes))
+
+    def present_wait(self):
+        _ck(lib().gkcu_readback_wait(self._ctx))
 
     def update_nodes_ptr(self, ptr, count):
         _ck(lib().gkcu_update_nodes(self._ctx, C.cast(ptr, C.POINTER(GkNodeProxy)), count))

@@ -393,6 +393,11 @@ int gkcu_render_resolve_strip(GkcuContext* ctx, const GkUniformBufferObject* ubo
 /* Blocking device->host copy of one storage image in its reference format
  * (fp16x4 / R32_UINT / RG32F / R32F / R16_UINT, VulkanBaseRenderer.cpp:439-457). */
 int gkcu_readback(GkcuContext* ctx, uint32_t rt_index, void* dst, size_t dst_bytes);
+/* Presenting without stalling the renderer: enqueues the device->host copy of RT_DENOISED behind the frame submitted last and
+ * returns at once. The copy runs on its own stream, so it overlaps the next frame's rt pass; the next compose pass waits for
+ * it before it overwrites the image. dst must stay valid (and should be pinned) until gkcu_readback_wait has returned. */
+int gkcu_readback_denoised_async(GkcuContext* ctx, void* dst, size_t dst_bytes);
+int gkcu_readback_wait(GkcuContext* ctx);
 /* Stencil-pass bring-up hooks used by the parity tests: overwrite one storage image from host memory (formats as in
  * gkcu_readback; PREV_* and OBJECTID_1 address the history slots), and run only reproject -> compose -> copy pass. */
 int gkcu_upload_image(GkcuContext* ctx, uint32_t rt_index, const void* src, size_t src_bytes);

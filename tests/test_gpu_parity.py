@@ -69,6 +69,38 @@ def test_rtiow_sky_multi_bounce(monkeypatch, sky, builder):
         r.close()
 
 
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_multi_lane_wavefront_is_bit_identical(monkeypatch, sky, lanes):
+    """GKCU_LANES deals the frame's tiles to independent wavefronts on their own streams (and GKCU_TLAS_FUSED_MAX=0 takes the
+    multi-launch TLAS builder): scheduling knobs only, every image and ray count must equal the single-lane frame bit for bit."""
+    W, H = 333, 187  # not a multiple of the 8 x 16 tiles
+    scene = host.Scene("RTIO.proc", samples=3, bounces=6, taa=True, denoiser=True)
+    scene.env(has_sky=True, has_sun=True)
+    scene.update_nodes()
+    frames = {}
+    for n in (1, lanes):
+        monkeypatch.setenv("GKCU_LANES", str(n))
+        monkeypatch.setenv("GKCU_TLAS_FUSED_MAX", "8192" if n == 1 else "0")
+        r = CudaPathTracingRenderer(0)
+        try:
+            r.CreateSwapChain((W, H))
+            r.OnPostLoadScene(scene, sky)
+            for f in (1, 2):
+                r.PreRender()
+                r.Render(scene.ubo(W, H, f), params())
+                r.BeforeNextFrame()
+            frames[n] = ({name: r.readback(RT[name]).copy() for name in ("OBJEDCTID_0", "SINGLE_DIFFUSE", "SINGLE_SPECULAR", "ACCUMLATE_DIFFUSE", "DENOISED")},
+                         r.counters())
+        finally:
+            r.close()
+    a, b = frames[1], frames[lanes]
+    for name in a[0]:
+        assert (a[0][name].view(np.uint16 if a[0][name].dtype == np.float16 else a[0][name].dtype) ==
+                b[0][name].view(np.uint16 if b[0][name].dtype == np.float16 else b[0][name].dtype)).all(), name
+    for k in ("primary_rays", "closest_hit_rays", "any_hit_rays"):
+        assert a[1][k] == b[1][k] and a[1][k] > 0
+
+
 def test_sun_shadow_rays_and_wavefront_equals_megakernel(sky):
     """Sun on: the bounce-loop NEE ray and DirectIlluminate's shadow ray (Shading.slang:1135-1144, 886-908) are any-hit
     queries. The wavefront and megakernel drivers must agree bit for bit."""
@@ -576,6 +608,40 @@ def test_full_size_properties_1080p(sky):
         g, c = out[0][0][y0:y0 + 4], ofr.image(RT["SINGLE_DIFFUSE"])[y0:y0 + 4]
         assert mismatch_fraction(g, c) <= 5e-3
         assert np.array_equal(out[0][3][y0:y0 + 4], ofr.image(RT["OBJEDCTID_0"])[y0:y0 + 4])
+
+
+def test_async_present_overlaps_the_next_frame_without_tearing(sky):
+    """gkcu_readback_denoised_async: the copy of frame A is enqueued, frame B is submitted at once; what arrives is frame A
+    (the compose pass of B waits for the copy), and B itself is unaffected."""
+    import torch
+    W, H = 640, 360
+    scene = host.Scene("RTIO.proc", samples=2, bounces=4, taa=True, denoiser=True)
+    scene.update_nodes()
+    ref = []
+    for mode in ("blocking", "async"):
+        r = CudaPathTracingRenderer(0)
+        try:
+            r.CreateSwapChain((W, H))
+            r.OnPostLoadScene(scene, sky)
+            if mode == "blocking":
+                for f in (1, 2):
+                    r.Render(scene.ubo(W, H, f), params())
+                    r.BeforeNextFrame()
+                    ref.append(r.readback(RT["DENOISED"]).copy())
+            else:
+                buf = torch.empty(W * H * 8, dtype=torch.uint8, pin_memory=True)
+                r.Render(scene.ubo(W, H, 1), params())
+                r.present_async(buf.data_ptr(), buf.numel())
+                r.Render(scene.ubo(W, H, 2), params())   # submitted while the copy may still be in flight
+                r.present_wait()
+                got = buf.numpy().view(np.float16).reshape(H, W, 4)
+                assert (got.view(np.uint16) == ref[0].view(np.uint16)).all()
+                r.BeforeNextFrame()
+                assert (r.readback(RT["DENOISED"]).view(np.uint16) == ref[1].view(np.uint16)).all()
+                with pytest.raises(GkcuError):
+                    r.present_async(buf.data_ptr(), 16)
+        finally:
+            r.close()
 
 
 def test_error_handling(renderer):
