@@ -39,3 +39,5 @@ tj = {k: sum(v) / len(v) for k, v in traffic.items()}
 tj["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches (ncu --set full; k_trace/k_shade: waves 10-11 of a frame)"
 json.dump(tj, open(f"{P}/traffic.json", "w"), indent=1)
 print(open(f"{P}/{tag}_launches_summary.txt").read()); print(json.dumps(tj, indent=1))
+
+subprocess.run([sys.executable, f"{ROOT}/scripts/ncu_table.py", tag])
