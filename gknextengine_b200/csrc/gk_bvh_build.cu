@@ -532,8 +532,18 @@ __device__ __forceinline__ void sah_partition_item(int i, int n, const uint32_t*
     }
     int dst;
     if (sp.fallback) dst = i;
-    else if (goLeft) dst = f + atomicAdd(&cursors[2 * slot], 1);
-    else dst = f + sp.nl + atomicAdd(&cursors[2 * slot + 1], 1);
+    else {
+        // warp-aggregated cursor bump: lanes going to the same side of the same node take one atomic together (near the root
+        // every box of the build would otherwise hit the same two counters)
+        const int key = 2 * slot + (goLeft ? 0 : 1);
+        const unsigned act = __activemask();
+        const unsigned peers = __match_any_sync(act, key);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cursors[key], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        dst = f + (goLeft ? 0 : sp.nl) + base + __popc(peers & ((1u << lane) - 1u));
+    }
     order_out[dst] = p;
     pos_node_out[dst] = left[node] + (goLeft ? 0 : 1);
 }
@@ -571,6 +581,7 @@ __global__ void k_collapse_next(int* counters, int level) {
 // The whole SAH build + wide collapse of a small input (the per-frame TLAS of a few thousand instances) in ONE block: the
 // level-synchronous phases above run back to back with __syncthreads() between them instead of ~130 tiny launches and three
 // host round trips (0.93 ms -> see profiles/r01_experiments.md for 1.9 k instances). Same per-item code, same tree.
+constexpr int kFusedSmemSlots = 24;  // open nodes whose bins fit the block-private copy (24 x 48 bins x 32 B = 36 KB)
 struct FusedBuild {
     int n, leaf_max, max_slots;
     const float4 *plo, *phi;
@@ -590,6 +601,7 @@ template <bool GRID>
 __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B) {
     // GRID: a cooperative launch of a few blocks, phases separated by grid-wide barriers; otherwise one block and __syncthreads()
     const int T = blockDim.x * gridDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ SahBin s_bins[kFusedSmemSlots * 3 * kSahBins];
     auto sync = [&]() {
         if (GRID) cooperative_groups::this_grid().sync();
         else __syncthreads();
@@ -649,7 +661,32 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B)
             B.bins[i] = b;
         }
         sync();
-        for (int i = t; i < n; i += T) sah_bin_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, B.bins);
+        if (nactive <= kFusedSmemSlots) {
+            // few open nodes, every box hits the same handful of bins: bin into a block-private copy in shared memory first and
+            // merge once per block (the top levels of a 100 k build otherwise serialise ~2 M same-address atomics each)
+            for (int i = threadIdx.x; i < nactive * 3 * kSahBins; i += blockDim.x) {
+                SahBin b;
+                b.lo[0] = b.lo[1] = b.lo[2] = 0x7FFFFFFF;
+                b.hi[0] = b.hi[1] = b.hi[2] = (int)0x80000000;
+                b.cnt = 0;
+                b.pad = 0;
+                s_bins[i] = b;
+            }
+            __syncthreads();
+            for (int i = t; i < n; i += T) sah_bin_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, s_bins);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nactive * 3 * kSahBins; i += blockDim.x) {
+                const SahBin b = s_bins[i];
+                if (b.cnt) {
+                    SahBin* g = B.bins + i;
+                    atomicMin(&g->lo[0], b.lo[0]); atomicMin(&g->lo[1], b.lo[1]); atomicMin(&g->lo[2], b.lo[2]);
+                    atomicMax(&g->hi[0], b.hi[0]); atomicMax(&g->hi[1], b.hi[1]); atomicMax(&g->hi[2], b.hi[2]);
+                    atomicAdd(&g->cnt, b.cnt);
+                }
+            }
+        } else {
+            for (int i = t; i < n; i += T) sah_bin_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, B.bins);
+        }
         sync();
         for (int sl = t; sl < nactive; sl += T)
             sah_split_item(sl, B.leaf_max, counters + 1, act_a, B.bins, B.nlo, B.nhi, B.left, B.right, B.first, B.count, counters, act_b, B.splits, B.cursors);
@@ -952,8 +989,8 @@ int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Nod
     B.bins = s.bins.as<SahBin>();
     B.qa = s.queue_a.as<int2>(); B.qb = s.queue_b.as<int2>();
     B.remap = remap; B.out = out; B.out_lo = out_lo; B.out_hi = out_hi;
-    // one item per thread up to 64 blocks; a single block for tiny inputs (no cooperative launch needed)
-    const int blocks = (int)std::min<size_t>(64, ((size_t)n + 255) / 256);
+    // one item per thread up to two blocks per SM (all co-resident: 64 registers x 256 threads); a single block for tiny inputs
+    const int blocks = (int)std::min<size_t>((size_t)c.sm_count * 2, ((size_t)n + 255) / 256);
     if (blocks <= 1) {
         k_build_fused<false><<<1, n <= 256 ? 256 : 1024, 0, st>>>(B);
     } else {
@@ -1116,7 +1153,7 @@ int build_tlas(Context& c) {
     c.launches += 1;
     Bvh2 b2;
     const char* tb = getenv("GKCU_TLAS_BUILDER");
-    const uint32_t fused_max = getenv("GKCU_TLAS_FUSED_MAX") ? (uint32_t)atoi(getenv("GKCU_TLAS_FUSED_MAX")) : 8192u;
+    const uint32_t fused_max = getenv("GKCU_TLAS_FUSED_MAX") ? (uint32_t)atoi(getenv("GKCU_TLAS_FUSED_MAX")) : 262144u;
     if (tb && std::string(tb) == "lbvh") {
         if (build_lbvh(c, m, m, b2)) return 1;
         if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;

@@ -178,7 +178,10 @@ def config5_single():
 
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    only = [a for a in sys.argv[1:] if a.startswith("config")]
     for fn in (config1, config3, config4, config5_single):
+        if only and fn.__name__ not in only:
+            continue
         t0 = time.time()
         fn()
         print(fn.__name__, f"{time.time() - t0:.1f}s", flush=True)
