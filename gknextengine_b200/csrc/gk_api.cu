@@ -138,7 +138,7 @@ int gkcu_destroy(GkcuContext* ctx) {
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
                       &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
-                      &c.inst_hi, &c.tlas_active_ids, &c.tex_table, &c.cubes, &c.voxels, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
+                      &c.inst_hi, &c.tlas_active_ids, &c.inst_flags, &c.select_tmp, &c.select_count, &c.node_stage, &c.node_stage_idx, &c.tex_table, &c.cubes, &c.voxels, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
                       &c.peer_flags};
     for (DevBuf* b : bufs) b->release();
     BuildScratch& s = c.scratch;
@@ -246,25 +246,25 @@ int gkcu_update_nodes(GkcuContext* ctx, const GkNodeProxy* nodes, uint32_t count
     if (!c.nodes.reserve(std::max<size_t>(1, count) * sizeof(GkNodeProxy))) return 1;
     if (count) GK_CUDA(cudaMemcpyAsync(c.nodes.p, nodes, (size_t)count * sizeof(GkNodeProxy), cudaMemcpyHostToDevice, c.stream));
     c.node_count = count;
-    // instances that make it into the TLAS (mask != 0, RayTraceBaseRenderer.cpp:178)
-    std::vector<uint32_t> ids;
-    ids.reserve(count);
-    for (uint32_t i = 0; i < count; ++i) {
-        uint32_t blas = nodes[i].modelId / 10;
-        bool a = nodes[i].visible && !nodes[i].nort && blas < c.model_count;
-        if (a) {
-            uint64_t idx = 0;
-            for (int s = 0; s < 10; ++s) idx += c.host_offsets[blas * 10 + s].indexCount;
-            if (idx / 3 == 0) a = false;
-        }
-        if (a) ids.push_back(i);
-    }
-    const uint32_t active = (uint32_t)ids.size();
-    if (!c.tlas_active_ids.reserve(std::max<size_t>(1, ids.size()) * 4)) return 1;
-    if (active) GK_CUDA(cudaMemcpyAsync(c.tlas_active_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c.stream));
-    c.tlas.prim_count = active;
+    // which instances make it into the TLAS (mask != 0, RayTraceBaseRenderer.cpp:178) is decided on the device by build_tlas
     c.tlas_dirty = true;
     GK_CUDA(cudaStreamSynchronize(c.stream));  // the caller may reuse its array
+    return 0;
+}
+
+int gkcu_update_nodes_sparse(GkcuContext* ctx, const uint32_t* indices, const GkNodeProxy* proxies, uint32_t count) {
+    CTX_OR_FAIL(ctx);
+    if (count == 0) return 0;
+    if (!indices || !proxies) { set_error("gkcu_update_nodes_sparse: null array"); return 1; }
+    if (c.node_count == 0) { set_error("gkcu_update_nodes_sparse: call gkcu_update_nodes first"); return 1; }
+    for (uint32_t k = 0; k < count; ++k)
+        if (indices[k] >= c.node_count) { set_error("gkcu_update_nodes_sparse: index beyond the node count"); return 1; }
+    if (!c.node_stage.reserve((size_t)count * sizeof(GkNodeProxy)) || !c.node_stage_idx.reserve((size_t)count * 4)) return 1;
+    GK_CUDA(cudaMemcpyAsync(c.node_stage.p, proxies, (size_t)count * sizeof(GkNodeProxy), cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaMemcpyAsync(c.node_stage_idx.p, indices, (size_t)count * 4, cudaMemcpyHostToDevice, c.stream));
+    if (scatter_nodes(c, count)) return 1;
+    c.tlas_dirty = true;
+    GK_CUDA(cudaStreamSynchronize(c.stream));  // the caller may reuse its arrays
     return 0;
 }
 
@@ -632,7 +632,7 @@ int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out) {
 }
 
 // Debug/validation hook (tests/test_gpu_bvh.py): raw device->host copies of the acceleration-structure pools.
-// what: 0 TLAS nodes, 1 BLAS nodes, 2 BLAS triangles, 3 instances, 4/5 TLAS node boxes lo/hi, 6 BLAS table.
+// what: 0 TLAS nodes, 1 BLAS nodes, 2 BLAS triangles, 3 instances, 4/5 TLAS node boxes lo/hi, 6 BLAS table, 7 NodeProxy array.
 int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, size_t bytes) {
     CTX_OR_FAIL(ctx);
     const DevBuf* b = nullptr;
@@ -644,6 +644,7 @@ int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, s
         case 4: b = &c.tlas_node_lo; break;
         case 5: b = &c.tlas_node_hi; break;
         case 6: b = &c.blas_table; break;
+        case 7: b = &c.nodes; break;
         default: set_error("gkcu_debug_read: bad selector"); return 1;
     }
     if (!b->p || offset + bytes > b->cap) { set_error("gkcu_debug_read: out of range"); return 1; }

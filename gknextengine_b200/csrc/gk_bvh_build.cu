@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <cooperative_groups.h>
 
@@ -729,7 +731,8 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B)
 // VkAccelerationStructureInstanceKHR equivalent (TopLevelAccelerationStructure.cpp:83-111): instance i <-> Nodes[i],
 // BLAS = modelId / 10, mask = visible && !nort (RayTraceBaseRenderer.cpp:172-179). Also the world box for the TLAS.
 __global__ void k_instances(const GkNodeProxy* __restrict__ nodes, uint32_t n, const uint4* __restrict__ blas_table, uint32_t model_count,
-                            InstanceRec* __restrict__ inst, float4* __restrict__ lo, float4* __restrict__ hi, uint4* __restrict__ shade_inst) {
+                            InstanceRec* __restrict__ inst, float4* __restrict__ lo, float4* __restrict__ hi, uint4* __restrict__ shade_inst,
+                            uint8_t* __restrict__ flags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const GkNodeProxy& nd = nodes[i];
@@ -774,6 +777,7 @@ __global__ void k_instances(const GkNodeProxy* __restrict__ nodes, uint32_t n, c
     // shading record: where the instance's primitives start in the shade-triangle pool + the node's first material ids
     shade_inst[(size_t)i * 2] = make_uint4(bt.w, nd.matId[0], nd.matId[1], nd.matId[2]);
     shade_inst[(size_t)i * 2 + 1] = make_uint4(nd.matId[3], nd.matId[4], nd.matId[5], nd.matId[6]);
+    flags[i] = active ? 1 : 0;
     if (active) {
         float4 bl = reinterpret_cast<const float4*>(blas_table)[blas * 3 + 1], bh = reinterpret_cast<const float4*>(blas_table)[blas * 3 + 2];
         float3 mn = f3(FLT_MAX, FLT_MAX, FLT_MAX), mx = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX), mag = f3(0, 0, 0);
@@ -1021,6 +1025,24 @@ int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Nod
 
 }  // namespace
 
+namespace {
+// gkcu_update_nodes_sparse: 13 lanes move the 13 x 16 bytes of one NodeProxy
+__global__ void k_scatter_nodes(const uint4* __restrict__ stage, const uint32_t* __restrict__ idx, uint32_t count, uint4* __restrict__ nodes) {
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) / 16, part = threadIdx.x & 15;
+    if (k >= count || part >= sizeof(GkNodeProxy) / 16) return;
+    nodes[(size_t)idx[k] * (sizeof(GkNodeProxy) / 16) + part] = stage[(size_t)k * (sizeof(GkNodeProxy) / 16) + part];
+}
+}  // namespace
+
+int scatter_nodes(Context& c, uint32_t count) {
+    static_assert(sizeof(GkNodeProxy) % 16 == 0, "NodeProxy is moved in 16-byte pieces");
+    k_scatter_nodes<<<(unsigned)(((size_t)count * 16 + 255) / 256), 256, 0, c.stream>>>(c.node_stage.as<uint4>(), c.node_stage_idx.as<uint32_t>(), count,
+                                                                                   c.nodes.as<uint4>());
+    c.launches++;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 gkd::TraceScene make_trace_scene(const Context& c) {
     gkd::TraceScene s;
     s.tlas = c.tlas_nodes.as<Node4>();
@@ -1140,9 +1162,23 @@ int build_tlas(Context& c) {
         !c.tlas_node_hi.reserve(((size_t)n + 4) * 16))
         return 1;
     if (!c.inst_lo.reserve((size_t)n * 16) || !c.inst_hi.reserve((size_t)n * 16) || !c.shade_inst.reserve((size_t)n * 32)) return 1;
+    if (!c.inst_flags.reserve(n) || !c.tlas_active_ids.reserve((size_t)n * 4) || !c.select_count.reserve(16)) return 1;
     k_instances<<<grid_for(n, 128), 128, 0, st>>>(c.nodes.as<GkNodeProxy>(), n, c.blas_table.as<uint4>(), c.model_count, c.instances.as<InstanceRec>(),
-                                             c.inst_lo.as<float4>(), c.inst_hi.as<float4>(), c.shade_inst.as<uint4>());
+                                             c.inst_lo.as<float4>(), c.inst_hi.as<float4>(), c.shade_inst.as<uint4>(), c.inst_flags.as<uint8_t>());
     c.launches += 1;
+    {   // the instances with a non-zero mask, in index order (stable compaction), and how many there are
+        thrust::counting_iterator<uint32_t> iota(0u);
+        size_t tmp = 0;
+        cub::DeviceSelect::Flagged(nullptr, tmp, iota, c.inst_flags.as<uint8_t>(), c.tlas_active_ids.as<uint32_t>(), c.select_count.as<uint32_t>(), (int)n, st);
+        if (!c.select_tmp.reserve(tmp)) return 1;
+        GK_CUDA(cub::DeviceSelect::Flagged(c.select_tmp.p, tmp, iota, c.inst_flags.as<uint8_t>(), c.tlas_active_ids.as<uint32_t>(), c.select_count.as<uint32_t>(),
+                                           (int)n, st));
+        uint32_t m_host = 0;
+        GK_CUDA(cudaMemcpyAsync(&m_host, c.select_count.p, 4, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        c.tlas.prim_count = m_host;
+        c.launches += 1;
+    }
     // only instances with a non-zero mask enter the TLAS (RayTraceBaseRenderer.cpp:178); their indices were listed by
     // gkcu_update_nodes. The TLAS is built with the SAH-binned builder by default: on RTIO.proc it halves the traversal time
     // compared with the Morton LBVH (the floor's 2 km box degrades the Morton order); GKCU_TLAS_BUILDER=lbvh selects the LBVH.

@@ -78,6 +78,8 @@ struct Context {
     DevBuf shade_tris;  // 32 B per primitive (primitive order): 3 normals + 3 uvs as fp16 + material slot, see gk_pathtrace.cu
     DevBuf shade_inst;  // 32 B per instance: shade-triangle base + the first 7 material ids of the node
     DevBuf tlas_nodes, tlas_node_lo, tlas_node_hi, instances, inst_lo, inst_hi, tlas_active_ids;
+    DevBuf inst_flags, select_tmp, select_count;  // device-side compaction of the instances that enter the TLAS
+    DevBuf node_stage, node_stage_idx;            // gkcu_update_nodes_sparse staging
     WideBvhInfo tlas;
     bool tlas_dirty = true;
     bool frame_built_tlas = false;
@@ -137,6 +139,7 @@ gkd::TraceScene make_trace_scene(const Context& c);
 int build_all_blas(Context& c);
 int refit_blas(Context& c, uint32_t model);
 int build_tlas(Context& c);
+int scatter_nodes(Context& c, uint32_t count);
 
 // gk_pathtrace.cu
 int path_resize(Context& c);

@@ -32,6 +32,8 @@ def lib():
         L.gkhost_scene_lights.restype = C.POINTER(GkLightObject)
         L.gkhost_scene_lights.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
         L.gkhost_project_sh.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(GkSphericalHarmonics)]
+        L.gkhost_scene_changed.restype = C.POINTER(C.c_uint32)
+        L.gkhost_scene_changed.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
         L.gkhost_scene_update_nodes.argtypes = [C.c_void_p]
         L.gkhost_scene_settings.argtypes = [C.c_void_p] + [C.c_int] * 8
         L.gkhost_scene_env.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
@@ -95,6 +97,12 @@ class Scene:
         n = C.c_uint32()
         p = lib().gkhost_scene_lights(self._h, C.byref(n))
         return p, n.value
+
+    def changed(self):
+        """(indices pointer, count, all_changed) of the proxies the last update_nodes() modified."""
+        n, a = C.c_uint32(), C.c_int()
+        p = lib().gkhost_scene_changed(self._h, C.byref(n), C.byref(a))
+        return p, n.value, bool(a.value)
 
     def update_nodes(self):
         """Scene::UpdateNodes: recompute NodeProxy[] (velocity tick included)."""

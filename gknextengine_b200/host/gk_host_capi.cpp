@@ -43,6 +43,13 @@ const GkLightObject* gkhost_scene_lights(void* h, uint32_t* count) {
 void gkhost_project_sh(const float* rgba, uint32_t width, uint32_t height, GkSphericalHarmonics* out) {
     *out = gk::ProjectHdrToSh(rgba, (int)width, (int)height);
 }
+// proxies changed by the last gkhost_scene_update_nodes; *all != 0: upload everything
+const uint32_t* gkhost_scene_changed(void* h, uint32_t* count, int* all) {
+    auto* s = static_cast<gk::Scene*>(h);
+    *count = (uint32_t)s->changed_proxies.size();
+    *all = s->all_proxies_changed ? 1 : 0;
+    return s->changed_proxies.data();
+}
 // Scene::UpdateNodes: ticks node velocities (first call after load reports every node as moved, Node.cpp:154-171)
 int gkhost_scene_update_nodes(void* h) { return static_cast<gk::Scene*>(h)->UpdateNodes() ? 1 : 0; }
 

@@ -417,7 +417,9 @@ void Scene::RebuildMeshBuffer() {
 }
 
 bool Scene::UpdateNodes() {  // Scene.cpp:443-492 + Node::GetNodeProxy (Node.cpp:136-152)
-    node_proxies.clear();
+    std::vector<GkNodeProxy> previous;
+    previous.swap(node_proxies);
+    node_proxies.reserve(previous.size());
     for (auto& node : nodes) {
         if (!node.visible) continue;
         mat4 combined;
@@ -435,6 +437,11 @@ bool Scene::UpdateNodes() {  // Scene.cpp:443-492 + Node::GetNodeProxy (Node.cpp
             node_proxies.push_back(p);
         }
     }
+    changed_proxies.clear();
+    all_proxies_changed = previous.size() != node_proxies.size();
+    if (!all_proxies_changed)
+        for (size_t i = 0; i < node_proxies.size(); ++i)
+            if (std::memcmp(&previous[i], &node_proxies[i], sizeof(GkNodeProxy)) != 0) changed_proxies.push_back((uint32_t)i);
     return !node_proxies.empty();
 }
 

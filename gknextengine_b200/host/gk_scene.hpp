@@ -114,6 +114,9 @@ public:
     std::vector<GkModelData> offsets;
     // UpdateNodes output
     std::vector<GkNodeProxy> node_proxies;
+    // proxies that differ from the previous UpdateNodes() (a renderer may upload only these); all_proxies_changed: the array was resized
+    std::vector<uint32_t> changed_proxies;
+    bool all_proxies_changed = true;
 
 private:
     bool has_prev_ubo_ = false;

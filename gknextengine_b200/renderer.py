@@ -44,6 +44,7 @@ def lib():
         L.gkcu_blas_build.argtypes = [P]
         L.gkcu_blas_refit.argtypes = [P, C.c_uint32, C.c_void_p, C.c_uint32]
         L.gkcu_update_nodes.argtypes = [P, C.POINTER(GkNodeProxy), C.c_uint32]
+        L.gkcu_update_nodes_sparse.argtypes = [P, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]
         L.gkcu_update_materials.argtypes = [P, C.POINTER(GkMaterial), C.c_uint32]
         L.gkcu_tlas_build.argtypes = [P]
         L.gkcu_set_sky.argtypes = [P, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
@@ -136,6 +137,19 @@ class CudaPathTracingRenderer:
     def AfterUpdateScene(self, scene):
         nodes, nn = scene.nodes()
         _ck(lib().gkcu_update_nodes(self._ctx, nodes, nn))
+
+    def AfterUpdateSceneSparse(self, scene):
+        """Like AfterUpdateScene, but uploads only the proxies the last Scene.update_nodes() changed (gkcu_update_nodes_sparse)."""
+        idx, n, all_changed = scene.changed()
+        if all_changed:
+            return self.AfterUpdateScene(scene)
+        if n == 0:
+            return
+        nodes, _ = scene.nodes()
+        ids = np.ctypeslib.as_array(idx, shape=(n,)).copy()
+        all_nodes = np.ctypeslib.as_array(C.cast(nodes, C.POINTER(C.c_uint8)), shape=(int(ids.max()) + 1, C.sizeof(GkNodeProxy)))
+        packed = np.ascontiguousarray(all_nodes[ids])
+        _ck(lib().gkcu_update_nodes_sparse(self._ctx, ids.ctypes.data_as(C.POINTER(C.c_uint32)), packed.ctypes.data, n))
 
     def PreRender(self):
         _ck(lib().gkcu_tlas_build(self._ctx))

@@ -322,6 +322,10 @@ int gkcu_blas_refit(GkcuContext* ctx, uint32_t model_index, const uint16_t* simp
 int gkcu_update_nodes(GkcuContext* ctx, const GkNodeProxy* nodes, uint32_t count);
 
 /* Replaces Scene::UpdateAllMaterials (src/Assets/Scene.cpp:393-408). */
+/* Sparse variant for scenes where few nodes change per frame (the reference re-uploads the whole array every frame, Scene.cpp:443-492):
+ * proxies[k] replaces node indices[k]; the node count stays what the last gkcu_update_nodes set. 208 B per changed node cross the
+ * bus instead of 208 B per node; a kernel scatters them. */
+int gkcu_update_nodes_sparse(GkcuContext* ctx, const uint32_t* indices, const GkNodeProxy* proxies, uint32_t count);
 int gkcu_update_materials(GkcuContext* ctx, const GkMaterial* materials, uint32_t count);
 
 /* Replaces RayTraceBaseRenderer::PreRender "TLAS Update" = TopLevelAccelerationStructure::Update, a full rebuild

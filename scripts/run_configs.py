@@ -123,7 +123,10 @@ def config4():
         scene.jitter_instances(f, 0.01)
         scene.update_nodes()
         t0 = time.perf_counter()
-        r.AfterUpdateScene(scene)
+        if f % 2:
+            r.AfterUpdateScene(scene)         # every NodeProxy (what the reference does, Scene.cpp:443-492)
+        else:
+            r.AfterUpdateSceneSparse(scene)   # only the proxies that changed
         upload_ms = 1e3 * (time.perf_counter() - t0)
         model = 1 + (f % 16)
         sv = scene.perturb_model(model, f)
@@ -133,7 +136,7 @@ def config4():
         r.Render(scene.ubo(W, H, f), p)
         r.BeforeNextFrame()
         t, c, k = r.timings(), r.counters(), r.kernel_stats()
-        rows.append(dict(tlas=t["tlas_update_ms"], refit=t["blas_refit_ms"], rt=t["rt_pass_ms"], frame=t["frame_ms"], upload=upload_ms, rays=rays(c),
+        rows.append(dict(sparse=(f % 2 == 0), changed=scene.changed()[1], tlas=t["tlas_update_ms"], refit=t["blas_refit_ms"], rt=t["rt_pass_ms"], frame=t["frame_ms"], upload=upload_ms, rays=rays(c),
                          trace=k["trace_ms"] + k["tail_ms"] + k["primary_ms"]))
     rows = rows[2:]
     cnt = scene.counts()
@@ -147,7 +150,9 @@ def config4():
         "instances": cnt["nodes"], "instanced_triangles": cnt["instanced_triangles"], "models": cnt["models"],
         "scene_load_blas_build_tlas_ms_wall": load_ms, "blas_build_ms": r.timings()["blas_build_ms"],
         "tlas_rebuild_ms": float(np.mean([x["tlas"] for x in rows])), "blas_refit_ms": float(np.mean([x["refit"] for x in rows])),
-        "node_upload_ms_wall": float(np.mean([x["upload"] for x in rows])),
+        "node_upload_full_ms_wall": float(np.mean([x["upload"] for x in rows if not x["sparse"]])),
+        "node_upload_sparse_ms_wall": float(np.mean([x["upload"] for x in rows if x["sparse"]])),
+        "proxies_changed_per_frame": float(np.mean([x["changed"] for x in rows])),
         "rt_pass_ms": float(np.mean([x["rt"] for x in rows])), "trace_kernels_ms": float(np.mean([x["trace"] for x in rows])),
         "frame_ms": float(np.mean([x["frame"] for x in rows])),
         "mrays_s_rt_pass": float(np.mean([x["rays"] / (x["rt"] * 1e3) for x in rows])),

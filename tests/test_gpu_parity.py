@@ -440,6 +440,49 @@ def test_blas_refit_and_dynamic_tlas(renderer):
     assert t["blas_refit_ms"] > 0 and t["tlas_update_ms"] > 0
 
 
+def test_sparse_node_updates_equal_full_uploads(renderer):
+    """gkcu_update_nodes_sparse: only the proxies Scene.update_nodes() changed cross the bus (1 % of the instances move per frame
+    in config 4; a moved node changes in the frame it moves and in the next one, when its previous transform catches up).
+    The device node array, the TLAS and the hits must equal those of a context that re-uploads everything."""
+    scene = host.Scene("LegoBricks.synth:4000")
+    scene.update_nodes()
+    full = CudaPathTracingRenderer(0)
+    try:
+        for r in (renderer, full):
+            r.CreateSwapChain((64, 64))
+            r.OnPostLoadScene(scene)
+        rays = random_rays(30000, seed=9, center=(0, 1.5, 0), spread=8.0)
+        rays["dy"] = -np.abs(rays["dy"])
+        sparse_counts = []
+        for step in range(1, 5):
+            if step < 4:
+                scene.jitter_instances(step, 0.01)
+            scene.update_nodes()
+            _, n_changed, all_changed = scene.changed()
+            assert not all_changed
+            sparse_counts.append(n_changed)
+            renderer.AfterUpdateSceneSparse(scene)
+            full.AfterUpdateScene(scene)
+            renderer.PreRender()
+            full.PreRender()
+            a, b = renderer.trace(rays), full.trace(rays)
+            for f in ("inst", "prim"):
+                assert np.array_equal(a[f], b[f])
+            assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+            n_nodes = renderer.debug_info()["instances"]
+            na = renderer.debug_read(7, 0, n_nodes * 52, np.uint32)
+            nb = full.debug_read(7, 0, n_nodes * 52, np.uint32)
+            assert np.array_equal(na, nb)
+        assert 0 < max(sparse_counts) < 0.05 * n_nodes and sparse_counts[-1] > 0  # step 4: nothing moved, last frame's movers settle
+        with pytest.raises(GkcuError):
+            import ctypes as C
+            from gknextengine_b200.renderer import _ck, lib
+            bad = np.array([n_nodes + 5], dtype=np.uint32)
+            _ck(lib().gkcu_update_nodes_sparse(renderer._ctx, bad.ctypes.data_as(C.POINTER(C.c_uint32)), np.zeros(208, np.uint8).ctypes.data, 1))
+    finally:
+        full.close()
+
+
 def test_coincident_instances_are_all_reachable(renderer):
     """Instances with identical boxes (bricks moved onto each other) cannot be separated by any split plane; every one of
     them must still be a TLAS leaf of its own."""
