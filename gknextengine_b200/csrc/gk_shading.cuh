@@ -98,8 +98,16 @@ GK_DEV float4 sky_color(const SceneView& S, float3 dir) {
 }
 
 // AmbientCube.slang:71-78, 178-223, 290-382
+// a / b for a constant b and its rounded reciprocal rb: one multiply and two FMAs (Markstein's correction) instead of the IEEE division
+// sequence. Bit-identical to a / b for the operands used here - checked exhaustively for a = 0..1023, b = 1023 and a = 0..255, b = 255
+// (tests/test_detmath.py) - which is what keeps the probe lookup equal to the oracle's plain divisions.
+GK_DEV float div_const(float a, float b, float rb) {
+    const float q = a * rb;
+    return __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
+}
 GK_DEV float4 unpackRGB10A2(uint32_t p) {
-    float r = float(p & 0x3FF) / 1023.0f, g = float((p >> 10) & 0x3FF) / 1023.0f, b = float((p >> 20) & 0x3FF) / 1023.0f;
+    const float rb = 1.0f / 1023.0f;
+    const float r = div_const(float(p & 0x3FF), 1023.0f, rb), g = div_const(float((p >> 10) & 0x3FF), 1023.0f, rb), b = div_const(float((p >> 20) & 0x3FF), 1023.0f, rb);
     return f4(r, g, b, 0.0f) * 512.f;
 }
 GK_DEV float4 sampleAmbientCubeHL2_Full(const GkAmbientCube& cube, float3 normal) {
@@ -146,7 +154,15 @@ struct DIAmbientCubeSampler { GK_DEV static float4 Sample(const GkAmbientCube& c
 // race allows (every neighbour seen in its pre-dispatch state) and makes the result deterministic.
 struct LiveCubes {
     const GkAmbientCube* cubes;
-    GK_DEV GkAmbientCube fetch(int idx) const { return cubes[idx]; }
+    GK_DEV GkAmbientCube fetch(int idx) const {  // read-only while the path tracer runs: seven 8-byte loads through the read-only path
+        const uint2* p = reinterpret_cast<const uint2*>(cubes + idx);
+        const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5), g = __ldg(p + 6);
+        GkAmbientCube r;
+        r.PosZ = a.x; r.NegZ = a.y; r.PosY = b.x; r.NegY = b.y; r.PosX = c.x; r.NegX = c.y;
+        r.PosZ_D = d.x; r.NegZ_D = d.y; r.PosY_D = e.x; r.NegY_D = e.y; r.PosX_D = f.x; r.NegX_D = f.y;
+        r.skyVisibility_pznzpyny = g.x; r.skyVisibility_pxnxs0s1 = g.y;
+        return r;
+    }
 };
 struct SnapshotCubes {
     const GkAmbientCube* cubes;
@@ -170,14 +186,23 @@ __device__ __noinline__ float4 interpolateAmbientCubesV2(const SceneView& S, con
     float3 fr = f3(nearpos.x - floorf(nearpos.x), nearpos.y - floorf(nearpos.y), nearpos.z - floorf(nearpos.z));
     float totalWeight = 0.0f;
     float4 result = f4(0, 0, 0, 0);
+    // the eight voxels' distance words first (independent 8-byte loads in flight together), then the probes that pass
+    uint2 vox[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int idx = (by + ((i >> 1) & 1)) * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + (bz + ((i >> 2) & 1)) * GK_CUBE_SIZE_XY + (bx + (i & 1));
+        vox[i] = reinterpret_cast<const uint2*>(S.voxels + idx)[1];
+    }
+    const float r255 = 1.0f / 255.0f;
+#pragma unroll
     for (int i = 0; i < 8; i++) {
         int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
         int idx = (by + oy) * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + (bz + oz) * GK_CUBE_SIZE_XY + (bx + ox);
-        const GkVoxelData voxel = S.voxels[idx];
-        uint32_t u0 = voxel.distanceToSolid_gg_z01, u1 = voxel.distanceToSolid_x01_y01;
-        float d0y = float((u0 >> 8) & 0xFF) / 255.0f, distPZ = float((u0 >> 16) & 0xFF) / 255.0f, distNZ = float((u0 >> 24) & 0xFF) / 255.0f;
-        float distPX = float(u1 & 0xFF) / 255.0f, distNX = float((u1 >> 8) & 0xFF) / 255.0f, distPY = float((u1 >> 16) & 0xFF) / 255.0f,
-              distNY = float((u1 >> 24) & 0xFF) / 255.0f;
+        const uint32_t u0 = vox[i].x, u1 = vox[i].y;
+        float d0y = div_const(float((u0 >> 8) & 0xFF), 255.0f, r255), distPZ = div_const(float((u0 >> 16) & 0xFF), 255.0f, r255),
+              distNZ = div_const(float((u0 >> 24) & 0xFF), 255.0f, r255);
+        float distPX = div_const(float(u1 & 0xFF), 255.0f, r255), distNX = div_const(float((u1 >> 8) & 0xFF), 255.0f, r255),
+              distPY = div_const(float((u1 >> 16) & 0xFF), 255.0f, r255), distNY = div_const(float((u1 >> 24) & 0xFF), 255.0f, r255);
         if (d0y < 0.01f) continue;
         float3 probeToLocal = fr - f3((float)ox, (float)oy, (float)oz);
         float distanceToProbe = length(probeToLocal);

@@ -27,3 +27,16 @@ def test_det_sincos_negative_and_symmetry():
         L.gko_det_sincos(-x, C.byref(s2), C.byref(c2))
         assert s2.value == -s.value and c2.value == c.value
         assert abs(s.value ** 2 + c.value ** 2 - 1) < 3e-7
+
+
+def test_constant_division_by_multiply_and_two_fmas_is_exact():
+    """gk_shading.cuh div_const: q = a * rb; q + fma(-q, b, a) * rb must equal the IEEE quotient a / b for every operand the probe lookup
+    feeds it (10-bit colour codes over 1023, bytes over 255), otherwise the CUDA lookup would drift from the oracle's plain divisions."""
+    f = np.float32
+    for b, n in ((1023, 1024), (255, 256)):
+        a = np.arange(n, dtype=np.float32)
+        rb = f(1.0) / f(b)
+        q = a * rb
+        r = (a.astype(np.float64) - q.astype(np.float64) * b).astype(np.float32)           # fma(-q, b, a): exact product, one rounding
+        got = (q.astype(np.float64) + r.astype(np.float64) * np.float64(rb)).astype(np.float32)  # fma(r, rb, q)
+        assert np.array_equal(got, a / f(b))
