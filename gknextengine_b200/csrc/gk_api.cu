@@ -138,7 +138,7 @@ int gkcu_destroy(GkcuContext* ctx) {
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
                       &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
-                      &c.inst_hi, &c.tlas_active_ids, &c.inst_flags, &c.select_tmp, &c.select_count, &c.node_stage, &c.node_stage_idx, &c.tex_table, &c.cubes, &c.voxels, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
+                      &c.inst_hi, &c.tlas_active_ids, &c.inst_flags, &c.select_tmp, &c.select_count, &c.node_stage, &c.node_stage_idx, &c.tex_table, &c.probes, &c.probe_meta, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
                       &c.peer_flags};
     for (DevBuf* b : bufs) b->release();
     BuildScratch& s = c.scratch;
@@ -307,13 +307,26 @@ int gkcu_set_sky(GkcuContext* ctx, uint32_t id, const float* rgba, uint32_t widt
     return upload_tex_table(c);
 }
 
+// host-side view of the packed device layout (gk_shading.cuh ProbeRec / ProbeMeta)
+struct HostProbeRec { uint32_t cube[14], dist0, dist1; };
+struct HostProbeMeta { uint32_t matId, age; };
+
 int gkcu_set_probes(GkcuContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels) {
     CTX_OR_FAIL(ctx);
     if (!cubes || !voxels) { c.has_probes = false; return 0; }
     size_t n = (size_t)GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z;
-    if (!c.cubes.reserve(n * sizeof(GkAmbientCube)) || !c.voxels.reserve(n * sizeof(GkVoxelData))) return 1;
-    GK_CUDA(cudaMemcpyAsync(c.cubes.p, cubes, n * sizeof(GkAmbientCube), cudaMemcpyHostToDevice, c.stream));
-    GK_CUDA(cudaMemcpyAsync(c.voxels.p, voxels, n * sizeof(GkVoxelData), cudaMemcpyHostToDevice, c.stream));
+    if (!c.probes.reserve(n * sizeof(HostProbeRec)) || !c.probe_meta.reserve(n * sizeof(HostProbeMeta))) return 1;
+    std::vector<HostProbeRec> rec(n);
+    std::vector<HostProbeMeta> meta(n);
+    for (size_t i = 0; i < n; ++i) {
+        memcpy(rec[i].cube, &cubes[i], sizeof(GkAmbientCube));
+        rec[i].dist0 = voxels[i].distanceToSolid_gg_z01;
+        rec[i].dist1 = voxels[i].distanceToSolid_x01_y01;
+        meta[i].matId = voxels[i].matId;
+        meta[i].age = voxels[i].age;
+    }
+    GK_CUDA(cudaMemcpyAsync(c.probes.p, rec.data(), n * sizeof(HostProbeRec), cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaMemcpyAsync(c.probe_meta.p, meta.data(), n * sizeof(HostProbeMeta), cudaMemcpyHostToDevice, c.stream));
     GK_CUDA(cudaStreamSynchronize(c.stream));
     c.has_probes = true;
     return 0;
@@ -368,8 +381,21 @@ int gkcu_probes_read(GkcuContext* ctx, GkAmbientCube* cubes, GkVoxelData* voxels
     if (!c.has_probes) { set_error("gkcu_probes_read: no probe state"); return 1; }
     const size_t n = (size_t)GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z;
     GK_CUDA(cudaStreamSynchronize(c.stream));
-    if (cubes) GK_CUDA(cudaMemcpy(cubes, c.cubes.p, n * sizeof(GkAmbientCube), cudaMemcpyDeviceToHost));
-    if (voxels) GK_CUDA(cudaMemcpy(voxels, c.voxels.p, n * sizeof(GkVoxelData), cudaMemcpyDeviceToHost));
+    if (cubes || voxels) {
+        std::vector<HostProbeRec> rec(n);
+        std::vector<HostProbeMeta> meta(n);
+        GK_CUDA(cudaMemcpy(rec.data(), c.probes.p, n * sizeof(HostProbeRec), cudaMemcpyDeviceToHost));
+        GK_CUDA(cudaMemcpy(meta.data(), c.probe_meta.p, n * sizeof(HostProbeMeta), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) {
+            if (cubes) memcpy(&cubes[i], rec[i].cube, sizeof(GkAmbientCube));
+            if (voxels) {
+                voxels[i].matId = meta[i].matId;
+                voxels[i].age = meta[i].age;
+                voxels[i].distanceToSolid_gg_z01 = rec[i].dist0;
+                voxels[i].distanceToSolid_x01_y01 = rec[i].dist1;
+            }
+        }
+    }
     if (pages) {
         if (!c.pages.p) { set_error("gkcu_probes_read: no page index (probes were set with gkcu_set_probes)"); return 1; }
         GK_CUDA(cudaMemcpy(pages, c.pages.p, (size_t)GK_PAGE_COUNT * GK_PAGE_COUNT * sizeof(GkPageIndex), cudaMemcpyDeviceToHost));

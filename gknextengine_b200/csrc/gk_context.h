@@ -97,7 +97,7 @@ struct Context {
     std::vector<Tex> textures;
     DevBuf tex_table;
     uint32_t tex_count = 0;
-    DevBuf cubes, voxels;
+    DevBuf probes, probe_meta;  // packed probe grid: 64-byte records + (material, age), see gk_shading.cuh
     bool has_probes = false;
     DevBuf pages, cube_snapshot, lights, sky_sh;  // probe bake: page index, snapshot of the range being baked, GPUScene.Lights / HDRSHs
     uint32_t light_count = 0, sky_sh_count = 0;

@@ -286,9 +286,13 @@ GK_DEV int advance(const SceneView& S, const PixelOut& O, const FrameCfg& cfg, c
             action = A_GEN_BOUNCE;
         }
     }
-    if (action == A_PROBE_END) {
-        P.rayColor = P.rayColor * interpolateAmbientCubesV2<FullAmbientCubeSampler>(S, LiveCubes{S.cubes}, P.pos, P.nrm);
-        action = A_END_SAMPLE;
+    {   // path termination in the probe grid: every lane of the warp takes part in the lookups of the few that need one
+        const bool probe_end = action == A_PROBE_END;
+        const float4 gi = interpolateAmbientCubesCoop<FullAmbientCubeSampler>(S, LiveCubes{S.probes}, probe_end, P.pos, P.nrm);
+        if (probe_end) {
+            P.rayColor = P.rayColor * gi;
+            action = A_END_SAMPLE;
+        }
     }
     bool first = false;
     if (action == A_END_SAMPLE) {  // :1159-1171: fold the path into the pixel's running sums
@@ -833,8 +837,8 @@ SceneView make_scene_view(const Context& c) {
     S.shade_inst = c.shade_inst.as<uint4>();
     S.textures = c.tex_table.as<TexDesc>();
     S.tex_count = c.tex_count;
-    S.cubes = c.has_probes ? c.cubes.as<GkAmbientCube>() : nullptr;
-    S.voxels = c.has_probes ? c.voxels.as<GkVoxelData>() : nullptr;
+    S.probes = c.has_probes ? c.probes.as<ProbeRec>() : nullptr;
+    S.probe_meta = c.has_probes ? c.probe_meta.as<ProbeMeta>() : nullptr;
     S.cam = c.ubo.as<GkUniformBufferObject>();
     S.lights = c.light_count ? c.lights.as<GkLightObject>() : nullptr;
     S.sky_sh = c.sky_sh.as<GkSphericalHarmonics>();

@@ -67,7 +67,7 @@ GK_DEV float detect_distance(const SceneView& S, float3 origin, float3 rayDir) {
     return vox_trace(S, origin, rayDir, kCubeUnit * 64, h) ? h.t : 255.0f;
 }
 
-__global__ void __launch_bounds__(128) k_voxelize(SceneView S, GkVoxelData* __restrict__ voxels, GkAmbientCube* __restrict__ cubes) {  // VoxelizeCube, :112-159
+__global__ void __launch_bounds__(128) k_voxelize(SceneView S, ProbeRec* __restrict__ probes, ProbeMeta* __restrict__ meta) {  // VoxelizeCube, :112-159
     const uint32_t gIdx = blockIdx.x * blockDim.x + threadIdx.x;
     if (gIdx >= kGridCount) return;
     const float3 origin = probe_origin(gIdx);
@@ -100,16 +100,18 @@ __global__ void __launch_bounds__(128) k_voxelize(SceneView S, GkVoxelData* __re
                                   (((uint32_t)(distPZ * 255.0f) & 0xFF) << 16) | (((uint32_t)(distNZ * 255.0f) & 0xFF) << 24);
     cube.distanceToSolid_x01_y01 = ((uint32_t)(distPX * 255.0f) & 0xFF) | (((uint32_t)(distNX * 255.0f) & 0xFF) << 8) |
                                    (((uint32_t)(distPY * 255.0f) & 0xFF) << 16) | (((uint32_t)(distNY * 255.0f) & 0xFF) << 24);
-    voxels[gIdx] = cube;
-    GkAmbientCube zero = {};
-    cubes[gIdx] = zero;  // Scene clears the cube buffer with the voxels on a full (non-incremental) pass
+    ProbeRec rec = {};  // colours cleared: a full (non-incremental) pass starts the bake over
+    rec.dist0 = cube.distanceToSolid_gg_z01;
+    rec.dist1 = cube.distanceToSolid_x01_y01;
+    probes[gIdx] = rec;
+    meta[gIdx] = ProbeMeta{cube.matId, cube.age};
 }
 
 // FCPUPageIndex::UpdateData / GetPage, :499-545: voxels with a material, counted per 16 m page of the 64 x 64 index.
-__global__ void k_page_index(const GkVoxelData* __restrict__ voxels, GkPageIndex* __restrict__ pages) {
+__global__ void k_page_index(const ProbeMeta* __restrict__ meta, GkPageIndex* __restrict__ pages) {
     const uint32_t gIdx = blockIdx.x * blockDim.x + threadIdx.x;
     if (gIdx >= kGridCount) return;
-    if (voxels[gIdx].matId == 0) return;
+    if (meta[gIdx].matId == 0) return;
     const float3 rel = probe_origin(gIdx) - f3(-512.0f, 0.0f, -512.0f);
     const int px = min(max((int)(rel.x / 16.0f), 0), GK_PAGE_COUNT - 1), pz = min(max((int)(rel.z / 16.0f), 0), GK_PAGE_COUNT - 1);
     atomicAdd(&pages[pz * GK_PAGE_COUNT + px].voxelCount, 1u);
@@ -125,19 +127,18 @@ __constant__ float2 c_grid4x4[16] = {{-0.75f, -0.75f}, {-0.25f, -0.75f}, {0.25f,
 // One block per probe, one thread per (face, ray): 6 faces x FACE_TRACING_COUNT = 96 rays in flight per probe. The per-ray
 // terms go through shared memory and are summed by one thread per face in ray order, so the sums round exactly like the
 // reference's sequential loop (AmbientCube.slang:494-518). Faces in the call order of RenderAmbientCubeOnly (:685-690).
-__global__ void __launch_bounds__(96) k_bake(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, SnapshotCubes F, GkAmbientCube* __restrict__ cubes,
-                                             GkVoxelData* __restrict__ voxels, uint32_t first) {
+__global__ void __launch_bounds__(96) k_bake(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, SnapshotCubes F, ProbeRec* __restrict__ probes,
+                                             ProbeMeta* __restrict__ meta, uint32_t first) {
     SceneView S = S_;
     S.cam = &cam;
     const uint32_t gIdx = first + blockIdx.x;
-    const GkVoxelData voxel = voxels[gIdx];
-    if ((voxel.distanceToSolid_gg_z01 & 0xFFu) >= 8u) return;  // only probes near a surface, :679
+    if ((probes[gIdx].dist0 & 0xFFu) >= 8u) return;  // only probes near a surface, :679
     __shared__ float4 s_term[6][16];
     __shared__ uint32_t s_hit[6][16];
     __shared__ uint32_t s_skyvis[6], s_sunvis;
     const int face = threadIdx.x >> 4, i = threadIdx.x & 15;
     const float3 basis = face == 0 ? f3(0, 1, 0) : face == 1 ? f3(0, -1, 0) : face == 2 ? f3(1, 0, 0) : face == 3 ? f3(-1, 0, 0) : face == 4 ? f3(0, 0, 1) : f3(0, 0, -1);
-    const uint32_t iterate = voxel.age;
+    const uint32_t iterate = meta[gIdx].age;
     const float3 origin = probe_origin(gIdx) + basis * kCubeUnit * 0.25f;
     {   // FaceTask, :494-518
         const float2 offset = c_grid3x3[iterate % 9u] * 0.25f;
@@ -208,18 +209,17 @@ __global__ void __launch_bounds__(96) k_bake(SceneView S_, const __grid_constant
         const uint32_t oldD = face == 0 ? old.PosY_D : face == 1 ? old.NegY_D : face == 2 ? old.PosX_D : face == 3 ? old.NegX_D : face == 4 ? old.PosZ_D : old.NegZ_D;
         const uint32_t oldI = face == 0 ? old.PosY : face == 1 ? old.NegY : face == 2 ? old.PosX : face == 3 ? old.NegX : face == 4 ? old.PosZ : old.NegZ;
         const uint32_t newD = LerpPackedColorAlt(oldD, directColor, currWeight), newI = LerpPackedColorAlt(oldI, bounceColor, currWeight);
-        GkAmbientCube* c = cubes + gIdx;
-        uint32_t* dD = face == 0 ? &c->PosY_D : face == 1 ? &c->NegY_D : face == 2 ? &c->PosX_D : face == 3 ? &c->NegX_D : face == 4 ? &c->PosZ_D : &c->NegZ_D;
-        uint32_t* dI = face == 0 ? &c->PosY : face == 1 ? &c->NegY : face == 2 ? &c->PosX : face == 3 ? &c->NegX : face == 4 ? &c->PosZ : &c->NegZ;
-        *dD = newD;
-        *dI = newI;
+        // GkAmbientCube word order: PosZ NegZ PosY NegY PosX NegX, then the same six with _D
+        const int w = face == 0 ? 2 : face == 1 ? 3 : face == 2 ? 4 : face == 3 ? 5 : face == 4 ? 0 : 1;
+        probes[gIdx].cube[6 + w] = newD;
+        probes[gIdx].cube[w] = newI;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const GkAmbientCube old = F.fetch((int)gIdx);
-        cubes[gIdx].skyVisibility_pznzpyny = (s_skyvis[4] & 0xFF) | ((s_skyvis[5] & 0xFF) << 8) | ((s_skyvis[0] & 0xFF) << 16) | ((s_skyvis[1] & 0xFF) << 24);
-        cubes[gIdx].skyVisibility_pxnxs0s1 = (s_skyvis[2] & 0xFF) | ((s_skyvis[3] & 0xFF) << 8) | ((s_sunvis & 0xFF) << 16) | (old.skyVisibility_pxnxs0s1 & 0xFF000000u);
-        voxels[gIdx].age = iterate + 1;
+        probes[gIdx].cube[12] = (s_skyvis[4] & 0xFF) | ((s_skyvis[5] & 0xFF) << 8) | ((s_skyvis[0] & 0xFF) << 16) | ((s_skyvis[1] & 0xFF) << 24);
+        probes[gIdx].cube[13] = (s_skyvis[2] & 0xFF) | ((s_skyvis[3] & 0xFF) << 8) | ((s_sunvis & 0xFF) << 16) | (old.skyVisibility_pxnxs0s1 & 0xFF000000u);
+        meta[gIdx].age = iterate + 1;
     }
 }
 
@@ -227,14 +227,14 @@ __global__ void __launch_bounds__(96) k_bake(SceneView S_, const __grid_constant
 
 int probes_voxelize(Context& c) {
     const size_t n = kGridCount;
-    if (!c.cubes.reserve(n * sizeof(GkAmbientCube)) || !c.voxels.reserve(n * sizeof(GkVoxelData)) ||
+    if (!c.probes.reserve(n * sizeof(ProbeRec)) || !c.probe_meta.reserve(n * sizeof(ProbeMeta)) ||
         !c.pages.reserve((size_t)GK_PAGE_COUNT * GK_PAGE_COUNT * sizeof(GkPageIndex)))
         return 1;
     SceneView S = make_scene_view(c);
     cudaStream_t st = c.stream;
-    k_voxelize<<<(kGridCount + 127) / 128, 128, 0, st>>>(S, c.voxels.as<GkVoxelData>(), c.cubes.as<GkAmbientCube>());
+    k_voxelize<<<(kGridCount + 127) / 128, 128, 0, st>>>(S, c.probes.as<ProbeRec>(), c.probe_meta.as<ProbeMeta>());
     GK_CUDA(cudaMemsetAsync(c.pages.p, 0, (size_t)GK_PAGE_COUNT * GK_PAGE_COUNT * sizeof(GkPageIndex), st));
-    k_page_index<<<(kGridCount + 255) / 256, 256, 0, st>>>(c.voxels.as<GkVoxelData>(), c.pages.as<GkPageIndex>());
+    k_page_index<<<(kGridCount + 255) / 256, 256, 0, st>>>(c.probe_meta.as<ProbeMeta>(), c.pages.as<GkPageIndex>());
     GK_CUDA(cudaGetLastError());
     c.has_probes = true;
     c.launches += 2;
@@ -245,12 +245,12 @@ int probes_bake(Context& c, const GkUniformBufferObject& ubo, uint32_t first, ui
     if (!c.has_probes) { set_error("gkcu_probes_bake: no probe state (call gkcu_probes_voxelize or gkcu_set_probes)"); return 1; }
     if ((uint64_t)first + count > kGridCount) { set_error("gkcu_probes_bake: range outside the 192 x 48 x 192 grid"); return 1; }
     if (count == 0) return 0;
-    if (!c.cube_snapshot.reserve((size_t)count * sizeof(GkAmbientCube))) return 1;
+    if (!c.cube_snapshot.reserve((size_t)count * sizeof(ProbeRec))) return 1;
     cudaStream_t st = c.stream;
-    GK_CUDA(cudaMemcpyAsync(c.cube_snapshot.p, c.cubes.as<GkAmbientCube>() + first, (size_t)count * sizeof(GkAmbientCube), cudaMemcpyDeviceToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(c.cube_snapshot.p, c.probes.as<ProbeRec>() + first, (size_t)count * sizeof(ProbeRec), cudaMemcpyDeviceToDevice, st));
     SceneView S = make_scene_view(c);
-    SnapshotCubes F{c.cubes.as<GkAmbientCube>(), c.cube_snapshot.as<GkAmbientCube>(), first, count};
-    k_bake<<<count, 96, 0, st>>>(S, ubo, F, c.cubes.as<GkAmbientCube>(), c.voxels.as<GkVoxelData>(), first);
+    SnapshotCubes F{c.probes.as<ProbeRec>(), c.cube_snapshot.as<ProbeRec>(), first, count};
+    k_bake<<<count, 96, 0, st>>>(S, ubo, F, c.probes.as<ProbeRec>(), c.probe_meta.as<ProbeMeta>(), first);
     GK_CUDA(cudaGetLastError());
     c.launches += 1;
     return 0;

@@ -8,6 +8,18 @@
 namespace gkcu {
 using namespace gkd;
 
+// Device layout of the probe grid. The reference keeps two arrays (AmbientCube 56 B, VoxelData 16 B, BasicTypes.slang:116-151); a lookup
+// needs a probe's two distance words and, if it passes, its 14 colour / visibility words. Here they share one 64-byte aligned record
+// (two 32-byte sectors of one line) and the words only the voxeliser and the bake touch (material, age) sit in a side array.
+// gkcu_set_probes / gkcu_probes_read convert from and to the reference's two arrays.
+struct __align__(64) ProbeRec {
+    uint32_t cube[14];   // GkAmbientCube word for word
+    uint32_t dist0;      // VoxelData.distanceToSolid_gg_z01
+    uint32_t dist1;      // VoxelData.distanceToSolid_x01_y01
+};
+struct ProbeMeta { uint32_t matId, age; };
+static_assert(sizeof(ProbeRec) == 64 && sizeof(GkAmbientCube) == 56, "probe record");
+
 struct TexDesc { const float4* texels; uint32_t w, h; uint32_t pad; };
 
 struct SceneView {
@@ -22,8 +34,8 @@ struct SceneView {
     const uint4* shade_inst;  // 2 x uint4 per instance
     const TexDesc* textures;
     uint32_t tex_count;
-    const GkAmbientCube* cubes;
-    const GkVoxelData* voxels;
+    const ProbeRec* probes;   // packed probe grid (nullptr: zero probe state)
+    const ProbeMeta* probe_meta;
     const GkUniformBufferObject* cam;
     const GkLightObject* lights;      // GPUScene.Lights (BasicTypes.slang:171-183)
     const GkSphericalHarmonics* sky_sh;  // GPUScene.HDRSHs, indexed like the textures (BasicTypes.slang:164-169)
@@ -152,67 +164,160 @@ struct DIAmbientCubeSampler { GK_DEV static float4 Sample(const GkAmbientCube& c
 // (Bake.HwAmbientCube.comp.slang -> FaceTask -> interpolateAmbientCubesV2): in the reference that is a data race inside one
 // dispatch. Here the range being baked is read from a snapshot taken before the launch, which picks one of the outcomes the
 // race allows (every neighbour seen in its pre-dispatch state) and makes the result deterministic.
+GK_DEV GkAmbientCube cube_of(const uint4 a, const uint4 b, const uint4 c, const uint4 d) {
+    GkAmbientCube r;
+    r.PosZ = a.x; r.NegZ = a.y; r.PosY = a.z; r.NegY = a.w; r.PosX = b.x; r.NegX = b.y;
+    r.PosZ_D = b.z; r.NegZ_D = b.w; r.PosY_D = c.x; r.NegY_D = c.y; r.PosX_D = c.z; r.NegX_D = c.w;
+    r.skyVisibility_pznzpyny = d.x; r.skyVisibility_pxnxs0s1 = d.y;
+    return r;
+}
 struct LiveCubes {
-    const GkAmbientCube* cubes;
-    GK_DEV GkAmbientCube fetch(int idx) const {  // read-only while the path tracer runs: seven 8-byte loads through the read-only path
-        const uint2* p = reinterpret_cast<const uint2*>(cubes + idx);
-        const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5), g = __ldg(p + 6);
-        GkAmbientCube r;
-        r.PosZ = a.x; r.NegZ = a.y; r.PosY = b.x; r.NegY = b.y; r.PosX = c.x; r.NegX = c.y;
-        r.PosZ_D = d.x; r.NegZ_D = d.y; r.PosY_D = e.x; r.NegY_D = e.y; r.PosX_D = f.x; r.NegX_D = f.y;
-        r.skyVisibility_pznzpyny = g.x; r.skyVisibility_pxnxs0s1 = g.y;
-        return r;
+    const ProbeRec* probes;
+    GK_DEV GkAmbientCube fetch(int idx) const {  // read-only while the path tracer runs: four 16-byte loads of one line, read-only path
+        const uint4* p = reinterpret_cast<const uint4*>(probes + idx);
+        return cube_of(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
     }
 };
 struct SnapshotCubes {
-    const GkAmbientCube* cubes;
-    const GkAmbientCube* snapshot;  // copies of cubes[first .. first + count)
+    const ProbeRec* probes;
+    const ProbeRec* snapshot;  // copies of probes[first .. first + count)
     uint32_t first, count;
     GK_DEV GkAmbientCube fetch(int idx) const {
         const uint32_t k = (uint32_t)idx - first;
-        return k < count ? snapshot[k] : cubes[idx];
+        const uint4* p = reinterpret_cast<const uint4*>(k < count ? snapshot + k : probes + idx);
+        return cube_of(p[0], p[1], p[2], p[3]);
     }
 };
 
+// One of the eight probes around a point (AmbientCube.slang:318-376): its trilinear weight and weighted sample, or pass = false when the
+// probe is inside geometry or hidden behind a surface.
+template <class Sampler, class Fetch>
+GK_DEV bool probe_term(const SceneView& S, const Fetch& F, int bx, int by, int bz, float3 fr, float3 normal, int i, float4& term, float& weight) {
+    const int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
+    const int idx = (by + oy) * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + (bz + oz) * GK_CUBE_SIZE_XY + (bx + ox);
+    const uint2 vox = reinterpret_cast<const uint2*>(S.probes + idx)[7];  // dist0, dist1: never written during a lookup or a bake
+    const uint32_t u0 = vox.x, u1 = vox.y;
+    const float r255 = 1.0f / 255.0f;
+    const float d0y = div_const(float((u0 >> 8) & 0xFF), 255.0f, r255), distPZ = div_const(float((u0 >> 16) & 0xFF), 255.0f, r255),
+                distNZ = div_const(float((u0 >> 24) & 0xFF), 255.0f, r255);
+    const float distPX = div_const(float(u1 & 0xFF), 255.0f, r255), distNX = div_const(float((u1 >> 8) & 0xFF), 255.0f, r255),
+                distPY = div_const(float((u1 >> 16) & 0xFF), 255.0f, r255), distNY = div_const(float((u1 >> 24) & 0xFF), 255.0f, r255);
+    if (d0y < 0.01f) return false;
+    const float3 probeToLocal = fr - f3((float)ox, (float)oy, (float)oz);
+    const float distanceToProbe = length(probeToLocal);
+    const float3 dir = normalize(probeToLocal);
+    const float hitLength = sqrtf(fmaxf(dir.x, 0.0f)) * distPX + sqrtf(fmaxf(-dir.x, 0.0f)) * distNX + sqrtf(fmaxf(dir.y, 0.0f)) * distPY +
+                            sqrtf(fmaxf(-dir.y, 0.0f)) * distNY + sqrtf(fmaxf(dir.z, 0.0f)) * distPZ + sqrtf(fmaxf(-dir.z, 0.0f)) * distNZ;
+    if (distanceToProbe > hitLength + 0.05f) return false;
+    const float wx = ox == 0 ? (1.0f - fr.x) : fr.x, wy = oy == 0 ? (1.0f - fr.y) : fr.y, wz = oz == 0 ? (1.0f - fr.z) : fr.z;
+    weight = wx * wy * wz;
+    term = Sampler::Sample(F.fetch(idx), normal) * weight;
+    return true;
+}
+
+// Warp-cooperative interpolateAmbientCubesV2 (AmbientCube.slang:290-382). In the shade kernel only a couple of lanes per warp end their
+// path in a given wave, so a per-lane lookup ran its 8 probes x ~350 instructions at 2 of 32 lanes (ncu, profiles/r01_experiments.md).
+// Here the lanes that need a lookup are served four at a time: lane l evaluates probe (l & 7) of the (l >> 3)-th requester, and lane 0 of
+// each group of eight adds the eight terms in probe order - the same order, and therefore the same rounding, as the reference's loop.
+// Every lane of a converged warp must call this (need = false for the ones that only help); a warp that arrives incomplete falls back
+// to per-lane evaluation.
+template <class Sampler, class Fetch>
+__device__ __noinline__ float4 interpolateAmbientCubesCoop(const SceneView& S, const Fetch& F, bool need, float3 inPos, float3 normal) {
+    const float3 CUBE_OFFSET = f3(-GK_CUBE_SIZE_XY / 2, -1.375f, -GK_CUBE_SIZE_XY / 2) * 0.25f;
+    const float3 nearpos = (inPos - CUBE_OFFSET) * (1.0f / 0.25f);
+    float4 out = f4(0, 0, 0, 0);
+    if (need && (nearpos.x < 0 || nearpos.y < 0 || nearpos.z < 0 || nearpos.x > GK_CUBE_SIZE_XY - 2 || nearpos.y > GK_CUBE_SIZE_Z - 2 ||
+                 nearpos.z > GK_CUBE_SIZE_XY - 2)) {
+        out = f4(0, 0, 0, 1);  // outside the probe grid
+        need = false;
+    }
+    if (!S.probes) return out;  // zero probe state: every probe is skipped at :327
+    const unsigned act = __activemask();
+    if (act != 0xffffffffu) {  // incomplete warp (last block, or a caller inside divergent code): per-lane evaluation
+        if (need) {
+            const int bx = (int)floorf(nearpos.x), by = (int)floorf(nearpos.y), bz = (int)floorf(nearpos.z);
+            const float3 fr = f3(nearpos.x - floorf(nearpos.x), nearpos.y - floorf(nearpos.y), nearpos.z - floorf(nearpos.z));
+            float totalWeight = 0.0f;
+            float4 result = f4(0, 0, 0, 0);
+            for (int i = 0; i < 8; i++) {
+                float4 term;
+                float weight;
+                if (!probe_term<Sampler>(S, F, bx, by, bz, fr, normal, i, term, weight)) continue;
+                result = result + term;
+                totalWeight += weight;
+            }
+            out = totalWeight > 0.0f ? result / totalWeight : f4(0, 0, 0, 0);
+        }
+        return out;
+    }
+    unsigned pending = __ballot_sync(0xffffffffu, need);
+    const int lane = threadIdx.x & 31, g = lane >> 3, i = lane & 7;
+    while (pending) {
+        // the g-th requester still pending is this group's customer (none: the group idles this round)
+        unsigned rem = pending;
+        for (int k = 0; k < g; ++k) rem &= rem - 1;
+        const int src = rem ? __ffs(rem) - 1 : -1;
+        const int from = src < 0 ? lane : src;
+        const float px = __shfl_sync(0xffffffffu, nearpos.x, from), py = __shfl_sync(0xffffffffu, nearpos.y, from), pz = __shfl_sync(0xffffffffu, nearpos.z, from);
+        const float nx = __shfl_sync(0xffffffffu, normal.x, from), ny = __shfl_sync(0xffffffffu, normal.y, from), nz = __shfl_sync(0xffffffffu, normal.z, from);
+        float4 term = f4(0, 0, 0, 0);
+        float weight = 0.0f;
+        bool pass = false;
+        if (src >= 0) {
+            const int bx = (int)floorf(px), by = (int)floorf(py), bz = (int)floorf(pz);
+            const float3 fr = f3(px - floorf(px), py - floorf(py), pz - floorf(pz));
+            pass = probe_term<Sampler>(S, F, bx, by, bz, fr, f3(nx, ny, nz), i, term, weight);
+        }
+        // lane 0 of the group adds the eight terms in probe order
+        float4 result = f4(0, 0, 0, 0);
+        float totalWeight = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int l = (lane & 24) + k;
+            const float tx = __shfl_sync(0xffffffffu, term.x, l), ty = __shfl_sync(0xffffffffu, term.y, l), tz = __shfl_sync(0xffffffffu, term.z, l),
+                        tw = __shfl_sync(0xffffffffu, term.w, l), w = __shfl_sync(0xffffffffu, weight, l);
+            const bool p = __shfl_sync(0xffffffffu, pass ? 1 : 0, l) != 0;
+            if (p) {
+                result = result + f4(tx, ty, tz, tw);
+                totalWeight += w;
+            }
+        }
+        const float4 res = totalWeight > 0.0f ? result / totalWeight : f4(0, 0, 0, 0);
+        // hand the four results to their requesters and retire them
+        unsigned served = 0;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+            const int s_lane = __shfl_sync(0xffffffffu, src, gg * 8);
+            const float rx = __shfl_sync(0xffffffffu, res.x, gg * 8), ry = __shfl_sync(0xffffffffu, res.y, gg * 8), rz = __shfl_sync(0xffffffffu, res.z, gg * 8),
+                        rw = __shfl_sync(0xffffffffu, res.w, gg * 8);
+            if (s_lane >= 0) {
+                served |= 1u << s_lane;
+                if (lane == s_lane) out = f4(rx, ry, rz, rw);
+            }
+        }
+        pending &= ~served;
+    }
+    return out;
+}
+
+// Per-lane form (callers inside divergent code, e.g. the probe bake's hit branch).
 template <class Sampler, class Fetch>
 __device__ __noinline__ float4 interpolateAmbientCubesV2(const SceneView& S, const Fetch& F, float3 inPos, float3 normal) {
     const float3 CUBE_OFFSET = f3(-GK_CUBE_SIZE_XY / 2, -1.375f, -GK_CUBE_SIZE_XY / 2) * 0.25f;
-    float3 nearpos = (inPos - CUBE_OFFSET) * (1.0f / 0.25f);
+    const float3 nearpos = (inPos - CUBE_OFFSET) * (1.0f / 0.25f);
     if (nearpos.x < 0 || nearpos.y < 0 || nearpos.z < 0 || nearpos.x > GK_CUBE_SIZE_XY - 2 || nearpos.y > GK_CUBE_SIZE_Z - 2 ||
         nearpos.z > GK_CUBE_SIZE_XY - 2)
         return f4(0, 0, 0, 1);
-    if (!S.cubes) return f4(0, 0, 0, 0);  // zero probe state: every probe is skipped at AmbientCube.slang:327
-    int bx = (int)floorf(nearpos.x), by = (int)floorf(nearpos.y), bz = (int)floorf(nearpos.z);
-    float3 fr = f3(nearpos.x - floorf(nearpos.x), nearpos.y - floorf(nearpos.y), nearpos.z - floorf(nearpos.z));
+    if (!S.probes) return f4(0, 0, 0, 0);
+    const int bx = (int)floorf(nearpos.x), by = (int)floorf(nearpos.y), bz = (int)floorf(nearpos.z);
+    const float3 fr = f3(nearpos.x - floorf(nearpos.x), nearpos.y - floorf(nearpos.y), nearpos.z - floorf(nearpos.z));
     float totalWeight = 0.0f;
     float4 result = f4(0, 0, 0, 0);
-    // the eight voxels' distance words first (independent 8-byte loads in flight together), then the probes that pass
-    uint2 vox[8];
-#pragma unroll
     for (int i = 0; i < 8; i++) {
-        const int idx = (by + ((i >> 1) & 1)) * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + (bz + ((i >> 2) & 1)) * GK_CUBE_SIZE_XY + (bx + (i & 1));
-        vox[i] = reinterpret_cast<const uint2*>(S.voxels + idx)[1];
-    }
-    const float r255 = 1.0f / 255.0f;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
-        int idx = (by + oy) * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + (bz + oz) * GK_CUBE_SIZE_XY + (bx + ox);
-        const uint32_t u0 = vox[i].x, u1 = vox[i].y;
-        float d0y = div_const(float((u0 >> 8) & 0xFF), 255.0f, r255), distPZ = div_const(float((u0 >> 16) & 0xFF), 255.0f, r255),
-              distNZ = div_const(float((u0 >> 24) & 0xFF), 255.0f, r255);
-        float distPX = div_const(float(u1 & 0xFF), 255.0f, r255), distNX = div_const(float((u1 >> 8) & 0xFF), 255.0f, r255),
-              distPY = div_const(float((u1 >> 16) & 0xFF), 255.0f, r255), distNY = div_const(float((u1 >> 24) & 0xFF), 255.0f, r255);
-        if (d0y < 0.01f) continue;
-        float3 probeToLocal = fr - f3((float)ox, (float)oy, (float)oz);
-        float distanceToProbe = length(probeToLocal);
-        float3 dir = normalize(probeToLocal);
-        float hitLength = sqrtf(fmaxf(dir.x, 0.0f)) * distPX + sqrtf(fmaxf(-dir.x, 0.0f)) * distNX + sqrtf(fmaxf(dir.y, 0.0f)) * distPY +
-                          sqrtf(fmaxf(-dir.y, 0.0f)) * distNY + sqrtf(fmaxf(dir.z, 0.0f)) * distPZ + sqrtf(fmaxf(-dir.z, 0.0f)) * distNZ;
-        if (distanceToProbe > hitLength + 0.05f) continue;
-        float wx = ox == 0 ? (1.0f - fr.x) : fr.x, wy = oy == 0 ? (1.0f - fr.y) : fr.y, wz = oz == 0 ? (1.0f - fr.z) : fr.z;
-        float weight = wx * wy * wz;
-        result = result + Sampler::Sample(F.fetch(idx), normal) * weight;
+        float4 term;
+        float weight;
+        if (!probe_term<Sampler>(S, F, bx, by, bz, fr, normal, i, term, weight)) continue;
+        result = result + term;
         totalWeight += weight;
     }
     return totalWeight > 0.0f ? result / totalWeight : f4(0, 0, 0, 0);

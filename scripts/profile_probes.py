@@ -12,12 +12,14 @@ r.CreateSwapChain((W, H))
 r.OnPostLoadScene(scene, sky)
 r.set_lights(scene); r.set_sky_sh(0, host.project_sh(sky))
 p = GkcuFrameParams(temporal_frames=16, spp_world=1)
-for probes in (False, True):
+modes = (True,) if "--probes-only" in sys.argv else (False, True)
+frames = 2 if "--probes-only" in sys.argv else 5
+for probes in modes:
     if probes:
         r.probes_voxelize()
         ubo = scene.ubo(W, H, 1)
         for f in range(120): r.PostRender(ubo, f)
-    for f in range(1, 5):
+    for f in range(1, frames):
         r.PreRender(); r.Render(scene.ubo(W, H, f), p); r.BeforeNextFrame()
     t, k = r.timings(), r.kernel_stats()
     print("probes" if probes else "zero  ", {x: round(t[x], 2) for x in ("rt_pass_ms",)}, {x: round(k[x], 2) for x in ("trace_ms", "shade_ms", "tail_ms", "primary_ms")}, r.counters()["closest_hit_rays"])
