@@ -150,6 +150,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--tracer", type=int, default=0, help="0 wavefront (default), 1 megakernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--probes", action="store_true",
+                    help="voxelise the probe grid, bake one full sweep before timing and record the per-frame bake dispatch like "
+                         "RayTraceBaseRenderer::PostRender; default: zero probe state (SURVEY 8d config 1/2)")
     ap.add_argument("--present", default="async", choices=["async", "blocking"],
                     help="e2e leg: async = double-buffered gkcu_readback_denoised_async overlapping the next frame; blocking = gkcu_readback")
     ap.add_argument("--reduce", default="peer", choices=["peer", "peer-hostbarrier", "nccl"],
@@ -194,6 +197,14 @@ def main():
     r = CudaPathTracingRenderer(local_rank)
     r.CreateSwapChain((WIDTH, HEIGHT))
     r.OnPostLoadScene(scene, sky)
+    if args.probes:
+        r.set_lights(scene)
+        r.set_sky_sh(0, host.project_sh(sky))
+        r.PreRender()
+        r.probes_voxelize()
+        ubo0 = scene.ubo(WIDTH, HEIGHT, 1)
+        for f in range(120):
+            r.PostRender(ubo0, f)
     ext = torch.cuda.ExternalStream(r.stream(), device=local_rank)
     params = GkcuFrameParams(temporal_frames=16, spp_world=world, spp_rank=rank, tracer=args.tracer, skip_post=1 if world > 1 else 0)
 
@@ -253,6 +264,8 @@ def main():
                 if rank == 0:
                     r.run_post(ubo, params)
             reduce_ev[1].record(ext)
+        if args.probes:
+            r.PostRender(ubo, total_frames)  # "hw-lightbake": 1/120 of the probe grid per frame (RayTraceBaseRenderer.cpp:225-274)
         return ubo
 
     def sync_all():
@@ -351,7 +364,7 @@ def main():
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "config2" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
+            "config": dict(workload_config(world), probes="voxelised + baked grid, bake dispatch every frame" if args.probes else "zero probe state"),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": node_bytes + 784,
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 8},
             "gpu_launches": int(launches),
