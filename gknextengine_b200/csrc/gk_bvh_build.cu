@@ -1199,7 +1199,7 @@ int build_tlas(Context& c) {
         if (build_sah(c, m, 1, b2)) return 1;
         if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
     }
-    // the traversal stack holds at most 3 entries per level plus one sentinel per instance entry
+    // the traversal stack holds at most 3 entries per level (TLAS levels + the deepest BLAS)
     size_t blas_levels = 0;
     for (auto& b : c.blas) blas_levels = std::max(blas_levels, b.level_start.size() > 0 ? b.level_start.size() - 1 : 0);
     size_t need = 3 * (c.tlas.level_start.size() - 1) + 3 * blas_levels + 2;

@@ -759,7 +759,7 @@ __global__ void k_resolve(RTView R, const float4* __restrict__ radiance, const f
 }
 
 // Fused multi-GPU reduce + resolve of one strip of rows: peer loads of every rank's un-normalised sums, rank-ordered sum,
-// Shading.slang:1175-1183, peer stores of the fp16 results into rank 0's SINGLE_* images. 80 B in per rank-pixel, 16 B out.
+// Shading.slang:1175-1183, peer stores of the fp16 results into rank 0's SINGLE_* images. 32 B in per rank and pixel (+ 16 B direct term), 16 B out.
 struct PeerRadiance { const float4* rad[GKCU_MAX_PEERS]; };
 __global__ void __launch_bounds__(256) k_resolve_strip(uint2* __restrict__ out_diffuse, uint2* __restrict__ out_specular, PeerRadiance P, int world,
                                                        const float4* __restrict__ direct0, const uint16_t* __restrict__ moment,
