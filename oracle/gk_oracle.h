@@ -10,6 +10,8 @@
  *   - struct layouts, against the reference's own dual-language header compiled as C++ (oracle/ref_layout_check.cpp)
  *   - the ray/BVH intersector, against the reference's vendored tinybvh v1.3.8 compiled from
  *     /root/reference/src/ThirdParty/tinybvh/tiny_bvh.h into oracle/_ref/ (same oracle source, -DGKO_TINYBVH)
+ *   - EvaluateSH / SampleIBL (the SH sky used by the probe bake), against the reference's dual-language GLSL header compiled as
+ *     C++ from /root/reference/assets/shaders/glsl_legacy/common/SampleIBL.glsl into oracle/_ref/libref_sh.so (oracle/ref_sh.cpp)
  *   - fixture known-answers generated here with libstdc++, in tests/golden/.
  */
 #ifndef GK_ORACLE_H

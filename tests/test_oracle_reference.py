@@ -130,3 +130,43 @@ def test_denoise_properties():
     assert np.ptp(out2.reshape(-1, 4), axis=0).max() == 0
     # the 0.001 fetch bias of the filtered path makes it slightly brighter than the unfiltered one
     assert (inner[0, 0] >= out2[0, 0, :3]).all()
+
+
+REF_SH = os.path.join(os.path.dirname(O.TINYBVH), "libref_sh.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SH), reason="oracle/_ref not built (reference not mounted)")
+def test_sample_ibl_rough_is_pinned_to_the_references_own_evaluate_sh():
+    """The oracle's SampleIBLRough (restating Shading.slang:146-192) against the reference's EvaluateSH / SampleIBL compiled from
+    assets/shaders/glsl_legacy/common/SampleIBL.glsl where it lies (oracle/ref_sh.cpp): random coefficients, directions and sky
+    rotations. The only difference allowed is sin/cos of the rotation angle (libm there, the pinned polynomial here): 2e-6 relative."""
+    import ctypes as C
+    from gknextengine_b200 import host
+    from gknextengine_b200._abi import GkSphericalHarmonics
+    ref = C.CDLL(REF_SH)
+    ref.ref_sample_ibl_sh.argtypes = [C.POINTER(C.c_float * 27), C.POINTER(C.c_float * 3), C.c_float, C.POINTER(C.c_float * 4)]
+    scene = host.Scene("CornellBox.proc", samples=1, bounces=4)
+    scene.update_nodes()
+    osc = O.OracleScene(scene)
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for trial in range(200):
+        co = rng.normal(size=(3, 9)).astype(np.float32) * np.float32(3.0)
+        sh = GkSphericalHarmonics()
+        for c in range(3):
+            for i in range(9):
+                sh.coefficients[c][i] = float(co[c, i])
+        osc.set_sky_sh(0, sh)
+        d = rng.normal(size=3).astype(np.float32)
+        d /= np.linalg.norm(d)
+        rot = float(rng.uniform(0, 2)) if trial % 4 else 0.0
+        a, b = (C.c_float * 4)(), (C.c_float * 4)()
+        osc.L.gko_sample_ibl_rough(osc._h, 0, (C.c_float * 3)(*d), rot, a)
+        ref.ref_sample_ibl_sh((C.c_float * 27)(*co.reshape(-1)), (C.c_float * 3)(*d), rot, b)
+        a, b = np.array(a), np.array(b)
+        scale = np.abs(co).sum(axis=1).max()
+        worst = max(worst, float(np.abs(a[:3] - b[:3]).max() / scale))
+        assert a[3] == b[3] == 1.0
+        if rot == 0.0:  # angle = pi: sin(pi) is ~ -8.7e-8 in both, cos exactly -1 -> identical arithmetic
+            assert np.abs(a[:3] - b[:3]).max() <= 2e-6 * scale
+    assert worst <= 2e-6
