@@ -1825,6 +1825,35 @@ void gko_random_in_hemisphere1(uint32_t seed[4], float out[3]) {
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 float gko_schlick(float cosine, float ior) { return Schlick(cosine, ior); }
+void gko_st2084(const float in[3], float out[3]) { f3 r = LinearToST2084UE(F3(in[0], in[1], in[2])); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void gko_align_with_normal(const float ray[3], const float n[3], float out[3]) {
+    f3 r = AlignWithNormal(F3(ray[0], ray[1], ray[2]), F3(n[0], n[1], n[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+float gko_random_float(uint32_t seed[4]) {
+    u4 s{seed[0], seed[1], seed[2], seed[3]};
+    float r = RandomFloat(s);
+    seed[0] = s.x; seed[1] = s.y; seed[2] = s.z; seed[3] = s.w;
+    return r;
+}
+void gko_random_float2(uint32_t seed[4], float out[2]) {
+    u4 s{seed[0], seed[1], seed[2], seed[3]};
+    f2 r = RandomFloat2(s);
+    seed[0] = s.x; seed[1] = s.y; seed[2] = s.z; seed[3] = s.w;
+    out[0] = r.x; out[1] = r.y;
+}
+void gko_random_in_unit_disk(uint32_t seed[4], float out[2]) {
+    u4 s{seed[0], seed[1], seed[2], seed[3]};
+    f2 r = RandomInUnitDisk(s);
+    seed[0] = s.x; seed[1] = s.y; seed[2] = s.z; seed[3] = s.w;
+    out[0] = r.x; out[1] = r.y;
+}
+void gko_random_in_cone(uint32_t seed[4], float cos_theta, float out[3]) {
+    u4 s{seed[0], seed[1], seed[2], seed[3]};
+    f3 r = RandomInCone(s, cos_theta);
+    seed[0] = s.x; seed[1] = s.y; seed[2] = s.z; seed[3] = s.w;
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
 void gko_det_sincos(float x, float* s, float* c) { gk_det_sincosf(x, s, c); }
 float* gko_radiance(GkoFrame* f, size_t* floats) { if (floats) *floats = f->radiance.size(); return f->radiance.data(); }
 void gko_resolve(GkoFrame* f, const GkUniformBufferObject* ubo) {

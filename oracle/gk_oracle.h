@@ -79,6 +79,12 @@ void gko_ggx_sampling(uint32_t seed[4], float roughness, const float normal[3], 
 void gko_random_in_hemisphere1(uint32_t seed[4], float out[3]);
 float gko_schlick(float cosine, float ior);
 void gko_det_sincos(float x, float* s, float* c);
+void gko_st2084(const float in[3], float out[3]);
+void gko_align_with_normal(const float ray[3], const float n[3], float out[3]);
+float gko_random_float(uint32_t seed[4]);
+void gko_random_float2(uint32_t seed[4], float out[2]);
+void gko_random_in_unit_disk(uint32_t seed[4], float out[2]);
+void gko_random_in_cone(uint32_t seed[4], float cos_theta, float out[3]);
 
 /* Multi-GPU sample split: with params.skip_post = 1 gko_render_frame traces only rank params.spp_rank's samples and
  * leaves the un-normalised sums in the radiance buffer: 2 planes of W*H float4 (FinalColor, FinalReflection) followed by the

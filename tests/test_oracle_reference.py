@@ -170,3 +170,78 @@ def test_sample_ibl_rough_is_pinned_to_the_references_own_evaluate_sh():
         if rot == 0.0:  # angle = pi: sin(pi) is ~ -8.7e-8 in both, cos exactly -1 -> identical arithmetic
             assert np.abs(a[:3] - b[:3]).max() <= 2e-6 * scale
     assert worst <= 2e-6
+
+
+REF_CF = os.path.join(os.path.dirname(O.TINYBVH), "libref_const_func.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CF), reason="oracle/_ref not built (reference not mounted)")
+def test_sampling_rng_and_tonemap_library_is_pinned_to_the_references_source():
+    """SURVEY 8a rows a19 / a25. The reference's own Const_Func.slang functions - extracted by line range where the file lies and compiled as
+    C++ (oracle/ref_const_func.cpp, oracle/Makefile) - against the oracle's restatements on random inputs:
+      bit-exact: pcg4d, uint_to_float, RandomFloat, RandomFloat2, Schlick, AlignWithNormal (ONB + to_world), GT tonemapper, ST2084;
+      <= 4e-6 absolute: the samplers that take sin/cos of a random angle (libm there, the pinned polynomial gk_det_sincosf here):
+      RandomInUnitDisk, RandomInCone, RandomInHemiSphere1, ggxSampling. The RNG state after each call must be identical."""
+    import ctypes as C
+    ref, L = C.CDLL(REF_CF), O.load()
+    f3, f2, u4 = C.c_float * 3, C.c_float * 2, C.c_uint32 * 4
+    for lib, pre in ((ref, "ref_"), (L, "gko_")):
+        getattr(lib, pre + "schlick").restype = C.c_float
+        getattr(lib, pre + "schlick").argtypes = [C.c_float, C.c_float]
+        getattr(lib, pre + "uint_to_float").restype = C.c_float
+        getattr(lib, pre + "uint_to_float").argtypes = [C.c_uint32]
+        getattr(lib, pre + "random_float").restype = C.c_float
+        getattr(lib, pre + "random_float").argtypes = [C.POINTER(u4)]
+        getattr(lib, pre + "random_float2").argtypes = [C.POINTER(u4), C.POINTER(f2)]
+        getattr(lib, pre + "random_in_unit_disk").argtypes = [C.POINTER(u4), C.POINTER(f2)]
+        getattr(lib, pre + "random_in_cone").argtypes = [C.POINTER(u4), C.c_float, C.POINTER(f3)]
+        getattr(lib, pre + "random_in_hemisphere1").argtypes = [C.POINTER(u4), C.POINTER(f3)]
+        getattr(lib, pre + "ggx_sampling").argtypes = [C.POINTER(u4), C.c_float, C.POINTER(f3), C.POINTER(f3)]
+        getattr(lib, pre + "align_with_normal").argtypes = [C.POINTER(f3), C.POINTER(f3), C.POINTER(f3)]
+        getattr(lib, pre + "st2084").argtypes = [C.POINTER(f3), C.POINTER(f3)]
+        getattr(lib, pre + "gt_tonemap").argtypes = [C.POINTER(f3), C.POINTER(f3)]
+        getattr(lib, pre + "pcg4d").argtypes = [C.POINTER(u4)]
+    bits = lambda a: np.array(a, dtype=np.float32).view(np.uint32).tolist()
+    rng = np.random.default_rng(2024)
+    worst = 0.0
+    for trial in range(3000):
+        seed = [int(x) for x in rng.integers(0, 2 ** 32, 4)]
+        if trial < 4:
+            seed = [[3, 5, 7, 0], [0, 0, 0, 0], [0xFFFFFFFF] * 4, [1919, 1079, 256, 0]][trial]
+        # integer / exact functions
+        a, b = u4(*seed), u4(*seed)
+        ref.ref_pcg4d(a); L.gko_pcg4d(b)
+        assert list(a) == list(b)
+        assert bits([ref.ref_uint_to_float(seed[0])]) == bits([L.gko_uint_to_float(seed[0])])
+        a, b = u4(*seed), u4(*seed)
+        assert bits([ref.ref_random_float(a)]) == bits([L.gko_random_float(b)]) and list(a) == list(b)
+        a, b, oa, ob = u4(*seed), u4(*seed), f2(), f2()
+        ref.ref_random_float2(a, oa); L.gko_random_float2(b, ob)
+        assert bits(oa) == bits(ob) and list(a) == list(b)
+        c, ior = float(rng.uniform(0, 1)), float(rng.uniform(1.0, 2.5))
+        assert bits([ref.ref_schlick(c, ior)]) == bits([L.gko_schlick(c, ior)])
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        if trial % 50 == 0:
+            n = np.array([0.0, 0.0, -1.0 if trial % 100 else 1.0])  # the ONB singularity side
+        ray = rng.normal(size=3)
+        oa, ob = f3(), f3()
+        ref.ref_align_with_normal(f3(*ray), f3(*n), oa); L.gko_align_with_normal(f3(*ray), f3(*n), ob)
+        assert bits(oa) == bits(ob)
+        col = np.abs(rng.normal(size=3)) * (10.0 ** rng.uniform(-3, 1.5))
+        ref.ref_gt_tonemap(f3(*col), oa); L.gko_gt_tonemap(f3(*col), ob)
+        assert bits(oa) == bits(ob)
+        ref.ref_st2084(f3(*(col * 100)), oa); L.gko_st2084(f3(*(col * 100)), ob)
+        assert bits(oa) == bits(ob)
+        # samplers with a trigonometric step
+        for name, extra, out_t in (("random_in_unit_disk", (), f2), ("random_in_hemisphere1", (), f3),
+                                   ("random_in_cone", (C.c_float(0.99999048),), f3), ("random_in_cone", (C.c_float(float(rng.uniform(-1, 1))),), f3)):
+            a, b, oa, ob = u4(*seed), u4(*seed), out_t(), out_t()
+            getattr(ref, "ref_" + name)(a, *extra, oa); getattr(L, "gko_" + name)(b, *extra, ob)
+            assert list(a) == list(b)
+            worst = max(worst, float(np.abs(np.array(oa) - np.array(ob)).max()))
+        rough = float(rng.uniform(0.0, 1.0))
+        a, b, oa, ob = u4(*seed), u4(*seed), f3(), f3()
+        ref.ref_ggx_sampling(a, rough, f3(*n), oa); L.gko_ggx_sampling(b, rough, f3(*n), ob)
+        assert list(a) == list(b)
+        worst = max(worst, float(np.abs(np.array(oa) - np.array(ob)).max()))
+    assert worst <= 4e-6, worst
