@@ -1703,6 +1703,13 @@ const GkVoxelData* gko_probes_voxels(GkoScene* s) { return s->voxels.data(); }
 const GkPageIndex* gko_probes_pages(GkoScene* s) { return s->pages.data(); }
 uint32_t gko_pack_rgb10a2(const float c[4]) { return GkoScene::packRGB10A2(F4(c[0], c[1], c[2], c[3])); }
 void gko_unpack_rgb10a2(uint32_t p, float out[4]) { f4 c = GkoScene::unpackRGB10A2(p); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w; }
+uint32_t gko_lerp_packed_color_alt(uint32_t c0, const float c1[4], float t) { return GkoScene::LerpPackedColorAlt(c0, F4(c1[0], c1[1], c1[2], c1[3]), t); }
+void gko_sample_ambient_cube(int which, const uint32_t cube14[14], const float n[3], float out[4]) {  /* which: 0 DI, 2 Full */
+    GkAmbientCube c;
+    memcpy(&c, cube14, sizeof(c));
+    f4 r = which == 0 ? GkoScene::sampleAmbientCubeHL2_DI(c, F3(n[0], n[1], n[2])) : GkoScene::sampleAmbientCubeHL2_Full(c, F3(n[0], n[1], n[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
 void gko_sample_ibl_rough(GkoScene* s, uint32_t id, const float dir[3], float rotate, float out[4]) {
     f4 c = s->SampleIBLRough(id, F3(dir[0], dir[1], dir[2]), rotate); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
 }

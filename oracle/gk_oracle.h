@@ -46,6 +46,8 @@ const GkVoxelData* gko_probes_voxels(GkoScene* s);
 const GkPageIndex* gko_probes_pages(GkoScene* s);
 uint32_t gko_pack_rgb10a2(const float c[4]);
 void gko_unpack_rgb10a2(uint32_t packed, float out[4]);
+uint32_t gko_lerp_packed_color_alt(uint32_t c0, const float c1[4], float t);
+void gko_sample_ambient_cube(int which, const uint32_t cube14[14], const float n[3], float out[4]); /* 0 DI, 2 Full */
 void gko_sample_ibl_rough(GkoScene* s, uint32_t id, const float dir[3], float rotate, float out[4]);
 
 GkoFrame* gko_frame_create(uint32_t width, uint32_t height);

@@ -49,6 +49,7 @@ struct float3 {
     float3() : x(0), y(0), z(0) {}
     float3(float a, float b_, float c) : x(a), y(b_), z(c) {}
     float3(float2 a, float c) : x(a.x), y(a.y), z(c) {}
+    float3& operator*=(float s) { x *= s; y *= s; z *= s; return *this; }
 };
 inline float3 operator+(float3 a, float3 b) { return float3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline float3 operator+(float a, float3 b) { return float3(a + b.x, a + b.y, a + b.z); }
@@ -62,6 +63,27 @@ inline float3 normalize(float3 a) { float inv = 1.0f / sqrt(dot(a, a)); return a
 inline float3 pow(float3 a, float3 b) { return float3(pow(a.x, b.x), pow(a.y, b.y), pow(a.z, b.z)); }
 inline float min(float a, float b) { return fminf(a, b); }
 inline float clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+struct float4 {
+    union {
+        struct { float x, y, z, w; };
+        struct { float r, g, b, a; };
+        float3 xyz;
+    };
+    float4() : x(0), y(0), z(0), w(0) {}
+    float4(float v) : x(v), y(v), z(v), w(v) {}
+    float4(float a_, float b_, float c, float d) : x(a_), y(b_), z(c), w(d) {}
+    float4& operator+=(float4 o) { x += o.x; y += o.y; z += o.z; w += o.w; return *this; }
+    float4& operator*=(float s) { x *= s; y *= s; z *= s; w *= s; return *this; }
+};
+inline float4 operator+(float4 a, float4 b) { return float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+inline float4 operator-(float4 a, float4 b) { return float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+inline float4 operator*(float4 a, float s) { return float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+inline float4 operator*(float s, float4 a) { return float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+inline float4 operator/(float4 a, float s) { return float4(a.x / s, a.y / s, a.z / s, a.w / s); }
+inline float4 clamp(float4 v, float4 lo, float4 hi) { return float4(clamp(v.x, lo.x, hi.x), clamp(v.y, lo.y, hi.y), clamp(v.z, lo.z, hi.z), clamp(v.w, lo.w, hi.w)); }
+inline float4 lerp(float4 a, float4 b, float t) { return a + (b - a) * t; }
+inline float max(float a, float b) { return fmaxf(a, b); }
 
 struct float3x3 {
     float3 row[3];
@@ -93,6 +115,10 @@ inline float2 asfloat(uint2 v) { return float2(asfloat(v.x), asfloat(v.y)); }
 
 #include "PreProcessor.slang"
 #include "const_func_gen.inc"
+struct AmbientCube {  // BasicTypes.slang:115-137; the layout itself is pinned by ref_layout_check
+    uint PosZ, NegZ, PosY, NegY, PosX, NegX, PosZ_D, NegZ_D, PosY_D, NegY_D, PosX_D, NegX_D, skyVisibility_pznzpyny, skyVisibility_pxnxs0s1;
+};
+#include "ambient_cube_gen.inc"
 }  // namespace ref
 
 using namespace ref;
@@ -122,5 +148,16 @@ void ref_random_in_hemisphere1(uint32_t* v, float* out) {
 void ref_ggx_sampling(uint32_t* v, float roughness, const float* n, float* out) {
     uint4 s(v[0], v[1], v[2], v[3]); float3 r = ggxSampling(s, roughness, float3(n[0], n[1], n[2]));
     v[0] = s.x; v[1] = s.y; v[2] = s.z; v[3] = s.w; out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+uint32_t ref_pack_rgb10a2(const float* c) { return packRGB10A2(float4(c[0], c[1], c[2], c[3])); }
+void ref_unpack_rgb10a2(uint32_t p, float* out) { float4 c = unpackRGB10A2(p); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w; }
+uint32_t ref_lerp_packed_color_alt(uint32_t c0, const float* c1, float t) { return LerpPackedColorAlt(c0, float4(c1[0], c1[1], c1[2], c1[3]), t); }
+// which: 0 DI, 1 LightCache, 2 Full
+void ref_sample_ambient_cube(int which, const uint32_t* cube14, const float* n, float* out) {
+    AmbientCube c;
+    std::memcpy(&c, cube14, sizeof(c));
+    float3 nn(n[0], n[1], n[2]);
+    float4 r = which == 0 ? sampleAmbientCubeHL2_DI(c, nn) : which == 1 ? sampleAmbientCubeHL2_LightCache(c, nn) : sampleAmbientCubeHL2_Full(c, nn);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 }

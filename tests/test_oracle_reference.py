@@ -245,3 +245,43 @@ def test_sampling_rng_and_tonemap_library_is_pinned_to_the_references_source():
         assert list(a) == list(b)
         worst = max(worst, float(np.abs(np.array(oa) - np.array(ob)).max()))
     assert worst <= 4e-6, worst
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CF), reason="oracle/_ref not built (reference not mounted)")
+def test_probe_colour_format_and_samplers_are_pinned_to_the_references_source():
+    """AmbientCube.slang:58-223 (packRGB10A2, unpackRGB10A2, LerpPackedColorAlt, sampleAmbientCubeHL2_DI and
+    _Full) compiled from the reference's file as C++ against the oracle's restatements: bit-exact on every 10-bit code, on random
+    colours including out-of-range and negative ones, on random temporal lerps, and on random cubes and normals."""
+    import ctypes as C
+    ref, L = C.CDLL(REF_CF), O.load()
+    f4, f3, c14 = C.c_float * 4, C.c_float * 3, C.c_uint32 * 14
+    for lib, pre in ((ref, "ref_"), (L, "gko_")):
+        getattr(lib, pre + "pack_rgb10a2").restype = C.c_uint32
+        getattr(lib, pre + "pack_rgb10a2").argtypes = [C.POINTER(f4)]
+        getattr(lib, pre + "unpack_rgb10a2").argtypes = [C.c_uint32, C.POINTER(f4)]
+        getattr(lib, pre + "lerp_packed_color_alt").restype = C.c_uint32
+        getattr(lib, pre + "lerp_packed_color_alt").argtypes = [C.c_uint32, C.POINTER(f4), C.c_float]
+        getattr(lib, pre + "sample_ambient_cube").argtypes = [C.c_int, C.POINTER(c14), C.POINTER(f3), C.POINTER(f4)]
+    bits = lambda a: np.array(a, dtype=np.float32).view(np.uint32).tolist()
+    for code in range(1024):
+        p = code | ((1023 - code) << 10) | (((code * 7) & 0x3FF) << 20) | ((code & 3) << 30)
+        a, b = f4(), f4()
+        ref.ref_unpack_rgb10a2(p, a); L.gko_unpack_rgb10a2(p, b)
+        assert bits(a) == bits(b)
+    rng = np.random.default_rng(77)
+    for trial in range(4000):
+        col = rng.normal(size=4) * (10.0 ** rng.uniform(-2, 3.2))
+        assert ref.ref_pack_rgb10a2(f4(*col)) == L.gko_pack_rgb10a2(f4(*col))
+        c0 = int(rng.integers(0, 2 ** 32))
+        t = 0.125 if trial % 2 else float(rng.uniform(0, 1))
+        assert ref.ref_lerp_packed_color_alt(c0, f4(*np.abs(col)), t) == L.gko_lerp_packed_color_alt(c0, f4(*np.abs(col)), t)
+        cube = c14(*[int(x) for x in rng.integers(0, 2 ** 32, 14)])
+        n = rng.normal(size=3)
+        if trial % 3 == 0:
+            n /= np.linalg.norm(n)
+        if trial % 97 == 0:
+            n[:] = 0  # sum of weights 0: the samplers' (sum > 0) guard
+        for which in (0, 2):
+            a, b = f4(), f4()
+            ref.ref_sample_ambient_cube(which, cube, f3(*n), a); L.gko_sample_ambient_cube(which, cube, f3(*n), b)
+            assert bits(a) == bits(b), (which, list(a), list(b))
