@@ -1703,6 +1703,21 @@ const GkVoxelData* gko_probes_voxels(GkoScene* s) { return s->voxels.data(); }
 const GkPageIndex* gko_probes_pages(GkoScene* s) { return s->pages.data(); }
 uint32_t gko_pack_rgb10a2(const float c[4]) { return GkoScene::packRGB10A2(F4(c[0], c[1], c[2], c[3])); }
 void gko_unpack_rgb10a2(uint32_t p, float out[4]) { f4 c = GkoScene::unpackRGB10A2(p); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w; }
+uint32_t gko_get_material_data(GkoScene* s, uint32_t node_plus1, uint32_t prim, const float ro[3], const float rd[3], float out[18]) {
+    Vertex v = get_material_dataV2(*s, node_plus1, prim, F3(ro[0], ro[1], ro[2]), F3(rd[0], rd[1], rd[2]));
+    const float o[18] = {v.Position.x, v.Position.y, v.Position.z, v.Normal.x, v.Normal.y, v.Normal.z, v.Tangent.x, v.Tangent.y, v.Tangent.z, v.TexCoord.x, v.TexCoord.y,
+                         v.LocalNormal.x, v.LocalNormal.y, v.LocalNormal.z, v.LocalTangent.x, v.LocalTangent.y, v.LocalTangent.z, v.LocalTangent.w};
+    for (int i = 0; i < 18; ++i) out[i] = o[i];
+    return v.MaterialIndex;
+}
+uint32_t gko_fetch_material_id(GkoScene* s, uint32_t node, uint32_t offset) { return FetchMaterialId(s->nodes[node], offset); }
+void gko_mikktspace(const float vnt[3], const float n[3], const float t[4], float out[3]) {
+    f3 r = Renderer::mikkTSpace(F3(vnt[0], vnt[1], vnt[2]), F3(n[0], n[1], n[2]), F4(t[0], t[1], t[2], t[3]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+float gko_calculate_weight(float centerDist, int sameObject, int isCenter, const float n[3], const float cn[3]) {
+    return calculateWeight(centerDist, sameObject != 0, isCenter != 0, F3(n[0], n[1], n[2]), F3(cn[0], cn[1], cn[2]));
+}
 uint32_t gko_lerp_packed_color_alt(uint32_t c0, const float c1[4], float t) { return GkoScene::LerpPackedColorAlt(c0, F4(c1[0], c1[1], c1[2], c1[3]), t); }
 void gko_sample_ambient_cube(int which, const uint32_t cube14[14], const float n[3], float out[4]) {  /* which: 0 DI, 2 Full */
     GkAmbientCube c;

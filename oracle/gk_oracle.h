@@ -46,6 +46,11 @@ const GkVoxelData* gko_probes_voxels(GkoScene* s);
 const GkPageIndex* gko_probes_pages(GkoScene* s);
 uint32_t gko_pack_rgb10a2(const float c[4]);
 void gko_unpack_rgb10a2(uint32_t packed, float out[4]);
+/* out: Position 3, Normal 3, Tangent.xyz 3, TexCoord 2, LocalNormal 3, LocalTangent 4; returns the material slot */
+uint32_t gko_get_material_data(GkoScene* s, uint32_t node_plus1, uint32_t prim, const float ro[3], const float rd[3], float out[18]);
+uint32_t gko_fetch_material_id(GkoScene* s, uint32_t node, uint32_t offset);
+void gko_mikktspace(const float vnt[3], const float n[3], const float t[4], float out[3]);
+float gko_calculate_weight(float centerDist, int sameObject, int isCenter, const float n[3], const float cn[3]);
 uint32_t gko_lerp_packed_color_alt(uint32_t c0, const float c1[4], float t);
 void gko_sample_ambient_cube(int which, const uint32_t cube14[14], const float n[3], float out[4]); /* 0 DI, 2 Full */
 void gko_sample_ibl_rough(GkoScene* s, uint32_t id, const float dir[3], float rotate, float out[4]);

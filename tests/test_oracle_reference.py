@@ -285,3 +285,74 @@ def test_probe_colour_format_and_samplers_are_pinned_to_the_references_source():
             a, b = f4(), f4()
             ref.ref_sample_ambient_cube(which, cube, f3(*n), a); L.gko_sample_ambient_cube(which, cube, f3(*n), b)
             assert bits(a) == bits(b), (which, list(a), list(b))
+
+
+REF_GF = os.path.join(os.path.dirname(O.TINYBVH), "libref_general_func.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GF), reason="oracle/_ref not built (reference not mounted)")
+def test_hit_attribute_reconstruction_is_pinned_to_the_references_source():
+    """Common.get_material_dataV2 (with UnpackVertexV2 inside), FetchMaterialId, mikkTSpace and
+    calculateWeight compiled from the reference's files as C++ (oracle/ref_general_func.cpp) against the oracle, on the real vertex / index /
+    node buffers of both procedural scenes: every output float bit-exact (world-space tangents to 1 ulp-scale 2e-7: the oracle does not
+    use them, it normalises them separately)."""
+    import ctypes as C
+    from gknextengine_b200 import host
+    ref, L = C.CDLL(REF_GF), O.load()
+    f18, f3, f4 = C.c_float * 18, C.c_float * 3, C.c_float * 4
+    ref.ref_get_material_data.restype = C.c_uint32
+    ref.ref_get_material_data.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(f3), C.POINTER(f3), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(f18)]
+    L.gko_get_material_data.restype = C.c_uint32
+    L.gko_get_material_data.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(f3), C.POINTER(f3), C.POINTER(f18)]
+    ref.ref_fetch_material_id.restype = L.gko_fetch_material_id.restype = C.c_uint32
+    ref.ref_fetch_material_id.argtypes = [C.c_void_p, C.c_uint32]
+    L.gko_fetch_material_id.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    ref.ref_mikktspace.argtypes = L.gko_mikktspace.argtypes = [C.POINTER(f3), C.POINTER(f3), C.POINTER(f4), C.POINTER(f3)]
+    ref.ref_calculate_weight.restype = L.gko_calculate_weight.restype = C.c_float
+    ref.ref_calculate_weight.argtypes = L.gko_calculate_weight.argtypes = [C.c_float, C.c_int, C.c_int, C.POINTER(f3), C.POINTER(f3)]
+    bits = lambda a: np.array(a, dtype=np.float32).view(np.uint32)
+    rng = np.random.default_rng(31)
+    for name in ("CornellBox.proc", "RTIO.proc"):
+        scene = host.Scene(name, samples=1, bounces=4)
+        scene.update_nodes()
+        osc = O.OracleScene(scene)
+        d = scene.desc()
+        nodes, n_nodes = scene.nodes()
+        node_bytes = C.cast(nodes, C.c_void_p)
+        models = np.ctypeslib.as_array(C.cast(d.offsets, C.POINTER(C.c_uint32)), shape=(d.offset_count, 16))
+        for trial in range(1500):
+            ni = int(rng.integers(0, n_nodes))
+            model_id = nodes[ni].modelId
+            tri_count = int(models[model_id, 1]) // 3
+            if tri_count == 0:
+                continue
+            prim = int(rng.integers(0, tri_count))
+            ro = f3(*rng.uniform(-8, 8, 3)); rd_ = rng.normal(size=3); rd = f3(*(rd_ / np.linalg.norm(rd_)))
+            a, b = f18(), f18()
+            ma = ref.ref_get_material_data(ni + 1, prim, ro, rd, node_bytes, C.cast(d.offsets, C.c_void_p), C.cast(d.vertices, C.c_void_p), C.cast(d.indices, C.c_void_p), a)
+            mb = L.gko_get_material_data(osc._h, ni + 1, prim, ro, rd, b)
+            assert ma == mb
+            ba, bb = bits(a), bits(b)
+            keep = np.r_[0:6, 9:18]                      # Position, Normal, TexCoord, LocalNormal, LocalTangent
+            both_nan = np.isnan(np.array(a)) & np.isnan(np.array(b))  # degenerate ray / triangle pairs: 1/0 -> inf/NaN identically
+            assert ((ba == bb) | both_nan)[keep].all(), (name, ni, prim, list(a), list(b))
+            ta, tb = np.array(a)[6:9], np.array(b)[6:9]
+            assert both_nan[6:9].all() or np.abs(ta - tb).max() <= 2e-7
+            for off in (0, 3, 15, 16, 40):
+                node_ptr = C.c_void_p(node_bytes.value + ni * 208)
+                assert ref.ref_fetch_material_id(node_ptr, off) == L.gko_fetch_material_id(osc._h, ni, off)
+    for trial in range(3000):
+        vnt, n, t = f3(*rng.uniform(0, 1, 3)), f3(*rng.normal(size=3)), f4(*rng.normal(size=3), float(rng.choice([0.0, 2.0])))
+        a, b = f3(), f3()
+        ref.ref_mikktspace(vnt, n, t, a); L.gko_mikktspace(vnt, n, t, b)
+        assert (bits(a) == bits(b)).all()
+        nn, cn = rng.normal(size=3), rng.normal(size=3)
+        nn /= np.linalg.norm(nn)
+        cn = nn + cn * float(rng.choice([0.0, 0.02, 0.2, 1.0]))
+        cn /= np.linalg.norm(cn)
+        dist = float(rng.uniform(0, 8))
+        for same in (0, 1):
+            for centre in (0, 1):
+                wa = ref.ref_calculate_weight(dist, same, centre, f3(*nn), f3(*cn))
+                wb = L.gko_calculate_weight(dist, same, centre, f3(*nn), f3(*cn))
+                assert bits([wa])[0] == bits([wb])[0]
