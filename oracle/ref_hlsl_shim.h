@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <utility>
 
 #undef M_PI
 #undef M_PI_2
@@ -27,6 +28,8 @@ struct float2 {
     float2() : x(0), y(0) {}
     float2(float v) : x(v), y(v) {}
     float2(float a, float b) : x(a), y(b) {}
+    template <class V, class = decltype(std::declval<V>().xy)>
+    explicit float2(const V& v) : x((float)v.x), y((float)v.y) {}  // float2(int2)
     float2& operator+=(float2 o) { x += o.x; y += o.y; return *this; }
 };
 inline float2 operator+(float2 a, float2 b) { return float2(a.x + b.x, a.y + b.y); }
@@ -37,11 +40,14 @@ inline float2 operator*(float a, float2 b) { return float2(a * b.x, a * b.y); }
 inline float2 operator*(float2 a, float b) { return float2(a.x * b, a.y * b); }
 inline float length(float2 a) { return sqrt(a.x * a.x + a.y * a.y); }
 
+struct float3;
+struct float3rgb { float x, y, z; inline operator float3() const; };  // `.rgb` of a float3
 struct float3 {
     union {
         struct { float x, y, z; };
         struct { float r, g, b; };
         float2 xy;
+        float3rgb rgb;
     };
     float3() : x(0), y(0), z(0) {}
     float3(float a, float b_, float c) : x(a), y(b_), z(c) {}
@@ -49,6 +55,7 @@ struct float3 {
     explicit float3(float v) : x(v), y(v), z(v) {}
     float3& operator*=(float s) { x *= s; y *= s; z *= s; return *this; }
 };
+inline float3rgb::operator float3() const { return float3(x, y, z); }
 inline float3 operator+(float3 a, float3 b) { return float3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline float3 operator+(float a, float3 b) { return float3(a + b.x, a + b.y, a + b.z); }
 inline float3 operator*(float3 a, float3 b) { return float3(a.x * b.x, a.y * b.y, a.z * b.z); }
@@ -70,6 +77,9 @@ struct float4 {
         struct { float x, y, z, w; };
         struct { float r, g, b, a; };
         float3 xyz;
+        float3 rgb;
+        float2 xy;
+        float2 rg;
     };
     float4() : x(0), y(0), z(0), w(0) {}
     float4(float v) : x(v), y(v), z(v), w(v) {}
@@ -117,7 +127,6 @@ struct half4 {
     operator float4() const { return float4((float)x, (float)y, (float)z, (float)w); }
 };
 inline uint16_t asuint16(half h) { return h.bits; }
-struct int2 { int x, y; };
 
 struct float3x3 {
     float3 row[3];
@@ -140,11 +149,17 @@ struct uint4 {
     };
     uint4() : x(0), y(0), z(0), w(0) {}
     uint4(uint a, uint b, uint c, uint d) : x(a), y(b), z(c), w(d) {}
+    explicit uint4(uint v) : x(v), y(v), z(v), w(v) {}
 };
 inline uint4 operator*(uint4 a, uint s) { return uint4(a.x * s, a.y * s, a.z * s, a.w * s); }
 inline uint4 operator+(uint4 a, uint s) { return uint4(a.x + s, a.y + s, a.z + s, a.w + s); }
 inline uint4 operator>>(uint4 a, uint s) { return uint4(a.x >> s, a.y >> s, a.z >> s, a.w >> s); }
 inline uint4 operator^(uint4 a, uint4 b) { return uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w); }
+struct bool4 { bool x, y, z, w; };
+inline bool any(bool4 b) { return b.x || b.y || b.z || b.w; }
+inline uint4 splat4(uint v) { return uint4(v, v, v, v); }
+inline bool4 operator!=(uint4 a, uint4 b) { return bool4{a.x != b.x, a.y != b.y, a.z != b.z, a.w != b.w}; }
+inline bool4 operator==(uint4 a, uint4 b) { return bool4{a.x == b.x, a.y == b.y, a.z == b.z, a.w == b.w}; }
 inline float asfloat(uint v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline float2 asfloat(uint2 v) { return float2(asfloat(v.x), asfloat(v.y)); }
 

@@ -356,3 +356,69 @@ def test_hit_attribute_reconstruction_is_pinned_to_the_references_source():
                 wa = ref.ref_calculate_weight(dist, same, centre, f3(*nn), f3(*cn))
                 wb = L.gko_calculate_weight(dist, same, centre, f3(*nn), f3(*cn))
                 assert bits([wa])[0] == bits([wb])[0]
+
+
+REF_ST = os.path.join(os.path.dirname(O.TINYBVH), "libref_stencils.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ST), reason="oracle/_ref not built (reference not mounted)")
+@pytest.mark.parametrize("W,H", [(67, 45), (64, 40)])
+def test_reproject_and_denoise_shaders_are_pinned_to_the_references_source(W, H):
+    """the reference's Process.ReProject.comp.slang and Process.DenoiseJBF.comp.slang compiled as C++ from the files
+    where they lie (oracle/ref_stencils.cpp: storage images in the reference's formats, an 8 x 8 thread group with a real barrier for the
+    groupshared tile) and run on random storage images, against the oracle's ReProjectPixel / DenoisePixel. ACCUM_* must be bit-identical in
+    every mode (temporal with 16 and 1 frames, progressive, fast reproject); RT_DENOISED bit-identical as well, SDR and HDR - both sides use
+    this machine's libm for exp / pow."""
+    import ctypes as C
+    from gknextengine_b200 import RT, GkcuFrameParams, host
+    ref = C.CDLL(REF_ST)
+    ref.ref_reproject.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    ref.ref_denoise.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(23)
+
+    def rnd16(hi=4.0):
+        return rng.uniform(0, hi, (H, W, 4)).astype(np.float16)
+
+    ids0 = rng.integers(0, 4, (H, W)).astype(np.uint32)
+    ids0[rng.uniform(size=(H, W)) < 0.05] = 65535
+    ids1 = np.where(rng.uniform(size=(H, W)) < 0.8, ids0, rng.integers(0, 4, (H, W))).astype(np.uint32)
+    nrm = rng.normal(size=(H, W, 4)).astype(np.float32)
+    nrm[..., :3] /= np.linalg.norm(nrm[..., :3], axis=2, keepdims=True)
+    nrm[::2] = np.float32([0, 1, 0, 0.3])
+    light = rnd16(); light[5:9, 7:12, :3] = 2000.0   # a light source: the bilateral weights underflow around it (NaN pixels must match too)
+    images = {
+        "SINGLE_DIFFUSE": light, "SINGLE_SPECULAR": rnd16(), "ALBEDO": rnd16(1.0), "NORMAL": nrm.astype(np.float16),
+        "SINGLE_PREV_DIFFUSE": rnd16(), "SINGLE_PREV_SPECULAR": rnd16(), "SINGLE_PREV_ALBEDO": rnd16(1.0),
+        "OBJEDCTID_0": ids0, "OBJEDCTID_1": ids1,
+        "MOTIONVECTOR": np.where(rng.uniform(size=(H, W, 1)) < 0.5, 0, rng.uniform(-6, 6, (H, W, 2))).astype(np.float32),
+        "MOTIONMOMENT": (rng.uniform(size=(H, W)) < 0.1).astype(np.uint16) * 3,
+    }
+    ofr = O.OracleFrame(W, H)
+    for mode in (dict(progressive=0, temporal_frames=16), dict(progressive=0, temporal_frames=1), dict(progressive=1, temporal_frames=16),
+                 dict(progressive=0, temporal_frames=8, fast_reproject=1)):
+        for hdr in (False, True):
+            scene = host.Scene("CornellBox.proc", denoiser=True, hdr=hdr)
+            ubo = scene.ubo(W, H, 1)
+            p = GkcuFrameParams(spp_world=1, **mode)
+            # reference side: its own copies of every image, ACCUM_* seeded with PREV_* (the state the copy pass leaves behind)
+            mine = {k: v.copy() for k, v in images.items()}
+            for acc, prev in (("ACCUMLATE_DIFFUSE", "SINGLE_PREV_DIFFUSE"), ("ACCUMLATE_SPECULAR", "SINGLE_PREV_SPECULAR"), ("ACCUMLATE_ALBEDO", "SINGLE_PREV_ALBEDO")):
+                mine[acc] = images[prev].copy()
+            mine["DENOISED"] = np.zeros((H, W, 4), np.float16)
+            table = (C.c_void_p * 32)()
+            for k, v in mine.items():
+                table[RT[k]] = v.ctypes.data
+            ref.ref_reproject(table, W, H, mode.get("progressive", 0), mode["temporal_frames"], mode.get("fast_reproject", 0))
+            ref.ref_denoise(table, W, H, C.cast(C.byref(ubo), C.c_void_p))
+            # oracle side
+            for k, v in images.items():
+                ofr.image(RT[k])[...] = v
+            for acc, prev in (("ACCUMLATE_DIFFUSE", "SINGLE_PREV_DIFFUSE"), ("ACCUMLATE_SPECULAR", "SINGLE_PREV_SPECULAR"), ("ACCUMLATE_ALBEDO", "SINGLE_PREV_ALBEDO")):
+                ofr.image(RT[acc])[...] = images[prev]
+            ofr.reproject(p)
+            ofr.denoise(ubo)
+            for name in ("ACCUMLATE_DIFFUSE", "ACCUMLATE_SPECULAR", "ACCUMLATE_ALBEDO", "DENOISED"):
+                a, b = mine[name].view(np.uint16), ofr.image(RT[name]).view(np.uint16)
+                bad = (a != b).any(axis=2)
+                assert not bad.any(), (name, mode, hdr, int(bad.sum()), np.argwhere(bad)[:3].tolist())
+    assert np.isnan(mine["DENOISED"].astype(np.float32)).any()  # the light's neighbourhood: 0 / 0 in the reference's arithmetic, reproduced
