@@ -1729,6 +1729,40 @@ void gko_sample_ibl_rough(GkoScene* s, uint32_t id, const float dir[3], float ro
     f4 c = s->SampleIBLRough(id, F3(dir[0], dir[1], dir[2]), rotate); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
 }
 
+// ---- services for oracle/ref_pathtrace.cpp (see gk_oracle.h)
+void gko_scene_arrays(GkoScene* s, GkoSceneArrays* out) {
+    out->nodes = s->nodes.data(); out->offsets = s->offsets.data(); out->vertices = s->vertices.data(); out->indices = s->indices.data();
+    out->materials = s->materials.data(); out->material_count = (uint32_t)s->materials.size(); out->node_count = (uint32_t)s->nodes.size();
+    out->cubes = s->cubes.empty() ? nullptr : s->cubes.data(); out->voxels = s->voxels.empty() ? nullptr : s->voxels.data();
+}
+void gko_trace_one(GkoScene* s, const GkcuRay* r, GkcuHit* hit, uint32_t any_hit) {
+    if (any_hit) {
+        bool occ = s->occluded(F3(r->ox, r->oy, r->oz), F3(r->dx, r->dy, r->dz), r->tmin, r->tmax);
+        *hit = {0, 0, 0, occ ? 0u : 0xFFFFFFFFu, 0};
+    } else {
+        Hit h = s->closest(F3(r->ox, r->oy, r->oz), F3(r->dx, r->dy, r->dz), r->tmin, r->tmax);
+        *hit = {h.t, h.u, h.v, h.inst, h.prim};
+    }
+}
+void gko_interpolate_ambient_cubes(GkoScene* s, int which, const float pos[3], const float n[3], float out[4]) {
+    f4 c = s->interpolateAmbientCubesT(F3(pos[0], pos[1], pos[2]), F3(n[0], n[1], n[2]), which == 0, nullptr, 0, 0);
+    out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
+void gko_instance_w2o(GkoScene* s, uint32_t inst, float out[12]) { std::memcpy(out, s->instances[inst].w2o, 48); }
+void gko_sample_texture(GkoScene* s, uint32_t id, float u, float v, float out[4]) { f4 c = s->sample_texture(id, f2{u, v}); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w; }
+void gko_cast_visibility(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t* packed) {
+    GkoFrame F;
+    F.w = w; F.h = h;
+    Renderer R(*s, F, *ubo);
+    const f4 origin = mul(ubo->ModelViewInverse, F4(0, 0, 0, 1));
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            uint32_t node1, prim;
+            R.CastVisibility((int)x, (int)y, xyz(origin), node1, prim);
+            packed[(size_t)y * w + x] = (node1 << 17) | (prim & 0x1FFFFu);
+        }
+}
+
 GkoFrame* gko_frame_create(uint32_t w, uint32_t h) {
     GkoFrame* f = new GkoFrame();
     f->w = w;

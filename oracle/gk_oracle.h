@@ -4,15 +4,23 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * library; the product (libgknext_cuda.so, gknextengine_b200/) never links, imports or calls it.
  *
- * PARITY STATUS: "parity unpinned" for the shading chain. The reference has no tests, golden images or
- * known-answer vectors for this path and its implementation is Slang shader code behind
- * Vulkan ray queries, which cannot be compiled or run in this container (no slangc, no Vulkan). What IS pinned:
+ * PARITY STATUS: pinned against the reference's own shader text, compiled as C++ where it lies (oracle/Makefile target `ref`,
+ * outputs only into the git-ignored oracle/_ref/, compared bit for bit by tests/test_oracle_reference.py):
+ *   - the whole RT pass: Core.PathTracing + Util.BufferClear with the Shading.slang classes and interpolateAmbientCubesV2 they run
+ *     (oracle/ref_pathtrace.cpp), every written storage image and both ray counts bit-identical over frames with motion
+ *   - the reproject and denoise passes: Process.ReProject + Process.DenoiseJBF compiled whole (oracle/ref_stencils.cpp)
+ *   - the function library: Const_Func.slang, GeneralFunc.slang, UnpackVertexV2, FetchMaterialId, mikkTSpace, calculateWeight, the
+ *     probe colour format and samplers (oracle/ref_const_func.cpp, oracle/ref_general_func.cpp)
  *   - struct layouts, against the reference's own dual-language header compiled as C++ (oracle/ref_layout_check.cpp)
  *   - the ray/BVH intersector, against the reference's vendored tinybvh v1.3.8 compiled from
  *     /root/reference/src/ThirdParty/tinybvh/tiny_bvh.h into oracle/_ref/ (same oracle source, -DGKO_TINYBVH)
  *   - EvaluateSH / SampleIBL (the SH sky used by the probe bake), against the reference's dual-language GLSL header compiled as
  *     C++ from /root/reference/assets/shaders/glsl_legacy/common/SampleIBL.glsl into oracle/_ref/libref_sh.so (oracle/ref_sh.cpp)
  *   - fixture known-answers generated here with libstdc++, in tests/golden/.
+ * "Parity unpinned" remains true only for what is hardware or driver in the reference, not source: the Vulkan driver's
+ * ray/triangle rule, the raster pass behind the visibility buffer, the texture sampler and the GPU's transcendental intrinsics.
+ * The reference has no tests, golden images or known-answer vectors for this path, and it cannot run here
+ * (no slangc, no Vulkan).
  */
 #ifndef GK_ORACLE_H
 #define GK_ORACLE_H
@@ -53,6 +61,7 @@ void gko_mikktspace(const float vnt[3], const float n[3], const float t[4], floa
 float gko_calculate_weight(float centerDist, int sameObject, int isCenter, const float n[3], const float cn[3]);
 uint32_t gko_lerp_packed_color_alt(uint32_t c0, const float c1[4], float t);
 void gko_sample_ambient_cube(int which, const uint32_t cube14[14], const float n[3], float out[4]); /* 0 DI, 2 Full */
+void gko_interpolate_ambient_cubes(GkoScene* s, int which, const float pos[3], const float n[3], float out[4]); /* 0 DI, 2 Full */
 void gko_sample_ibl_rough(GkoScene* s, uint32_t id, const float dir[3], float rotate, float out[4]);
 
 GkoFrame* gko_frame_create(uint32_t width, uint32_t height);
@@ -98,6 +107,21 @@ void gko_random_in_cone(uint32_t seed[4], float cos_theta, float out[3]);
  * direct-term plane (rank 0 only, zero elsewhere). gko_resolve turns (summed) planes into SINGLE_DIFFUSE / SINGLE_SPECULAR. */
 float* gko_radiance(GkoFrame* f, size_t* floats);
 void gko_resolve(GkoFrame* f, const GkUniformBufferObject* ubo);
+
+/* Services for oracle/ref_pathtrace.cpp, which compiles the reference's path-tracing shader text as C++ and needs the parts of the
+ * pipeline that are hardware, not shader source: the ray query (this oracle's intersector), the bilinear texture sampler, and the
+ * visibility buffer the raster pass would have written. Serial, one element per call. */
+typedef struct GkoSceneArrays {
+    const GkNodeProxy* nodes; const GkModelData* offsets; const GkGPUVertex* vertices; const uint32_t* indices;
+    const GkMaterial* materials; uint32_t material_count, node_count;
+    const GkAmbientCube* cubes; const GkVoxelData* voxels; /* NULL until gko_set_probes / gko_probes_voxelize */
+} GkoSceneArrays;
+void gko_scene_arrays(GkoScene* s, GkoSceneArrays* out);
+void gko_trace_one(GkoScene* s, const GkcuRay* ray, GkcuHit* hit, uint32_t any_hit);
+void gko_instance_w2o(GkoScene* s, uint32_t inst, float out[12]); /* world-to-object, 3 rows x 4 columns */
+void gko_sample_texture(GkoScene* s, uint32_t id, float u, float v, float out[4]);
+/* packed[y*w+x] = ((node + 1) << 17) | primitive, 0 = no geometry: the RT_MINIGBUFFER texel format (Shading.slang:348-349) */
+void gko_cast_visibility(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t* packed);
 
 #ifdef __cplusplus
 }

@@ -16,10 +16,19 @@
 
 namespace ref {
 using std::abs;
+#ifndef REF_TRIG_FROM_ORACLE
 using std::cos;
+#endif
 using std::fma;
 using std::pow;
+#ifndef REF_TRIG_FROM_ORACLE
 using std::sin;
+#else
+// sin / cos are hardware intrinsics in the shader; the whole-pass pin gives them the oracle's pinned polynomial (gk_oracle.h)
+extern "C" void gko_det_sincos(float x, float* s, float* c);
+inline float sin(float x) { float s, c; gko_det_sincos(x, &s, &c); return s; }
+inline float cos(float x) { float s, c; gko_det_sincos(x, &s, &c); return c; }
+#endif
 using std::sqrt;
 typedef uint32_t uint;
 
@@ -41,13 +50,14 @@ inline float2 operator*(float2 a, float b) { return float2(a.x * b, a.y * b); }
 inline float length(float2 a) { return sqrt(a.x * a.x + a.y * a.y); }
 
 struct float3;
-struct float3rgb { float x, y, z; inline operator float3() const; };  // `.rgb` of a float3
+struct float3rgb { float x, y, z; inline operator float3() const; inline float3rgb& operator=(const float3& v); };  // `.rgb` of a float3
 struct float3 {
     union {
         struct { float x, y, z; };
         struct { float r, g, b; };
         float2 xy;
         float3rgb rgb;
+        float3rgb xyz;
     };
     float3() : x(0), y(0), z(0) {}
     float3(float a, float b_, float c) : x(a), y(b_), z(c) {}
@@ -56,6 +66,7 @@ struct float3 {
     float3& operator*=(float s) { x *= s; y *= s; z *= s; return *this; }
 };
 inline float3rgb::operator float3() const { return float3(x, y, z); }
+inline float3rgb& float3rgb::operator=(const float3& v) { x = v.x; y = v.y; z = v.z; return *this; }
 inline float3 operator+(float3 a, float3 b) { return float3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline float3 operator+(float a, float3 b) { return float3(a + b.x, a + b.y, a + b.z); }
 inline float3 operator*(float3 a, float3 b) { return float3(a.x * b.x, a.y * b.y, a.z * b.z); }
@@ -85,6 +96,7 @@ struct float4 {
     float4(float v) : x(v), y(v), z(v), w(v) {}
     float4(float a_, float b_, float c, float d) : x(a_), y(b_), z(c), w(d) {}
     float4(float3 v, float d) : x(v.x), y(v.y), z(v.z), w(d) {}
+    float4(float2 v, float c, float d) : x(v.x), y(v.y), z(c), w(d) {}
     float4& operator+=(float4 o) { x += o.x; y += o.y; z += o.z; w += o.w; return *this; }
     float4& operator*=(float s) { x *= s; y *= s; z *= s; w *= s; return *this; }
 };

@@ -15,127 +15,9 @@
 #include <thread>
 #include <vector>
 
-#include "ref_hlsl_shim.h"
+#include "ref_image_shim.h"
 
 namespace ref {
-using std::exp;
-using std::floor;
-
-// ---- more vector vocabulary
-struct int2;
-struct int2xy { int x, y; };
-struct int2 {
-    union {
-        struct { int x, y; };
-        int2xy xy;
-    };
-    int2() : x(0), y(0) {}
-    int2(int a, int b) : x(a), y(b) {}
-    int2(int2xy v) : x(v.x), y(v.y) {}
-    explicit int2(uint2 v) : x((int)v.x), y((int)v.y) {}
-    explicit int2(float2 v) : x((int)v.x), y((int)v.y) {}
-};
-inline int2 operator+(int2 a, int2 b) { return int2(a.x + b.x, a.y + b.y); }
-inline int2 operator+(int2xy a, int2 b) { return int2(a.x + b.x, a.y + b.y); }
-inline int2 operator+(int2 a, int b) { return int2(a.x + b, a.y + b); }
-inline int2 operator*(int2 a, int b) { return int2(a.x * b, a.y * b); }
-struct bool2 { bool x, y; };
-inline bool all(bool2 b) { return b.x && b.y; }
-// int < uint follows the usual arithmetic conversions (HLSL / Slang as C): the int operand becomes unsigned, so a negative coordinate fails
-inline bool2 operator<(int2 a, uint2 b) { return bool2{(uint)a.x < b.x, (uint)a.y < b.y}; }
-inline bool2 operator>=(int2 a, int2 b) { return bool2{a.x >= b.x, a.y >= b.y}; }
-struct uint3 {
-    union {
-        struct { uint x, y, z; };
-        uint2 xy;
-    };
-    uint3(uint a, uint b, uint c) : x(a), y(b), z(c) {}
-};
-inline uint2 yx(uint3 v) { return uint2{v.y, v.x}; }
-inline float2 to_float2(int2 v) { return float2((float)v.x, (float)v.y); }
-inline float2 floor(float2 v) { return float2(std::floor(v.x), std::floor(v.y)); }
-inline float2 frac(float2 v) { return float2(v.x - std::floor(v.x), v.y - std::floor(v.y)); }
-inline float length(float v) { return std::fabs(v); }
-inline float3 lerp(float3 a, float3 b, float t) { return a + (b - a) * t; }
-inline float3 clamp(float3 v, float lo, float hi) { return float3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
-inline int max(int a, int b) { return a > b ? a : b; }
-inline float3& operator+=(float3& a, float3 b) { a = a + b; return a; }
-inline float3& operator/=(float3& a, float s) { a = a / s; return a; }
-inline float4& operator/=(float4& a, float s) { a = a / s; return a; }
-
-// ---- storage images
-inline uint16_t f2h(float f) { _Float16 h = (_Float16)f; uint16_t b; std::memcpy(&b, &h, 2); return b; }  // round to nearest even
-inline float h2f(uint16_t b) { _Float16 h; std::memcpy(&h, &b, 2); return (float)h; }
-enum { FMT_F16X4 = 0, FMT_RG32F = 1 };
-struct ImgF4 {
-    uint8_t* base; int w, h, fmt;
-    bool inside(int x, int y) const { return x >= 0 && y >= 0 && x < w && y < h; }
-    float4 load(int x, int y) const {
-        if (!base || !inside(x, y)) return float4(0, 0, 0, 0);
-        if (fmt == FMT_RG32F) { const float* p = (const float*)base + ((size_t)y * w + x) * 2; return float4(p[0], p[1], 0.0f, 1.0f); }
-        const uint16_t* p = (const uint16_t*)base + ((size_t)y * w + x) * 4;
-        return float4(h2f(p[0]), h2f(p[1]), h2f(p[2]), h2f(p[3]));
-    }
-    void store(int x, int y, float4 v) {
-        if (!base || !inside(x, y) || fmt != FMT_F16X4) return;
-        uint16_t* p = (uint16_t*)base + ((size_t)y * w + x) * 4;
-        p[0] = f2h(v.x); p[1] = f2h(v.y); p[2] = f2h(v.z); p[3] = f2h(v.w);
-    }
-    struct RGB : float3 {  // value loaded when the texel is addressed; assignment is a read-modify-write that keeps alpha
-        ImgF4* img; int px, py;
-        RGB(ImgF4* i, int x, int y, float3 v) : float3(v), img(i), px(x), py(y) {}
-        RGB& operator=(float3 v) { float4 o = img->load(px, py); img->store(px, py, float4(v, o.w)); return *this; }
-    };
-    struct RG : float2 { RG(float2 v) : float2(v) {} };
-    struct Texel {
-        ImgF4* img; int px, py; float4 v;
-        RGB rgb; RG rg;
-        Texel(ImgF4* i, int x, int y) : img(i), px(x), py(y), v(i->load(x, y)), rgb(i, x, y, float3(v.x, v.y, v.z)), rg(float2(v.x, v.y)) {}
-        operator float4() const { return v; }
-        Texel& operator=(float4 n) { img->store(px, py, n); return *this; }
-    };
-    Texel operator[](int2 p) { return Texel(this, p.x, p.y); }
-};
-struct ImgU {
-    const uint8_t* base; int w, h, bytes;  // bytes per texel: 4 (R32_UINT) or 2 (R16_UINT)
-    struct Texel { uint r; operator uint() const { return r; } };
-    Texel operator[](int2 p) const {
-        if (!base || p.x < 0 || p.y < 0 || p.x >= w || p.y >= h) return Texel{0u};
-        const size_t i = (size_t)p.y * w + p.x;
-        return Texel{bytes == 4 ? ((const uint32_t*)base)[i] : (uint)((const uint16_t*)base)[i]};
-    }
-};
-template <class T> struct RWTexture2DSel;
-template <> struct RWTexture2DSel<float4> { typedef ImgF4 type; };
-template <> struct RWTexture2DSel<uint> { typedef ImgU type; };
-template <class T> using RWTexture2D = typename RWTexture2DSel<T>::type;
-
-// ---- the camera block: the reference's own BasicTypes.slang, as src/Assets/UniformBuffer.hpp:30-48 includes it into C++
-#define float4x4 float4x4
-#define half4 half4
-#define public
-#define bool uint32_t
-#include "BasicTypes.slang"
-#undef public
-#undef bool
-
-struct GpuSceneShim { UniformBufferObject* Camera; };
-struct BindlessShim {
-    // storage-image indices, assets/shaders/common/BindlessTexture.slang:8-30
-    static const int RT_ACCUMLATE_DIFFUSE = 0, RT_SINGLE_DIFFUSE = 1, RT_OBJEDCTID_0 = 3, RT_OBJEDCTID_1 = 4, RT_MOTIONVECTOR = 5, RT_ALBEDO = 6, RT_NORMAL = 7,
-                     RT_DENOISED = 9, RT_ACCUMLATE_SPECULAR = 11, RT_SINGLE_SPECULAR = 12, RT_ACCUMLATE_ALBEDO = 13, RT_MOTIONMOMENT = 14,
-                     RT_SINGLE_PREV_DIFFUSE = 20, RT_SINGLE_PREV_SPECULAR = 21, RT_SINGLE_PREV_ALBEDO = 22;
-    ImgF4 f4[32];
-    ImgU u[32];
-    GpuSceneShim scene;
-    template <class T> RWTexture2D<T> GetStorageTexture(int index);
-    template <class T> uint2 GetStorageTextureDimensions(int index) { return uint2{(uint)f4[index].w, (uint)f4[index].h}; }
-    GpuSceneShim& GetGpuscene() { return scene; }
-};
-template <> inline ImgF4 BindlessShim::GetStorageTexture<float4>(int index) { return f4[index]; }
-template <> inline ImgU BindlessShim::GetStorageTexture<uint>(int index) { return u[index]; }
-static BindlessShim Bindless;
-
 // ---- a thread group for GroupMemoryBarrierWithGroupSync()
 static std::barrier<>* g_group_barrier = nullptr;
 inline void GroupMemoryBarrierWithGroupSync() { g_group_barrier->arrive_and_wait(); }
@@ -157,9 +39,9 @@ static void bind(void* const* images, int w, int h) {
     const int f16[] = {0, 1, 6, 7, 9, 11, 12, 13, 20, 21, 22};
     for (int i : f16) Bindless.f4[i] = ImgF4{(uint8_t*)images[i], w, h, FMT_F16X4};
     Bindless.f4[5] = ImgF4{(uint8_t*)images[5], w, h, FMT_RG32F};
-    Bindless.u[3] = ImgU{(const uint8_t*)images[3], w, h, 4};
-    Bindless.u[4] = ImgU{(const uint8_t*)images[4], w, h, 4};
-    Bindless.u[14] = ImgU{(const uint8_t*)images[14], w, h, 2};
+    Bindless.u[3] = ImgU{(uint8_t*)images[3], w, h, 4};
+    Bindless.u[4] = ImgU{(uint8_t*)images[4], w, h, 4};
+    Bindless.u[14] = ImgU{(uint8_t*)images[14], w, h, 2};
 }
 
 extern "C" {

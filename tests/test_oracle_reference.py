@@ -422,3 +422,123 @@ def test_reproject_and_denoise_shaders_are_pinned_to_the_references_source(W, H)
                 bad = (a != b).any(axis=2)
                 assert not bad.any(), (name, mode, hdr, int(bad.sum()), np.argwhere(bad)[:3].tolist())
     assert np.isnan(mine["DENOISED"].astype(np.float32)).any()  # the light's neighbourhood: 0 / 0 in the reference's arithmetic, reproduced
+
+
+REF_PT = os.path.join(os.path.dirname(O.TINYBVH), "libref_pathtrace.so")
+
+
+def _ref_pathtrace_lib():
+    import ctypes as C
+    ref = C.CDLL(REF_PT)
+    ref.ref_pathtrace.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    ref.ref_interpolate_ambient_cubes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    return ref
+
+
+def _random_probe_grid(osc, scene, rng):
+    """Real voxel distances (the oracle's voxeliser, pinned through the GPU parity tests and the CPU bake tests) under random packed colours."""
+    osc.set_lights(scene)
+    osc.probes_voxelize()
+    cubes, vox, _ = osc.probes_read()
+    words = cubes.view(np.uint32).reshape(len(cubes), -1)
+    words[...] = rng.integers(0, 2**32, words.shape, dtype=np.uint64).astype(np.uint32)
+    osc.set_probes(cubes, vox)
+    return cubes, vox
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PT), reason="oracle/_ref not built (reference not mounted)")
+def test_probe_lookup_is_pinned_to_the_references_source():
+    """interpolateAmbientCubesV2<Full | DI> (AmbientCube.slang:290-382) compiled as C++ from the file where it lies, against
+    the oracle's interpolateAmbientCubesT on the voxelised Cornell box with random probe colours: points inside and outside the grid, on
+    cell boundaries, next to walls (occluded probes) and in free space."""
+    import ctypes as C
+    ref = _ref_pathtrace_lib()
+    scene = host.Scene("CornellBox.proc", samples=1, bounces=4)
+    scene.update_nodes()
+    osc = O.OracleScene(scene)
+    rng = np.random.default_rng(3)
+    cubes, vox = _random_probe_grid(osc, scene, rng)
+    L = osc.L
+    L.gko_interpolate_ambient_cubes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    pts = np.concatenate([rng.uniform((-3.2, -0.5, -3.2), (3.2, 6.0, 3.2), (4000, 3)), rng.uniform(-30, 30, (300, 3)),
+                          np.round(rng.uniform((-3, 0, -3), (3, 5.5, 3), (300, 3)) * 4) / 4 + np.float32([0, -0.375 + 0.03125, 0])]).astype(np.float32)
+    nrm = rng.normal(size=(len(pts), 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[::7] = np.float32([0, 1, 0])
+    a, b = (C.c_float * 4)(), (C.c_float * 4)()
+    nonzero = 0
+    for which in (0, 2):
+        for p, n in zip(pts, nrm):
+            pp, nn = (C.c_float * 3)(*p), (C.c_float * 3)(*n)
+            ref.ref_interpolate_ambient_cubes(which, cubes.ctypes.data, vox.ctypes.data, pp, nn, a)
+            L.gko_interpolate_ambient_cubes(osc._h, which, pp, nn, b)
+            assert np.array_equal(np.float32(list(a)).view(np.uint32), np.float32(list(b)).view(np.uint32)), (which, p, n, list(a), list(b))
+            nonzero += any(a[:3])
+    assert nonzero > 2000
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PT), reason="oracle/_ref not built (reference not mounted)")
+@pytest.mark.parametrize("name,setup", [("CornellBox.proc", "textures"), ("RTIO.proc", "sky+sun+aperture"), ("CornellBox.proc", "fastgather")])
+def test_rt_pass_is_pinned_to_the_references_source(name, setup):
+    """the reference's Core.PathTracing.comp.slang and Util.BufferClear.comp.slang compiled whole as C++, with
+    the classes of Shading.slang they run (FVisibilityBufferRayCasterV2, FHardwareRayTracerV2, FHardwareDirectIlluminatorV2,
+    FPathTracingRendererV2, CalculateMotionVectorV2, FetchGBufferV2, SampleIBLV2) and interpolateAmbientCubesV2, against the oracle's RT pass.
+    The ray query, the texture sampler and the visibility buffer are the oracle's (they are hardware in the reference, not shader text; see
+    oracle/ref_pathtrace.cpp), so what is pinned is the integrator: control flow, RNG order, shading arithmetic and every image store. Every
+    storage image the pass writes must be bit-identical over three frames with moving geometry, and so must the ray counts."""
+    import ctypes as C
+    ref = _ref_pathtrace_lib()
+    W, H = 52, 30  # not a multiple of the 8 x 8 group: out-of-range threads run and their stores are dropped
+    rng = np.random.default_rng(5)
+    scene = host.Scene(name, samples=3, bounces=4, taa=True, fast_gather=(setup == "fastgather"))
+    sky = None
+    if "sky" in setup:
+        scene.env(has_sky=True, has_sun=True)
+        sky = host.make_sky(64, 32)
+    scene.update_nodes()
+    osc, ofr = O.OracleScene(scene, sky), O.OracleFrame(W, H)
+    _random_probe_grid(osc, scene, rng)
+    if setup == "textures":
+        nrm = rng.normal(size=(32, 32, 3)) * 0.35 + np.array([0, 0, 1.0])
+        nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+        for idx, tex in ((1, rng.uniform(0.2, 1.0, (16, 16, 4))), (2, rng.uniform(0.0, 1.0, (8, 32, 4))), (3, np.concatenate([nrm * 0.5 + 0.5, np.ones((32, 32, 1))], axis=2))):
+            osc.set_sky(idx, tex.astype(np.float32))
+        mats, nm = scene.materials()
+        for i in range(nm):
+            if mats[i].MaterialModel != 4:
+                mats[i].DiffuseTextureId, mats[i].MRATextureId, mats[i].NormalTextureId = 1, 2, 3
+                mats[i].Fuzziness = 0.8
+                mats[i].Metalness = 0.5 if i % 2 else 0.0
+        osc.L.gko_update_materials(osc._h, mats, nm)
+    osc.L.gko_cast_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    mine = {"SINGLE_DIFFUSE": np.full((H, W, 4), 7, np.float16), "SINGLE_SPECULAR": np.full((H, W, 4), 7, np.float16), "ALBEDO": np.zeros((H, W, 4), np.float16),
+            "NORMAL": np.zeros((H, W, 4), np.float16), "OBJEDCTID_0": np.zeros((H, W), np.uint32), "MOTIONVECTOR": np.zeros((H, W, 2), np.float32),
+            "PREV_DEPTHBUFFER": np.zeros((H, W), np.float32), "MOTIONMOMENT": np.zeros((H, W), np.uint16), "MINIGBUFFER": np.zeros((H, W), np.uint32)}
+    table = (C.c_void_p * 64)()  # [32 + rt] = optional fp32 shadow images (diagnostics), unused here
+    for k, v in mine.items():
+        table[RT[k]] = v.ctypes.data
+    p = GkcuFrameParams(temporal_frames=16, spp_world=1)
+    counters = (C.c_uint64 * 2)()
+    moved = False
+    for f in range(1, 4):
+        if f == 2:  # move the scene between frames: motion vectors and the motion-moment counter (4 x samples on moving pixels)
+            scene.jitter_instances(f, 0.6)
+            scene.update_nodes()
+            osc.update_nodes(scene)
+        ubo = scene.ubo(W, H, f, model_rotation_deg=4.0 * f)
+        if "aperture" in setup:
+            ubo.Aperture, ubo.FocusDistance = 0.4, 6.0
+        osc.L.gko_cast_visibility(osc._h, C.byref(ubo), W, H, mine["MINIGBUFFER"].ctypes.data)
+        ref.ref_pathtrace(osc._h, C.byref(ubo), table, W, H, counters)
+        ofr.render(osc, ubo, p, run_post=False)
+        for k in ("OBJEDCTID_0", "MOTIONMOMENT", "ALBEDO", "NORMAL", "MOTIONVECTOR", "PREV_DEPTHBUFFER", "SINGLE_DIFFUSE", "SINGLE_SPECULAR"):
+            a, b = mine[k], ofr.image(RT[k])
+            ua, ub = a.view(np.uint16 if a.dtype.itemsize == 2 else np.uint32), b.view(np.uint16 if b.dtype.itemsize == 2 else np.uint32)
+            bad = (ua != ub).reshape(H, W, -1).any(axis=2)
+            assert not bad.any(), (k, f, int(bad.sum()), np.argwhere(bad)[:3].tolist(), a[bad][:2].tolist(), b[bad][:2].tolist())
+        c = ofr.counters()
+        assert (counters[0], counters[1]) == (c["closest"], c["any"]), (f, list(counters), c)
+        moved |= bool(mine["MOTIONMOMENT"].any())
+        assert counters[0] > W * H and (counters[1] > W * H // 4) == ("sun" in setup)  # sun shadow rays only where there is a sun
+        assert np.isfinite(mine["SINGLE_DIFFUSE"].astype(np.float32)).all() and mine["SINGLE_DIFFUSE"].astype(np.float32).max() > 0.05
+    assert moved and (mine["OBJEDCTID_0"] != 65535).mean() > 0.3
