@@ -1734,6 +1734,7 @@ void gko_scene_arrays(GkoScene* s, GkoSceneArrays* out) {
     out->nodes = s->nodes.data(); out->offsets = s->offsets.data(); out->vertices = s->vertices.data(); out->indices = s->indices.data();
     out->materials = s->materials.data(); out->material_count = (uint32_t)s->materials.size(); out->node_count = (uint32_t)s->nodes.size();
     out->cubes = s->cubes.empty() ? nullptr : s->cubes.data(); out->voxels = s->voxels.empty() ? nullptr : s->voxels.data();
+    out->lights = s->lights.data(); out->light_count = (uint32_t)s->lights.size(); out->sky_sh = s->sky_sh.data(); out->sky_sh_count = (uint32_t)s->sky_sh.size();
 }
 void gko_trace_one(GkoScene* s, const GkcuRay* r, GkcuHit* hit, uint32_t any_hit) {
     if (any_hit) {

@@ -8,6 +8,7 @@
  * outputs only into the git-ignored oracle/_ref/, compared bit for bit by tests/test_oracle_reference.py):
  *   - the whole RT pass: Core.PathTracing + Util.BufferClear with the Shading.slang classes and interpolateAmbientCubesV2 they run
  *     (oracle/ref_pathtrace.cpp), every written storage image and both ray counts bit-identical over frames with motion
+ *   - the probe bake: Bake.HwAmbientCube with FGpuProbeGenerator, EvaluateSH / SampleIBLRough (same file), cubes and ages bit-identical
  *   - the reproject and denoise passes: Process.ReProject + Process.DenoiseJBF compiled whole (oracle/ref_stencils.cpp)
  *   - the function library: Const_Func.slang, GeneralFunc.slang, UnpackVertexV2, FetchMaterialId, mikkTSpace, calculateWeight, the
  *     probe colour format and samplers (oracle/ref_const_func.cpp, oracle/ref_general_func.cpp)
@@ -115,6 +116,7 @@ typedef struct GkoSceneArrays {
     const GkNodeProxy* nodes; const GkModelData* offsets; const GkGPUVertex* vertices; const uint32_t* indices;
     const GkMaterial* materials; uint32_t material_count, node_count;
     const GkAmbientCube* cubes; const GkVoxelData* voxels; /* NULL until gko_set_probes / gko_probes_voxelize */
+    const GkLightObject* lights; const GkSphericalHarmonics* sky_sh; uint32_t light_count, sky_sh_count;
 } GkoSceneArrays;
 void gko_scene_arrays(GkoScene* s, GkoSceneArrays* out);
 void gko_trace_one(GkoScene* s, const GkcuRay* ray, GkcuHit* hit, uint32_t any_hit);

@@ -155,6 +155,9 @@ struct GpuSceneShim {
     ModelData* Offsets;
     AmbientCube* Cubes;
     VoxelData* Voxels;
+    LightObject* Lights;
+    SphericalHarmonics* HDRSHs;
+    uint custom_data_0;
     void* TLAS;
     RaytracingAccelerationStructure GetTLAS() { return RaytracingAccelerationStructure{TLAS}; }
 };

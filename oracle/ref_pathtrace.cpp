@@ -2,6 +2,8 @@
 // RT pass can be pinned against the reference's own text:
 //   assets/shaders/Core.PathTracing.comp.slang   whole file: main
 //   assets/shaders/Util.BufferClear.comp.slang   whole file: main
+//   assets/shaders/Bake.HwAmbientCube.comp.slang whole file: main (the probe bake), with FGpuProbeGenerator
+//                                                (AmbientCube.slang:470-692), the sample grids (17-57), EvaluateSH + SampleIBLRough (Shading.slang:146-192)
 //   assets/shaders/common/Shading.slang          the trace distances (15-18), CalculateMotionVectorV2 (50-72), FetchGBufferV2 (82-112),
 //                                                SampleIBLV2 (194-199), FVisibilityBufferRayCasterV2 (336-495), FHardwareRayTracerV2
 //                                                (735-827), FHardwareDirectIlluminatorV2 (886-908), FPathTracingRendererV2 (995-1261)
@@ -126,8 +128,17 @@ struct IDirectIlluminator {
 #include "ambient_lookup_gen.inc"
 template <int FLAGS> uint RayQuery<FLAGS>::CommittedRayInstanceCustomIndex() const { return Bindless.GetGpuscene().Nodes[h.inst].instanceId; }
 #include "shading_gen.inc"
+struct IProbeGenerator {  // AmbientCube.slang:464-468
+    virtual void Render(IRayTracer& tracer, float3 origin, uint CubeIdx, uint4& RandomSeed) = 0;
+    virtual void RenderAmbientCubeOnly(IRayTracer& tracer, float3 origin, uint CubeIdx, uint4& RandomSeed) = 0;
+};
+inline float lerp(float a, float b, float t) { return a + (b - a) * t; }
+#include "probe_bake_gen.inc"
 namespace pathtracing {
 #include "pathtracing_gen.inc"
+}
+namespace bake {
+#include "bake_gen.inc"
 }
 namespace bufferclear {
 #include "bufferclear_gen.inc"
@@ -171,6 +182,35 @@ void ref_pathtrace(GkoScene* scene, const void* ubo, void* const* images, int w,
         for (int x = 0; x < (w + 7) / 8 * 8; ++x) bufferclear::bufferclear_main(uint3((uint)x, (uint)y, 0u));
     for (int y = 0; y < (h + 7) / 8 * 8; ++y)
         for (int x = 0; x < (w + 7) / 8 * 8; ++x) pathtracing::pathtracing_main(uint3((uint)x, (uint)y, 0u));
+    counters[0] = g_closest;
+    counters[1] = g_any;
+    S.Camera = nullptr;
+}
+
+// Bake.HwAmbientCube.comp.slang over probes [first, first + count) of caller-provided probe arrays (updated in place), one thread after the
+// other in index order (SceneList / Scene.cpp dispatches it with custom_data_0 = first)
+void ref_probes_bake(GkoScene* scene, const void* ubo, void* cubes, void* voxels, uint32_t first, uint32_t count, uint64_t* counters) {
+    g_scene = scene;
+    g_closest = g_any = 0;
+    UniformBufferObject cam;
+    std::memcpy(&cam, ubo, sizeof(cam));
+    GkoSceneArrays a;
+    gko_scene_arrays(scene, &a);
+    GpuSceneShim& S = Bindless.scene;
+    S.Camera = &cam;
+    S.Nodes = (NodeProxy*)a.nodes;
+    S.Vertices = (GPUVertex*)a.vertices;
+    S.Indices = (uint*)a.indices;
+    S.Materials = (Material*)a.materials;
+    S.Offsets = (ModelData*)a.offsets;
+    S.Lights = (LightObject*)a.lights;
+    S.HDRSHs = (SphericalHarmonics*)a.sky_sh;
+    S.Cubes = (AmbientCube*)cubes;
+    S.Voxels = (VoxelData*)voxels;
+    S.TLAS = scene;
+    S.custom_data_0 = first;
+    static_assert(sizeof(LightObject) == 80 && sizeof(SphericalHarmonics) == 112 && sizeof(AmbientCube) == 56, "reference layouts");
+    for (uint32_t i = 0; i < count; ++i) bake::bake_main(uint3(i, 0u, 0u));
     counters[0] = g_closest;
     counters[1] = g_any;
     S.Camera = nullptr;

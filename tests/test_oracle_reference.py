@@ -542,3 +542,58 @@ def test_rt_pass_is_pinned_to_the_references_source(name, setup):
         assert counters[0] > W * H and (counters[1] > W * H // 4) == ("sun" in setup)  # sun shadow rays only where there is a sun
         assert np.isfinite(mine["SINGLE_DIFFUSE"].astype(np.float32)).all() and mine["SINGLE_DIFFUSE"].astype(np.float32).max() > 0.05
     assert moved and (mine["OBJEDCTID_0"] != 65535).mean() > 0.3
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PT), reason="oracle/_ref not built (reference not mounted)")
+@pytest.mark.parametrize("name,sky", [("CornellBox.proc", False), ("RTIO.proc", True)])
+def test_probe_bake_is_pinned_to_the_references_source(name, sky):
+    """the reference's Bake.HwAmbientCube.comp.slang compiled whole as C++ with FGpuProbeGenerator (RenderAmbientCubeOnly,
+    FaceTask, FetchLight), EvaluateSH / SampleIBLRough and the DI probe lookup, against the oracle's BakeCube on probe rows through the scene.
+    The reference's threads read neighbouring probes while other threads update them (a race on the GPU); the oracle and the CUDA kernel read
+    a snapshot of the range being baked instead. To compare the two deterministically the probes of the baked rows are flagged 'inside
+    geometry' (second distance byte 0), which every lookup skips (AmbientCube.slang:327) while the bake itself only looks at the first byte -
+    so all light comes from probes outside the rows and the order of the threads cannot matter. Cubes (14 words), ages and ray counts must be
+    bit-identical after two bake passes (the second one blends into the first: LerpPackedColorAlt, sky visibility bytes, jitter by age)."""
+    import ctypes as C
+    from gknextengine_b200._abi import GK_CUBE_SIZE_XY
+    ref = _ref_pathtrace_lib()
+    ref.ref_probes_bake.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    rng = np.random.default_rng(9)
+    scene = host.Scene(name, samples=1, bounces=4)
+    skyimg = None
+    if sky:
+        scene.env(has_sky=True, has_sun=True)
+        skyimg = host.make_sky(64, 32)
+    scene.update_nodes()
+    osc = O.OracleScene(scene, skyimg)
+    # the reference evaluates the SH sky on every miss, enabled or not (AmbientCube.slang:515), so a set of coefficients must be bound
+    osc.set_sky_sh(0, host.project_sh(skyimg if sky else np.full((16, 32, 4), 0.25, np.float32)))
+    cubes, vox = _random_probe_grid(osc, scene, rng)
+    ubo = scene.ubo(64, 36, 1)
+    # rows of 64 probes along x through the middle of the scene at several heights / depths
+    rows = []
+    for (y, z) in ((3, 96), (9, 90), (14, 101), (22, 96), (2, 106)):
+        first = y * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + z * GK_CUBE_SIZE_XY + 64
+        rows.append(first)
+        vox["distanceToSolid_gg_z01"][first:first + 64] &= np.uint32(0xFFFF00FF)  # inside byte = 0: never looked up
+    osc.set_probes(cubes, vox)
+    mine_c, mine_v = cubes.copy(), vox.copy()
+    counters = (C.c_uint64 * 2)()
+    baked = 0
+    for rep in range(2):
+        for first in rows:
+            ref.ref_probes_bake(osc._h, C.byref(ubo), mine_c.ctypes.data, mine_v.ctypes.data, first, 64, counters)
+            osc.probes_bake(ubo, first, 64)
+            oc, ov, _ = osc.probes_read()
+            a, b = mine_c[first:first + 64].view(np.uint32).reshape(64, -1), oc[first:first + 64].view(np.uint32).reshape(64, -1)
+            assert np.array_equal(a, b), (rep, first, np.argwhere(a != b)[:4].tolist())
+            assert np.array_equal(mine_v["age"][first:first + 64], ov["age"][first:first + 64])
+            n_baked = int((mine_v["age"][first:first + 64] == rep + 1).sum())
+            baked += n_baked
+            assert counters[0] == n_baked * 6 * 16, (list(counters), n_baked)
+    # untouched outside the rows
+    mask = np.ones(len(cubes), bool)
+    for first in rows:
+        mask[first:first + 64] = False
+    assert np.array_equal(mine_c[mask].view(np.uint32), cubes[mask].view(np.uint32))
+    assert baked > 100
