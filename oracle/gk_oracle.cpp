@@ -1749,6 +1749,12 @@ void gko_interpolate_ambient_cubes(GkoScene* s, int which, const float pos[3], c
     f4 c = s->interpolateAmbientCubesT(F3(pos[0], pos[1], pos[2]), F3(n[0], n[1], n[2]), which == 0, nullptr, 0, 0);
     out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
 }
+int gko_vox_trace(GkoScene* s, const float o[3], const float d[3], float dist, float* t, float normal[3], uint32_t* material) {
+    f3 n;
+    bool hit = s->VoxTrace(F3(o[0], o[1], o[2]), F3(d[0], d[1], d[2]), dist, *t, n, *material);
+    if (hit) { normal[0] = n.x; normal[1] = n.y; normal[2] = n.z; }
+    return hit ? 1 : 0;
+}
 void gko_instance_w2o(GkoScene* s, uint32_t inst, float out[12]) { std::memcpy(out, s->instances[inst].w2o, 48); }
 void gko_sample_texture(GkoScene* s, uint32_t id, float u, float v, float out[4]) { f4 c = s->sample_texture(id, f2{u, v}); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w; }
 void gko_cast_visibility(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t* packed) {

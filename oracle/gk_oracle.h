@@ -9,6 +9,7 @@
  *   - the whole RT pass: Core.PathTracing + Util.BufferClear with the Shading.slang classes and interpolateAmbientCubesV2 they run
  *     (oracle/ref_pathtrace.cpp), every written storage image and both ray counts bit-identical over frames with motion
  *   - the probe bake: Bake.HwAmbientCube with FGpuProbeGenerator, EvaluateSH / SampleIBLRough (same file), cubes and ages bit-identical
+ *   - the probe voxeliser and page index: line ranges of src/Assets/CPUAccelerationStructure.cpp compiled unmodified (oracle/ref_voxelizer.cpp)
  *   - the reproject and denoise passes: Process.ReProject + Process.DenoiseJBF compiled whole (oracle/ref_stencils.cpp)
  *   - the function library: Const_Func.slang, GeneralFunc.slang, UnpackVertexV2, FetchMaterialId, mikkTSpace, calculateWeight, the
  *     probe colour format and samplers (oracle/ref_const_func.cpp, oracle/ref_general_func.cpp)
@@ -120,6 +121,8 @@ typedef struct GkoSceneArrays {
 } GkoSceneArrays;
 void gko_scene_arrays(GkoScene* s, GkoSceneArrays* out);
 void gko_trace_one(GkoScene* s, const GkcuRay* ray, GkcuHit* hit, uint32_t any_hit);
+/* the CPU baker's TraceRay (CPUAccelerationStructure.cpp:42-66): face normal through the node matrix, material of vertex 0 */
+int gko_vox_trace(GkoScene* s, const float o[3], const float d[3], float dist, float* t, float normal[3], uint32_t* material);
 void gko_instance_w2o(GkoScene* s, uint32_t inst, float out[12]); /* world-to-object, 3 rows x 4 columns */
 void gko_sample_texture(GkoScene* s, uint32_t id, float u, float v, float out[4]);
 /* packed[y*w+x] = ((node + 1) << 17) | primitive, 0 = no geometry: the RT_MINIGBUFFER texel format (Shading.slang:348-349) */

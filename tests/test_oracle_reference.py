@@ -597,3 +597,43 @@ def test_probe_bake_is_pinned_to_the_references_source(name, sky):
         mask[first:first + 64] = False
     assert np.array_equal(mine_c[mask].view(np.uint32), cubes[mask].view(np.uint32))
     assert baked > 100
+
+
+REF_VX = os.path.join(os.path.dirname(O.TINYBVH), "libref_voxelizer.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_VX), reason="oracle/_ref not built (reference not mounted)")
+@pytest.mark.parametrize("name", ["CornellBox.proc", "RTIO.proc"])
+def test_voxeliser_and_page_index_are_pinned_to_the_references_source(name):
+    """the reference's CPU voxeliser (VoxelizeCube, InsideGeometry, DetectDistance, PackBytes) and page index
+    (FCPUPageIndex::UpdateData / GetPage), line ranges of src/Assets/CPUAccelerationStructure.cpp compiled unmodified (oracle/ref_voxelizer.cpp),
+    against the oracle's VoxelizeCube / UpdatePageIndex: the four VoxelData words of every probe in slabs through the scene and all 4096 page
+    records must be identical."""
+    import ctypes as C
+    from gknextengine_b200._abi import GK_CUBE_SIZE_XY
+    from gknextengine_b200.renderer import CudaPathTracingRenderer as R
+    ref = C.CDLL(REF_VX)
+    ref.ref_voxelize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    ref.ref_page_index.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    scene = host.Scene(name, samples=1, bounces=4)
+    scene.update_nodes()
+    osc = O.OracleScene(scene)
+    osc.set_lights(scene)
+    osc.probes_voxelize()
+    _, vox, pages = osc.probes_read(pages=True)
+    layer = GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY
+    checked = solid = 0
+    for y in (0, 1, 2, 5, 11, 23, 30):   # horizontal slabs of the grid, 13 824 probes each
+        first, count = y * layer + 60 * GK_CUBE_SIZE_XY, 72 * GK_CUBE_SIZE_XY   # rows z = 60 .. 131 around the origin
+        mine = np.zeros(count, dtype=R.VOXEL_DTYPE)
+        ref.ref_voxelize(osc._h, first, count, mine.ctypes.data)
+        theirs = vox[first:first + count]
+        for f in ("matId", "age", "distanceToSolid_gg_z01", "distanceToSolid_x01_y01"):
+            bad = mine[f] != theirs[f]
+            assert not bad.any(), (y, f, int(bad.sum()), np.argwhere(bad)[:3].tolist(), mine[f][bad][:3].tolist(), theirs[f][bad][:3].tolist())
+        checked += count
+        solid += int((mine["matId"] != 0).sum())
+    assert checked > 90000 and solid > 50
+    mine_pages = np.zeros(len(pages), dtype=R.PAGE_DTYPE)
+    ref.ref_page_index(vox.ctypes.data, len(vox), mine_pages.ctypes.data)
+    assert np.array_equal(mine_pages.view(np.uint32), pages.view(np.uint32)) and int(mine_pages["voxelCount"].sum()) == int((vox["matId"] != 0).sum()) > 0
