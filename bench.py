@@ -34,6 +34,10 @@ SCENE = "RTIO.proc"
 TRACE_BYTES_PER_RAY = 32 + 4 + 16 + 4
 PAIR_BYTES_CLOSEST, PAIR_BYTES_ANY = 436, 100
 PRIMARY_BYTES_PER_PIXEL, REPROJECT_BYTES_PER_PIXEL, DENOISE_BYTES_PER_PIXEL = 36 + 2, 98, 44
+# Warp instructions per pixel of the two stencil kernels (ncu smsp__inst_executed.sum / 1920x1080, profiles/r01_ncu_misc.txt): both kernels
+# are bound by instruction issue, not by HBM - the reference's arithmetic (36 bilateral taps with an IEEE division and an exp each, 25
+# weighted taps with two divisions each) kept bit for bit - so the bench also reports them against the SM issue rate (4 warp instr / clk / SM).
+REPROJECT_WARP_INSTR_PER_PIXEL, DENOISE_WARP_INSTR_PER_PIXEL, SM_COUNT, ISSUE_PER_SM_CLK = 137084257 / 2073600, 177308860 / 2073600, 148, 4
 
 
 def load_peaks():
@@ -409,6 +413,13 @@ def main():
             "denoise": {"achieved": DENOISE_BYTES_PER_PIXEL * px * args.steps / (pass_ms["compose_pass_ms"] * 1e-3) / 1e9 if pass_ms["compose_pass_ms"] else 0.0,
                         "bytes_per_pixel": DENOISE_BYTES_PER_PIXEL},
             "unit": "GB/s", "peak": peak}
+        sm_mhz = (clocks or {}).get("sm_mhz") or 0
+        if sm_mhz:
+            issue_peak = SM_COUNT * ISSUE_PER_SM_CLK * sm_mhz * 1e6
+            for name, key, ipp in (("reproject", "reproject_pass_ms", REPROJECT_WARP_INSTR_PER_PIXEL), ("denoise", "compose_pass_ms", DENOISE_WARP_INSTR_PER_PIXEL)):
+                if pass_ms[key]:
+                    out["roofline_stencils"][name].update({"bound": "issue", "warp_instr_per_pixel": round(ipp, 2),
+                                                           "issue_frac": ipp * px * args.steps / (pass_ms[key] * 1e-3) / issue_peak})
         if world == 1 and not args.no_cpu_baseline:
             ubo = scene.ubo(WIDTH, HEIGHT, 1)
             p1 = GkcuFrameParams(temporal_frames=16, spp_world=1)
