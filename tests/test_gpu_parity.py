@@ -732,3 +732,56 @@ def test_error_handling(renderer):
     renderer.Render(ubo, p)  # still usable after errors
     renderer.BeforeNextFrame()
     assert renderer.counters()["primary_rays"] == 64 * 64
+
+
+def test_cuda_frames_match_the_references_own_shaders_compiled_as_cpp(renderer):
+    """CUDA against the reference's text directly, without the oracle's restatement in between: oracle/_ref/libref_pathtrace.so and
+    libref_stencils.so are the reference's Util.BufferClear, Core.PathTracing, Process.ReProject and Process.DenoiseJBF shaders (with the
+    Shading.slang / AmbientCube.slang classes they run) compiled as C++ where they lie (oracle/Makefile `ref`, built when the reference is
+    mounted; the binaries travel to the GPU box like the other built libraries). Only the hardware parts come from the oracle: the ray
+    query, the texture sampler and the visibility buffer. Five whole frames with temporal accumulation, moving geometry, textures and
+    normal maps on the Cornell box: every storage image bit-identical, RT_DENOISED within 2 fp16 ulps (pow / exp of two libms)."""
+    from gknextengine_b200._abi import GK_CUBE_COUNT
+    from helpers import CompiledReferenceFrame, textured_cornell_materials
+    if not CompiledReferenceFrame.available():
+        pytest.skip("oracle/_ref not built (reference not mounted when the snapshot was taken)")
+    W, H = 168, 94
+    rng = np.random.default_rng(17)
+    scene = host.Scene("CornellBox.proc", samples=2, bounces=4, taa=True, denoiser=True)
+    scene.update_nodes()
+    osc, _ = setup_pair(renderer, scene, W, H)
+    textures, mats, nm = textured_cornell_materials(scene, rng)
+    for idx, tex in textures:
+        renderer.set_sky(idx, tex)
+        osc.set_sky(idx, tex)
+    renderer.update_materials(scene)
+    osc.L.gko_update_materials(osc._h, mats, nm)
+    # zero probe state on both sides (the reference dereferences the probe arrays, so they must exist)
+    osc.set_probes(np.zeros(GK_CUBE_COUNT, CudaPathTracingRenderer.CUBE_DTYPE), np.zeros(GK_CUBE_COUNT, CudaPathTracingRenderer.VOXEL_DTYPE))
+    ref = CompiledReferenceFrame(W, H)
+    p = params()
+    worst_ulps = 0
+    for f in range(1, 6):
+        if f == 3:
+            scene.jitter_instances(2, 0.6)
+            scene.update_nodes()
+            osc.update_nodes(scene)
+            renderer.AfterUpdateScene(scene)
+        ubo = scene.ubo(W, H, f)
+        renderer.PreRender()
+        renderer.Render(ubo, p)
+        renderer.BeforeNextFrame()
+        ref.render(osc, ubo)
+        for name in ("OBJEDCTID_0", "ALBEDO", "NORMAL", "MOTIONVECTOR", "MOTIONMOMENT", "PREV_DEPTHBUFFER", "SINGLE_DIFFUSE", "SINGLE_SPECULAR",
+                     "ACCUMLATE_DIFFUSE", "ACCUMLATE_SPECULAR", "ACCUMLATE_ALBEDO"):
+            g = renderer.readback(RT[name])
+            bad = ref.mismatches(name, g)
+            assert not bad.any(), (name, f, int(bad.sum()), np.argwhere(bad)[:3].tolist(), g[bad][:2].tolist(), ref.images[name][bad][:2].tolist())
+        gc = renderer.counters()
+        assert (gc["closest_hit_rays"], gc["any_hit_rays"]) == (ref.closest, ref.any)
+        g, c = renderer.readback(RT["DENOISED"]), ref.images["DENOISED"]
+        fg, fc = np.isfinite(g.astype(np.float32)).all(axis=2), np.isfinite(c.astype(np.float32)).all(axis=2)
+        assert (fg == fc).mean() > 0.999
+        worst_ulps = max(worst_ulps, int(half_ulp_diff(g, c)[fg & fc].max()))
+        ref.end_frame()
+    assert worst_ulps <= 2 and ref.images["MOTIONMOMENT"].any()

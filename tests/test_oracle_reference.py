@@ -637,3 +637,42 @@ def test_voxeliser_and_page_index_are_pinned_to_the_references_source(name):
     mine_pages = np.zeros(len(pages), dtype=R.PAGE_DTYPE)
     ref.ref_page_index(vox.ctypes.data, len(vox), mine_pages.ctypes.data)
     assert np.array_equal(mine_pages.view(np.uint32), pages.view(np.uint32)) and int(mine_pages["voxelCount"].sum()) == int((vox["matId"] != 0).sum()) > 0
+
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PT) or not os.path.exists(REF_ST), reason="oracle/_ref not built (reference not mounted)")
+def test_whole_frames_over_time_are_pinned_to_the_references_source():
+    """The passes together, frame after frame: BufferClear -> PathTracing -> ReProject -> DenoiseJBF -> copy pass, all from the reference's
+    compiled shader text (helpers.CompiledReferenceFrame), against the oracle's gko_render_frame + gko_end_frame_copies over six frames of the
+    textured Cornell box with geometry that moves in frame 3 (history rejection by the motion moment, 4 x samples on moving pixels, temporal
+    blend afterwards). Every storage image bit-identical, RT_DENOISED included (same libm on both sides)."""
+    from helpers import CompiledReferenceFrame, textured_cornell_materials
+    W, H = 72, 44
+    rng = np.random.default_rng(17)
+    scene = host.Scene("CornellBox.proc", samples=2, bounces=4, taa=True, denoiser=True)
+    scene.update_nodes()
+    osc, ofr = O.OracleScene(scene), O.OracleFrame(W, H)
+    textures, mats, nm = textured_cornell_materials(scene, rng)
+    for idx, tex in textures:
+        osc.set_sky(idx, tex)
+    osc.L.gko_update_materials(osc._h, mats, nm)
+    _random_probe_grid(osc, scene, rng)
+    ref = CompiledReferenceFrame(W, H)
+    p = GkcuFrameParams(temporal_frames=16, spp_world=1)
+    for f in range(1, 7):
+        if f == 3:
+            scene.jitter_instances(2, 0.6)
+            scene.update_nodes()
+            osc.update_nodes(scene)
+        ubo = scene.ubo(W, H, f)
+        ref.render(osc, ubo)
+        ofr.render(osc, ubo, p)
+        for name in ("OBJEDCTID_0", "ALBEDO", "NORMAL", "MOTIONVECTOR", "MOTIONMOMENT", "PREV_DEPTHBUFFER", "SINGLE_DIFFUSE", "SINGLE_SPECULAR",
+                     "ACCUMLATE_DIFFUSE", "ACCUMLATE_SPECULAR", "ACCUMLATE_ALBEDO", "DENOISED"):
+            bad = ref.mismatches(name, ofr.image(RT[name]))
+            assert not bad.any(), (name, f, int(bad.sum()), np.argwhere(bad)[:3].tolist())
+        c = ofr.counters()
+        assert (ref.closest, ref.any) == (c["closest"], c["any"])
+        ref.end_frame()
+        ofr.end_frame_copies()
+    assert ref.images["MOTIONMOMENT"].any() and ref.images["ACCUMLATE_DIFFUSE"].astype(np.float32).max() > 0.05
