@@ -734,33 +734,50 @@ def test_error_handling(renderer):
     assert renderer.counters()["primary_rays"] == 64 * 64
 
 
-def test_cuda_frames_match_the_references_own_shaders_compiled_as_cpp(renderer):
+@pytest.mark.parametrize("setup", ["cornell-textures", "cornell-aperture-probes", "rtio-sky-sun"])
+def test_cuda_frames_match_the_references_own_shaders_compiled_as_cpp(renderer, sky, setup):
     """CUDA against the reference's text directly, without the oracle's restatement in between: oracle/_ref/libref_pathtrace.so and
     libref_stencils.so are the reference's Util.BufferClear, Core.PathTracing, Process.ReProject and Process.DenoiseJBF shaders (with the
     Shading.slang / AmbientCube.slang classes they run) compiled as C++ where they lie (oracle/Makefile `ref`, built when the reference is
     mounted; the binaries travel to the GPU box like the other built libraries). Only the hardware parts come from the oracle: the ray
-    query, the texture sampler and the visibility buffer. Five whole frames with temporal accumulation, moving geometry, textures and
-    normal maps on the Cornell box: every storage image bit-identical, RT_DENOISED within 2 fp16 ulps (pow / exp of two libms)."""
+    query, the texture sampler and the visibility buffer. Five whole frames with temporal accumulation and moving geometry:
+      cornell-textures         textures + normal maps, zero probe state: every storage image bit-identical
+      cornell-aperture-probes  depth of field (the CoC re-read of the visibility buffer) and random probe data at path termination: bit-identical
+      rtio-sky-sun             1939 instances, dielectrics, sky + sun: G-buffer bit-identical, radiance on all but <= 2e-3 of the pixels
+                               (atan2 / acos of the sky lookup: CUDA vs glibc flips an fp16 rounding here and there)
+    RT_DENOISED within 2 fp16 ulps (pow / exp of two libms)."""
     from gknextengine_b200._abi import GK_CUBE_COUNT
+    from gknextengine_b200.renderer import _ck, lib
     from helpers import CompiledReferenceFrame, textured_cornell_materials
     if not CompiledReferenceFrame.available():
         pytest.skip("oracle/_ref not built (reference not mounted when the snapshot was taken)")
     W, H = 168, 94
     rng = np.random.default_rng(17)
-    scene = host.Scene("CornellBox.proc", samples=2, bounces=4, taa=True, denoiser=True)
+    rtio = setup == "rtio-sky-sun"
+    scene = host.Scene("RTIO.proc" if rtio else "CornellBox.proc", samples=2, bounces=6 if rtio else 4, taa=True, denoiser=True)
+    if rtio:
+        scene.env(has_sky=True, has_sun=True)
+    if setup == "cornell-aperture-probes":
+        scene.camera(aperture=0.3, focal_distance=9.0)
     scene.update_nodes()
-    osc, _ = setup_pair(renderer, scene, W, H)
-    textures, mats, nm = textured_cornell_materials(scene, rng)
-    for idx, tex in textures:
-        renderer.set_sky(idx, tex)
-        osc.set_sky(idx, tex)
-    renderer.update_materials(scene)
-    osc.L.gko_update_materials(osc._h, mats, nm)
-    # zero probe state on both sides (the reference dereferences the probe arrays, so they must exist)
-    osc.set_probes(np.zeros(GK_CUBE_COUNT, CudaPathTracingRenderer.CUBE_DTYPE), np.zeros(GK_CUBE_COUNT, CudaPathTracingRenderer.VOXEL_DTYPE))
+    osc, _ = setup_pair(renderer, scene, W, H, sky if rtio else None)
+    if setup == "cornell-textures":
+        textures, mats, nm = textured_cornell_materials(scene, rng)
+        for idx, tex in textures:
+            renderer.set_sky(idx, tex)
+            osc.set_sky(idx, tex)
+        renderer.update_materials(scene)
+        osc.L.gko_update_materials(osc._h, mats, nm)
+    if setup == "cornell-aperture-probes":
+        cubes = rng.integers(0, 2 ** 32, size=(GK_CUBE_COUNT, 14), dtype=np.uint32)
+        voxels = rng.integers(0, 2 ** 32, size=(GK_CUBE_COUNT, 4), dtype=np.uint32)
+        _ck(lib().gkcu_set_probes(renderer._ctx, cubes.ctypes.data, voxels.ctypes.data))
+        osc.L.gko_set_probes(osc._h, cubes.ctypes.data, voxels.ctypes.data)
+    else:  # zero probe state on both sides (the reference dereferences the probe arrays, so they must exist)
+        osc.set_probes(np.zeros(GK_CUBE_COUNT, CudaPathTracingRenderer.CUBE_DTYPE), np.zeros(GK_CUBE_COUNT, CudaPathTracingRenderer.VOXEL_DTYPE))
     ref = CompiledReferenceFrame(W, H)
     p = params()
-    worst_ulps = 0
+    worst_ulps, limit = 0, (2e-3 if rtio else 0.0)
     for f in range(1, 6):
         if f == 3:
             scene.jitter_instances(2, 0.6)
@@ -776,12 +793,17 @@ def test_cuda_frames_match_the_references_own_shaders_compiled_as_cpp(renderer):
                      "ACCUMLATE_DIFFUSE", "ACCUMLATE_SPECULAR", "ACCUMLATE_ALBEDO"):
             g = renderer.readback(RT[name])
             bad = ref.mismatches(name, g)
-            assert not bad.any(), (name, f, int(bad.sum()), np.argwhere(bad)[:3].tolist(), g[bad][:2].tolist(), ref.images[name][bad][:2].tolist())
+            allowed = limit if name in RADIANCE_NAMES else 0.0
+            assert bad.mean() <= allowed, (name, f, int(bad.sum()), np.argwhere(bad)[:3].tolist(), g[bad][:2].tolist(), ref.images[name][bad][:2].tolist())
         gc = renderer.counters()
         assert (gc["closest_hit_rays"], gc["any_hit_rays"]) == (ref.closest, ref.any)
         g, c = renderer.readback(RT["DENOISED"]), ref.images["DENOISED"]
         fg, fc = np.isfinite(g.astype(np.float32)).all(axis=2), np.isfinite(c.astype(np.float32)).all(axis=2)
         assert (fg == fc).mean() > 0.999
-        worst_ulps = max(worst_ulps, int(half_ulp_diff(g, c)[fg & fc].max()))
+        over = (half_ulp_diff(g, c) > 2).any(axis=2) & fg & fc
+        assert over.mean() <= limit, (f, int(over.sum()))
         ref.end_frame()
-    assert worst_ulps <= 2 and ref.images["MOTIONMOMENT"].any()
+    assert ref.images["MOTIONMOMENT"].any() or rtio
+
+
+RADIANCE_NAMES = ("SINGLE_DIFFUSE", "SINGLE_SPECULAR", "ACCUMLATE_DIFFUSE", "ACCUMLATE_SPECULAR", "ACCUMLATE_ALBEDO")
