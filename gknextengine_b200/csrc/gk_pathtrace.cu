@@ -136,8 +136,10 @@ GK_DEV PrimVertex get_material_dataV2(const SceneView& S, uint32_t nodeIdx, uint
     return r;
 }
 
-GK_DEV float3 pixel_ray_dir(const GkUniformBufferObject* C, int x, int y, int w, int h) {  // Shading.slang:350-356
-    float2 uv = make_float2((float)x / (float)w * 2.0f - 1.0f, (float)y / (float)h * 2.0f - 1.0f);
+// The shading ray of a pixel goes through its corner (offset 0, Shading.slang:350-356); the visibility ray that stands in for the raster
+// pass goes through its centre (offset 0.5), where the rasteriser samples coverage and depth (Rast.VisibilityPass.vert.slang:9-23).
+GK_DEV float3 pixel_ray_dir(const GkUniformBufferObject* C, int x, int y, int w, int h, float offset = 0.0f) {
+    float2 uv = make_float2(((float)x + offset) / (float)w * 2.0f - 1.0f, ((float)y + offset) / (float)h * 2.0f - 1.0f);
     float4 target = mul(C->ProjectionInverse, f4(uv.x, uv.y, 1, 1));
     float3 tn = normalize(xyz(target));
     float4 dir = mul(C->ModelViewInverse, f4(tn.x, tn.y, tn.z, 0));
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
         float3 origin = xyz(origin4);
         float3 ray_dir = pixel_ray_dir(C, x, y, R.w, R.h);
         Hit h;
-        trace_ray<false>(S.ts, origin, ray_dir, GK_EPS, GK_PRIMARY_T_MAX, h);
+        trace_ray<false>(S.ts, origin, pixel_ray_dir(C, x, y, R.w, R.h, 0.5f), GK_EPS, GK_PRIMARY_T_MAX, h);
         nprimary++;
         float4 zero = f4(0, 0, 0, 0);
         if (h.inst == GK_NO_HIT) {  // Shading.slang:1193-1201
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
                 if (ox != x || oy != y) {
                     float3 fdir = pixel_ray_dir(C, ox, oy, R.w, R.h);
                     Hit h2;
-                    trace_ray<false>(S.ts, origin, fdir, GK_EPS, GK_PRIMARY_T_MAX, h2);
+                    trace_ray<false>(S.ts, origin, pixel_ray_dir(C, ox, oy, R.w, R.h, 0.5f), GK_EPS, GK_PRIMARY_T_MAX, h2);
                     nprimary++;
                     if (h2.inst != GK_NO_HIT) {
                         PrimVertex cand = get_material_dataV2(S, h2.inst, h2.prim, origin, fdir);

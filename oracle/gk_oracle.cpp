@@ -1117,11 +1117,12 @@ struct Renderer {  // FPathTracingRendererV2, Shading.slang:995-1261, configured
         return S.occluded(rayOrigin, rayDir, EPS, PT_MAX_TRACE_DISTANCE);
     }
 
-    // Primary visibility: the reference reads a rasterised visibility buffer (Shading.slang:348-349); a GPU without a
-    // rasteriser casts the same pixel-corner ray instead (what FHardwarePrimaryRayCaster does, :283-334). Returns
-    // (node index + 1, primitive) in the vis-buffer convention, 0 = no geometry.
+    // Primary visibility: the reference reads a visibility buffer rasterised from the same camera (Rast.VisibilityPass.vert.slang:9-23,
+    // read at Shading.slang:348-349). The rasteriser samples coverage and depth at the pixel CENTRE, so the stand-in for a GPU without one
+    // is the closest hit of the ray through the pixel centre; the shading ray that TracePrimaryRay then intersects with that triangle's
+    // plane stays the pixel-corner ray of the text (:350-356). Returns (node index + 1, primitive) in the vis-buffer convention, 0 = none.
     void CastVisibility(int x, int y, f3 origin, uint32_t& node1, uint32_t& prim) {
-        f2 uv = f2{(float)x / (float)F.w * 2.0f - 1.0f, (float)y / (float)F.h * 2.0f - 1.0f};
+        f2 uv = f2{((float)x + 0.5f) / (float)F.w * 2.0f - 1.0f, ((float)y + 0.5f) / (float)F.h * 2.0f - 1.0f};
         f4 target = mul(Camera.ProjectionInverse, F4(uv.x, uv.y, 1, 1));
         f3 tn = normalize(xyz(target));
         f4 dir = mul(Camera.ModelViewInverse, F4(tn.x, tn.y, tn.z, 0));
