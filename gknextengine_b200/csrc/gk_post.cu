@@ -297,11 +297,11 @@ GK_DEV float GranTurismoTonemapper(float x) {
     float P = 1, a = 0.7f, m = 0.22f, l = 0.4f, c = 1.33f, b = 0;
     float l0 = (P - m) * l / a;
     float L_x = m + a * (x - m);
-    float T_x = m * powf(x / m, c) + b;
+    float T_x = m * gk_det_powf(x / m, c) + b;
     float S0 = m + l0;
     float S1 = m + a * l0;
     float C2 = a * P / (P - S1);
-    float S_x = P - (P - S1) * powf(e, -(C2 * (x - S0) / P));
+    float S_x = P - (P - S1) * gk_det_powf(e, -(C2 * (x - S0) / P));
     float w0_x = 1 - W_f(x, 0, m);
     float w2_x = H_f(x, m + l0, m + l0);
     float w1_x = 1 - w0_x - w2_x;
@@ -311,10 +311,10 @@ GK_DEV float3 GT_Tonemapping(float3 x) { return f3(GranTurismoTonemapper(x.x), G
 GK_DEV float ST2084(float lin) {
     const float m1 = 0.1593017578125f, m2 = 78.84375f, c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f, C = 10000.f;
     float L = lin / C;
-    float Lm = powf(L, m1);
+    float Lm = gk_det_powf(L, m1);
     float N1 = (c1 + c2 * Lm), N2 = (1.0f + c3 * Lm);
     float N = N1 * (1.0f / N2);
-    return powf(N, m2);
+    return gk_det_powf(N, m2);
 }
 
 __global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
                 const float lumi = t.w;
                 const float dist = clampf(float(i * i + j * j) / float(DR * DR), 0.0f, 1.0f);
                 const float dlum = (CenterLum - lumi) * (CenterLum - lumi);
-                const float Fi = expf(-dist * dist / (2.0f * sigma * sigma));
-                const float Li = expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
+                const float Fi = gk_det_expf(-dist * dist / (2.0f * sigma * sigma));
+                const float Li = gk_det_expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
                 Total = Total + Ci * Fi * Li;
                 Weight += Fi * Li;
             }
@@ -423,8 +423,8 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise_tma(const __grid_constant_
             const float lumi = t.w;
             const float dist = clampf(float(i * i + j * j) / float(DR * DR), 0.0f, 1.0f);
             const float dlum = (CenterLum - lumi) * (CenterLum - lumi);
-            const float Fi = expf(-dist * dist / (2.0f * sigma * sigma));
-            const float Li = expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
+            const float Fi = gk_det_expf(-dist * dist / (2.0f * sigma * sigma));
+            const float Li = gk_det_expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
             Total = Total + Ci * Fi * Li;
             Weight += Fi * Li;
         }

@@ -100,7 +100,7 @@ GK_DEV float4 sample_texture(const SceneView& S, uint32_t id, float2 uv) {
 
 GK_DEV float4 SampleIBLV2(const SceneView& S, uint32_t skyIdx, float3 direction, float rotate) {  // Shading.slang:194-199
     float3 d = normalize(direction);
-    float2 t = make_float2((atan2f(d.x, d.z) + GK_M_PI * rotate) * GK_M_1_OVER_TWO_PI, acosf(d.y) * GK_M_1_PI);
+    float2 t = make_float2((gk_det_atan2f(d.x, d.z) + GK_M_PI * rotate) * GK_M_1_OVER_TWO_PI, gk_det_acosf(d.y) * GK_M_1_PI);
     float4 s = sample_texture(S, skyIdx, t);
     return f4(fminf(10.f, s.x), fminf(10.f, s.y), fminf(10.f, s.z), fminf(1.f, s.w));
 }

@@ -10,8 +10,12 @@
  * nvcc -fmad=false, g++ -ffp-contract=off). sqrt and division are IEEE-exact on both sides.
  * Max error vs. libm is < 2 ulp on [0, 2*pi] (tests/test_detmath.py).
  *
- * Leaf-only transcendentals (atan2/acos for the sky lookup, pow/exp in the tonemapper and the
- * bilateral weights) stay on libm / CUDA math: they never influence control flow.
+ * The leaf transcendentals - atan2/acos of the sky lookup (Shading.slang:194-199), exp of the bilateral weights
+ * (Process.DenoiseJBF.comp.slang), pow of the tonemappers (Const_Func.slang:51-126) - never influence control flow, but two
+ * libms round them differently and an fp16 store then flips here and there. They are pinned the same way (Cephes single-precision
+ * kernels, plain mul/add, IEEE sqrt/div), so that every storage image is bit-identical between the CUDA renderer and its checker:
+ * gk_det_atan2f, gk_det_acosf, gk_det_expf, gk_det_logf, gk_det_powf. Errors vs. libm: a few ulp (tests/test_detmath.py); pow is
+ * exp(y * log(x)), i.e. relative error ~1e-7 * |y ln x| like a GPU's intrinsic.
  */
 #ifndef GK_DETMATH_H
 #define GK_DETMATH_H
@@ -44,5 +48,112 @@ GK_HD void gk_det_sincosf(float xx, float* s, float* c) {
 
 GK_HD float gk_det_sinf(float x) { float s, c; gk_det_sincosf(x, &s, &c); return s; }
 GK_HD float gk_det_cosf(float x) { float s, c; gk_det_sincosf(x, &s, &c); return c; }
+
+
+GK_HD float gk_det_bits2f(unsigned int u) { union { unsigned int u; float f; } c; c.u = u; return c.f; }
+GK_HD unsigned int gk_det_f2bits(float f) { union { unsigned int u; float f; } c; c.f = f; return c.u; }
+
+GK_HD float gk_det_atanf(float xx) {
+    float sign = 1.0f, x = xx, y;
+    if (x < 0.0f) { sign = -1.0f; x = -x; }
+    if (x > 2.414213562373095f) { y = 1.5707963267948966f; x = -(1.0f / x); }        /* tan(3 pi / 8) */
+    else if (x > 0.4142135623730950f) { y = 0.7853981633974483f; x = (x - 1.0f) / (x + 1.0f); }  /* tan(pi / 8) */
+    else y = 0.0f;
+    const float z = x * x;
+    y = y + ((((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * x + x);
+    return sign * y;
+}
+
+/* atan2(y, x) with the C library's quadrant conventions (NaN in -> NaN out) */
+GK_HD float gk_det_atan2f(float y, float x) {
+    const float PI = 3.14159265358979323846f, PIO2 = 1.5707963267948966f;
+    if (x != x || y != y) return x + y;
+    int code = 0;
+    if (x < 0.0f) code = 2;
+    if (y < 0.0f) code |= 1;
+    if (x == 0.0f) {
+        if (code & 1) return -PIO2;
+        if (y == 0.0f) return 0.0f;
+        return PIO2;
+    }
+    if (y == 0.0f) return (code & 2) ? PI : 0.0f;
+    const float w = code == 2 ? PI : (code == 3 ? -PI : 0.0f);
+    return w + gk_det_atanf(y / x);
+}
+
+GK_HD float gk_det_asinf(float xx) {
+    float sign = 1.0f, a = xx, x, z;
+    if (a < 0.0f) { sign = -1.0f; a = -a; }
+    if (a != a) return xx;  /* NaN in -> the same NaN out, like libm: keeps two compilations of the same formula bit-identical */
+    if (a > 1.0f) return gk_det_bits2f(0x7FC00000u);
+    if (a < 1.0e-4f) return xx;
+    int flag = 0;
+    if (a > 0.5f) { z = 0.5f * (1.0f - a); x = sqrtf(z); flag = 1; }
+    else { x = a; z = x * x; }
+    z = ((((4.2163199048e-2f * z + 2.4181311049e-2f) * z + 4.5470025998e-2f) * z + 7.4953002686e-2f) * z + 1.6666752422e-1f) * z * x + x;
+    if (flag) { z = z + z; z = 1.5707963267948966f - z; }
+    return sign * z;
+}
+
+GK_HD float gk_det_acosf(float x) {
+    if (x < -0.5f) return 3.14159265358979323846f - 2.0f * gk_det_asinf(sqrtf(0.5f * (1.0f + x)));
+    if (x > 0.5f) return 2.0f * gk_det_asinf(sqrtf(0.5f * (1.0f - x)));
+    return 1.5707963267948966f - gk_det_asinf(x);
+}
+
+/* z * 2^n for n in [-300, 300], in at most three exactly representable power-of-two factors */
+GK_HD float gk_det_scalbnf(float z, int n) {
+    if (n > 127) { z = z * gk_det_bits2f(254u << 23); n -= 127; if (n > 127) { z = z * gk_det_bits2f(254u << 23); n -= 127; if (n > 127) n = 127; } }
+    else if (n < -126) { z = z * gk_det_bits2f(1u << 23); n += 126; if (n < -126) { z = z * gk_det_bits2f(1u << 23); n += 126; if (n < -126) n = -126; } }
+    return z * gk_det_bits2f((unsigned int)(n + 127) << 23);
+}
+
+GK_HD float gk_det_expf(float xx) {
+    if (xx != xx) return xx;
+    if (xx > 88.72283905206835f) return gk_det_bits2f(0x7F800000u);
+    if (xx < -103.278929903431851103f) return 0.0f;
+    float x = xx;
+    float z = floorf(1.44269504088896341f * x + 0.5f);
+    x = x - z * 0.693359375f;
+    x = x - z * -2.12194440e-4f;
+    const int n = (int)z;
+    z = x * x;
+    z = (((((1.9875691500e-4f * x + 1.3981999507e-3f) * x + 8.3334519073e-3f) * x + 4.1665795894e-2f) * x + 1.6666665459e-1f) * x + 5.0000001201e-1f) * z + x + 1.0f;
+    return gk_det_scalbnf(z, n);
+}
+
+/* natural logarithm of a positive finite number; 0 -> -inf, negative / NaN -> NaN, +inf -> +inf */
+GK_HD float gk_det_logf(float xx) {
+    if (xx != xx) return xx;
+    if (xx < 0.0f) return gk_det_bits2f(0x7FC00000u);
+    if (xx == 0.0f) return gk_det_bits2f(0xFF800000u);
+    unsigned int u = gk_det_f2bits(xx);
+    if (u == 0x7F800000u) return xx;
+    int e = 0;
+    if (u < 0x00800000u) { xx = xx * 33554432.0f; e = -25; u = gk_det_f2bits(xx); }  /* subnormal: scale by 2^25 */
+    e += (int)(u >> 23) - 126;                                                     /* xx = m * 2^e with m in [0.5, 1) */
+    float x = gk_det_bits2f((u & 0x007FFFFFu) | 0x3F000000u);
+    if (x < 0.707106781186547524f) { e -= 1; x = x + x - 1.0f; }
+    else x = x - 1.0f;
+    float z = x * x;
+    float y = ((((((((7.0376836292e-2f * x - 1.1514610310e-1f) * x + 1.1676998740e-1f) * x - 1.2420140846e-1f) * x + 1.4249322787e-1f) * x - 1.6668057665e-1f) * x +
+                 2.0000714765e-1f) * x - 2.4999993993e-1f) * x + 3.3333331174e-1f) * x * z;
+    const float fe = (float)e;
+    y = y + -2.12194440e-4f * fe;
+    y = y + -0.5f * z;
+    z = x + y;
+    z = z + 0.693359375f * fe;
+    return z;
+}
+
+/* pow for the tonemappers: x >= 0 expected. pow(0, y > 0) = 0, pow(x, 0) = 1, pow(negative, y) = NaN, pow(+inf, y > 0) = +inf */
+GK_HD float gk_det_powf(float x, float y) {
+    if (y == 0.0f) return 1.0f;
+    if (x != x) return x;
+    if (y != y) return y;
+    if (x < 0.0f) return gk_det_bits2f(0x7FC00000u);
+    if (x == 0.0f) return y > 0.0f ? 0.0f : gk_det_bits2f(0x7F800000u);
+    return gk_det_expf(y * gk_det_logf(x));
+}
 
 #endif /* GK_DETMATH_H */

@@ -193,10 +193,10 @@ inline f3 LinearToST2084UE(f3 lin) {
     float in[3] = {lin.x, lin.y, lin.z}, out[3];
     for (int i = 0; i < 3; ++i) {
         float L = in[i] / C;
-        float Lm = powf(L, m1);
+        float Lm = gk_det_powf(L, m1);
         float N1 = (c1 + c2 * Lm), N2 = (1.0f + c3 * Lm);
         float N = N1 * (1.0f / N2);
-        out[i] = powf(N, m2);
+        out[i] = gk_det_powf(N, m2);
     }
     return F3(out[0], out[1], out[2]);
 }
@@ -216,11 +216,11 @@ inline float GranTurismoTonemapper(float x) {
     float P = 1, a = 0.7f, m = 0.22f, l = 0.4f, c = 1.33f, b = 0;
     float l0 = (P - m) * l / a;
     float L_x = m + a * (x - m);
-    float T_x = m * powf(x / m, c) + b;
+    float T_x = m * gk_det_powf(x / m, c) + b;
     float S0 = m + l0;
     float S1 = m + a * l0;
     float C2 = a * P / (P - S1);
-    float S_x = P - (P - S1) * powf(e, -(C2 * (x - S0) / P));
+    float S_x = P - (P - S1) * gk_det_powf(e, -(C2 * (x - S0) / P));
     float w0_x = 1 - W_f(x, 0, m);
     float w2_x = H_f(x, m + l0, m + l0);
     float w1_x = 1 - w0_x - w2_x;
@@ -702,7 +702,7 @@ struct GkoScene {
     f4 SampleIBLV2(uint32_t skyIdx, f3 direction, float rotate, float roughness) const {  // Shading.slang:194-199
         (void)roughness;  // the path tracer always passes 0 -> mip 0
         f3 d = normalize(direction);
-        f2 t = f2{(atan2f(d.x, d.z) + M_PI_F * rotate) * M_1_OVER_TWO_PI_F, acosf(d.y) * M_1_PI_F};
+        f2 t = f2{(gk_det_atan2f(d.x, d.z) + M_PI_F * rotate) * M_1_OVER_TWO_PI_F, gk_det_acosf(d.y) * M_1_PI_F};
         f4 s = sample_texture(skyIdx, t);
         return F4(fminf(10.f, s.x), fminf(10.f, s.y), fminf(10.f, s.z), fminf(1.f, s.w));
     }
@@ -1566,8 +1566,8 @@ void DenoisePixel(GkoFrame& F, const GkUniformBufferObject& Camera, int dx, int 
                 const float lumi = dot(Ci, F3(0.212671f, 0.715160f, 0.072169f));
                 const float dist = clampf(float(i * i + j * j) / float(WINDOW_R * WINDOW_R), 0.0f, 1.0f);
                 const float dlum = (CenterLum - lumi) * (CenterLum - lumi);
-                const float Fi = expf(-dist * dist / (2.0f * sigma * sigma));
-                const float Li = expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
+                const float Fi = gk_det_expf(-dist * dist / (2.0f * sigma * sigma));
+                const float Li = gk_det_expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
                 Total = Total + Ci * Fi * Li;
                 Weight += Fi * Li;
             }
@@ -1919,6 +1919,15 @@ void gko_random_in_cone(uint32_t seed[4], float cos_theta, float out[3]) {
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 void gko_det_sincos(float x, float* s, float* c) { gk_det_sincosf(x, s, c); }
+float gko_det_math(int fn, float a, float b) {
+    switch (fn) {
+        case 0: return gk_det_atan2f(a, b);
+        case 1: return gk_det_acosf(a);
+        case 2: return gk_det_expf(a);
+        case 3: return gk_det_logf(a);
+        default: return gk_det_powf(a, b);
+    }
+}
 float* gko_radiance(GkoFrame* f, size_t* floats) { if (floats) *floats = f->radiance.size(); return f->radiance.data(); }
 void gko_resolve(GkoFrame* f, const GkUniformBufferObject* ubo) {
     const size_t n = (size_t)f->w * f->h;

@@ -97,6 +97,7 @@ void gko_ggx_sampling(uint32_t seed[4], float roughness, const float normal[3], 
 void gko_random_in_hemisphere1(uint32_t seed[4], float out[3]);
 float gko_schlick(float cosine, float ior);
 void gko_det_sincos(float x, float* s, float* c);
+float gko_det_math(int fn, float a, float b); /* include/gk_detmath.h: 0 atan2(a, b), 1 acos(a), 2 exp(a), 3 log(a), 4 pow(a, b) */
 void gko_st2084(const float in[3], float out[3]);
 void gko_align_with_normal(const float ray[3], const float n[3], float out[3]);
 float gko_random_float(uint32_t seed[4]);

@@ -6,6 +6,7 @@
 // the HLSL vocabulary they use. Floating literals are single precision as in Slang (-fsingle-precision-constant), products and sums
 // are not contracted (-ffp-contract=off), dot / mul / normalize are defined the way the oracle defines them (left-to-right, unfused).
 // Built only when /root/reference is mounted. TEST INFRASTRUCTURE ONLY.
+#define REF_DET_MATH
 #include "ref_hlsl_shim.h"
 
 namespace ref {

@@ -14,20 +14,27 @@
 #undef M_1_PI
 #undef M_2_PI
 
+#ifdef REF_DET_MATH
+#include "../include/gk_detmath.h"
+#endif
+
 namespace ref {
 using std::abs;
-#ifndef REF_TRIG_FROM_ORACLE
-using std::cos;
-#endif
 using std::fma;
-using std::pow;
-#ifndef REF_TRIG_FROM_ORACLE
-using std::sin;
+#ifdef REF_DET_MATH
+// sin / cos / atan2 / acos / exp / pow are hardware intrinsics in the shaders, with driver-defined rounding. The pins give them the pinned
+// kernels of the numeric contract (include/gk_detmath.h) that the oracle and the CUDA renderer use, so that whole passes compare bit for bit.
+inline float sin(float x) { return gk_det_sinf(x); }
+inline float cos(float x) { return gk_det_cosf(x); }
+inline float atan2(float y, float x) { return gk_det_atan2f(y, x); }
+inline float acos(float x) { return gk_det_acosf(x); }
+inline float exp(float x) { return gk_det_expf(x); }
+inline float pow(float x, float y) { return gk_det_powf(x, y); }
 #else
-// sin / cos are hardware intrinsics in the shader; the whole-pass pin gives them the oracle's pinned polynomial (gk_oracle.h)
-extern "C" void gko_det_sincos(float x, float* s, float* c);
-inline float sin(float x) { float s, c; gko_det_sincos(x, &s, &c); return s; }
-inline float cos(float x) { float s, c; gko_det_sincos(x, &s, &c); return c; }
+using std::cos;
+using std::exp;
+using std::pow;
+using std::sin;
 #endif
 using std::sqrt;
 typedef uint32_t uint;

@@ -7,7 +7,6 @@
 #include "ref_hlsl_shim.h"
 
 namespace ref {
-using std::exp;
 using std::floor;
 
 // ---- more vector vocabulary

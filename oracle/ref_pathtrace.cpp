@@ -18,12 +18,12 @@
 // What is hardware, not shader text, comes from the oracle through its service exports (gk_oracle.h): RayQuery = the oracle's
 // intersector (closest hit by (t, instance, primitive), any hit), the texture sampler, and the visibility buffer that the reference's
 // raster pass writes (the caller fills RT_MINIGBUFFER by casting pixel-corner rays). HLSL intrinsics (reflect, refract, distance, mul,
-// atan2, acos ...) are defined here the way the oracle defines them, and sin / cos are the oracle's pinned polynomial. So this pins the integrator: the control flow, the order of RNG
+// ...) are defined here the way the oracle defines them, and sin / cos / atan2 / acos / exp / pow are the pinned kernels of include/gk_detmath.h. So this pins the integrator: the control flow, the order of RNG
 // draws, every shading formula and every image store of the RT pass. Built only when /root/reference is mounted. TEST INFRASTRUCTURE ONLY.
 #include <atomic>
 
 #define REF_WITH_SCENE
-#define REF_TRIG_FROM_ORACLE
+#define REF_DET_MATH
 #include "gk_oracle.h"
 #include "ref_image_shim.h"
 
@@ -57,8 +57,6 @@ inline float3 refract(float3 i, float3 n, float eta) {
     if (k < 0.0f) return float3(0, 0, 0);
     return i * eta - n * (eta * ni + sqrt(k));
 }
-inline float atan2(float y, float x) { return atan2f(y, x); }
-inline float acos(float x) { return acosf(x); }
 inline float4 min(float4 a, float4 b) { return float4(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z), min(a.w, b.w)); }
 inline float4 operator/(uint4 a, float s) { return float4((float)a.x / s, (float)a.y / s, (float)a.z / s, (float)a.w / s); }
 inline float4& operator*=(float4& a, float4 b) { a = a * b; return a; }

@@ -15,6 +15,7 @@
 #include <thread>
 #include <vector>
 
+#define REF_DET_MATH
 #include "ref_image_shim.h"
 
 namespace ref {

@@ -1,4 +1,6 @@
 """Shared helpers of the parity tests: build a scene, render it with the CUDA renderer and with the CPU oracle, compare."""
+import os
+
 import numpy as np
 
 import oracle_lib as O
@@ -17,8 +19,19 @@ def half_ulp_diff(a, b):
     return np.abs(ai - bi)
 
 
+def denoised_ulps(g, c):
+    """fp16 ulp distance per channel of two RT_DENOISED images; NaN on both sides (0 / 0 of the bilateral weights next to a light, a zero
+    refraction direction) counts as equal - the two processors spell NaN differently."""
+    ulps = half_ulp_diff(g, c)
+    ulps[np.isnan(g.astype(np.float32)) & np.isnan(c.astype(np.float32))] = 0
+    return ulps
+
+
 def mismatch_fraction(a, b):
+    """Fraction of pixels that differ; a NaN on both sides counts as equal (the two processors spell NaN differently)."""
     ne = a != b
+    if a.dtype.kind == "f":
+        ne &= ~(np.isnan(a) & np.isnan(b))
     if ne.ndim == 3:
         ne = ne.any(axis=2)
     return float(ne.mean())
@@ -38,10 +51,9 @@ def setup_pair(renderer, scene, width, height, sky=None):
     return osc, ofr
 
 
-def check_frame(renderer, ofr, exact_fraction=0.0, radiance_fraction=0.0, denoise_ulps=2, images=None):
-    """Compares the storage images of the last frame. Integer / G-buffer images must match bit-exactly on all but
-    `exact_fraction` of the pixels; radiance images likewise with `radiance_fraction`; RT_DENOISED within `denoise_ulps`
-    fp16 ulps (libm pow/exp differ between CUDA and glibc)."""
+def check_frame(renderer, ofr, exact_fraction=0.0, radiance_fraction=0.0, denoise_ulps=0, images=None):
+    """Compares the storage images of the last frame with the oracle's. Since the leaf transcendentals are pinned too (include/gk_detmath.h)
+    every image, RT_DENOISED included, is expected bit-identical; the fraction arguments remain for experiments and default to 0."""
     report = {}
     for name in images or (EXACT_IMAGES + RADIANCE_IMAGES):
         g, c = renderer.readback(RT[name]), ofr.image(RT[name])
@@ -49,8 +61,7 @@ def check_frame(renderer, ofr, exact_fraction=0.0, radiance_fraction=0.0, denois
         report[name] = frac
         limit = exact_fraction if name in EXACT_IMAGES else radiance_fraction
         assert frac <= limit, f"{name}: {frac:.3e} of the pixels differ from the oracle (limit {limit:.1e})"
-    g, c = renderer.readback(RT["DENOISED"]), ofr.image(RT["DENOISED"])
-    ulps = half_ulp_diff(g, c)
+    ulps = denoised_ulps(renderer.readback(RT["DENOISED"]), ofr.image(RT["DENOISED"]))
     report["DENOISED_max_ulps"] = int(ulps.max())
     bad = float((ulps > denoise_ulps).any(axis=2).mean())
     assert bad <= max(radiance_fraction, exact_fraction), f"RT_DENOISED: {bad:.3e} of the pixels differ by more than {denoise_ulps} fp16 ulps"

@@ -40,3 +40,45 @@ def test_constant_division_by_multiply_and_two_fmas_is_exact():
         r = (a.astype(np.float64) - q.astype(np.float64) * b).astype(np.float32)           # fma(-q, b, a): exact product, one rounding
         got = (q.astype(np.float64) + r.astype(np.float64) * np.float64(rb)).astype(np.float32)  # fma(r, rb, q)
         assert np.array_equal(got, a / f(b))
+
+
+def _det(L, fn, a, b=0.0):
+    L.gko_det_math.restype = C.c_float
+    L.gko_det_math.argtypes = [C.c_int, C.c_float, C.c_float]
+    return L.gko_det_math(fn, float(a), float(b))
+
+
+def _ulps(got, ref):
+    return abs(np.float64(got) - ref) / np.spacing(np.float32(max(abs(ref), 2.0 ** -100)))
+
+
+def test_det_leaf_transcendentals_accuracy_and_special_values():
+    """gk_det_atan2f / acosf / expf / logf / powf (sky lookup, bilateral weights, tonemappers): a few ulp from the exact function over the
+    ranges the renderer feeds them, and the C library's conventions at the special values."""
+    L = O.load()
+    rng = np.random.default_rng(4)
+    worst = dict(atan2=0.0, acos=0.0, exp=0.0, log=0.0, pow=0.0)
+    for _ in range(20000):
+        a, b = np.float32(rng.uniform(-1, 1)), np.float32(rng.uniform(-1, 1))
+        worst["atan2"] = max(worst["atan2"], _ulps(_det(L, 0, a, b), np.arctan2(np.float64(a), np.float64(b))))
+        worst["acos"] = max(worst["acos"], _ulps(_det(L, 1, a), np.arccos(np.float64(a))))
+        x = np.float32(-80.0 * rng.uniform() ** 2)
+        worst["exp"] = max(worst["exp"], _ulps(_det(L, 2, x), np.exp(np.float64(x))))
+        p = np.float32(10.0 ** rng.uniform(-6, 3))
+        worst["log"] = max(worst["log"], _ulps(_det(L, 3, p), np.log(np.float64(p))))
+        y = np.float32(rng.choice([1.33, 0.1593017578125, 78.84375, 2.2]))
+        base = np.float32(rng.uniform(0.05, 1.2)) if y > 50 else p
+        ref = np.float64(base) ** np.float64(y)
+        if 1e-30 < ref < 1e30:
+            # pow = exp(y log x): the error grows with |y ln x| (like a GPU's intrinsic), so it is measured relative to that
+            rel = abs(np.float64(_det(L, 4, base, y)) - ref) / ref
+            worst["pow"] = max(worst["pow"], rel / max(1.0, abs(np.float64(y) * np.log(np.float64(base)))))
+    assert worst["atan2"] <= 4 and worst["acos"] <= 2 and worst["exp"] <= 2 and worst["log"] <= 2 and worst["pow"] < 4e-7, worst
+    inf, nan = np.float32(np.inf), np.float32(np.nan)
+    assert _det(L, 0, 0.0, -1.0) == np.float32(np.pi) and _det(L, 0, 0.0, 1.0) == 0.0 and _det(L, 0, 1.0, 0.0) == np.float32(np.pi / 2) and _det(L, 0, -1.0, 0.0) == -np.float32(np.pi / 2)
+    assert _det(L, 1, 1.0) == 0.0 and _det(L, 1, -1.0) == np.float32(np.pi) and _det(L, 1, 0.0) == np.float32(np.pi / 2) and np.isnan(_det(L, 1, 1.5))
+    assert _det(L, 2, 0.0) == 1.0 and _det(L, 2, -200.0) == 0.0 and _det(L, 2, 100.0) == inf and 0 < _det(L, 2, -100.0) < 1e-40  # gradual underflow
+    assert _det(L, 3, 1.0) == 0.0 and _det(L, 3, 0.0) == -inf and np.isnan(_det(L, 3, -1.0)) and _det(L, 3, inf) == inf
+    assert _det(L, 4, 0.0, 1.33) == 0.0 and _det(L, 4, 5.0, 0.0) == 1.0 and np.isnan(_det(L, 4, -1.0, 1.33)) and _det(L, 4, inf, 2.0) == inf and _det(L, 4, 1.0, 78.0) == 1.0
+    for fn in range(5):
+        assert np.isnan(_det(L, fn, nan, 1.0))
