@@ -401,8 +401,8 @@ GK_DEV void enqueue(const PathView& V, int qi, bool want, uint32_t pixel, int re
 
 // ------------------------------------------------------------------------------------------------ kernels
 // Primary visibility + G-buffer (FPathTracingRendererV2::Init/PrimaryHit, Shading.slang:1187-1241, with the visibility
-// buffer lookup of FVisibilityBufferRayCasterV2::TracePrimaryRay, :338-494, replaced by a closest-hit cast of the same
-// pixel-corner ray), the buffer clear (Util.BufferClear.comp.slang:5-14), and the first ray of sample 0.
+// buffer lookup of FVisibilityBufferRayCasterV2::TracePrimaryRay, :338-494, replaced by a closest-hit cast through the pixel
+// centre, where the raster pass samples), the buffer clear (Util.BufferClear.comp.slang:5-14), and the first ray of sample 0.
 __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, const __grid_constant__ PathLanes L, FrameCfg cfg, unsigned long long* ray_counters) {
     const PathView& V = L.v[(blockIdx.x + blockIdx.y) % L.n];  // checkerboard of tiles over the lanes
     SceneView S = S_;

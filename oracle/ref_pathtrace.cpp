@@ -17,7 +17,7 @@
 //
 // What is hardware, not shader text, comes from the oracle through its service exports (gk_oracle.h): RayQuery = the oracle's
 // intersector (closest hit by (t, instance, primitive), any hit), the texture sampler, and the visibility buffer that the reference's
-// raster pass writes (the caller fills RT_MINIGBUFFER by casting pixel-corner rays). HLSL intrinsics (reflect, refract, distance, mul,
+// raster pass writes (the caller fills RT_MINIGBUFFER by casting rays through the pixel centres, gko_cast_visibility). HLSL intrinsics (reflect, refract, distance, mul,
 // ...) are defined here the way the oracle defines them, and sin / cos / atan2 / acos / exp / pow are the pinned kernels of include/gk_detmath.h. So this pins the integrator: the control flow, the order of RNG
 // draws, every shading formula and every image store of the RT pass. Built only when /root/reference is mounted. TEST INFRASTRUCTURE ONLY.
 #include <atomic>
