@@ -37,7 +37,7 @@ PRIMARY_BYTES_PER_PIXEL, REPROJECT_BYTES_PER_PIXEL, DENOISE_BYTES_PER_PIXEL = 36
 # Warp instructions per pixel of the two stencil kernels (ncu smsp__inst_executed.sum / 1920x1080, profiles/r01_ncu_misc.txt): both kernels
 # are bound by instruction issue, not by HBM - the reference's arithmetic (36 bilateral taps with an IEEE division and an exp each, 25
 # weighted taps with two divisions each) kept bit for bit - so the bench also reports them against the SM issue rate (4 warp instr / clk / SM).
-REPROJECT_WARP_INSTR_PER_PIXEL, DENOISE_WARP_INSTR_PER_PIXEL, SM_COUNT, ISSUE_PER_SM_CLK = 137084257 / 2073600, 177308860 / 2073600, 148, 4
+REPROJECT_WARP_INSTR_PER_PIXEL, DENOISE_WARP_INSTR_PER_PIXEL, SM_COUNT, ISSUE_PER_SM_CLK = 137084257 / 2073600, 287836077 / 2073600, 148, 4
 
 
 def load_peaks():

@@ -13,7 +13,7 @@
  * The leaf transcendentals - atan2/acos of the sky lookup (Shading.slang:194-199), exp of the bilateral weights
  * (Process.DenoiseJBF.comp.slang), pow of the tonemappers (Const_Func.slang:51-126) - never influence control flow, but two
  * libms round them differently and an fp16 store then flips here and there. They are pinned the same way (Cephes single-precision
- * kernels, plain mul/add, IEEE sqrt/div), so that every storage image is bit-identical between the CUDA renderer and its checker:
+ * kernels in plain mul/add, explicit fmaf in exp, IEEE sqrt/div), so that every storage image is bit-identical between the CUDA renderer and its checker:
  * gk_det_atan2f, gk_det_acosf, gk_det_expf, gk_det_logf, gk_det_powf. Errors vs. libm: a few ulp (tests/test_detmath.py); pow is
  * exp(y * log(x)), i.e. relative error ~1e-7 * |y ln x| like a GPU's intrinsic.
  */
@@ -101,25 +101,24 @@ GK_HD float gk_det_acosf(float x) {
     return 1.5707963267948966f - gk_det_asinf(x);
 }
 
-/* z * 2^n for n in [-300, 300], in at most three exactly representable power-of-two factors */
-GK_HD float gk_det_scalbnf(float z, int n) {
-    if (n > 127) { z = z * gk_det_bits2f(254u << 23); n -= 127; if (n > 127) { z = z * gk_det_bits2f(254u << 23); n -= 127; if (n > 127) n = 127; } }
-    else if (n < -126) { z = z * gk_det_bits2f(1u << 23); n += 126; if (n < -126) { z = z * gk_det_bits2f(1u << 23); n += 126; if (n < -126) n = -126; } }
-    return z * gk_det_bits2f((unsigned int)(n + 127) << 23);
-}
-
-GK_HD float gk_det_expf(float xx) {
-    if (xx != xx) return xx;
-    if (xx > 88.72283905206835f) return gk_det_bits2f(0x7F800000u);
-    if (xx < -103.278929903431851103f) return 0.0f;
-    float x = xx;
-    float z = floorf(1.44269504088896341f * x + 0.5f);
-    x = x - z * 0.693359375f;
-    x = x - z * -2.12194440e-4f;
-    const int n = (int)z;
-    z = x * x;
-    z = (((((1.9875691500e-4f * x + 1.3981999507e-3f) * x + 8.3334519073e-3f) * x + 4.1665795894e-2f) * x + 1.6666665459e-1f) * x + 5.0000001201e-1f) * z + x + 1.0f;
-    return gk_det_scalbnf(z, n);
+/* exp with gradual underflow. The polynomial and the reduction use explicit fused multiply-adds (fmaf rounds once on both processors), and
+ * the scaling by 2^n is two exact power-of-two factors, so the kernel stays short: it runs 42 times per pixel in the bilateral filter. */
+GK_HD float gk_det_expf(float x) {
+    if (!(x >= -103.9720840454f)) return x != x ? x : 0.0f;  /* below ln(2^-150): 0; NaN in -> the same NaN out */
+    if (x > 88.72283905206835f) return gk_det_bits2f(0x7F800000u);
+    const float k = floorf(fmaf(x, 1.44269504088896341f, 0.5f));
+    float r = fmaf(k, -0.693359375f, x);
+    r = fmaf(k, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    p = fmaf(p, r * r, r) + 1.0f;
+    const int n = (int)k;            /* -150 .. 128 */
+    const int n1 = n >> 1, n2 = n - n1; /* both factors are normal numbers; only the last product can round (into the subnormals) */
+    return p * gk_det_bits2f((unsigned int)(n1 + 127) << 23) * gk_det_bits2f((unsigned int)(n2 + 127) << 23);
 }
 
 /* natural logarithm of a positive finite number; 0 -> -inf, negative / NaN -> NaN, +inf -> +inf */

@@ -9,7 +9,8 @@ python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_n1.json 2> $O/${TAG}_ben
 tail -c 2500 $O/${TAG}_bench_n1.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches.csv \
     python scripts/profile_frame.py 2 > $O/${TAG}_launches.log 2>&1
-for k in k_trace k_shade; do
+# QUICK=1 skips the two big captures (reuse them when only the small kernels changed)
+for k in $([ -n "$QUICK" ] || echo k_trace k_shade); do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 10 -c 2 -o $O/${TAG}_prof_$k -f \
       python scripts/profile_frame.py 1 > $O/${TAG}_prof_$k.log 2>&1
 done
