@@ -106,6 +106,33 @@ uint32_t gkhost_scene_perturb_model(void* h, uint32_t model, uint32_t step, uint
     std::memcpy(out, v.data(), v.size() * 2);
     return n;
 }
+// FProcModel::CreateCornellBox / CreateBox / CreateSphere by number (gk::CreateProcModel). vertices: 13 words each (position 3, normal 3,
+// tangent 4, uv 2 as floats, material slot as uint32); pass NULL arrays to query the counts. Returns the number of materials pushed.
+uint32_t gkhost_proc_model(int kind, const float* args, void* vertices, uint32_t* vertex_count, uint32_t* indices, uint32_t* index_count,
+                           GkMaterial* materials, GkLightObject* light) {
+    std::vector<GkMaterial> mats;
+    std::vector<GkLightObject> lights;
+    gk::Model m = gk::CreateProcModel(kind, args, mats, lights);
+    *vertex_count = (uint32_t)m.vertices.size();
+    *index_count = (uint32_t)m.indices.size();
+    if (vertices) {
+        uint32_t* w = static_cast<uint32_t*>(vertices);
+        for (const auto& v : m.vertices) {
+            const float f[12] = {v.Position.x, v.Position.y, v.Position.z, v.Normal.x, v.Normal.y, v.Normal.z, v.Tangent.x, v.Tangent.y, v.Tangent.z, v.Tangent.w,
+                                 v.TexCoord.x, v.TexCoord.y};
+            std::memcpy(w, f, 48);
+            w[12] = v.MaterialIndex;
+            w += 13;
+        }
+    }
+    if (indices) std::memcpy(indices, m.indices.data(), m.indices.size() * 4);
+    if (materials) std::memcpy(materials, mats.data(), mats.size() * sizeof(GkMaterial));
+    if (light && !lights.empty()) *light = lights[0];
+    return (uint32_t)mats.size();
+}
+void gkhost_material(int kind, const float* diffuse, float a, float b, GkMaterial* out) {
+    *out = gk::MakeMaterialByKind(kind, gk::vec3(diffuse[0], diffuse[1], diffuse[2]), a, b);
+}
 void gkhost_make_sky(uint32_t width, uint32_t height, float* rgba) {
     std::vector<float> v;
     gk::MakeProceduralSky(width, height, v);

@@ -616,4 +616,19 @@ void MakeProceduralSky(uint32_t width, uint32_t height, std::vector<float>& rgba
     }
 }
 
+// The procedural generators by number (0 Cornell box: args = scale; 1 box: p0, p1; 2 sphere: centre, radius), for tools and tests.
+Model CreateProcModel(int kind, const float* a, std::vector<GkMaterial>& materials, std::vector<GkLightObject>& lights) {
+    if (kind == 0) return CreateCornellBox(a[0], materials, lights);
+    if (kind == 1) return CreateBox(vec3(a[0], a[1], a[2]), vec3(a[3], a[4], a[5]));
+    return CreateSphere(vec3(a[0], a[1], a[2]), a[3]);
+}
+GkMaterial MakeMaterialByKind(int kind, vec3 d, float a, float b) {  // Material.hpp:10-38 in declaration order
+    switch (kind) {
+        case 0: return MaterialLambertian(d);
+        case 1: return MaterialMetallic(d, a);
+        case 2: return MaterialMixture(d, a);
+        case 3: return MaterialDielectric(a, b);
+        default: return MaterialDiffuseLight(d);
+    }
+}
 }  // namespace gk

@@ -124,6 +124,8 @@ private:
 };
 
 GkMaterial MaterialLambertian(vec3 diffuse);
+Model CreateProcModel(int kind, const float* args, std::vector<GkMaterial>& materials, std::vector<GkLightObject>& lights);
+GkMaterial MakeMaterialByKind(int kind, vec3 diffuse, float a, float b);
 GkMaterial MaterialMetallic(vec3 diffuse, float fuzziness);
 GkMaterial MaterialMixture(vec3 diffuse, float fuzziness);
 GkMaterial MaterialDielectric(float refractionIndex, float fuzziness);

@@ -693,3 +693,48 @@ def test_sky_sh_projection_is_pinned_to_the_references_source():
         got = np.float32([[mine.coefficients[c][i] for i in range(9)] for c in range(3)]).reshape(-1)
         assert np.array_equal(got.view(np.uint32), np.float32(list(out)).view(np.uint32)), (img.shape, got[:4], list(out)[:4])
         assert np.abs(got).max() > 0
+
+
+REF_PM = os.path.join(os.path.dirname(O.TINYBVH), "libref_procmodel.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PM), reason="oracle/_ref not built (reference not mounted)")
+def test_procedural_models_and_materials_are_pinned_to_the_references_source():
+    """The inputs of BASELINE configs 1 and 2: FProcModel::CreateCornellBox / CreateBox / CreateSphere (src/Assets/FProcModel.cpp:9-254) and the
+    Material constructors (src/Assets/Material.hpp:8-81), compiled unmodified from the files where they lie (oracle/ref_procmodel.cpp), against
+    the host library's generators (gkhost_proc_model / gkhost_material): every vertex (position, normal, tangent, uv, material slot), every
+    index, the four Cornell materials, the quad light and all five material kinds bit-identical."""
+    import ctypes as C
+    from gknextengine_b200.host import lib as hostlib
+    ref, H = C.CDLL(REF_PM), hostlib()
+    sig = [C.c_int, C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
+    for fn in (ref.ref_proc_model, H.gkhost_proc_model):
+        fn.argtypes, fn.restype = sig, C.c_uint32
+    for fn in (ref.ref_material, H.gkhost_material):
+        fn.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_void_p]
+
+    def gen(fn, kind, args):
+        a = (C.c_float * 6)(*args)
+        nv, ni = C.c_uint32(), C.c_uint32()
+        fn(kind, a, None, C.byref(nv), None, C.byref(ni), None, None)
+        v, i = np.zeros((nv.value, 13), np.uint32), np.zeros(ni.value, np.uint32)
+        mats, light = np.zeros((8, 16), np.uint32), np.zeros(20, np.uint32)
+        nm = fn(kind, a, v.ctypes.data, C.byref(nv), i.ctypes.data, C.byref(ni), mats.ctypes.data, light.ctypes.data)
+        return v, i, mats[:nm, :14], light  # 14 words: the 56 bytes the reference's struct defines (the rest is padding there, reserved words here)
+
+    rng = np.random.default_rng(8)
+    cases = [(0, [5.55]), (0, [1.0]), (1, [-1000, -0.5, -1000, 1000, 0, 1000]), (1, [-0.8, 0, -0.8, 0.8, 1.6, 0.8]), (2, [0, 0, 0, 0.2]), (2, [0, 0, 0, 1.0]),
+             (2, [*rng.uniform(-5, 5, 3), 0.37])]
+    for kind, args in cases:
+        args = list(args) + [0.0] * (6 - len(args))
+        rv, ri, rm, rl = gen(ref.ref_proc_model, kind, args)
+        hv, hi, hm, hl = gen(H.gkhost_proc_model, kind, args)
+        assert rv.shape == hv.shape and np.array_equal(rv, hv), (kind, args, np.argwhere(rv != hv)[:4].tolist())
+        assert np.array_equal(ri, hi) and np.array_equal(rm, hm) and np.array_equal(rl, hl), (kind, args)
+    assert gen(ref.ref_proc_model, 2, [0, 0, 0, 0.2, 0, 0])[0].shape == (561, 13) and len(gen(ref.ref_proc_model, 0, [5.55] + [0] * 5)[1]) == 36
+    d = (C.c_float * 3)(0.3, 0.6, 0.9)
+    for kind, a, b in ((0, 0, 0), (1, 0.25, 0), (2, 0.5, 0), (3, 1.5, 0.1), (4, 0, 0)):
+        x, y = np.zeros(16, np.uint32), np.zeros(16, np.uint32)
+        ref.ref_material(kind, d, a, b, x.ctypes.data)
+        H.gkhost_material(kind, d, a, b, y.ctypes.data)
+        assert np.array_equal(x[:14], y[:14]), (kind, x[:14].tolist(), y[:14].tolist())
