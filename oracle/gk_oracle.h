@@ -19,7 +19,8 @@
  *   - EvaluateSH / SampleIBL (the SH sky used by the probe bake), against the reference's dual-language GLSL header compiled as
  *     C++ from /root/reference/assets/shaders/glsl_legacy/common/SampleIBL.glsl into oracle/_ref/libref_sh.so (oracle/ref_sh.cpp),
  *     and the host's ProjectHdrToSh against src/Assets/Texture.cpp:180-258 compiled unmodified (same file)
- *   - the host library's procedural models and materials against src/Assets/FProcModel.cpp + Material.hpp compiled unmodified (oracle/ref_procmodel.cpp)
+ *   - the host library's procedural models, materials and the two procedural scenes (node positions, ids, material table) against
+ *     src/Assets/FProcModel.cpp, Material.hpp and src/Runtime/SceneList.cpp compiled unmodified (oracle/ref_procmodel.cpp)
  *   - fixture known-answers generated here with libstdc++, in tests/golden/.
  * "Parity unpinned" remains true only for what is hardware or driver in the reference, not source: the Vulkan driver's
  * ray/triangle rule, the raster pass behind the visibility buffer, the texture sampler and the GPU's transcendental intrinsics.

@@ -3,6 +3,7 @@
 // material table and quad light that BASELINE configs 1 and 2 are rendered from:
 //   src/Assets/FProcModel.cpp  9-254   AddTriangle, FProcModel::CreateCornellBox, CreateBox, CreateSphere   (copied unmodified)
 //   src/Assets/Material.hpp    8-81    struct Material with its constructors, struct FMaterial               (copied unmodified)
+//   src/Runtime/SceneList.cpp  27-227  CreateMaterial, AddRayTracingInOneWeekendCommonScene, RayTracingInOneWeekend, CornellBox     (copied unmodified)
 // This file supplies what those lines refer to but which lives elsewhere in the engine: the few glm types they use (glm is not in this
 // image), Vertex (Vertex.hpp:10-16), LightObject (BasicTypes.slang:171-183, layout pinned by ref_layout_check), the Model constructor
 // (Model.hpp:146; the MikkTSpace pass it triggers is an external library and is not reproduced) and the FProcModel declaration.
@@ -10,9 +11,13 @@
 #define _USE_MATH_DEFINES
 #include <math.h>
 
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -31,6 +36,16 @@ struct vec3 {
     template <class A, class B, class C> vec3(A a, B b, C c) : x((float)a), y((float)b), z((float)c) {}
 };
 inline vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline float length(const vec3& a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+// rotations and the camera matrix go through glm in the engine; here only their arguments are recorded (the scene pins compare translations,
+// model / instance / material ids and the material table, which is where the random stream goes)
+struct quat {
+    float w, x, y, z; vec3 euler; bool from_euler;
+    quat(float w_, float x_, float y_, float z_) : w(w_), x(x_), y(y_), z(z_), from_euler(false) {}
+    explicit quat(const vec3& e) : w(0), x(0), y(0), z(0), euler(e), from_euler(true) {}
+};
+struct mat4 { vec3 eye, center, up; };
+inline mat4 lookAt(const vec3& eye, const vec3& center, const vec3& up) { return mat4{eye, center, up}; }
 struct vec4 {
     float x, y, z, w;
     vec4() : x(0), y(0), z(0), w(0) {}
@@ -59,7 +74,53 @@ public:
     static uint32_t CreateCornellBox(const float scale, std::vector<Model>& models, std::vector<FMaterial>& materials, std::vector<LightObject>& lights);
 };
 #include "procmodel_gen.inc"
+struct Texture;
+struct AnimationTrack {};
+struct Camera { std::string name; glm::mat4 ModelView; float FieldOfView, Aperture, FocalDistance; };
+struct EnvironmentSetting {  // Model.hpp:20-38, the members the scene functions set
+    std::vector<Camera> cameras;
+    float ControlSpeed = 5.0f;
+    bool GammaCorrection = true, HasSky = true, HasSun = false;
+};
 }  // namespace Assets
+namespace JPH { struct BodyID { uint32_t id = 0; }; enum class EMotionType { Static, Kinematic, Dynamic }; }
+namespace Assets {
+class Node {  // Node.h:13-62, what the scene functions call
+public:
+    enum class ENodeMobility { Static, Dynamic, Kinematic };
+    static std::shared_ptr<Node> CreateNode(std::string name, glm::vec3 translation, glm::quat rotation, glm::vec3 scale, uint32_t modelId, uint32_t instanceId, bool replace) {
+        auto n = std::make_shared<Node>();
+        n->translation = translation; n->scale = scale; n->modelId = modelId; n->instanceId = instanceId;
+        n->materials.fill(0u);
+        return n;
+    }
+    void SetVisible(bool v) { visible = v; }
+    void SetMaterial(const std::array<uint32_t, 16>& m) { materials = m; }
+    void SetMobility(ENodeMobility) {}
+    void BindPhysicsBody(JPH::BodyID) {}
+    glm::vec3 translation, scale;
+    uint32_t modelId = 0, instanceId = 0;
+    bool visible = false;
+    std::array<uint32_t, 16> materials;
+};
+}  // namespace Assets
+struct PhysicsShim { JPH::BodyID CreateSphereBody(glm::vec3, float, JPH::EMotionType) { return JPH::BodyID{}; } };
+struct NextEngine {
+    static NextEngine* GetInstance() { static NextEngine e; return &e; }
+    PhysicsShim* GetPhysicsEngine() { static PhysicsShim p; return &p; }
+};
+namespace Utilities { namespace NameHelper { inline std::string RandomName(size_t) { return "node"; } } }  // names come from std::random_device in the engine
+namespace scenelist {
+#include "scenelist_gen.inc"
+// SceneList::LoadScene (SceneList.cpp:259-285) for the two procedural names
+bool Load(const std::string& filename, Assets::EnvironmentSetting& camera, std::vector<std::shared_ptr<Assets::Node>>& nodes, std::vector<Assets::Model>& models,
+          std::vector<Assets::FMaterial>& materials, std::vector<Assets::LightObject>& lights, std::vector<Assets::AnimationTrack>& tracks) {
+    materials.push_back({Material::Lambertian(vec3(0.73f, 0.73f, 0.73f)), "root_default"});
+    if (filename == "CornellBox.proc") { CornellBox(camera, nodes, models, materials, lights, tracks); return true; }
+    if (filename == "RTIO.proc") { RayTracingInOneWeekend(camera, nodes, models, materials, lights, tracks); return true; }
+    return false;
+}
+}  // namespace scenelist
 
 using namespace Assets;
 static_assert(sizeof(Material) == 64 && sizeof(LightObject) == 80, "reference layouts");
@@ -92,6 +153,30 @@ uint32_t ref_proc_model(int kind, const float* a, void* vertices, uint32_t* vert
         for (size_t i = 0; i < mats.size(); ++i) std::memcpy(static_cast<char*>(materials) + 64 * i, &mats[i].gpuMaterial_, 64);
     if (light && !lights.empty()) std::memcpy(light, &lights[0], 80);
     return (uint32_t)mats.size();
+}
+// The whole procedural scene: per node 24 words (translation 3 floats, scale 3 floats, modelId, instanceId, 16 material ids), the material
+// table (64 bytes each), counts[0..3] = nodes, materials, models, lights; flags[0..1] = HasSky, HasSun. NULL arrays to query the counts.
+int ref_scene(const char* name, uint32_t* nodes24, void* materials, uint32_t* counts, uint32_t* flags) {
+    Assets::EnvironmentSetting env;
+    std::vector<std::shared_ptr<Assets::Node>> nodes;
+    std::vector<Model> models;
+    std::vector<FMaterial> mats;
+    std::vector<LightObject> lights;
+    std::vector<Assets::AnimationTrack> tracks;
+    if (!scenelist::Load(name, env, nodes, models, mats, lights, tracks)) return 0;
+    counts[0] = (uint32_t)nodes.size(); counts[1] = (uint32_t)mats.size(); counts[2] = (uint32_t)models.size(); counts[3] = (uint32_t)lights.size();
+    flags[0] = env.HasSky; flags[1] = env.HasSun;
+    if (nodes24)
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            uint32_t* w = nodes24 + 24 * i;
+            const float f[6] = {nodes[i]->translation.x, nodes[i]->translation.y, nodes[i]->translation.z, nodes[i]->scale.x, nodes[i]->scale.y, nodes[i]->scale.z};
+            std::memcpy(w, f, 24);
+            w[6] = nodes[i]->modelId; w[7] = nodes[i]->instanceId;
+            for (int k = 0; k < 16; ++k) w[8 + k] = nodes[i]->materials[k];
+        }
+    if (materials)
+        for (size_t i = 0; i < mats.size(); ++i) std::memcpy(static_cast<char*>(materials) + 64 * i, &mats[i].gpuMaterial_, 64);
+    return 1;
 }
 // Material::Lambertian / Metallic / Mixture / Dielectric / DiffuseLight (declaration order 0..4)
 void ref_material(int kind, const float* d, float a, float b, void* out64) {

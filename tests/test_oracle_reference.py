@@ -738,3 +738,42 @@ def test_procedural_models_and_materials_are_pinned_to_the_references_source():
         ref.ref_material(kind, d, a, b, x.ctypes.data)
         H.gkhost_material(kind, d, a, b, y.ctypes.data)
         assert np.array_equal(x[:14], y[:14]), (kind, x[:14].tolist(), y[:14].tolist())
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PM), reason="oracle/_ref not built (reference not mounted)")
+@pytest.mark.parametrize("name", ["CornellBox.proc", "RTIO.proc"])
+def test_procedural_scenes_are_pinned_to_the_references_source(name):
+    """The scenes BASELINE configs 1 and 2 are rendered from: SceneList's CornellBox and RayTracingInOneWeekend (src/Runtime/SceneList.cpp:27-227,
+    with LoadScene's root material, :262), compiled unmodified (oracle/ref_procmodel.cpp) against the host library's scene of the same name:
+    node for node the translation (bit pattern), model index, instance id and the 16 material slots, and the whole material table - for
+    RTIO.proc that is the mt19937(42) stream deciding 1 935 sphere positions and 1 940 materials. Rotations, scales and the camera go through
+    glm in the engine (not in the mount) and are not compared here beyond scale = 1 for the RTIOW spheres."""
+    import ctypes as C
+    from gknextengine_b200._abi import GkMaterial, GkNodeProxy
+    ref = C.CDLL(REF_PM)
+    ref.ref_scene.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32 * 4), C.POINTER(C.c_uint32 * 2)]
+    counts, flags = (C.c_uint32 * 4)(), (C.c_uint32 * 2)()
+    assert ref.ref_scene(name.encode(), None, None, counts, flags) == 1
+    nn, nm = counts[0], counts[1]
+    rn, rm = np.zeros((nn, 24), np.uint32), np.zeros((nm, 16), np.uint32)
+    ref.ref_scene(name.encode(), rn.ctypes.data, rm.ctypes.data, counts, flags)
+    scene = host.Scene(name)
+    scene.update_nodes()
+    hp, hn = scene.nodes()
+    mp, hm = scene.materials()
+    assert (hn, hm) == (nn, nm) and scene.counts()["models"] == counts[2], (hn, hm, list(counts))
+    if name == "RTIO.proc":
+        assert (nn, nm) == (1939, 1940)  # SURVEY appendix C
+    hnodes = np.frombuffer((C.c_uint8 * (C.sizeof(GkNodeProxy) * hn)).from_address(C.addressof(hp.contents) if hasattr(hp, "contents") else C.cast(hp, C.c_void_p).value),
+                           dtype=np.uint32).reshape(hn, -1)
+    # GkNodeProxy words: instanceId 0, modelId 1, visible 2, nort 3, worldTS 4..19 (column-major: translation = words 16..18), prevTS 20..35, matId 36..51
+    assert np.array_equal(hnodes[:, 16:19], rn[:, 0:3]), np.argwhere(hnodes[:, 16:19] != rn[:, 0:3])[:4].tolist()
+    # NodeProxy.modelId = model * 10 + section (Scene.cpp:475); these models have one section
+    assert np.array_equal(hnodes[:, 1], rn[:, 6] * 10) and np.array_equal(hnodes[:, 0], rn[:, 7]) and np.array_equal(hnodes[:, 36:52], rn[:, 8:24])
+    if name == "RTIO.proc":
+        ident = np.float32([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]).view(np.uint32)
+        assert (hnodes[:, 4:16] == ident).all() and (rn[:, 3:6] == np.float32(1).view(np.uint32)).all()
+    hmats = np.frombuffer((C.c_uint8 * (C.sizeof(GkMaterial) * hm)).from_address(C.cast(mp, C.c_void_p).value), dtype=np.uint32).reshape(hm, 16)
+    assert np.array_equal(hmats[:, :14], rm[:, :14]), np.argwhere(hmats[:, :14] != rm[:, :14])[:4].tolist()
+    ubo = scene.ubo(64, 36, 1)
+    assert (bool(ubo.HasSky), bool(ubo.HasSun)) == (bool(flags[0]), bool(flags[1]))
