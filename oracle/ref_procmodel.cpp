@@ -4,6 +4,7 @@
 //   src/Assets/FProcModel.cpp  9-254   AddTriangle, FProcModel::CreateCornellBox, CreateBox, CreateSphere   (copied unmodified)
 //   src/Assets/Material.hpp    8-81    struct Material with its constructors, struct FMaterial               (copied unmodified)
 //   src/Runtime/SceneList.cpp  27-227  CreateMaterial, AddRayTracingInOneWeekendCommonScene, RayTracingInOneWeekend, CornellBox     (copied unmodified)
+//   src/Runtime/Engine.cpp     642-651 HaltonSequence (the TAA jitter of the projection, :771-777)                                    (copied unmodified)
 // This file supplies what those lines refer to but which lives elsewhere in the engine: the few glm types they use (glm is not in this
 // image), Vertex (Vertex.hpp:10-16), LightObject (BasicTypes.slang:171-183, layout pinned by ref_layout_check), the Model constructor
 // (Model.hpp:146; the MikkTSpace pass it triggers is an external library and is not reproduced) and the FProcModel declaration.
@@ -122,6 +123,10 @@ bool Load(const std::string& filename, Assets::EnvironmentSetting& camera, std::
 }
 }  // namespace scenelist
 
+namespace engine {
+#include "halton_gen.inc"
+}
+
 using namespace Assets;
 static_assert(sizeof(Material) == 64 && sizeof(LightObject) == 80, "reference layouts");
 
@@ -178,6 +183,7 @@ int ref_scene(const char* name, uint32_t* nodes24, void* materials, uint32_t* co
         for (size_t i = 0; i < mats.size(); ++i) std::memcpy(static_cast<char*>(materials) + 64 * i, &mats[i].gpuMaterial_, 64);
     return 1;
 }
+float ref_halton(int index, int base) { return engine::HaltonSequence(index, base); }
 // Material::Lambertian / Metallic / Mixture / Dielectric / DiffuseLight (declaration order 0..4)
 void ref_material(int kind, const float* d, float a, float b, void* out64) {
     Material m;

@@ -777,3 +777,25 @@ def test_procedural_scenes_are_pinned_to_the_references_source(name):
     assert np.array_equal(hmats[:, :14], rm[:, :14]), np.argwhere(hmats[:, :14] != rm[:, :14])[:4].tolist()
     ubo = scene.ubo(64, 36, 1)
     assert (bool(ubo.HasSky), bool(ubo.HasSun)) == (bool(flags[0]), bool(flags[1]))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PM), reason="oracle/_ref not built (reference not mounted)")
+def test_taa_jitter_is_pinned_to_the_references_halton_sequence():
+    """The sub-pixel jitter of the projection (Engine.cpp:771-777) comes from HaltonSequence (Engine.cpp:642-651, compiled unmodified): the host
+    library's UBO must carry (halton(i + 1, 2) - 0.5) / width * 2 and (halton(i + 1, 3) - 0.5) / height * 2 in Projection[2][0..1], bit for bit,
+    for every frame of the 16-frame cycle and beyond."""
+    import ctypes as C
+    ref = C.CDLL(REF_PM)
+    ref.ref_halton.restype, ref.ref_halton.argtypes = C.c_float, [C.c_int, C.c_int]
+    W, H, TF = 1920, 1080, 16
+    scene = host.Scene("CornellBox.proc", taa=True, temporal_frames=TF)
+    f = np.float32
+    for frame in list(range(0, 40)) + [1000, 65535]:
+        u = scene.ubo(W, H, frame)
+        i = frame % TF
+        jx = (f(ref.ref_halton(i + 1, 2)) - f(0.5)) / f(W) * f(2.0)
+        jy = (f(ref.ref_halton(i + 1, 3)) - f(0.5)) / f(H) * f(2.0)
+        got = np.float32([u.Projection.m[2][0], u.Projection.m[2][1]])
+        assert np.array_equal(got.view(np.uint32), np.float32([jx, jy]).view(np.uint32)), (frame, got, jx, jy)
+    u = host.Scene("CornellBox.proc", taa=False).ubo(W, H, 3)
+    assert u.Projection.m[2][0] == 0.0 and u.Projection.m[2][1] == 0.0
