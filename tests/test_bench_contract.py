@@ -1,0 +1,39 @@
+"""The bench contract on CPU: the reference arm of bench.py runs here (it times the CPU port), prints exactly one JSON line with the keys the
+driver reads, and the committed round profile of the CUDA arm carries the same contract plus roofline / cpu_baseline / e2e / clocks."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert BASE_KEYS <= set(j) and j["impl"] == "reference" and j["metric"] and j["unit"] == "Mrays/s" and j["higher_is_better"] is True
+    assert j["value"] > 0 and j["n_gpus"] == 1 and j["steps"] == 1 and "workload" in j["config"] and j["vs_baseline"] is None
+    cb = j["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_committed_round_profile_carries_the_contract():
+    path = os.path.join(ROOT, "profiles", "r01_bench_n1.json")
+    j = json.loads([ln for ln in open(path).read().splitlines() if ln.strip().startswith("{")][-1])
+    assert BASE_KEYS <= set(j) and j["n_gpus"] == 1 and j["warmup"] >= 3 and j["gpu_launches"] > 0 and j["data"].startswith("synthetic")
+    r = j["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
+    e = j["e2e"]
+    assert 0 < e["value"] <= j["value"] * 1.001 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    c = j["clocks"]
+    assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    cb = j["cpu_baseline"]
+    assert cb["value"] > 0 and cb["cores"] >= 1 and cb["kind"] == "port" and cb["sample"]
+    for k in ("reproject", "denoise"):
+        assert j["roofline_stencils"][k]["bound"] == "issue" and 0 < j["roofline_stencils"][k]["issue_frac"] < 1
