@@ -11,7 +11,8 @@ SURVEY 8e); the un-normalised radiance sums are reduced to rank 0 with NCCL and 
   e2e            the same through the public API with HOST buffers: NodeProxy[] + UBO H2D from pinned memory and the
                  RT_DENOISED D2H read every step, wall-clock between synchronisations
   roofline       dominant kernel (k_trace) against the measured HBM peak, see DESIGN.md for the byte accounting
-  cpu_baseline   the CPU oracle (scalar port of the reference shaders) on the host cores, bounded sample of the same frame
+  cpu_baseline   the reference's RT-pass shaders compiled as C++ (oracle/_ref, kind "reference") or, without them, the CPU oracle port (kind "port")
+                 on all host cores, bounded sample of the same frame
 
 --impl reference times that CPU port alone (the reference's Slang/Vulkan path cannot run without slangc/Vulkan).
 """
@@ -105,8 +106,67 @@ def cpu_port_sample(scene, sky, ubo, params, bands, band_rows, threads=0):
     return rays, secs
 
 
+class CompiledReference:
+    """The reference's own RT pass - Util.BufferClear + Core.PathTracing with the Shading.slang / AmbientCube.slang classes they run - compiled
+    as C++ from the reference's sources into oracle/_ref/libref_pathtrace.so (oracle/ref_pathtrace.cpp; built when the reference is mounted, the
+    binary travels with the repo). Ray queries, the texture sampler and the visibility buffer of the raster pass are served by the CPU oracle's
+    BVH (they are hardware in the reference). Multi-threaded over rows."""
+
+    def __init__(self, scene, sky):
+        import ctypes as C
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        from gknextengine_b200 import RT
+        from gknextengine_b200._abi import GK_CUBE_COUNT
+        from gknextengine_b200.renderer import CudaPathTracingRenderer as R
+        path = os.path.join(os.path.dirname(O.TINYBVH), "libref_pathtrace.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.C, self.lib = C, C.CDLL(path)
+        self.lib.ref_pathtrace_rows.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        self.osc = O.OracleScene(scene, sky)
+        # zero probe state (SURVEY 8d config 1 / 2); the shader dereferences the probe arrays, so they must exist
+        self.osc.set_probes(np.zeros(GK_CUBE_COUNT, R.CUBE_DTYPE), np.zeros(GK_CUBE_COUNT, R.VOXEL_DTYPE))
+        self.osc.L.gko_cast_visibility_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+        W, H = WIDTH, HEIGHT
+        self.images = {"SINGLE_DIFFUSE": np.zeros((H, W, 4), np.float16), "SINGLE_SPECULAR": np.zeros((H, W, 4), np.float16), "ALBEDO": np.zeros((H, W, 4), np.float16),
+                       "NORMAL": np.zeros((H, W, 4), np.float16), "OBJEDCTID_0": np.zeros((H, W), np.uint32), "MINIGBUFFER": np.zeros((H, W), np.uint32),
+                       "MOTIONVECTOR": np.zeros((H, W, 2), np.float32), "PREV_DEPTHBUFFER": np.zeros((H, W), np.float32), "MOTIONMOMENT": np.zeros((H, W), np.uint16)}
+        self.table = (C.c_void_p * 64)()
+        for k, v in self.images.items():
+            self.table[RT[k]] = v.ctypes.data
+
+    def sample(self, ubo, bands, band_rows, threads=0):
+        """(rays, seconds) of the RT pass on `bands` evenly spaced bands of `band_rows` rows; the visibility cast stands in for the raster pass
+        and is timed and counted as the primary rays, like in the CUDA renderer's rt pass."""
+        C = self.C
+        counters = (C.c_uint64 * 2)()
+        rays, secs = 0, 0.0
+        for b in range(bands):
+            y0 = int((b + 0.5) * HEIGHT / bands) - band_rows // 2
+            t0 = time.perf_counter()
+            self.osc.L.gko_cast_visibility_rows(self.osc._h, C.byref(ubo), WIDTH, HEIGHT, y0, y0 + band_rows, threads, self.images["MINIGBUFFER"].ctypes.data)
+            self.lib.ref_pathtrace_rows(self.osc._h, C.byref(ubo), self.table, WIDTH, HEIGHT, y0, y0 + band_rows, threads, counters)
+            secs += time.perf_counter() - t0
+            rays += band_rows * WIDTH + counters[0] + counters[1]
+        return rays, secs
+
+
+def cpu_sample(scene, sky, ubo, params, bands, band_rows):
+    """The CPU baseline of one frame sample: the compiled reference shaders when oracle/_ref holds them (kind "reference"), else the oracle
+    port (kind "port"). Returns (rays, seconds, kind, description)."""
+    try:
+        ref = CompiledReference(scene, sky)
+        rays, secs = ref.sample(ubo, bands, band_rows)
+        return rays, secs, "reference", "the reference's Core.PathTracing shader compiled as C++ (oracle/_ref/libref_pathtrace.so), ray queries on the CPU oracle's BVH"
+    except Exception:  # library not built (reference not mounted when the repo was built) or unusable here: the port always exists
+        rays, secs = cpu_port_sample(scene, sky, ubo, params, bands, band_rows)
+        return rays, secs, "port", "CPU port of the reference shaders (oracle/)"
+
+
 def reference_arm(args):
-    """--impl reference: the reference-semantics CPU port on all host cores; rank 0 only."""
+    """--impl reference: the reference's RT pass on all host cores (compiled shader text if present, else the CPU port); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -119,19 +179,24 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     bands, band_rows = 8, 8  # 64 of 1080 rows per step
     total_rays, total_s = 0, 0.0
+    try:
+        ref = CompiledReference(scene, sky)
+        kind, what = "reference", "the reference's Core.PathTracing shader compiled as C++ (oracle/_ref/libref_pathtrace.so), ray queries on the CPU oracle's BVH"
+    except Exception:
+        ref, kind, what = None, "port", "CPU port of the reference shaders (oracle/)"
     for step in range(args.warmup + args.steps):
         ubo = scene.ubo(WIDTH, HEIGHT, step + 1)
-        rays, secs = cpu_port_sample(scene, sky, ubo, params, bands, band_rows)
+        rays, secs = ref.sample(ubo, bands, band_rows) if ref else cpu_port_sample(scene, sky, ubo, params, bands, band_rows)
         if step >= args.warmup:
             total_rays += rays
             total_s += secs
     value = total_rays / total_s / 1e6
-    sample = f"{bands} bands x {band_rows} rows of the {WIDTH}x{HEIGHT} frame per step, rt pass only"
+    sample = f"{bands} bands x {band_rows} rows of the {WIDTH}x{HEIGHT} frame per step, rt pass only; {what}"
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -424,9 +489,9 @@ def main():
             ubo = scene.ubo(WIDTH, HEIGHT, 1)
             p1 = GkcuFrameParams(temporal_frames=16, spp_world=1)
             bands, band_rows = 27, 40  # the whole frame: ~10 s of CPU work on a 16-core host
-            crays, csecs = cpu_port_sample(scene, sky, ubo, p1, bands, band_rows)
-            out["cpu_baseline"] = {"value": crays / csecs / 1e6, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                   "sample": f"{bands} bands x {band_rows} rows of the {WIDTH}x{HEIGHT} frame (rt pass), {csecs:.1f} s of CPU work",
+            crays, csecs, ckind, cwhat = cpu_sample(scene, sky, ubo, p1, bands, band_rows)
+            out["cpu_baseline"] = {"value": crays / csecs / 1e6, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": ckind,
+                                   "sample": f"{bands} bands x {band_rows} rows of the {WIDTH}x{HEIGHT} frame (rt pass), {csecs:.1f} s of CPU work; {cwhat}",
                                    "ms_per_frame_extrapolated": 1e3 * csecs * HEIGHT / (bands * band_rows)}
         print(json.dumps(out))
     r.close()

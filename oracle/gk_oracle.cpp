@@ -1758,17 +1758,19 @@ int gko_vox_trace(GkoScene* s, const float o[3], const float d[3], float dist, f
 }
 void gko_instance_w2o(GkoScene* s, uint32_t inst, float out[12]) { std::memcpy(out, s->instances[inst].w2o, 48); }
 void gko_sample_texture(GkoScene* s, uint32_t id, float u, float v, float out[4]) { f4 c = s->sample_texture(id, f2{u, v}); out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w; }
-void gko_cast_visibility(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t* packed) {
+void gko_cast_visibility_rows(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, int threads, uint32_t* packed) {
     GkoFrame F;
     F.w = w; F.h = h;
-    Renderer R(*s, F, *ubo);
     const f4 origin = mul(ubo->ModelViewInverse, F4(0, 0, 0, 1));
-    for (uint32_t y = 0; y < h; ++y)
-        for (uint32_t x = 0; x < w; ++x) {
-            uint32_t node1, prim;
-            R.CastVisibility((int)x, (int)y, xyz(origin), node1, prim);
-            packed[(size_t)y * w + x] = (node1 << 17) | (prim & 0x1FFFFu);
-        }
+    parallel_pixels(y0, std::min(y1, h), w, threads, [&](int x, int y) {
+        Renderer R(*s, F, *ubo);
+        uint32_t node1, prim;
+        R.CastVisibility(x, y, xyz(origin), node1, prim);
+        packed[(size_t)y * w + x] = (node1 << 17) | (prim & 0x1FFFFu);
+    });
+}
+void gko_cast_visibility(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t* packed) {
+    gko_cast_visibility_rows(s, ubo, w, h, 0, h, 1, packed);
 }
 
 GkoFrame* gko_frame_create(uint32_t w, uint32_t h) {

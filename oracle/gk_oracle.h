@@ -131,6 +131,8 @@ void gko_instance_w2o(GkoScene* s, uint32_t inst, float out[12]); /* world-to-ob
 void gko_sample_texture(GkoScene* s, uint32_t id, float u, float v, float out[4]);
 /* packed[y*w+x] = ((node + 1) << 17) | primitive, 0 = no geometry: the RT_MINIGBUFFER texel format (Shading.slang:348-349) */
 void gko_cast_visibility(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t* packed);
+/* rows [y0, y1) only, on `threads` threads (0 = all cores) */
+void gko_cast_visibility_rows(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, int threads, uint32_t* packed);
 
 #ifdef __cplusplus
 }

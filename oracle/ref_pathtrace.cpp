@@ -21,6 +21,8 @@
 // ...) are defined here the way the oracle defines them, and sin / cos / atan2 / acos / exp / pow are the pinned kernels of include/gk_detmath.h. So this pins the integrator: the control flow, the order of RNG
 // draws, every shading formula and every image store of the RT pass. Built only when /root/reference is mounted. TEST INFRASTRUCTURE ONLY.
 #include <atomic>
+#include <thread>
+#include <vector>
 
 #define REF_WITH_SCENE
 #define REF_DET_MATH
@@ -29,7 +31,7 @@
 
 namespace ref {
 static GkoScene* g_scene = nullptr;
-static uint64_t g_closest = 0, g_any = 0;
+static std::atomic<uint64_t> g_closest{0}, g_any{0};
 
 inline float4 Sampler2D::SampleLevel(float2 uv, float lod) const {
     float4 r;
@@ -87,7 +89,7 @@ template <int FLAGS> struct RayQuery {
     bool Proceed() {
         const bool any = (FLAGS & RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
         gko_trace_one((GkoScene*)scene, &r, &h, any ? 1u : 0u);
-        (any ? g_any : g_closest)++;
+        (any ? g_any : g_closest).fetch_add(1, std::memory_order_relaxed);
         return false;
     }
     uint CommittedStatus() const { return h.inst != 0xFFFFFFFFu ? COMMITTED_TRIANGLE_HIT : COMMITTED_NOTHING; }
@@ -148,10 +150,13 @@ using namespace ref;
 extern "C" {
 // images[rt] = the storage image in its reference format, indexed by the reference's RT_* numbers (NULL = unbound);
 // images[2] = RT_MINIGBUFFER (R32_UINT), images[10] = RT_PREV_DEPTHBUFFER (R32F), images[14] = RT_MOTIONMOMENT (R16_UINT, read and written).
-// counters[0] = closest-hit queries, counters[1] = any-hit queries. One frame: Util.BufferClear, then Core.PathTracing (PathTracingRenderer.cpp:96-124).
-void ref_pathtrace(GkoScene* scene, const void* ubo, void* const* images, int w, int h, uint64_t* counters) {
+// counters[0] = closest-hit queries, counters[1] = any-hit queries.
+// Rows [y0, y1) only (whole 8-row groups are not required: every thread of the two dispatches is independent), on `threads` host threads
+// (0 = all cores): the timed CPU baseline of bench.py. Threads write disjoint pixels; the scene block and the images are read-only / per pixel.
+void ref_pathtrace_rows(GkoScene* scene, const void* ubo, void* const* images, int w, int h, int y0, int y1, int threads, uint64_t* counters) {
     g_scene = scene;
-    g_closest = g_any = 0;
+    g_closest = 0;
+    g_any = 0;
     const int f16[] = {1, 6, 7, 12};
     for (int i : f16) Bindless.f4[i] = ImgF4{(uint8_t*)images[i], w, h, FMT_F16X4, (float*)images[i + 32]};  // images[32 + rt]: optional fp32 shadow
     Bindless.f4[5] = ImgF4{(uint8_t*)images[5], w, h, FMT_RG32F};
@@ -175,21 +180,36 @@ void ref_pathtrace(GkoScene* scene, const void* ubo, void* const* images, int w,
     S.Cubes = (AmbientCube*)a.cubes;
     S.Voxels = (VoxelData*)a.voxels;
     S.TLAS = scene;
-    // both dispatches cover ceil(w/8) x ceil(h/8) groups of 8 x 8 threads
-    for (int y = 0; y < (h + 7) / 8 * 8; ++y)
-        for (int x = 0; x < (w + 7) / 8 * 8; ++x) bufferclear::bufferclear_main(uint3((uint)x, (uint)y, 0u));
-    for (int y = 0; y < (h + 7) / 8 * 8; ++y)
-        for (int x = 0; x < (w + 7) / 8 * 8; ++x) pathtracing::pathtracing_main(uint3((uint)x, (uint)y, 0u));
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int xs = (w + 7) / 8 * 8;
+    std::atomic<int> next{y0};
+    auto worker = [&]() {
+        for (;;) {
+            const int y = next.fetch_add(1);
+            if (y >= y1) break;
+            for (int x = 0; x < xs; ++x) bufferclear::bufferclear_main(uint3((uint)x, (uint)y, 0u));
+            for (int x = 0; x < xs; ++x) pathtracing::pathtracing_main(uint3((uint)x, (uint)y, 0u));
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
     counters[0] = g_closest;
     counters[1] = g_any;
     S.Camera = nullptr;
+}
+// One frame: Util.BufferClear, then Core.PathTracing (PathTracingRenderer.cpp:96-124); both dispatches cover ceil(w/8) x ceil(h/8) groups of 8 x 8
+void ref_pathtrace(GkoScene* scene, const void* ubo, void* const* images, int w, int h, uint64_t* counters) {
+    ref_pathtrace_rows(scene, ubo, images, w, h, 0, (h + 7) / 8 * 8, 1, counters);
 }
 
 // Bake.HwAmbientCube.comp.slang over probes [first, first + count) of caller-provided probe arrays (updated in place), one thread after the
 // other in index order (SceneList / Scene.cpp dispatches it with custom_data_0 = first)
 void ref_probes_bake(GkoScene* scene, const void* ubo, void* cubes, void* voxels, uint32_t first, uint32_t count, uint64_t* counters) {
     g_scene = scene;
-    g_closest = g_any = 0;
+    g_closest = 0;
+    g_any = 0;
     UniformBufferObject cam;
     std::memcpy(&cam, ubo, sizeof(cam));
     GkoSceneArrays a;

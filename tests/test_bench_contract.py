@@ -34,6 +34,32 @@ def test_committed_round_profile_carries_the_contract():
     c = j["clocks"]
     assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     cb = j["cpu_baseline"]
-    assert cb["value"] > 0 and cb["cores"] >= 1 and cb["kind"] == "port" and cb["sample"]
+    assert cb["value"] > 0 and cb["cores"] >= 1 and cb["kind"] in ("port", "reference") and cb["sample"]
     for k in ("reproject", "denoise"):
         assert j["roofline_stencils"][k]["bound"] == "issue" and 0 < j["roofline_stencils"][k]["issue_frac"] < 1
+
+
+def test_cpu_baseline_reference_and_port_trace_the_same_rays_and_threads_do_not_change_results():
+    """bench.py's CPU baseline: the compiled reference shaders (kind "reference", multi-threaded over rows) and the oracle port must count the
+    same rays on the same band of the bench frame, and the thread count must not change a single pixel."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from gknextengine_b200 import GkcuFrameParams, host
+    scene = host.Scene(bench.SCENE, samples=2, bounces=bench.BOUNCES, taa=True, temporal_frames=16, denoiser=True)
+    scene.update_nodes()
+    sky = host.make_sky(64, 32)
+    try:
+        ref = bench.CompiledReference(scene, sky)
+    except FileNotFoundError:
+        import pytest
+        pytest.skip("oracle/_ref not built (reference not mounted)")
+    ubo = scene.ubo(bench.WIDTH, bench.HEIGHT, 3)
+    rays1, _ = ref.sample(ubo, 1, 2, threads=1)
+    band = slice(bench.HEIGHT // 2 - 1, bench.HEIGHT // 2 + 1)
+    first = {k: v[band].copy() for k, v in ref.images.items()}
+    rays4, _ = ref.sample(ubo, 1, 2, threads=4)
+    assert rays1 == rays4 and all(np.array_equal(first[k].view(np.uint8), ref.images[k][band].view(np.uint8)) for k in first)
+    prays, _ = bench.cpu_port_sample(scene, sky, ubo, GkcuFrameParams(temporal_frames=16, spp_world=1), 1, 2)
+    assert prays == rays1 and rays1 > 2 * bench.WIDTH * 3
+    assert first["SINGLE_DIFFUSE"].astype(np.float32).max() > 0
