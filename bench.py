@@ -14,7 +14,8 @@ SURVEY 8e); the un-normalised radiance sums are reduced to rank 0 with NCCL and 
   cpu_baseline   the reference's RT-pass shaders compiled as C++ (oracle/_ref, kind "reference") or, without them, the CPU oracle port (kind "port")
                  on all host cores, bounded sample of the same frame
 
---impl reference times that CPU port alone (the reference's Slang/Vulkan path cannot run without slangc/Vulkan).
+--impl reference times that CPU baseline alone (the reference's Slang/Vulkan path itself cannot run without slangc/Vulkan; its shader text
+compiled as C++ can).
 """
 import argparse
 import ctypes as C
