@@ -1,7 +1,7 @@
 // Compiles the reference's own sampling / RNG / tonemapping source (assets/shaders/common/Const_Func.slang and PreProcessor.slang) as
 // C++ so that tests can pin the oracle's restatements of SURVEY 8a rows a19 and a25 against it. The Slang file is not valid C++ as a
 // whole (swizzles, resource types), so oracle/Makefile extracts the line ranges of the functions below with sed into
-// oracle/_ref/const_func_gen.inc (a build product next to the other _ref outputs, never committed) and only rewrites the parameter
+// oracle/_ref/const_func_gen.inc (a make intermediate: deleted again as soon as the library is linked, never committed) and only rewrites the parameter
 // qualifiers (`inout T x` / `out T x` -> `T& x`, `public` dropped); the function bodies are the reference's text. This file supplies
 // the HLSL vocabulary they use. Floating literals are single precision as in Slang (-fsingle-precision-constant), products and sums
 // are not contracted (-ffp-contract=off), dot / mul / normalize are defined the way the oracle defines them (left-to-right, unfused).
