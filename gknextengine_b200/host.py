@@ -121,6 +121,10 @@ class Scene:
         lib().gkhost_scene_counts(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(t))
         return dict(nodes=a.value, models=b.value, materials=c.value, instanced_triangles=t.value)
 
+    def set_node_visible(self, node, visible):
+        """Node::SetVisible; the proxy stays in place with visible = 0 (the TLAS instance is masked out)."""
+        lib().gkhost_scene_set_node_visible(self._h, node, int(visible))
+
     def jitter_instances(self, step, fraction):
         lib().gkhost_scene_jitter_instances(self._h, step, fraction)
 

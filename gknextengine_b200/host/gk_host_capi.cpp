@@ -95,6 +95,11 @@ void gkhost_scene_counts(void* h, uint32_t* nodes, uint32_t* models, uint32_t* m
     for (auto& n : s->nodes) t += s->models[n.modelId].indices.size() / 3;
     *instanced_triangles = t;
 }
+// Node::SetVisible (Node.h:41). The next UpdateNodes keeps the node's proxies and clears their `visible` word (Scene.cpp:456-476).
+void gkhost_scene_set_node_visible(void* h, uint32_t node, int visible) {
+    auto* s = static_cast<gk::Scene*>(h);
+    if (node < s->nodes.size()) s->nodes[node].visible = visible != 0;
+}
 void gkhost_scene_jitter_instances(void* h, uint32_t step, float fraction) { static_cast<gk::Scene*>(h)->JitterInstances(step, fraction); }
 // returns the vertex count; out must hold 4 * vertex_count halfs (call with out = NULL to query)
 uint32_t gkhost_scene_perturb_model(void* h, uint32_t model, uint32_t step, uint16_t* out) {

@@ -421,7 +421,7 @@ bool Scene::UpdateNodes() {  // Scene.cpp:443-492 + Node::GetNodeProxy (Node.cpp
     previous.swap(node_proxies);
     node_proxies.reserve(previous.size());
     for (auto& node : nodes) {
-        if (!node.visible) continue;
+        if (node.modelId == 0xFFFFFFFFu) continue;  // Node::IsDrawable(): invisible nodes keep their proxy (visible = 0 masks the TLAS instance)
         mat4 combined;
         node.TickVelocity(combined);
         const Model& model = models[node.modelId];
@@ -429,7 +429,7 @@ bool Scene::UpdateNodes() {  // Scene.cpp:443-492 + Node::GetNodeProxy (Node.cpp
             GkNodeProxy p{};
             p.instanceId = node.instanceId;
             p.modelId = node.modelId * 10 + section;
-            p.visible = 1;
+            p.visible = node.visible ? 1 : 0;
             p.nort = section == 0 ? 0 : 1;
             p.worldTS = node.transform.pod();
             p.combinedPrevTS = combined.pod();

@@ -111,3 +111,22 @@ def test_lego_synth_workload_shape():
 def test_sky_is_deterministic_and_finite():
     a, b = host.make_sky(64, 32), host.make_sky(64, 32)
     assert np.array_equal(a, b) and np.isfinite(a).all() and a[..., :3].min() >= 0 and (a[..., 3] == 1).all()
+
+
+def test_invisible_nodes_keep_their_proxy_with_the_visible_word_cleared():
+    """Scene::UpdateNodesGpuDriven (Scene.cpp:443-492) records every drawable node, visible or not: instance i of the TLAS is Nodes[i], so hiding
+    a node must not shift the others - its proxy stays, with visible = 0 (the TLAS mask hides it, TopLevelAccelerationStructure.cpp:83-111)."""
+    scene = host.Scene("CornellBox.proc")
+    scene.update_nodes()
+    p, n = scene.nodes()
+    before = [(p[i].instanceId, p[i].modelId, p[i].visible) for i in range(n)]
+    scene.set_node_visible(1, False)
+    scene.update_nodes()
+    p, n2 = scene.nodes()
+    after = [(p[i].instanceId, p[i].modelId, p[i].visible) for i in range(n2)]
+    assert n2 == n and after[1] == (before[1][0], before[1][1], 0) and after[0] == before[0] and after[2] == before[2]
+    assert scene.changed()[1] == 1  # exactly one proxy differs from the previous frame
+    scene.set_node_visible(1, True)
+    scene.update_nodes()
+    p, _ = scene.nodes()
+    assert p[1].visible == 1
