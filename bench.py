@@ -36,10 +36,7 @@ SCENE = "RTIO.proc"
 TRACE_BYTES_PER_RAY = 32 + 4 + 16 + 4
 PAIR_BYTES_CLOSEST, PAIR_BYTES_ANY = 436, 100
 PRIMARY_BYTES_PER_PIXEL, REPROJECT_BYTES_PER_PIXEL, DENOISE_BYTES_PER_PIXEL = 36 + 2, 98, 44
-# Warp instructions per pixel of the two stencil kernels (ncu smsp__inst_executed.sum / 1920x1080, profiles/r01_ncu_misc.txt): both kernels
-# are bound by instruction issue, not by HBM - the reference's arithmetic (36 bilateral taps with an IEEE division and an exp each, 25
-# weighted taps with two divisions each) kept bit for bit - so the bench also reports them against the SM issue rate (4 warp instr / clk / SM).
-REPROJECT_WARP_INSTR_PER_PIXEL, DENOISE_WARP_INSTR_PER_PIXEL, SM_COUNT, ISSUE_PER_SM_CLK = 137084257 / 2073600, 287836077 / 2073600, 148, 4
+# Both stencil kernels are bound by instruction issue, not by HBM (ncu: profiles/r02_ncu_table.md); the bench reports their algorithmic GB/s only.
 
 
 def load_peaks():
@@ -111,9 +108,10 @@ class CompiledReference:
     """The reference's own RT pass - Util.BufferClear + Core.PathTracing with the Shading.slang / AmbientCube.slang classes they run - compiled
     as C++ from the reference's sources into oracle/_ref/libref_pathtrace.so (oracle/ref_pathtrace.cpp; built when the reference is mounted, the
     binary travels with the repo). Ray queries, the texture sampler and the visibility buffer of the raster pass are served by the CPU oracle's
-    BVH (they are hardware in the reference). Multi-threaded over rows."""
+    intersector (they are hardware in the reference): the reference's vendored tinybvh when oracle/_ref holds that build. Multi-threaded over
+    8 x 8 pixel groups."""
 
-    def __init__(self, scene, sky):
+    def __init__(self, scene, sky, query="tinybvh"):
         import ctypes as C
         import numpy as np
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -121,12 +119,17 @@ class CompiledReference:
         from gknextengine_b200 import RT
         from gknextengine_b200._abi import GK_CUBE_COUNT
         from gknextengine_b200.renderer import CudaPathTracingRenderer as R
-        path = os.path.join(os.path.dirname(O.TINYBVH), "libref_pathtrace.so")
+        # the reference's own CPU ray query (vendored tinybvh, used like src/Assets/CPUAccelerationStructure.cpp:172-284) when that build exists
+        path = os.path.join(os.path.dirname(O.TINYBVH), "libref_pathtrace_tinybvh.so")
+        oracle_path, self.query = O.TINYBVH, "the reference's vendored tinybvh 1.3.8"
+        if query != "tinybvh" or not (os.path.exists(path) and os.path.exists(O.TINYBVH)):
+            path = os.path.join(os.path.dirname(O.TINYBVH), "libref_pathtrace.so")
+            oracle_path, self.query = O.NATIVE, "the CPU oracle's BVH2"
         if not os.path.exists(path):
             raise FileNotFoundError(path)
+        self.osc = O.OracleScene(scene, sky, lib_path=oracle_path)  # first: the shader library links against this intersector library
         self.C, self.lib = C, C.CDLL(path)
         self.lib.ref_pathtrace_rows.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
-        self.osc = O.OracleScene(scene, sky)
         # zero probe state; the shader dereferences the probe arrays, so they must exist
         self.osc.set_probes(np.zeros(GK_CUBE_COUNT, R.CUBE_DTYPE), np.zeros(GK_CUBE_COUNT, R.VOXEL_DTYPE))
         self.osc.L.gko_cast_visibility_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
@@ -162,7 +165,7 @@ def cpu_sample(scene, sky, ubo, params, bands, band_rows):
         cmd = [sys.executable, os.path.abspath(__file__), "--cpu-leg", f"{bands},{band_rows}", "--workload", "config5" if WIDTH == 3840 else "config2"]
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
         j = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
-        return j["rays"], j["secs"], "reference", "the reference's Core.PathTracing shader compiled as C++ (oracle/_ref/libref_pathtrace.so), ray queries on the CPU oracle's BVH"
+        return j["rays"], j["secs"], "reference", f"the reference's Core.PathTracing shader compiled as C++ (oracle/_ref/libref_pathtrace*.so), ray queries on {j['query']}"
     except Exception:  # library not built (reference not mounted when the repo was built) or unusable here: the port always exists
         rays, secs = cpu_port_sample(scene, sky, ubo, params, bands, band_rows)
         return rays, secs, "port", "CPU port of the reference shaders (oracle/)"
@@ -178,7 +181,7 @@ def cpu_leg(spec):
     ubo = scene.ubo(WIDTH, HEIGHT, 1)
     ref.sample(ubo, 2, 2)  # untimed: first touch of the image pages, thread start-up
     rays, secs = ref.sample(ubo, bands, band_rows)
-    print(json.dumps({"rays": int(rays), "secs": secs}))
+    print(json.dumps({"rays": int(rays), "secs": secs, "query": ref.query}))
 
 
 def reference_arm(args):
@@ -193,11 +196,11 @@ def reference_arm(args):
     sky = host.make_sky(1024, 512)
     params = GkcuFrameParams(temporal_frames=16, spp_world=1)
     cores = os.cpu_count() or 1
-    bands, band_rows = 8, 8  # 64 of 1080 rows per step
+    bands, band_rows = 8, 16  # 128 of 1080 rows per step; work items are 8 x 8 pixel groups: 480 per band, enough for any host
     total_rays, total_s = 0, 0.0
     try:
         ref = CompiledReference(scene, sky)
-        kind, what = "reference", "the reference's Core.PathTracing shader compiled as C++ (oracle/_ref/libref_pathtrace.so), ray queries on the CPU oracle's BVH"
+        kind, what = "reference", f"the reference's Core.PathTracing shader compiled as C++ (oracle/_ref/libref_pathtrace*.so), ray queries on {ref.query}"
     except Exception:
         ref, kind, what = None, "port", "CPU port of the reference shaders (oracle/)"
     for step in range(args.warmup + args.steps):
@@ -211,20 +214,22 @@ def reference_arm(args):
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.gpus),
+        "data": "synthetic", "config": workload_config(args.gpus, args.probes),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(n):
+def workload_config(n, probes=False):
     name = "BASELINE configs[1]" if (WIDTH, HEIGHT) == (1920, 1080) else "SURVEY 8d config 5 (qx50.glb absent: declared stand-in scene)"
     return {"workload": f"{name}: RayTracingInOneWeekend procedural scene (RTIO.proc), {WIDTH}x{HEIGHT}, {SPP} spp per GPU "
                         f"({SPP * n} spp/frame), {BOUNCES} bounces, procedural sky stand-in, steady state, temporal reproject + bilateral denoise",
             "scene": SCENE, "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_per_frame": SPP * n, "bounces": BOUNCES,
             "parallelism": f"spp-split x{n}, scene replica per GPU" if n > 1 else "single GPU",
             "l2": "working set (queue slots + hit records + per-pixel path state ~240 B/px, storage images 122 B/px: ~750 MB at 1080p) exceeds the 126 MB L2; "
-                  "no explicit flush"}
+                  "no explicit flush",
+            "sky": "procedural equirect sky (host.make_sky 1024x512); river_road_2.hdr is not in the mount, gkcu_set_sky takes any RGBA32F equirect (host.load_hdr)",
+            "probes": "voxelised + baked grid, bake dispatch every frame" if probes else "zero probe state"}
 
 
 def main():
@@ -235,6 +240,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--tracer", type=int, default=0, help="0 wavefront (default), 1 megakernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the config-5 strong-scaling block (4K, 64 spp split over the GPUs)")
     ap.add_argument("--cpu-leg", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--probes", action="store_true",
                     help="voxelise the probe grid, bake one full sweep before timing and record the per-frame bake dispatch like "
@@ -248,22 +254,16 @@ def main():
                     help="config2: BASELINE configs[1], 1080p, 16 spp per GPU (weak scaling). config5: SURVEY 8d config 5, 3840x2160, 64 spp per frame "
                          "split over the GPUs (strong scaling)")
     args = ap.parse_args()
-    global WIDTH, HEIGHT, SPP
-    if args.workload == "config5":
-        WIDTH, HEIGHT = 3840, 2160
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.cpu_leg:
+        set_workload(args.workload, 1)
         return cpu_leg(args.cpu_leg)
     if args.impl == "reference":
+        set_workload(args.workload, 1)
         return reference_arm(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
-
-    from gknextengine_b200 import RT, CudaPathTracingRenderer, GkcuFrameParams, host
-    from gknextengine_b200._abi import GkNodeProxy
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -274,11 +274,45 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = run_ours(args, args.workload, args.steps, args.warmup, world, rank, local_rank, full=True)
+    if args.workload == "config2" and not args.no_strong and 64 % world == 0:
+        # The north-star multi-GPU configuration next to the weak-scaling headline: SURVEY 8d config 5, 3840x2160, 64 spp per frame SPLIT over
+        # the GPUs (strong scaling: total work fixed), device-timed, a few frames. Reported as a block of the same line.
+        st = run_ours(args, "config5", min(args.steps, 5), 3, world, rank, local_rank, full=False)
+        if rank == 0:
+            out["strong"] = {"workload": st["config"]["workload"], "scaling": "strong", "value": st["value"], "unit": "Mrays/s", "ms_per_step": st["ms_per_step"],
+                             "steps": st["steps"], "warmup": st["warmup"], "spp_per_gpu": st["config"]["spp_per_gpu"], "width": 3840, "height": 2160,
+                             "passes_ms_per_frame_rank0": st["passes_ms_per_frame_rank0"], "multi_gpu": st.get("multi_gpu")}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
-    if args.workload == "config5":
+
+def set_workload(workload, world):
+    global WIDTH, HEIGHT, SPP
+    if workload == "config5":
+        WIDTH, HEIGHT = 3840, 2160
         if 64 % world:
             raise SystemExit("config5 splits 64 spp: --gpus must divide 64")
         SPP = 64 // world
+    else:
+        WIDTH, HEIGHT, SPP = 1920, 1080, 16
+
+
+def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
+    """One measurement of `workload` on this rank's GPU: device-resident timing always; the end-to-end leg, the roofline objects and the CPU
+    baseline only when `full`. Returns the JSON object on rank 0 (None elsewhere)."""
+    import numpy as np  # noqa: F401
+    import torch
+    import torch.distributed as dist
+
+    from gknextengine_b200 import RT, CudaPathTracingRenderer, GkcuFrameParams, host
+    from gknextengine_b200._abi import GkNodeProxy
+
+    set_workload(workload, world)
+    args = argparse.Namespace(**vars(args))
+    args.steps, args.warmup, args.workload = steps, warmup, workload
     scene = host.Scene(SCENE, samples=SPP * world, bounces=BOUNCES, taa=True, temporal_frames=16, denoiser=True)
     scene.update_nodes()  # steady state: combinedPrevTS = identity, MOTIONMOMENT stays 0
     sky = host.make_sky(1024, 512)
@@ -408,53 +442,56 @@ def main():
         ms, rays, launches = float(mx[0]), float(sm[1]), float(sm[2])
     value = rays / (ms * 1e-3) / 1e6
 
-    # ---- end to end through the public API with host buffers (e2e)
-    nodes_ptr, nn = scene.nodes()
-    node_bytes = nn * C.sizeof(GkNodeProxy)
-    pinned_nodes = torch.empty(node_bytes, dtype=torch.uint8, pin_memory=True)
-    pinned_out = [torch.empty(WIDTH * HEIGHT * 8, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    e2e_rays = 0
-    sync_all()
-    t0 = time.perf_counter()
-    for _step in range(args.steps):
-        scene.update_nodes()  # Scene::UpdateNodes on the host (Scene.cpp:410-492)
+    e2e_value, e2e_s, node_bytes = 0.0, 0.0, 0
+    if full:
+        # ---- end to end through the public API with host buffers (e2e)
         nodes_ptr, nn = scene.nodes()
-        C.memmove(pinned_nodes.data_ptr(), nodes_ptr, node_bytes)
-        r.update_nodes_ptr(pinned_nodes.data_ptr(), nn)  # H2D NodeProxy[]
-        frame(tf)  # H2D UBO inside
-        tf += 1
+        node_bytes = nn * C.sizeof(GkNodeProxy)
+        pinned_nodes = torch.empty(node_bytes, dtype=torch.uint8, pin_memory=True)
+        pinned_out = [torch.empty(WIDTH * HEIGHT * 8, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        e2e_rays = 0
+        sync_all()
+        t0 = time.perf_counter()
+        for _step in range(args.steps):
+            scene.update_nodes()  # Scene::UpdateNodes on the host (Scene.cpp:410-492)
+            nodes_ptr, nn = scene.nodes()
+            C.memmove(pinned_nodes.data_ptr(), nodes_ptr, node_bytes)
+            r.update_nodes_ptr(pinned_nodes.data_ptr(), nn)  # H2D NodeProxy[]
+            frame(tf)  # H2D UBO inside
+            tf += 1
+            if rank == 0:
+                # D2H of the frame's RT_DENOISED every step, double-buffered: the copy runs on the renderer's copy stream and overlaps
+                # the next frame's rt pass; the copy of the previous step is complete before its buffer is reused
+                out_buf = pinned_out[_step & 1]
+                if args.present == "async":
+                    r.present_wait()
+                    r.present_async(out_buf.data_ptr(), out_buf.numel())
+                else:
+                    r.readback_into(RT["DENOISED"], out_buf.data_ptr(), out_buf.numel())
+            c = r.counters()
+            e2e_rays += c["primary_rays"] + c["closest_hit_rays"] + c["any_hit_rays"]
         if rank == 0:
-            # D2H of the frame's RT_DENOISED every step, double-buffered: the copy runs on the renderer's copy stream and overlaps
-            # the next frame's rt pass; the copy of the previous step is complete before its buffer is reused
-            out_buf = pinned_out[_step & 1]
-            if args.present == "async":
-                r.present_wait()
-                r.present_async(out_buf.data_ptr(), out_buf.numel())
-            else:
-                r.readback_into(RT["DENOISED"], out_buf.data_ptr(), out_buf.numel())
-        c = r.counters()
-        e2e_rays += c["primary_rays"] + c["closest_hit_rays"] + c["any_hit_rays"]
-    if rank == 0:
-        r.present_wait()
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    est = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        mx = est.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = est.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_rays = float(mx[0]), float(sm[1])
-    e2e_value = e2e_rays / e2e_s / 1e6
+            r.present_wait()
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        est = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            mx = est.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = est.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            e2e_s, e2e_rays = float(mx[0]), float(sm[1])
+        e2e_value = e2e_rays / e2e_s / 1e6
 
+    out = None
     if rank == 0:
         peak, peak_kind = load_peaks()
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "config2" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), probes="voxelised + baked grid, bake dispatch every frame" if args.probes else "zero probe state"),
+            "config": workload_config(world, args.probes),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": 1e3 * e2e_s / args.steps, "h2d_bytes_per_step": node_bytes + 784,
-                    "d2h_bytes_per_step": WIDTH * HEIGHT * 8},
+                    "d2h_bytes_per_step": WIDTH * HEIGHT * 8} if full else None,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "tracer": "wavefront" if args.tracer == 0 else "megakernel",
@@ -497,14 +534,7 @@ def main():
             "denoise": {"achieved": DENOISE_BYTES_PER_PIXEL * px * args.steps / (pass_ms["compose_pass_ms"] * 1e-3) / 1e9 if pass_ms["compose_pass_ms"] else 0.0,
                         "bytes_per_pixel": DENOISE_BYTES_PER_PIXEL},
             "unit": "GB/s", "peak": peak}
-        sm_mhz = (clocks or {}).get("sm_mhz") or 0
-        if sm_mhz:
-            issue_peak = SM_COUNT * ISSUE_PER_SM_CLK * sm_mhz * 1e6
-            for name, key, ipp in (("reproject", "reproject_pass_ms", REPROJECT_WARP_INSTR_PER_PIXEL), ("denoise", "compose_pass_ms", DENOISE_WARP_INSTR_PER_PIXEL)):
-                if pass_ms[key]:
-                    out["roofline_stencils"][name].update({"bound": "issue", "warp_instr_per_pixel": round(ipp, 2),
-                                                           "issue_frac": ipp * px * args.steps / (pass_ms[key] * 1e-3) / issue_peak})
-        if world == 1 and not args.no_cpu_baseline:
+        if full and world == 1 and not args.no_cpu_baseline:
             ubo = scene.ubo(WIDTH, HEIGHT, 1)
             p1 = GkcuFrameParams(temporal_frames=16, spp_world=1)
             bands, band_rows = 27, 40  # the whole frame: ~10 s of CPU work on a 16-core host
@@ -512,10 +542,8 @@ def main():
             out["cpu_baseline"] = {"value": crays / csecs / 1e6, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": ckind,
                                    "sample": f"{bands} bands x {band_rows} rows of the {WIDTH}x{HEIGHT} frame (rt pass), {csecs:.1f} s of CPU work; {cwhat}",
                                    "ms_per_frame_extrapolated": 1e3 * csecs * HEIGHT / (bands * band_rows)}
-        print(json.dumps(out))
     r.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return out if rank == 0 else None
 
 
 if __name__ == "__main__":

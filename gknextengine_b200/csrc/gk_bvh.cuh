@@ -160,7 +160,15 @@ struct Trav {
     int sp_inst;       // stack height when the current instance was entered: popping down to it leaves the instance
     bool any;          // first-hit query
     bool done;
+#ifdef GK_TRAV_STATS
+    uint32_t st[8];    // diagnostics build: TLAS node steps, BLAS node steps, children hit, pushes, culled pops, instance entries, leaf steps, triangle tests
+#endif
 };
+#ifdef GK_TRAV_STATS
+#define GK_STAT(T, k, v) ((T).st[k] += (v))
+#else
+#define GK_STAT(T, k, v) ((void)0)
+#endif
 
 // Slab distances are evaluated as t = plane * idir + adj with adj = -(ro * idir): one FMA per plane. adj carries a rounding
 // error of half an ulp (|adj| * 2^-24) which the cancellation in plane * idir + adj can make large relative to t, so the
@@ -194,6 +202,9 @@ GK_DEV void trav_init(Trav& T, W& world, const TraceScene& S, float3 o, float3 d
     T.sp_inst = 0;
     T.any = any;
     T.done = S.tlas_nodes == 0;
+#ifdef GK_TRAV_STATS
+    for (int k = 0; k < 8; ++k) T.st[k] = 0;
+#endif
 }
 
 // Pops the next node to visit (culling entries that are already farther than the best hit); once every node the current
@@ -208,7 +219,7 @@ GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
         }
         if (T.sp == 0) { T.done = true; return; }
         const uint2 e = stack.pop(T.sp);
-        if (__uint_as_float(e.y) > T.best.t) continue;
+        if (__uint_as_float(e.y) > T.best.t) { GK_STAT(T, 4, 1); continue; }
         T.cur = e.x;
         return;
     }
@@ -249,6 +260,8 @@ GK_DEV void trav_node_step(Trav& T, const W& world, const TraceScene& S, St& sta
         tn[c] = hit ? npad : inf;
     }
     const uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
+    GK_STAT(T, T.cur_inst == GK_NO_HIT ? 0 : 1, 1);
+    GK_STAT(T, 2, (tn[0] < inf) + (tn[1] < inf) + (tn[2] < inf) + (tn[3] < inf));
     // continue with the nearest child; the second nearest goes on top of the stack, the rest below it in slot order
     // (entries carry their entry distance, so a far one is culled when it is popped)
     int i0 = 0;
@@ -266,7 +279,8 @@ GK_DEV void trav_node_step(Trav& T, const W& world, const TraceScene& S, St& sta
         if (i1 >= 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                if (c != i0 && c != i1 && tn[c] < inf) stack.push(T.sp, make_uint2(ref[c], __float_as_uint(tn[c])));
+                if (c != i0 && c != i1 && tn[c] < inf) { GK_STAT(T, 3, 1); stack.push(T.sp, make_uint2(ref[c], __float_as_uint(tn[c]))); }
+            GK_STAT(T, 3, 1);
             stack.push(T.sp, make_uint2(ref[i1], __float_as_uint(t1)));
         }
     } else {
@@ -285,6 +299,7 @@ GK_DEV void trav_leaf_step(Trav& T, const W& world, const TraceScene& S, St& sta
         const float4* ir = reinterpret_cast<const float4*>(S.inst + ii);
         const float4 r0 = __ldg(ir), r1 = __ldg(ir + 1), r2 = __ldg(ir + 2);
         const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ir) + 3);
+        GK_STAT(T, 5, 1);
         if (meta.z) {
             const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
             const float3 rd = xform_vec(m, world.d());
@@ -299,6 +314,8 @@ GK_DEV void trav_leaf_step(Trav& T, const W& world, const TraceScene& S, St& sta
         }
     } else {
         const uint32_t first = T.cur & 0x0FFFFFFFu, count = ((T.cur >> 28) & 7u) + 1u;
+        GK_STAT(T, 6, 1);
+        GK_STAT(T, 7, count);
         for (uint32_t i = 0; i < count; ++i) {
             const float4* tp = T.tris + (size_t)(first + i) * 3;
             const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);

@@ -667,8 +667,23 @@ __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V,
         if (slot < n) {
             float4 o = ray_o[slot], d = ray_d[slot];
             Hit h;
+#ifdef GK_TRAV_STATS
+            {   // diagnostics build (scripts/trav_stats.py): per-frame traversal statistics in counts[32..], see fetch_ray_counters
+                LocalStack stack; Trav T; WorldRegs world;
+                const bool any = (V.slot_pixel[qi][slot] & 0x80000000u) != 0;
+                trav_init(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, any);
+                while (!T.done) {
+                    if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, world, ts, stack);
+                    else trav_leaf_step(T, world, ts, stack);
+                }
+                h = T.best;
+                unsigned long long* g = reinterpret_cast<unsigned long long*>(V.counts + 32);
+                for (int k = 0; k < 8; ++k) atomicAdd(g + k + (any ? 8 : 0), (unsigned long long)T.st[k]);
+            }
+#else
             if (V.slot_pixel[qi][slot] & 0x80000000u) trace_ray<true>(ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h);
             else trace_ray<false>(ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h);
+#endif
             V.hit_tuv[slot] = f4(h.t, h.u, h.v, __uint_as_float(h.inst));
             V.hit_prim[slot] = h.prim;
         }
@@ -1028,6 +1043,9 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
         // per lane: primary / closest / any ray counters (3 x u64) and the wavefront statistics (rays, launches)
         GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 8, ray_counters_of(l), 24, cudaMemcpyDeviceToHost, ls[l]));
         GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 16, L.v[l].counts + 12, 8, cudaMemcpyDeviceToHost, ls[l]));
+#ifdef GK_TRAV_STATS
+        GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 32, L.v[l].counts + 32, 128, cudaMemcpyDeviceToHost, ls[l]));
+#endif
         if (lanes > 1) {
             cudaEventRecord(c.lane_ev[l][2], ls[l]);
             cudaStreamWaitEvent(st, c.lane_ev[l][2], 0);  // the post passes on the context stream follow every lane
@@ -1054,6 +1072,16 @@ void fetch_ray_counters(Context& c) {
         c.counters.any_hit_rays += h[2];
         c.kstats.trace_rays += hc[16];
         c.kstats.trace_launches += hc[17];
+#ifdef GK_TRAV_STATS
+        {
+            const unsigned long long* g = reinterpret_cast<const unsigned long long*>(hc + 32);
+            static const char* names[8] = {"tlas_node_steps", "blas_node_steps", "children_hit", "pushes", "culled_pops", "instance_entries", "leaf_steps", "tri_tests"};
+            fprintf(stderr, "TRAV_STATS wavefront_rays=%u", hc[16]);
+            for (int k = 0; k < 8; ++k) fprintf(stderr, " closest_%s=%llu", names[k], g[k]);
+            for (int k = 0; k < 8; ++k) fprintf(stderr, " any_%s=%llu", names[k], g[8 + k]);
+            fprintf(stderr, "\n");
+        }
+#endif
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c.lane_ev[l][0], c.lane_ev[l][1]) == cudaSuccess) c.kstats.tail_ms += ms;
     }

@@ -31,7 +31,8 @@
 
 namespace ref {
 static GkoScene* g_scene = nullptr;
-static std::atomic<uint64_t> g_closest{0}, g_any{0};
+static std::atomic<uint64_t> g_closest{0}, g_any{0};  // totals, folded in once per worker thread
+static thread_local uint64_t t_closest = 0, t_any = 0;  // per-thread ray counters: no shared cache line on the ray path
 
 inline float4 Sampler2D::SampleLevel(float2 uv, float lod) const {
     float4 r;
@@ -89,7 +90,7 @@ template <int FLAGS> struct RayQuery {
     bool Proceed() {
         const bool any = (FLAGS & RAY_FLAG_ACCEPT_FIRST_HIT_AND_END_SEARCH) != 0;
         gko_trace_one((GkoScene*)scene, &r, &h, any ? 1u : 0u);
-        (any ? g_any : g_closest).fetch_add(1, std::memory_order_relaxed);
+        ++(any ? t_any : t_closest);
         return false;
     }
     uint CommittedStatus() const { return h.inst != 0xFFFFFFFFu ? COMMITTED_TRIANGLE_HIT : COMMITTED_NOTHING; }
@@ -181,15 +182,26 @@ void ref_pathtrace_rows(GkoScene* scene, const void* ubo, void* const* images, i
     S.Voxels = (VoxelData*)a.voxels;
     S.TLAS = scene;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    const int xs = (w + 7) / 8 * 8;
-    std::atomic<int> next{y0};
+    // Work items are 8 x 8 pixel groups (the shader's numthreads) handed out by an atomic counter, so a band of a few rows still
+    // keeps every host core busy; both dispatches of a group run back to back on one thread (its pixels are independent of the others').
+    const int gx = (w + 7) / 8, gy0 = y0 / 8, gy1 = (y1 + 7) / 8;
+    const int64_t total = (int64_t)gx * (gy1 - gy0);
+    std::atomic<int64_t> next{0};
     auto worker = [&]() {
+        t_closest = t_any = 0;
         for (;;) {
-            const int y = next.fetch_add(1);
-            if (y >= y1) break;
-            for (int x = 0; x < xs; ++x) bufferclear::bufferclear_main(uint3((uint)x, (uint)y, 0u));
-            for (int x = 0; x < xs; ++x) pathtracing::pathtracing_main(uint3((uint)x, (uint)y, 0u));
+            const int64_t i = next.fetch_add(1);
+            if (i >= total) break;
+            const int bx = (int)(i % gx) * 8, by = (gy0 + (int)(i / gx)) * 8;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int y = std::max(by, y0); y < std::min(by + 8, y1); ++y)
+                    for (int x = bx; x < bx + 8; ++x) {
+                        if (pass == 0) bufferclear::bufferclear_main(uint3((uint)x, (uint)y, 0u));
+                        else pathtracing::pathtracing_main(uint3((uint)x, (uint)y, 0u));
+                    }
         }
+        g_closest += t_closest;
+        g_any += t_any;
     };
     std::vector<std::thread> pool;
     for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
@@ -208,8 +220,7 @@ void ref_pathtrace(GkoScene* scene, const void* ubo, void* const* images, int w,
 // other in index order (SceneList / Scene.cpp dispatches it with custom_data_0 = first)
 void ref_probes_bake(GkoScene* scene, const void* ubo, void* cubes, void* voxels, uint32_t first, uint32_t count, uint64_t* counters) {
     g_scene = scene;
-    g_closest = 0;
-    g_any = 0;
+    t_closest = t_any = 0;  // single-threaded: the calling thread's counters are the totals
     UniformBufferObject cam;
     std::memcpy(&cam, ubo, sizeof(cam));
     GkoSceneArrays a;
@@ -229,8 +240,8 @@ void ref_probes_bake(GkoScene* scene, const void* ubo, void* cubes, void* voxels
     S.custom_data_0 = first;
     static_assert(sizeof(LightObject) == 80 && sizeof(SphericalHarmonics) == 112 && sizeof(AmbientCube) == 56, "reference layouts");
     for (uint32_t i = 0; i < count; ++i) bake::bake_main(uint3(i, 0u, 0u));
-    counters[0] = g_closest;
-    counters[1] = g_any;
+    counters[0] = t_closest;
+    counters[1] = t_any;
     S.Camera = nullptr;
 }
 

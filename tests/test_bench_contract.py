@@ -50,7 +50,7 @@ def test_cpu_baseline_reference_and_port_trace_the_same_rays_and_threads_do_not_
     scene.update_nodes()
     sky = host.make_sky(64, 32)
     try:
-        ref = bench.CompiledReference(scene, sky)
+        ref = bench.CompiledReference(scene, sky, query="native")
     except FileNotFoundError:
         import pytest
         pytest.skip("oracle/_ref not built (reference not mounted)")
@@ -63,3 +63,33 @@ def test_cpu_baseline_reference_and_port_trace_the_same_rays_and_threads_do_not_
     prays, _ = bench.cpu_port_sample(scene, sky, ubo, GkcuFrameParams(temporal_frames=16, spp_world=1), 1, 2)
     assert prays == rays1 and rays1 > 2 * bench.WIDTH * 3
     assert first["SINGLE_DIFFUSE"].astype(np.float32).max() > 0
+
+
+def test_cpu_baseline_runs_on_the_references_own_tinybvh_and_scales_over_pixel_groups():
+    """The timed CPU arm answers ray queries with the reference's vendored tinybvh (src/Assets/CPUAccelerationStructure.cpp:172-284 usage) and hands
+    out 8 x 8 pixel groups, so a thin band still occupies every core; thread count must not change a pixel, and the ray count must agree with the
+    native-intersector build to within the edge-tie budget (the two intersectors differ only on triangle edges)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from gknextengine_b200 import host
+    scene = host.Scene(bench.SCENE, samples=2, bounces=bench.BOUNCES, taa=True, temporal_frames=16, denoiser=True)
+    scene.update_nodes()
+    sky = host.make_sky(64, 32)
+    try:
+        ref = bench.CompiledReference(scene, sky)
+    except FileNotFoundError:
+        import pytest
+        pytest.skip("oracle/_ref not built (reference not mounted)")
+    if "tinybvh" not in ref.query:
+        import pytest
+        pytest.skip("tinybvh build of the compiled reference not present")
+    ubo = scene.ubo(bench.WIDTH, bench.HEIGHT, 3)
+    rays1, _ = ref.sample(ubo, 1, 8, threads=1)
+    band = slice(bench.HEIGHT // 2 - 4, bench.HEIGHT // 2 + 4)
+    first = {k: v[band].copy() for k, v in ref.images.items()}
+    rays8, _ = ref.sample(ubo, 1, 8, threads=8)
+    assert rays1 == rays8 and all(np.array_equal(first[k].view(np.uint8), ref.images[k][band].view(np.uint8)) for k in first)
+    native = bench.CompiledReference(scene, sky, query="native")
+    nrays, _ = native.sample(ubo, 1, 8, threads=8)
+    assert abs(nrays - rays1) <= 2e-3 * nrays
