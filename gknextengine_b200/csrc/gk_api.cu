@@ -108,6 +108,7 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     if (const char* e = getenv("GKCU_SHADE_MINB")) c.shade_minb = atoi(e);
     if (const char* e = getenv("GKCU_TRACE_CARVEOUT")) c.trace_carveout = std::max(-1, std::min(100, atoi(e)));
     if (const char* e = getenv("GKCU_REFILL")) c.refill_below = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("GKCU_NODE_FORMAT")) c.node_format = atoi(e) == 4 ? 4 : 8;
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
     for (auto& e : c.ev) cudaEventCreate(&e);
     for (auto& e : c.kev) cudaEventCreate(&e);
@@ -137,7 +138,7 @@ int gkcu_destroy(GkcuContext* ctx) {
     for (auto& t : c.textures)
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
-                      &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.instances, &c.inst_lo,
+                      &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.blas_leaf, &c.tlas_leaf, &c.instances, &c.inst_lo,
                       &c.inst_hi, &c.tlas_active_ids, &c.inst_flags, &c.select_tmp, &c.select_count, &c.node_stage, &c.node_stage_idx, &c.tex_table, &c.probes, &c.probe_meta, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
                       &c.peer_flags};
     for (DevBuf* b : bufs) b->release();
@@ -658,7 +659,8 @@ int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out) {
 }
 
 // Debug/validation hook (tests/test_gpu_bvh.py): raw device->host copies of the acceleration-structure pools.
-// what: 0 TLAS nodes, 1 BLAS nodes, 2 BLAS triangles, 3 instances, 4/5 TLAS node boxes lo/hi, 6 BLAS table, 7 NodeProxy array.
+// what: 0 TLAS nodes, 1 BLAS nodes, 2 BLAS triangles, 3 instances, 4/5 TLAS node boxes lo/hi, 6 BLAS table, 7 NodeProxy array,
+// 8/9 TLAS / BLAS leaf tables (Node8), 10/11 BLAS node boxes lo/hi.
 int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, size_t bytes) {
     CTX_OR_FAIL(ctx);
     const DevBuf* b = nullptr;
@@ -671,6 +673,10 @@ int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, s
         case 5: b = &c.tlas_node_hi; break;
         case 6: b = &c.blas_table; break;
         case 7: b = &c.nodes; break;
+        case 8: b = &c.tlas_leaf; break;
+        case 9: b = &c.blas_leaf; break;
+        case 10: b = &c.blas_node_lo; break;
+        case 11: b = &c.blas_node_hi; break;
         default: set_error("gkcu_debug_read: bad selector"); return 1;
     }
     if (!b->p || offset + bytes > b->cap) { set_error("gkcu_debug_read: out of range"); return 1; }
@@ -678,10 +684,11 @@ int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, s
     GK_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }
-// out[0] TLAS node count, [1] TLAS levels, [2] instance count, [3] model count, [4 + 4m ..] per model: node_base, node_count, tri_base, prim_count
+// out[0] TLAS node count, [1] TLAS levels, [2] instance count, [3] model count, [4 + 4m ..] per model: node_base, node_count, tri_base, prim_count;
+// behind the models: node format (4 | 8), TLAS leaf-table entries, then per model: leaf_base, leaf_count (Node8 leaf tables)
 int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity) {
     CTX_OR_FAIL(ctx);
-    if (capacity < 4 + 4 * c.model_count) { set_error("gkcu_debug_info: capacity"); return 1; }
+    if (capacity < 6 + 6 * c.model_count) { set_error("gkcu_debug_info: capacity"); return 1; }
     if (c.tlas_dirty && c.blas_built && build_tlas(c)) return 1;
     out[0] = c.tlas.node_count;
     out[1] = c.tlas.level_start.empty() ? 0 : (uint32_t)c.tlas.level_start.size() - 1;
@@ -692,6 +699,13 @@ int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity) {
         out[5 + 4 * m] = c.blas[m].node_count;
         out[6 + 4 * m] = c.blas[m].tri_base;
         out[7 + 4 * m] = c.blas[m].prim_count;
+    }
+    uint32_t* ext = out + 4 + 4 * c.model_count;
+    ext[0] = (uint32_t)c.node_format;
+    ext[1] = c.tlas.leaf_count;
+    for (uint32_t m = 0; m < c.model_count && m < c.blas.size(); ++m) {
+        ext[2 + 2 * m] = c.blas[m].leaf_base;
+        ext[3 + 2 * m] = c.blas[m].leaf_count;
     }
     return 0;
 }

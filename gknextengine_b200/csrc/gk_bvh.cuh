@@ -2,8 +2,13 @@
 // Replaces what VK_KHR_ray_query + RT cores do for the reference (RayQuery.TraceRayInline/Proceed at
 // assets/shaders/common/Shading.slang:749-756, 794-801); B200 has no RT cores, so this is the hot loop.
 //
-// Layout (all 16-byte aligned, read with 128-bit loads):
-//   Node4      128 B   4-wide node, fp32 child boxes in plane-major order (one cache line)
+// Layout (all 16-byte aligned, read with 128-bit loads). Two node formats, selected per context (GKCU_NODE_FORMAT):
+//   Node8      128 B   8-wide QUANTISED node: child boxes as 11-bit integers on a per-node power-of-two grid,
+//                      stored as fp16 bit patterns in plane-major order, so decoding a plane is one f16->f32 conversion on
+//                      the FMA pipe and one FMA; children are addressed as base + slot, a traversal-stack entry is a
+//                      (base, slot mask) group
+//   Node4      128 B   4-wide node, fp32 child boxes in plane-major order (default: the kernel is bound by instruction issue and
+//                      the 8-wide step costs twice the instructions for 23 % fewer steps, profiles/r02_experiments.md)
 //   leaf tris   48 B   3 x float4 (v0|prim id, v1, v2), stored in leaf order
 //   InstanceRec 64 B   world->object 3x4 + BLAS offsets; TLAS leaves reference one instance each
 // Semantics (shared with the CPU checker): a hit needs tmin < t < tmax, no face culling; the committed closest hit
@@ -22,10 +27,30 @@ struct __align__(16) Node4 {
 };
 static_assert(sizeof(Node4) == 128, "Node4 must be 128 bytes (one cache line)");
 
+// 8-wide quantised node. Child c's box on axis a is [o_a + qlo_a[c] * s_a, o_a + qhi_a[c] * s_a] with s_a a power of two and
+// the q's integers in [0, 2048] (exact in fp16), rounded outward by the builder. Children are stored internal nodes first:
+// slots [0, ni) are the nodes child_base + slot, slots [ni, n) are the leaf-table entries lb + slot (lb = first leaf - ni, kept
+// >= 0 by eight slack entries in front of every leaf table). An empty slot has qlo = +inf, qhi = -inf and can never be hit.
+// A leaf-table entry is a triangle range (first | (count - 1) << 28, absolute in the triangle pool) in a BLAS and an instance
+// index in the TLAS.
+struct __align__(16) Node8 {
+    float ox, oy, oz;
+    uint32_t link;       // child_base (bits 0..23) | n << 24 | ni << 28
+    float sx, sy, sz;
+    uint32_t lb;
+    uint16_t q[6][8];    // qlo_x, qhi_x, qlo_y, qhi_y, qlo_z, qhi_z
+};
+static_assert(sizeof(Node8) == 128, "Node8 must be 128 bytes (one cache line)");
+#ifndef GK_N8_TMIN
+#define GK_N8_TMIN 1  // Node8 stack entries carry the entry distance of their nearest member (24 bits) and are culled as a whole when popped
+#endif
+#define GK_Q_MAX 2047.0f
+#define GK_LEAF_SLACK 8u
+
 struct __align__(16) InstanceRec {
     float w2o[12];       // world->object, 3 rows x 4
     uint32_t node_base;  // BLAS root index in the BLAS node pool
-    uint32_t tri_base;   // first leaf-ordered triangle of the BLAS in the triangle pool
+    uint32_t tri_base;   // Node4: first leaf-ordered triangle of the BLAS in the triangle pool; Node8: first entry of the BLAS's leaf table
     uint32_t active;     // visible && !nort && BLAS non-empty (VkAccelerationStructureInstanceKHR.mask)
     uint32_t blas;
 };
@@ -40,11 +65,14 @@ static_assert(sizeof(InstanceRec) == 64, "InstanceRec must be 64 bytes");
 #endif
 
 struct TraceScene {
-    const Node4* tlas;
+    const Node4* tlas;    // Node4 or Node8 array (both 128 B per node), see fmt
     const Node4* blas;
     const float4* tris;
     const InstanceRec* inst;
+    const uint32_t* tlas_leaf;  // Node8: leaf tables
+    const uint32_t* blas_leaf;
     uint32_t tlas_nodes;  // 0 -> empty scene
+    uint32_t fmt;         // 4 or 8
 };
 
 struct Hit {
@@ -143,18 +171,19 @@ struct LocalStack {
 // ---------------------------------------------------------------------------------------------------------------------
 // Traversal state machine. One ray per lane; the same three steps serve the simple per-ray loop (trace_ray) and the
 // persistent-thread kernel (k_trace), which lets a warp run node steps together and leaf steps together and refills
-// finished lanes with new rays.
+// finished lanes with new rays. FMT selects the node format (4: Node4, 8: Node8).
 struct Trav {
     float3 ro;         // current-space origin (world or object)
     float3 idir;       // current-space reciprocal direction
-    float3 adjn, adjf; // slab offsets -ro * idir, lowered / raised by their own rounding error (see set_space)
+    float3 adjn, adjf; // Node4: slab offsets -ro * idir, lowered / raised by their own rounding error (see set_space)
     uint32_t sgn;      // bit a: idir[a] < 0, i.e. the near plane of axis a is the child's upper plane
     float tmin, tmax;
     Hit best;
     RayShear sh;
     const uint4* nodes;
     const float4* tris;
-    uint32_t cur;      // current node reference
+    const uint32_t* leaf;  // Node8: leaf table of the current space
+    uint32_t cur;      // current item: node index, or GK_LEAF_BIT | leaf reference
     uint32_t cur_inst; // GK_NO_HIT while in the TLAS
     int sp;
     int sp_inst;       // stack height when the current instance was entered: popping down to it leaves the instance
@@ -170,32 +199,40 @@ struct Trav {
 #define GK_STAT(T, k, v) ((void)0)
 #endif
 
-// Slab distances are evaluated as t = plane * idir + adj with adj = -(ro * idir): one FMA per plane. adj carries a rounding
+// Node4: slab distances are evaluated as t = plane * idir + adj with adj = -(ro * idir): one FMA per plane. adj carries a rounding
 // error of half an ulp (|adj| * 2^-24) which the cancellation in plane * idir + adj can make large relative to t, so the
 // near-plane offset is lowered and the far-plane offset raised by 4 ulps of |adj|; the remaining error (one rounding of the
 // FMA result) is relative to t and covered by the relative padding in node_test. The slabs therefore never reject a box
 // that the exact ray enters, which is what makes the closest hit independent of the tree.
+// Node8 derives its offsets per node (the quantisation origin enters them), so only ro / idir / sgn are kept.
+template <int FMT>
 GK_DEV void set_space(Trav& T, float3 ro, float3 idir) {
     T.ro = ro;
     T.idir = idir;
-    const float ax = -(ro.x * idir.x), ay = -(ro.y * idir.y), az = -(ro.z * idir.z);
-    const float ex = fabsf(ax) * 2.4e-7f, ey = fabsf(ay) * 2.4e-7f, ez = fabsf(az) * 2.4e-7f;
-    T.adjn = f3(ax - ex, ay - ey, az - ez);
-    T.adjf = f3(ax + ex, ay + ey, az + ez);
+    if (FMT == 4) {
+        const float ax = -(ro.x * idir.x), ay = -(ro.y * idir.y), az = -(ro.z * idir.z);
+        // + 1e-14 world units (|idir| * 1e-14 in t): a ray lying in a face plane of a box (direction component 0, origin on the
+        // plane) is inside it, like in the CPU checker's slab test
+        const float ex = __fmaf_rn(fabsf(ax), 2.4e-7f, fabsf(idir.x) * 1e-14f), ey = __fmaf_rn(fabsf(ay), 2.4e-7f, fabsf(idir.y) * 1e-14f),
+                    ez = __fmaf_rn(fabsf(az), 2.4e-7f, fabsf(idir.z) * 1e-14f);
+        T.adjn = f3(ax - ex, ay - ey, az - ez);
+        T.adjf = f3(ax + ex, ay + ey, az + ez);
+    }
     T.sgn = (idir.x < 0.0f ? 1u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 4u : 0u);
 }
 
-template <class W>
+template <int FMT, class W>
 GK_DEV void trav_init(Trav& T, W& world, const TraceScene& S, float3 o, float3 d, float tmin, float tmax, bool any) {
     const float3 idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
     world.set(o, d, idir);
-    set_space(T, o, idir);
+    set_space<FMT>(T, o, idir);
     T.tmin = tmin; T.tmax = tmax;
     T.best.t = tmax; T.best.u = 0.0f; T.best.v = 0.0f; T.best.inst = GK_NO_HIT; T.best.prim = 0;
     T.sh.kx = T.sh.ky = T.sh.kz = 0;
     T.sh.Sx = T.sh.Sy = T.sh.Sz = 0.0f;
     T.nodes = reinterpret_cast<const uint4*>(S.tlas);
     T.tris = S.tris;
+    T.leaf = S.tlas_leaf;
     T.cur = 0;
     T.cur_inst = GK_NO_HIT;
     T.sp = 0;
@@ -207,17 +244,29 @@ GK_DEV void trav_init(Trav& T, W& world, const TraceScene& S, float3 o, float3 d
 #endif
 }
 
-// Pops the next node to visit (culling entries that are already farther than the best hit); once every node the current
-// instance pushed has been consumed the ray goes back to world space and the TLAS.
-template <class W, class St>
+// Pops the next item to visit; once every entry the current instance pushed has been consumed the ray goes back to world
+// space and the TLAS. Node4 entries are (child reference, entry distance) and are culled here when they lie beyond the best
+// hit; Node8 entries are (base, slot mask) groups that hand out one child per pop (a child beyond the best hit is rejected by
+// its own node step or triangle test).
+template <int FMT, class W, class St>
 GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
     for (;;) {
         if (T.cur_inst != GK_NO_HIT && T.sp == T.sp_inst) {
-            set_space(T, world.o(), world.widir());
+            set_space<FMT>(T, world.o(), world.widir());
             T.nodes = reinterpret_cast<const uint4*>(S.tlas);
+            if (FMT == 8) T.leaf = S.tlas_leaf;
             T.cur_inst = GK_NO_HIT;
         }
         if (T.sp == 0) { T.done = true; return; }
+        if (FMT == 8) {
+            const uint2 e = stack.e[T.sp - 1];
+            if (GK_N8_TMIN && __uint_as_float(e.y & ~0xFFu) > T.best.t) { GK_STAT(T, 4, 1); --T.sp; continue; }
+            const uint32_t m = e.y & 0xFFu, rest = m & (m - 1u);
+            if (rest) stack.e[T.sp - 1].y = (e.y & ~0xFFu) | rest;
+            else --T.sp;
+            T.cur = e.x + (uint32_t)(__ffs((int)m) - 1);
+            return;
+        }
         const uint2 e = stack.pop(T.sp);
         if (__uint_as_float(e.y) > T.best.t) { GK_STAT(T, 4, 1); continue; }
         T.cur = e.x;
@@ -225,13 +274,12 @@ GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
     }
 }
 
-// Internal node: test the 4 child boxes, continue with the nearest, push the others (second nearest on top).
+// Internal node, Node4: test the 4 child boxes, continue with the nearest, push the others (second nearest on top).
 // Node4 keeps the planes as fp32 in structure-of-arrays order, so the near and far planes of an axis are two 16-byte loads
-// picked by the sign of the ray direction and every plane costs exactly one FMA: the kernel is bound by instruction issue,
-// not by bytes (profiles/r01_experiments.md), and the 8-bit quantised nodes it replaces spent 12 of their 31 instructions
-// per child on unpacking. The interval is padded by a few ulps on both ends (see set_space).
+// picked by the sign of the ray direction and every plane costs exactly one FMA. The interval is padded by a few ulps on
+// both ends (see set_space).
 template <class W, class St>
-GK_DEV void trav_node_step(Trav& T, const W& world, const TraceScene& S, St& stack) {
+GK_DEV void trav_node_step4(Trav& T, const W& world, const TraceScene& S, St& stack) {
     const uint4* np = T.nodes + (size_t)T.cur * 8;
     const uint32_t ix = T.sgn & 1u, iy = (T.sgn >> 1) & 1u, iz = T.sgn >> 2;
     const uint4 nx = __ldg(np + ix), fx = __ldg(np + (ix ^ 1u));
@@ -269,7 +317,7 @@ GK_DEV void trav_node_step(Trav& T, const W& world, const TraceScene& S, St& sta
     if (tn[1] < t0) { t0 = tn[1]; i0 = 1; }
     if (tn[2] < t0) { t0 = tn[2]; i0 = 2; }
     if (tn[3] < t0) { t0 = tn[3]; i0 = 3; }
-    if (!(t0 < inf)) { trav_pop(T, world, S, stack); return; }
+    if (!(t0 < inf)) { trav_pop<4>(T, world, S, stack); return; }
     if (GK_PUSH_ORDERED) {
         int i1 = -1;
         float t1 = inf;
@@ -291,11 +339,84 @@ GK_DEV void trav_node_step(Trav& T, const W& world, const TraceScene& S, St& sta
     T.cur = ref[i0];
 }
 
-// Leaf: a TLAS leaf enters the instance's BLAS in object space (t is preserved by the affine map); a BLAS leaf tests triangles.
+// Internal node, Node8. Per axis the plane distances are t = q * S + C with S = s * idir (exact: s is a power of two) and
+// C = (o - ro) * idir; q * S is exact in the FMA, so the only rounding errors are the two roundings of C, the rounding of idir
+// and the final rounding of the FMA, together at most 4 * 2^-24 * (|C| + 2048 |S|): the near offset is lowered and the far
+// offset raised by P = 2.5e-7 |C| + 5e-4 |S| (5e-4 of one grid cell). The slabs therefore never reject a box the exact ray
+// enters, which keeps the closest hit independent of the tree. The warp continues with the nearest hit child; the others stay
+// behind as at most two stack entries (internal children, leaf children), each a (base, slot mask) group.
+GK_DEV float2 gk_h2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+#define GK_N8_SENT 0x7F000000u
 template <class W, class St>
+GK_DEV void trav_node_step8(Trav& T, const W& world, const TraceScene& S, St& stack) {
+    const uint4* np = T.nodes + (size_t)T.cur * 8;
+    const uint32_t ix = T.sgn & 1u, iy = (T.sgn >> 1) & 1u, iz = T.sgn >> 2;
+    const uint4 h0 = __ldg(np), h1 = __ldg(np + 1);
+    const uint4 nx = __ldg(np + 2 + ix), fx = __ldg(np + 2 + (ix ^ 1u));
+    const uint4 ny = __ldg(np + 4 + iy), fy = __ldg(np + 4 + (iy ^ 1u));
+    const uint4 nz = __ldg(np + 6 + iz), fz = __ldg(np + 6 + (iz ^ 1u));
+    // per-axis scale and the two padded offsets
+    const float Sx = __uint_as_float(h1.x) * T.idir.x, Sy = __uint_as_float(h1.y) * T.idir.y, Sz = __uint_as_float(h1.z) * T.idir.z;
+    const float Cx = (__uint_as_float(h0.x) - T.ro.x) * T.idir.x, Cy = (__uint_as_float(h0.y) - T.ro.y) * T.idir.y, Cz = (__uint_as_float(h0.z) - T.ro.z) * T.idir.z;
+    const float Px = __fmaf_rn(fabsf(Cx), 2.5e-7f, fabsf(Sx) * 5e-4f), Py = __fmaf_rn(fabsf(Cy), 2.5e-7f, fabsf(Sy) * 5e-4f),
+                Pz = __fmaf_rn(fabsf(Cz), 2.5e-7f, fabsf(Sz) * 5e-4f);
+    const float Cnx = Cx - Px, Cfx = Cx + Px, Cny = Cy - Py, Cfy = Cy + Py, Cnz = Cz - Pz, Cfz = Cz + Pz;
+    const uint32_t wnx[4] = {nx.x, nx.y, nx.z, nx.w}, wfx[4] = {fx.x, fx.y, fx.z, fx.w};
+    const uint32_t wny[4] = {ny.x, ny.y, ny.z, ny.w}, wfy[4] = {fy.x, fy.y, fy.z, fy.w};
+    const uint32_t wnz[4] = {nz.x, nz.y, nz.z, nz.w}, wfz[4] = {fz.x, fz.y, fz.z, fz.w};
+    const float tcap = T.best.t;
+    uint32_t kmin = GK_N8_SENT | 7u, k2 = GK_N8_SENT | 7u, mask = 0u;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const float2 qnx = gk_h2(wnx[w]), qfx = gk_h2(wfx[w]), qny = gk_h2(wny[w]), qfy = gk_h2(wfy[w]), qnz = gk_h2(wnz[w]), qfz = gk_h2(wfz[w]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = 2 * w + h;
+            const float x0 = __fmaf_rn(h ? qnx.y : qnx.x, Sx, Cnx), x1 = __fmaf_rn(h ? qfx.y : qfx.x, Sx, Cfx);
+            const float y0 = __fmaf_rn(h ? qny.y : qny.x, Sy, Cny), y1 = __fmaf_rn(h ? qfy.y : qfy.x, Sy, Cfy);
+            const float z0 = __fmaf_rn(h ? qnz.y : qnz.x, Sz, Cnz), z1 = __fmaf_rn(h ? qfz.y : qfz.x, Sz, Cfz);
+            const float n = fmaxf(fmaxf(x0, y0), fmaxf(z0, T.tmin));
+            const float f = fminf(fminf(x1, y1), fminf(z1, tcap));
+            const bool hit = n <= f;  // an empty slot has qlo = +inf, qhi = -inf: n = +inf, f = -inf
+            // n >= tmin > 0, so its bit pattern orders like the float: the slot index rides in the three lowest mantissa bits
+            const uint32_t key = hit ? ((__float_as_uint(n) & ~7u) | (uint32_t)c) : (GK_N8_SENT | (uint32_t)c);
+            if (GK_N8_TMIN) {  // smallest and second smallest key
+                const uint32_t hi = max(kmin, key);
+                kmin = min(kmin, key);
+                k2 = min(k2, hi);
+            } else {
+                kmin = min(kmin, key);
+            }
+            mask |= hit ? (1u << c) : 0u;
+        }
+    }
+    GK_STAT(T, T.cur_inst == GK_NO_HIT ? 0 : 1, 1);
+    GK_STAT(T, 2, __popc(mask));
+    if (kmin >= GK_N8_SENT) { trav_pop<8>(T, world, S, stack); return; }
+    const uint32_t s1 = kmin & 7u, ni = h0.w >> 28, cb = h0.w & 0x00FFFFFFu, lb = GK_LEAF_BIT | h1.w;
+    const uint32_t rest = mask & ~(1u << s1), low = (1u << ni) - 1u;
+    // the entry distance of the nearest child that stays behind bounds both groups from below (the slot bits and the low byte of
+    // the float are cleared: rounded down, i.e. conservative)
+    const uint32_t tb = GK_N8_TMIN ? (k2 & ~0xFFu) : 0u;
+    const uint32_t im = rest & low, lm = rest & ~low;
+    if (im) { GK_STAT(T, 3, 1); stack.push(T.sp, make_uint2(cb, tb | im)); }
+    if (lm) { GK_STAT(T, 3, 1); stack.push(T.sp, make_uint2(lb, tb | lm)); }  // leaves on top: they tighten the best hit before the deeper nodes
+    T.cur = (s1 < ni ? cb : lb) + s1;
+}
+
+template <int FMT, class W, class St>
+GK_DEV void trav_node_step(Trav& T, const W& world, const TraceScene& S, St& stack) {
+    if (FMT == 8) trav_node_step8(T, world, S, stack);
+    else trav_node_step4(T, world, S, stack);
+}
+
+// Leaf: a TLAS leaf enters the instance's BLAS in object space (t is preserved by the affine map); a BLAS leaf tests triangles.
+template <int FMT, class W, class St>
 GK_DEV void trav_leaf_step(Trav& T, const W& world, const TraceScene& S, St& stack) {
+    uint32_t ref = T.cur & 0x0FFFFFFFu;
+    if (FMT == 8) ref = __ldg(T.leaf + (T.cur & 0x7FFFFFFFu));  // leaf-table entry: instance index or triangle range
     if (T.cur_inst == GK_NO_HIT) {
-        const uint32_t ii = T.cur & 0x0FFFFFFFu;
+        const uint32_t ii = FMT == 8 ? ref : (T.cur & 0x0FFFFFFFu);
         const float4* ir = reinterpret_cast<const float4*>(S.inst + ii);
         const float4 r0 = __ldg(ir), r1 = __ldg(ir + 1), r2 = __ldg(ir + 2);
         const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ir) + 3);
@@ -303,17 +424,19 @@ GK_DEV void trav_leaf_step(Trav& T, const W& world, const TraceScene& S, St& sta
         if (meta.z) {
             const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
             const float3 rd = xform_vec(m, world.d());
-            set_space(T, xform_point(m, world.o()), f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z)));
+            set_space<FMT>(T, xform_point(m, world.o()), f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z)));
             T.sh = make_shear(rd);
             T.sp_inst = T.sp;
             T.nodes = reinterpret_cast<const uint4*>(S.blas + meta.x);
-            T.tris = S.tris + (size_t)meta.y * 3;
+            if (FMT == 8) T.leaf = S.blas_leaf + meta.y;
+            else T.tris = S.tris + (size_t)meta.y * 3;
             T.cur_inst = ii;
             T.cur = 0;
             return;
         }
     } else {
-        const uint32_t first = T.cur & 0x0FFFFFFFu, count = ((T.cur >> 28) & 7u) + 1u;
+        const uint32_t first = FMT == 8 ? (ref & 0x0FFFFFFFu) : (T.cur & 0x0FFFFFFFu);
+        const uint32_t count = FMT == 8 ? (ref >> 28) + 1u : ((T.cur >> 28) & 7u) + 1u;
         GK_STAT(T, 6, 1);
         GK_STAT(T, 7, count);
         for (uint32_t i = 0; i < count; ++i) {
@@ -341,21 +464,27 @@ GK_DEV void trav_leaf_step(Trav& T, const W& world, const TraceScene& S, St& sta
             }
         }
     }
-    trav_pop(T, world, S, stack);
+    trav_pop<FMT>(T, world, S, stack);
 }
 
 // Closest hit (ANY = false) or first hit (ANY = true; best.inst != GK_NO_HIT means occluded): the simple per-ray loop.
-template <bool ANY>
-GK_DEV void trace_ray(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, Hit& best) {
+template <bool ANY, int FMT>
+GK_DEV void trace_ray_fmt(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, Hit& best) {
     LocalStack stack;
     Trav T;
     WorldRegs world;
-    trav_init(T, world, S, o, d, tmin, tmax, ANY);
+    trav_init<FMT>(T, world, S, o, d, tmin, tmax, ANY);
     while (!T.done) {
-        if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, world, S, stack);
-        else trav_leaf_step(T, world, S, stack);
+        if (!(T.cur & GK_LEAF_BIT)) trav_node_step<FMT>(T, world, S, stack);
+        else trav_leaf_step<FMT>(T, world, S, stack);
     }
     best = T.best;
+}
+// The kernels off the hot path pick the format at run time (both loops are compiled in); k_trace is instantiated per format.
+template <bool ANY>
+GK_DEV void trace_ray(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, Hit& best) {
+    if (S.fmt == 8) trace_ray_fmt<ANY, 8>(S, o, d, tmin, tmax, best);
+    else trace_ray_fmt<ANY, 4>(S, o, d, tmin, tmax, best);
 }
 
 }  // namespace gkd

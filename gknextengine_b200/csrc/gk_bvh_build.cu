@@ -216,6 +216,109 @@ __device__ __forceinline__ float box_area(float4 lo, float4 hi) {
     return dx * dy + dy * dz + dz * dx;
 }
 
+// Node8 (gk_bvh.cuh): quantise the child boxes onto the node's power-of-two grid, rounded outward. The checks use directed
+// roundings of o + q * s, so a plane is moved one more cell out whenever the rounded sum could lie on the wrong side.
+__device__ void write_node8(Node8* out, int nk, int ni, const ChildBox* ch, uint32_t child_base, uint32_t lb) {
+    float3 plo = f3(FLT_MAX, FLT_MAX, FLT_MAX), phi = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int c = 0; c < nk; ++c) {
+        plo = f3(fminf(plo.x, ch[c].lo.x), fminf(plo.y, ch[c].lo.y), fminf(plo.z, ch[c].lo.z));
+        phi = f3(fmaxf(phi.x, ch[c].hi.x), fmaxf(phi.y, ch[c].hi.y), fmaxf(phi.z, ch[c].hi.z));
+    }
+    const float o[3] = {plo.x, plo.y, plo.z}, e[3] = {phi.x - plo.x, phi.y - plo.y, phi.z - plo.z};
+    float sc[3];
+    for (int a = 0; a < 3; ++a) {
+        int ex = 0;
+        const float need = e[a] / GK_Q_MAX * 1.000001f;  // the subtraction above was rounded
+        sc[a] = 1.0f;
+        if (need > 0.0f && need < 1e30f) { frexpf(need, &ex); sc[a] = ldexpf(1.0f, ex); }
+        sc[a] = fmaxf(sc[a], 1e-18f);
+    }
+    Node8 node;
+    node.ox = o[0]; node.oy = o[1]; node.oz = o[2];
+    node.sx = sc[0]; node.sy = sc[1]; node.sz = sc[2];
+    node.link = child_base | ((uint32_t)nk << 24) | ((uint32_t)ni << 28);
+    node.lb = lb;
+    for (int c = 0; c < 8; ++c) {
+        if (c >= nk) {
+            for (int a = 0; a < 3; ++a) { node.q[2 * a][c] = 0x7C00; node.q[2 * a + 1][c] = 0xFC00; }  // +inf / -inf: never hit
+            continue;
+        }
+        const float lo[3] = {ch[c].lo.x, ch[c].lo.y, ch[c].lo.z}, hi[3] = {ch[c].hi.x, ch[c].hi.y, ch[c].hi.z};
+        for (int a = 0; a < 3; ++a) {
+            float ql = floorf((lo[a] - o[a]) / sc[a]), qh = ceilf((hi[a] - o[a]) / sc[a]);
+            ql = fmaxf(ql, 0.0f);
+            if (__fmaf_ru(ql, sc[a], o[a]) > lo[a]) ql = fmaxf(ql - 1.0f, 0.0f);  // o <= lo, so q = 0 is always on the right side
+            if (__fmaf_rd(qh, sc[a], o[a]) < hi[a]) qh += 1.0f;
+            if (__fmaf_rd(qh, sc[a], o[a]) < hi[a]) qh += 1.0f;
+            node.q[2 * a][c] = __half_as_ushort(__float2half_rd(ql));   // integers <= 2048 are exact in fp16; the directed
+            node.q[2 * a + 1][c] = __half_as_ushort(__float2half_ru(qh));  // conversions only matter if the grid were ever exceeded
+        }
+    }
+    *out = node;
+}
+
+// One BFS level of the BVH2 -> Node8 collapse. Like collapse_item below, but up to eight children, the internal children in
+// the first slots and in consecutive node slots, the leaf children behind them with consecutive leaf-table entries.
+__device__ __forceinline__ void collapse_item8(int i, const int2* qin, int2* qout, int* nout, int* node_counter, int* leaf_counter,
+                                  const float4* nlo, const float4* nhi, const int* left, const int* right, const int* first, const int* count,
+                                  int leaf_max, const uint32_t* order, const uint32_t* remap, int tlas_mode, uint32_t tri_base_abs, Node8* out,
+                                  uint32_t* leaf_out, float4* out_lo, float4* out_hi) {
+    const int2 e = qin[i];
+    int kids[8];
+    int nk;
+#define GK_IS_LEAF2(n2) (left[n2] < 0 || count[n2] <= leaf_max)
+    if (GK_IS_LEAF2(e.x)) {  // degenerate: the whole BVH is one leaf
+        kids[0] = e.x;
+        nk = 1;
+    } else {
+        kids[0] = left[e.x];
+        kids[1] = right[e.x];
+        nk = 2;
+        while (nk < 8) {
+            int best = -1;
+            float barea = -1.0f;
+            for (int k = 0; k < nk; ++k) {
+                if (GK_IS_LEAF2(kids[k])) continue;
+                const float a = box_area(nlo[kids[k]], nhi[kids[k]]);
+                if (a > barea) { barea = a; best = k; }
+            }
+            if (best < 0) break;
+            const int n2 = kids[best];
+            kids[best] = left[n2];
+            kids[nk++] = right[n2];
+        }
+    }
+    // internal children first (stable)
+    int ord[8], ni = 0;
+    for (int k = 0; k < nk; ++k)
+        if (!GK_IS_LEAF2(kids[k])) ord[ni++] = kids[k];
+    int nl = 0;
+    for (int k = 0; k < nk; ++k)
+        if (GK_IS_LEAF2(kids[k])) ord[ni + nl++] = kids[k];
+    uint32_t cb = 0, l0 = 0;
+    if (ni) {
+        cb = (uint32_t)atomicAdd(node_counter, ni);
+        const int q = atomicAdd(nout, ni);
+        for (int r = 0; r < ni; ++r) qout[q + r] = make_int2(ord[r], (int)cb + r);
+    }
+    if (nl) l0 = (uint32_t)atomicAdd(leaf_counter, nl);
+    ChildBox ch[8];
+    for (int k = 0; k < nk; ++k) {
+        const int n2 = ord[k];
+        const float4 l = nlo[n2], h = nhi[n2];
+        ch[k].lo = f3(l.x, l.y, l.z);
+        ch[k].hi = f3(h.x, h.y, h.z);
+        ch[k].ref = 0;
+        if (k >= ni) {
+            const uint32_t f = (uint32_t)first[n2];
+            leaf_out[l0 + (k - ni)] = tlas_mode ? remap[order[f]] : ((tri_base_abs + f) | ((uint32_t)(count[n2] - 1) << 28));
+        }
+    }
+    write_node8(out + e.y, nk, ni, ch, cb, nl ? l0 - (uint32_t)ni : 0u);
+    out_lo[e.y] = nlo[e.x];
+    out_hi[e.y] = nhi[e.x];
+}
+
 // One BFS level of the BVH2 -> Node4 collapse. Entry = (bvh2 node, node4 slot). A bvh2 node with <= leaf_max primitives
 // becomes a leaf reference; otherwise the largest-area internal child is opened until there are 4 children.
 __device__ __forceinline__ void collapse_item(int i, const int2* qin, const int* nin_ptr, int2* qout, int* nout, int* node_counter,
@@ -270,14 +373,19 @@ __device__ __forceinline__ void collapse_item(int i, const int2* qin, const int*
     out_lo[e.y] = l;
     out_hi[e.y] = h;
 }
+struct Wide8Out { int fmt; int* leaf_counter; uint32_t* leaf_out; uint32_t tri_base_abs; };
 __global__ void k_collapse_level(const int2* __restrict__ qin, const int* __restrict__ nin_ptr, int2* __restrict__ qout, int* __restrict__ nout, int* __restrict__ node_counter,
                                  const float4* __restrict__ nlo, const float4* __restrict__ nhi, const int* __restrict__ left,
                                  const int* __restrict__ right, const int* __restrict__ first, const int* __restrict__ count, int leaf_max,
                                  const uint32_t* __restrict__ order, const uint32_t* __restrict__ remap, int tlas_mode, Node4* __restrict__ out, float4* __restrict__ out_lo,
-                                 float4* __restrict__ out_hi) {
+                                 float4* __restrict__ out_hi, Wide8Out w8) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *nin_ptr) return;
-    collapse_item(i, qin, nin_ptr, qout, nout, node_counter, nlo, nhi, left, right, first, count, leaf_max, order, remap, tlas_mode, out, out_lo, out_hi);
+    if (w8.fmt == 8)
+        collapse_item8(i, qin, qout, nout, node_counter, w8.leaf_counter, nlo, nhi, left, right, first, count, leaf_max, order, remap, tlas_mode, w8.tri_base_abs,
+                       reinterpret_cast<Node8*>(out), w8.leaf_out, out_lo, out_hi);
+    else
+        collapse_item(i, qin, nin_ptr, qout, nout, node_counter, nlo, nhi, left, right, first, count, leaf_max, order, remap, tlas_mode, out, out_lo, out_hi);
 }
 
 __global__ void k_write_tris(const uint16_t* __restrict__ simple, const uint32_t* __restrict__ indices, uint32_t vertex_offset,
@@ -355,6 +463,42 @@ __global__ void k_refit_level(Node4* __restrict__ nodes, float4* __restrict__ no
         nhi = f3(fmaxf(nhi.x, hi.x), fmaxf(nhi.y, hi.y), fmaxf(nhi.z, hi.z));
     }
     write_node4(nodes + i, nk, ch);
+    node_lo[i] = f4(nlo.x, nlo.y, nlo.z, 0);
+    node_hi[i] = f4(nhi.x, nhi.y, nhi.z, 0);
+}
+
+// Node8 refit of one BFS level: the child boxes come from the triangles (leaf-table ranges, absolute in the triangle pool) or
+// from the already refitted deeper level; the node is re-quantised on its new grid, links and slot order stay.
+__global__ void k_refit_level8(Node8* __restrict__ nodes, float4* __restrict__ node_lo, float4* __restrict__ node_hi, uint32_t begin, uint32_t end,
+                               const float4* __restrict__ tris_pool, const uint32_t* __restrict__ leaf) {
+    uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    const uint32_t link = nodes[i].link, lb = nodes[i].lb;
+    const int nk = (int)((link >> 24) & 15u), ni = (int)(link >> 28);
+    const uint32_t cb = link & 0x00FFFFFFu;
+    ChildBox ch[8];
+    float3 nlo = f3(FLT_MAX, FLT_MAX, FLT_MAX), nhi = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int k = 0; k < nk; ++k) {
+        float3 lo, hi;
+        if (k >= ni) {
+            const uint32_t rec = leaf[lb + (uint32_t)k], first = rec & 0x0FFFFFFFu, cnt = (rec >> 28) + 1u;
+            lo = f3(FLT_MAX, FLT_MAX, FLT_MAX);
+            hi = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+            for (uint32_t t = 0; t < cnt * 3; ++t) {
+                const float4 v = tris_pool[(size_t)first * 3 + t];
+                lo = f3(fminf(lo.x, v.x), fminf(lo.y, v.y), fminf(lo.z, v.z));
+                hi = f3(fmaxf(hi.x, v.x), fmaxf(hi.y, v.y), fmaxf(hi.z, v.z));
+            }
+        } else {
+            const float4 l = node_lo[cb + (uint32_t)k], h = node_hi[cb + (uint32_t)k];
+            lo = f3(l.x, l.y, l.z);
+            hi = f3(h.x, h.y, h.z);
+        }
+        ch[k].lo = lo; ch[k].hi = hi; ch[k].ref = 0;
+        nlo = f3(fminf(nlo.x, lo.x), fminf(nlo.y, lo.y), fminf(nlo.z, lo.z));
+        nhi = f3(fmaxf(nhi.x, hi.x), fmaxf(nhi.y, hi.y), fmaxf(nhi.z, hi.z));
+    }
+    write_node8(nodes + i, nk, ni, ch, cb, lb);
     node_lo[i] = f4(nlo.x, nlo.y, nlo.z, 0);
     node_hi[i] = f4(nhi.x, nhi.y, nhi.z, 0);
 }
@@ -598,6 +742,7 @@ struct FusedBuild {
     const uint32_t* remap;
     Node4* out;
     float4 *out_lo, *out_hi;
+    Wide8Out w8;
 };
 template <bool GRID>
 __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B) {
@@ -706,15 +851,20 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B)
     }
     // collapse to Node4, BFS; counters[8] node4 counter, [9] next-level queue size, [10] this level's queue size, [16 + L] level table
     int2 *qa = B.qa, *qb = B.qb;
-    if (t == 0) { qa[0] = make_int2(0, 0); counters[8] = 1; counters[9] = 0; counters[10] = 1; }
+    if (t == 0) { qa[0] = make_int2(0, 0); counters[8] = 1; counters[9] = 0; counters[10] = 1; counters[12] = (int)GK_LEAF_SLACK; }
     for (int i = t; i < 48; i += T) counters[16 + i] = 0;
     sync();
     for (int level = 0; level < 46; ++level) {
         const int nin = counters[10];
         if (nin == 0) break;
-        for (int i = t; i < nin; i += T)
-            collapse_item(i, qa, counters + 10, qb, counters + 9, counters + 8, B.nlo, B.nhi, B.left, B.right, B.first, B.count, B.leaf_max, ord_a, B.remap,
-                          B.remap ? 1 : 0, B.out, B.out_lo, B.out_hi);
+        for (int i = t; i < nin; i += T) {
+            if (B.w8.fmt == 8)
+                collapse_item8(i, qa, qb, counters + 9, counters + 8, counters + 12, B.nlo, B.nhi, B.left, B.right, B.first, B.count, B.leaf_max, ord_a, B.remap,
+                               B.remap ? 1 : 0, B.w8.tri_base_abs, reinterpret_cast<Node8*>(B.out), B.w8.leaf_out, B.out_lo, B.out_hi);
+            else
+                collapse_item(i, qa, counters + 10, qb, counters + 9, counters + 8, B.nlo, B.nhi, B.left, B.right, B.first, B.count, B.leaf_max, ord_a, B.remap,
+                              B.remap ? 1 : 0, B.out, B.out_lo, B.out_hi);
+        }
         sync();
         if (t == 0) {
             counters[16 + level + 2] = counters[8];
@@ -921,22 +1071,23 @@ int build_sah(Context& c, uint32_t n, int leaf_max, Bvh2& out) {
 
 // BVH2 -> Node4 (BFS), returns node count and the level table.
 int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, const uint32_t* remap, Node4* out, float4* out_lo, float4* out_hi,
-             WideBvhInfo& info) {
+             WideBvhInfo& info, Wide8Out w8) {
     BuildScratch& s = c.scratch;
     cudaStream_t st = c.stream;
     int* counters = s.counters.as<int>();  // [8] node counter, [9] out-queue count
     int2 *qa = s.queue_a.as<int2>(), *qb = s.queue_b.as<int2>();
     int2 root = make_int2(b.root, 0);
-    int init[3] = {1, 0, 1};  // [8] node4 counter, [9] next-level queue size, [10] this level's queue size
+    int init[5] = {1, 0, 1, 0, (int)GK_LEAF_SLACK};  // [8] node counter, [9] next-level queue size, [10] this level's queue size, [12] leaf-table cursor
+    w8.leaf_counter = counters + 12;
     GK_CUDA(cudaMemcpyAsync(qa, &root, sizeof(root), cudaMemcpyHostToDevice, st));
-    GK_CUDA(cudaMemcpyAsync(counters + 8, init, 12, cudaMemcpyHostToDevice, st));
+    GK_CUDA(cudaMemcpyAsync(counters + 8, init, 20, cudaMemcpyHostToDevice, st));
     GK_CUDA(cudaMemsetAsync(counters + 16, 0, 48 * 4, st));
     (void)n_prims;
     int levels_run = 0;
     for (int level = 0; level < 46; ++level) {
-        const size_t ub = level < 15 ? std::min<size_t>((size_t)n_prims + 1, (size_t)1 << (2 * level)) : (size_t)n_prims + 1;
+        const size_t ub = level < 10 ? std::min<size_t>((size_t)n_prims + 1, (size_t)1 << (3 * level)) : (size_t)n_prims + 1;
         k_collapse_level<<<grid_for(ub, 128), 128, 0, st>>>(qa, counters + 10, qb, counters + 9, counters + 8, b.lo, b.hi, b.left, b.right, b.first, b.count,
-                                                            leaf_max, b.order, remap, remap ? 1 : 0, out, out_lo, out_hi);
+                                                            leaf_max, b.order, remap, remap ? 1 : 0, out, out_lo, out_hi, w8);
         k_collapse_next<<<1, 1, 0, st>>>(counters, level);
         c.launches += 2;
         std::swap(qa, qb);
@@ -951,10 +1102,11 @@ int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, const ui
     // level table: counters[16 + L] = first node of level L (level 0 starts at 0, level 1 at 1)
     int table[48];
     GK_CUDA(cudaMemcpyAsync(table, counters + 16, 48 * 4, cudaMemcpyDeviceToHost, st));
-    int last[3];
-    GK_CUDA(cudaMemcpyAsync(last, counters + 8, 12, cudaMemcpyDeviceToHost, st));
+    int last[5];
+    GK_CUDA(cudaMemcpyAsync(last, counters + 8, 20, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
     if (last[2] != 0) { set_error("BVH collapse did not terminate (tree deeper than 46 wide levels)"); return 1; }
+    info.leaf_count = (uint32_t)last[4];
     // level table: table[L] = first node of BFS level L; table[L + 2] was written after level L had been processed
     info.level_start.clear();
     info.level_start.push_back(0);
@@ -970,7 +1122,7 @@ int collapse(Context& c, const Bvh2& b, uint32_t n_prims, int leaf_max, const ui
 }
 
 // Small inputs: bounds + SAH build + collapse in one single-block launch, one host read at the end.
-int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Node4* out, float4* out_lo, float4* out_hi, WideBvhInfo& info) {
+int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Node4* out, float4* out_lo, float4* out_hi, WideBvhInfo& info, Wide8Out w8) {
     BuildScratch& s = c.scratch;
     cudaStream_t st = c.stream;
     size_t max_slots = n / (leaf_max + 1) + 2;
@@ -993,6 +1145,7 @@ int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Nod
     B.bins = s.bins.as<SahBin>();
     B.qa = s.queue_a.as<int2>(); B.qb = s.queue_b.as<int2>();
     B.remap = remap; B.out = out; B.out_lo = out_lo; B.out_hi = out_hi;
+    B.w8 = w8;
     // one item per thread up to two blocks per SM (all co-resident: 64 registers x 256 threads); a single block for tiny inputs
     const int blocks = (int)std::min<size_t>((size_t)c.sm_count * 2, ((size_t)n + 255) / 256);
     if (blocks <= 1) {
@@ -1003,13 +1156,14 @@ int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Nod
     }
     c.launches += 1;
     int table[48];
-    int last[4];
+    int last[5];
     GK_CUDA(cudaMemcpyAsync(table, B.counters + 16, 48 * 4, cudaMemcpyDeviceToHost, st));
-    GK_CUDA(cudaMemcpyAsync(last, B.counters + 8, 16, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaMemcpyAsync(last, B.counters + 8, 20, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
     GK_CUDA(cudaGetLastError());
     if (last[2] != 0) { set_error("BVH collapse did not terminate (tree deeper than 46 wide levels)"); return 1; }
     const int levels_run = last[3];
+    info.leaf_count = (uint32_t)last[4];
     info.level_start.clear();
     info.level_start.push_back(0);
     table[0] = 0;
@@ -1049,7 +1203,10 @@ gkd::TraceScene make_trace_scene(const Context& c) {
     s.blas = c.blas_nodes.as<Node4>();
     s.tris = c.blas_tris.as<float4>();
     s.inst = c.instances.as<InstanceRec>();
+    s.tlas_leaf = c.tlas_leaf.as<uint32_t>();
+    s.blas_leaf = c.blas_leaf.as<uint32_t>();
     s.tlas_nodes = c.tlas.node_count;
+    s.fmt = (uint32_t)c.node_format;
     return s;
 }
 
@@ -1071,18 +1228,22 @@ int build_all_blas(Context& c) {
     size_t node_cap = total_prims + 2 * (size_t)c.model_count + 4;
     if (!c.blas_nodes.reserve(node_cap * sizeof(Node4)) || !c.blas_node_lo.reserve(node_cap * 16) || !c.blas_node_hi.reserve(node_cap * 16) ||
         !c.blas_tris.reserve((total_prims + 1) * 48) || !c.blas_tri_prim.reserve((total_prims + 1) * 4) ||
-        !c.blas_table.reserve((size_t)(c.model_count + 1) * 48) || !c.shade_tris.reserve((total_prims + 1) * 32))
+        !c.blas_table.reserve((size_t)(c.model_count + 1) * 48) || !c.shade_tris.reserve((total_prims + 1) * 32) ||
+        !c.blas_leaf.reserve((total_prims + (size_t)(c.model_count + 1) * GK_LEAF_SLACK) * 4))
         return 1;
     cudaEventRecord(c.ev[6], st);
-    uint32_t node_base = 0, tri_base = 0;
+    uint32_t node_base = 0, tri_base = 0, leaf_base = 0;
     std::vector<float> table((size_t)c.model_count * 12, 0.0f);
     for (uint32_t m = 0; m < c.model_count; ++m) {
         WideBvhInfo& bi = c.blas[m];
         bi.node_base = node_base;
         bi.tri_base = tri_base;
         uint32_t n = bi.prim_count;
+        bi.leaf_base = leaf_base;
+        bi.leaf_count = 0;
         uint32_t* tb = reinterpret_cast<uint32_t*>(&table[(size_t)m * 12]);
-        tb[0] = node_base; tb[1] = tri_base; tb[2] = n; tb[3] = tri_base;  // shade triangles use the same per-model base, primitive order
+        // Node8 instances carry the BLAS's leaf-table base where Node4 instances carry its triangle base (InstanceRec::tri_base)
+        tb[0] = node_base; tb[1] = c.node_format == 8 ? leaf_base : tri_base; tb[2] = n; tb[3] = tri_base;  // shade triangles use the per-model triangle base, primitive order
         if (n == 0) continue;
         if (n >= (1u << 28)) { set_error("BLAS with >= 2^28 triangles"); return 1; }
         BuildScratch& s = c.scratch;
@@ -1094,7 +1255,8 @@ int build_all_blas(Context& c) {
         if (c.blas_builder == 1) { if (build_sah(c, n, kBlasLeafMax, b2)) return 1; }
         else { if (build_lbvh(c, n, n, b2)) return 1; }
         Node4* out = c.blas_nodes.as<Node4>() + node_base;
-        if (collapse(c, b2, n, kBlasLeafMax, nullptr, out, c.blas_node_lo.as<float4>() + node_base, c.blas_node_hi.as<float4>() + node_base, bi)) return 1;
+        Wide8Out w8{c.node_format, nullptr, c.blas_leaf.as<uint32_t>() + leaf_base, tri_base};
+        if (collapse(c, b2, n, kBlasLeafMax, nullptr, out, c.blas_node_lo.as<float4>() + node_base, c.blas_node_hi.as<float4>() + node_base, bi, w8)) return 1;
         k_write_tris<<<grid_for(n), 256, 0, st>>>(c.simple.as<uint16_t>(), c.indices.as<uint32_t>(), bi.vertex_offset, bi.index_offset, b2.order, n,
                                                   c.blas_tris.as<float4>() + (size_t)tri_base * 3, c.blas_tri_prim.as<uint32_t>() + tri_base);
         k_shade_tris<<<grid_for(n), 256, 0, st>>>(c.vertices.as<uint2>(), c.indices.as<uint32_t>(), bi.vertex_offset, bi.index_offset, n,
@@ -1111,6 +1273,7 @@ int build_all_blas(Context& c) {
         tf[8] = rh.x; tf[9] = rh.y; tf[10] = rh.z; tf[11] = 0;
         node_base += bi.node_count;
         tri_base += n;
+        leaf_base += c.node_format == 8 ? bi.leaf_count : 0u;
     }
     GK_CUDA(cudaMemcpyAsync(c.blas_table.p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st));
     cudaEventRecord(c.ev[7], st);
@@ -1136,7 +1299,11 @@ int refit_blas(Context& c, uint32_t model) {
     for (int L = (int)bi.level_start.size() - 2; L >= 0; --L) {
         uint32_t b = bi.level_start[L], e = bi.level_start[L + 1];
         if (e <= b) continue;
-        k_refit_level<<<grid_for(e - b, 128), 128, 0, st>>>(nodes, nlo, nhi, b, e, c.blas_tris.as<float4>() + (size_t)bi.tri_base * 3);
+        if (c.node_format == 8)
+            k_refit_level8<<<grid_for(e - b, 128), 128, 0, st>>>(reinterpret_cast<Node8*>(nodes), nlo, nhi, b, e, c.blas_tris.as<float4>(),
+                                                                 c.blas_leaf.as<uint32_t>() + bi.leaf_base);
+        else
+            k_refit_level<<<grid_for(e - b, 128), 128, 0, st>>>(nodes, nlo, nhi, b, e, c.blas_tris.as<float4>() + (size_t)bi.tri_base * 3);
         c.launches += 1;
     }
     // the root box feeds the instance boxes of the next TLAS build
@@ -1162,7 +1329,10 @@ int build_tlas(Context& c) {
         !c.tlas_node_hi.reserve(((size_t)n + 4) * 16))
         return 1;
     if (!c.inst_lo.reserve((size_t)n * 16) || !c.inst_hi.reserve((size_t)n * 16) || !c.shade_inst.reserve((size_t)n * 32)) return 1;
-    if (!c.inst_flags.reserve(n) || !c.tlas_active_ids.reserve((size_t)n * 4) || !c.select_count.reserve(16)) return 1;
+    if (!c.inst_flags.reserve(n) || !c.tlas_active_ids.reserve((size_t)n * 4) || !c.select_count.reserve(16) ||
+        !c.tlas_leaf.reserve(((size_t)n + GK_LEAF_SLACK) * 4))
+        return 1;
+    const Wide8Out w8{c.node_format, nullptr, c.tlas_leaf.as<uint32_t>(), 0u};
     k_instances<<<grid_for(n, 128), 128, 0, st>>>(c.nodes.as<GkNodeProxy>(), n, c.blas_table.as<uint4>(), c.model_count, c.instances.as<InstanceRec>(),
                                              c.inst_lo.as<float4>(), c.inst_hi.as<float4>(), c.shade_inst.as<uint4>(), c.inst_flags.as<uint8_t>());
     c.launches += 1;
@@ -1192,17 +1362,19 @@ int build_tlas(Context& c) {
     const uint32_t fused_max = getenv("GKCU_TLAS_FUSED_MAX") ? (uint32_t)atoi(getenv("GKCU_TLAS_FUSED_MAX")) : 262144u;
     if (tb && std::string(tb) == "lbvh") {
         if (build_lbvh(c, m, m, b2)) return 1;
-        if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+        if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas, w8)) return 1;
     } else if (m <= fused_max) {
-        if (build_fused(c, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+        if (build_fused(c, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas, w8)) return 1;
     } else {
         if (build_sah(c, m, 1, b2)) return 1;
-        if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas)) return 1;
+        if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas, w8)) return 1;
     }
-    // the traversal stack holds at most 3 entries per level (TLAS levels + the deepest BLAS)
+    // the traversal stack holds at most 3 (Node4: one per sibling) or 2 (Node8: one group of nodes, one of leaves) entries per
+    // level (TLAS levels + the deepest BLAS)
     size_t blas_levels = 0;
     for (auto& b : c.blas) blas_levels = std::max(blas_levels, b.level_start.size() > 0 ? b.level_start.size() - 1 : 0);
-    size_t need = 3 * (c.tlas.level_start.size() - 1) + 3 * blas_levels + 2;
+    const size_t per_level = c.node_format == 8 ? 2 : 3;
+    size_t need = per_level * (c.tlas.level_start.size() - 1) + per_level * blas_levels + 2;
     if (need > GK_TRAV_STACK) {
         char msg[160];
         snprintf(msg, sizeof(msg), "acceleration structure too deep for the traversal stack (%zu TLAS + %zu BLAS levels need %zu entries, have %d)",

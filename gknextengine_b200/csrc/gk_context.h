@@ -34,6 +34,7 @@ struct WideBvhInfo {
     uint32_t tri_base = 0;      // BLAS only: first leaf-ordered triangle in the triangle pool
     uint32_t prim_count = 0;
     uint32_t vertex_offset = 0, index_offset = 0;
+    uint32_t leaf_base = 0, leaf_count = 0;  // Node8: this BVH's slice of the leaf table (the first GK_LEAF_SLACK entries are slack)
     std::vector<uint32_t> level_start;  // node index (relative) of each BFS level, size levels+1
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
 };
@@ -78,6 +79,7 @@ struct Context {
     DevBuf shade_tris;  // 32 B per primitive (primitive order): 3 normals + 3 uvs as fp16 + material slot, see gk_pathtrace.cu
     DevBuf shade_inst;  // 32 B per instance: shade-triangle base + the first 7 material ids of the node
     DevBuf tlas_nodes, tlas_node_lo, tlas_node_hi, instances, inst_lo, inst_hi, tlas_active_ids;
+    DevBuf blas_leaf, tlas_leaf;  // Node8 leaf tables (triangle ranges / instance indices)
     DevBuf inst_flags, select_tmp, select_count;  // device-side compaction of the instances that enter the TLAS
     DevBuf node_stage, node_stage_idx;            // gkcu_update_nodes_sparse staging
     WideBvhInfo tlas;
@@ -88,7 +90,9 @@ struct Context {
     int trace_variant = 5;  // GKCU_TRACE_VARIANT: 5 vote-selected step kind, 6 blocks/SM (default); 0 one step of any kind per iteration; 2 warp-granular batches, no refill
     int use_tma = 1;        // GKCU_TMA=0 falls back to plain-load staging of the stencil tiles (2 / 3: only reproject / only denoise)
     int shade_minb = 7;     // GKCU_SHADE_MINB: 8 compiles k_shade for 8 blocks/SM (<= 64 registers)
-    int trace_carveout = -1;  // k_trace shared-memory carve-out in percent (GKCU_TRACE_CARVEOUT), -1 = driver default
+    int trace_carveout = -1;  // k_trace shared-memory carve-out in percent (GKCU_TRACE_CARVEOUT), -1 = sized to the resident blocks
+    int carveout_applied = 0; // trace_carveout + 2 once the function attribute has been set on this context's device
+    int node_format = 4;      // GKCU_NODE_FORMAT: 4 = fp32 4-wide Node4 (default: 4.5 % faster on the bench frame, profiles/r02_experiments.md), 8 = quantised 8-wide Node8 (gk_bvh.cuh)
     int refill_below = 16;  // k_trace: refill idle lanes when fewer than this many lanes are busy (GKCU_REFILL)
     int blas_builder = 1;  // 0 = LBVH, 1 = SAH-binned (GKCU_BLAS_BUILDER=lbvh|sah)
 

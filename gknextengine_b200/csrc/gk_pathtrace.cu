@@ -13,6 +13,9 @@
 #include <cstdio>
 #include <type_traits>
 
+#ifndef GK_NODE_REPEAT
+#define GK_NODE_REPEAT 1
+#endif
 #ifndef GK_TRACE_MINB
 #define GK_TRACE_MINB 6  // resident blocks per SM k_trace<5> is compiled for (6 -> 80 registers; 8 -> 64 is 6% slower since the fp32 nodes)
 #endif
@@ -573,7 +576,7 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
 // lanes in another state sit the iteration out instead of serialising a second code path; compiled for GK_TRACE_MINB
 // blocks/SM with the world-space ray parked in shared memory. VARIANT 0: every lane advances one step of whatever kind
 // per iteration (the baseline the vote is measured against, profiles/r01_experiments.md).
-template <int VARIANT>
+template <int VARIANT, int FMT>
 __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below) {
     const uint32_t n = V.counts[qi];
     // the other queue (this wave's output, last wave's input) is idle while this kernel runs: clear its size here instead of
@@ -604,7 +607,7 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
                     slot = base + __popc(idle & ((1u << lane) - 1u));
                     if (slot < n) {
                         const float4 o = __ldcs(ray_o + slot), d = __ldcs(ray_d + slot);  // streamed: keep L1 for nodes and stacks
-                        trav_init(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, (__ldcs(slot_pixel + slot) & 0x80000000u) != 0);
+                        trav_init<FMT>(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, (__ldcs(slot_pixel + slot) & 0x80000000u) != 0);
                         busy = true;
                     }
                 }
@@ -615,8 +618,8 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
         if (VARIANT == 0) {
             do {
                 if (busy && !T.done) {
-                    if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, world, ts, stack);
-                    else trav_leaf_step(T, world, ts, stack);
+                    if (!(T.cur & GK_LEAF_BIT)) trav_node_step<FMT>(T, world, ts, stack);
+                    else trav_leaf_step<FMT>(T, world, ts, stack);
                 }
                 if (busy && T.done) {
                     __stcs(V.hit_tuv + slot, f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst)));
@@ -635,11 +638,15 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
                 const int nN = __popc(bN), nI = __popc(bI), nT = __popc(bT);
                 if (nN + nI + nT < (drained ? 1 : refill_below)) break;  // too few lanes left: refill (or finish)
                 if (nN >= nT && nN >= nI) {
-                    if (wN) trav_node_step(T, world, ts, stack);
+                    if (wN) trav_node_step<FMT>(T, world, ts, stack);
+#if GK_NODE_REPEAT > 1
+                    // most lanes continue with another node: take a second node step before the next vote
+                    if (wN && !T.done && !(T.cur & GK_LEAF_BIT)) trav_node_step<FMT>(T, world, ts, stack);
+#endif
                 } else if (nT >= nI) {
-                    if (wT) trav_leaf_step(T, world, ts, stack);
+                    if (wT) trav_leaf_step<FMT>(T, world, ts, stack);
                 } else {
-                    if (wI) trav_leaf_step(T, world, ts, stack);
+                    if (wI) trav_leaf_step<FMT>(T, world, ts, stack);
                 }
                 if (busy && T.done) {
                     __stcs(V.hit_tuv + slot, f4(T.best.t, T.best.u, T.best.v, __uint_as_float(T.best.inst)));
@@ -671,10 +678,18 @@ __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V,
             {   // diagnostics build (scripts/trav_stats.py): per-frame traversal statistics in counts[32..], see fetch_ray_counters
                 LocalStack stack; Trav T; WorldRegs world;
                 const bool any = (V.slot_pixel[qi][slot] & 0x80000000u) != 0;
-                trav_init(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, any);
-                while (!T.done) {
-                    if (!(T.cur & GK_LEAF_BIT)) trav_node_step(T, world, ts, stack);
-                    else trav_leaf_step(T, world, ts, stack);
+                if (ts.fmt == 8) {
+                    trav_init<8>(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, any);
+                    while (!T.done) {
+                        if (!(T.cur & GK_LEAF_BIT)) trav_node_step<8>(T, world, ts, stack);
+                        else trav_leaf_step<8>(T, world, ts, stack);
+                    }
+                } else {
+                    trav_init<4>(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, any);
+                    while (!T.done) {
+                        if (!(T.cur & GK_LEAF_BIT)) trav_node_step<4>(T, world, ts, stack);
+                        else trav_leaf_step<4>(T, world, ts, stack);
+                    }
                 }
                 h = T.best;
                 unsigned long long* g = reinterpret_cast<unsigned long long*>(V.counts + 32);
@@ -928,18 +943,21 @@ void path_release(Context& c) {
 int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {
     // k_trace<5> is sensitive to L1 capacity (nodes, triangles and the spilled part of the stacks live there): ask for exactly the
     // shared memory its 8 resident blocks need and leave the rest of the 256 KB array to L1.
-    static int carveout_set = -2;
-    if (carveout_set != c.trace_carveout) {
+    if (c.carveout_applied != c.trace_carveout + 2) {  // per context (= per device): cudaFuncSetAttribute applies to the current device
         int pct = c.trace_carveout;
-        if (pct < 0) {
-            cudaFuncAttributes fa;
-            int smem_sm = 0;
-            if (cudaFuncGetAttributes(&fa, k_trace<5>) == cudaSuccess &&
-                cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c.device) == cudaSuccess && smem_sm > 0)
-                pct = std::min(100, (int)((GK_TRACE_MINB * (fa.sharedSizeBytes + 1024) * 100 + smem_sm - 1) / smem_sm));
+        for (int fmt = 0; fmt < 2; ++fmt) {
+            const void* fn = fmt ? (const void*)k_trace<5, 8> : (const void*)k_trace<5, 4>;
+            int p = pct;
+            if (p < 0) {
+                cudaFuncAttributes fa;
+                int smem_sm = 0;
+                if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess &&
+                    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c.device) == cudaSuccess && smem_sm > 0)
+                    p = std::min(100, (int)((GK_TRACE_MINB * (fa.sharedSizeBytes + 1024) * 100 + smem_sm - 1) / smem_sm));
+            }
+            if (p >= 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, p);
         }
-        if (pct >= 0) cudaFuncSetAttribute(k_trace<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        carveout_set = c.trace_carveout;
+        c.carveout_applied = c.trace_carveout + 2;
     }
     cudaStream_t st = c.stream;
     PathBuffers& b = *c.path;
@@ -1001,8 +1019,14 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                     const uint32_t blocks = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 8u);
                     cudaEventRecord(c.wev[l][3 * w], s2);
                     if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half);
-                    else if (c.trace_variant == 0) k_trace<0><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
-                    else k_trace<5><<<std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u), 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                    else if (c.trace_variant == 0) {
+                        if (c.node_format == 8) k_trace<0, 8><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                        else k_trace<0, 4><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                    } else {
+                        const uint32_t tb = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u);
+                        if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                        else k_trace<5, 4><<<tb, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                    }
                     cudaEventRecord(c.wev[l][3 * w + 1], s2);
                     const uint32_t sb = (bound[l] + 127) / 128;
                     if (c.shade_minb == 8) k_shade<8><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));

@@ -292,12 +292,14 @@ class CudaPathTracingRenderer:
 
     # ---- validation hooks
     def debug_info(self):
-        cap = 4 + 4 * 4096
+        cap = 6 + 6 * 4096
         out = (C.c_uint32 * cap)()
         _ck(lib().gkcu_debug_info(self._ctx, out, cap))
-        models = [dict(node_base=out[4 + 4 * m], node_count=out[5 + 4 * m], tri_base=out[6 + 4 * m], prim_count=out[7 + 4 * m])
+        ext = 4 + 4 * out[3]
+        models = [dict(node_base=out[4 + 4 * m], node_count=out[5 + 4 * m], tri_base=out[6 + 4 * m], prim_count=out[7 + 4 * m],
+                       leaf_base=out[ext + 2 + 2 * m], leaf_count=out[ext + 3 + 2 * m])
                   for m in range(out[3])]
-        return dict(tlas_nodes=out[0], tlas_levels=out[1], instances=out[2], models=models)
+        return dict(tlas_nodes=out[0], tlas_levels=out[1], instances=out[2], models=models, node_format=out[ext], tlas_leaf_count=out[ext + 1])
 
     def debug_read(self, what, offset, count, dtype):
         arr = np.zeros(count, dtype=dtype)

@@ -342,8 +342,13 @@ inline bool slab(const Box& b, f3 o, f3 id, float tmin, float tbest) {
     float tx0 = (b.lo.x - o.x) * id.x, tx1 = (b.hi.x - o.x) * id.x;
     float ty0 = (b.lo.y - o.y) * id.y, ty1 = (b.hi.y - o.y) * id.y;
     float tz0 = (b.lo.z - o.z) * id.z, tz1 = (b.hi.z - o.z) * id.z;
-    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
-    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tbest));
+    // A ray that lies IN a face plane of the box (direction component 0, origin on the plane) gives a slab interval that ends at
+    // exactly 0; every axis interval is therefore widened by 1e-14 world units (|id| * 1e-14 in t), far below fp32 resolution
+    // unless the origin sits on the plane: the test is inclusive, so every triangle whose box the ray touches is tested and the
+    // closest hit does not depend on the tree (nor on how far a quantised tree rounds its boxes outward).
+    const float px = fabsf(id.x) * 1e-14f, py = fabsf(id.y) * 1e-14f, pz = fabsf(id.z) * 1e-14f;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1) - px, fminf(ty0, ty1) - py), fmaxf(fminf(tz0, tz1) - pz, tmin));
+    float tf = fminf(fminf(fmaxf(tx0, tx1) + px, fmaxf(ty0, ty1) + py), fminf(fmaxf(tz0, tz1) + pz, tbest));
     return tn * 0.9999990f - 1e-7f <= tf * 1.0000010f + 1e-7f;
 }
 

@@ -44,10 +44,12 @@ def test_config1_cornell_box_ids_and_radiance(renderer, tracer):
     assert rep["OBJEDCTID_0"] == 0.0
 
 
-@pytest.mark.parametrize("builder", ["lbvh", "sah"])
-def test_rtiow_sky_multi_bounce(monkeypatch, sky, builder):
-    """RTIOW (1939 instances, dielectric / metallic / lambertian spheres, sky): both BLAS builders."""
+@pytest.mark.parametrize("builder,node_format", [("lbvh", 8), ("sah", 8), ("sah", 4), ("lbvh", 4)])
+def test_rtiow_sky_multi_bounce(monkeypatch, sky, builder, node_format):
+    """RTIOW (1939 instances, dielectric / metallic / lambertian spheres, sky): both BLAS builders, both node formats (the quantised 8-wide
+    Node8 and the fp32 4-wide Node4, gk_bvh.cuh) - the closest hit does not depend on the tree, so every image stays bit-identical."""
     monkeypatch.setenv("GKCU_BLAS_BUILDER", builder)
+    monkeypatch.setenv("GKCU_NODE_FORMAT", str(node_format))
     r = CudaPathTracingRenderer(0)
     try:
         W, H = 480, 270
