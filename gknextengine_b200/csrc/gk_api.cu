@@ -197,7 +197,22 @@ int gkcu_scene_upload(GkcuContext* ctx, const GkcuSceneDesc* d) {
     CTX_OR_FAIL(ctx);
     if (!d || !d->vertices || !d->simple_vertices || !d->indices || !d->offsets) { set_error("gkcu_scene_upload: null array"); return 1; }
     if (d->offset_count != d->model_count * 10) { set_error("gkcu_scene_upload: offsets must hold 10 sections per model"); return 1; }
+    // validate everything before the context is touched: a rejected upload leaves the previous scene (and its BLAS) intact
+    for (uint32_t m = 0; m < d->model_count; ++m) {
+        const GkModelData& md = d->offsets[m * 10];
+        uint64_t idx = 0;
+        for (int s = 0; s < 10; ++s) idx += d->offsets[m * 10 + s].indexCount;
+        if ((uint64_t)md.indexOffset + idx > d->index_count || (uint64_t)md.vertexOffset + md.vertexCount > d->vertex_count) {
+            set_error("gkcu_scene_upload: ModelData ranges exceed the buffers");
+            return 1;
+        }
+        for (uint64_t i = 0; i < idx; ++i)
+            if (d->indices[md.indexOffset + i] >= md.vertexCount) { set_error("gkcu_scene_upload: index beyond the model's vertex count"); return 1; }
+    }
     cudaStream_t st = c.stream;
+    c.blas_built = false;  // from here on the old acceleration structures no longer describe the buffers
+    c.tlas_dirty = true;
+    c.tlas.node_count = 0;
     if (!c.vertices.reserve((size_t)d->vertex_count * sizeof(GkGPUVertex)) || !c.simple.reserve((size_t)d->vertex_count * 8) ||
         !c.indices.reserve((size_t)d->index_count * 4) || !c.offsets.reserve((size_t)d->offset_count * sizeof(GkModelData)))
         return 1;
@@ -211,18 +226,6 @@ int gkcu_scene_upload(GkcuContext* ctx, const GkcuSceneDesc* d) {
     c.offset_count = d->offset_count;
     c.model_count = d->model_count;
     c.host_offsets.assign(d->offsets, d->offsets + d->offset_count);
-    for (uint32_t m = 0; m < c.model_count; ++m) {
-        const GkModelData& md = c.host_offsets[m * 10];
-        uint64_t idx = 0;
-        for (int s = 0; s < 10; ++s) idx += c.host_offsets[m * 10 + s].indexCount;
-        if ((uint64_t)md.indexOffset + idx > d->index_count || (uint64_t)md.vertexOffset + md.vertexCount > d->vertex_count) {
-            set_error("gkcu_scene_upload: ModelData ranges exceed the buffers");
-            return 1;
-        }
-    }
-    c.blas_built = false;
-    c.tlas_dirty = true;
-    c.tlas.node_count = 0;
     return 0;
 }
 
@@ -408,7 +411,8 @@ static int frame_prologue(Context& c, const GkUniformBufferObject* ubo, const Gk
     if (!ubo || !params) { set_error("null ubo/params"); return 1; }
     if (c.rt.w == 0) { set_error("call gkcu_resize first"); return 1; }
     if (!c.blas_built) { set_error("call gkcu_scene_upload + gkcu_blas_build first"); return 1; }
-    if (params->spp_world > 1 && params->spp_rank >= params->spp_world) { set_error("spp_rank >= spp_world"); return 1; }
+    if (params->spp_rank >= std::max(1u, params->spp_world)) { set_error("spp_rank >= max(1, spp_world)"); return 1; }
+    if (params->spp_world > GKCU_MAX_PEERS) { set_error("spp_world > 8"); return 1; }
     GK_CUDA(cudaMemcpyAsync(c.ubo.p, ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, c.stream));
     return 0;
 }
@@ -472,8 +476,9 @@ static void drop_peers(Context& c) {
     for (void* p : c.ipc_opened) cudaIpcCloseMemHandle(p);
     c.ipc_opened.clear();
     memset(c.peer, 0, sizeof(c.peer));
-    c.peer_epoch = 0;
-    if (c.peer_flags.p) cudaMemset(c.peer_flags.p, 0, 32 * 8);
+    // The barrier epoch and the flag block survive: the peers keep counting, and a rank that restarted at 0 would see their old
+    // flags as "arrived" and read sums that are not written yet. (A resize frees the buffers the peers imported, so every rank of
+    // the group has to import again after any of them resized - see gkcu.h.)
 }
 
 int gkcu_peer_export(GkcuContext* ctx, uint32_t what, void* handle, void** device_ptr) {

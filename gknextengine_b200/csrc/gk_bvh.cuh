@@ -41,6 +41,9 @@ struct __align__(16) Node8 {
     uint16_t q[6][8];    // qlo_x, qhi_x, qlo_y, qhi_y, qlo_z, qhi_z
 };
 static_assert(sizeof(Node8) == 128, "Node8 must be 128 bytes (one cache line)");
+#ifndef GK_NODE_LD256
+#define GK_NODE_LD256 0  // Node4 node step: 256-bit plane loads (experiment, profiles/r02_experiments.md)
+#endif
 #ifndef GK_N8_TMIN
 #define GK_N8_TMIN 1  // Node8 stack entries carry the entry distance of their nearest member (24 bits) and are culled as a whole when popped
 #endif
@@ -85,6 +88,11 @@ GK_DEV float safe_rcp(float x) {
     return __frcp_rn(x);  // correctly rounded, == 1.0f / x
 }
 GK_DEV float sel3(int k, float3 v) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+// 256-bit read-only global load (sm_100: LDG.E.ENL2.256), p must be 32-byte aligned
+GK_DEV void ld256(const void* p, float (&v)[8]) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
 
 struct RayShear {
     int kx, ky, kz;
@@ -258,7 +266,7 @@ GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
             T.cur_inst = GK_NO_HIT;
         }
         if (T.sp == 0) { T.done = true; return; }
-        if (FMT == 8) {
+        if constexpr (FMT == 8) {
             const uint2 e = stack.e[T.sp - 1];
             if (GK_N8_TMIN && __uint_as_float(e.y & ~0xFFu) > T.best.t) { GK_STAT(T, 4, 1); --T.sp; continue; }
             const uint32_t m = e.y & 0xFFu, rest = m & (m - 1u);
@@ -266,11 +274,12 @@ GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
             else --T.sp;
             T.cur = e.x + (uint32_t)(__ffs((int)m) - 1);
             return;
+        } else {
+            const uint2 e = stack.pop(T.sp);
+            if (__uint_as_float(e.y) > T.best.t) { GK_STAT(T, 4, 1); continue; }
+            T.cur = e.x;
+            return;
         }
-        const uint2 e = stack.pop(T.sp);
-        if (__uint_as_float(e.y) > T.best.t) { GK_STAT(T, 4, 1); continue; }
-        T.cur = e.x;
-        return;
     }
 }
 
@@ -278,10 +287,30 @@ GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
 // Node4 keeps the planes as fp32 in structure-of-arrays order, so the near and far planes of an axis are two 16-byte loads
 // picked by the sign of the ray direction and every plane costs exactly one FMA. The interval is padded by a few ulps on
 // both ends (see set_space).
-template <class W, class St>
-GK_DEV void trav_node_step4(Trav& T, const W& world, const TraceScene& S, St& stack) {
+// trav_node_core4 returns false when no child is hit (the caller pops); trav_node_step4 = core + pop.
+template <class St>
+GK_DEV bool trav_node_core4(Trav& T, St& stack) {
     const uint4* np = T.nodes + (size_t)T.cur * 8;
     const uint32_t ix = T.sgn & 1u, iy = (T.sgn >> 1) & 1u, iz = T.sgn >> 2;
+#if GK_NODE_LD256
+    // One 256-bit load per axis (sm_100: LDG.E.256) brings the lower and the upper planes of the four children; the ray's sign picks
+    // which half is the near side. Four load instructions per node instead of seven: the L1 data pipe (one wavefront per lane and
+    // load, since every lane reads its own node) is as busy as the issue slots in this kernel.
+    float pnx[4], pfx[4], pny[4], pfy[4], pnz[4], pfz[4];
+    {
+        float a[8], b[8], c[8];
+        ld256(np, a);
+        ld256(np + 2, b);
+        ld256(np + 4, c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            pnx[k] = ix ? a[4 + k] : a[k]; pfx[k] = ix ? a[k] : a[4 + k];
+            pny[k] = iy ? b[4 + k] : b[k]; pfy[k] = iy ? b[k] : b[4 + k];
+            pnz[k] = iz ? c[4 + k] : c[k]; pfz[k] = iz ? c[k] : c[4 + k];
+        }
+    }
+    const uint4 n1 = __ldg(np + 6);
+#else
     const uint4 nx = __ldg(np + ix), fx = __ldg(np + (ix ^ 1u));
     const uint4 ny = __ldg(np + 2 + iy), fy = __ldg(np + 2 + (iy ^ 1u));
     const uint4 nz = __ldg(np + 4 + iz), fz = __ldg(np + 4 + (iz ^ 1u));
@@ -292,6 +321,7 @@ GK_DEV void trav_node_step4(Trav& T, const W& world, const TraceScene& S, St& st
     const float pfy[4] = {__uint_as_float(fy.x), __uint_as_float(fy.y), __uint_as_float(fy.z), __uint_as_float(fy.w)};
     const float pnz[4] = {__uint_as_float(nz.x), __uint_as_float(nz.y), __uint_as_float(nz.z), __uint_as_float(nz.w)};
     const float pfz[4] = {__uint_as_float(fz.x), __uint_as_float(fz.y), __uint_as_float(fz.z), __uint_as_float(fz.w)};
+#endif
     const float tfcap = __fmaf_rn(T.best.t, 1.000001f, 1e-7f);
     const float inf = __int_as_float(0x7f800000);
     float tn[4];
@@ -317,7 +347,7 @@ GK_DEV void trav_node_step4(Trav& T, const W& world, const TraceScene& S, St& st
     if (tn[1] < t0) { t0 = tn[1]; i0 = 1; }
     if (tn[2] < t0) { t0 = tn[2]; i0 = 2; }
     if (tn[3] < t0) { t0 = tn[3]; i0 = 3; }
-    if (!(t0 < inf)) { trav_pop<4>(T, world, S, stack); return; }
+    if (!(t0 < inf)) return false;
     if (GK_PUSH_ORDERED) {
         int i1 = -1;
         float t1 = inf;
@@ -337,6 +367,11 @@ GK_DEV void trav_node_step4(Trav& T, const W& world, const TraceScene& S, St& st
             if (c != i0 && tn[c] < inf) stack.push(T.sp, make_uint2(ref[c], __float_as_uint(tn[c])));
     }
     T.cur = ref[i0];
+    return true;
+}
+template <class W, class St>
+GK_DEV void trav_node_step4(Trav& T, const W& world, const TraceScene& S, St& stack) {
+    if (!trav_node_core4(T, stack)) trav_pop<4>(T, world, S, stack);
 }
 
 // Internal node, Node8. Per axis the plane distances are t = q * S + C with S = s * idir (exact: s is a power of two) and
@@ -410,30 +445,34 @@ GK_DEV void trav_node_step(Trav& T, const W& world, const TraceScene& S, St& sta
     else trav_node_step4(T, world, S, stack);
 }
 
-// Leaf: a TLAS leaf enters the instance's BLAS in object space (t is preserved by the affine map); a BLAS leaf tests triangles.
+// A TLAS leaf enters the instance's BLAS in object space (t is preserved by the affine map); false for an inactive instance.
+template <int FMT, class W>
+GK_DEV bool trav_enter_instance(Trav& T, const W& world, const TraceScene& S, uint32_t ii) {
+    const float4* ir = reinterpret_cast<const float4*>(S.inst + ii);
+    const float4 r0 = __ldg(ir), r1 = __ldg(ir + 1), r2 = __ldg(ir + 2);
+    const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ir) + 3);
+    GK_STAT(T, 5, 1);
+    if (!meta.z) return false;
+    const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+    const float3 rd = xform_vec(m, world.d());
+    set_space<FMT>(T, xform_point(m, world.o()), f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z)));
+    T.sh = make_shear(rd);
+    T.sp_inst = T.sp;
+    T.nodes = reinterpret_cast<const uint4*>(S.blas + meta.x);
+    if (FMT == 8) T.leaf = S.blas_leaf + meta.y;
+    else T.tris = S.tris + (size_t)meta.y * 3;
+    T.cur_inst = ii;
+    T.cur = 0;
+    return true;
+}
+
+// Leaf: a TLAS leaf enters the instance, a BLAS leaf tests its triangles.
 template <int FMT, class W, class St>
 GK_DEV void trav_leaf_step(Trav& T, const W& world, const TraceScene& S, St& stack) {
     uint32_t ref = T.cur & 0x0FFFFFFFu;
     if (FMT == 8) ref = __ldg(T.leaf + (T.cur & 0x7FFFFFFFu));  // leaf-table entry: instance index or triangle range
     if (T.cur_inst == GK_NO_HIT) {
-        const uint32_t ii = FMT == 8 ? ref : (T.cur & 0x0FFFFFFFu);
-        const float4* ir = reinterpret_cast<const float4*>(S.inst + ii);
-        const float4 r0 = __ldg(ir), r1 = __ldg(ir + 1), r2 = __ldg(ir + 2);
-        const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ir) + 3);
-        GK_STAT(T, 5, 1);
-        if (meta.z) {
-            const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-            const float3 rd = xform_vec(m, world.d());
-            set_space<FMT>(T, xform_point(m, world.o()), f3(safe_rcp(rd.x), safe_rcp(rd.y), safe_rcp(rd.z)));
-            T.sh = make_shear(rd);
-            T.sp_inst = T.sp;
-            T.nodes = reinterpret_cast<const uint4*>(S.blas + meta.x);
-            if (FMT == 8) T.leaf = S.blas_leaf + meta.y;
-            else T.tris = S.tris + (size_t)meta.y * 3;
-            T.cur_inst = ii;
-            T.cur = 0;
-            return;
-        }
+        if (trav_enter_instance<FMT>(T, world, S, FMT == 8 ? ref : (T.cur & 0x0FFFFFFFu))) return;
     } else {
         const uint32_t first = FMT == 8 ? (ref & 0x0FFFFFFFu) : (T.cur & 0x0FFFFFFFu);
         const uint32_t count = FMT == 8 ? (ref >> 28) + 1u : ((T.cur >> 28) & 7u) + 1u;

@@ -1316,7 +1316,16 @@ int refit_blas(Context& c, uint32_t model) {
     return 0;
 }
 
+static int build_tlas_impl(Context& c);
 int build_tlas(Context& c) {
+    const int r = build_tlas_impl(c);
+    if (r) {  // a failed build leaves no TLAS behind and stays pending: the next frame fails again instead of rendering an empty scene
+        c.tlas.node_count = 0;
+        c.tlas_dirty = true;
+    }
+    return r;
+}
+static int build_tlas_impl(Context& c) {
     cudaStream_t st = c.stream;
     uint32_t n = c.node_count;
     c.tlas.node_count = 0;

@@ -58,6 +58,7 @@ struct PathLanes { PathView v[4]; uint32_t n; };
 struct PathBuffers {
     DevBuf rng, pos_mat, nrm_flags, dir_cnt, ray_color, final_color, final_refl, prim_pos_mat, prim_nrm_cnt, prim_albedo;
     DevBuf ray_o, ray_d, slot_pixel[2], hit_tuv, hit_prim, counts, radiance, direct;
+    DevBuf pool_stack;  // k_trace_pool: traversal stacks, [lane][block][depth][slot]
     uint32_t* host_counts = nullptr;  // pinned, 64 words per lane
     size_t pixels = 0;
     size_t lane_cap = 0;  // queue capacity of one lane
@@ -658,6 +659,282 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- pool tracer
+// k_trace_pool: the rays of a block live in a POOL of slots in shared memory instead of in the registers of a fixed lane, and
+// every slot waits in the queue of the step kind it needs next (node walk, triangle leaf, instance entry, stack pop, refill).
+// A phase gives each warp up to 32 slots of ONE kind - full chunks first - so the step code runs with (almost) all lanes active,
+// where the lane-owned loop of k_trace executes with ~15 of 32 (ncu, profiles/). The price is the state round trip through shared
+// memory (about 20 words per step), one block barrier per phase and a traversal stack in global memory ([depth][slot] per block,
+// L1-resident like the local-memory stack it replaces). Per ray the sequence of node tests, pushes, pops and triangle tests is
+// exactly that of trace_ray, so the result is bit-identical. Node4 only.
+#ifndef GK_POOL_MINB
+#define GK_POOL_MINB 4
+#endif
+#define GK_POOL 256
+#ifndef GK_POOL_MIN_CHUNK
+#define GK_POOL_MIN_CHUNK 20  // a rest smaller than this waits for more slots of its kind
+#endif
+#ifndef GK_POOL_ROUNDS
+#define GK_POOL_ROUNDS 2      // chunks per warp and phase
+#endif
+enum { PK_FREE = 0, PK_POP = 1, PK_TRI = 2, PK_INST = 3, PK_NODE = 4, PK_COUNT = 5 };
+#define PP_SGN_SHIFT 16
+#define PP_ANY (1u << 19)
+#define PP_HAS_HIT (1u << 20)
+
+struct PoolSmem {
+    float ro[3][GK_POOL], idir[3][GK_POOL];  // current-space ray
+    float world[9][GK_POOL];                 // world-space origin, direction, reciprocal direction (WorldSmem layout)
+    float sh[3][GK_POOL];                    // watertight-test shear of the current space
+    float best_t[GK_POOL];
+    uint32_t shk[GK_POOL];                   // kx | ky << 2 | kz << 4
+    uint32_t cur[GK_POOL], nbase[GK_POOL], tbase[GK_POOL], cinst[GK_POOL], pack[GK_POOL], qslot[GK_POOL];
+    uint16_t ring[PK_COUNT][2 * GK_POOL];    // per kind: ring buffer of waiting slots; twice the pool, so that the slots appended in a phase
+                                             // (at most the pool) can never wrap onto entries dealt in the same phase and not read yet
+    uint32_t pushed[3][8];                   // slots appended per kind in phase p, p + 1, p + 2 (rotating); [7]: the ray queue ran empty
+};
+
+// traversal stack of one slot in global memory: entry d of slot s of this block at [d][s]
+struct PoolStack {
+    uint2* base;
+    GK_DEV void push(int& sp, uint2 v) { base[(size_t)sp * GK_POOL] = v; ++sp; }
+    GK_DEV uint2 pop(int& sp) { --sp; return base[(size_t)sp * GK_POOL]; }
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(128, GK_POOL_MINB) k_trace_pool(TraceScene ts, PathView V, int qi, size_t half, uint2* __restrict__ stack_mem) {
+    static_assert(FMT == 4, "the pool tracer walks Node4 trees");
+    __shared__ PoolSmem sm;
+    const uint32_t n = V.counts[qi];
+    if (blockIdx.x == 0 && threadIdx.x == 0) V.counts[qi ^ 1] = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4* ray_o = V.ray_o + (size_t)qi * half;
+    const float4* ray_d = V.ray_d + (size_t)qi * half;
+    const uint32_t* slot_pixel = V.slot_pixel[qi];
+    uint2* const my_stack = stack_mem + (size_t)blockIdx.x * GK_TRAV_STACK * GK_POOL;
+    for (int i = threadIdx.x; i < GK_POOL; i += blockDim.x) sm.ring[PK_FREE][i] = (uint16_t)i;
+    if (threadIdx.x < 24) (&sm.pushed[0][0])[threadIdx.x] = 0;
+    bool drained = false;  // uniform: read from the counter set of the previous phase
+    uint32_t head[PK_COUNT], tail[PK_COUNT];
+#pragma unroll
+    for (int k = 0; k < PK_COUNT; ++k) { head[k] = 0; tail[k] = 0; }
+    tail[PK_FREE] = GK_POOL;
+    uint32_t p_prev = 2, p_cur = 0, p_next = 1;  // counter sets: read, push, clear
+    __syncthreads();
+    for (uint32_t phase = 0;; ++phase) {
+        if (phase) {
+#pragma unroll
+            for (int k = 0; k < PK_COUNT; ++k) tail[k] += sm.pushed[p_prev][k];
+            drained = drained || sm.pushed[p_prev][7] != 0;
+        }
+        if (threadIdx.x < 8) sm.pushed[p_next][threadIdx.x] = 0;
+        if (drained && tail[PK_FREE] - head[PK_FREE] == GK_POOL) break;  // every slot is free and no ray is left
+        // ---- deal chunks of up to 32 waiting slots to the warps (every thread computes the same deal from the same counters): a kind
+        // offers its full chunks and a rest of at least GK_POOL_MIN_CHUNK slots; smaller rests keep waiting for company unless nothing
+        // else is left, then the largest one runs. Up to GK_POOL_ROUNDS chunks per warp and phase, chunk c goes to warp c % 4.
+        uint32_t avail[PK_COUNT], nch[PK_COUNT], pre[PK_COUNT + 1];
+#pragma unroll
+        for (int k = 0; k < PK_COUNT; ++k) avail[k] = tail[k] - head[k];
+        if (drained) avail[PK_FREE] = 0;
+        pre[0] = 0;
+#pragma unroll
+        for (int k = 0; k < PK_COUNT; ++k) {
+            nch[k] = (avail[k] >> 5) + ((avail[k] & 31u) >= (uint32_t)GK_POOL_MIN_CHUNK ? 1u : 0u);
+            pre[k + 1] = pre[k] + nch[k];
+        }
+        if (pre[PK_COUNT] == 0) {  // only small rests are left: run the largest
+            uint32_t best = 0;
+            int kb = -1;
+#pragma unroll
+            for (int k = 0; k < PK_COUNT; ++k)
+                if (avail[k] > best) { best = avail[k]; kb = k; }
+#pragma unroll
+            for (int k = 0; k < PK_COUNT; ++k) {
+                nch[k] = k == kb ? 1u : 0u;
+                pre[k + 1] = pre[k] + nch[k];
+            }
+        }
+        const uint32_t total = min(pre[PK_COUNT], 4u * GK_POOL_ROUNDS);
+        uint32_t begin_of[PK_COUNT];
+#pragma unroll
+        for (int k = 0; k < PK_COUNT; ++k) {
+            begin_of[k] = head[k];
+            const uint32_t dealt = min(nch[k], total > pre[k] ? total - pre[k] : 0u);
+            head[k] += min(avail[k], dealt << 5);
+        }
+      for (uint32_t round = 0; round < (uint32_t)GK_POOL_ROUNDS; ++round) {
+        const uint32_t chunk = (uint32_t)warp + 4u * round;
+        if (chunk >= total) break;  // warp-uniform
+        int my_kind = 0;
+        uint32_t my_begin = 0, my_cnt = 0;
+#pragma unroll
+        for (int k = 0; k < PK_COUNT; ++k) {
+            if (chunk >= pre[k] && chunk < pre[k + 1]) {
+                my_kind = k;
+                my_begin = begin_of[k] + ((chunk - pre[k]) << 5);
+                my_cnt = min(32u, avail[k] - ((chunk - pre[k]) << 5));
+            }
+        }
+        // ---- run one step of my_kind on my chunk
+        const bool act = (uint32_t)lane < my_cnt;
+        const uint32_t slot = act ? sm.ring[my_kind][(my_begin + lane) & (2 * GK_POOL - 1)] : 0u;
+        int next = -1;  // queue the slot goes to afterwards
+        if (my_kind == PK_FREE) {
+            // refill: one atomic per warp takes the next rays from the queue
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(V.counts + 2, my_cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + my_cnt >= n && lane == 0) sm.pushed[p_cur][7] = 1;
+            if (act) {
+                const uint32_t q = base + lane;
+                next = PK_FREE;
+                if (q < n) {
+                    const float4 o = __ldcs(ray_o + q), d = __ldcs(ray_d + q);
+                    const bool any = (__ldcs(slot_pixel + q) & 0x80000000u) != 0;
+                    Trav T;
+                    WorldSmem<GK_POOL> world;
+                    world.p = &sm.world[0][slot];
+                    trav_init<FMT>(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, any);
+                    // the miss record; a hit overwrites it
+                    __stcs(V.hit_tuv + q, f4(T.best.t, 0.0f, 0.0f, __uint_as_float(GK_NO_HIT)));
+                    __stcs(V.hit_prim + q, 0u);
+                    if (!T.done) {
+                        sm.ro[0][slot] = T.ro.x; sm.ro[1][slot] = T.ro.y; sm.ro[2][slot] = T.ro.z;
+                        sm.idir[0][slot] = T.idir.x; sm.idir[1][slot] = T.idir.y; sm.idir[2][slot] = T.idir.z;
+                        sm.best_t[slot] = T.best.t;
+                        sm.cur[slot] = 0u;
+                        sm.nbase[slot] = 0xFFFFFFFFu;
+                        sm.tbase[slot] = 0u;
+                        sm.cinst[slot] = GK_NO_HIT;
+                        sm.pack[slot] = (T.sgn << PP_SGN_SHIFT) | (any ? PP_ANY : 0u);
+                        sm.qslot[slot] = q;
+                        next = PK_NODE;
+                    }
+                }
+            }
+        } else if (my_kind == PK_NODE) {
+            if (act) {
+                Trav T;
+                const uint32_t pk = sm.pack[slot], nb = sm.nbase[slot];
+                set_space<FMT>(T, f3(sm.ro[0][slot], sm.ro[1][slot], sm.ro[2][slot]), f3(sm.idir[0][slot], sm.idir[1][slot], sm.idir[2][slot]));
+                T.tmin = GK_EPS;
+                T.best.t = sm.best_t[slot];
+                T.cur = sm.cur[slot];
+                T.cur_inst = 0;  // only feeds the statistics build
+                T.sp = (int)(pk & 0xFFu);
+                T.nodes = reinterpret_cast<const uint4*>(nb == 0xFFFFFFFFu ? ts.tlas : ts.blas + nb);
+                PoolStack stack{my_stack + slot};
+                if (trav_node_core4(T, stack)) {
+                    sm.cur[slot] = T.cur;
+                    next = !(T.cur & GK_LEAF_BIT) ? PK_NODE : (nb == 0xFFFFFFFFu ? PK_INST : PK_TRI);
+                } else {
+                    next = PK_POP;
+                }
+                sm.pack[slot] = (pk & ~0xFFu) | (uint32_t)T.sp;
+            }
+        } else if (my_kind == PK_INST || my_kind == PK_TRI || my_kind == PK_POP) {
+            if (act) {
+                Trav T;
+                uint32_t pk = sm.pack[slot];
+                WorldSmem<GK_POOL> world;
+                world.p = &sm.world[0][slot];
+                T.cur = sm.cur[slot];
+                T.cur_inst = sm.cinst[slot];
+                T.sp = (int)(pk & 0xFFu);
+                T.sp_inst = (int)((pk >> 8) & 0xFFu);
+                T.best.t = sm.best_t[slot];
+                T.done = false;
+                bool pop = true, space_changed = false;
+                if (my_kind == PK_INST) {
+                    if (trav_enter_instance<FMT>(T, world, ts, T.cur & 0x0FFFFFFFu)) {
+                        const InstanceRec* ir = ts.inst + T.cur_inst;
+                        sm.nbase[slot] = __ldg(&ir->node_base);
+                        sm.tbase[slot] = __ldg(&ir->tri_base);
+                        sm.sh[0][slot] = T.sh.Sx; sm.sh[1][slot] = T.sh.Sy; sm.sh[2][slot] = T.sh.Sz;
+                        sm.shk[slot] = (uint32_t)T.sh.kx | ((uint32_t)T.sh.ky << 2) | ((uint32_t)T.sh.kz << 4);
+                        pop = false;
+                        space_changed = true;
+                        next = PK_NODE;
+                    }
+                } else if (my_kind == PK_TRI) {
+                    const float3 ro = f3(sm.ro[0][slot], sm.ro[1][slot], sm.ro[2][slot]);
+                    RayShear sh;
+                    const uint32_t k3 = sm.shk[slot];
+                    sh.kx = (int)(k3 & 3u); sh.ky = (int)((k3 >> 2) & 3u); sh.kz = (int)((k3 >> 4) & 3u);
+                    sh.Sx = sm.sh[0][slot]; sh.Sy = sm.sh[1][slot]; sh.Sz = sm.sh[2][slot];
+                    const float4* tris = ts.tris + (size_t)sm.tbase[slot] * 3;
+                    const uint32_t q = sm.qslot[slot];
+                    const uint32_t first = T.cur & 0x0FFFFFFFu, count = ((T.cur >> 28) & 7u) + 1u;
+                    for (uint32_t i = 0; i < count; ++i) {
+                        const float4* tp = tris + (size_t)(first + i) * 3;
+                        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                        float t, b1, b2;
+                        if (!tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), ro, sh, t, b1, b2)) continue;
+                        if (!(t > GK_EPS && t < GK_PT_MAX_TRACE_DISTANCE)) continue;
+                        const uint32_t p = __float_as_uint(a.w);
+                        if (pk & PP_ANY) {  // first hit ends the query
+                            __stcs(V.hit_tuv + q, f4(t, 0.0f, 0.0f, __uint_as_float(T.cur_inst)));
+                            __stcs(V.hit_prim + q, p);
+                            T.done = true;
+                            break;
+                        }
+                        bool better = !(pk & PP_HAS_HIT) || t < T.best.t;
+                        if (!better && t == T.best.t) {  // tie: (instance, primitive) order; the record of the best hit is in global memory
+                            const uint32_t bi = __float_as_uint(__ldcg(&V.hit_tuv[q].w)), bp = __ldcg(V.hit_prim + q);
+                            better = T.cur_inst < bi || (T.cur_inst == bi && p < bp);
+                        }
+                        if (better) {
+                            T.best.t = t;
+                            pk |= PP_HAS_HIT;
+                            __stcg(V.hit_tuv + q, f4(t, b1, b2, __uint_as_float(T.cur_inst)));
+                            __stcg(V.hit_prim + q, p);
+                        }
+                    }
+                    sm.best_t[slot] = T.best.t;
+                    if (T.done) { pop = false; next = PK_FREE; }
+                }
+                if (pop) {
+                    const uint32_t inst_before = T.cur_inst;
+                    PoolStack stack{my_stack + slot};
+                    trav_pop<FMT>(T, world, ts, stack);
+                    if (T.done) next = PK_FREE;
+                    else next = !(T.cur & GK_LEAF_BIT) ? PK_NODE : (T.cur_inst == GK_NO_HIT ? PK_INST : PK_TRI);
+                    space_changed = T.cur_inst != inst_before;  // left the instance: back in world space
+                    if (space_changed) sm.nbase[slot] = 0xFFFFFFFFu;
+                    sm.cur[slot] = T.cur;
+                }
+                if (space_changed) {
+                    sm.ro[0][slot] = T.ro.x; sm.ro[1][slot] = T.ro.y; sm.ro[2][slot] = T.ro.z;
+                    sm.idir[0][slot] = T.idir.x; sm.idir[1][slot] = T.idir.y; sm.idir[2][slot] = T.idir.z;
+                    sm.cinst[slot] = T.cur_inst;
+                    pk = (pk & ~(7u << PP_SGN_SHIFT)) | (T.sgn << PP_SGN_SHIFT);
+                    if (my_kind == PK_INST) sm.cur[slot] = T.cur;
+                }
+                sm.pack[slot] = (pk & ~0xFFFFu) | (uint32_t)T.sp | ((uint32_t)T.sp_inst << 8);
+            }
+        }
+        // ---- append the slots to the queues of their next step (one shared-memory atomic per kind and warp)
+        {
+            const unsigned live = __ballot_sync(0xffffffffu, next >= 0);
+            if (next >= 0) {
+                const unsigned peers = __match_any_sync(live, next);
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&sm.pushed[p_cur][next], (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                uint32_t t0 = 0;
+#pragma unroll
+                for (int k = 0; k < PK_COUNT; ++k)
+                    if (k == next) t0 = tail[k];
+                sm.ring[next][(t0 + base + __popc(peers & ((1u << lane) - 1u))) & (2 * GK_POOL - 1)] = (uint16_t)slot;
+            }
+        }
+      }
+        const uint32_t tp = p_prev; p_prev = p_cur; p_cur = p_next; p_next = tp;
+        __syncthreads();
+    }
+}
+
 // The first version: a warp takes 32 rays, every lane runs the simple per-ray loop, the warp refills when all are done.
 __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V, int qi, size_t half) {
     const uint32_t n = V.counts[qi];
@@ -797,7 +1074,7 @@ __global__ void __launch_bounds__(256) k_resolve_strip(uint2* __restrict__ out_d
                                                        const float4* __restrict__ direct0, const uint16_t* __restrict__ moment,
                                                        const __grid_constant__ GkUniformBufferObject cam, uint32_t n, uint32_t first, uint32_t last) {
     const uint32_t pixel = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (pixel >= last) return;
+    if (pixel >= last || pixel >= n) return;
     float4 fc = __ldcs(P.rad[0] + pixel), fr = __ldcs(P.rad[0] + (size_t)n + pixel);
     for (int r = 1; r < world; ++r) {
         fc = fc + __ldcs(P.rad[r] + pixel);
@@ -921,7 +1198,8 @@ int path_resize(Context& c) {
               b.ray_color.reserve(2 * m * 16) && b.final_color.reserve(n * 16) && b.final_refl.reserve(n * 16) && b.prim_pos_mat.reserve(n * 16) &&
               b.prim_nrm_cnt.reserve(n * 16) && b.prim_albedo.reserve(n * 16) && b.ray_o.reserve(2 * m * 16) && b.ray_d.reserve(2 * m * 16) &&
               b.slot_pixel[0].reserve(m * 4) && b.slot_pixel[1].reserve(m * 4) && b.hit_tuv.reserve(m * 16) && b.hit_prim.reserve(m * 4) &&
-              b.counts.reserve(4 * 64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16);
+              b.counts.reserve(4 * 64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16) &&
+              b.pool_stack.reserve((size_t)b.lanes * c.sm_count * GK_POOL_MINB * GK_TRAV_STACK * GK_POOL * sizeof(uint2));
     if (!ok) return 1;
     // ranks other than 0 never write the direct-term plane; keep it defined for a host that resolves on such a context
     GK_CUDA(cudaMemsetAsync(b.direct.p, 0, n * 16, c.stream));
@@ -933,7 +1211,7 @@ void path_release(Context& c) {
     if (!c.path) return;
     PathBuffers& b = *c.path;
     for (DevBuf* d : {&b.rng, &b.pos_mat, &b.nrm_flags, &b.dir_cnt, &b.ray_color, &b.final_color, &b.final_refl, &b.prim_pos_mat, &b.prim_nrm_cnt,
-                      &b.prim_albedo, &b.ray_o, &b.ray_d, &b.slot_pixel[0], &b.slot_pixel[1], &b.hit_tuv, &b.hit_prim, &b.counts, &b.radiance, &b.direct})
+                      &b.prim_albedo, &b.ray_o, &b.ray_d, &b.slot_pixel[0], &b.slot_pixel[1], &b.hit_tuv, &b.hit_prim, &b.counts, &b.radiance, &b.direct, &b.pool_stack})
         d->release();
     if (b.host_counts) cudaFreeHost(b.host_counts);
     delete c.path;
@@ -1022,6 +1300,9 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                     else if (c.trace_variant == 0) {
                         if (c.node_format == 8) k_trace<0, 8><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
                         else k_trace<0, 4><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                    } else if (c.trace_variant == 6 && c.node_format == 4) {
+                        const uint32_t pb = std::min<uint32_t>((bound[l] + GK_POOL - 1) / GK_POOL, (uint32_t)c.sm_count * GK_POOL_MINB);
+                        k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * c.sm_count * GK_POOL_MINB * GK_TRAV_STACK * GK_POOL);
                     } else {
                         const uint32_t tb = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u);
                         if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
@@ -1148,6 +1429,7 @@ void* peer_local_buffer(Context& c, uint32_t what) {
 int run_resolve_strip(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {
     const int world = (int)std::max(1u, p.spp_world);
     if (world > GKCU_MAX_PEERS) { set_error("gkcu_render_resolve_strip: spp_world > 8"); return 1; }
+    if ((int)p.spp_rank >= world) { set_error("gkcu_render_resolve_strip: spp_rank >= spp_world"); return 1; }
     PeerRadiance P{};
     for (int r = 0; r < world; ++r) {
         P.rad[r] = static_cast<const float4*>(c.peer[r][GKCU_PEER_RADIANCE]);

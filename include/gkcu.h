@@ -382,7 +382,8 @@ int gkcu_render_resolve(GkcuContext* ctx, const GkUniformBufferObject* ubo, cons
  *                     device pointer (for contexts of the same process).
  *   gkcu_peer_import: registers rank `rank`'s buffer `what`; pass the handle from another process, or handle = NULL and the
  *                     raw pointer for a context of this process. Needed: RADIANCE of every rank; DIRECT, SINGLE_DIFFUSE and
- *                     SINGLE_SPECULAR of rank 0. Imports are dropped by gkcu_resize.
+ *                     SINGLE_SPECULAR of rank 0. Imports are dropped by gkcu_resize, which also frees the buffers this rank exported:
+ *                     after ANY rank of a group resized, every rank must export / import again (the barrier counters keep running).
  * If FLAGS of every rank is imported as well, gkcu_render_resolve_strip does both barriers itself on the device: each rank
  * stores a frame counter into every peer's flag block when its sums are complete / its strip has landed, and a one-warp
  * kernel polls the local block (acquire, system scope; gives up after ~2 s and reports it at gkcu_synchronize). The host then

@@ -72,6 +72,29 @@ def test_rtiow_sky_multi_bounce(monkeypatch, sky, builder, node_format):
         r.close()
 
 
+def test_pool_tracer_variant_is_bit_identical(monkeypatch, sky):
+    """GKCU_TRACE_VARIANT=6: k_trace_pool keeps the rays of a block in a shared-memory pool and runs every step kind with full warps
+    (profiles/r02_experiments.md; slower than the lane-owned k_trace, kept as a measured alternative). Same per-ray sequence of node tests,
+    pushes and pops, so every image must stay bit-identical to the oracle."""
+    monkeypatch.setenv("GKCU_TRACE_VARIANT", "6")
+    r = CudaPathTracingRenderer(0)
+    try:
+        W, H = 640, 360
+        scene = host.Scene("RTIO.proc", samples=4, bounces=8, taa=True, denoiser=True)
+        scene.env(True, True)
+        scene.update_nodes()
+        osc, ofr = setup_pair(r, scene, W, H, sky)
+        ubo = scene.ubo(W, H, 1)
+        r.Render(ubo, params())
+        r.BeforeNextFrame()
+        ofr.render(osc, ubo, params())
+        check_frame(r, ofr)
+        gc, oc = r.counters(), ofr.counters()
+        assert gc["wavefront_iterations"] > 0 and (gc["closest_hit_rays"], gc["any_hit_rays"]) == (oc["closest"], oc["any"]) and oc["any"] > 0
+    finally:
+        r.close()
+
+
 @pytest.mark.parametrize("lanes", [2, 3])
 def test_multi_lane_wavefront_is_bit_identical(monkeypatch, sky, lanes):
     """GKCU_LANES deals the frame's tiles to independent wavefronts on their own streams (and GKCU_TLAS_FUSED_MAX=0 takes the
