@@ -27,6 +27,11 @@ def lib():
         L.gkhost_scene_desc.argtypes = [C.c_void_p, C.POINTER(GkcuSceneDesc)]
         L.gkhost_scene_nodes.restype = C.POINTER(GkNodeProxy)
         L.gkhost_scene_nodes.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        for fn in ("gkhost_scene_provoke_indices", "gkhost_scene_reorders"):
+            getattr(L, fn).restype = C.POINTER(C.c_uint32)
+            getattr(L, fn).argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.gkhost_scene_model_indices.restype = C.POINTER(C.c_uint32)
+        L.gkhost_scene_model_indices.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.gkhost_scene_materials.restype = C.POINTER(GkMaterial)
         L.gkhost_scene_materials.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
         L.gkhost_scene_lights.restype = C.POINTER(GkLightObject)
@@ -87,6 +92,21 @@ class Scene:
         n = C.c_uint32()
         p = lib().gkhost_scene_nodes(self._h, C.byref(n))
         return p, n.value
+
+    def raster_buffers(self):
+        """(provoking index buffer, GPUScene.Reorders) of Scene::RebuildMeshBuffer as numpy arrays (Scene.cpp:224-250)."""
+        n = C.c_uint32()
+        p = lib().gkhost_scene_provoke_indices(self._h, C.byref(n))
+        provoke = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+        p = lib().gkhost_scene_reorders(self._h, C.byref(n))
+        reorders = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+        return provoke, reorders
+
+    def model_indices(self, model):
+        """The authored (pre-rotation) model-local index buffer of one model."""
+        n = C.c_uint32()
+        p = lib().gkhost_scene_model_indices(self._h, model, C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
 
     def materials(self):
         n = C.c_uint32()

@@ -25,6 +25,29 @@ void gkhost_scene_desc(void* h, GkcuSceneDesc* out) {
     out->offset_count = (uint32_t)s->offsets.size();
     out->model_count = (uint32_t)s->models.size();
 }
+// The raster-side buffers of Scene::RebuildMeshBuffer (Scene.cpp:224-250): the provoking index buffer and GPUScene.Reorders, plus the
+// authored (pre-rotation) model-local indices of model `model` for checks.
+const uint32_t* gkhost_scene_provoke_indices(void* h, uint32_t* count) {
+    auto* s = static_cast<gk::Scene*>(h);
+    *count = (uint32_t)s->provoke_indices.size();
+    return s->provoke_indices.data();
+}
+const uint32_t* gkhost_scene_reorders(void* h, uint32_t* count) {
+    auto* s = static_cast<gk::Scene*>(h);
+    *count = (uint32_t)s->reorders.size();
+    return s->reorders.data();
+}
+const uint32_t* gkhost_scene_model_indices(void* h, uint32_t model, uint32_t* count) {
+    auto* s = static_cast<gk::Scene*>(h);
+    if (model >= s->models.size()) { *count = 0; return nullptr; }
+    *count = (uint32_t)s->models[model].indices.size();
+    return s->models[model].indices.data();
+}
+
+uint32_t gkhost_provoking_index_buffer(uint32_t* destination, uint32_t* reorder, const uint32_t* indices, uint32_t index_count, uint32_t vertex_count) {
+    return (uint32_t)gk::GenerateProvokingIndexBuffer(destination, reorder, indices, index_count, vertex_count);
+}
+
 const GkNodeProxy* gkhost_scene_nodes(void* h, uint32_t* count) {
     auto* s = static_cast<gk::Scene*>(h);
     *count = (uint32_t)s->node_proxies.size();

@@ -380,8 +380,50 @@ static GkGPUVertex MakeVertex(const Vertex& v) {
     return g;
 }
 
+// meshopt_generateProvokingIndexBuffer (meshoptimizer >= 0.22, src/indexgenerator.cpp; a vcpkg dependency of the reference that is not
+// in the mount, called at Scene.cpp:230), restated from the published algorithm: every triangle is rotated so that its first
+// ("provoking") vertex is one no earlier triangle provoked - among the unseen corners the one of least remaining valence - and gets a
+// fresh slot in `reorder`; the other two corners are remapped to the slot of the vertex they reference (cloned when that vertex never
+// provoked). destination[] indexes reorder[], reorder[] holds original vertex ids. Returns the number of reorder entries.
+size_t GenerateProvokingIndexBuffer(uint32_t* destination, uint32_t* reorder, const uint32_t* indices, size_t index_count, size_t vertex_count) {
+    std::vector<uint32_t> remap(vertex_count, ~0u);
+    std::vector<uint8_t> valence(vertex_count, 0);  // 8-bit counters like the original: an overflow only perturbs the heuristic, and identically
+    for (size_t i = 0; i < index_count; ++i) valence[indices[i]]++;
+    uint32_t reorder_offset = 0;
+    for (size_t i = 0; i < index_count; i += 3) {
+        uint32_t a = indices[i + 0], b = indices[i + 1], c = indices[i + 2];
+        const uint32_t va = remap[a] == ~0u ? valence[a] : ~0u;
+        const uint32_t vb = remap[b] == ~0u ? valence[b] : ~0u;
+        const uint32_t vc = remap[c] == ~0u ? valence[c] : ~0u;
+        if (vb != ~0u && vb <= va && vb <= vc) {  // abc -> bca
+            const uint32_t t = a;
+            a = b, b = c, c = t;
+        } else if (vc != ~0u && vc <= va && vc <= vb) {  // abc -> cab
+            const uint32_t t = c;
+            c = b, b = a, a = t;
+        }
+        const uint32_t newidx = reorder_offset;
+        if (remap[a] == ~0u) remap[a] = newidx;
+        reorder[reorder_offset++] = a;
+        destination[i + 0] = newidx;
+        destination[i + 1] = b;
+        destination[i + 2] = c;
+        valence[a]--; valence[b]--; valence[c]--;
+    }
+    int step = 1;
+    for (size_t i = 1; i < index_count; i += step, step ^= 3) {  // the two non-provoking corners of every triangle
+        const uint32_t index = destination[i];
+        if (remap[index] == ~0u) {
+            remap[index] = reorder_offset;
+            reorder[reorder_offset++] = index;
+        }
+        destination[i] = remap[index];
+    }
+    return reorder_offset;
+}
+
 void Scene::RebuildMeshBuffer() {
-    gpu_vertices.clear(); simple_vertices.clear(); prim_indices.clear(); offsets.clear();
+    gpu_vertices.clear(); simple_vertices.clear(); prim_indices.clear(); offsets.clear(); provoke_indices.clear(); reorders.clear();
     for (auto& model : models) {
         const uint32_t vertexOffset = (uint32_t)gpu_vertices.size();
         for (auto& v : model.vertices) {
@@ -391,27 +433,34 @@ void Scene::RebuildMeshBuffer() {
             simple_vertices.push_back(to_float16(v.Position.z));
             simple_vertices.push_back(to_float16(v.Position.x));
         }
-        // <= 65535-triangle sections, 10 ModelData slots per model (Scene.cpp:204-256). The meshopt provoking-vertex
-        // rotation (Scene.cpp:224-236) only rotates vertex order inside a triangle and is not reproduced
-        // (meshoptimizer is an external dependency; oracle and CUDA share this index buffer).
+        // <= 65535-triangle sections, 10 ModelData slots per model (Scene.cpp:204-256). Every section goes through the provoking-vertex
+        // index generator (Scene.cpp:224-250): `provoke_indices` (GPUScene's raster index buffer) indexes `reorders` (absolute vertex
+        // ids), and `prim_indices` = reorder[provoke[i]] are the model-local vertex ids in the ROTATED corner order - the buffer the
+        // shaders call Indices and the BLAS is built from.
         const uint32_t maxIndicesPerSlice = 65535 * 3;
         uint32_t total = (uint32_t)model.indices.size();
         uint32_t slices = (total + maxIndicesPerSlice - 1) / maxIndicesPerSlice;
         uint32_t process = std::min<uint32_t>(slices, 10);
-        const uint32_t modelIndexOffset = (uint32_t)prim_indices.size();
-        auto md = [&](uint32_t indexOffset, uint32_t count) {
+        const uint32_t modelIndexOffset = (uint32_t)prim_indices.size(), modelReorderOffset = (uint32_t)reorders.size();
+        auto md = [&](uint32_t indexOffset, uint32_t count, uint32_t reorderOffset) {
             GkModelData d{};
             d.indexOffset = indexOffset; d.indexCount = count; d.vertexOffset = vertexOffset; d.vertexCount = (uint32_t)model.vertices.size();
             d.localAabbMin = {model.aabb_min.x, model.aabb_min.y, model.aabb_min.z, 1};
             d.localAabbMax = {model.aabb_max.x, model.aabb_max.y, model.aabb_max.z, 1};
+            d.reorderOffset = reorderOffset;
             return d;
         };
         for (uint32_t sl = 0; sl < process; ++sl) {
-            uint32_t begin = sl * maxIndicesPerSlice, end = std::min(begin + maxIndicesPerSlice, total);
-            offsets.push_back(md((uint32_t)prim_indices.size(), end - begin));
-            prim_indices.insert(prim_indices.end(), model.indices.begin() + begin, model.indices.begin() + end);
+            const uint32_t begin = sl * maxIndicesPerSlice, end = std::min(begin + maxIndicesPerSlice, total), n = end - begin;
+            offsets.push_back(md((uint32_t)prim_indices.size(), n, (uint32_t)reorders.size()));
+            std::vector<uint32_t> provoke(n), reorder(model.vertices.size() + n / 3);
+            if (n > 0) reorder.resize(GenerateProvokingIndexBuffer(provoke.data(), reorder.data(), model.indices.data() + begin, n, model.vertices.size()));
+            else reorder.clear();
+            for (uint32_t i = 0; i < n; ++i) prim_indices.push_back(reorder[provoke[i]]);
+            provoke_indices.insert(provoke_indices.end(), provoke.begin(), provoke.end());
+            for (uint32_t r : reorder) reorders.push_back(r + vertexOffset);  // "reorder is absolute vertex index"
         }
-        for (uint32_t sl = process; sl < 10; ++sl) offsets.push_back(md(modelIndexOffset, 0));
+        for (uint32_t sl = process; sl < 10; ++sl) offsets.push_back(md(modelIndexOffset, 0, modelReorderOffset));
         model.section_count = std::max<uint32_t>(process, 1);
     }
 }

@@ -110,7 +110,9 @@ public:
     // RebuildMeshBuffer outputs
     std::vector<GkGPUVertex> gpu_vertices;
     std::vector<uint16_t> simple_vertices;  // half4 per vertex
-    std::vector<uint32_t> prim_indices;     // "PrimAddress" == GPUScene.Indices
+    std::vector<uint32_t> prim_indices;     // "PrimAddress" == GPUScene.Indices: model-local vertex ids, corners in provoking order
+    std::vector<uint32_t> provoke_indices;  // the raster index buffer (indexes reorders through ModelData.reorderOffset), Scene.cpp:247
+    std::vector<uint32_t> reorders;         // GPUScene.Reorders: absolute vertex ids, Scene.cpp:240-248
     std::vector<GkModelData> offsets;
     // UpdateNodes output
     std::vector<GkNodeProxy> node_proxies;
@@ -136,5 +138,8 @@ GkSphericalHarmonics ProjectHdrToSh(const float* rgba, int width, int height);
 // Procedural stand-in for the sky HDR (assets/textures/river_road_2.hdr is data that cannot travel with this
 // repo): a deterministic analytic equirect RGBA32F image, rows top (+Y) to bottom.
 void MakeProceduralSky(uint32_t width, uint32_t height, std::vector<float>& rgba);
+
+// meshopt_generateProvokingIndexBuffer restated (Scene.cpp:230), see gk_scene.cpp
+size_t GenerateProvokingIndexBuffer(uint32_t* destination, uint32_t* reorder, const uint32_t* indices, size_t index_count, size_t vertex_count);
 
 }  // namespace gk

@@ -130,3 +130,54 @@ def test_invisible_nodes_keep_their_proxy_with_the_visible_word_cleared():
     scene.update_nodes()
     p, _ = scene.nodes()
     assert p[1].visible == 1
+
+
+def test_provoking_vertex_index_buffers():
+    """Scene::RebuildMeshBuffer passes every section through meshopt_generateProvokingIndexBuffer (Scene.cpp:224-250; meshoptimizer is not in
+    the mount, the published algorithm is restated in host/gk_scene.cpp). Properties of the three buffers it yields: every triangle of
+    GPUScene.Indices is a ROTATION of the authored triangle; Reorders[provoke[i]] is that same vertex; the provoking (first) index of every
+    triangle is unique in its section, which is what lets a flat-interpolated vertex attribute carry a per-triangle value."""
+    for name in ("CornellBox.proc", "RTIO.proc", "LegoBricks.synth:50"):
+        s = host.Scene(name)
+        d = s.desc()
+        prim = np.ctypeslib.as_array(d.indices, shape=(d.index_count,))
+        provoke, reorders = s.raster_buffers()
+        assert len(provoke) == len(prim)
+        for m in range(d.model_count):
+            off = [d.offsets[m * 10 + k] for k in range(10)]
+            authored = s.model_indices(m)
+            done = 0
+            for o in off:
+                if o.indexCount == 0:
+                    continue
+                tri = prim[o.indexOffset:o.indexOffset + o.indexCount].reshape(-1, 3)
+                src = authored[done:done + o.indexCount].reshape(-1, 3)
+                done += o.indexCount
+                rot = [(tri == np.roll(src, -k, axis=1)).all(axis=1) for k in range(3)]
+                assert (rot[0] | rot[1] | rot[2]).all(), "a triangle is not a rotation of the authored one"
+                pv = provoke[o.indexOffset:o.indexOffset + o.indexCount]
+                assert (reorders[o.reorderOffset + pv] - o.vertexOffset == prim[o.indexOffset:o.indexOffset + o.indexCount]).all()
+                first = pv.reshape(-1, 3)[:, 0]
+                assert len(np.unique(first)) == len(first), "provoking vertices must be unique per section"
+                assert pv.max() < len(reorders) - o.reorderOffset and len(reorders) - o.reorderOffset <= o.vertexCount + o.indexCount // 3 + (len(reorders) - o.reorderOffset)
+            assert done == len(authored)
+    # known answer, worked by hand from the algorithm: two triangles sharing an edge, 4 vertices, valence = [1, 2, 2, 1].
+    #   tri (0,1,2): all corners unseen, a = 0 has the least valence -> stays, slot 0 = vertex 0; valence -> [0, 1, 1, 1]
+    #   tri (2,1,3): all corners unseen with valence 1 each; the tie goes to b (the "bca" test comes first) -> (1,3,2), slot 1 = vertex 1
+    #   second pass over the non-provoking corners: vertex 1 already has slot 1; vertex 2 -> slot 2; vertex 3 -> slot 3
+    #   => provoke = [0,1,2, 1,3,2], reorder = [0,1,2,3]
+    import ctypes as C
+    L = host.lib()
+    L.gkhost_provoking_index_buffer.restype = C.c_uint32
+    L.gkhost_provoking_index_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    idx = np.array([0, 1, 2, 2, 1, 3], np.uint32)
+    dst, reo = np.zeros(6, np.uint32), np.zeros(4 + 2, np.uint32)
+    n = L.gkhost_provoking_index_buffer(dst.ctypes.data, reo.ctypes.data, idx.ctypes.data, 6, 4)
+    assert n == 4 and dst.tolist() == [0, 1, 2, 1, 3, 2] and reo[:4].tolist() == [0, 1, 2, 3]
+    # a fan around vertex 0: the shared vertex can provoke only once, the later triangles rotate to a fresh corner
+    idx = np.array([0, 1, 2, 0, 2, 3, 0, 3, 4], np.uint32)
+    dst, reo = np.zeros(9, np.uint32), np.zeros(5 + 3, np.uint32)
+    n = L.gkhost_provoking_index_buffer(dst.ctypes.data, reo.ctypes.data, idx.ctypes.data, 9, 5)
+    tri = reo[dst].reshape(3, 3)
+    assert n == 5 and len(set(dst.reshape(3, 3)[:, 0].tolist())) == 3
+    assert tri.tolist() == [[1, 2, 0], [2, 3, 0], [3, 4, 0]]  # each time b is the unseen corner of least remaining valence (ties go to b)
