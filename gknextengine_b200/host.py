@@ -50,6 +50,8 @@ def lib():
         L.gkhost_scene_perturb_model.restype = C.c_uint32
         L.gkhost_scene_perturb_model.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.gkhost_make_sky.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+        L.gkhost_last_error.restype = C.c_char_p
+        L.gkhost_load_hdr.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.gkhost_to_float16.restype = C.c_uint16
         L.gkhost_to_float16.argtypes = [C.c_float]
         L.gkhost_mat4_inverse.argtypes = [C.c_void_p, C.c_void_p]
@@ -58,13 +60,14 @@ def lib():
 
 
 class Scene:
-    """SceneList::LoadScene + Scene::RebuildMeshBuffer: 'CornellBox.proc', 'RTIO.proc', 'LegoBricks.synth[:N]'."""
+    """SceneList::LoadScene + Scene::RebuildMeshBuffer: 'CornellBox.proc', 'RTIO.proc', 'LegoBricks.synth[:N]', or a .glb file (a path, or a
+    name looked up in $GKCU_ASSET_DIR and the reference's assets/models; FSceneLoader::LoadGLTFScene's mapping rules, host/gk_gltf.cpp)."""
 
     def __init__(self, name, samples=8, bounces=5, max_bounces=10, taa=True, temporal_frames=16, denoiser=False, hdr=False,
                  fast_gather=False):
         self._h = lib().gkhost_scene_create(name.encode())
         if not self._h:
-            raise ValueError(f"unknown scene {name!r}")
+            raise ValueError(f"cannot load scene {name!r}: {lib().gkhost_last_error().decode(errors='replace')}")
         self.name = name
         self.settings(samples, bounces, max_bounces, taa, temporal_frames, denoiser, hdr, fast_gather)
 
@@ -159,6 +162,17 @@ def make_sky(width=1024, height=512):
     """Procedural stand-in for assets/textures/river_road_2.hdr (sky id 0, Engine.cpp:855): RGBA32F equirect."""
     out = np.zeros((height, width, 4), dtype=np.float32)
     lib().gkhost_make_sky(width, height, out.ctypes.data)
+    return out
+
+
+def load_hdr(path):
+    """A Radiance .hdr equirect picture as (H, W, 4) float32, rows top to bottom - what stbi_loadf hands to the reference's texture pool
+    (src/Assets/Texture.cpp:390-432) and what gkcu_set_sky takes."""
+    w, h = C.c_uint32(), C.c_uint32()
+    if lib().gkhost_load_hdr(path.encode(), None, C.byref(w), C.byref(h)):
+        raise ValueError(f"{path}: {lib().gkhost_last_error().decode(errors='replace')}")
+    out = np.zeros((h.value, w.value, 4), dtype=np.float32)
+    lib().gkhost_load_hdr(path.encode(), out.ctypes.data, C.byref(w), C.byref(h))
     return out
 
 

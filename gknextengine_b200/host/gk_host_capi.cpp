@@ -5,11 +5,19 @@
 
 #include "gk_scene.hpp"
 
+static thread_local std::string g_host_error;
+
 extern "C" {
+
+const char* gkhost_last_error() { return g_host_error.c_str(); }
 
 void* gkhost_scene_create(const char* name) {
     auto* s = new gk::Scene();
-    if (!s->Load(name)) { delete s; return nullptr; }
+    if (!s->Load(name)) {
+        g_host_error = s->last_error.empty() ? std::string("unknown scene ") + name : s->last_error;
+        delete s;
+        return nullptr;
+    }
     return s;
 }
 void gkhost_scene_destroy(void* h) { delete static_cast<gk::Scene*>(h); }
@@ -42,6 +50,17 @@ const uint32_t* gkhost_scene_model_indices(void* h, uint32_t model, uint32_t* co
     if (model >= s->models.size()) { *count = 0; return nullptr; }
     *count = (uint32_t)s->models[model].indices.size();
     return s->models[model].indices.data();
+}
+
+// Radiance .hdr -> RGBA32F. First call with rgba = NULL for the size; returns 0 on success, the message through gkhost_last_error().
+int gkhost_load_hdr(const char* path, float* rgba, uint32_t* width, uint32_t* height) {
+    std::vector<float> px;
+    uint32_t w = 0, h = 0;
+    if (!gk::LoadHdrImage(path, px, w, h, g_host_error)) return 1;
+    *width = w;
+    *height = h;
+    if (rgba) std::memcpy(rgba, px.data(), px.size() * sizeof(float));
+    return 0;
 }
 
 uint32_t gkhost_provoking_index_buffer(uint32_t* destination, uint32_t* reorder, const uint32_t* indices, uint32_t index_count, uint32_t vertex_count) {
@@ -115,7 +134,8 @@ void gkhost_scene_counts(void* h, uint32_t* nodes, uint32_t* models, uint32_t* m
     *models = (uint32_t)s->models.size();
     *materials = (uint32_t)s->materials.size();
     uint64_t t = 0;
-    for (auto& n : s->nodes) t += s->models[n.modelId].indices.size() / 3;
+    for (auto& n : s->nodes)
+        if (n.modelId < s->models.size()) t += s->models[n.modelId].indices.size() / 3;  // camera / group nodes carry no model
     *instanced_triangles = t;
 }
 // Node::SetVisible (Node.h:41). The next UpdateNodes keeps the node's proxies and clears their `visible` word (Scene.cpp:456-476).

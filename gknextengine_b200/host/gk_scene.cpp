@@ -362,6 +362,14 @@ bool Scene::Load(const std::string& name) {
         auto pos = name.find(':');
         if (pos != std::string::npos) count = (uint32_t)std::stoul(name.substr(pos + 1));
         LoadLegoSynth(*this, count);
+    } else if (name.size() > 4 && name.compare(name.size() - 4, 4, ".glb") == 0) {
+        // SceneList::LoadScene -> FSceneLoader::LoadGLTFScene (SceneList.cpp:264-291): a path, or a file name looked up in
+        // $GKCU_ASSET_DIR and in the reference's assets/models when that tree is mounted
+        std::string err, path = name;
+        auto exists = [](const std::string& p) { FILE* f = std::fopen(p.c_str(), "rb"); if (f) std::fclose(f); return f != nullptr; };
+        if (!exists(path) && std::getenv("GKCU_ASSET_DIR")) path = std::string(std::getenv("GKCU_ASSET_DIR")) + "/" + name;
+        if (!exists(path)) path = "/root/reference/assets/models/" + name;
+        if (!LoadGlbScene(*this, path, err)) { last_error = err; return false; }
     } else return false;
     RebuildMeshBuffer();
     UpdateNodes();

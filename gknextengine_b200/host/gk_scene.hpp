@@ -119,6 +119,7 @@ public:
     // proxies that differ from the previous UpdateNodes() (a renderer may upload only these); all_proxies_changed: the array was resized
     std::vector<uint32_t> changed_proxies;
     bool all_proxies_changed = true;
+    std::string last_error;  // why Load() failed
 
 private:
     bool has_prev_ubo_ = false;
@@ -138,6 +139,11 @@ GkSphericalHarmonics ProjectHdrToSh(const float* rgba, int width, int height);
 // Procedural stand-in for the sky HDR (assets/textures/river_road_2.hdr is data that cannot travel with this
 // repo): a deterministic analytic equirect RGBA32F image, rows top (+Y) to bottom.
 void MakeProceduralSky(uint32_t width, uint32_t height, std::vector<float>& rgba);
+
+// gk_gltf.cpp: FSceneLoader::LoadGLTFScene for .glb files (appends models / materials / nodes, sets camera and environment) and the
+// Radiance .hdr reader behind the sky textures (stbi_loadf at src/Assets/Texture.cpp:390-432): RGBA32F, rows top to bottom
+bool LoadGlbScene(Scene& s, const std::string& path, std::string& error);
+bool LoadHdrImage(const std::string& path, std::vector<float>& rgba, uint32_t& width, uint32_t& height, std::string& error);
 
 // meshopt_generateProvokingIndexBuffer restated (Scene.cpp:230), see gk_scene.cpp
 size_t GenerateProvokingIndexBuffer(uint32_t* destination, uint32_t* reorder, const uint32_t* indices, size_t index_count, size_t vertex_count);
