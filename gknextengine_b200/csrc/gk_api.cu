@@ -133,6 +133,8 @@ int gkcu_destroy(GkcuContext* ctx) {
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
     drop_peers(c);
+    gkcu_unbind_external_image(ctx, GK_RT_DENOISED);
+    gkcu_bind_external_semaphore(ctx, GKCU_EXT_OPAQUE_FD, -1);
     path_release(c);
     free_targets(c.rt);
     for (auto& t : c.textures)
@@ -172,6 +174,7 @@ int gkcu_resize(GkcuContext* ctx, uint32_t width, uint32_t height) {
     if (c.copy_stream) GK_CUDA(cudaStreamSynchronize(c.copy_stream));
     c.copy_pending = false;
     drop_peers(c);
+    gkcu_unbind_external_image(ctx, GK_RT_DENOISED);  // the bound image had the old extent
     RenderTargets& t = c.rt;
     free_targets(t);
     size_t n = (size_t)width * height;
@@ -417,6 +420,15 @@ static int frame_prologue(Context& c, const GkUniformBufferObject* ubo, const Gk
     return 0;
 }
 
+// zero-copy present: tell the consumer of the bound external image that RT_DENOISED is complete
+static int signal_present(Context& c) {
+    if (!c.ext_sem) return 0;
+    cudaExternalSemaphoreSignalParams sp{};
+    sp.params.fence.value = ++c.ext_sem_value;  // ignored by binary semaphores (VK_SEMAPHORE_TYPE_BINARY)
+    GK_CUDA(cudaSignalExternalSemaphoresAsync(&c.ext_sem, &sp, 1, c.stream));
+    return 0;
+}
+
 static void end_frame_swaps(Context& c) {
     // copy pass (PathTracingRenderer.cpp:160-182) + object-id copy (VulkanBaseRenderer.cpp:1136-1152) as pointer swaps:
     // next frame's PREV_* / OBJECTID_1 are this frame's ACCUM_* / OBJECTID_0.
@@ -439,6 +451,7 @@ int gkcu_render_frame(GkcuContext* ctx, const GkUniformBufferObject* ubo, const 
         cudaEventRecord(c.ev[3], st);
         if (run_denoise(c, *ubo)) return 1;
         cudaEventRecord(c.ev[4], st);
+        if (signal_present(c)) return 1;
         end_frame_swaps(c);
     } else {
         cudaEventRecord(c.ev[3], st);
@@ -466,6 +479,7 @@ int gkcu_render_resolve(GkcuContext* ctx, const GkUniformBufferObject* ubo, cons
     cudaEventRecord(c.ev[3], st);
     if (run_denoise(c, *ubo)) return 1;
     cudaEventRecord(c.ev[4], st);
+    if (signal_present(c)) return 1;
     end_frame_swaps(c);
     cudaEventRecord(c.ev[5], st);
     c.counters.kernel_launches += c.launches - launches0;
@@ -553,7 +567,7 @@ int gkcu_readback(GkcuContext* ctx, uint32_t rt_index, void* dst, size_t dst_byt
         case GK_RT_SINGLE_SPECULAR: src = t.single_specular; bytes = n * 8; break;
         case GK_RT_ALBEDO: src = t.albedo; bytes = n * 8; break;
         case GK_RT_NORMAL: src = t.normal; bytes = n * 8; break;
-        case GK_RT_DENOISED: src = t.denoised; bytes = n * 8; break;
+        case GK_RT_DENOISED: src = t.denoised_out(); bytes = n * 8; break;
         case GK_RT_MOTIONVECTOR: src = t.motion; bytes = n * 8; break;
         case GK_RT_PREV_DEPTHBUFFER: src = t.prev_depth; bytes = n * 4; break;
         case GK_RT_MOTIONMOMENT: src = t.moment; bytes = n * 2; break;
@@ -579,7 +593,7 @@ int gkcu_readback_denoised_async(GkcuContext* ctx, void* dst, size_t dst_bytes) 
     }
     GK_CUDA(cudaEventRecord(c.copy_ready, c.stream));           // the frame that produced the image
     GK_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_ready, 0));
-    GK_CUDA(cudaMemcpyAsync(dst, t.denoised, bytes, cudaMemcpyDeviceToHost, c.copy_stream));
+    GK_CUDA(cudaMemcpyAsync(dst, t.denoised_out(), bytes, cudaMemcpyDeviceToHost, c.copy_stream));
     GK_CUDA(cudaEventRecord(c.copy_done, c.copy_stream));       // run_denoise waits for this before it overwrites the image
     c.copy_pending = true;
     return 0;
@@ -633,6 +647,7 @@ int gkcu_run_post(GkcuContext* ctx, const GkUniformBufferObject* ubo, const Gkcu
     cudaEventRecord(c.ev[3], c.stream);
     if (run_denoise(c, *ubo)) return 1;
     cudaEventRecord(c.ev[4], c.stream);
+    if (signal_present(c)) return 1;
     end_frame_swaps(c);
     cudaEventRecord(c.ev[5], c.stream);
     return 0;
@@ -741,3 +756,103 @@ int gkcu_trace_rays(GkcuContext* ctx, const GkcuRay* rays, uint32_t count, GkcuH
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------- zero-copy present (external memory / semaphore)
+namespace {
+// driver entry points of the virtual-memory API, fetched like cuTensorMapEncodeTiled (the library links cudart only)
+template <class Fn>
+Fn driver_fn(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return reinterpret_cast<Fn>(p);
+}
+int unbind_external(Context& c) {
+    cudaStreamSynchronize(c.stream);
+    if (c.copy_stream) cudaStreamSynchronize(c.copy_stream);
+    c.rt.denoised_ext = nullptr;
+    if (c.ext_mem) { cudaDestroyExternalMemory(c.ext_mem); c.ext_mem = nullptr; }
+    if (c.ext_vmm_va) {
+        typedef int (*UnmapFn)(unsigned long long, size_t);
+        typedef int (*FreeFn)(unsigned long long, size_t);
+        typedef int (*ReleaseFn)(unsigned long long);
+        auto unmap = driver_fn<UnmapFn>("cuMemUnmap");
+        auto afree = driver_fn<FreeFn>("cuMemAddressFree");
+        auto release = driver_fn<ReleaseFn>("cuMemRelease");
+        if (unmap) unmap(c.ext_vmm_va, c.ext_vmm_size);
+        if (afree) afree(c.ext_vmm_va, c.ext_vmm_size);
+        if (release) release(c.ext_vmm_handle);
+        c.ext_vmm_va = c.ext_vmm_handle = 0;
+        c.ext_vmm_size = 0;
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int gkcu_unbind_external_image(GkcuContext* ctx, uint32_t rt_index) {
+    CTX_OR_FAIL(ctx);
+    if (rt_index != GK_RT_DENOISED) { set_error("gkcu_unbind_external_image: only RT_DENOISED can be bound"); return 1; }
+    return unbind_external(c);
+}
+
+extern "C" int gkcu_bind_external_image(GkcuContext* ctx, uint32_t rt_index, uint32_t handle_type, int fd, size_t size_bytes, size_t offset_bytes,
+                                        uint32_t row_pitch_bytes) {
+    CTX_OR_FAIL(ctx);
+    if (rt_index != GK_RT_DENOISED) { set_error("gkcu_bind_external_image: only RT_DENOISED (the image the engine presents) can be bound"); return 1; }
+    if (c.rt.w == 0) { set_error("gkcu_bind_external_image: call gkcu_resize first"); return 1; }
+    const size_t need = (size_t)c.rt.w * c.rt.h * 8;
+    if (row_pitch_bytes != 0 && row_pitch_bytes != c.rt.w * 8) { set_error("gkcu_bind_external_image: only tightly packed linear images (row pitch = width * 8) are supported"); return 1; }
+    if (fd < 0 || offset_bytes % 16 != 0 || offset_bytes + need > size_bytes) { set_error("gkcu_bind_external_image: bad descriptor, unaligned offset or allocation too small for the image"); return 1; }
+    unbind_external(c);
+    if (handle_type == GKCU_EXT_OPAQUE_FD) {
+        cudaExternalMemoryHandleDesc hd{};
+        hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+        hd.handle.fd = fd;  // ownership passes to CUDA on success (like vkGetMemoryFdKHR's contract on the importing side)
+        hd.size = size_bytes;
+        GK_CUDA(cudaImportExternalMemory(&c.ext_mem, &hd));
+        cudaExternalMemoryBufferDesc bd{};
+        bd.offset = offset_bytes;
+        bd.size = need;
+        void* p = nullptr;
+        if (!check(cudaExternalMemoryGetMappedBuffer(&p, c.ext_mem, &bd), "cudaExternalMemoryGetMappedBuffer")) { unbind_external(c); return 1; }
+        c.rt.denoised_ext = static_cast<uint2*>(p);
+    } else if (handle_type == GKCU_EXT_CUDA_VMM_FD) {
+        struct AccessDesc { int loc_type; int loc_id; int flags; };  // CUmemAccessDesc {CUmemLocation{type, id}, flags}
+        typedef int (*ImportFn)(unsigned long long*, void*, int);
+        typedef int (*ReserveFn)(unsigned long long*, size_t, size_t, unsigned long long, unsigned long long);
+        typedef int (*MapFn)(unsigned long long, size_t, size_t, unsigned long long, unsigned long long);
+        typedef int (*AccessFn)(unsigned long long, size_t, const AccessDesc*, size_t);
+        auto import = driver_fn<ImportFn>("cuMemImportFromShareableHandle");
+        auto reserve = driver_fn<ReserveFn>("cuMemAddressReserve");
+        auto map = driver_fn<MapFn>("cuMemMap");
+        auto access = driver_fn<AccessFn>("cuMemSetAccess");
+        if (!import || !reserve || !map || !access) { set_error("gkcu_bind_external_image: the CUDA virtual-memory API is unavailable"); return 1; }
+        unsigned long long h = 0, va = 0;
+        if (import(&h, (void*)(uintptr_t)fd, 1 /* CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR */) != 0) { set_error("cuMemImportFromShareableHandle failed"); return 1; }
+        c.ext_vmm_handle = h;
+        c.ext_vmm_size = size_bytes;
+        if (reserve(&va, size_bytes, 0, 0, 0) != 0) { set_error("cuMemAddressReserve failed"); unbind_external(c); return 1; }
+        c.ext_vmm_va = va;
+        AccessDesc ad{1 /* CU_MEM_LOCATION_TYPE_DEVICE */, c.device, 3 /* CU_MEM_ACCESS_FLAGS_PROT_READWRITE */};
+        if (map(va, size_bytes, 0, h, 0) != 0 || access(va, size_bytes, &ad, 1) != 0) { set_error("cuMemMap / cuMemSetAccess failed"); unbind_external(c); return 1; }
+        c.rt.denoised_ext = reinterpret_cast<uint2*>(va + offset_bytes);
+    } else {
+        set_error("gkcu_bind_external_image: unknown handle type");
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int gkcu_bind_external_semaphore(GkcuContext* ctx, uint32_t handle_type, int fd) {
+    CTX_OR_FAIL(ctx);
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.ext_sem) { cudaDestroyExternalSemaphore(c.ext_sem); c.ext_sem = nullptr; }
+    if (fd < 0) return 0;  // unbind
+    if (handle_type != GKCU_EXT_OPAQUE_FD) { set_error("gkcu_bind_external_semaphore: only OPAQUE_FD semaphores"); return 1; }
+    cudaExternalSemaphoreHandleDesc sd{};
+    sd.type = cudaExternalSemaphoreHandleTypeOpaqueFd;
+    sd.handle.fd = fd;
+    GK_CUDA(cudaImportExternalSemaphore(&c.ext_sem, &sd));
+    c.ext_sem_value = 0;
+    return 0;
+}

@@ -58,6 +58,8 @@ struct RenderTargets {
     float* prev_depth = nullptr;
     uint16_t* moment = nullptr;
     int cur = 0;  // accum_*[cur] is this frame's ACCUM, [cur^1] is PREV; objectid[cur] is OBJECTID_0
+    uint2* denoised_ext = nullptr;  // RT_DENOISED bound to imported external memory (gkcu_bind_external_image): the compose pass writes here
+    uint2* denoised_out() const { return denoised_ext ? denoised_ext : denoised; }
 };
 
 struct PathBuffers;  // gk_pathtrace.cu
@@ -135,6 +137,14 @@ struct Context {
     DevBuf peer_flags;          // this rank's flag block: ready[8], done[8], timeouts (uint64 each), written by the peers
     uint64_t peer_epoch = 0;
     std::vector<void*> ipc_opened;
+
+    // zero-copy present: imported memory behind RT_DENOISED and the semaphore signalled after the compose pass
+    cudaExternalMemory_t ext_mem = nullptr;      // GKCU_EXT_OPAQUE_FD
+    unsigned long long ext_vmm_handle = 0;       // GKCU_EXT_CUDA_VMM_FD: CUmemGenericAllocationHandle
+    unsigned long long ext_vmm_va = 0;           // ... and the address range it is mapped at
+    size_t ext_vmm_size = 0;
+    cudaExternalSemaphore_t ext_sem = nullptr;
+    uint64_t ext_sem_value = 0;
 };
 
 gkd::TraceScene make_trace_scene(const Context& c);

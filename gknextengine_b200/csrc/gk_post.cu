@@ -485,7 +485,7 @@ int run_denoise(Context& c, const GkUniformBufferObject& ubo) {
     DenoiseArgs A;
     A.w = (int)t.w; A.h = (int)t.h;
     A.accum_diffuse = t.accum_diffuse[t.cur]; A.accum_specular = t.accum_specular[t.cur]; A.accum_albedo = t.accum_albedo[t.cur];
-    A.denoised = t.denoised;
+    A.denoised = t.denoised_out();
     A.cam = c.ubo.as<GkUniformBufferObject>();
     dim3 grid((t.w + DBX - 1) / DBX, (t.h + DBY - 1) / DBY), block(DBX, DBY);
     CUtensorMap map;

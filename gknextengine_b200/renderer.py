@@ -40,6 +40,9 @@ def lib():
         L.gkcu_create.argtypes = [C.c_int, C.POINTER(P)]
         L.gkcu_destroy.argtypes = [P]
         L.gkcu_resize.argtypes = [P, C.c_uint32, C.c_uint32]
+        L.gkcu_bind_external_image.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int, C.c_size_t, C.c_size_t, C.c_uint32]
+        L.gkcu_unbind_external_image.argtypes = [P, C.c_uint32]
+        L.gkcu_bind_external_semaphore.argtypes = [P, C.c_uint32, C.c_int]
         L.gkcu_scene_upload.argtypes = [P, C.POINTER(GkcuSceneDesc)]
         L.gkcu_blas_build.argtypes = [P]
         L.gkcu_blas_refit.argtypes = [P, C.c_uint32, C.c_void_p, C.c_uint32]
@@ -277,6 +280,18 @@ class CudaPathTracingRenderer:
 
     def present_wait(self):
         _ck(lib().gkcu_readback_wait(self._ctx))
+
+    EXT_OPAQUE_FD, EXT_CUDA_VMM_FD = 0, 1
+
+    def bind_external_image(self, rt, handle_type, fd, size_bytes, offset_bytes=0, row_pitch_bytes=0):
+        """Zero-copy present: RT_DENOISED lives in imported external memory (the engine's exportable render image, RenderImage.hpp:30-37)."""
+        _ck(lib().gkcu_bind_external_image(self._ctx, rt, handle_type, fd, size_bytes, offset_bytes, row_pitch_bytes))
+
+    def unbind_external_image(self, rt):
+        _ck(lib().gkcu_unbind_external_image(self._ctx, rt))
+
+    def bind_external_semaphore(self, handle_type, fd):
+        _ck(lib().gkcu_bind_external_semaphore(self._ctx, handle_type, fd))
 
     def update_nodes_ptr(self, ptr, count):
         _ck(lib().gkcu_update_nodes(self._ctx, C.cast(ptr, C.POINTER(GkNodeProxy)), count))

@@ -411,6 +411,25 @@ int gkcu_run_post(GkcuContext* ctx, const GkUniformBufferObject* ubo, const Gkcu
 int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, size_t bytes);
 int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity);
 int gkcu_synchronize(GkcuContext* ctx);
+
+/* ---------------------------------------------------------------------- zero-copy present
+ * The engine can create a render image whose memory is exportable as an OPAQUE_FD (RenderImage(..., external = true),
+ * src/Vulkan/RenderImage.hpp:30-37; VkExternalMemoryImageCreateInfo at src/Vulkan/Image.cpp:46-58; VkExportMemoryAllocateInfo at
+ * src/Vulkan/DeviceMemory.cpp:103-112 - today used for OIDN). gkcu_bind_external_image imports that memory and makes it RT_DENOISED:
+ * the compose pass then writes the final image where the engine's resolve blit (VulkanBaseRenderer.cpp:1045-1069) reads it, and the
+ * per-frame device->host copy of the headless path disappears. The image must be linear and tightly packed (row pitch = width * 8
+ * bytes, R16G16B16A16_SFLOAT); an optimal-tiled image needs an array mapping and is not supported. handle_type:
+ *   GKCU_EXT_OPAQUE_FD    a Vulkan VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT descriptor (cudaImportExternalMemory; CUDA owns the fd afterwards)
+ *   GKCU_EXT_CUDA_VMM_FD  a cuMemExportToShareableHandle POSIX descriptor of another CUDA process / allocator (cuMemImportFromShareableHandle)
+ * gkcu_bind_external_semaphore imports a VK_EXTERNAL_SEMAPHORE_HANDLE_TYPE_OPAQUE_FD semaphore that every frame signals after the compose pass
+ * (fd = -1 unbinds). gkcu_resize and gkcu_destroy drop the bindings. */
+enum { GKCU_EXT_OPAQUE_FD = 0, GKCU_EXT_CUDA_VMM_FD = 1 };
+int gkcu_bind_external_image(GkcuContext* ctx, uint32_t rt_index, uint32_t handle_type, int fd, size_t size_bytes, size_t offset_bytes,
+                             uint32_t row_pitch_bytes);
+int gkcu_unbind_external_image(GkcuContext* ctx, uint32_t rt_index);
+int gkcu_bind_external_semaphore(GkcuContext* ctx, uint32_t handle_type, int fd);
+
+
 int gkcu_get_timings(GkcuContext* ctx, GkcuTimings* out);
 int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out);
 int gkcu_get_kernel_stats(GkcuContext* ctx, GkcuKernelStats* out);

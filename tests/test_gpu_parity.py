@@ -712,6 +712,76 @@ def test_async_present_overlaps_the_next_frame_without_tearing(sky):
             r.close()
 
 
+def test_zero_copy_present_into_imported_external_memory(sky):
+    """gkcu_bind_external_image (SURVEY 8f row f3 groundwork): RT_DENOISED is written straight into memory imported from a file descriptor,
+    the way the engine exports a render image (RenderImage(..., external = true), src/Vulkan/RenderImage.hpp:30-37, DeviceMemory.cpp:103-112).
+    Without Vulkan on the box the exporter is a second CUDA allocation (cuMemCreate + cuMemExportToShareableHandle, POSIX fd), which this test
+    also maps itself to read the pixels back without going through the renderer. The image must equal the oracle's, the internal image must stay
+    untouched, and unbinding must restore the internal target."""
+    import os
+    from cuda.bindings import driver as cu
+
+    def ck(res):
+        assert res[0] == cu.CUresult.CUDA_SUCCESS, res[0]
+        return res[1] if len(res) == 2 else res[1:]
+
+    W, H = 640, 360
+    r = CudaPathTracingRenderer(0)
+    try:
+        scene = host.Scene("RTIO.proc", samples=2, bounces=4, taa=True, denoiser=True)
+        scene.update_nodes()
+        osc, ofr = setup_pair(r, scene, W, H, sky)
+        ck(cu.cuInit(0))
+        prop = cu.CUmemAllocationProp()
+        prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+        prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        prop.location.id = 0
+        prop.requestedHandleTypes = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+        gran = ck(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_MINIMUM))
+        offset = 4096  # the image does not start at the beginning of the allocation (a Vulkan memory offset)
+        size = ((offset + W * H * 8 + gran - 1) // gran) * gran
+        handle = ck(cu.cuMemCreate(size, prop, 0))
+        fd = ck(cu.cuMemExportToShareableHandle(handle, cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0))
+        va = ck(cu.cuMemAddressReserve(size, 0, 0, 0))
+        ck(cu.cuMemMap(va, size, 0, handle, 0))
+        acc = cu.CUmemAccessDesc()
+        acc.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        acc.location.id = 0
+        acc.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+        ck(cu.cuMemSetAccess(va, size, [acc], 1))
+        ck(cu.cuMemsetD8(va, 0xEE, size))
+        with pytest.raises(GkcuError):
+            r.bind_external_image(RT["DENOISED"], r.EXT_CUDA_VMM_FD, int(fd), W * H * 8, offset)  # allocation too small for image + offset
+        with pytest.raises(GkcuError):
+            r.bind_external_image(RT["ALBEDO"], r.EXT_CUDA_VMM_FD, int(fd), size, offset)
+        r.bind_external_image(RT["DENOISED"], r.EXT_CUDA_VMM_FD, int(fd), size, offset, W * 8)
+        ubo = scene.ubo(W, H, 1)
+        r.Render(ubo, params())
+        r.BeforeNextFrame()
+        ofr.render(osc, ubo, params())
+        raw = np.zeros(size, np.uint8)
+        ck(cu.cuMemcpyDtoH(raw.ctypes.data, va, size))
+        got = raw[offset:offset + W * H * 8].view(np.float16).reshape(H, W, 4)
+        assert int(denoised_ulps(got, ofr.image(RT["DENOISED"])).max()) == 0            # the exporter sees the frame, bit for bit
+        assert (raw[:offset] == 0xEE).all() and (raw[offset + W * H * 8:] == 0xEE).all()  # nothing else was touched
+        assert int(denoised_ulps(r.readback(RT["DENOISED"]), ofr.image(RT["DENOISED"])).max()) == 0  # readback follows the binding
+        r.unbind_external_image(RT["DENOISED"])
+        assert not r.readback(RT["DENOISED"]).view(np.uint16).any()  # the internal image was never written while the binding was active
+        ubo = scene.ubo(W, H, 2)
+        r.Render(ubo, params())
+        r.BeforeNextFrame()
+        ofr.render(osc, ubo, params())
+        assert int(denoised_ulps(r.readback(RT["DENOISED"]), ofr.image(RT["DENOISED"])).max()) == 0
+        with pytest.raises(GkcuError):
+            r.bind_external_semaphore(r.EXT_OPAQUE_FD, os.open(os.devnull, os.O_RDONLY))  # not a semaphore descriptor
+        os.close(int(fd))
+        ck(cu.cuMemUnmap(va, size))
+        ck(cu.cuMemAddressFree(va, size))
+        ck(cu.cuMemRelease(handle))
+    finally:
+        r.close()
+
+
 def test_cpp_headless_harness_runs_the_renderer_switch(tmp_path):
     """The C++ host mirror (gk::HeadlessBaseRenderer -> RegisterLogicRenderer / SwitchLogicRenderer(ERT_CudaPathTracing) -> DrawFrame ->
     CudaPathTracingRenderer -> C ABI) end to end: the binary renders Cornell frames with the probe bake on, reports the reference's
