@@ -58,7 +58,8 @@ struct PathLanes { PathView v[4]; uint32_t n; };
 struct PathBuffers {
     DevBuf rng, pos_mat, nrm_flags, dir_cnt, ray_color, final_color, final_refl, prim_pos_mat, prim_nrm_cnt, prim_albedo;
     DevBuf ray_o, ray_d, slot_pixel[2], hit_tuv, hit_prim, counts, radiance, direct;
-    DevBuf pool_stack;  // k_trace_pool: traversal stacks, [lane][block][depth][slot]
+    DevBuf pool_stack;  // k_trace_pool / k_trace_wpool: traversal stacks, [lane][block (, warp)][depth][slot]
+    size_t pool_stack_stride = 0;  // uint2 entries per lane
     uint32_t* host_counts = nullptr;  // pinned, 64 words per lane
     size_t pixels = 0;
     size_t lane_cap = 0;  // queue capacity of one lane
@@ -935,6 +936,221 @@ __global__ void __launch_bounds__(128, GK_POOL_MINB) k_trace_pool(TraceScene ts,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- warp-pool tracer
+// k_trace_wpool: the pool idea without the block. Every WARP owns GK_WPOOL ray slots in shared memory and one queue per step kind;
+// an iteration takes up to 32 slots of the kind that has a full chunk waiting (else the largest rest) and runs that step with
+// (almost) all lanes active. No block barrier, no atomics - the queues are private to the warp - and a smaller state record: the
+// world-space ray is re-read from the ray queue when an instance is entered or left, the BLAS bases from the instance record.
+// Per ray the sequence of node tests, pushes, pops and triangle tests is that of trace_ray: bit-identical results. Node4 only.
+#ifndef GK_WPOOL
+#define GK_WPOOL 128
+#endif
+#ifndef GK_WPOOL_MINB
+#define GK_WPOOL_MINB 4
+#endif
+static_assert(GK_WPOOL <= 128 && GK_WPOOL % 32 == 0, "slot ids are bytes, rings have 128 entries");
+
+struct WPoolSmem {
+    float ro[3][GK_WPOOL], idir[3][GK_WPOOL];  // current-space ray
+    float sh[3][GK_WPOOL];                     // watertight-test shear of the current space
+    float best_t[GK_WPOOL];
+    uint32_t shk[GK_WPOOL];                    // kx | ky << 2 | kz << 4
+    uint32_t cur[GK_WPOOL], nbase[GK_WPOOL], cinst[GK_WPOOL], pack[GK_WPOOL], qslot[GK_WPOOL];
+    uint8_t ring[PK_COUNT][128];               // per kind: ring buffer of waiting slots
+};
+
+// the world-space ray of a slot, re-read from the ray queue (instance entry / exit only)
+struct WorldQueue {
+    const float4 *ro, *rd;
+    GK_DEV float3 o() const { const float4 v = __ldg(ro); return f3(v.x, v.y, v.z); }
+    GK_DEV float3 d() const { const float4 v = __ldg(rd); return f3(v.x, v.y, v.z); }
+    GK_DEV float3 widir() const { const float3 v = d(); return f3(safe_rcp(v.x), safe_rcp(v.y), safe_rcp(v.z)); }
+    GK_DEV void set(float3, float3, float3) {}
+};
+struct WPoolStack {
+    uint2* base;
+    GK_DEV void push(int& sp, uint2 v) { base[(size_t)sp * GK_WPOOL] = v; ++sp; }
+    GK_DEV uint2 pop(int& sp) { --sp; return base[(size_t)sp * GK_WPOOL]; }
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(128, GK_WPOOL_MINB) k_trace_wpool(TraceScene ts, PathView V, int qi, size_t half, uint2* __restrict__ stack_mem) {
+    static_assert(FMT == 4, "the pool tracers walk Node4 trees");
+    __shared__ WPoolSmem smem[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WPoolSmem& sm = smem[warp];
+    const uint32_t n = V.counts[qi];
+    if (blockIdx.x == 0 && threadIdx.x == 0) V.counts[qi ^ 1] = 0;
+    const float4* ray_o = V.ray_o + (size_t)qi * half;
+    const float4* ray_d = V.ray_d + (size_t)qi * half;
+    const uint32_t* slot_pixel = V.slot_pixel[qi];
+    uint2* const my_stack = stack_mem + ((size_t)blockIdx.x * 4 + warp) * GK_TRAV_STACK * GK_WPOOL;
+    for (int i = lane; i < GK_WPOOL; i += 32) sm.ring[PK_FREE][i] = (uint8_t)i;
+    uint32_t head[PK_COUNT], tail[PK_COUNT];  // warp-uniform
+#pragma unroll
+    for (int k = 0; k < PK_COUNT; ++k) { head[k] = 0; tail[k] = 0; }
+    tail[PK_FREE] = GK_WPOOL;
+    bool drained = false;
+    __syncwarp();
+    for (;;) {
+        // ---- pick the step kind: the first (in priority order) with a full chunk waiting, else the largest rest
+        int kind = -1;
+        uint32_t cnt = 0;
+        {
+            uint32_t best = 0;
+#pragma unroll
+            for (int k = 0; k < PK_COUNT; ++k) {
+                uint32_t a = tail[k] - head[k];
+                if (k == PK_FREE && drained) a = 0;
+                if (best < 32u && a > best) { best = a; kind = k; }  // the first kind that reaches 32 wins, otherwise the largest
+            }
+            cnt = min(best, 32u);
+        }
+        if (kind < 0) break;  // every slot is free and the queue is empty
+        uint32_t begin = 0;
+#pragma unroll
+        for (int k = 0; k < PK_COUNT; ++k)
+            if (k == kind) { begin = head[k]; head[k] += cnt; }
+        const bool act = (uint32_t)lane < cnt;
+        const uint32_t slot = act ? sm.ring[kind][(begin + lane) & 127u] : 0u;
+        int next = -1;
+        if (kind == PK_FREE) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(V.counts + 2, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + cnt >= n) drained = true;
+            if (act) {
+                const uint32_t q = base + lane;
+                next = PK_FREE;
+                if (q < n) {
+                    const float4 o = __ldcs(ray_o + q), d = __ldcs(ray_d + q);
+                    const bool any = (__ldcs(slot_pixel + q) & 0x80000000u) != 0;
+                    Trav T;
+                    WorldQueue world{ray_o + q, ray_d + q};
+                    trav_init<FMT>(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, any);
+                    __stcs(V.hit_tuv + q, f4(T.best.t, 0.0f, 0.0f, __uint_as_float(GK_NO_HIT)));  // the miss record; a hit overwrites it
+                    __stcs(V.hit_prim + q, 0u);
+                    if (!T.done) {
+                        sm.ro[0][slot] = T.ro.x; sm.ro[1][slot] = T.ro.y; sm.ro[2][slot] = T.ro.z;
+                        sm.idir[0][slot] = T.idir.x; sm.idir[1][slot] = T.idir.y; sm.idir[2][slot] = T.idir.z;
+                        sm.best_t[slot] = T.best.t;
+                        sm.cur[slot] = 0u;
+                        sm.nbase[slot] = 0xFFFFFFFFu;
+                        sm.cinst[slot] = GK_NO_HIT;
+                        sm.pack[slot] = any ? PP_ANY : 0u;
+                        sm.qslot[slot] = q;
+                        next = PK_NODE;
+                    }
+                }
+            }
+        } else if (kind == PK_NODE) {
+            if (act) {
+                Trav T;
+                const uint32_t pk = sm.pack[slot], nb = sm.nbase[slot];
+                set_space<FMT>(T, f3(sm.ro[0][slot], sm.ro[1][slot], sm.ro[2][slot]), f3(sm.idir[0][slot], sm.idir[1][slot], sm.idir[2][slot]));
+                T.tmin = GK_EPS;
+                T.best.t = sm.best_t[slot];
+                T.cur = sm.cur[slot];
+                T.cur_inst = 0;  // only feeds the statistics build
+                T.sp = (int)(pk & 0xFFu);
+                T.nodes = reinterpret_cast<const uint4*>(nb == 0xFFFFFFFFu ? ts.tlas : ts.blas + nb);
+                WPoolStack stack{my_stack + slot};
+                if (trav_node_core4(T, stack)) {
+                    sm.cur[slot] = T.cur;
+                    next = !(T.cur & GK_LEAF_BIT) ? PK_NODE : (nb == 0xFFFFFFFFu ? PK_INST : PK_TRI);
+                } else {
+                    next = PK_POP;
+                }
+                sm.pack[slot] = (pk & ~0xFFu) | (uint32_t)T.sp;
+            }
+        } else {
+            if (act) {
+                Trav T;
+                uint32_t pk = sm.pack[slot];
+                const uint32_t q = sm.qslot[slot];
+                WorldQueue world{ray_o + q, ray_d + q};
+                T.cur = sm.cur[slot];
+                T.cur_inst = sm.cinst[slot];
+                T.sp = (int)(pk & 0xFFu);
+                T.sp_inst = (int)((pk >> 8) & 0xFFu);
+                T.best.t = sm.best_t[slot];
+                T.done = false;
+                bool pop = true, space_changed = false;
+                if (kind == PK_INST) {
+                    if (trav_enter_instance<FMT>(T, world, ts, T.cur & 0x0FFFFFFFu)) {
+                        sm.nbase[slot] = __ldg(&ts.inst[T.cur_inst].node_base);
+                        sm.sh[0][slot] = T.sh.Sx; sm.sh[1][slot] = T.sh.Sy; sm.sh[2][slot] = T.sh.Sz;
+                        sm.shk[slot] = (uint32_t)T.sh.kx | ((uint32_t)T.sh.ky << 2) | ((uint32_t)T.sh.kz << 4);
+                        sm.cur[slot] = 0u;
+                        pop = false;
+                        space_changed = true;
+                        next = PK_NODE;
+                    }
+                } else if (kind == PK_TRI) {
+                    const float3 ro = f3(sm.ro[0][slot], sm.ro[1][slot], sm.ro[2][slot]);
+                    RayShear sh;
+                    const uint32_t k3 = sm.shk[slot];
+                    sh.kx = (int)(k3 & 3u); sh.ky = (int)((k3 >> 2) & 3u); sh.kz = (int)((k3 >> 4) & 3u);
+                    sh.Sx = sm.sh[0][slot]; sh.Sy = sm.sh[1][slot]; sh.Sz = sm.sh[2][slot];
+                    const float4* tris = ts.tris + (size_t)__ldg(&ts.inst[T.cur_inst].tri_base) * 3;
+                    const uint32_t first = T.cur & 0x0FFFFFFFu, count = ((T.cur >> 28) & 7u) + 1u;
+                    for (uint32_t i = 0; i < count; ++i) {
+                        const float4* tp = tris + (size_t)(first + i) * 3;
+                        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                        float t, b1, b2;
+                        if (!tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), ro, sh, t, b1, b2)) continue;
+                        if (!(t > GK_EPS && t < GK_PT_MAX_TRACE_DISTANCE)) continue;
+                        const uint32_t p = __float_as_uint(a.w);
+                        if (pk & PP_ANY) {  // first hit ends the query
+                            __stcs(V.hit_tuv + q, f4(t, 0.0f, 0.0f, __uint_as_float(T.cur_inst)));
+                            __stcs(V.hit_prim + q, p);
+                            T.done = true;
+                            break;
+                        }
+                        bool better = !(pk & PP_HAS_HIT) || t < T.best.t;
+                        if (!better && t == T.best.t) {  // tie: (instance, primitive) order; the record of the best hit is in global memory
+                            const uint32_t bi = __float_as_uint(__ldcg(&V.hit_tuv[q].w)), bp = __ldcg(V.hit_prim + q);
+                            better = T.cur_inst < bi || (T.cur_inst == bi && p < bp);
+                        }
+                        if (better) {
+                            T.best.t = t;
+                            pk |= PP_HAS_HIT;
+                            __stcg(V.hit_tuv + q, f4(t, b1, b2, __uint_as_float(T.cur_inst)));
+                            __stcg(V.hit_prim + q, p);
+                        }
+                    }
+                    sm.best_t[slot] = T.best.t;
+                    if (T.done) { pop = false; next = PK_FREE; }
+                }
+                if (pop) {
+                    const uint32_t inst_before = T.cur_inst;
+                    WPoolStack stack{my_stack + slot};
+                    trav_pop<FMT>(T, world, ts, stack);
+                    if (T.done) next = PK_FREE;
+                    else next = !(T.cur & GK_LEAF_BIT) ? PK_NODE : (T.cur_inst == GK_NO_HIT ? PK_INST : PK_TRI);
+                    space_changed = T.cur_inst != inst_before;  // left the instance: back in world space
+                    if (space_changed) sm.nbase[slot] = 0xFFFFFFFFu;
+                    sm.cur[slot] = T.cur;
+                }
+                if (space_changed) {
+                    sm.ro[0][slot] = T.ro.x; sm.ro[1][slot] = T.ro.y; sm.ro[2][slot] = T.ro.z;
+                    sm.idir[0][slot] = T.idir.x; sm.idir[1][slot] = T.idir.y; sm.idir[2][slot] = T.idir.z;
+                    sm.cinst[slot] = T.cur_inst;
+                }
+                sm.pack[slot] = (pk & ~0xFFFFu) | (uint32_t)T.sp | ((uint32_t)T.sp_inst << 8);
+            }
+        }
+        // ---- append the slots to the queues of their next step: the queues are private to the warp, a ballot per kind is all it takes
+#pragma unroll
+        for (int k = 0; k < PK_COUNT; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, next == k);
+            if (next == k) sm.ring[k][(tail[k] + __popc(m & ((1u << lane) - 1u))) & 127u] = (uint8_t)slot;
+            tail[k] += __popc(m);
+        }
+        __syncwarp();
+    }
+}
+
 // The first version: a warp takes 32 rays, every lane runs the simple per-ray loop, the warp refills when all are done.
 __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V, int qi, size_t half) {
     const uint32_t n = V.counts[qi];
@@ -1199,7 +1415,8 @@ int path_resize(Context& c) {
               b.prim_nrm_cnt.reserve(n * 16) && b.prim_albedo.reserve(n * 16) && b.ray_o.reserve(2 * m * 16) && b.ray_d.reserve(2 * m * 16) &&
               b.slot_pixel[0].reserve(m * 4) && b.slot_pixel[1].reserve(m * 4) && b.hit_tuv.reserve(m * 16) && b.hit_prim.reserve(m * 4) &&
               b.counts.reserve(4 * 64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16) &&
-              b.pool_stack.reserve((size_t)b.lanes * c.sm_count * GK_POOL_MINB * GK_TRAV_STACK * GK_POOL * sizeof(uint2));
+              b.pool_stack.reserve((size_t)b.lanes * c.sm_count * std::max<size_t>((size_t)GK_POOL_MINB * GK_POOL, (size_t)GK_WPOOL_MINB * 4 * GK_WPOOL) * GK_TRAV_STACK * sizeof(uint2));
+    b.pool_stack_stride = (size_t)c.sm_count * std::max<size_t>((size_t)GK_POOL_MINB * GK_POOL, (size_t)GK_WPOOL_MINB * 4 * GK_WPOOL) * GK_TRAV_STACK;
     if (!ok) return 1;
     // ranks other than 0 never write the direct-term plane; keep it defined for a host that resolves on such a context
     GK_CUDA(cudaMemsetAsync(b.direct.p, 0, n * 16, c.stream));
@@ -1300,9 +1517,12 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                     else if (c.trace_variant == 0) {
                         if (c.node_format == 8) k_trace<0, 8><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
                         else k_trace<0, 4><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                    } else if (c.trace_variant == 7 && c.node_format == 4) {
+                        const uint32_t pb = std::min<uint32_t>((bound[l] + 4 * GK_WPOOL - 1) / (4 * GK_WPOOL), (uint32_t)c.sm_count * GK_WPOOL_MINB);
+                        k_trace_wpool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride);
                     } else if (c.trace_variant == 6 && c.node_format == 4) {
                         const uint32_t pb = std::min<uint32_t>((bound[l] + GK_POOL - 1) / GK_POOL, (uint32_t)c.sm_count * GK_POOL_MINB);
-                        k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * c.sm_count * GK_POOL_MINB * GK_TRAV_STACK * GK_POOL);
+                        k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride);
                     } else {
                         const uint32_t tb = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u);
                         if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);

@@ -72,11 +72,12 @@ def test_rtiow_sky_multi_bounce(monkeypatch, sky, builder, node_format):
         r.close()
 
 
-def test_pool_tracer_variant_is_bit_identical(monkeypatch, sky):
-    """GKCU_TRACE_VARIANT=6: k_trace_pool keeps the rays of a block in a shared-memory pool and runs every step kind with full warps
-    (profiles/r02_experiments.md; slower than the lane-owned k_trace, kept as a measured alternative). Same per-ray sequence of node tests,
-    pushes and pops, so every image must stay bit-identical to the oracle."""
-    monkeypatch.setenv("GKCU_TRACE_VARIANT", "6")
+@pytest.mark.parametrize("variant", [6, 7])
+def test_pool_tracer_variants_are_bit_identical(monkeypatch, sky, variant):
+    """GKCU_TRACE_VARIANT=6 / 7: k_trace_pool / k_trace_wpool keep the rays of a block / of a warp in a shared-memory pool and run every step
+    kind with (almost) full warps (profiles/r02_experiments.md: 27 / 22 lanes per instruction instead of 14, but slower than the lane-owned
+    k_trace; kept as measured alternatives). Same per-ray sequence of node tests, pushes and pops, so every image must stay bit-identical."""
+    monkeypatch.setenv("GKCU_TRACE_VARIANT", str(variant))
     r = CudaPathTracingRenderer(0)
     try:
         W, H = 640, 360
