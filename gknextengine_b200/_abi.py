@@ -61,7 +61,14 @@ class GkcuSceneDesc(C.Structure):
 
 class GkcuFrameParams(C.Structure):
     _fields_ = [("progressive", C.c_uint32), ("temporal_frames", C.c_int32), ("fast_reproject", C.c_uint32), ("spp_rank", C.c_uint32),
-                ("spp_world", C.c_uint32), ("tracer", C.c_uint32), ("skip_post", C.c_uint32), ("reserved", C.c_uint32)]
+                ("spp_world", C.c_uint32), ("tracer", C.c_uint32), ("skip_post", C.c_uint32), ("primary_visibility", C.c_uint32)]
+
+
+class GkGPUDrivenStat(C.Structure):  # BasicTypes.slang:13-20
+    _fields_ = [(n, C.c_uint32) for n in ("ProcessedCount", "VisibleCount", "CulledCount", "TriangleCount", "CulledTriangleCount", "pad0", "pad1", "pad2")]
+
+
+DRAW_CMD_DTYPE = np.dtype([("indexCount", "<u4"), ("instanceCount", "<u4"), ("firstIndex", "<u4"), ("vertexOffset", "<i4"), ("firstInstance", "<u4")])  # VkDrawIndexedIndirectCommand
 
 
 class GkcuTimings(C.Structure):
@@ -97,7 +104,7 @@ RT = dict(ACCUMLATE_DIFFUSE=0, SINGLE_DIFFUSE=1, MINIGBUFFER=2, OBJEDCTID_0=3, O
           DENOISED=9, PREV_DEPTHBUFFER=10, ACCUMLATE_SPECULAR=11, SINGLE_SPECULAR=12, ACCUMLATE_ALBEDO=13, MOTIONMOMENT=14,
           SINGLE_PREV_DIFFUSE=20, SINGLE_PREV_SPECULAR=21, SINGLE_PREV_ALBEDO=22, EXT_PRIMITIVEID=64)
 RT_FORMAT = {
-    0: (np.float16, 4), 1: (np.float16, 4), 3: (np.uint32, 1), 4: (np.uint32, 1), 5: (np.float32, 2), 6: (np.float16, 4),
+    0: (np.float16, 4), 1: (np.float16, 4), 2: (np.uint32, 1), 3: (np.uint32, 1), 4: (np.uint32, 1), 5: (np.float32, 2), 6: (np.float16, 4),
     7: (np.float16, 4), 9: (np.float16, 4), 10: (np.float32, 1), 11: (np.float16, 4), 12: (np.float16, 4), 13: (np.float16, 4),
     14: (np.uint16, 1), 20: (np.float16, 4), 21: (np.float16, 4), 22: (np.float16, 4), 64: (np.uint32, 1),
 }

@@ -49,7 +49,7 @@ static void free_targets(RenderTargets& t) {
     void** ptrs[] = {(void**)&t.accum_diffuse[0], (void**)&t.accum_diffuse[1], (void**)&t.accum_specular[0], (void**)&t.accum_specular[1],
                      (void**)&t.accum_albedo[0], (void**)&t.accum_albedo[1], (void**)&t.single_diffuse, (void**)&t.single_specular,
                      (void**)&t.albedo, (void**)&t.normal, (void**)&t.denoised, (void**)&t.objectid[0], (void**)&t.objectid[1],
-                     (void**)&t.primitiveid, (void**)&t.motion, (void**)&t.prev_depth, (void**)&t.moment};
+                     (void**)&t.primitiveid, (void**)&t.motion, (void**)&t.prev_depth, (void**)&t.moment, (void**)&t.minigbuffer};
     for (void** p : ptrs) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -72,10 +72,22 @@ static int upload_tex_table(Context& c) {
 
 using namespace gkcu;
 
+// A failed call of the previous entry point (or of another library on this thread) can leave a non-sticky CUDA error behind; cub and the
+// GK_CUDA checks would report it as their own. Every entry point starts clean; GKCU_DEBUG=1 names the call that left it.
+static void clear_stale_error(Context& c, const char* api) {
+    const cudaError_t stale = cudaGetLastError();
+    if (stale != cudaSuccess) {
+        static const bool dbg = getenv("GKCU_DEBUG") != nullptr;
+        if (dbg) fprintf(stderr, "gkcu: %s entered with the stale CUDA error '%s' left by %s\n", api, cudaGetErrorString(stale), c.last_api ? c.last_api : "(nothing)");
+    }
+    c.last_api = api;
+}
+
 #define CTX_OR_FAIL(ctx)                                   \
     if (!(ctx)) { set_error("null context"); return 1; }   \
     Context& c = (ctx)->c;                                 \
-    if (!check(cudaSetDevice(c.device), "cudaSetDevice")) return 1;
+    if (!check(cudaSetDevice(c.device), "cudaSetDevice")) return 1; \
+    clear_stale_error(c, __func__);
 
 extern "C" {
 
@@ -107,6 +119,8 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     if (const char* e = getenv("GKCU_TMA")) c.use_tma = atoi(e);
     if (const char* e = getenv("GKCU_SHADE_MINB")) c.shade_minb = atoi(e);
     if (const char* e = getenv("GKCU_TRACE_CARVEOUT")) c.trace_carveout = std::max(-1, std::min(100, atoi(e)));
+    if (const char* e = getenv("GKCU_SORT_RAYS")) c.sort_rays = std::max(0, std::min(19, atoi(e)));
+    if (const char* e = getenv("GKCU_SORT_EXTENT")) c.sort_extent = (float)atof(e);
     if (const char* e = getenv("GKCU_REFILL")) c.refill_below = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("GKCU_NODE_FORMAT")) c.node_format = atoi(e) == 4 ? 4 : 8;
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
@@ -140,7 +154,7 @@ int gkcu_destroy(GkcuContext* ctx) {
     for (auto& t : c.textures)
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
-                      &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.blas_leaf, &c.tlas_leaf, &c.instances, &c.inst_lo,
+                      &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.blas_leaf, &c.tlas_leaf, &c.raster_indices, &c.reorders, &c.draw_cmds, &c.gpu_stats, &c.vis_keys, &c.raster_large, &c.raster_counters, &c.instances, &c.inst_lo,
                       &c.inst_hi, &c.tlas_active_ids, &c.inst_flags, &c.select_tmp, &c.select_count, &c.node_stage, &c.node_stage_idx, &c.tex_table, &c.probes, &c.probe_meta, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
                       &c.peer_flags};
     for (DevBuf* b : bufs) b->release();
@@ -186,7 +200,8 @@ int gkcu_resize(GkcuContext* ctx, uint32_t width, uint32_t height) {
     }
     if (alloc_zero((void**)&t.single_diffuse, n * 8, st) || alloc_zero((void**)&t.single_specular, n * 8, st) || alloc_zero((void**)&t.albedo, n * 8, st) ||
         alloc_zero((void**)&t.normal, n * 8, st) || alloc_zero((void**)&t.denoised, n * 8, st) || alloc_zero((void**)&t.primitiveid, n * 4, st) ||
-        alloc_zero((void**)&t.motion, n * 8, st) || alloc_zero((void**)&t.prev_depth, n * 4, st) || alloc_zero((void**)&t.moment, n * 2, st))
+        alloc_zero((void**)&t.motion, n * 8, st) || alloc_zero((void**)&t.prev_depth, n * 4, st) || alloc_zero((void**)&t.moment, n * 2, st) ||
+        alloc_zero((void**)&t.minigbuffer, n * 4, st))
         return 1;
     t.w = width;
     t.h = height;
@@ -213,6 +228,7 @@ int gkcu_scene_upload(GkcuContext* ctx, const GkcuSceneDesc* d) {
             if (d->indices[md.indexOffset + i] >= md.vertexCount) { set_error("gkcu_scene_upload: index beyond the model's vertex count"); return 1; }
     }
     cudaStream_t st = c.stream;
+    c.raster_index_count = c.reorder_count = 0;  // the raster-side buffers belong to the previous scene
     c.blas_built = false;  // from here on the old acceleration structures no longer describe the buffers
     c.tlas_dirty = true;
     c.tlas.node_count = 0;
@@ -443,6 +459,9 @@ int gkcu_render_frame(GkcuContext* ctx, const GkUniformBufferObject* ubo, const 
     cudaEventRecord(c.ev[0], st);
     c.frame_built_tlas = c.tlas_dirty;
     if (c.tlas_dirty && build_tlas(c)) return 1;  // RayTraceBaseRenderer::PreRender "TLAS Update"
+    if (params->primary_visibility) {             // VulkanBaseRenderer::PreRender "gpu cull" + "visibility pass"
+        if (run_gpu_cull(c, *ubo) || run_visibility_pass(c, *ubo)) return 1;
+    }
     cudaEventRecord(c.ev[1], st);
     if (run_rt_pass(c, *ubo, *params)) return 1;
     cudaEventRecord(c.ev[2], st);
@@ -572,6 +591,7 @@ int gkcu_readback(GkcuContext* ctx, uint32_t rt_index, void* dst, size_t dst_byt
         case GK_RT_PREV_DEPTHBUFFER: src = t.prev_depth; bytes = n * 4; break;
         case GK_RT_MOTIONMOMENT: src = t.moment; bytes = n * 2; break;
         case GK_RT_EXT_PRIMITIVEID: src = t.primitiveid; bytes = n * 4; break;
+        case GK_RT_MINIGBUFFER: src = t.minigbuffer; bytes = n * 4; break;
         default: set_error("gkcu_readback: unknown storage image index"); return 1;
     }
     if (!dst || dst_bytes < bytes) { set_error("gkcu_readback: destination too small"); return 1; }
@@ -629,6 +649,8 @@ int gkcu_upload_image(GkcuContext* ctx, uint32_t rt_index, const void* src, size
         case GK_RT_NORMAL: dst = t.normal; bytes = n * 8; break;
         case GK_RT_MOTIONVECTOR: dst = t.motion; bytes = n * 8; break;
         case GK_RT_MOTIONMOMENT: dst = t.moment; bytes = n * 2; break;
+        case GK_RT_MINIGBUFFER: dst = t.minigbuffer; bytes = n * 4; break;
+        case GK_RT_PREV_DEPTHBUFFER: dst = t.prev_depth; bytes = n * 4; break;
         default: set_error("gkcu_upload_image: unsupported storage image index"); return 1;
     }
     if (src_bytes != bytes) { set_error("gkcu_upload_image: size mismatch"); return 1; }
@@ -854,5 +876,56 @@ extern "C" int gkcu_bind_external_semaphore(GkcuContext* ctx, uint32_t handle_ty
     sd.handle.fd = fd;
     GK_CUDA(cudaImportExternalSemaphore(&c.ext_sem, &sd));
     c.ext_sem_value = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------- visibility front end (gk_raster.cu)
+extern "C" int gkcu_scene_upload_raster(GkcuContext* ctx, const uint32_t* raster_indices, uint32_t index_count, const uint32_t* reorders, uint32_t reorder_count) {
+    CTX_OR_FAIL(ctx);
+    if (!raster_indices || !reorders) { set_error("gkcu_scene_upload_raster: null array"); return 1; }
+    if (c.model_count == 0) { set_error("gkcu_scene_upload_raster: call gkcu_scene_upload first"); return 1; }
+    if (index_count != c.index_count) { set_error("gkcu_scene_upload_raster: the raster index buffer must have as many indices as GPUScene.Indices"); return 1; }
+    for (uint32_t i = 0; i < c.offset_count; ++i) {  // every index of a section must land inside Reorders, every Reorders entry inside the vertex buffer
+        const GkModelData& md = c.host_offsets[i];
+        for (uint32_t k = 0; k < md.indexCount; ++k)
+            if ((uint64_t)raster_indices[md.indexOffset + k] + md.reorderOffset >= reorder_count) { set_error("gkcu_scene_upload_raster: index beyond Reorders"); return 1; }
+    }
+    for (uint32_t i = 0; i < reorder_count; ++i)
+        if (reorders[i] >= c.vertex_count) { set_error("gkcu_scene_upload_raster: Reorders entry beyond the vertex buffer"); return 1; }
+    if (!c.raster_indices.reserve((size_t)std::max(1u, index_count) * 4) || !c.reorders.reserve((size_t)std::max(1u, reorder_count) * 4)) return 1;
+    GK_CUDA(cudaMemcpyAsync(c.raster_indices.p, raster_indices, (size_t)index_count * 4, cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaMemcpyAsync(c.reorders.p, reorders, (size_t)reorder_count * 4, cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    c.raster_index_count = index_count;
+    c.reorder_count = reorder_count;
+    return 0;
+}
+
+extern "C" int gkcu_cull(GkcuContext* ctx, const GkUniformBufferObject* ubo) {
+    CTX_OR_FAIL(ctx);
+    if (!ubo || c.rt.w == 0 || c.model_count == 0) { set_error("gkcu_cull: null ubo, or no images / scene yet"); return 1; }
+    return run_gpu_cull(c, *ubo);
+}
+
+extern "C" int gkcu_visibility_pass(GkcuContext* ctx, const GkUniformBufferObject* ubo) {
+    CTX_OR_FAIL(ctx);
+    if (!ubo || c.rt.w == 0 || c.model_count == 0) { set_error("gkcu_visibility_pass: null ubo, or no images / scene yet"); return 1; }
+    if (c.raster_index_count == 0) { set_error("gkcu_visibility_pass: call gkcu_scene_upload_raster first"); return 1; }
+    return run_visibility_pass(c, *ubo);
+}
+
+extern "C" int gkcu_get_gpu_driven_stats(GkcuContext* ctx, GkGPUDrivenStat* out) {
+    CTX_OR_FAIL(ctx);
+    if (!out || !c.gpu_stats.p) { set_error("gkcu_get_gpu_driven_stats: null out, or gkcu_cull has not run"); return 1; }
+    GK_CUDA(cudaMemcpyAsync(out, c.gpu_stats.p, sizeof(GkGPUDrivenStat), cudaMemcpyDeviceToHost, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+extern "C" int gkcu_read_draw_commands(GkcuContext* ctx, void* dst, uint32_t count) {
+    CTX_OR_FAIL(ctx);
+    if (!dst || !c.draw_cmds.p || count > c.draw_count || c.draw_count == 0xFFFFFFFFu) { set_error("gkcu_read_draw_commands: null dst, gkcu_cull has not run, or count beyond the batches"); return 1; }
+    GK_CUDA(cudaMemcpyAsync(dst, c.draw_cmds.p, (size_t)count * 20, cudaMemcpyDeviceToHost, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }

@@ -57,6 +57,7 @@ struct RenderTargets {
     float2* motion = nullptr;
     float* prev_depth = nullptr;
     uint16_t* moment = nullptr;
+    uint32_t* minigbuffer = nullptr;  // RT_MINIGBUFFER: the visibility buffer (R32_UINT), written by the visibility pass
     int cur = 0;  // accum_*[cur] is this frame's ACCUM, [cur^1] is PREV; objectid[cur] is OBJECTID_0
     uint2* denoised_ext = nullptr;  // RT_DENOISED bound to imported external memory (gkcu_bind_external_image): the compose pass writes here
     uint2* denoised_out() const { return denoised_ext ? denoised_ext : denoised; }
@@ -68,6 +69,7 @@ struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    const char* last_api = nullptr;  // name of the previous C-ABI entry point (diagnostics)
 
     // scene (GPUScene buffers, BasicTypes.slang:261-291)
     DevBuf vertices, simple, indices, offsets, materials, nodes;
@@ -82,6 +84,9 @@ struct Context {
     DevBuf shade_inst;  // 32 B per instance: shade-triangle base + the first 7 material ids of the node
     DevBuf tlas_nodes, tlas_node_lo, tlas_node_hi, instances, inst_lo, inst_hi, tlas_active_ids;
     DevBuf blas_leaf, tlas_leaf;  // Node8 leaf tables (triangle ranges / instance indices)
+    // visibility front end (gk_raster.cu): GPUScene.Indices of the raster pass + GPUScene.Reorders, IndirectDrawCommands, GPUDrivenStats
+    DevBuf raster_indices, reorders, draw_cmds, gpu_stats, vis_keys, raster_large, raster_counters;
+    uint32_t raster_index_count = 0, reorder_count = 0, draw_count = 0xFFFFFFFFu;
     DevBuf inst_flags, select_tmp, select_count;  // device-side compaction of the instances that enter the TLAS
     DevBuf node_stage, node_stage_idx;            // gkcu_update_nodes_sparse staging
     WideBvhInfo tlas;
@@ -95,6 +100,8 @@ struct Context {
     int trace_carveout = -1;  // k_trace shared-memory carve-out in percent (GKCU_TRACE_CARVEOUT), -1 = sized to the resident blocks
     int carveout_applied = 0; // trace_carveout + 2 once the function attribute has been set on this context's device
     int node_format = 4;      // GKCU_NODE_FORMAT: 4 = fp32 4-wide Node4 (default: 4.5 % faster on the bench frame, profiles/r02_experiments.md), 8 = quantised 8-wide Node8 (gk_bvh.cuh)
+    int sort_rays = 0;      // GKCU_SORT_RAYS = bits per axis of the origin grid the rays of a wave are sorted on before k_trace (0 = queue order)
+    float sort_extent = 0;  // GKCU_SORT_EXTENT: side of the origin grid's cube around the world origin (0 = the TLAS root box)
     int refill_below = 16;  // k_trace: refill idle lanes when fewer than this many lanes are busy (GKCU_REFILL)
     int blas_builder = 1;  // 0 = LBVH, 1 = SAH-binned (GKCU_BLAS_BUILDER=lbvh|sah)
 
@@ -165,6 +172,10 @@ void fetch_ray_counters(Context& c);
 int radiance_buffer(Context& c, void** ptr, size_t* bytes);
 int run_resolve_strip(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p);
 void* peer_local_buffer(Context& c, uint32_t what);
+
+// gk_raster.cu
+int run_gpu_cull(Context& c, const GkUniformBufferObject& ubo);
+int run_visibility_pass(Context& c, const GkUniformBufferObject& ubo);
 
 // gk_probes.cu
 int probes_voxelize(Context& c);

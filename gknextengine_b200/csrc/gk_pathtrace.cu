@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <type_traits>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #ifndef GK_NODE_REPEAT
 #define GK_NODE_REPEAT 1
 #endif
@@ -33,6 +35,7 @@ struct RTView {
     float2* motion;
     float* prev_depth;
     uint16_t* moment;
+    const uint32_t* vis;  // RT_MINIGBUFFER when the frame takes its primary visibility from the rasterised buffer, else nullptr
 };
 
 // Per-pixel path state (SoA, 16-byte records) + per-slot ray/hit records of the wavefront queues.
@@ -51,6 +54,7 @@ struct PathView {
     uint32_t* hit_prim;
     uint32_t* counts;           // [0],[1] queue sizes (ping-pong), [2] trace cursor, [4..] ray counters
     float4 *radiance, *direct;  // multi-GPU: un-normalised sums (2 planes) and rank 0's direct term
+    const uint32_t* order;      // k_trace: queue position -> slot (rays binned by origin cell and direction), nullptr = queue order
 };
 
 struct PathLanes { PathView v[4]; uint32_t n; };
@@ -58,6 +62,8 @@ struct PathLanes { PathView v[4]; uint32_t n; };
 struct PathBuffers {
     DevBuf rng, pos_mat, nrm_flags, dir_cnt, ray_color, final_color, final_refl, prim_pos_mat, prim_nrm_cnt, prim_albedo;
     DevBuf ray_o, ray_d, slot_pixel[2], hit_tuv, hit_prim, counts, radiance, direct;
+    DevBuf sort_keys[2], sort_vals[2], sort_tmp;  // ray reordering (GKCU_SORT_RAYS)
+    size_t sort_tmp_bytes = 0;
     DevBuf pool_stack;  // k_trace_pool / k_trace_wpool: traversal stacks, [lane][block (, warp)][depth][slot]
     size_t pool_stack_stride = 0;  // uint2 entries per lane
     uint32_t* host_counts = nullptr;  // pinned, 64 words per lane
@@ -426,8 +432,14 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
         float3 origin = xyz(origin4);
         float3 ray_dir = pixel_ray_dir(C, x, y, R.w, R.h);
         Hit h;
-        trace_ray<false>(S.ts, origin, pixel_ray_dir(C, x, y, R.w, R.h, 0.5f), GK_EPS, GK_PRIMARY_T_MAX, h);
-        nprimary++;
+        if (R.vis) {  // FVisibilityBufferRayCasterV2::TracePrimaryRay, Shading.slang:348-349: the visibility buffer the raster pass wrote
+            const uint32_t v = R.vis[pixel];
+            h.inst = v ? ((v >> 17) & 0x7FFFu) - 1u : GK_NO_HIT;
+            h.prim = v & 0x1FFFFu;
+        } else {
+            trace_ray<false>(S.ts, origin, pixel_ray_dir(C, x, y, R.w, R.h, 0.5f), GK_EPS, GK_PRIMARY_T_MAX, h);
+            nprimary++;
+        }
         float4 zero = f4(0, 0, 0, 0);
         if (h.inst == GK_NO_HIT) {  // Shading.slang:1193-1201
             float4 sky = sky_color(S, ray_dir);
@@ -469,8 +481,14 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
                 if (ox != x || oy != y) {
                     float3 fdir = pixel_ray_dir(C, ox, oy, R.w, R.h);
                     Hit h2;
-                    trace_ray<false>(S.ts, origin, pixel_ray_dir(C, ox, oy, R.w, R.h, 0.5f), GK_EPS, GK_PRIMARY_T_MAX, h2);
-                    nprimary++;
+                    if (R.vis) {
+                        const uint32_t v = R.vis[(size_t)oy * R.w + ox];
+                        h2.inst = v ? ((v >> 17) & 0x7FFFu) - 1u : GK_NO_HIT;
+                        h2.prim = v & 0x1FFFFu;
+                    } else {
+                        trace_ray<false>(S.ts, origin, pixel_ray_dir(C, ox, oy, R.w, R.h, 0.5f), GK_EPS, GK_PRIMARY_T_MAX, h2);
+                        nprimary++;
+                    }
                     if (h2.inst != GK_NO_HIT) {
                         PrimVertex cand = get_material_dataV2(S, h2.inst, h2.prim, origin, fdir);
                         bool cancel = false;
@@ -572,6 +590,38 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
     if ((threadIdx.x & 31) == 0 && nprimary) atomicAdd(ray_counters + 0, (unsigned long long)nprimary);
 }
 
+// Ray reordering (GKCU_SORT_RAYS): key = Morton code of the origin's cell on a 2^bits grid over the TLAS root box, then 6 bits of direction
+// (octant + dominant axis + a half-space bit). The rays stay where they are; k_trace walks them through the sorted index, so hits land in
+// the slots the shade kernel expects and the result cannot depend on the order.
+GK_DEV unsigned long long spread3(uint32_t v) {  // 21 bits -> every third bit
+    unsigned long long x = v & 0x1FFFFFull;
+    x = (x | x << 32) & 0x1F00000000FFFFull;
+    x = (x | x << 16) & 0x1F0000FF0000FFull;
+    x = (x | x << 8) & 0x100F00F00F00F00Full;
+    x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__global__ void k_ray_keys(PathView V, int qi, size_t half, uint32_t nmax, float3 lo, float3 inv_extent, int bits, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmax) return;
+    unsigned long long key = ~0ull;
+    if (i < V.counts[qi]) {
+        const float4 o = V.ray_o[(size_t)qi * half + i], d = V.ray_d[(size_t)qi * half + i];
+        const float scale = (float)(1u << bits);
+        const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - lo.x) * inv_extent.x * scale, 0.0f), scale - 1.0f);
+        const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - lo.y) * inv_extent.y * scale, 0.0f), scale - 1.0f);
+        const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - lo.z) * inv_extent.z * scale, 0.0f), scale - 1.0f);
+        const unsigned long long m = spread3(cx) | spread3(cy) << 1 | spread3(cz) << 2;
+        const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+        const uint32_t major = ax >= ay && ax >= az ? 0u : (ay >= az ? 1u : 2u);
+        const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+        key = m << 5 | oct << 2 | major;
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+
 // Persistent-thread traversal: every lane owns one ray, and lanes whose ray has terminated pull the next ray from the queue
 // (one atomic per warp) as soon as the number of busy lanes drops below `refill_below`. VARIANT 5 (default): each iteration
 // the warp votes and executes only the step kind most lanes are waiting for (node walk, instance entry or triangle leaf);
@@ -608,6 +658,7 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
                 if (!busy) {
                     slot = base + __popc(idle & ((1u << lane) - 1u));
                     if (slot < n) {
+                        if (V.order) slot = __ldcs(V.order + slot);
                         const float4 o = __ldcs(ray_o + slot), d = __ldcs(ray_d + slot);  // streamed: keep L1 for nodes and stacks
                         trav_init<FMT>(T, world, ts, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), GK_EPS, GK_PT_MAX_TRACE_DISTANCE, (__ldcs(slot_pixel + slot) & 0x80000000u) != 0);
                         busy = true;
@@ -1378,6 +1429,7 @@ RTView make_rt_view(const Context& c) {
     R.w = t.w; R.h = t.h;
     R.single_diffuse = t.single_diffuse; R.single_specular = t.single_specular; R.albedo = t.albedo; R.normal = t.normal;
     R.objectid0 = t.objectid[t.cur]; R.primitiveid = t.primitiveid; R.motion = t.motion; R.prev_depth = t.prev_depth; R.moment = t.moment;
+    R.vis = nullptr;
     return R;
 }
 // Lane `lane` of the frame: its own pair of queues (capacity lane_cap each) and counters; the per-pixel state is shared.
@@ -1395,6 +1447,7 @@ PathView make_path_view(const Context& c, int lane = 0) {
     V.hit_tuv = b.hit_tuv.as<float4>() + h; V.hit_prim = b.hit_prim.as<uint32_t>() + h;
     V.counts = b.counts.as<uint32_t>() + (size_t)lane * 64;
     V.radiance = b.radiance.as<float4>(); V.direct = b.direct.as<float4>();
+    V.order = nullptr;
     return V;
 }
 
@@ -1416,6 +1469,12 @@ int path_resize(Context& c) {
               b.slot_pixel[0].reserve(m * 4) && b.slot_pixel[1].reserve(m * 4) && b.hit_tuv.reserve(m * 16) && b.hit_prim.reserve(m * 4) &&
               b.counts.reserve(4 * 64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16) &&
               b.pool_stack.reserve((size_t)b.lanes * c.sm_count * std::max<size_t>((size_t)GK_POOL_MINB * GK_POOL, (size_t)GK_WPOOL_MINB * 4 * GK_WPOOL) * GK_TRAV_STACK * sizeof(uint2));
+    if (c.sort_rays) {
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)b.lane_cap, 0, 64, c.stream);
+        b.sort_tmp_bytes = tmp;
+        ok = ok && b.sort_keys[0].reserve(m * 8) && b.sort_keys[1].reserve(m * 8) && b.sort_vals[0].reserve(m * 4) && b.sort_vals[1].reserve(m * 4) && b.sort_tmp.reserve(tmp);
+    }
     b.pool_stack_stride = (size_t)c.sm_count * std::max<size_t>((size_t)GK_POOL_MINB * GK_POOL, (size_t)GK_WPOOL_MINB * 4 * GK_WPOOL) * GK_TRAV_STACK;
     if (!ok) return 1;
     // ranks other than 0 never write the direct-term plane; keep it defined for a host that resolves on such a context
@@ -1428,7 +1487,7 @@ void path_release(Context& c) {
     if (!c.path) return;
     PathBuffers& b = *c.path;
     for (DevBuf* d : {&b.rng, &b.pos_mat, &b.nrm_flags, &b.dir_cnt, &b.ray_color, &b.final_color, &b.final_refl, &b.prim_pos_mat, &b.prim_nrm_cnt,
-                      &b.prim_albedo, &b.ray_o, &b.ray_d, &b.slot_pixel[0], &b.slot_pixel[1], &b.hit_tuv, &b.hit_prim, &b.counts, &b.radiance, &b.direct, &b.pool_stack})
+                      &b.prim_albedo, &b.ray_o, &b.ray_d, &b.slot_pixel[0], &b.slot_pixel[1], &b.hit_tuv, &b.hit_prim, &b.counts, &b.radiance, &b.direct, &b.pool_stack, &b.sort_keys[0], &b.sort_keys[1], &b.sort_vals[0], &b.sort_vals[1], &b.sort_tmp})
         d->release();
     if (b.host_counts) cudaFreeHost(b.host_counts);
     delete c.path;
@@ -1458,6 +1517,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     PathBuffers& b = *c.path;
     SceneView S = make_scene_view(c);
     RTView R = make_rt_view(c);
+    if (p.primary_visibility) R.vis = c.rt.minigbuffer;
     const int lanes = b.lanes;
     PathLanes L{};
     L.n = (uint32_t)lanes;
@@ -1512,6 +1572,23 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 cudaStream_t s2 = ls[l];
                 for (int w = 0; w < chunk; ++w) {
                     const uint32_t blocks = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 8u);
+                    PathView Vt = V;
+                    if (c.sort_rays) {
+                        const uint32_t nmax = bound[l];
+                        const float3 lo = make_float3(c.tlas.root_lo[0], c.tlas.root_lo[1], c.tlas.root_lo[2]);
+                        float3 ext = make_float3(c.sort_extent > 0 ? c.sort_extent : c.tlas.root_hi[0] - lo.x, c.sort_extent > 0 ? c.sort_extent : c.tlas.root_hi[1] - lo.y, c.sort_extent > 0 ? c.sort_extent : c.tlas.root_hi[2] - lo.z);
+                        float3 lo2 = lo;
+                        if (c.sort_extent > 0) lo2 = make_float3(-0.5f * c.sort_extent, -0.5f * c.sort_extent, -0.5f * c.sort_extent);
+                        const float3 inv = make_float3(1.0f / std::max(ext.x, 1e-20f), 1.0f / std::max(ext.y, 1e-20f), 1.0f / std::max(ext.z, 1e-20f));
+                        const int bits = std::max(1, std::min(19, c.sort_rays));
+                        unsigned long long *k0 = b.sort_keys[0].as<unsigned long long>() + (size_t)l * b.lane_cap, *k1 = b.sort_keys[1].as<unsigned long long>() + (size_t)l * b.lane_cap;
+                        uint32_t *v0 = b.sort_vals[0].as<uint32_t>() + (size_t)l * b.lane_cap, *v1 = b.sort_vals[1].as<uint32_t>() + (size_t)l * b.lane_cap;
+                        k_ray_keys<<<(nmax + 255) / 256, 256, 0, s2>>>(V, qi[l], half, nmax, lo2, inv, bits, k0, v0);
+                        size_t tmp = b.sort_tmp_bytes;
+                        GK_CUDA(cub::DeviceRadixSort::SortPairs(b.sort_tmp.p, tmp, k0, k1, v0, v1, (int)nmax, 0, 3 * bits + 5, s2));
+                        Vt.order = v1;
+                        c.launches += 2;
+                    }
                     cudaEventRecord(c.wev[l][3 * w], s2);
                     if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half);
                     else if (c.trace_variant == 0) {
@@ -1525,8 +1602,8 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                         k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride);
                     } else {
                         const uint32_t tb = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u);
-                        if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
-                        else k_trace<5, 4><<<tb, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                        if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below);
+                        else k_trace<5, 4><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below);
                     }
                     cudaEventRecord(c.wev[l][3 * w + 1], s2);
                     const uint32_t sb = (bound[l] + 127) / 128;

@@ -40,6 +40,11 @@ def lib():
         L.gkcu_create.argtypes = [C.c_int, C.POINTER(P)]
         L.gkcu_destroy.argtypes = [P]
         L.gkcu_resize.argtypes = [P, C.c_uint32, C.c_uint32]
+        L.gkcu_scene_upload_raster.argtypes = [P, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.gkcu_cull.argtypes = [P, C.POINTER(GkUniformBufferObject)]
+        L.gkcu_visibility_pass.argtypes = [P, C.POINTER(GkUniformBufferObject)]
+        L.gkcu_get_gpu_driven_stats.argtypes = [P, C.c_void_p]
+        L.gkcu_read_draw_commands.argtypes = [P, C.c_void_p, C.c_uint32]
         L.gkcu_bind_external_image.argtypes = [P, C.c_uint32, C.c_uint32, C.c_int, C.c_size_t, C.c_size_t, C.c_uint32]
         L.gkcu_unbind_external_image.argtypes = [P, C.c_uint32]
         L.gkcu_bind_external_semaphore.argtypes = [P, C.c_uint32, C.c_int]
@@ -133,9 +138,31 @@ class CudaPathTracingRenderer:
         mats, nm = scene.materials()
         _ck(lib().gkcu_update_materials(self._ctx, mats, nm))
         _ck(lib().gkcu_blas_build(self._ctx))
+        if hasattr(scene, "raster_buffers"):  # the buffers only the visibility pass reads (Scene.cpp:240-250)
+            provoke, reorders = scene.raster_buffers()
+            _ck(lib().gkcu_scene_upload_raster(self._ctx, provoke.ctypes.data, len(provoke), reorders.ctypes.data, len(reorders)))
         self.AfterUpdateScene(scene)
         if sky is not None:
             self.set_sky(0, sky)
+
+    # ---- visibility front end (VulkanBaseRenderer::PreRender: "gpu cull", "visibility pass")
+    def cull(self, ubo):
+        _ck(lib().gkcu_cull(self._ctx, C.byref(ubo)))
+
+    def visibility_pass(self, ubo):
+        _ck(lib().gkcu_visibility_pass(self._ctx, C.byref(ubo)))
+
+    def gpu_driven_stats(self):
+        from ._abi import GkGPUDrivenStat
+        st = GkGPUDrivenStat()
+        _ck(lib().gkcu_get_gpu_driven_stats(self._ctx, C.byref(st)))
+        return {n: getattr(st, n) for n in ("ProcessedCount", "VisibleCount", "CulledCount", "TriangleCount", "CulledTriangleCount")}
+
+    def draw_commands(self, count):
+        from ._abi import DRAW_CMD_DTYPE
+        out = np.zeros(count, DRAW_CMD_DTYPE)
+        _ck(lib().gkcu_read_draw_commands(self._ctx, out.ctypes.data, count))
+        return out
 
     def AfterUpdateScene(self, scene):
         nodes, nn = scene.nodes()

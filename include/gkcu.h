@@ -252,8 +252,14 @@ typedef struct GkcuFrameParams {
     uint32_t spp_world;
     uint32_t tracer;            /* 0 = wavefront (default), 1 = megakernel (one thread per pixel) */
     uint32_t skip_post;         /* 1 = stop after the rt pass (radiance sums left un-normalised for a reduce) */
-    uint32_t reserved;
+    uint32_t primary_visibility; /* 0 = a ray through the pixel centre (default; no size limits), 1 = the reference's front end: gpu cull +
+                                  * rasterised visibility buffer (VulkanBaseRenderer.cpp:597-725), read like FVisibilityBufferRayCasterV2 */
 } GkcuFrameParams;
+
+/* GPUDrivenStat (assets/shaders/common/BasicTypes.slang:13-20): counters of the gpu cull, read back by Scene::UpdateNodes (Scene.cpp:412-419) */
+typedef struct GkGPUDrivenStat {
+    uint32_t ProcessedCount, VisibleCount, CulledCount, TriangleCount, CulledTriangleCount, pad[3];
+} GkGPUDrivenStat;
 
 typedef struct GkcuTimings {   /* names follow the reference's GPU timer scopes (PathTracingRenderer.cpp:111,126,138,160) */
     float tlas_update_ms;      /* "TLAS Update" (RayTraceBaseRenderer.cpp:209) */
@@ -411,6 +417,22 @@ int gkcu_run_post(GkcuContext* ctx, const GkUniformBufferObject* ubo, const Gkcu
 int gkcu_debug_read(GkcuContext* ctx, uint32_t what, size_t offset, void* dst, size_t bytes);
 int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity);
 int gkcu_synchronize(GkcuContext* ctx);
+
+
+/* ---------------------------------------------------------------------- visibility front end
+ * gkcu_scene_upload_raster: the two buffers of Scene::RebuildMeshBuffer only the raster pass reads - the provoking index buffer
+ *   (GPUScene.Indices of the draw, src/Assets/Scene.cpp:247) and GPUScene.Reorders (:240-248); ModelData.reorderOffset points into the latter.
+ * gkcu_cull: "gpu cull" (assets/shaders/Task.GpuCull.comp.slang:199-227, VulkanBaseRenderer.cpp:603-647): one VkDrawIndexedIndirectCommand
+ *   per NodeProxy from a frustum test and an occlusion test against last frame's RT_PREV_DEPTHBUFFER, plus the GPUDrivenStat counters.
+ * gkcu_visibility_pass: "visibility pass" (Rast.VisibilityPass.{vert,frag}.slang, VulkanBaseRenderer.cpp:673-724): RT_MINIGBUFFER =
+ *   ((node + 1) & 0x7FFF) << 17 | (triangle & 0x1FFFF) of the nearest front-facing triangle at every pixel centre (software rasteriser
+ *   with the Vulkan rules: near clip, 8 sub-pixel bits, back-face culling, top-left rule, depth LESS). At most 32 767 proxies.
+ * gkcu_render_frame runs both itself when params->primary_visibility = 1. */
+int gkcu_scene_upload_raster(GkcuContext* ctx, const uint32_t* raster_indices, uint32_t index_count, const uint32_t* reorders, uint32_t reorder_count);
+int gkcu_cull(GkcuContext* ctx, const GkUniformBufferObject* ubo);
+int gkcu_visibility_pass(GkcuContext* ctx, const GkUniformBufferObject* ubo);
+int gkcu_get_gpu_driven_stats(GkcuContext* ctx, GkGPUDrivenStat* out);
+int gkcu_read_draw_commands(GkcuContext* ctx, void* dst, uint32_t count); /* count x VkDrawIndexedIndirectCommand (20 bytes) */
 
 /* ---------------------------------------------------------------------- zero-copy present
  * The engine can create a render image whose memory is exportable as an OPAQUE_FD (RenderImage(..., external = true),

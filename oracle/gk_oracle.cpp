@@ -467,6 +467,7 @@ struct GkoScene {
     std::vector<GkPageIndex> pages;
     std::vector<GkLightObject> lights;
     std::vector<GkSphericalHarmonics> sky_sh;
+    std::vector<uint32_t> raster_indices, reorders;  // the raster pass's index buffer and GPUScene.Reorders (Scene.cpp:240-250)
 #ifdef GKO_TINYBVH
     tinybvh::BVH ttlas;
     std::vector<tinybvh::BLASInstance> tinst;
@@ -1021,6 +1022,8 @@ struct GkoFrame {
     std::vector<float> motion;  // RG32F
     std::vector<float> prev_depth;
     std::vector<uint16_t> moment;
+    std::vector<uint32_t> vis;    // RT_MINIGBUFFER: the rasterised visibility buffer (primary_visibility = 1)
+    bool use_vis = false;
     std::vector<float> radiance;  // multi-GPU split: FinalColor | FinalReflection | direct planes (float4 per pixel)
     std::atomic<uint64_t> primary_rays{0}, closest_rays{0}, any_rays{0};
     double rt_seconds = 0;
@@ -1127,6 +1130,12 @@ struct Renderer {  // FPathTracingRendererV2, Shading.slang:995-1261, configured
     // is the closest hit of the ray through the pixel centre; the shading ray that TracePrimaryRay then intersects with that triangle's
     // plane stays the pixel-corner ray of the text (:350-356). Returns (node index + 1, primitive) in the vis-buffer convention, 0 = none.
     void CastVisibility(int x, int y, f3 origin, uint32_t& node1, uint32_t& prim) {
+        if (F.use_vis) {  // Shading.slang:348-349: unpack the visibility buffer the raster pass wrote
+            const uint32_t v = F.vis[(size_t)y * F.w + x];
+            node1 = (v >> 17) & 0x7FFFu;
+            prim = v & 0x1FFFFu;
+            return;
+        }
         f2 uv = f2{((float)x + 0.5f) / (float)F.w * 2.0f - 1.0f, ((float)y + 0.5f) / (float)F.h * 2.0f - 1.0f};
         f4 target = mul(Camera.ProjectionInverse, F4(uv.x, uv.y, 1, 1));
         f3 tn = normalize(xyz(target));
@@ -1778,6 +1787,188 @@ void gko_cast_visibility(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t
     gko_cast_visibility_rows(s, ubo, w, h, 0, h, 1, packed);
 }
 
+
+// ------------------------------------------------------------------------------------------------- visibility front end
+// "gpu cull": Task.GpuCull.comp.slang:199-227 with IsAABBInFrustum (:127-197) and IsOccludedVolume (:56-115), one NodeProxy at a time.
+// "visibility pass": Rast.VisibilityPass.{vert,frag}.slang under the Vulkan rasterisation rules (the fixed-function unit of the reference): near clip,
+// perspective divide, viewport transform, 8 sub-pixel bits, back faces culled by the sign of the area (cull BACK, front face counter-clockwise,
+// PipelineCommon/CommonComputePipeline.cpp:201-202), coverage at pixel centres with the top-left rule, depth z/w interpolated in screen space, LESS (:221),
+// depth ties to the smaller id. Restated independently of csrc/gk_raster.cu from the same specification; both must agree bit for bit.
+namespace {
+struct DrawCmdO { uint32_t indexCount, instanceCount, firstIndex; int32_t vertexOffset; uint32_t firstInstance; };
+
+GkMat4 MatMul(const GkMat4& a, const GkMat4& b) {
+    GkMat4 r;
+    for (int c = 0; c < 4; ++c)
+        for (int row = 0; row < 4; ++row)
+            r.m[c][row] = a.m[0][row] * b.m[c][0] + a.m[1][row] * b.m[c][1] + a.m[2][row] * b.m[c][2] + a.m[3][row] * b.m[c][3];
+    return r;
+}
+
+bool AABBInFrustum(f3 mn, f3 mx, const GkMat4& wvp) {
+    f4 clip[8];
+    for (int i = 0; i < 8; ++i) clip[i] = mul(wvp, F4(i & 1 ? mx.x : mn.x, i & 2 ? mx.y : mn.y, i & 4 ? mx.z : mn.z, 1.0f));
+    auto all_outside = [&](auto inside) {
+        for (int i = 0; i < 8; ++i)
+            if (inside(clip[i])) return false;
+        return true;
+    };
+    if (all_outside([](f4 c) { return c.x >= -c.w; })) return false;
+    if (all_outside([](f4 c) { return c.x <= c.w; })) return false;
+    if (all_outside([](f4 c) { return c.y >= -c.w; })) return false;
+    if (all_outside([](f4 c) { return c.y <= c.w; })) return false;
+    if (all_outside([](f4 c) { return c.z >= -c.w; })) return false;
+    if (all_outside([](f4 c) { return c.z <= c.w; })) return false;
+    return true;
+}
+
+bool OccludedVolume(f3 mn, f3 mx, const GkMat4& wvp, const float* prev_depth, uint32_t w, uint32_t h) {
+    const int GRID = 6;
+    const float GRID_M1 = GRID - 1;
+    for (int x = 0; x < GRID; x++)
+        for (int y = 0; y < GRID; y++)
+            for (int z = 0; z < GRID; z++) {
+                const f3 g = F3(mn.x + (mx.x - mn.x) * (float(x) / GRID_M1), mn.y + (mx.y - mn.y) * (float(y) / GRID_M1), mn.z + (mx.z - mn.z) * (float(z) / GRID_M1));
+                const f4 c = mul(wvp, F4(g.x, g.y, g.z, 1.0f));
+                const f3 ndc = F3(c.x / c.w, c.y / c.w, c.z / c.w);
+                if (fabsf(ndc.x) > 1.0f || fabsf(ndc.y) > 1.0f || ndc.z < 0.0f || ndc.z > 1.0f) return false;
+                const float u = ndc.x * 0.5f + 0.5f, v = ndc.y * 0.5f + 0.5f;
+                const int px = (int)(u * float(w)), py = (int)(v * float(h));
+                if (px < 0 || px >= (int)w || py < 0 || py >= (int)h) return false;
+                if (prev_depth[(size_t)py * w + px] > ndc.z - 0.0001f) return false;
+            }
+    return true;
+}
+
+struct Frag { uint64_t key; };
+
+int64_t SnapFixed(float v) {
+    const float s = floorf(v * 256.0f + 0.5f);
+    const float lim = 1073741824.0f;  // 2^30
+    if (!(s > -lim)) return -(int64_t(1) << 30);
+    if (!(s < lim)) return int64_t(1) << 30;
+    return (int64_t)s;
+}
+int64_t CeilDiv256(int64_t a) { return a >= 0 ? (a + 255) / 256 : -((-a) / 256); }
+int64_t FloorDiv256(int64_t a) { return a >= 0 ? a / 256 : -((-a + 255) / 256); }
+
+// one triangle given in clip space, all z >= 0
+void RasterClipped(const f4* c, uint32_t w, uint32_t h, uint32_t id, std::vector<uint64_t>& keys) {
+    int64_t X[3], Y[3];
+    float Z[3];
+    for (int k = 0; k < 3; ++k) {
+        const float nx = c[k].x / c[k].w, ny = c[k].y / c[k].w;
+        Z[k] = c[k].z / c[k].w;
+        X[k] = SnapFixed((nx + 1.0f) * ((float)w * 0.5f));
+        Y[k] = SnapFixed((ny + 1.0f) * ((float)h * 0.5f));
+    }
+    const int64_t area2 = (X[1] - X[0]) * (Y[2] - Y[0]) - (X[2] - X[0]) * (Y[1] - Y[0]);
+    if (area2 >= 0) return;  // back-facing (or degenerate): the Vulkan area -area2 / 2 must be positive for a counter-clockwise front face
+    std::swap(X[1], X[2]); std::swap(Y[1], Y[2]); std::swap(Z[1], Z[2]);  // edge functions positive inside
+    const int64_t x0 = std::max<int64_t>(0, CeilDiv256(std::min({X[0], X[1], X[2]}) - 128)), x1 = std::min<int64_t>((int64_t)w - 1, FloorDiv256(std::max({X[0], X[1], X[2]}) - 128));
+    const int64_t y0 = std::max<int64_t>(0, CeilDiv256(std::min({Y[0], Y[1], Y[2]}) - 128)), y1 = std::min<int64_t>((int64_t)h - 1, FloorDiv256(std::max({Y[0], Y[1], Y[2]}) - 128));
+    for (int64_t py = y0; py <= y1; ++py)
+        for (int64_t px = x0; px <= x1; ++px) {
+            const int64_t Px = px * 256 + 128, Py = py * 256 + 128;
+            int64_t E[3];
+            bool inside = true;
+            for (int i = 0; i < 3 && inside; ++i) {
+                const int a = (i + 1) % 3, b = (i + 2) % 3;
+                const int64_t dx = X[b] - X[a], dy = Y[b] - Y[a];
+                E[i] = dx * (Py - Y[a]) - dy * (Px - X[a]);
+                const bool topleft = dy < 0 || (dy == 0 && dx > 0);
+                if (E[i] < 0 || (E[i] == 0 && !topleft)) inside = false;
+            }
+            if (!inside) continue;
+            const double area = (double)(E[0] + E[1] + E[2]);
+            const double zs = ((double)E[0] * (double)Z[0] + (double)E[1] * (double)Z[1]) + (double)E[2] * (double)Z[2];
+            const float z = (float)(zs / area);
+            if (!(z >= 0.0f && z < 1.0f)) continue;
+            uint32_t zb;
+            std::memcpy(&zb, &z, 4);
+            const uint64_t key = ((uint64_t)zb << 32) | id;
+            uint64_t& dst = keys[(size_t)py * w + px];
+            if (key < dst) dst = key;
+        }
+}
+}  // namespace
+
+void gko_set_raster_buffers(GkoScene* s, const uint32_t* raster_indices, uint32_t index_count, const uint32_t* reorders, uint32_t reorder_count) {
+    s->raster_indices.assign(raster_indices, raster_indices + index_count);
+    s->reorders.assign(reorders, reorders + reorder_count);
+}
+
+// cmds: count x VkDrawIndexedIndirectCommand (5 words), stats: GPUDrivenStat (8 words)
+void gko_cull(GkoScene* s, const GkUniformBufferObject* ubo, const float* prev_depth, uint32_t w, uint32_t h, uint32_t* cmds, uint32_t* stats) {
+    GkGPUDrivenStat st{};
+    for (size_t i = 0; i < s->nodes.size(); ++i) {
+        const GkNodeProxy& node = s->nodes[i];
+        const GkModelData& model = s->offsets[node.modelId];
+        const GkMat4 mvp = MatMul(ubo->ViewProjection, node.worldTS);
+        const f3 mn = F3(model.localAabbMin.x, model.localAabbMin.y, model.localAabbMin.z), mx = F3(model.localAabbMax.x, model.localAabbMax.y, model.localAabbMax.z);
+        bool shouldDraw = node.visible > 0 && AABBInFrustum(mn, mx, mvp);
+        if (shouldDraw) {
+            st.ProcessedCount += 1;
+            st.TriangleCount += model.indexCount / 3;
+            if (OccludedVolume(mn, mx, mvp, prev_depth, w, h)) {
+                st.CulledCount += 1;
+                st.CulledTriangleCount += model.indexCount / 3;
+                shouldDraw = false;
+            }
+        }
+        DrawCmdO c;
+        c.instanceCount = shouldDraw ? 1 : 0;
+        c.firstInstance = shouldDraw ? (uint32_t)i : 0;
+        c.indexCount = shouldDraw ? model.indexCount : 0;
+        c.firstIndex = shouldDraw ? model.indexOffset : 0;
+        c.vertexOffset = shouldDraw ? (int32_t)model.reorderOffset : 0;
+        std::memcpy(cmds + i * 5, &c, 20);
+    }
+    std::memcpy(stats, &st, sizeof(st));
+}
+
+void gko_visibility_pass(GkoScene* s, const GkUniformBufferObject* ubo, const uint32_t* cmds, uint32_t count, uint32_t w, uint32_t h, uint32_t* vis) {
+    std::vector<uint64_t> keys((size_t)w * h, (uint64_t)0x3F800000u << 32);
+    for (uint32_t b = 0; b < count; ++b) {
+        DrawCmdO cmd;
+        std::memcpy(&cmd, cmds + (size_t)b * 5, 20);
+        if (cmd.instanceCount == 0 || cmd.indexCount == 0) continue;
+        const GkMat4 mvp = MatMul(ubo->ViewProjection, s->nodes[cmd.firstInstance].worldTS);
+        const uint32_t instanceIdx = cmd.firstInstance + 1;
+        for (uint32_t t = 0; t < cmd.indexCount / 3; ++t) {
+            f4 c[3];
+            uint32_t triangleIdx = 0;
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t vertexIndex = s->raster_indices[cmd.firstIndex + 3 * t + k] + (uint32_t)cmd.vertexOffset;
+                if (k == 0) triangleIdx = vertexIndex - (uint32_t)cmd.vertexOffset;
+                const uint32_t vi = s->reorders[vertexIndex];
+                c[k] = mul(mvp, F4(h2f(s->simple[(size_t)vi * 4]), h2f(s->simple[(size_t)vi * 4 + 1]), h2f(s->simple[(size_t)vi * 4 + 2]), 1.0f));
+            }
+            const uint32_t id = ((instanceIdx & 0x7FFFu) << 17) | (triangleIdx & 0x1FFFFu);
+            const bool in[3] = {c[0].z >= 0.0f, c[1].z >= 0.0f, c[2].z >= 0.0f};
+            if (in[0] && in[1] && in[2]) { RasterClipped(c, w, h, id, keys); continue; }
+            if (!in[0] && !in[1] && !in[2]) continue;
+            f4 poly[4];
+            int n = 0;
+            for (int k = 0; k < 3; ++k) {  // Sutherland-Hodgman against z >= 0, in vertex order
+                const f4 a = c[k], bb = c[(k + 1) % 3];
+                if (in[k]) poly[n++] = a;
+                if (in[k] != in[(k + 1) % 3]) {
+                    const float tt = a.z / (a.z - bb.z);
+                    poly[n++] = F4(a.x + (bb.x - a.x) * tt, a.y + (bb.y - a.y) * tt, 0.0f, a.w + (bb.w - a.w) * tt);
+                }
+            }
+            const f4 t0[3] = {poly[0], poly[1], poly[2]};
+            RasterClipped(t0, w, h, id, keys);
+            if (n == 4) {
+                const f4 t1[3] = {poly[0], poly[2], poly[3]};
+                RasterClipped(t1, w, h, id, keys);
+            }
+        }
+    }
+    for (size_t i = 0; i < keys.size(); ++i) vis[i] = (uint32_t)(keys[i] & 0xFFFFFFFFull);
+}
+
 GkoFrame* gko_frame_create(uint32_t w, uint32_t h) {
     GkoFrame* f = new GkoFrame();
     f->w = w;
@@ -1792,6 +1983,7 @@ GkoFrame* gko_frame_create(uint32_t w, uint32_t h) {
     f->motion.assign(n * 2, 0.f);
     f->prev_depth.assign(n, 0.f);
     f->moment.assign(n, 0);
+    f->vis.assign(n, 0);
     f->radiance.assign(n * 12, 0.f);
     return f;
 }
@@ -1818,6 +2010,12 @@ int gko_render_frame(GkoScene* s, GkoFrame* f, const GkUniformBufferObject* ubo,
     f->primary_rays = 0;
     f->closest_rays = 0;
     f->any_rays = 0;
+    f->use_vis = params->primary_visibility != 0;
+    if (f->use_vis) {  // VulkanBaseRenderer::PreRender: "gpu cull" against last frame's depth, then the "visibility pass" (whole image)
+        std::vector<uint32_t> cmds(std::max<size_t>(1, s->nodes.size()) * 5), stats(8);
+        gko_cull(s, ubo, f->prev_depth.data(), f->w, f->h, cmds.data(), stats.data());
+        gko_visibility_pass(s, ubo, cmds.data(), (uint32_t)s->nodes.size(), f->w, f->h, f->vis.data());
+    }
     auto t0 = std::chrono::steady_clock::now();
     parallel_pixels(y0, y1, f->w, threads, [&](int x, int y) { RenderPixel(*s, *f, *ubo, *params, x, y); });
     f->rt_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1845,6 +2043,7 @@ void* gko_image(GkoFrame* f, uint32_t rt, size_t* bytes) {
         case GK_RT_NORMAL: return ret16(f->normal);
         case GK_RT_DENOISED: return ret16(f->denoised);
         case GK_RT_MOTIONMOMENT: return ret16(f->moment);
+        case GK_RT_MINIGBUFFER: return ret32(f->vis);
         case GK_RT_OBJEDCTID_0: return ret32(f->objectid0);
         case GK_RT_OBJEDCTID_1: return ret32(f->objectid1);
         case GK_RT_EXT_PRIMITIVEID: return ret32(f->primitiveid);

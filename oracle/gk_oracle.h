@@ -131,6 +131,10 @@ void gko_instance_w2o(GkoScene* s, uint32_t inst, float out[12]); /* world-to-ob
 void gko_sample_texture(GkoScene* s, uint32_t id, float u, float v, float out[4]);
 /* packed[y*w+x] = ((node + 1) << 17) | primitive, 0 = no geometry: the RT_MINIGBUFFER texel format (Shading.slang:348-349) */
 void gko_cast_visibility(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t* packed);
+/* the visibility front end (Task.GpuCull.comp.slang, Rast.VisibilityPass.*.slang): cull -> draw commands + counters, software raster -> RT_MINIGBUFFER */
+void gko_set_raster_buffers(GkoScene* s, const uint32_t* raster_indices, uint32_t index_count, const uint32_t* reorders, uint32_t reorder_count);
+void gko_cull(GkoScene* s, const GkUniformBufferObject* ubo, const float* prev_depth, uint32_t w, uint32_t h, uint32_t* cmds, uint32_t* stats);
+void gko_visibility_pass(GkoScene* s, const GkUniformBufferObject* ubo, const uint32_t* cmds, uint32_t count, uint32_t w, uint32_t h, uint32_t* vis);
 /* rows [y0, y1) only, on `threads` threads (0 = all cores) */
 void gko_cast_visibility_rows(GkoScene* s, const GkUniformBufferObject* ubo, uint32_t w, uint32_t h, uint32_t y0, uint32_t y1, int threads, uint32_t* packed);
 

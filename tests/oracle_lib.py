@@ -39,6 +39,9 @@ def load(path=NATIVE):
     L.gko_pack_rgb10a2.argtypes = [C.POINTER(C.c_float * 4)]
     L.gko_unpack_rgb10a2.argtypes = [C.c_uint32, C.POINTER(C.c_float * 4)]
     L.gko_sample_ibl_rough.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float * 3), C.c_float, C.POINTER(C.c_float * 4)]
+    L.gko_set_raster_buffers.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.gko_cull.argtypes = [C.c_void_p, C.POINTER(GkUniformBufferObject), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.gko_visibility_pass.argtypes = [C.c_void_p, C.POINTER(GkUniformBufferObject), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     L.gko_intersector_name.restype = C.c_char_p
     L.gko_frame_create.restype = C.c_void_p
     L.gko_frame_create.argtypes = [C.c_uint32, C.c_uint32]
@@ -82,6 +85,9 @@ class OracleScene:
         mats, nm = scene.materials()
         self.L.gko_update_materials(self._h, mats, nm)
         self.update_nodes(scene)
+        if hasattr(scene, "raster_buffers"):
+            provoke, reorders = scene.raster_buffers()
+            self.L.gko_set_raster_buffers(self._h, provoke.ctypes.data, len(provoke), reorders.ctypes.data, len(reorders))
         if sky is not None:
             self.set_sky(0, sky)
 
@@ -93,6 +99,25 @@ class OracleScene:
     def update_nodes(self, scene):
         nodes, nn = scene.nodes()
         self.L.gko_update_nodes(self._h, nodes, nn)
+        self._node_count = nn
+
+    # ---- visibility front end
+    def cull(self, ubo, prev_depth):
+        """(draw commands, GPUDrivenStat dict) of Task.GpuCull against the depth image `prev_depth` (H, W) float32."""
+        from gknextengine_b200._abi import DRAW_CMD_DTYPE
+        prev_depth = np.ascontiguousarray(prev_depth, dtype=np.float32)
+        cmds = np.zeros(max(1, self._node_count), DRAW_CMD_DTYPE)
+        stats = np.zeros(8, np.uint32)
+        self.L.gko_cull(self._h, C.byref(ubo), prev_depth.ctypes.data, prev_depth.shape[1], prev_depth.shape[0], cmds.ctypes.data, stats.ctypes.data)
+        names = ("ProcessedCount", "VisibleCount", "CulledCount", "TriangleCount", "CulledTriangleCount")
+        return cmds[:self._node_count], {n: int(stats[i]) for i, n in enumerate(names)}
+
+    def visibility_pass(self, ubo, cmds, width, height):
+        """RT_MINIGBUFFER (H, W) uint32 of the software raster of the draw commands."""
+        cmds = np.ascontiguousarray(cmds)
+        vis = np.zeros((height, width), np.uint32)
+        self.L.gko_visibility_pass(self._h, C.byref(ubo), cmds.ctypes.data, len(cmds), width, height, vis.ctypes.data)
+        return vis
 
     def set_sky(self, idx, rgba):
         rgba = np.ascontiguousarray(rgba, dtype=np.float32)
