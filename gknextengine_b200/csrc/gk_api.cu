@@ -130,10 +130,13 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
         for (auto& e : l) cudaEventCreate(&e);
     for (auto& l : c.lane_ev)
         for (auto& e : l) cudaEventCreate(&e);
+    for (auto& l : c.pev)
+        for (auto& e : l) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (const char* e = getenv("GKCU_KERNEL_TIMING")) c.kernel_timing = atoi(e) != 0;
     for (auto& st : c.lane_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     if (const char* e = getenv("GKCU_LANES")) c.lanes = std::max(1, std::min(4, atoi(e)));
     if (const char* e = getenv("GKCU_TAIL_DIV")) c.tail_div = std::max(1, std::min(65536, atoi(e)));
-    if (const char* e = getenv("GKCU_WAVE_CHUNK")) c.wave_chunk = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("GKCU_WAVE_CHUNK")) c.wave_chunk = std::max(1, std::min(7, atoi(e)));
     if (!c.ubo.reserve(sizeof(GkUniformBufferObject))) { delete ctx; return 1; }
     *out_ctx = ctx;
     return 0;
@@ -168,6 +171,9 @@ int gkcu_destroy(GkcuContext* ctx) {
     for (auto& e : c.kev)
         if (e) cudaEventDestroy(e);
     for (auto& l : c.wev)
+        for (auto& e : l)
+            if (e) cudaEventDestroy(e);
+    for (auto& l : c.pev)
         for (auto& e : l)
             if (e) cudaEventDestroy(e);
     for (auto& l : c.lane_ev)
@@ -749,6 +755,12 @@ int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity) {
         ext[2 + 2 * m] = c.blas[m].leaf_base;
         ext[3 + 2 * m] = c.blas[m].leaf_count;
     }
+    return 0;
+}
+
+int gkcu_set_kernel_timing(GkcuContext* ctx, uint32_t enabled) {
+    CTX_OR_FAIL(ctx);
+    c.kernel_timing = enabled ? 1 : 0;
     return 0;
 }
 

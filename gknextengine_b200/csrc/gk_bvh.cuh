@@ -66,6 +66,9 @@ static_assert(sizeof(InstanceRec) == 64, "InstanceRec must be 64 bytes");
 #ifndef GK_PUSH_ORDERED
 #define GK_PUSH_ORDERED 1
 #endif
+#ifndef GK_NODE_BF
+#define GK_NODE_BF 1  // Node4 node step: branch-free ordering and pushes (0: the compare-and-push ladder, for A/B)
+#endif
 
 struct TraceScene {
     const Node4* tlas;    // Node4 or Node8 array (both 128 B per node), see fmt
@@ -148,6 +151,7 @@ GK_DEV float3 xform_vec(const float* m, float3 p) {
 // Where a traversal keeps its world-space ray while it is inside an instance: registers for the simple per-ray loop,
 // shared memory for k_trace (nine registers fewer per lane; the values are only touched when an instance is entered or left).
 struct WorldRegs {
+    static constexpr bool kKeepsTlasSpace = false;
     float3 o_, d_, widir_;
     GK_DEV void set(float3 o, float3 d, float3 widir) { o_ = o; d_ = d; widir_ = widir; }
     GK_DEV float3 o() const { return o_; }
@@ -156,6 +160,7 @@ struct WorldRegs {
 };
 template <int STRIDE>
 struct WorldSmem {
+    static constexpr bool kKeepsTlasSpace = false;
     float* p;  // p[k * STRIDE], k = 0..8, one column per thread
     GK_DEV void set(float3 o, float3 d, float3 widir) {
         p[0] = o.x; p[STRIDE] = o.y; p[2 * STRIDE] = o.z;
@@ -166,6 +171,34 @@ struct WorldSmem {
     GK_DEV float3 d() const { return f3(p[3 * STRIDE], p[4 * STRIDE], p[5 * STRIDE]); }
     GK_DEV float3 widir() const { return f3(p[6 * STRIDE], p[7 * STRIDE], p[8 * STRIDE]); }
 };
+// k_trace<5, 4>: sixteen words per thread - the world-space ray and, next to it, the Node4 slab constants of the TLAS space
+// (padded offsets and the sign mask), so that leaving an instance is ten shared-memory loads instead of recomputing set_space
+// with three of 32 lanes active (6 % of the kernel's warp instructions, profiles/r02_base_k_trace.txt).
+#ifndef GK_EXIT_SMEM
+#define GK_EXIT_SMEM 1
+#endif
+template <int STRIDE>
+struct WorldSmemX {
+    static constexpr bool kKeepsTlasSpace = GK_EXIT_SMEM != 0;
+    float* p;  // p[k * STRIDE], k = 0..15
+    GK_DEV void set(float3 o, float3 d, float3 widir) {
+        p[0] = o.x; p[STRIDE] = o.y; p[2 * STRIDE] = o.z;
+        p[3 * STRIDE] = d.x; p[4 * STRIDE] = d.y; p[5 * STRIDE] = d.z;
+        p[6 * STRIDE] = widir.x; p[7 * STRIDE] = widir.y; p[8 * STRIDE] = widir.z;
+    }
+    GK_DEV float3 o() const { return f3(p[0], p[STRIDE], p[2 * STRIDE]); }
+    GK_DEV float3 d() const { return f3(p[3 * STRIDE], p[4 * STRIDE], p[5 * STRIDE]); }
+    GK_DEV float3 widir() const { return f3(p[6 * STRIDE], p[7 * STRIDE], p[8 * STRIDE]); }
+    GK_DEV void keep(float3 adjn, float3 adjf, uint32_t sgn) {
+        p[9 * STRIDE] = adjn.x; p[10 * STRIDE] = adjn.y; p[11 * STRIDE] = adjn.z;
+        p[12 * STRIDE] = adjf.x; p[13 * STRIDE] = adjf.y; p[14 * STRIDE] = adjf.z;
+        p[15 * STRIDE] = __uint_as_float(sgn);
+    }
+    GK_DEV float3 adjn() const { return f3(p[9 * STRIDE], p[10 * STRIDE], p[11 * STRIDE]); }
+    GK_DEV float3 adjf() const { return f3(p[12 * STRIDE], p[13 * STRIDE], p[14 * STRIDE]); }
+    GK_DEV uint32_t sgn() const { return __float_as_uint(p[15 * STRIDE]); }
+};
+
 
 // Traversal stack: a per-thread array in local memory, entries are (node reference, entry distance). Keeping the top levels
 // in shared memory instead was measured and is slower (k_trace is sensitive to L1 capacity and the carve-out costs more than
@@ -174,6 +207,7 @@ struct LocalStack {
     uint2 e[GK_TRAV_STACK];
     GK_DEV void push(int& sp, uint2 v) { e[sp++] = v; }
     GK_DEV uint2 pop(int& sp) { return e[--sp]; }
+    GK_DEV void put(int at, uint2 v) { e[at] = v; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -234,6 +268,7 @@ GK_DEV void trav_init(Trav& T, W& world, const TraceScene& S, float3 o, float3 d
     const float3 idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
     world.set(o, d, idir);
     set_space<FMT>(T, o, idir);
+    if constexpr (W::kKeepsTlasSpace && FMT == 4) world.keep(T.adjn, T.adjf, T.sgn);
     T.tmin = tmin; T.tmax = tmax;
     T.best.t = tmax; T.best.u = 0.0f; T.best.v = 0.0f; T.best.inst = GK_NO_HIT; T.best.prim = 0;
     T.sh.kx = T.sh.ky = T.sh.kz = 0;
@@ -260,7 +295,11 @@ template <int FMT, class W, class St>
 GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
     for (;;) {
         if (T.cur_inst != GK_NO_HIT && T.sp == T.sp_inst) {
-            set_space<FMT>(T, world.o(), world.widir());
+            if constexpr (W::kKeepsTlasSpace && FMT == 4) {  // T.ro is not read in world space (Node4 slabs use adjn / adjf, triangles live in object space)
+                T.idir = world.widir(); T.adjn = world.adjn(); T.adjf = world.adjf(); T.sgn = world.sgn();
+            } else {
+                set_space<FMT>(T, world.o(), world.widir());
+            }
             T.nodes = reinterpret_cast<const uint4*>(S.tlas);
             if (FMT == 8) T.leaf = S.tlas_leaf;
             T.cur_inst = GK_NO_HIT;
@@ -340,6 +379,36 @@ GK_DEV bool trav_node_core4(Trav& T, St& stack) {
     const uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
     GK_STAT(T, T.cur_inst == GK_NO_HIT ? 0 : 1, 1);
     GK_STAT(T, 2, (tn[0] < inf) + (tn[1] < inf) + (tn[2] < inf) + (tn[3] < inf));
+#if GK_NODE_BF
+    {
+        // Branch-free ordering: every hit child gets its rank among the hit children from six comparisons of distinct keys (entry
+        // distance, slot index in the two lowest mantissa bits); rank 0 is visited next, rank r > 0 is stored at stack position
+        // sp + nhit - 1 - r with a predicated store, i.e. the stack holds them far to near. All lanes of the node step run the same
+        // ~45 instructions; the compare-and-push ladder this replaces ran its pushes with 4-5 of 32 lanes (24 % of the kernel's warp
+        // instructions, profiles/r02_base_k_trace.txt). The stored entry distance is the key with the slot bits cleared: rounded
+        // down, so the cull at pop time stays conservative.
+        const uint32_t kInf = 0x7F800000u;
+        uint32_t key[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            key[c] = tn[c] < inf ? ((__float_as_uint(fmaxf(tn[c], 0.0f)) & ~3u) | (uint32_t)c) : (kInf | (uint32_t)c);
+        const int p01 = key[0] < key[1], p02 = key[0] < key[2], p03 = key[0] < key[3], p12 = key[1] < key[2], p13 = key[1] < key[3], p23 = key[2] < key[3];
+        const int r[4] = {3 - p01 - p02 - p03, p01 + 2 - p12 - p13, p02 + p12 + 1 - p23, p03 + p13 + p23};
+        const int nhit = (key[0] < kInf) + (key[1] < kInf) + (key[2] < kInf) + (key[3] < kInf);
+        if (nhit == 0) return false;
+        const int top = T.sp + nhit - 1;
+        uint32_t next = ref[3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (key[c] < kInf && r[c] > 0) stack.put(top - r[c], make_uint2(ref[c], key[c] & ~3u));
+            if (c < 3 && r[c] == 0) next = ref[c];
+        }
+        GK_STAT(T, 3, nhit - 1);
+        T.sp = top;
+        T.cur = next;
+        return true;
+    }
+#endif
     // continue with the nearest child; the second nearest goes on top of the stack, the rest below it in slot order
     // (entries carry their entry distance, so a far one is culled when it is popped)
     int i0 = 0;

@@ -1148,7 +1148,11 @@ int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Nod
     B.w8 = w8;
     // one item per thread up to two blocks per SM (all co-resident: 64 registers x 256 threads); a single block for tiny inputs
     const int blocks = (int)std::min<size_t>((size_t)c.sm_count * 2, ((size_t)n + 255) / 256);
-    if (blocks <= 1) {
+    // One block with __syncthreads() between the phases instead of the cooperative grid was measured for RTIO's 1 936 instances: 1.20 ms
+    // against 0.73 ms (the phases are bound by the latency of their global atomics, which one SM cannot overlap) - so only tiny inputs
+    // take the single block (GKCU_FUSED_SINGLE_MAX to re-measure, profiles/r02_experiments.md)
+    static const uint32_t single_max = getenv("GKCU_FUSED_SINGLE_MAX") ? (uint32_t)atoi(getenv("GKCU_FUSED_SINGLE_MAX")) : 0u;
+    if (blocks <= 1 || n <= single_max) {
         k_build_fused<false><<<1, n <= 256 ? 256 : 1024, 0, st>>>(B);
     } else {
         void* args[] = {&B};

@@ -123,7 +123,10 @@ struct Context {
     GkcuCounters counters{};
     GkcuKernelStats kstats{};
     cudaEvent_t kev[8] = {};
-    cudaEvent_t wev[4][24] = {};  // per lane: trace/shade brackets of the waves of one chunk
+    cudaEvent_t wev[4][24] = {};  // per lane: trace/shade brackets of the last 8 waves (ring)
+    cudaEvent_t pev[4][8] = {};   // per lane: "queue size of wave k has reached the host" (ring, no timing)
+    int wave_seen[4] = {}, wave_launched[4] = {};  // waves of the last frame whose events the host has read / that were launched
+    int kernel_timing = 1;        // GKCU_KERNEL_TIMING=0: no per-wave event brackets (GkcuKernelStats.trace_ms / shade_ms stay 0)
     // The frame's pixels can be dealt to `lanes` independent wavefronts on their own streams (checkerboard of 8 x 16 tiles), so one
     // lane's shade kernel and the thin end of its trace kernel overlap the other lanes' kernels (GKCU_LANES, 1..4). Measured: 2 lanes
     // -0.7 %, 3 lanes +2 %, 4 lanes +5 % (the kernels already fill the GPU; overlap only shares it), so the default is one lane.
@@ -131,7 +134,7 @@ struct Context {
     cudaStream_t lane_stream[4] = {};
     cudaEvent_t lane_ev[4][4] = {};  // per lane: tail begin / end, done; [0][3]: primary done
     int tail_div = 64;         // the wavefront hands over to k_tail once the wave is narrower than pixels / tail_div (GKCU_TAIL_DIV)
-    int wave_chunk = 4;        // waves launched between two host polls of the queue size (GKCU_WAVE_CHUNK)
+    int wave_chunk = 6;        // how many waves the launches may run ahead of the queue sizes the host has read, 1..7 (GKCU_WAVE_CHUNK)
     cudaEvent_t ev[8] = {};
     uint64_t launches = 0;
     DevBuf trace_rays, trace_hits;

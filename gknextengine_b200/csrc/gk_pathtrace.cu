@@ -590,6 +590,16 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
     if ((threadIdx.x & 31) == 0 && nprimary) atomicAdd(ray_counters + 0, (unsigned long long)nprimary);
 }
 
+// Device-side end of the wavefront: counts[3] = (queue index + 1) of the queue the wavefront stopped at, 0 while it runs. The first
+// k_trace that finds its input queue at or below `stop_below` raises it; every kernel of the loop launched after that returns at once
+// and k_tail picks the queue up. All blocks of a kernel take the same decision: the flag only ever goes from 0 to non-zero, and the
+// queue size a k_trace reads is not written while it runs.
+GK_DEV bool wave_stopped(const PathView& V, int qi, uint32_t n, uint32_t stop_below) {
+    if (V.counts[3] == 0 && n > stop_below) return false;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && V.counts[3] == 0) V.counts[3] = (uint32_t)qi + 1u;
+    return true;
+}
+
 // Ray reordering (GKCU_SORT_RAYS): key = Morton code of the origin's cell on a 2^bits grid over the TLAS root box, then 6 bits of direction
 // (octant + dominant axis + a half-space bit). The rays stay where they are; k_trace walks them through the sorted index, so hits land in
 // the slots the shade kernel expects and the result cannot depend on the order.
@@ -629,8 +639,9 @@ __global__ void k_ray_keys(PathView V, int qi, size_t half, uint32_t nmax, float
 // blocks/SM with the world-space ray parked in shared memory. VARIANT 0: every lane advances one step of whatever kind
 // per iteration (the baseline the vote is measured against, profiles/r01_experiments.md).
 template <int VARIANT, int FMT>
-__global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below) {
+__global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace(TraceScene ts, PathView V, int qi, size_t half, int refill_below, uint32_t stop_below) {
     const uint32_t n = V.counts[qi];
+    if (wave_stopped(V, qi, n, stop_below)) return;
     // the other queue (this wave's output, last wave's input) is idle while this kernel runs: clear its size here instead of
     // with a memset between the kernels
     if (blockIdx.x == 0 && threadIdx.x == 0) V.counts[qi ^ 1] = 0;
@@ -638,8 +649,8 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
     const float4* ray_o = V.ray_o + (size_t)qi * half;
     const float4* ray_d = V.ray_d + (size_t)qi * half;
     const uint32_t* slot_pixel = V.slot_pixel[qi];
-    __shared__ float s_world[VARIANT == 5 ? 9 * 128 : 1];
-    typename std::conditional<VARIANT == 5, WorldSmem<128>, WorldRegs>::type world;
+    __shared__ float s_world[VARIANT == 5 ? 16 * 128 : 1];
+    typename std::conditional<VARIANT == 5, WorldSmemX<128>, WorldRegs>::type world;
     if constexpr (VARIANT == 5) world.p = s_world + threadIdx.x;
     LocalStack stack;
     Trav T;
@@ -751,13 +762,15 @@ struct PoolStack {
     uint2* base;
     GK_DEV void push(int& sp, uint2 v) { base[(size_t)sp * GK_POOL] = v; ++sp; }
     GK_DEV uint2 pop(int& sp) { --sp; return base[(size_t)sp * GK_POOL]; }
+    GK_DEV void put(int at, uint2 v) { base[(size_t)at * GK_POOL] = v; }
 };
 
 template <int FMT>
-__global__ void __launch_bounds__(128, GK_POOL_MINB) k_trace_pool(TraceScene ts, PathView V, int qi, size_t half, uint2* __restrict__ stack_mem) {
+__global__ void __launch_bounds__(128, GK_POOL_MINB) k_trace_pool(TraceScene ts, PathView V, int qi, size_t half, uint2* __restrict__ stack_mem, uint32_t stop_below) {
     static_assert(FMT == 4, "the pool tracer walks Node4 trees");
     __shared__ PoolSmem sm;
     const uint32_t n = V.counts[qi];
+    if (wave_stopped(V, qi, n, stop_below)) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) V.counts[qi ^ 1] = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4* ray_o = V.ray_o + (size_t)qi * half;
@@ -1012,6 +1025,7 @@ struct WPoolSmem {
 
 // the world-space ray of a slot, re-read from the ray queue (instance entry / exit only)
 struct WorldQueue {
+    static constexpr bool kKeepsTlasSpace = false;
     const float4 *ro, *rd;
     GK_DEV float3 o() const { const float4 v = __ldg(ro); return f3(v.x, v.y, v.z); }
     GK_DEV float3 d() const { const float4 v = __ldg(rd); return f3(v.x, v.y, v.z); }
@@ -1022,15 +1036,17 @@ struct WPoolStack {
     uint2* base;
     GK_DEV void push(int& sp, uint2 v) { base[(size_t)sp * GK_WPOOL] = v; ++sp; }
     GK_DEV uint2 pop(int& sp) { --sp; return base[(size_t)sp * GK_WPOOL]; }
+    GK_DEV void put(int at, uint2 v) { base[(size_t)at * GK_WPOOL] = v; }
 };
 
 template <int FMT>
-__global__ void __launch_bounds__(128, GK_WPOOL_MINB) k_trace_wpool(TraceScene ts, PathView V, int qi, size_t half, uint2* __restrict__ stack_mem) {
+__global__ void __launch_bounds__(128, GK_WPOOL_MINB) k_trace_wpool(TraceScene ts, PathView V, int qi, size_t half, uint2* __restrict__ stack_mem, uint32_t stop_below) {
     static_assert(FMT == 4, "the pool tracers walk Node4 trees");
     __shared__ WPoolSmem smem[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WPoolSmem& sm = smem[warp];
     const uint32_t n = V.counts[qi];
+    if (wave_stopped(V, qi, n, stop_below)) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) V.counts[qi ^ 1] = 0;
     const float4* ray_o = V.ray_o + (size_t)qi * half;
     const float4* ray_d = V.ray_d + (size_t)qi * half;
@@ -1203,8 +1219,9 @@ __global__ void __launch_bounds__(128, GK_WPOOL_MINB) k_trace_wpool(TraceScene t
 }
 
 // The first version: a warp takes 32 rays, every lane runs the simple per-ray loop, the warp refills when all are done.
-__global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V, int qi, size_t half) {
+__global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V, int qi, size_t half, uint32_t stop_below) {
     const uint32_t n = V.counts[qi];
+    if (wave_stopped(V, qi, n, stop_below)) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) V.counts[qi ^ 1] = 0;
     const int lane = threadIdx.x & 31;
     const float4* ray_o = V.ray_o + (size_t)qi * half;
@@ -1254,7 +1271,9 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
     SceneView S = S_;
     S.cam = &cam;
-    const uint32_t n = V.counts[qi];
+    const uint4 hdr = *reinterpret_cast<const uint4*>(V.counts);  // queue sizes, trace cursor, stop flag: one load
+    if (hdr.w) return;  // the wavefront has stopped (wave_stopped): the queue is k_tail's
+    const uint32_t n = qi ? hdr.y : hdr.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         V.counts[2] = 0;  // trace cursor of the next wave (this wave's k_trace is done)
         if (n) { V.counts[12] += n; V.counts[13] += 1; }  // rays and launches of the wavefront part, for the statistics
@@ -1290,9 +1309,10 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
 }
 
 // Tail / megakernel: every thread runs its pixel's program to completion with the traversal inlined.
-__global__ void __launch_bounds__(128) k_tail(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
+__global__ void __launch_bounds__(128) k_tail(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters, int after_wavefront) {
     SceneView S = S_;
     S.cam = &cam;
+    if (after_wavefront && V.counts[3]) qi = (int)V.counts[3] - 1;  // the queue the device stopped the wavefront at (wave_stopped)
     const uint32_t n = V.counts[qi];
     PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
     const size_t half = (size_t)R.w * R.h;
@@ -1550,28 +1570,54 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     int qi[4] = {0, 0, 0, 0};
     uint32_t bound[4] = {0, 0, 0, 0};
     bool active[4] = {false, false, false, false};
+    uint32_t tail_threshold = 0xFFFFFFFFu;
     if (p.tracer == 0) {
-        // Wavefront loop while the wave is wide; k_tail finishes the thin tail in one launch. The queue can only shrink (every
-        // path has at most one successor), so the last size the host has seen bounds the grids of the following waves: the
-        // host polls the size only every `wave_chunk` waves and the kernels read the exact size from device memory.
-        const uint32_t tail_threshold = std::max<uint32_t>(pixels / (uint32_t)std::max(1, c.tail_div), (uint32_t)c.sm_count * 128u) / (uint32_t)lanes;
-        const int chunk = std::max(1, std::min(c.wave_chunk, 8));
+        // Wavefront loop while the wave is wide; k_tail finishes the thin tail in one launch. The DEVICE decides when the wavefront ends:
+        // the first k_trace that finds its queue at or below the threshold raises the stop flag (counts[3] = queue + 1) and every later
+        // kernel of the loop returns at once, so the host never has to wait for a queue size before it launches the next wave. It still
+        // reads the sizes - asynchronously, through a ring of pinned words that trails the launches by up to kRing - 1 waves - for two
+        // things: the grids of the following waves (the queue can only shrink: every path has at most one successor, so an old size is
+        // an upper bound) and to stop launching once a size at or below the threshold has come back. The GPU therefore always has
+        // several waves queued (no launch gaps), and the few waves launched past the stop cost two empty kernels each.
+        tail_threshold = std::max<uint32_t>(pixels / (uint32_t)std::max(1, c.tail_div), (uint32_t)c.sm_count * 128u) / (uint32_t)lanes;
+        constexpr int kRing = 8;
+        const int ahead = std::max(1, std::min(kRing - 1, c.wave_chunk));
         for (int l = 0; l < lanes; ++l) GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l, L.v[l].counts + 0, 4, cudaMemcpyDeviceToHost, ls[l]));
         bool any = false;
+        int launched[4] = {0, 0, 0, 0}, seen[4] = {0, 0, 0, 0};  // waves launched / waves whose resulting queue size the host has read
         for (int l = 0; l < lanes; ++l) {
             GK_CUDA(cudaStreamSynchronize(ls[l]));
             bound[l] = b.host_counts[64 * l];
             active[l] = bound[l] > tail_threshold;
             any = any || active[l];
         }
+        auto consume = [&](int l, bool block) {  // read the sizes that have arrived (block: wait for the oldest outstanding one first)
+            while (seen[l] < launched[l]) {
+                const int k = seen[l] % kRing;
+                if (block) { GK_CUDA(cudaEventSynchronize(c.pev[l][k])); block = false; }
+                else if (cudaEventQuery(c.pev[l][k]) != cudaSuccess) break;
+                if (c.kernel_timing) {
+                    float a = 0, bms = 0;
+                    cudaEventElapsedTime(&a, c.wev[l][3 * k], c.wev[l][3 * k + 1]);
+                    cudaEventElapsedTime(&bms, c.wev[l][3 * k + 1], c.wev[l][3 * k + 2]);
+                    ks.trace_ms += a;
+                    ks.shade_ms += bms;
+                }
+                bound[l] = std::min(bound[l], b.host_counts[64 * l + 20 + k]);
+                if (bound[l] <= tail_threshold) active[l] = false;
+                ++seen[l];
+            }
+            return 0;
+        };
         while (any) {
+            any = false;
             for (int l = 0; l < lanes; ++l) {
                 if (!active[l]) continue;
                 const PathView& V = L.v[l];
                 const size_t half = V.pixels;
                 cudaStream_t s2 = ls[l];
-                for (int w = 0; w < chunk; ++w) {
-                    const uint32_t blocks = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 8u);
+                const int k = launched[l] % kRing;
+                {
                     PathView Vt = V;
                     if (c.sort_rays) {
                         const uint32_t nmax = bound[l];
@@ -1589,57 +1635,57 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                         Vt.order = v1;
                         c.launches += 2;
                     }
-                    cudaEventRecord(c.wev[l][3 * w], s2);
-                    if (c.trace_variant == 2) k_trace_simple<<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half);
-                    else if (c.trace_variant == 0) {
-                        if (c.node_format == 8) k_trace<0, 8><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
-                        else k_trace<0, 4><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below);
+                    if (c.kernel_timing) cudaEventRecord(c.wev[l][3 * k], s2);
+                    const uint32_t thr = tail_threshold;
+                    if (c.trace_variant == 2) {
+                        const uint32_t blocks = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 8u);
+                        k_trace_simple<<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, thr);
+                    } else if (c.trace_variant == 0) {
+                        const uint32_t blocks = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 8u);
+                        if (c.node_format == 8) k_trace<0, 8><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below, thr);
+                        else k_trace<0, 4><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below, thr);
                     } else if (c.trace_variant == 7 && c.node_format == 4) {
                         const uint32_t pb = std::min<uint32_t>((bound[l] + 4 * GK_WPOOL - 1) / (4 * GK_WPOOL), (uint32_t)c.sm_count * GK_WPOOL_MINB);
-                        k_trace_wpool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride);
+                        k_trace_wpool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride, thr);
                     } else if (c.trace_variant == 6 && c.node_format == 4) {
                         const uint32_t pb = std::min<uint32_t>((bound[l] + GK_POOL - 1) / GK_POOL, (uint32_t)c.sm_count * GK_POOL_MINB);
-                        k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride);
+                        k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride, thr);
                     } else {
                         const uint32_t tb = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u);
-                        if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below);
-                        else k_trace<5, 4><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below);
+                        if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below, thr);
+                        else k_trace<5, 4><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below, thr);
                     }
-                    cudaEventRecord(c.wev[l][3 * w + 1], s2);
+                    if (c.kernel_timing) cudaEventRecord(c.wev[l][3 * k + 1], s2);
                     const uint32_t sb = (bound[l] + 127) / 128;
                     if (c.shade_minb == 8) k_shade<8><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
                     else if (c.shade_minb == 7) k_shade<7><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
                     else if (c.shade_minb == 6) k_shade<6><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
                     else if (c.shade_minb == 10) k_shade<10><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
                     else k_shade<1><<<sb, 128, 0, s2>>>(S, ubo, R, V, cfg, qi[l], ray_counters_of(l));
-                    cudaEventRecord(c.wev[l][3 * w + 2], s2);
+                    if (c.kernel_timing) cudaEventRecord(c.wev[l][3 * k + 2], s2);
                     c.launches += 2;
                     qi[l] ^= 1;
                     ++iterations;
                 }
-                GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l, V.counts + qi[l], 4, cudaMemcpyDeviceToHost, s2));
-            }
-            any = false;
-            for (int l = 0; l < lanes; ++l) {
-                if (!active[l]) continue;
-                GK_CUDA(cudaStreamSynchronize(ls[l]));
-                for (int w = 0; w < chunk; ++w) {
-                    float a = 0, bms = 0;
-                    cudaEventElapsedTime(&a, c.wev[l][3 * w], c.wev[l][3 * w + 1]);
-                    cudaEventElapsedTime(&bms, c.wev[l][3 * w + 1], c.wev[l][3 * w + 2]);
-                    ks.trace_ms += a;
-                    ks.shade_ms += bms;
-                }
-                bound[l] = b.host_counts[64 * l];
-                active[l] = bound[l] > tail_threshold;
+                // the size of the queue this wave leaves behind: min(real size, size at which the wavefront stopped) - both bound what follows
+                GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 20 + k, V.counts + qi[l], 4, cudaMemcpyDeviceToHost, s2));
+                cudaEventRecord(c.pev[l][k], s2);
+                ++launched[l];
+                if (consume(l, launched[l] - seen[l] > ahead)) return 1;
                 any = any || active[l];
             }
         }
+        for (int l = 0; l < lanes; ++l) {  // the waves still in flight are timed once the frame has been synchronised (fetch_ray_counters)
+            c.wave_seen[l] = seen[l];
+            c.wave_launched[l] = launched[l];
+        }
+    } else {
+        for (int l = 0; l < 4; ++l) c.wave_seen[l] = c.wave_launched[l] = 0;
     }
     for (int l = 0; l < lanes; ++l) {
         const uint32_t blocks = std::min<uint32_t>((pixels / lanes + 127) / 128, (uint32_t)c.sm_count * 16u);
         cudaEventRecord(c.lane_ev[l][0], ls[l]);
-        k_tail<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l));
+        k_tail<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), p.tracer == 0 ? 1 : 0);
         cudaEventRecord(c.lane_ev[l][1], ls[l]);
         c.launches++;
         // per lane: primary / closest / any ray counters (3 x u64) and the wavefront statistics (rays, launches)
@@ -1686,6 +1732,13 @@ void fetch_ray_counters(Context& c) {
 #endif
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c.lane_ev[l][0], c.lane_ev[l][1]) == cudaSuccess) c.kstats.tail_ms += ms;
+        for (; c.kernel_timing && c.wave_seen[l] < c.wave_launched[l]; ++c.wave_seen[l]) {  // waves the host had not looked at when it queued the tail
+            const int k = c.wave_seen[l] % 8;
+            float a = 0, bms = 0;
+            if (cudaEventElapsedTime(&a, c.wev[l][3 * k], c.wev[l][3 * k + 1]) == cudaSuccess) c.kstats.trace_ms += a;
+            if (cudaEventElapsedTime(&bms, c.wev[l][3 * k + 1], c.wev[l][3 * k + 2]) == cudaSuccess) c.kstats.shade_ms += bms;
+        }
+        c.wave_seen[l] = c.wave_launched[l];
     }
     c.kstats.shade_launches = c.kstats.trace_launches;
     float ms = 0;

@@ -455,6 +455,9 @@ int gkcu_bind_external_semaphore(GkcuContext* ctx, uint32_t handle_type, int fd)
 int gkcu_get_timings(GkcuContext* ctx, GkcuTimings* out);
 int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out);
 int gkcu_get_kernel_stats(GkcuContext* ctx, GkcuKernelStats* out);
+/* Per-launch CUDA-event brackets around the k_trace / k_shade launches of the wavefront (GkcuKernelStats.trace_ms / shade_ms) cost about
+ * 4 us per event, 0.7 ms on a 60-wave frame. On (1) by default; 0 leaves trace_ms / shade_ms at 0 and the frame without those gaps. */
+int gkcu_set_kernel_timing(GkcuContext* ctx, uint32_t enabled);
 /* cudaStream_t of the context as an integer handle, for callers that time with events or enqueue collectives. */
 uint64_t gkcu_stream(GkcuContext* ctx);
 
