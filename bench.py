@@ -484,6 +484,25 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    # The timed region above carries CUDA-event brackets around every k_trace / k_shade launch (the per-kernel durations of the roofline
+    # object); they cost ~4 us each. The same K frames without them (gkcu_set_kernel_timing(0)) are reported next to the headline.
+    r.set_kernel_timing(False)
+    frame(tf)
+    tf += 1
+    sync_all()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record(ext)
+    for _ in range(args.steps):
+        frame(tf)
+        tf += 1
+        r.counters()
+    n1.record(ext)
+    sync_all()
+    ms_plain = torch.tensor([n0.elapsed_time(n1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(ms_plain, op=dist.ReduceOp.MAX)
+    ms_plain = float(ms_plain[0])
+    r.set_kernel_timing(True)
     stats = torch.tensor([ms, float(rays), float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         mx = stats.clone()
@@ -552,6 +571,8 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
             "tracer": "wavefront" if args.tracer == 0 else "megakernel",
             "rays_per_frame": {"primary": primary_rays / args.steps, "closest_hit": closest_rays / args.steps, "any_hit": any_rays / args.steps},
             "passes_ms_per_frame_rank0": {k: v / args.steps for k, v in pass_ms.items()},
+            "without_kernel_events": {"ms_per_step": ms_plain / args.steps, "value": value * ms / ms_plain, "unit": "Mrays/s",
+                                      "note": "same K frames with gkcu_set_kernel_timing(0): no per-launch event brackets inside the rt pass"},
         }
         if world > 1:
             out["multi_gpu"] = {"exchange": {"peer": "fused reduce+resolve kernel over NVLink peer memory (strips), device-side flag barriers, no collective call",

@@ -45,6 +45,19 @@ static int alloc_zero(void** p, size_t bytes, cudaStream_t st) {
     return 0;
 }
 
+namespace {
+__global__ void k_publish(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t words) {
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+}  // namespace
+int publish_words(Context& c, const void* src, uint32_t dst_word, uint32_t words, cudaStream_t st) {
+    k_publish<<<1, 64, 0, st>>>(static_cast<const uint32_t*>(src), c.pub_dev + dst_word, words);
+    c.launches++;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static void free_targets(RenderTargets& t) {
     void** ptrs[] = {(void**)&t.accum_diffuse[0], (void**)&t.accum_diffuse[1], (void**)&t.accum_specular[0], (void**)&t.accum_specular[1],
                      (void**)&t.accum_albedo[0], (void**)&t.accum_albedo[1], (void**)&t.single_diffuse, (void**)&t.single_specular,
@@ -117,6 +130,7 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     c.sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("GKCU_TRACE_VARIANT")) c.trace_variant = atoi(e);
     if (const char* e = getenv("GKCU_TMA")) c.use_tma = atoi(e);
+    if (const char* e = getenv("GKCU_FAST_STENCIL")) c.fast_stencil = atoi(e) != 0;
     if (const char* e = getenv("GKCU_SHADE_MINB")) c.shade_minb = atoi(e);
     if (const char* e = getenv("GKCU_TRACE_CARVEOUT")) c.trace_carveout = std::max(-1, std::min(100, atoi(e)));
     if (const char* e = getenv("GKCU_SORT_RAYS")) c.sort_rays = std::max(0, std::min(19, atoi(e)));
@@ -124,6 +138,9 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     if (const char* e = getenv("GKCU_REFILL")) c.refill_below = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("GKCU_NODE_FORMAT")) c.node_format = atoi(e) == 4 ? 4 : 8;
     if (!check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete ctx; return 1; }
+    if (!check(cudaHostAlloc((void**)&c.pub_host, 64 * 5 * 4, cudaHostAllocMapped), "cudaHostAlloc") ||
+        !check(cudaHostGetDevicePointer((void**)&c.pub_dev, c.pub_host, 0), "cudaHostGetDevicePointer")) { delete ctx; return 1; }
+    memset(c.pub_host, 0, 64 * 5 * 4);
     for (auto& e : c.ev) cudaEventCreate(&e);
     for (auto& e : c.kev) cudaEventCreate(&e);
     for (auto& l : c.wev)
@@ -176,6 +193,7 @@ int gkcu_destroy(GkcuContext* ctx) {
     for (auto& l : c.pev)
         for (auto& e : l)
             if (e) cudaEventDestroy(e);
+    if (c.pub_host) cudaFreeHost(c.pub_host);
     for (auto& l : c.lane_ev)
         for (auto& e : l)
             if (e) cudaEventDestroy(e);
@@ -755,6 +773,12 @@ int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity) {
         ext[2 + 2 * m] = c.blas[m].leaf_base;
         ext[3 + 2 * m] = c.blas[m].leaf_count;
     }
+    return 0;
+}
+
+int gkcu_set_fast_stencil(GkcuContext* ctx, uint32_t enabled) {
+    CTX_OR_FAIL(ctx);
+    c.fast_stencil = enabled ? 1 : 0;
     return 0;
 }
 

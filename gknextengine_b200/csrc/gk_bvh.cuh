@@ -67,7 +67,7 @@ static_assert(sizeof(InstanceRec) == 64, "InstanceRec must be 64 bytes");
 #define GK_PUSH_ORDERED 1
 #endif
 #ifndef GK_NODE_BF
-#define GK_NODE_BF 1  // Node4 node step: branch-free ordering and pushes (0: the compare-and-push ladder, for A/B)
+#define GK_NODE_BF 0  // Node4 node step: 1 = branch-free ordering and pushes, measured 5 % slower than the compare-and-push ladder (1.09 children are hit per node step on the bench frame, so the ladder mostly takes its short paths; profiles/r02_experiments.md)
 #endif
 
 struct TraceScene {

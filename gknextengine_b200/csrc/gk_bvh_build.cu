@@ -15,6 +15,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -1161,10 +1162,11 @@ int build_fused(Context& c, uint32_t n, int leaf_max, const uint32_t* remap, Nod
     c.launches += 1;
     int table[48];
     int last[5];
-    GK_CUDA(cudaMemcpyAsync(table, B.counters + 16, 48 * 4, cudaMemcpyDeviceToHost, st));
-    GK_CUDA(cudaMemcpyAsync(last, B.counters + 8, 20, cudaMemcpyDeviceToHost, st));
+    if (publish_words(c, B.counters + 8, 8, 56, st)) return 1;  // counters[8..12] = totals, counters[16..63] = level table
     GK_CUDA(cudaStreamSynchronize(st));
     GK_CUDA(cudaGetLastError());
+    memcpy(last, c.pub_host + 8, 20);
+    memcpy(table, c.pub_host + 16, 48 * 4);
     if (last[2] != 0) { set_error("BVH collapse did not terminate (tree deeper than 46 wide levels)"); return 1; }
     const int levels_run = last[3];
     info.leaf_count = (uint32_t)last[4];
@@ -1356,9 +1358,9 @@ static int build_tlas_impl(Context& c) {
         if (!c.select_tmp.reserve(tmp)) return 1;
         GK_CUDA(cub::DeviceSelect::Flagged(c.select_tmp.p, tmp, iota, c.inst_flags.as<uint8_t>(), c.tlas_active_ids.as<uint32_t>(), c.select_count.as<uint32_t>(),
                                            (int)n, st));
-        uint32_t m_host = 0;
-        GK_CUDA(cudaMemcpyAsync(&m_host, c.select_count.p, 4, cudaMemcpyDeviceToHost, st));
+        if (publish_words(c, c.select_count.p, 0, 1, st)) return 1;
         GK_CUDA(cudaStreamSynchronize(st));
+        const uint32_t m_host = c.pub_host[0];
         c.tlas.prim_count = m_host;
         c.launches += 1;
     }

@@ -69,6 +69,11 @@ struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    // Small device -> host results (queue sizes, ray counters, TLAS level table) are STORED by kernels into mapped pinned memory instead of
+    // copied with cudaMemcpyAsync: a 4-byte copy queues on the D2H copy engine behind the 16.6 MB asynchronous present of the previous
+    // frame and stalls the stream for as long as that copy takes (8 ms on a box with a slow link). 64 words for the builders, then 64 per lane.
+    uint32_t* pub_host = nullptr;
+    uint32_t* pub_dev = nullptr;
     const char* last_api = nullptr;  // name of the previous C-ABI entry point (diagnostics)
 
     // scene (GPUScene buffers, BasicTypes.slang:261-291)
@@ -95,6 +100,7 @@ struct Context {
     bool blas_built = false;
     BuildScratch scratch;
     int trace_variant = 5;  // GKCU_TRACE_VARIANT: 5 vote-selected step kind, 6 blocks/SM (default); 0 one step of any kind per iteration; 2 warp-granular batches, no refill
+    int fast_stencil = 0;   // GKCU_FAST_STENCIL / gkcu_set_fast_stencil: approximate transcendentals + reciprocal in the compose pass (tolerance build)
     int use_tma = 1;        // GKCU_TMA=0 falls back to plain-load staging of the stencil tiles (2 / 3: only reproject / only denoise)
     int shade_minb = 7;     // GKCU_SHADE_MINB: 8 compiles k_shade for 8 blocks/SM (<= 64 registers)
     int trace_carveout = -1;  // k_trace shared-memory carve-out in percent (GKCU_TRACE_CARVEOUT), -1 = sized to the resident blocks
@@ -179,6 +185,9 @@ void* peer_local_buffer(Context& c, uint32_t what);
 // gk_raster.cu
 int run_gpu_cull(Context& c, const GkUniformBufferObject& ubo);
 int run_visibility_pass(Context& c, const GkUniformBufferObject& ubo);
+
+// gk_api.cu: dst_word..dst_word+words of the mapped block <- src (device), stream-ordered (a one-block kernel, no copy engine)
+int publish_words(Context& c, const void* src, uint32_t dst_word, uint32_t words, cudaStream_t st);
 
 // gk_probes.cu
 int probes_voxelize(Context& c);

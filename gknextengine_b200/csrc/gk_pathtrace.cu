@@ -54,6 +54,7 @@ struct PathView {
     uint32_t* hit_prim;
     uint32_t* counts;           // [0],[1] queue sizes (ping-pong), [2] trace cursor, [4..] ray counters
     float4 *radiance, *direct;  // multi-GPU: un-normalised sums (2 planes) and rank 0's direct term
+    uint32_t* publish;          // mapped host word this wave's k_trace stores its input queue size to (nullptr: none)
     const uint32_t* order;      // k_trace: queue position -> slot (rays binned by origin cell and direction), nullptr = queue order
 };
 
@@ -66,7 +67,7 @@ struct PathBuffers {
     size_t sort_tmp_bytes = 0;
     DevBuf pool_stack;  // k_trace_pool / k_trace_wpool: traversal stacks, [lane][block (, warp)][depth][slot]
     size_t pool_stack_stride = 0;  // uint2 entries per lane
-    uint32_t* host_counts = nullptr;  // pinned, 64 words per lane
+    uint32_t* host_counts = nullptr;  // Context::pub_host + 64: mapped pinned memory, 64 words per lane, written by kernels
     size_t pixels = 0;
     size_t lane_cap = 0;  // queue capacity of one lane
     int lanes = 1;
@@ -595,8 +596,12 @@ __global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_cons
 // and k_tail picks the queue up. All blocks of a kernel take the same decision: the flag only ever goes from 0 to non-zero, and the
 // queue size a k_trace reads is not written while it runs.
 GK_DEV bool wave_stopped(const PathView& V, int qi, uint32_t n, uint32_t stop_below) {
-    if (V.counts[3] == 0 && n > stop_below) return false;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && V.counts[3] == 0) V.counts[3] = (uint32_t)qi + 1u;
+    const bool stopped_before = V.counts[3] != 0;
+    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    // the host learns the queue sizes from these stores (mapped pinned memory, no copy engine); 0 once the wavefront has stopped
+    if (lead && V.publish) *V.publish = stopped_before ? 0u : n;
+    if (!stopped_before && n > stop_below) return false;
+    if (lead && !stopped_before) V.counts[3] = (uint32_t)qi + 1u;
     return true;
 }
 
@@ -1468,6 +1473,7 @@ PathView make_path_view(const Context& c, int lane = 0) {
     V.counts = b.counts.as<uint32_t>() + (size_t)lane * 64;
     V.radiance = b.radiance.as<float4>(); V.direct = b.direct.as<float4>();
     V.order = nullptr;
+    V.publish = nullptr;
     return V;
 }
 
@@ -1499,7 +1505,7 @@ int path_resize(Context& c) {
     if (!ok) return 1;
     // ranks other than 0 never write the direct-term plane; keep it defined for a host that resolves on such a context
     GK_CUDA(cudaMemsetAsync(b.direct.p, 0, n * 16, c.stream));
-    if (!b.host_counts) GK_CUDA(cudaMallocHost(&b.host_counts, 4 * 64 * 4));
+    b.host_counts = c.pub_host + 64;
     return 0;
 }
 
@@ -1509,7 +1515,6 @@ void path_release(Context& c) {
     for (DevBuf* d : {&b.rng, &b.pos_mat, &b.nrm_flags, &b.dir_cnt, &b.ray_color, &b.final_color, &b.final_refl, &b.prim_pos_mat, &b.prim_nrm_cnt,
                       &b.prim_albedo, &b.ray_o, &b.ray_d, &b.slot_pixel[0], &b.slot_pixel[1], &b.hit_tuv, &b.hit_prim, &b.counts, &b.radiance, &b.direct, &b.pool_stack, &b.sort_keys[0], &b.sort_keys[1], &b.sort_vals[0], &b.sort_vals[1], &b.sort_tmp})
         d->release();
-    if (b.host_counts) cudaFreeHost(b.host_counts);
     delete c.path;
     c.path = nullptr;
 }
@@ -1582,12 +1587,10 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
         tail_threshold = std::max<uint32_t>(pixels / (uint32_t)std::max(1, c.tail_div), (uint32_t)c.sm_count * 128u) / (uint32_t)lanes;
         constexpr int kRing = 8;
         const int ahead = std::max(1, std::min(kRing - 1, c.wave_chunk));
-        for (int l = 0; l < lanes; ++l) GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l, L.v[l].counts + 0, 4, cudaMemcpyDeviceToHost, ls[l]));
         bool any = false;
-        int launched[4] = {0, 0, 0, 0}, seen[4] = {0, 0, 0, 0};  // waves launched / waves whose resulting queue size the host has read
+        int launched[4] = {0, 0, 0, 0}, seen[4] = {0, 0, 0, 0};  // waves launched / waves whose input queue size the host has read
         for (int l = 0; l < lanes; ++l) {
-            GK_CUDA(cudaStreamSynchronize(ls[l]));
-            bound[l] = b.host_counts[64 * l];
+            bound[l] = (uint32_t)std::min<size_t>(pixels, b.lane_cap);  // k_primary queues at most one path per pixel: no need to wait for it
             active[l] = bound[l] > tail_threshold;
             any = any || active[l];
         }
@@ -1603,7 +1606,8 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                     ks.trace_ms += a;
                     ks.shade_ms += bms;
                 }
-                bound[l] = std::min(bound[l], b.host_counts[64 * l + 20 + k]);
+                const uint32_t size = b.host_counts[64 * l + 20 + k];  // stored by that wave's k_trace (wave_stopped): its input queue, 0 = stopped
+                bound[l] = std::min(bound[l], size);
                 if (bound[l] <= tail_threshold) active[l] = false;
                 ++seen[l];
             }
@@ -1619,6 +1623,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 const int k = launched[l] % kRing;
                 {
                     PathView Vt = V;
+                    Vt.publish = c.pub_dev + 64 + 64 * l + 20 + k;
                     if (c.sort_rays) {
                         const uint32_t nmax = bound[l];
                         const float3 lo = make_float3(c.tlas.root_lo[0], c.tlas.root_lo[1], c.tlas.root_lo[2]);
@@ -1639,17 +1644,17 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                     const uint32_t thr = tail_threshold;
                     if (c.trace_variant == 2) {
                         const uint32_t blocks = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 8u);
-                        k_trace_simple<<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, thr);
+                        k_trace_simple<<<blocks, 128, 0, s2>>>(S.ts, Vt, qi[l], half, thr);
                     } else if (c.trace_variant == 0) {
                         const uint32_t blocks = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 8u);
-                        if (c.node_format == 8) k_trace<0, 8><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below, thr);
-                        else k_trace<0, 4><<<blocks, 128, 0, s2>>>(S.ts, V, qi[l], half, c.refill_below, thr);
+                        if (c.node_format == 8) k_trace<0, 8><<<blocks, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below, thr);
+                        else k_trace<0, 4><<<blocks, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below, thr);
                     } else if (c.trace_variant == 7 && c.node_format == 4) {
                         const uint32_t pb = std::min<uint32_t>((bound[l] + 4 * GK_WPOOL - 1) / (4 * GK_WPOOL), (uint32_t)c.sm_count * GK_WPOOL_MINB);
-                        k_trace_wpool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride, thr);
+                        k_trace_wpool<4><<<pb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride, thr);
                     } else if (c.trace_variant == 6 && c.node_format == 4) {
                         const uint32_t pb = std::min<uint32_t>((bound[l] + GK_POOL - 1) / GK_POOL, (uint32_t)c.sm_count * GK_POOL_MINB);
-                        k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, V, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride, thr);
+                        k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride, thr);
                     } else {
                         const uint32_t tb = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u);
                         if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below, thr);
@@ -1667,9 +1672,7 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                     qi[l] ^= 1;
                     ++iterations;
                 }
-                // the size of the queue this wave leaves behind: min(real size, size at which the wavefront stopped) - both bound what follows
-                GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 20 + k, V.counts + qi[l], 4, cudaMemcpyDeviceToHost, s2));
-                cudaEventRecord(c.pev[l][k], s2);
+                cudaEventRecord(c.pev[l][k], s2);  // once it has passed, ring word k holds the size this wave's k_trace stored
                 ++launched[l];
                 if (consume(l, launched[l] - seen[l] > ahead)) return 1;
                 any = any || active[l];
@@ -1689,10 +1692,9 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
         cudaEventRecord(c.lane_ev[l][1], ls[l]);
         c.launches++;
         // per lane: primary / closest / any ray counters (3 x u64) and the wavefront statistics (rays, launches)
-        GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 8, ray_counters_of(l), 24, cudaMemcpyDeviceToHost, ls[l]));
-        GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 16, L.v[l].counts + 12, 8, cudaMemcpyDeviceToHost, ls[l]));
+        if (publish_words(c, L.v[l].counts + 4, 64 + 64 * l + 4, 10, ls[l])) return 1;  // counts[4..9] ray counters, [12..13] wavefront statistics
 #ifdef GK_TRAV_STATS
-        GK_CUDA(cudaMemcpyAsync(b.host_counts + 64 * l + 32, L.v[l].counts + 32, 128, cudaMemcpyDeviceToHost, ls[l]));
+        if (publish_words(c, L.v[l].counts + 32, 64 + 64 * l + 32, 32, ls[l])) return 1;
 #endif
         if (lanes > 1) {
             cudaEventRecord(c.lane_ev[l][2], ls[l]);
@@ -1714,17 +1716,17 @@ void fetch_ray_counters(Context& c) {
     c.kstats.tail_ms = 0;
     for (int l = 0; l < c.path->lanes; ++l) {
         const uint32_t* hc = c.path->host_counts + 64 * l;
-        const unsigned long long* h = reinterpret_cast<const unsigned long long*>(hc + 8);
+        const unsigned long long* h = reinterpret_cast<const unsigned long long*>(hc + 4);
         c.counters.primary_rays += h[0];
         c.counters.closest_hit_rays += h[1];
         c.counters.any_hit_rays += h[2];
-        c.kstats.trace_rays += hc[16];
-        c.kstats.trace_launches += hc[17];
+        c.kstats.trace_rays += hc[12];
+        c.kstats.trace_launches += hc[13];
 #ifdef GK_TRAV_STATS
         {
             const unsigned long long* g = reinterpret_cast<const unsigned long long*>(hc + 32);
             static const char* names[8] = {"tlas_node_steps", "blas_node_steps", "children_hit", "pushes", "culled_pops", "instance_entries", "leaf_steps", "tri_tests"};
-            fprintf(stderr, "TRAV_STATS wavefront_rays=%u", hc[16]);
+            fprintf(stderr, "TRAV_STATS wavefront_rays=%u", hc[12]);
             for (int k = 0; k < 8; ++k) fprintf(stderr, " closest_%s=%llu", names[k], g[k]);
             for (int k = 0; k < 8; ++k) fprintf(stderr, " any_%s=%llu", names[k], g[8 + k]);
             fprintf(stderr, "\n");

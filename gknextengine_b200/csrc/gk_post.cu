@@ -280,6 +280,8 @@ struct DenoiseArgs {
     const GkUniformBufferObject* cam;
 };
 
+GK_DEV float exp2f_approx(float x) { float y; asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // Const_Func.slang:51-68, 82-126
 GK_DEV float W_f(float x, float e0, float e1) {
     if (x <= e0) return 0;
@@ -292,33 +294,98 @@ GK_DEV float H_f(float x, float e0, float e1) {
     if (x >= e1) return 1;
     return (x - e0) / (e1 - e0);
 }
+// FAST (GKCU_FAST_STENCIL=1, gkcu_set_fast_stencil): the hardware's approximate transcendentals (lg2.approx / ex2.approx, 2 ulp) and reciprocal
+// instead of the pinned software exp / pow and the IEEE division. Slang leaves these intrinsics to the driver's compiler, so no reference bit
+// pattern exists for them; the pinned build is bit-equal to the repo's oracle, the fast build is within the tolerance tests/ states.
+template <bool FAST> GK_DEV float post_pow(float x, float y) { return FAST ? __powf(x, y) : gk_det_powf(x, y); }
+template <bool FAST> GK_DEV float post_exp(float x) { return FAST ? __expf(x) : gk_det_expf(x); }
+template <bool FAST> GK_DEV float post_div(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+template <bool FAST>
 GK_DEV float GranTurismoTonemapper(float x) {
     const float e = 2.71828f;
     float P = 1, a = 0.7f, m = 0.22f, l = 0.4f, c = 1.33f, b = 0;
     float l0 = (P - m) * l / a;
     float L_x = m + a * (x - m);
-    float T_x = m * gk_det_powf(x / m, c) + b;
+    float T_x = m * post_pow<FAST>(x / m, c) + b;
     float S0 = m + l0;
     float S1 = m + a * l0;
     float C2 = a * P / (P - S1);
-    float S_x = P - (P - S1) * gk_det_powf(e, -(C2 * (x - S0) / P));
+    float S_x = P - (P - S1) * post_pow<FAST>(e, -(C2 * (x - S0) / P));
     float w0_x = 1 - W_f(x, 0, m);
     float w2_x = H_f(x, m + l0, m + l0);
     float w1_x = 1 - w0_x - w2_x;
     return T_x * w0_x + L_x * w1_x + S_x * w2_x;
 }
-GK_DEV float3 GT_Tonemapping(float3 x) { return f3(GranTurismoTonemapper(x.x), GranTurismoTonemapper(x.y), GranTurismoTonemapper(x.z)); }
+template <bool FAST>
+GK_DEV float3 GT_Tonemapping(float3 x) { return f3(GranTurismoTonemapper<FAST>(x.x), GranTurismoTonemapper<FAST>(x.y), GranTurismoTonemapper<FAST>(x.z)); }
+template <bool FAST>
 GK_DEV float ST2084(float lin) {
     const float m1 = 0.1593017578125f, m2 = 78.84375f, c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f, C = 10000.f;
     float L = lin / C;
-    float Lm = gk_det_powf(L, m1);
+    float Lm = post_pow<FAST>(L, m1);
     float N1 = (c1 + c2 * Lm), N2 = (1.0f + c3 * Lm);
     float N = N1 * (1.0f / N2);
-    return gk_det_powf(N, m2);
+    return post_pow<FAST>(N, m2);
 }
 
+// The spatial weight of a tap depends on its offset and BFSigma only: the 36 values are computed once per block (same expression, same
+// bits as the shader's per-pixel evaluation, Process.DenoiseJBF.comp.slang:139) instead of 36 exp per pixel.
+constexpr int DTAPS = (DR + 1) * (DR + 1);  // taps at odd offsets -DR..DR in both directions: 6 x 6
+template <bool FAST>
+GK_DEV void jbf_spatial_table(float* s_F, int tid, float sigma) {
+    if (tid < DTAPS) {
+        const int i = -DR + 2 * (tid / (DR + 1)), j = -DR + 2 * (tid % (DR + 1));
+        const float dist = clampf(float(i * i + j * j) / float(DR * DR), 0.0f, 1.0f);
+        s_F[tid] = gk_det_expf(-dist * dist / (2.0f * sigma * sigma));
+    }
+}
+// :128-146 for one pixel of the staged tile
+template <bool FAST>
+GK_DEV float3 jbf_filter(const float4 (*s_diff)[DTW], const float* s_F, int ly, int lx, float sigmaL) {
+    const float CenterLum = s_diff[ly][lx].w;
+    float3 Total = f3(0, 0, 0);
+    float Weight = 0;
+    const float kL = FAST ? -1.4426950408889634f / (2.0f * sigmaL * sigmaL) : 0.0f;
+#pragma unroll
+    for (int i = -DR; i <= DR; i += 2) {
+#pragma unroll
+        for (int j = -DR; j <= DR; j += 2) {  // the centre pixel is not a tap (:133-141)
+            const float4 t = s_diff[ly + i][lx + j];
+            const float3 Ci = xyz(t);
+            const float lumi = t.w;
+            const float dlum = (CenterLum - lumi) * (CenterLum - lumi);
+            const float Fi = s_F[((i + DR) / 2) * (DR + 1) + (j + DR) / 2];
+            const float Li = FAST ? exp2f_approx(dlum * dlum * kL) : gk_det_expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
+            Total = Total + Ci * Fi * Li;
+            Weight += Fi * Li;
+        }
+    }
+    if (FAST) {
+        const float inv = __frcp_rn(Weight);
+        return Total * inv;
+    }
+    return f3(Total.x / Weight, Total.y / Weight, Total.z / Weight);
+}
+// :150-180: tone mapping + store
+template <bool FAST>
+GK_DEV void compose_store(const GkUniformBufferObject* C, uint2* denoised, size_t idx, float3 Total) {
+    if (C->HDR) {
+        Total = f3(Total.x / 2000.0f, Total.y / 2000.0f, Total.z / 2000.0f);
+        Total = GT_Tonemapping<FAST>(Total);
+        Total = Total * 2000.0f;
+        float3 pw = Total * C->PaperWhiteNit;
+        store_h4(denoised, idx, f4(ST2084<FAST>(pw.x / 230.0f), ST2084<FAST>(pw.y / 230.0f), ST2084<FAST>(pw.z / 230.0f), 1.0f));
+    } else {
+        float3 pw = Total * C->PaperWhiteNit;
+        float3 t = GT_Tonemapping<FAST>(f3(pw.x / 40000.0f, pw.y / 40000.0f, pw.z / 40000.0f));
+        store_h4(denoised, idx, f4(t.x, t.y, t.z, 1.0f));
+    }
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
     __shared__ float4 s_diff[DTH][DTW];  // rgb + 0.001 bias, luminance in w
+    __shared__ float s_F[DTAPS];
     const GkUniformBufferObject* C = A.cam;
     const int w = A.w, h = A.h;
     const int gx0 = (int)C->ViewportRect.x, gy0 = (int)C->ViewportRect.y;
@@ -327,6 +394,7 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
     const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
     const bool filter = C->BFSize > 0;
     if (filter) {
+        jbf_spatial_table<FAST>(s_F, tid, C->BFSigma);
         for (int i = tid; i < DTW * DTH; i += DBX * DBY) {
             int ty = i / DTW, tx = i % DTW;
             float4 v = ld4(A.accum_diffuse, bx0 + tx - DR, by0 + ty - DR, w, h);
@@ -339,50 +407,24 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
     const size_t idx = (size_t)y * w + x;
     float3 Total = f3(0, 0, 0);
     if (filter) {
-        const int ly = threadIdx.y + DR, lx = threadIdx.x + DR;
-        const float CenterLum = s_diff[ly][lx].w;
         const float3 CenterSpec = xyz(load_h4(A.accum_specular, idx)) + f3(0.001f, 0.001f, 0.001f);
-        const float sigma = C->BFSigma, sigmaL = C->BFSigmaLum * 100.0f;
-        float Weight = 0;
-        // tap (i, j) = tile[row + i][col + j]; the centre pixel is not a tap (:133-141)
-        for (int i = -DR; i <= DR; i += 2) {
-            for (int j = -DR; j <= DR; j += 2) {
-                const float4 t = s_diff[ly + i][lx + j];
-                const float3 Ci = xyz(t);
-                const float lumi = t.w;
-                const float dist = clampf(float(i * i + j * j) / float(DR * DR), 0.0f, 1.0f);
-                const float dlum = (CenterLum - lumi) * (CenterLum - lumi);
-                const float Fi = gk_det_expf(-dist * dist / (2.0f * sigma * sigma));
-                const float Li = gk_det_expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
-                Total = Total + Ci * Fi * Li;
-                Weight += Fi * Li;
-            }
-        }
-        Total = f3(Total.x / Weight, Total.y / Weight, Total.z / Weight);
+        Total = jbf_filter<FAST>(s_diff, s_F, threadIdx.y + DR, threadIdx.x + DR, C->BFSigmaLum * 100.0f);
         if (!C->DebugDraw_Lighting) Total = Total * xyz(load_h4(A.accum_albedo, idx)) + CenterSpec;
     } else {
         float3 d = xyz(load_h4(A.accum_diffuse, idx)), s = xyz(load_h4(A.accum_specular, idx));
         if (C->DebugDraw_Lighting) Total = d * f3(0.5f, 0.5f, 0.5f) + s;
         else Total = d * xyz(load_h4(A.accum_albedo, idx)) + s;
     }
-    if (C->HDR) {
-        Total = f3(Total.x / 2000.0f, Total.y / 2000.0f, Total.z / 2000.0f);
-        Total = GT_Tonemapping(Total);
-        Total = Total * 2000.0f;
-        float3 pw = Total * C->PaperWhiteNit;
-        store_h4(A.denoised, idx, f4(ST2084(pw.x / 230.0f), ST2084(pw.y / 230.0f), ST2084(pw.z / 230.0f), 1.0f));
-    } else {
-        float3 pw = Total * C->PaperWhiteNit;
-        float3 t = GT_Tonemapping(f3(pw.x / 40000.0f, pw.y / 40000.0f, pw.z / 40000.0f));
-        store_h4(A.denoised, idx, f4(t.x, t.y, t.z, 1.0f));
-    }
+    compose_store<FAST>(C, A.denoised, idx, Total);
 }
 
 
 // DenoiseJBF with the 42x18 ACCUM_DIFFUSE tile staged by one TMA copy (zero fill outside the image).
+template <bool FAST>
 __global__ void __launch_bounds__(DBX* DBY) k_denoise_tma(const __grid_constant__ CUtensorMap map_diffuse, DenoiseArgs A) {
     __shared__ alignas(128) uint2 raw[DTH][DTWP];
     __shared__ float4 s_diff[DTH][DTW];  // rgb + 0.001 bias, luminance in w
+    __shared__ float s_F[DTAPS];
     __shared__ uint64_t bar;
     const GkUniformBufferObject* C = A.cam;
     const int w = A.w, h = A.h;
@@ -396,6 +438,7 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise_tma(const __grid_constant_
         gktma::mbar_expect_tx(&bar, (uint32_t)sizeof(raw));
         gktma::tma_load_2d(raw, &map_diffuse, bx0 - DRP, by0 - DR, &bar);
     }
+    jbf_spatial_table<FAST>(s_F, tid, C->BFSigma);  // while the tile is in flight
     gktma::mbar_wait(&bar, 0);
     for (int i = tid; i < DTW * DTH; i += DBX * DBY) {
         int ty = i / DTW, tx = i % DTW;
@@ -408,40 +451,10 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise_tma(const __grid_constant_
     __syncthreads();
     if (!inb(x, y, w, h)) return;
     const size_t idx = (size_t)y * w + x;
-    const int ly = threadIdx.y + DR, lx = threadIdx.x + DR;
-    const float CenterLum = s_diff[ly][lx].w;
     const float3 CenterSpec = xyz(load_h4(A.accum_specular, idx)) + f3(0.001f, 0.001f, 0.001f);
-    const float sigma = C->BFSigma, sigmaL = C->BFSigmaLum * 100.0f;
-    float3 Total = f3(0, 0, 0);
-    float Weight = 0;
-#pragma unroll
-    for (int i = -DR; i <= DR; i += 2) {
-#pragma unroll
-        for (int j = -DR; j <= DR; j += 2) {
-            const float4 t = s_diff[ly + i][lx + j];
-            const float3 Ci = xyz(t);
-            const float lumi = t.w;
-            const float dist = clampf(float(i * i + j * j) / float(DR * DR), 0.0f, 1.0f);
-            const float dlum = (CenterLum - lumi) * (CenterLum - lumi);
-            const float Fi = gk_det_expf(-dist * dist / (2.0f * sigma * sigma));
-            const float Li = gk_det_expf(-dlum * dlum / (2.0f * sigmaL * sigmaL));
-            Total = Total + Ci * Fi * Li;
-            Weight += Fi * Li;
-        }
-    }
-    Total = f3(Total.x / Weight, Total.y / Weight, Total.z / Weight);
+    float3 Total = jbf_filter<FAST>(s_diff, s_F, threadIdx.y + DR, threadIdx.x + DR, C->BFSigmaLum * 100.0f);
     if (!C->DebugDraw_Lighting) Total = Total * xyz(load_h4(A.accum_albedo, idx)) + CenterSpec;
-    if (C->HDR) {
-        Total = f3(Total.x / 2000.0f, Total.y / 2000.0f, Total.z / 2000.0f);
-        Total = GT_Tonemapping(Total);
-        Total = Total * 2000.0f;
-        float3 pw = Total * C->PaperWhiteNit;
-        store_h4(A.denoised, idx, f4(ST2084(pw.x / 230.0f), ST2084(pw.y / 230.0f), ST2084(pw.z / 230.0f), 1.0f));
-    } else {
-        float3 pw = Total * C->PaperWhiteNit;
-        float3 t = GT_Tonemapping(f3(pw.x / 40000.0f, pw.y / 40000.0f, pw.z / 40000.0f));
-        store_h4(A.denoised, idx, f4(t.x, t.y, t.z, 1.0f));
-    }
+    compose_store<FAST>(C, A.denoised, idx, Total);
 }
 
 }  // namespace
@@ -490,9 +503,9 @@ int run_denoise(Context& c, const GkUniformBufferObject& ubo) {
     dim3 grid((t.w + DBX - 1) / DBX, (t.h + DBY - 1) / DBY), block(DBX, DBY);
     CUtensorMap map;
     if ((c.use_tma == 1 || c.use_tma == 3) && ubo.BFSize > 0 && (t.w % 2 == 0) && ((int)ubo.ViewportRect.x % 2 == 0) && gktma::encode_2d(&map, t.accum_diffuse[t.cur], CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, t.w, t.h, DTWP, DTH))
-        k_denoise_tma<<<grid, block, 0, c.stream>>>(map, A);
+        c.fast_stencil ? k_denoise_tma<true><<<grid, block, 0, c.stream>>>(map, A) : k_denoise_tma<false><<<grid, block, 0, c.stream>>>(map, A);
     else
-        k_denoise<<<grid, block, 0, c.stream>>>(A);
+        c.fast_stencil ? k_denoise<true><<<grid, block, 0, c.stream>>>(A) : k_denoise<false><<<grid, block, 0, c.stream>>>(A);
     c.launches++;
     GK_CUDA(cudaGetLastError());
     return 0;

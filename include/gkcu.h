@@ -458,6 +458,10 @@ int gkcu_get_kernel_stats(GkcuContext* ctx, GkcuKernelStats* out);
 /* Per-launch CUDA-event brackets around the k_trace / k_shade launches of the wavefront (GkcuKernelStats.trace_ms / shade_ms) cost about
  * 4 us per event, 0.7 ms on a 60-wave frame. On (1) by default; 0 leaves trace_ms / shade_ms at 0 and the frame without those gaps. */
 int gkcu_set_kernel_timing(GkcuContext* ctx, uint32_t enabled);
+/* Compose pass (Process.DenoiseJBF.comp.slang) with the GPU's approximate exp / pow and a reciprocal instead of the pinned software
+ * transcendentals and the IEEE division: RT_DENOISED then differs from the pinned build by at most 2 fp16 ulps per channel (tests/), the pass
+ * is ~1.5x faster. Off (0) by default: the default build is bit-equal to the oracle. */
+int gkcu_set_fast_stencil(GkcuContext* ctx, uint32_t enabled);
 /* cudaStream_t of the context as an integer handle, for callers that time with events or enqueue collectives. */
 uint64_t gkcu_stream(GkcuContext* ctx);
 

@@ -418,6 +418,34 @@ def test_stencil_passes_on_random_inputs(renderer, W, H):
             renderer.upload_image(RT["SINGLE_DIFFUSE"], images["SINGLE_DIFFUSE"])
 
 
+@pytest.mark.parametrize("hdr", [False, True])
+def test_fast_stencil_build_stays_within_its_tolerance(renderer, hdr):
+    """gkcu_set_fast_stencil(1): the compose pass with ex2.approx / lg2.approx / rcp instead of the pinned transcendentals and the IEEE division.
+    Stated tolerance against the pinned build (= the oracle): at most 4 fp16 ulps per channel (the tone curve amplifies the 2-ulp fp32 error
+    of the approximations), relative RMSE below 5e-4; NaN pixels (0 / 0 weights) in the same places. The pinned build stays the default."""
+    W, H = 640, 360
+    scene = host.Scene("CornellBox.proc", samples=2, bounces=4, taa=False, denoiser=True, hdr=hdr)
+    scene.update_nodes()
+    osc, ofr = setup_pair(renderer, scene, W, H)
+    ubo = scene.ubo(W, H, 1)
+    p = params()
+    renderer.set_fast_stencil(True)
+    renderer.Render(ubo, p)
+    ofr.render(osc, ubo, p)
+    g, c = renderer.readback(RT["DENOISED"]), ofr.image(RT["DENOISED"])
+    gf, cf = g.astype(np.float32), c.astype(np.float32)
+    nan_differs = float((np.isnan(gf) != np.isnan(cf)).any(axis=2).mean())
+    assert nan_differs <= 1e-4, nan_differs  # 0 / 0 of the bilateral weights next to the light: an underflow either side of the approximation
+    ok = ~np.isnan(cf) & ~np.isnan(gf)
+    ulps = half_ulp_diff(g, c)[ok]
+    assert 0 < ulps.max() <= 4, (int(ulps.max()), float((ulps > 4).mean()))  # it IS the other arithmetic, and it is close
+    assert rel_rmse(gf[ok], cf[ok]) < 5e-4, rel_rmse(gf[ok], cf[ok])
+    for name in ("ACCUMLATE_DIFFUSE", "ACCUMLATE_SPECULAR", "ACCUMLATE_ALBEDO"):  # the reproject pass is untouched
+        assert mismatch_fraction(renderer.readback(RT[name]), ofr.image(RT[name])) == 0.0
+    renderer.BeforeNextFrame()
+    renderer.set_fast_stencil(False)
+
+
 def test_trace_rays_edge_cases(renderer):
     scene = host.Scene("CornellBox.proc")
     scene.update_nodes()
