@@ -290,6 +290,11 @@ int gkcu_blas_refit(GkcuContext* ctx, uint32_t model_index, const uint16_t* simp
 int gkcu_update_nodes(GkcuContext* ctx, const GkNodeProxy* nodes, uint32_t count) {
     CTX_OR_FAIL(ctx);
     if (count && !nodes) { set_error("gkcu_update_nodes: null array"); return 1; }
+    if (c.skip_unchanged_nodes) {  // gkcu_set_skip_unchanged_nodes: identical proxies keep the TLAS (and skip the upload)
+        const size_t bytes = (size_t)count * sizeof(GkNodeProxy);
+        if (count == c.node_count && !c.tlas_dirty && c.nodes_shadow.size() == bytes && (bytes == 0 || memcmp(c.nodes_shadow.data(), nodes, bytes) == 0)) return 0;
+        c.nodes_shadow.assign(reinterpret_cast<const uint8_t*>(nodes), reinterpret_cast<const uint8_t*>(nodes) + bytes);
+    }
     if (!c.nodes.reserve(std::max<size_t>(1, count) * sizeof(GkNodeProxy))) return 1;
     if (count) GK_CUDA(cudaMemcpyAsync(c.nodes.p, nodes, (size_t)count * sizeof(GkNodeProxy), cudaMemcpyHostToDevice, c.stream));
     c.node_count = count;
@@ -310,6 +315,7 @@ int gkcu_update_nodes_sparse(GkcuContext* ctx, const uint32_t* indices, const Gk
     GK_CUDA(cudaMemcpyAsync(c.node_stage.p, proxies, (size_t)count * sizeof(GkNodeProxy), cudaMemcpyHostToDevice, c.stream));
     GK_CUDA(cudaMemcpyAsync(c.node_stage_idx.p, indices, (size_t)count * 4, cudaMemcpyHostToDevice, c.stream));
     if (scatter_nodes(c, count)) return 1;
+    c.nodes_shadow.clear();  // the shadow copy no longer matches the device array
     c.tlas_dirty = true;
     GK_CUDA(cudaStreamSynchronize(c.stream));  // the caller may reuse its arrays
     return 0;
@@ -329,6 +335,7 @@ int gkcu_update_materials(GkcuContext* ctx, const GkMaterial* materials, uint32_
 int gkcu_tlas_build(GkcuContext* ctx) {
     CTX_OR_FAIL(ctx);
     if (!c.blas_built) { set_error("gkcu_tlas_build: call gkcu_blas_build first"); return 1; }
+    if (c.skip_unchanged_nodes && !c.tlas_dirty) { c.timings.tlas_update_ms = 0; c.frame_built_tlas = false; return 0; }
     cudaEventRecord(c.kev[7], c.stream);
     int r = build_tlas(c);
     cudaEventRecord(c.ev[7], c.stream);
@@ -773,6 +780,13 @@ int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity) {
         ext[2 + 2 * m] = c.blas[m].leaf_base;
         ext[3 + 2 * m] = c.blas[m].leaf_count;
     }
+    return 0;
+}
+
+int gkcu_set_skip_unchanged_nodes(GkcuContext* ctx, uint32_t enabled) {
+    CTX_OR_FAIL(ctx);
+    c.skip_unchanged_nodes = enabled ? 1 : 0;
+    c.nodes_shadow.clear();
     return 0;
 }
 

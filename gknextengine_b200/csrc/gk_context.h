@@ -96,6 +96,8 @@ struct Context {
     DevBuf node_stage, node_stage_idx;            // gkcu_update_nodes_sparse staging
     WideBvhInfo tlas;
     bool tlas_dirty = true;
+    int skip_unchanged_nodes = 0;        // gkcu_set_skip_unchanged_nodes: gkcu_update_nodes keeps the TLAS when the proxies are byte-identical
+    std::vector<uint8_t> nodes_shadow;   // host copy of the last full NodeProxy[] upload (only kept while the option is on)
     bool frame_built_tlas = false;
     bool blas_built = false;
     BuildScratch scratch;

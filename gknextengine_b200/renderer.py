@@ -81,6 +81,7 @@ def lib():
         L.gkcu_get_kernel_stats.argtypes = [P, C.POINTER(GkcuKernelStats)]
         L.gkcu_set_kernel_timing.argtypes = [P, C.c_uint32]
         L.gkcu_set_fast_stencil.argtypes = [P, C.c_uint32]
+        L.gkcu_set_skip_unchanged_nodes.argtypes = [P, C.c_uint32]
         L.gkcu_stream.restype = C.c_uint64
         L.gkcu_stream.argtypes = [P]
         L.gkcu_trace_rays.argtypes = [P, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
@@ -293,6 +294,9 @@ class CudaPathTracingRenderer:
         c = GkcuCounters()
         _ck(lib().gkcu_get_counters(self._ctx, C.byref(c)))
         return {n: getattr(c, n) for n, _ in GkcuCounters._fields_}
+
+    def set_skip_unchanged_nodes(self, enabled):
+        _ck(lib().gkcu_set_skip_unchanged_nodes(self._ctx, int(bool(enabled))))
 
     def set_fast_stencil(self, enabled):
         _ck(lib().gkcu_set_fast_stencil(self._ctx, int(bool(enabled))))

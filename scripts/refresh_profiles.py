@@ -36,7 +36,24 @@ for k, out in (("k_trace", "trace"), ("k_shade", "shade"), ("misc", "misc")):
             return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[i]]
         traffic.setdefault(name, []).append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
 tj = {k: sum(v) / len(v) for k, v in traffic.items()}
-tj["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches (ncu --set full; k_trace/k_shade: waves 10-11 of a frame)"
+tj["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu). k_trace / k_shade: mean over ALL launches of one whole frame (the launches roofline.achieved averages over); the others: mean over the captured launches of a --set full pass"
+# whole-frame traffic of the wavefront kernels: every launch of one frame, metrics-only pass
+ft = f"{G}/{tag}_frame_traffic.csv"
+if os.path.exists(ft):
+    rows = [r for r in csv.reader(open(ft, errors="replace")) if len(r) > 10]
+    h = rows[0]; kn, mn, mv, mu, idc = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit"), h.index("ID")
+    per = {}
+    for r in rows[1:]:
+        if not r[mn].startswith("dram__bytes"): continue
+        name = r[kn].split("(")[0].split("<")[0].replace("void ", "").split("::")[-1]
+        x = float(r[mv].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r[mu]]
+        per.setdefault(name, {}).setdefault(r[idc], 0.0)
+        per[name][r[idc]] += x
+    for name, d in per.items():
+        tj[name] = sum(d.values()) / len(d)
+        tj[name + "_launches_in_frame"] = len(d)
+        tj[name + "_frame_total_bytes"] = sum(d.values())
+    shutil.copy(ft, f"{P}/{tag}_frame_traffic.csv")
 json.dump(tj, open(f"{P}/traffic.json", "w"), indent=1)
 print(open(f"{P}/{tag}_launches_summary.txt").read()); print(json.dumps(tj, indent=1))
 

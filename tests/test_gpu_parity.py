@@ -495,6 +495,40 @@ def test_blas_refit_and_dynamic_tlas(renderer):
     assert t["blas_refit_ms"] > 0 and t["tlas_update_ms"] > 0
 
 
+def test_skip_unchanged_nodes_keeps_the_tlas_and_the_images(renderer):
+    """gkcu_set_skip_unchanged_nodes: a byte-identical NodeProxy[] neither crosses the bus nor rebuilds the TLAS; a moved instance does."""
+    scene = host.Scene("LegoBricks.synth:2000")
+    scene.update_nodes()
+    osc, _ = setup_pair(renderer, scene, 64, 64)
+    rays = random_rays(20000, seed=9, center=(0, 1.5, 0), spread=8.0)
+    renderer.set_skip_unchanged_nodes(True)
+    renderer.AfterUpdateScene(scene)
+    renderer.PreRender()
+    assert renderer.timings()["tlas_update_ms"] > 0
+    first = renderer.trace(rays)
+    scene.update_nodes()  # nothing moved (combinedPrevTS has caught up after the second call)
+    scene.update_nodes()
+    renderer.AfterUpdateScene(scene)
+    renderer.PreRender()
+    renderer.AfterUpdateScene(scene)
+    renderer.PreRender()
+    assert renderer.timings()["tlas_update_ms"] == 0
+    again = renderer.trace(rays)
+    assert np.array_equal(first, again)
+    scene.jitter_instances(1, 0.05)
+    scene.update_nodes()
+    renderer.AfterUpdateScene(scene)
+    osc.update_nodes(scene)
+    renderer.PreRender()
+    assert renderer.timings()["tlas_update_ms"] > 0
+    hg, hc = renderer.trace(rays), osc.trace(rays)
+    assert np.array_equal(hg["inst"], hc["inst"]) and np.array_equal(hg["t"].view(np.uint32), hc["t"].view(np.uint32))
+    assert not np.array_equal(hg["inst"], first["inst"])
+    renderer.set_skip_unchanged_nodes(False)
+    renderer.PreRender()
+    assert renderer.timings()["tlas_update_ms"] > 0  # the default rebuilds every frame, like the reference
+
+
 def test_sparse_node_updates_equal_full_uploads(renderer):
     """gkcu_update_nodes_sparse: only the proxies Scene.update_nodes() changed cross the bus (1 % of the instances move per frame
     in config 4; a moved node changes in the frame it moves and in the next one, when its previous transform catches up).
