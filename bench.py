@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, SPP, BOUNCES = 1920, 1080, 16, 8
+SKY_PATH = None  # --sky: a Radiance .hdr equirect (e.g. the reference's assets/textures/river_road_2.hdr) instead of the procedural stand-in
 SCENE = "RTIO.proc"
 # algorithmic bytes (DESIGN.md "Byte accounting"): per closest-hit ray 436 B, per any-hit ray 100 B for the
 # trace+shade pair; the share k_trace itself moves is the ray record it reads and the hit record it writes.
@@ -37,6 +38,13 @@ TRACE_BYTES_PER_RAY = 32 + 4 + 16 + 4
 PAIR_BYTES_CLOSEST, PAIR_BYTES_ANY = 436, 100
 PRIMARY_BYTES_PER_PIXEL, REPROJECT_BYTES_PER_PIXEL, DENOISE_BYTES_PER_PIXEL = 36 + 2, 98, 44
 # Both stencil kernels are bound by instruction issue, not by HBM (ncu: profiles/r02_ncu_table.md); the bench reports their algorithmic GB/s only.
+
+
+def bench_sky(host):
+    """Sky id 0 of the workload (Engine.cpp:855): the file given with --sky, else the procedural stand-in."""
+    if SKY_PATH:
+        return host.load_hdr(SKY_PATH)
+    return host.make_sky(1024, 512)
 
 
 def load_peaks():
@@ -163,6 +171,8 @@ def cpu_sample(scene, sky, ubo, params, bands, band_rows):
     so that whatever happens there the port can still be timed and the bench line printed."""
     try:
         cmd = [sys.executable, os.path.abspath(__file__), "--cpu-leg", f"{bands},{band_rows}", "--workload", "config5" if WIDTH == 3840 else "config2"]
+        if SKY_PATH:
+            cmd += ["--sky", SKY_PATH]
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
         j = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
         return j["rays"], j["secs"], "reference", f"the reference's Core.PathTracing shader compiled as C++ (oracle/_ref/libref_pathtrace*.so), ray queries on {j['query']}"
@@ -177,7 +187,7 @@ def cpu_leg(spec):
     bands, band_rows = (int(x) for x in spec.split(","))
     scene = host.Scene(SCENE, samples=SPP, bounces=BOUNCES, taa=True, temporal_frames=16, denoiser=True)
     scene.update_nodes()
-    ref = CompiledReference(scene, host.make_sky(1024, 512))
+    ref = CompiledReference(scene, bench_sky(host))
     ubo = scene.ubo(WIDTH, HEIGHT, 1)
     ref.sample(ubo, 2, 2)  # untimed: first touch of the image pages, thread start-up
     rays, secs = ref.sample(ubo, bands, band_rows)
@@ -193,7 +203,7 @@ def reference_arm(args):
 
     scene = host.Scene(SCENE, samples=SPP * args.gpus, bounces=BOUNCES, taa=True, temporal_frames=16, denoiser=True)
     scene.update_nodes()
-    sky = host.make_sky(1024, 512)
+    sky = bench_sky(host)
     params = GkcuFrameParams(temporal_frames=16, spp_world=1)
     cores = os.cpu_count() or 1
     bands, band_rows = 8, 16  # 128 of 1080 rows per step; work items are 8 x 8 pixel groups: 480 per band, enough for any host
@@ -274,12 +284,14 @@ def zero_copy_leg(r, scene, frame, sync_all, steps, tf, pinned_nodes, node_bytes
 def workload_config(n, probes=False):
     name = "BASELINE configs[1]" if (WIDTH, HEIGHT) == (1920, 1080) else "SURVEY 8d config 5 (qx50.glb absent: declared stand-in scene)"
     return {"workload": f"{name}: RayTracingInOneWeekend procedural scene (RTIO.proc), {WIDTH}x{HEIGHT}, {SPP} spp per GPU "
-                        f"({SPP * n} spp/frame), {BOUNCES} bounces, procedural sky stand-in, steady state, temporal reproject + bilateral denoise",
+                        f"({SPP * n} spp/frame), {BOUNCES} bounces, {'sky ' + os.path.basename(SKY_PATH) if SKY_PATH else 'procedural sky stand-in'}, steady state, temporal reproject + bilateral denoise",
             "scene": SCENE, "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_per_frame": SPP * n, "bounces": BOUNCES,
             "parallelism": f"spp-split x{n}, scene replica per GPU" if n > 1 else "single GPU",
             "l2": "working set (queue slots + hit records + per-pixel path state ~240 B/px, storage images 122 B/px: ~750 MB at 1080p) exceeds the 126 MB L2; "
                   "no explicit flush",
-            "sky": "procedural equirect sky (host.make_sky 1024x512); river_road_2.hdr is not in the mount, gkcu_set_sky takes any RGBA32F equirect (host.load_hdr)",
+            "sky": f"Radiance .hdr equirect {os.path.basename(SKY_PATH)} (--sky, host.load_hdr)" if SKY_PATH else
+                   "procedural equirect sky (host.make_sky 1024x512): the reference's assets/textures/river_road_2.hdr is reference content that neither "
+                   "enters the repo nor travels to the GPU box; gkcu_set_sky takes any RGBA32F equirect and --sky PATH loads a Radiance .hdr",
             "probes": "voxelised + baked grid, bake dispatch every frame" if probes else "zero probe state"}
 
 
@@ -293,6 +305,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the config-5 strong-scaling block (4K, 64 spp split over the GPUs)")
     ap.add_argument("--cpu-leg", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--sky", default=None, help="Radiance .hdr equirect used as sky 0 instead of the procedural stand-in")
     ap.add_argument("--probes", action="store_true",
                     help="voxelise the probe grid, bake one full sweep before timing and record the per-frame bake dispatch like "
                          "RayTraceBaseRenderer::PostRender; default: zero probe state (SURVEY 8d config 1/2)")
@@ -305,6 +318,8 @@ def main():
                     help="config2: BASELINE configs[1], 1080p, 16 spp per GPU (weak scaling). config5: SURVEY 8d config 5, 3840x2160, 64 spp per frame "
                          "split over the GPUs (strong scaling)")
     args = ap.parse_args()
+    global SKY_PATH
+    SKY_PATH = args.sky
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.cpu_leg:
         set_workload(args.workload, 1)
@@ -366,7 +381,7 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
     args.steps, args.warmup, args.workload = steps, warmup, workload
     scene = host.Scene(SCENE, samples=SPP * world, bounces=BOUNCES, taa=True, temporal_frames=16, denoiser=True)
     scene.update_nodes()  # steady state: combinedPrevTS = identity, MOTIONMOMENT stays 0
-    sky = host.make_sky(1024, 512)
+    sky = bench_sky(host)
     r = CudaPathTracingRenderer(local_rank)
     r.CreateSwapChain((WIDTH, HEIGHT))
     r.OnPostLoadScene(scene, sky)
