@@ -311,8 +311,10 @@ def main():
                          "RayTraceBaseRenderer::PostRender; default: zero probe state (SURVEY 8d config 1/2)")
     ap.add_argument("--present", default="async", choices=["async", "blocking"],
                     help="e2e leg: async = double-buffered gkcu_readback_denoised_async overlapping the next frame; blocking = gkcu_readback")
-    ap.add_argument("--reduce", default="peer", choices=["peer", "peer-hostbarrier", "nccl"],
-                    help="multi-GPU: peer = fused reduce + resolve kernel over NVLink peer memory with device-side barriers (default); "
+    ap.add_argument("--reduce", default="peer-post", choices=["peer-post", "peer", "peer-hostbarrier", "nccl"],
+                    help="multi-GPU: peer-post = every rank resolves, reprojects and composes its own strip over NVLink peer memory, history strips "
+                         "mirrored to all ranks, nothing left to rank 0 alone (default); peer = fused reduce + resolve kernel over peer memory with "
+                         "device-side barriers, post passes on rank 0; "
                          "peer-hostbarrier = same kernel bracketed by two 4-byte NCCL all-reduces; nccl = ncclReduce to rank 0, resolve there")
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
                     help="config2: BASELINE configs[1], 1080p, 16 spp per GPU (weak scaling). config5: SURVEY 8d config 5, 3840x2160, 64 spp per frame "
@@ -406,7 +408,7 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
         radiance = torch.as_tensor(_Buf(), device=f"cuda:{local_rank}")
         if args.reduce != "nccl":
             # ship every rank's buffers as cudaIpcMemHandles; each rank opens its peers' (NVLink peer access)
-            mine = {what: r.peer_export(what)[0] for what in range(5)}
+            mine = {what: r.peer_export(what)[0] for what in range(r.PEER_KINDS)}
             everyone = [None] * world
             dist.all_gather_object(everyone, mine)
             for pr in range(world):
@@ -414,12 +416,12 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
                     r.peer_import(pr, r.PEER_RADIANCE, ptr=r.peer_export(r.PEER_RADIANCE)[1])
                 else:
                     r.peer_import(pr, r.PEER_RADIANCE, handle=everyone[pr][r.PEER_RADIANCE])
-                if args.reduce == "peer":
+                for what in ((r.PEER_FLAGS,) if args.reduce == "peer" else (r.PEER_FLAGS,) + r.PEER_ACCUM if args.reduce == "peer-post" else ()):
                     if pr == rank:
-                        r.peer_import(pr, r.PEER_FLAGS, ptr=r.peer_export(r.PEER_FLAGS)[1])
+                        r.peer_import(pr, what, ptr=r.peer_export(what)[1])
                     else:
-                        r.peer_import(pr, r.PEER_FLAGS, handle=everyone[pr][r.PEER_FLAGS])
-            for what in (r.PEER_DIRECT, r.PEER_SINGLE_DIFFUSE, r.PEER_SINGLE_SPECULAR):
+                        r.peer_import(pr, what, handle=everyone[pr][what])
+            for what in (r.PEER_DIRECT, r.PEER_SINGLE_DIFFUSE, r.PEER_SINGLE_SPECULAR, r.PEER_DENOISED):
                 if rank == 0:
                     r.peer_import(0, what, ptr=r.peer_export(what)[1])
                 else:
@@ -439,6 +441,8 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
                     dist.reduce(radiance, dst=0, op=dist.ReduceOp.SUM)
                 if rank == 0:
                     r.Resolve(ubo, params)
+            elif args.reduce == "peer-post":
+                r.ResolvePostStrip(ubo, params)  # barrier, strip resolve + strip reproject (history mirrored to all ranks) + strip compose into rank 0, barrier
             elif args.reduce == "peer":
                 r.ResolveStrip(ubo, params)    # device-side barrier, peer loads of my strip from every rank, peer stores into rank 0's SINGLE_*, barrier
                 if rank == 0:
@@ -590,7 +594,8 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
                                       "note": "same K frames with gkcu_set_kernel_timing(0): no per-launch event brackets inside the rt pass"},
         }
         if world > 1:
-            out["multi_gpu"] = {"exchange": {"peer": "fused reduce+resolve kernel over NVLink peer memory (strips), device-side flag barriers, no collective call",
+            out["multi_gpu"] = {"exchange": {"peer-post": "strip-parallel tail over NVLink peer memory: every rank resolves (+7 halo rows), reprojects (+5) and composes its strip, mirrors its ACCUM_* strip into every rank, stores its RT_DENOISED strip into rank 0; device-side flag barriers, no collective call",
+                                             "peer": "fused reduce+resolve kernel over NVLink peer memory (strips), device-side flag barriers, no collective call",
                                              "peer-hostbarrier": "fused reduce+resolve kernel over NVLink peer memory (strips) between two 4-byte NCCL all-reduces",
                                              "nccl": "ncclReduce(sum, fp32) to rank 0 + resolve on rank 0"}[args.reduce],
                                 "exchange_resolve_post_ms_per_frame_rank0": reduce_ms[0] / args.steps,

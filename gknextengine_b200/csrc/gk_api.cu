@@ -150,8 +150,10 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     for (auto& l : c.pev)
         for (auto& e : l) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (const char* e = getenv("GKCU_KERNEL_TIMING")) c.kernel_timing = atoi(e) != 0;
-    for (auto& st : c.lane_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     if (const char* e = getenv("GKCU_LANES")) c.lanes = std::max(1, std::min(4, atoi(e)));
+    // lane streams only when the frame is split into lanes: every stream takes one of the device's hardware queues (8 by default), and two
+    // streams that share a queue serialise - fatal for kernels that wait for a kernel of another context (the multi-GPU device barrier)
+    for (int l = 0; l < 4 && c.lanes > 1; ++l) cudaStreamCreateWithFlags(&c.lane_stream[l], cudaStreamNonBlocking);
     if (const char* e = getenv("GKCU_TAIL_DIV")) c.tail_div = std::max(1, std::min(65536, atoi(e)));
     if (const char* e = getenv("GKCU_WAVE_CHUNK")) c.wave_chunk = std::max(1, std::min(7, atoi(e)));
     if (!c.ubo.reserve(sizeof(GkUniformBufferObject))) { delete ctx; return 1; }
@@ -561,7 +563,12 @@ int gkcu_peer_export(GkcuContext* ctx, uint32_t what, void* handle, void** devic
 
 int gkcu_peer_import(GkcuContext* ctx, uint32_t rank, uint32_t what, const void* handle, void* device_ptr) {
     CTX_OR_FAIL(ctx);
-    if (rank >= GKCU_MAX_PEERS || what > GKCU_PEER_FLAGS) { set_error("gkcu_peer_import: rank >= 8 or unknown buffer"); return 1; }
+    if (rank >= GKCU_MAX_PEERS || what >= GKCU_PEER_KINDS) { set_error("gkcu_peer_import: rank >= 8 or unknown buffer"); return 1; }
+    if (!c.preloaded) {  // a context that imports peers is about to run multi-GPU frames
+        path_preload();
+        post_preload();
+        c.preloaded = true;
+    }
     void* p = device_ptr;
     if (handle) {
         cudaIpcMemHandle_t h;
@@ -579,6 +586,21 @@ int gkcu_render_resolve_strip(GkcuContext* ctx, const GkUniformBufferObject* ubo
     if (frame_prologue(c, ubo, params)) return 1;
     const uint64_t launches0 = c.launches;
     if (run_resolve_strip(c, *ubo, *params)) return 1;
+    c.counters.kernel_launches += c.launches - launches0;
+    return 0;
+}
+
+int gkcu_render_resolve_post_strip(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params) {
+    CTX_OR_FAIL(ctx);
+    if (frame_prologue(c, ubo, params)) return 1;
+    const uint64_t launches0 = c.launches;
+    cudaEventRecord(c.ev[2], c.stream);
+    if (run_resolve_post_strip(c, *ubo, *params)) return 1;
+    cudaEventRecord(c.ev[3], c.stream);
+    cudaEventRecord(c.ev[4], c.stream);
+    if (params->spp_rank == 0 && signal_present(c)) return 1;
+    end_frame_swaps(c);
+    cudaEventRecord(c.ev[5], c.stream);
     c.counters.kernel_launches += c.launches - launches0;
     return 0;
 }

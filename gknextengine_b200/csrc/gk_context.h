@@ -151,7 +151,8 @@ struct Context {
     bool copy_pending = false;
 
     // multi-GPU peer resolve: peer[rank][what] device pointers (local, same-process, or opened from an IPC handle)
-    void* peer[GKCU_MAX_PEERS][5] = {};
+    void* peer[GKCU_MAX_PEERS][GKCU_PEER_KINDS] = {};
+    bool preloaded = false;  // the kernels of the multi-GPU frame tail have been resolved (path_preload / post_preload)
     DevBuf peer_flags;          // this rank's flag block: ready[8], done[8], timeouts (uint64 each), written by the peers
     uint64_t peer_epoch = 0;
     std::vector<void*> ipc_opened;
@@ -182,6 +183,9 @@ int run_trace_rays(Context& c, uint32_t count, bool any_hit);
 void fetch_ray_counters(Context& c);
 int radiance_buffer(Context& c, void** ptr, size_t* bytes);
 int run_resolve_strip(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p);
+int run_resolve_post_strip(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p);
+void path_preload();
+void post_preload();
 void* peer_local_buffer(Context& c, uint32_t what);
 
 // gk_raster.cu
@@ -196,7 +200,14 @@ int probes_voxelize(Context& c);
 int probes_bake(Context& c, const GkUniformBufferObject& ubo, uint32_t first, uint32_t count);
 
 // gk_post.cu
-int run_reproject(Context& c, const GkcuFrameParams& p);
-int run_denoise(Context& c, const GkUniformBufferObject& ubo);
+// Strip-parallel post of a multi-GPU frame (gkcu_render_resolve_post_strip): the reproject pass runs on rows [y_begin, y_end) and mirrors the
+// rows [own_y0, own_y1) it owns into the other ranks' ACCUM_* images, the compose pass runs on the owned rows and writes `denoised`.
+struct PostStrip {
+    int y_begin = 0, y_end = 0, own_y0 = 0, own_y1 = 0, n_mirror = 0;
+    uint2 *mirror_diffuse[GKCU_MAX_PEERS - 1] = {}, *mirror_specular[GKCU_MAX_PEERS - 1] = {}, *mirror_albedo[GKCU_MAX_PEERS - 1] = {};
+    uint2* denoised = nullptr;  // where the compose pass stores (rank 0's RT_DENOISED over peer memory); nullptr = the local image
+};
+int run_reproject(Context& c, const GkcuFrameParams& p, const PostStrip* strip = nullptr);
+int run_denoise(Context& c, const GkUniformBufferObject& ubo, const PostStrip* strip = nullptr);
 
 }  // namespace gkcu

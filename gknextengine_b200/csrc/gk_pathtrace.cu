@@ -1768,6 +1768,13 @@ void* peer_local_buffer(Context& c, uint32_t what) {
         case GKCU_PEER_DIRECT: return c.path->direct.p;
         case GKCU_PEER_SINGLE_DIFFUSE: return c.rt.single_diffuse;
         case GKCU_PEER_SINGLE_SPECULAR: return c.rt.single_specular;
+        case GKCU_PEER_ACCUM_DIFFUSE_0: return c.rt.accum_diffuse[0];
+        case GKCU_PEER_ACCUM_DIFFUSE_1: return c.rt.accum_diffuse[1];
+        case GKCU_PEER_ACCUM_SPECULAR_0: return c.rt.accum_specular[0];
+        case GKCU_PEER_ACCUM_SPECULAR_1: return c.rt.accum_specular[1];
+        case GKCU_PEER_ACCUM_ALBEDO_0: return c.rt.accum_albedo[0];
+        case GKCU_PEER_ACCUM_ALBEDO_1: return c.rt.accum_albedo[1];
+        case GKCU_PEER_DENOISED: return c.rt.denoised;
         case GKCU_PEER_FLAGS:
             if (!c.peer_flags.p) {
                 if (!c.peer_flags.reserve(32 * 8)) return nullptr;
@@ -1815,6 +1822,72 @@ int run_resolve_strip(Context& c, const GkUniformBufferObject& ubo, const GkcuFr
         c.launches += 2;
     }
     c.launches++;
+    GK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+void path_preload() {  // see post_preload (gk_post.cu)
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_resolve_strip);
+    cudaFuncGetAttributes(&fa, k_resolve);
+    cudaFuncGetAttributes(&fa, k_peer_signal);
+    cudaFuncGetAttributes(&fa, k_peer_wait);
+}
+
+// The tail of a multi-GPU frame with nothing left to rank 0 alone, see gkcu_render_resolve_post_strip (include/gkcu.h).
+int run_resolve_post_strip(Context& c, const GkUniformBufferObject& ubo, const GkcuFrameParams& p) {
+    const int world = (int)std::max(1u, p.spp_world), rank = (int)p.spp_rank;
+    if (world > GKCU_MAX_PEERS) { set_error("gkcu_render_resolve_post_strip: spp_world > 8"); return 1; }
+    if (rank >= world) { set_error("gkcu_render_resolve_post_strip: spp_rank >= spp_world"); return 1; }
+    if (c.rt.denoised_ext) { set_error("gkcu_render_resolve_post_strip: RT_DENOISED is bound to external memory; use gkcu_render_resolve_strip + gkcu_run_post"); return 1; }
+    const int cur = c.rt.cur;
+    PeerRadiance P{};
+    PeerFlags F{};
+    PostStrip S;
+    for (int r = 0; r < world; ++r) {
+        P.rad[r] = static_cast<const float4*>(c.peer[r][GKCU_PEER_RADIANCE]);
+        F.block[r] = static_cast<unsigned long long*>(c.peer[r][GKCU_PEER_FLAGS]);
+        void *ad = c.peer[r][GKCU_PEER_ACCUM_DIFFUSE_0 + cur], *as = c.peer[r][GKCU_PEER_ACCUM_SPECULAR_0 + cur], *aa = c.peer[r][GKCU_PEER_ACCUM_ALBEDO_0 + cur];
+        if (!P.rad[r] || !F.block[r] || !ad || !as || !aa || !c.peer[r][GKCU_PEER_ACCUM_DIFFUSE_0 + (cur ^ 1)] || !c.peer[r][GKCU_PEER_ACCUM_SPECULAR_0 + (cur ^ 1)] ||
+            !c.peer[r][GKCU_PEER_ACCUM_ALBEDO_0 + (cur ^ 1)]) {
+            set_error("gkcu_render_resolve_post_strip: radiance / flags / ACCUM_* buffers of rank " + std::to_string(r) + " not imported");
+            return 1;
+        }
+        if (r != rank) {
+            S.mirror_diffuse[S.n_mirror] = static_cast<uint2*>(ad);
+            S.mirror_specular[S.n_mirror] = static_cast<uint2*>(as);
+            S.mirror_albedo[S.n_mirror] = static_cast<uint2*>(aa);
+            ++S.n_mirror;
+        }
+    }
+    void *d0 = c.peer[0][GKCU_PEER_DIRECT], *dn0 = c.peer[0][GKCU_PEER_DENOISED];
+    if (!d0 || !dn0) { set_error("gkcu_render_resolve_post_strip: rank 0's direct / RT_DENOISED buffers not imported"); return 1; }
+    const int h = (int)c.rt.h, w = (int)c.rt.w;
+    const uint32_t n = (uint32_t)w * (uint32_t)h;
+    S.own_y0 = (int)((uint64_t)rank * h / world);
+    S.own_y1 = (int)((uint64_t)(rank + 1) * h / world);
+    S.y_begin = std::max(0, S.own_y0 - 5);   // the compose pass reads ACCUM_DIFFUSE 5 rows either side (Process.DenoiseJBF.comp.slang:133)
+    S.y_end = std::min(h, S.own_y1 + 5);
+    const int ry0 = std::max(0, S.y_begin - 2), ry1 = std::min(h, S.y_end + 2);  // the reproject pass reads SINGLE_* 2 rows either side (:120-139)
+    S.denoised = rank == 0 ? nullptr : static_cast<uint2*>(dn0);
+    cudaStream_t st = c.stream;
+    if (rank == 0 && c.copy_pending) {  // the asynchronous present of the previous frame still reads RT_DENOISED, which the other ranks are about to write
+        cudaStreamWaitEvent(st, c.copy_done, 0);
+        c.copy_pending = false;
+    }
+    unsigned long long* mine = F.block[rank];
+    ++c.peer_epoch;
+    k_peer_signal<<<1, 32, 0, st>>>(F, world, rank, 0, c.peer_epoch);   // my sums are complete (and rank 0's image is free)
+    k_peer_wait<<<1, 32, 0, st>>>(mine, world, 0, c.peer_epoch);        // ... and so are everybody's
+    const uint32_t first = (uint32_t)ry0 * (uint32_t)w, last = (uint32_t)ry1 * (uint32_t)w;
+    if (last > first)
+        k_resolve_strip<<<(last - first + 255) / 256, 256, 0, st>>>(c.rt.single_diffuse, c.rt.single_specular, P, world, static_cast<const float4*>(d0), c.rt.moment, ubo, n, first, last);
+    c.launches += 3;
+    if (run_reproject(c, p, &S)) return 1;
+    if (run_denoise(c, ubo, &S)) return 1;
+    k_peer_signal<<<1, 32, 0, st>>>(F, world, rank, 8, c.peer_epoch);   // my strip of RT_DENOISED and of everyone's history has landed; I no longer read anyone's sums
+    k_peer_wait<<<1, 32, 0, st>>>(mine, world, 8, c.peer_epoch);        // all strips landed: rank 0 may present, everyone may start the next frame
+    c.launches += 2;
     GK_CUDA(cudaGetLastError());
     return 0;
 }

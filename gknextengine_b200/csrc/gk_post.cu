@@ -5,6 +5,8 @@
 // loads return 0 and out-of-bounds stores are dropped, like Vulkan robust image access.
 // The "copy pass" (ACCUM -> PREV x3, PathTracingRenderer.cpp:160-182) and the object-id copy (VulkanBaseRenderer.cpp:1136-1152)
 // are pointer swaps done by the caller; ReProject therefore writes ACCUM.a = PREV.a where the reference leaves alpha untouched.
+#include <algorithm>
+
 #include "gk_context.h"
 #include "gk_tma.cuh"
 
@@ -34,7 +36,25 @@ struct ReprojArgs {
     const uint16_t* moment;
     uint32_t progressive, fast_reproject;
     int temporal_frames;
+    // strip-parallel post (multi-GPU): only rows [y_begin, y_end) are processed; rows [own_y0, own_y1) are also stored into the ACCUM_*
+    // images of n_mirror other ranks over peer memory, so that every rank holds the whole history for the next frame's reprojection
+    int y_begin, y_end, own_y0, own_y1, n_mirror;
+    uint2 *mirror_diffuse[GKCU_MAX_PEERS - 1], *mirror_specular[GKCU_MAX_PEERS - 1], *mirror_albedo[GKCU_MAX_PEERS - 1];
 };
+
+GK_DEV void store_accum(const ReprojArgs& A, size_t idx, int y, float4 d, float4 s, float4 a) {
+    store_h4(A.accum_diffuse, idx, d);
+    store_h4(A.accum_specular, idx, s);
+    store_h4(A.accum_albedo, idx, a);
+    if (A.n_mirror && y >= A.own_y0 && y < A.own_y1) {
+        const uint2 dd = A.accum_diffuse[idx], ss = A.accum_specular[idx], aa = A.accum_albedo[idx];  // the fp16 bits just stored
+        for (int r = 0; r < A.n_mirror; ++r) {
+            A.mirror_diffuse[r][idx] = dd;
+            A.mirror_specular[r][idx] = ss;
+            A.mirror_albedo[r][idx] = aa;
+        }
+    }
+}
 
 GK_DEV bool inb(int x, int y, int w, int h) { return x >= 0 && y >= 0 && x < w && y < h; }
 GK_DEV float4 ld4(const uint2* img, int x, int y, int w, int h) { return inb(x, y, w, h) ? load_h4(img, (size_t)y * w + x) : f4(0, 0, 0, 0); }
@@ -68,16 +88,15 @@ __global__ void __launch_bounds__(RBX* RBY) k_reproject(ReprojArgs A) {
     __shared__ uint32_t s_id[RTH][RTW];
     __shared__ float s_mlen[RMHH][RMW];
     const int w = A.w, h = A.h;
-    const int bx0 = blockIdx.x * RBX, by0 = blockIdx.y * RBY;
+    const int bx0 = blockIdx.x * RBX, by0 = A.y_begin + blockIdx.y * RBY;
     const int tid = threadIdx.y * RBX + threadIdx.x;
     const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
     const float k512 = clampf(1.0f / 512.0f, 0.0f, 1.0f);
     if (A.progressive) {  // :95-101
-        if (x < w && y < h) {
+        if (x < w && y < A.y_end) {
             size_t i = (size_t)y * w + x;
-            store_h4(A.accum_diffuse, i, lerp4(load_h4(A.prev_diffuse, i), load_h4(A.single_diffuse, i), k512));
-            store_h4(A.accum_specular, i, lerp4(load_h4(A.prev_specular, i), load_h4(A.single_specular, i), k512));
-            store_h4(A.accum_albedo, i, lerp4(load_h4(A.prev_albedo, i), load_h4(A.albedo, i), k512));
+            store_accum(A, i, y, lerp4(load_h4(A.prev_diffuse, i), load_h4(A.single_diffuse, i), k512),
+                        lerp4(load_h4(A.prev_specular, i), load_h4(A.single_specular, i), k512), lerp4(load_h4(A.prev_albedo, i), load_h4(A.albedo, i), k512));
         }
         return;
     }
@@ -99,7 +118,7 @@ __global__ void __launch_bounds__(RBX* RBY) k_reproject(ReprojArgs A) {
         s_mlen[ty][tx] = length(m);
     }
     __syncthreads();
-    if (x >= w || y >= h) return;
+    if (x >= w || y >= A.y_end) return;
     const size_t idx = (size_t)y * w + x;
     const int lx = threadIdx.x + RH, ly = threadIdx.y + RH;
     auto h4 = [](uint2 v) {
@@ -151,13 +170,10 @@ __global__ void __launch_bounds__(RBX* RBY) k_reproject(ReprojArgs A) {
         float3 s = lerp3(historySpecular, xyz(currSpecularSample), currKeep);
         float3 a = lerp3(historyAlbedo, xyz(currAlbedoSample), currKeep);
         // ".rgb =" stores keep the texel's alpha, which after the copy pass equals PREV's alpha
-        store_h4(A.accum_diffuse, idx, f4(d.x, d.y, d.z, load_h4(A.prev_diffuse, idx).w));
-        store_h4(A.accum_specular, idx, f4(s.x, s.y, s.z, load_h4(A.prev_specular, idx).w));
-        store_h4(A.accum_albedo, idx, f4(a.x, a.y, a.z, load_h4(A.prev_albedo, idx).w));
+        store_accum(A, idx, y, f4(d.x, d.y, d.z, load_h4(A.prev_diffuse, idx).w), f4(s.x, s.y, s.z, load_h4(A.prev_specular, idx).w),
+                    f4(a.x, a.y, a.z, load_h4(A.prev_albedo, idx).w));
     } else {
-        store_h4(A.accum_diffuse, idx, currDiffuseSample);
-        store_h4(A.accum_specular, idx, currSpecularSample);
-        store_h4(A.accum_albedo, idx, currAlbedoSample);
+        store_accum(A, idx, y, currDiffuseSample, currSpecularSample, currAlbedoSample);
     }
 }
 
@@ -182,7 +198,7 @@ __global__ void __launch_bounds__(RBX* RBY) k_reproject_tma(const __grid_constan
     __shared__ float s_mlen[RMHH][RMW];
     __shared__ uint64_t bar;
     const int w = A.w, h = A.h;
-    const int bx0 = blockIdx.x * RBX, by0 = blockIdx.y * RBY;
+    const int bx0 = blockIdx.x * RBX, by0 = A.y_begin + blockIdx.y * RBY;
     const int tid = threadIdx.y * RBX + threadIdx.x;
     const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
     if (tid == 0) gktma::mbar_init(&bar, 1);
@@ -212,7 +228,7 @@ __global__ void __launch_bounds__(RBX* RBY) k_reproject_tma(const __grid_constan
         s_mlen[ty][tx] = length(r_motion[ty][tx]);
     }
     __syncthreads();
-    if (x >= w || y >= h) return;
+    if (x >= w || y >= A.y_end) return;
     const size_t idx = (size_t)y * w + x;
     const int lx = threadIdx.x + RH, ly = threadIdx.y + RH;
     float4 currDiffuseSample = s_diff[ly][lx], currSpecularSample = s_spec[ly][lx], currAlbedoSample = load_h4(A.albedo, idx);
@@ -258,13 +274,10 @@ __global__ void __launch_bounds__(RBX* RBY) k_reproject_tma(const __grid_constan
         float3 d = lerp3(historyDiffuse, xyz(currDiffuseSample), currKeep);
         float3 s = lerp3(historySpecular, xyz(currSpecularSample), currKeep);
         float3 a = lerp3(historyAlbedo, xyz(currAlbedoSample), currKeep);
-        store_h4(A.accum_diffuse, idx, f4(d.x, d.y, d.z, load_h4(A.prev_diffuse, idx).w));
-        store_h4(A.accum_specular, idx, f4(s.x, s.y, s.z, load_h4(A.prev_specular, idx).w));
-        store_h4(A.accum_albedo, idx, f4(a.x, a.y, a.z, load_h4(A.prev_albedo, idx).w));
+        store_accum(A, idx, y, f4(d.x, d.y, d.z, load_h4(A.prev_diffuse, idx).w), f4(s.x, s.y, s.z, load_h4(A.prev_specular, idx).w),
+                    f4(a.x, a.y, a.z, load_h4(A.prev_albedo, idx).w));
     } else {
-        store_h4(A.accum_diffuse, idx, currDiffuseSample);
-        store_h4(A.accum_specular, idx, currSpecularSample);
-        store_h4(A.accum_albedo, idx, currAlbedoSample);
+        store_accum(A, idx, y, currDiffuseSample, currSpecularSample, currAlbedoSample);
     }
 }
 
@@ -278,6 +291,7 @@ struct DenoiseArgs {
     const uint2 *accum_diffuse, *accum_specular, *accum_albedo;
     uint2* denoised;
     const GkUniformBufferObject* cam;
+    int y_begin, y_end;  // rows processed (strip-parallel post: this rank's strip; `denoised` may then be rank 0's image over peer memory)
 };
 
 GK_DEV float exp2f_approx(float x) { float y; asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -389,7 +403,7 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
     const GkUniformBufferObject* C = A.cam;
     const int w = A.w, h = A.h;
     const int gx0 = (int)C->ViewportRect.x, gy0 = (int)C->ViewportRect.y;
-    const int bx0 = blockIdx.x * DBX + gx0, by0 = blockIdx.y * DBY + gy0;
+    const int bx0 = blockIdx.x * DBX + gx0, by0 = blockIdx.y * DBY + gy0 + A.y_begin;
     const int tid = threadIdx.y * DBX + threadIdx.x;
     const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
     const bool filter = C->BFSize > 0;
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise(DenoiseArgs A) {
         }
         __syncthreads();
     }
-    if (!inb(x, y, w, h)) return;
+    if (!inb(x, y, w, h) || y >= A.y_end) return;
     const size_t idx = (size_t)y * w + x;
     float3 Total = f3(0, 0, 0);
     if (filter) {
@@ -429,7 +443,7 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise_tma(const __grid_constant_
     const GkUniformBufferObject* C = A.cam;
     const int w = A.w, h = A.h;
     const int gx0 = (int)C->ViewportRect.x, gy0 = (int)C->ViewportRect.y;
-    const int bx0 = blockIdx.x * DBX + gx0, by0 = blockIdx.y * DBY + gy0;
+    const int bx0 = blockIdx.x * DBX + gx0, by0 = blockIdx.y * DBY + gy0 + A.y_begin;
     const int tid = threadIdx.y * DBX + threadIdx.x;
     const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
     if (tid == 0) gktma::mbar_init(&bar, 1);
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise_tma(const __grid_constant_
         s_diff[ty][tx] = f4(c.x, c.y, c.z, dot(c, f3(0.212671f, 0.715160f, 0.072169f)));
     }
     __syncthreads();
-    if (!inb(x, y, w, h)) return;
+    if (!inb(x, y, w, h) || y >= A.y_end) return;
     const size_t idx = (size_t)y * w + x;
     const float3 CenterSpec = xyz(load_h4(A.accum_specular, idx)) + f3(0.001f, 0.001f, 0.001f);
     float3 Total = jbf_filter<FAST>(s_diff, s_F, threadIdx.y + DR, threadIdx.x + DR, C->BFSigmaLum * 100.0f);
@@ -459,9 +473,23 @@ __global__ void __launch_bounds__(DBX* DBY) k_denoise_tma(const __grid_constant_
 
 }  // namespace
 
-int run_reproject(Context& c, const GkcuFrameParams& p) {
+// CUDA loads a kernel's code at its first launch (lazy loading), and that load waits for the device to drain. In a multi-GPU frame the first
+// launch of these kernels would come while this rank's barrier kernel is spinning for its peers - with several ranks in one process (the tests)
+// that is a deadlock until the barrier times out. Resolve them up front.
+void post_preload() {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_reproject);
+    cudaFuncGetAttributes(&fa, k_reproject_tma<0>);
+    cudaFuncGetAttributes(&fa, k_reproject_tma<2>);
+    cudaFuncGetAttributes(&fa, k_denoise<false>);
+    cudaFuncGetAttributes(&fa, k_denoise<true>);
+    cudaFuncGetAttributes(&fa, k_denoise_tma<false>);
+    cudaFuncGetAttributes(&fa, k_denoise_tma<true>);
+}
+
+int run_reproject(Context& c, const GkcuFrameParams& p, const PostStrip* strip) {
     RenderTargets& t = c.rt;
-    ReprojArgs A;
+    ReprojArgs A{};
     A.w = (int)t.w; A.h = (int)t.h;
     A.single_diffuse = t.single_diffuse; A.single_specular = t.single_specular; A.albedo = t.albedo; A.normal = t.normal;
     A.prev_diffuse = t.accum_diffuse[t.cur ^ 1]; A.prev_specular = t.accum_specular[t.cur ^ 1]; A.prev_albedo = t.accum_albedo[t.cur ^ 1];
@@ -469,7 +497,14 @@ int run_reproject(Context& c, const GkcuFrameParams& p) {
     A.objectid0 = t.objectid[t.cur]; A.objectid1 = t.objectid[t.cur ^ 1];
     A.motion = t.motion; A.moment = t.moment;
     A.progressive = p.progressive; A.fast_reproject = p.fast_reproject; A.temporal_frames = p.temporal_frames;
-    dim3 grid((t.w + RBX - 1) / RBX, (t.h + RBY - 1) / RBY), block(RBX, RBY);
+    A.y_begin = 0; A.y_end = (int)t.h; A.own_y0 = A.own_y1 = 0; A.n_mirror = 0;
+    if (strip) {
+        A.y_begin = std::max(0, strip->y_begin); A.y_end = std::min((int)t.h, strip->y_end);
+        A.own_y0 = strip->own_y0; A.own_y1 = strip->own_y1; A.n_mirror = strip->n_mirror;
+        for (int r = 0; r < strip->n_mirror; ++r) { A.mirror_diffuse[r] = strip->mirror_diffuse[r]; A.mirror_specular[r] = strip->mirror_specular[r]; A.mirror_albedo[r] = strip->mirror_albedo[r]; }
+        if (A.y_end <= A.y_begin) return 0;
+    }
+    dim3 grid((t.w + RBX - 1) / RBX, (A.y_end - A.y_begin + RBY - 1) / RBY), block(RBX, RBY);
     // TMA staging needs 16-byte aligned rows (even width for the 8-byte pixels, width % 4 == 0 for the 4-byte ids)
     ReprojMaps M;
     const bool tma = (c.use_tma == 1 || c.use_tma == 2) && !p.progressive && (t.w % 4 == 0) &&
@@ -489,7 +524,7 @@ int run_reproject(Context& c, const GkcuFrameParams& p) {
     return 0;
 }
 
-int run_denoise(Context& c, const GkUniformBufferObject& ubo) {
+int run_denoise(Context& c, const GkUniformBufferObject& ubo, const PostStrip* strip) {
     if (c.copy_pending) {  // an asynchronous present of the previous frame still reads RT_DENOISED
         cudaStreamWaitEvent(c.stream, c.copy_done, 0);
         c.copy_pending = false;
@@ -500,7 +535,13 @@ int run_denoise(Context& c, const GkUniformBufferObject& ubo) {
     A.accum_diffuse = t.accum_diffuse[t.cur]; A.accum_specular = t.accum_specular[t.cur]; A.accum_albedo = t.accum_albedo[t.cur];
     A.denoised = t.denoised_out();
     A.cam = c.ubo.as<GkUniformBufferObject>();
-    dim3 grid((t.w + DBX - 1) / DBX, (t.h + DBY - 1) / DBY), block(DBX, DBY);
+    A.y_begin = 0; A.y_end = (int)t.h;
+    if (strip) {
+        A.y_begin = std::max(0, strip->own_y0); A.y_end = std::min((int)t.h, strip->own_y1);
+        if (strip->denoised) A.denoised = strip->denoised;
+        if (A.y_end <= A.y_begin) return 0;
+    }
+    dim3 grid((t.w + DBX - 1) / DBX, (A.y_end - A.y_begin + DBY - 1) / DBY), block(DBX, DBY);
     CUtensorMap map;
     if ((c.use_tma == 1 || c.use_tma == 3) && ubo.BFSize > 0 && (t.w % 2 == 0) && ((int)ubo.ViewportRect.x % 2 == 0) && gktma::encode_2d(&map, t.accum_diffuse[t.cur], CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, t.w, t.h, DTWP, DTH))
         c.fast_stencil ? k_denoise_tma<true><<<grid, block, 0, c.stream>>>(map, A) : k_denoise_tma<false><<<grid, block, 0, c.stream>>>(map, A);

@@ -64,6 +64,7 @@ def lib():
         L.gkcu_probes_read.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gkcu_peer_export.argtypes = [P, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
         L.gkcu_peer_import.argtypes = [P, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.gkcu_render_resolve_post_strip.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
         L.gkcu_render_resolve_strip.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
         L.gkcu_render_frame.argtypes = [P, C.POINTER(GkUniformBufferObject), C.POINTER(GkcuFrameParams)]
         L.gkcu_radiance_buffer.argtypes = [P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -247,6 +248,9 @@ class CudaPathTracingRenderer:
         return p.value, n.value
 
     PEER_RADIANCE, PEER_DIRECT, PEER_SINGLE_DIFFUSE, PEER_SINGLE_SPECULAR, PEER_FLAGS = 0, 1, 2, 3, 4
+    PEER_ACCUM = (5, 6, 7, 8, 9, 10)  # both halves of the ACCUM_DIFFUSE / SPECULAR / ALBEDO ping-pong pairs
+    PEER_DENOISED = 11
+    PEER_KINDS = 12
 
     def peer_export(self, what):
         """(64-byte cudaIpcMemHandle, raw device pointer) of one of this rank's buffers."""
@@ -264,6 +268,11 @@ class CudaPathTracingRenderer:
         """Fused reduce + resolve of this rank's strip over peer memory. With every rank's PEER_FLAGS imported the two cross-rank
         barriers run on the device; otherwise the caller brackets this call with its own stream-ordered barriers."""
         _ck(lib().gkcu_render_resolve_strip(self._ctx, C.byref(ubo), C.byref(params)))
+
+    def ResolvePostStrip(self, ubo, params):
+        """The whole tail of a multi-GPU frame on every rank: strip resolve + strip reproject (history mirrored to every rank) + strip compose
+        into rank 0's RT_DENOISED, between two device barriers (gkcu_render_resolve_post_strip)."""
+        _ck(lib().gkcu_render_resolve_post_strip(self._ctx, C.byref(ubo), C.byref(params)))
 
     def Resolve(self, ubo, params):
         _ck(lib().gkcu_render_resolve(self._ctx, C.byref(ubo), C.byref(params)))

@@ -396,9 +396,19 @@ int gkcu_render_resolve(GkcuContext* ctx, const GkUniformBufferObject* ubo, cons
  * issues no collective at all. */
 #define GKCU_IPC_HANDLE_BYTES 64
 #define GKCU_MAX_PEERS 8
-enum { GKCU_PEER_RADIANCE = 0, GKCU_PEER_DIRECT = 1, GKCU_PEER_SINGLE_DIFFUSE = 2, GKCU_PEER_SINGLE_SPECULAR = 3, GKCU_PEER_FLAGS = 4 };
+enum { GKCU_PEER_RADIANCE = 0, GKCU_PEER_DIRECT = 1, GKCU_PEER_SINGLE_DIFFUSE = 2, GKCU_PEER_SINGLE_SPECULAR = 3, GKCU_PEER_FLAGS = 4,
+       /* strip-parallel post (gkcu_render_resolve_post_strip): both halves of the ACCUM_* ping-pong pairs of every rank, RT_DENOISED of rank 0 */
+       GKCU_PEER_ACCUM_DIFFUSE_0 = 5, GKCU_PEER_ACCUM_DIFFUSE_1 = 6, GKCU_PEER_ACCUM_SPECULAR_0 = 7, GKCU_PEER_ACCUM_SPECULAR_1 = 8,
+       GKCU_PEER_ACCUM_ALBEDO_0 = 9, GKCU_PEER_ACCUM_ALBEDO_1 = 10, GKCU_PEER_DENOISED = 11, GKCU_PEER_KINDS = 12 };
 int gkcu_peer_export(GkcuContext* ctx, uint32_t what, void* handle, void** device_ptr);
 int gkcu_peer_import(GkcuContext* ctx, uint32_t rank, uint32_t what, const void* handle, void* device_ptr);
+/* The whole tail of a multi-GPU frame on every rank, nothing left to rank 0 alone (replaces gkcu_render_resolve_strip + gkcu_run_post on rank 0):
+ * device barrier -> this rank resolves its strip of rows (+ 7 halo rows either side, from every rank's radiance sums over peer memory) into its
+ * OWN SINGLE_* images -> reproject pass on the strip + 5 halo rows, the owned rows also stored into every other rank's ACCUM_* (so all ranks
+ * hold the full history the next frame's reprojection may look up anywhere) -> compose pass on the owned rows, stored into rank 0's
+ * RT_DENOISED -> device barrier -> ping-pong swap. Halo rows are recomputed, not exchanged: identical inputs, identical bits. Needs, from
+ * every rank, RADIANCE, FLAGS and the six ACCUM_* buffers, and from rank 0 DIRECT and DENOISED (gkcu_peer_import). */
+int gkcu_render_resolve_post_strip(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params);
 int gkcu_render_resolve_strip(GkcuContext* ctx, const GkUniformBufferObject* ubo, const GkcuFrameParams* params);
 
 /* Blocking device->host copy of one storage image in its reference format

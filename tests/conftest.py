@@ -4,6 +4,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Several tests run 2-3 renderer contexts on ONE GPU as stand-ins for 2-3 GPUs, with device-side barriers between their streams: a kernel of one
+# context waits for a kernel of another. Streams that share a hardware queue would serialise those kernels, so give the device more queues than
+# the default 8 (must be set before the CUDA context exists). One process per GPU, as in production and bench.py, does not need it.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

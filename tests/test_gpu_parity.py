@@ -706,6 +706,57 @@ def test_peer_memory_strip_resolve_matches_oracle(sky, world, device_barrier):
         r.close()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_strip_parallel_post_over_peer_memory_matches_oracle(sky, world):
+    """gkcu_render_resolve_post_strip: every rank resolves, reprojects and composes its own strip of rows (halo rows recomputed), mirrors its
+    history strip into every other rank and stores its part of RT_DENOISED into rank 0 - nothing is left to rank 0 alone. `world` contexts on
+    one GPU stand in for `world` GPUs. Five frames of an orbiting camera, so the reprojection looks up history rows that another rank wrote:
+    rank 0's RT_DENOISED and EVERY rank's ACCUM_* must equal the oracle's frame up to the association of the per-rank partial sums (the
+    oracle keeps one running sum per pixel; a handful of fp16 stores flip, same allowance as test_peer_memory_strip_resolve_matches_oracle),
+    and all ranks must hold IDENTICAL history images - that is what the mirrored strips are for."""
+    W, H = 256, 146  # uneven strips for three ranks
+    scene = host.Scene("RTIO.proc", samples=6, bounces=4, taa=True, temporal_frames=8, denoiser=True)
+    scene.update_nodes()
+    rs = []
+    for rank in range(world):
+        r = CudaPathTracingRenderer(0)
+        r.CreateSwapChain((W, H))
+        r.OnPostLoadScene(scene, sky)
+        rs.append(r)
+    exports = [{what: r.peer_export(what)[1] for what in range(r.PEER_KINDS)} for r in rs]
+    for r in rs:
+        for rank in range(world):
+            for what in (r.PEER_RADIANCE, r.PEER_FLAGS) + r.PEER_ACCUM:
+                r.peer_import(rank, what, ptr=exports[rank][what])
+        for what in (r.PEER_DIRECT, r.PEER_DENOISED):
+            r.peer_import(0, what, ptr=exports[0][what])
+    osc, ofr = O.OracleScene(scene, sky), O.OracleFrame(W, H)
+    limit = 2e-3
+    try:
+        for f in range(1, 6):
+            ubo = scene.ubo(W, H, f, model_rotation_deg=(f / 60.0) * 40.0)
+            for rank, r in enumerate(rs):
+                r.Render(ubo, params(spp_world=world, spp_rank=rank, skip_post=1, temporal_frames=8))
+            for rank, r in enumerate(rs):
+                r.ResolvePostStrip(ubo, params(spp_world=world, spp_rank=rank, skip_post=1, temporal_frames=8))
+            for r in rs:
+                r.BeforeNextFrame()
+            ofr.render(osc, ubo, params(spp_world=world, temporal_frames=8))
+            ulps = denoised_ulps(rs[0].readback(RT["DENOISED"]), ofr.image(RT["DENOISED"]))
+            assert float((ulps > 2).any(axis=2).mean()) <= limit, (f, int(ulps.max()))
+            for name in ("SINGLE_PREV_DIFFUSE", "SINGLE_PREV_SPECULAR", "SINGLE_PREV_ALBEDO"):  # the swap has happened: this frame's accumulation is PREV now
+                mine = [r.readback(RT[name]) for r in rs]
+                assert mismatch_fraction(mine[0], ofr.image(RT[name])) <= limit * f, (f, name)  # differences accumulate through the history
+                for rank in range(1, world):
+                    assert np.array_equal(mine[rank].view(np.uint16), mine[0].view(np.uint16)), (f, rank, name)
+        assert np.abs(rs[0].readback(RT["MOTIONVECTOR"])).max() > 0.05
+        with pytest.raises(GkcuError):
+            rs[0].ResolvePostStrip(ubo, params(spp_world=world + 1, spp_rank=0, skip_post=1))  # rank `world` never imported
+    finally:
+        for r in rs:
+            r.close()
+
+
 def test_full_size_properties_1080p(sky):
     """BASELINE config 2 at full size (1920x1080, 16 spp, 8 bounces): size-independent properties — determinism, exact ray
     accounting, wavefront == megakernel, finite output — plus oracle parity on sampled rows."""
