@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B)
     }
     // collapse to Node4, BFS; counters[8] node4 counter, [9] next-level queue size, [10] this level's queue size, [16 + L] level table
     int2 *qa = B.qa, *qb = B.qb;
-    if (t == 0) { qa[0] = make_int2(0, 0); counters[8] = 1; counters[9] = 0; counters[10] = 1; counters[12] = (int)GK_LEAF_SLACK; }
+    if (t == 0) { qa[0] = make_int2(0, 0); counters[8] = 1; counters[9] = 0; counters[10] = 1; counters[12] = (int)GK_LEAF_SLACK; counters[13] = counters[14] = counters[15] = 0; }  // 13-15: unused, published with the rest
     for (int i = t; i < 48; i += T) counters[16 + i] = 0;
     sync();
     for (int level = 0; level < 46; ++level) {

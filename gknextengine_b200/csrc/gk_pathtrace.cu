@@ -377,15 +377,24 @@ GK_DEV void store_slot(const PathView& V, int qi, uint32_t slot, uint32_t pixel,
         V.dir[i] = f4(P.dir.x, P.dir.y, P.dir.z, 0.0f);
     }
 }
-GK_DEV void load_slot(const PathView& V, const SceneView& S, int qi, uint32_t slot, bool any, PathRegs& P) {
+// the four records every slot has, as loaded (k_shade issues these loads before it knows the queue size, see there)
+struct SlotRaw { float4 o, d, ray_color; uint4 rng; };
+GK_DEV SlotRaw load_slot_raw(const PathView& V, int qi, uint32_t slot) {
     const size_t i = (size_t)qi * V.pixels + slot;
-    const float4 o = V.ray_o[i], d = V.ray_d[i];
+    SlotRaw r;
+    r.o = V.ray_o[i]; r.d = V.ray_d[i]; r.rng = V.rng[i]; r.ray_color = V.ray_color[i];
+    return r;
+}
+GK_DEV void load_slot(const PathView& V, const SceneView& S, int qi, uint32_t slot, bool any, PathRegs& P, const SlotRaw* raw = nullptr) {
+    const size_t i = (size_t)qi * V.pixels + slot;
+    const SlotRaw r = raw ? *raw : load_slot_raw(V, qi, slot);
+    const float4 o = r.o, d = r.d;
     P.ro = f3(o.x, o.y, o.z); P.flags = __float_as_uint(o.w);
     P.rd = f3(d.x, d.y, d.z);
     const uint32_t cnt = __float_as_uint(d.w);
     P.sample = cnt & 0xFFFF; P.bounce = cnt >> 16;
-    P.rng = V.rng[i];
-    P.rayColor = V.ray_color[i];
+    P.rng = r.rng;
+    P.rayColor = r.ray_color;
     if (any) {
         const float4 a = V.pos_mat[i], b = V.nrm[i], c = V.dir[i];
         P.pos = f3(a.x, a.y, a.z); P.mat = __float_as_uint(a.w);
@@ -1276,6 +1285,20 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
     SceneView S = S_;
     S.cam = &cam;
+    // The slot's records are requested BEFORE the queue size: every block used to start by waiting a full memory round trip for the 16-byte
+    // header (13 % of the kernel's stall samples, profiles/r02_experiments.md) and only then issue its loads. The grid never exceeds the
+    // queue's capacity, so a slot beyond the current size is allocated memory with stale contents that are simply not used.
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_cap = slot < (uint32_t)V.pixels;
+    uint32_t sp = 0, hprim = 0;
+    float4 hv = f4(0, 0, 0, 0);
+    SlotRaw raw{};
+    if (in_cap) {
+        sp = V.slot_pixel[qi][slot];
+        hv = V.hit_tuv[slot];
+        hprim = V.hit_prim[slot];
+        raw = load_slot_raw(V, qi, slot);
+    }
     const uint4 hdr = *reinterpret_cast<const uint4*>(V.counts);  // queue sizes, trace cursor, stop flag: one load
     if (hdr.w) return;  // the wavefront has stopped (wave_stopped): the queue is k_tail's
     const uint32_t n = qi ? hdr.y : hdr.x;
@@ -1285,18 +1308,14 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
     }
     PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
     uint32_t nclosest = 0, nany = 0;
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool want = false;
     int req = REQ_DONE;
     uint32_t pixel = 0;
     PathRegs P;
-    if (slot < n) {
-        const size_t i = (size_t)qi * V.pixels + slot;
-        const uint32_t sp = V.slot_pixel[qi][slot];
-        const float4 hv = V.hit_tuv[slot];
+    if (slot < n && in_cap) {
         Hit h;
-        h.t = hv.x; h.u = hv.y; h.v = hv.z; h.inst = __float_as_uint(hv.w); h.prim = V.hit_prim[slot];
-        load_slot(V, S, qi, slot, (sp & 0x80000000u) != 0, P);
+        h.t = hv.x; h.u = hv.y; h.v = hv.z; h.inst = __float_as_uint(hv.w); h.prim = hprim;
+        load_slot(V, S, qi, slot, (sp & 0x80000000u) != 0, P, &raw);
         pixel = sp & 0x7FFFFFFFu;
         if (sp & 0x80000000u) nany++; else nclosest++;
         req = advance(S, O, cfg, V, pixel, P, h);

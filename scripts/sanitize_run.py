@@ -40,3 +40,36 @@ for (W, H) in ((96, 56), (101, 57)):          # TMA stencils / plain-load stenci
         print(name, W, H, r.counters())
         r.close()
 print("sanitize run finished")
+
+# ---- round 2 additions: visibility front end, quantised nodes, tolerance stencil, unchanged-node skip, strip-parallel tail (one rank: its own peer)
+for fmt in ("4", "8"):
+    os.environ["GKCU_NODE_FORMAT"] = fmt
+    W, H = 96, 56
+    scene = host.Scene("RTIO.proc", samples=2, bounces=4, taa=True, denoiser=True)
+    scene.update_nodes()
+    r = CudaPathTracingRenderer(0)
+    r.CreateSwapChain((W, H))
+    r.OnPostLoadScene(scene, host.make_sky(64, 32))
+    pv = GkcuFrameParams(temporal_frames=16, spp_world=1, primary_visibility=1)
+    for f in range(1, 3):                       # the second frame culls against the first frame's depth
+        r.Render(scene.ubo(W, H, f), pv)
+        r.BeforeNextFrame()
+    print("visibility front end", fmt, r.gpu_driven_stats())
+    r.set_fast_stencil(True)
+    r.set_skip_unchanged_nodes(True)
+    r.set_kernel_timing(False)
+    for f in range(3, 5):
+        r.AfterUpdateScene(scene)
+        r.PreRender()
+        r.Render(scene.ubo(W, H, f), GkcuFrameParams(temporal_frames=16, spp_world=1))
+        r.BeforeNextFrame()
+    r.set_fast_stencil(False)
+    for what in range(r.PEER_KINDS):
+        r.peer_import(0, what, ptr=r.peer_export(what)[1])
+    for f in range(5, 7):
+        ps = GkcuFrameParams(temporal_frames=16, spp_world=1, spp_rank=0, skip_post=1)
+        r.Render(scene.ubo(W, H, f), ps)
+        r.ResolvePostStrip(scene.ubo(W, H, f), ps)
+        r.BeforeNextFrame()
+    print("node format", fmt, r.counters())
+    r.close()
