@@ -132,6 +132,9 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     if (const char* e = getenv("GKCU_TMA")) c.use_tma = atoi(e);
     if (const char* e = getenv("GKCU_FAST_STENCIL")) c.fast_stencil = atoi(e) != 0;
     if (const char* e = getenv("GKCU_SHADE_MINB")) c.shade_minb = atoi(e);
+    if (const char* e = getenv("GKCU_TRACE_RPB")) c.trace_rpb = std::max(32, std::min(65536, atoi(e)));
+    if (const char* e = getenv("GKCU_TRACE_GRID")) c.trace_grid_mult = std::max(1, std::min(64, atoi(e)));
+    if (const char* e = getenv("GKCU_MATCH_CARVEOUT")) c.match_carveout = atoi(e) != 0;
     if (const char* e = getenv("GKCU_TRACE_CARVEOUT")) c.trace_carveout = std::max(-1, std::min(100, atoi(e)));
     if (const char* e = getenv("GKCU_SORT_RAYS")) c.sort_rays = std::max(0, std::min(19, atoi(e)));
     if (const char* e = getenv("GKCU_SORT_EXTENT")) c.sort_extent = (float)atof(e);

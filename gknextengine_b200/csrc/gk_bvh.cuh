@@ -47,6 +47,9 @@ static_assert(sizeof(Node8) == 128, "Node8 must be 128 bytes (one cache line)");
 #ifndef GK_N8_TMIN
 #define GK_N8_TMIN 1  // Node8 stack entries carry the entry distance of their nearest member (24 bits) and are culled as a whole when popped
 #endif
+#ifndef GK_FOLD_PAD
+#define GK_FOLD_PAD 0  // Node4 node step: the relative / absolute padding of the slab interval is folded into the per-ray constants (8 FMAs fewer per step)
+#endif
 #define GK_Q_MAX 2047.0f
 #define GK_LEAF_SLACK 8u
 
@@ -210,6 +213,19 @@ struct LocalStack {
     GK_DEV void put(int at, uint2 v) { e[at] = v; }
 };
 
+// The same stack with its top entry in registers: a pop hands out the register pair and requests the entry below it, whose load
+// latency is then hidden behind the node step that follows instead of sitting between the pop and its cull test
+// (8.6 % of k_trace's stall samples, profiles/r02_base_k_trace.txt). Element sp - 1 lives in `top`, elements 0 .. sp - 2 in e[].
+#ifndef GK_TOS_REG
+#define GK_TOS_REG 0
+#endif
+struct TosStack {
+    uint2 e[GK_TRAV_STACK];
+    uint2 top;
+    GK_DEV void push(int& sp, uint2 v) { if (sp > 0) e[sp - 1] = top; top = v; ++sp; }
+    GK_DEV uint2 pop(int& sp) { const uint2 r = top; --sp; if (sp > 0) top = e[sp - 1]; return r; }
+};
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Traversal state machine. One ray per lane; the same three steps serve the simple per-ray loop (trace_ray) and the
 // persistent-thread kernel (k_trace), which lets a warp run node steps together and leaf steps together and refills
@@ -219,6 +235,10 @@ struct Trav {
     float3 idir;       // current-space reciprocal direction
     float3 adjn, adjf; // Node4: slab offsets -ro * idir, lowered / raised by their own rounding error (see set_space)
     uint32_t sgn;      // bit a: idir[a] < 0, i.e. the near plane of axis a is the child's upper plane
+#if GK_FOLD_PAD
+    float3 idn, idf;   // Node4: idir scaled by the relative padding of the near / far side (see set_space)
+    float tminp;       // tmin with the near-side padding applied
+#endif
     float tmin, tmax;
     Hit best;
     RayShear sh;
@@ -247,6 +267,17 @@ struct Trav {
 // FMA result) is relative to t and covered by the relative padding in node_test. The slabs therefore never reject a box
 // that the exact ray enters, which is what makes the closest hit independent of the tree.
 // Node8 derives its offsets per node (the quantisation origin enters them), so only ro / idir / sgn are kept.
+#if GK_FOLD_PAD
+GK_DEV void fold_idir(Trav& T) {
+    T.idn = f3(T.idir.x * 0.999999f, T.idir.y * 0.999999f, T.idir.z * 0.999999f);
+    T.idf = f3(T.idir.x * 1.000001f, T.idir.y * 1.000001f, T.idir.z * 1.000001f);
+}
+GK_DEV void fold_pad(Trav& T) {
+    fold_idir(T);
+    T.adjn = f3(__fmaf_rn(T.adjn.x, 0.999999f, -1e-7f), __fmaf_rn(T.adjn.y, 0.999999f, -1e-7f), __fmaf_rn(T.adjn.z, 0.999999f, -1e-7f));
+    T.adjf = f3(__fmaf_rn(T.adjf.x, 1.000001f, 1e-7f), __fmaf_rn(T.adjf.y, 1.000001f, 1e-7f), __fmaf_rn(T.adjf.z, 1.000001f, 1e-7f));
+}
+#endif
 template <int FMT>
 GK_DEV void set_space(Trav& T, float3 ro, float3 idir) {
     T.ro = ro;
@@ -255,10 +286,18 @@ GK_DEV void set_space(Trav& T, float3 ro, float3 idir) {
         const float ax = -(ro.x * idir.x), ay = -(ro.y * idir.y), az = -(ro.z * idir.z);
         // + 1e-14 world units (|idir| * 1e-14 in t): a ray lying in a face plane of a box (direction component 0, origin on the
         // plane) is inside it, like in the CPU checker's slab test
-        const float ex = __fmaf_rn(fabsf(ax), 2.4e-7f, fabsf(idir.x) * 1e-14f), ey = __fmaf_rn(fabsf(ay), 2.4e-7f, fabsf(idir.y) * 1e-14f),
-                    ez = __fmaf_rn(fabsf(az), 2.4e-7f, fabsf(idir.z) * 1e-14f);
+        const float kUlps = GK_FOLD_PAD ? 3.6e-7f : 2.4e-7f;
+        const float ex = __fmaf_rn(fabsf(ax), kUlps, fabsf(idir.x) * 1e-14f), ey = __fmaf_rn(fabsf(ay), kUlps, fabsf(idir.y) * 1e-14f),
+                    ez = __fmaf_rn(fabsf(az), kUlps, fabsf(idir.z) * 1e-14f);
         T.adjn = f3(ax - ex, ay - ey, az - ez);
         T.adjf = f3(ax + ex, ay + ey, az + ez);
+#if GK_FOLD_PAD
+        // The node step pads the entry distance n = max(plane * idir + adjn) to n * 0.999999 - 1e-7 and the exit distance likewise
+        // upwards. Both are linear in n, so the factors move into the constants: plane * (idir * 0.999999) + (adjn * 0.999999 - 1e-7).
+        // The two extra roundings (of the scaled idir and of the scaled offset) are each half an ulp of a term bounded by |adj| + |t|;
+        // the 6-ulp lowering of |adj| above (3.6e-7 instead of the 4 ulps the unfolded form needs) and the 1e-6 relative padding cover them.
+        fold_pad(T);
+#endif
     }
     T.sgn = (idir.x < 0.0f ? 1u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 4u : 0u);
 }
@@ -270,6 +309,9 @@ GK_DEV void trav_init(Trav& T, W& world, const TraceScene& S, float3 o, float3 d
     set_space<FMT>(T, o, idir);
     if constexpr (W::kKeepsTlasSpace && FMT == 4) world.keep(T.adjn, T.adjf, T.sgn);
     T.tmin = tmin; T.tmax = tmax;
+#if GK_FOLD_PAD
+    T.tminp = __fmaf_rn(tmin, 0.999999f, -1e-7f);
+#endif
     T.best.t = tmax; T.best.u = 0.0f; T.best.v = 0.0f; T.best.inst = GK_NO_HIT; T.best.prim = 0;
     T.sh.kx = T.sh.ky = T.sh.kz = 0;
     T.sh.Sx = T.sh.Sy = T.sh.Sz = 0.0f;
@@ -297,6 +339,9 @@ GK_DEV void trav_pop(Trav& T, const W& world, const TraceScene& S, St& stack) {
         if (T.cur_inst != GK_NO_HIT && T.sp == T.sp_inst) {
             if constexpr (W::kKeepsTlasSpace && FMT == 4) {  // T.ro is not read in world space (Node4 slabs use adjn / adjf, triangles live in object space)
                 T.idir = world.widir(); T.adjn = world.adjn(); T.adjf = world.adjf(); T.sgn = world.sgn();
+#if GK_FOLD_PAD
+                fold_idir(T);  // the kept offsets are the folded ones
+#endif
             } else {
                 set_space<FMT>(T, world.o(), world.widir());
             }
@@ -366,6 +411,14 @@ GK_DEV bool trav_node_core4(Trav& T, St& stack) {
     float tn[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
+#if GK_FOLD_PAD
+        const float x0 = __fmaf_rn(pnx[c], T.idn.x, T.adjn.x), x1 = __fmaf_rn(pfx[c], T.idf.x, T.adjf.x);
+        const float y0 = __fmaf_rn(pny[c], T.idn.y, T.adjn.y), y1 = __fmaf_rn(pfy[c], T.idf.y, T.adjf.y);
+        const float z0 = __fmaf_rn(pnz[c], T.idn.z, T.adjn.z), z1 = __fmaf_rn(pfz[c], T.idf.z, T.adjf.z);
+        const float npad = fmaxf(fmaxf(x0, y0), fmaxf(z0, T.tminp));
+        const float fpad = fminf(fminf(x1, y1), z1);
+        const bool hit = (npad <= fpad) && (npad <= tfcap);  // an empty slot: npad = +inf, fpad = -inf
+#else
         const float x0 = __fmaf_rn(pnx[c], T.idir.x, T.adjn.x), x1 = __fmaf_rn(pfx[c], T.idir.x, T.adjf.x);
         const float y0 = __fmaf_rn(pny[c], T.idir.y, T.adjn.y), y1 = __fmaf_rn(pfy[c], T.idir.y, T.adjf.y);
         const float z0 = __fmaf_rn(pnz[c], T.idir.z, T.adjn.z), z1 = __fmaf_rn(pfz[c], T.idir.z, T.adjf.z);
@@ -374,6 +427,7 @@ GK_DEV bool trav_node_core4(Trav& T, St& stack) {
         const float npad = __fmaf_rn(n, 0.999999f, -1e-7f);
         // an empty slot has lo = +inf, hi = -inf: n = +inf, f = -inf, never a hit
         const bool hit = (npad <= __fmaf_rn(f, 1.000001f, 1e-7f)) && (npad <= tfcap);
+#endif
         tn[c] = hit ? npad : inf;
     }
     const uint32_t ref[4] = {n1.x, n1.y, n1.z, n1.w};
@@ -411,31 +465,36 @@ GK_DEV bool trav_node_core4(Trav& T, St& stack) {
 #endif
     // continue with the nearest child; the second nearest goes on top of the stack, the rest below it in slot order
     // (entries carry their entry distance, so a far one is culled when it is popped)
+    // The child references travel with the distances through the two searches (selects): indexing ref[] with i0 / i1 would put the array
+    // in local memory - a 16-byte store and two loads per node step and lane, a third of the kernel's L1 wavefronts, which are what
+    // bounds it (l1tex data pipe 77 % busy, profiles/r02_experiments.md section 9).
     int i0 = 0;
     float t0 = tn[0];
-    if (tn[1] < t0) { t0 = tn[1]; i0 = 1; }
-    if (tn[2] < t0) { t0 = tn[2]; i0 = 2; }
-    if (tn[3] < t0) { t0 = tn[3]; i0 = 3; }
+    uint32_t r0 = ref[0];
+    if (tn[1] < t0) { t0 = tn[1]; i0 = 1; r0 = ref[1]; }
+    if (tn[2] < t0) { t0 = tn[2]; i0 = 2; r0 = ref[2]; }
+    if (tn[3] < t0) { t0 = tn[3]; i0 = 3; r0 = ref[3]; }
     if (!(t0 < inf)) return false;
     if (GK_PUSH_ORDERED) {
         int i1 = -1;
         float t1 = inf;
+        uint32_t r1 = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            if (c != i0 && tn[c] < t1) { t1 = tn[c]; i1 = c; }
+            if (c != i0 && tn[c] < t1) { t1 = tn[c]; i1 = c; r1 = ref[c]; }
         if (i1 >= 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 if (c != i0 && c != i1 && tn[c] < inf) { GK_STAT(T, 3, 1); stack.push(T.sp, make_uint2(ref[c], __float_as_uint(tn[c]))); }
             GK_STAT(T, 3, 1);
-            stack.push(T.sp, make_uint2(ref[i1], __float_as_uint(t1)));
+            stack.push(T.sp, make_uint2(r1, __float_as_uint(t1)));
         }
     } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
             if (c != i0 && tn[c] < inf) stack.push(T.sp, make_uint2(ref[c], __float_as_uint(tn[c])));
     }
-    T.cur = ref[i0];
+    T.cur = r0;
     return true;
 }
 template <class W, class St>

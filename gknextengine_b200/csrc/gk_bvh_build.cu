@@ -545,11 +545,18 @@ __device__ __forceinline__ int sah_bin_of(float c, float lo, float hi) {
 }
 
 // slot_of[node] = active slot or -1
+// slot_of[] is either reset to -1 after every level (the multi-kernel build) or left as written (the fused build, which saves the
+// pass and its barrier): there an entry is valid only if the level's active list names the node at that slot.
+__device__ __forceinline__ int sah_slot_of(int node, const int* slot_of, const int* active, int nactive) {
+    int slot = slot_of[node];
+    if (active && (slot < 0 || slot >= nactive || active[slot] != node)) slot = -1;
+    return slot;
+}
 __device__ __forceinline__ void sah_bin_item(int i, int n, const uint32_t* order, const int* pos_node, const int* slot_of,
                           const float4* plo, const float4* phi, const float4* nlo,
-                          const float4* nhi, SahBin* bins) {
+                          const float4* nhi, SahBin* bins, const int* active = nullptr, int nactive = 0) {
     int node = pos_node[i];
-    int slot = slot_of[node];
+    int slot = sah_slot_of(node, slot_of, active, nactive);
     if (slot < 0) return;
     uint32_t p = order[i];
     float4 a = plo[p], b = phi[p], l = nlo[node], h = nhi[node];
@@ -574,7 +581,8 @@ __global__ void k_sah_bin(int n, const uint32_t* __restrict__ order, const int* 
 struct SahSplit { int axis, plane, nl, fallback; };
 
 __device__ __forceinline__ void sah_split_item(int s, int leaf_max, const int* nactive_ptr, const int* active, const SahBin* bins, float4* nlo, float4* nhi, int* left,
-                            int* right, int* first, int* count, int* counters, int* next_active, SahSplit* splits, int* cursors) {
+                            int* right, int* first, int* count, int* counters, int* next_active, SahSplit* splits, int* cursors, int* next_count = nullptr) {
+    if (!next_count) next_count = &counters[2];
     int node = active[s];
     int cnt = count[node];
     float bestCost = FLT_MAX;
@@ -643,8 +651,8 @@ __device__ __forceinline__ void sah_split_item(int s, int leaf_max, const int* n
     splits[s] = sp;
     cursors[2 * s] = 0;
     cursors[2 * s + 1] = 0;
-    if (sp.nl > leaf_max) next_active[atomicAdd(&counters[2], 1)] = c0;
-    if (cnt - sp.nl > leaf_max) next_active[atomicAdd(&counters[2], 1)] = c0 + 1;
+    if (sp.nl > leaf_max) next_active[atomicAdd(next_count, 1)] = c0;
+    if (cnt - sp.nl > leaf_max) next_active[atomicAdd(next_count, 1)] = c0 + 1;
 }
 __global__ void k_sah_split(int leaf_max, const int* __restrict__ nactive_ptr, const int* __restrict__ active, const SahBin* __restrict__ bins, float4* nlo, float4* nhi, int* left,
                             int* right, int* first, int* count, int* counters, int* next_active, SahSplit* splits, int* cursors) {
@@ -657,9 +665,9 @@ __device__ __forceinline__ void sah_partition_item(int i, int n, const uint32_t*
                                 const float4* plo, const float4* phi, const float4* nlo,
                                 const float4* nhi, const int* left, const int* first,
                                 const SahSplit* splits, int* cursors, uint32_t* order_out,
-                                int* pos_node_out) {
+                                int* pos_node_out, const int* active = nullptr, int nactive = 0) {
     int node = pos_node[i];
-    int slot = slot_of[node];
+    int slot = sah_slot_of(node, slot_of, active, nactive);
     uint32_t p = order[i];
     if (slot < 0 || splits[slot].axis == -2) {
         order_out[i] = p;
@@ -782,8 +790,23 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B)
     uint32_t *ord_a = B.ord_a, *ord_b = B.ord_b;
     int *pn_a = B.pn_a, *pn_b = B.pn_b, *act_a = B.act_a, *act_b = B.act_b;
     int* counters = B.counters;
+    auto clear_bins = [&](int nslots) {
+        for (int i = t; i < nslots * 3 * kSahBins; i += T) {
+            SahBin b;
+            b.lo[0] = b.lo[1] = b.lo[2] = 0x7FFFFFFF;
+            b.hi[0] = b.hi[1] = b.hi[2] = (int)0x80000000;
+            b.cnt = 0;
+            b.pad = 0;
+            B.bins[i] = b;
+        }
+    };
+    // Three barriers per level (bin | split | partition) instead of six: the open-node counts rotate through three words, so the count
+    // a level accumulates for its successor was zeroed a whole level earlier; slot_of[] is never reset (a stale entry fails the check
+    // against the level's active list, sah_slot_of); the partition phase also clears the bins and marks the slots of the next level.
+    // counters[1 + L % 3] = open nodes of level L.
     for (int i = t; i < n; i += T) { ord_a[i] = i; pn_a[i] = 0; }
-    for (int i = t; i < 2 * n + 2; i += T) B.slot_of[i] = -1;
+    for (int i = t; i < 2 * n + 2; i += T) B.slot_of[i] = i == 0 ? 0 : -1;
+    clear_bins(1);
     if (t == 0) {  // k_sah_init
         B.nlo[0] = f4(o2f(B.bounds[0]), o2f(B.bounds[1]), o2f(B.bounds[2]), 0);
         B.nhi[0] = f4(o2f(B.bounds[3]), o2f(B.bounds[4]), o2f(B.bounds[5]), 0);
@@ -794,21 +817,14 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B)
         counters[0] = 1;
         counters[1] = (n > B.leaf_max) ? 1 : 0;
         counters[2] = 0;
+        counters[3] = 0;
     }
     sync();
     for (int level = 0; level < 512; ++level) {
-        const int nactive = counters[1];
+        const int nactive = counters[1 + level % 3];
         if (nactive == 0) break;
-        for (int i = t; i < nactive; i += T) B.slot_of[act_a[i]] = i;
-        for (int i = t; i < nactive * 3 * kSahBins; i += T) {
-            SahBin b;
-            b.lo[0] = b.lo[1] = b.lo[2] = 0x7FFFFFFF;
-            b.hi[0] = b.hi[1] = b.hi[2] = (int)0x80000000;
-            b.cnt = 0;
-            b.pad = 0;
-            B.bins[i] = b;
-        }
-        sync();
+        int* next_count = counters + 1 + (level + 1) % 3;
+        if (t == 0) counters[1 + (level + 2) % 3] = 0;  // the count of level - 1: every thread read it before that level's barriers
         if (nactive <= kFusedSmemSlots) {
             // few open nodes, every box hits the same handful of bins: bin into a block-private copy in shared memory first and
             // merge once per block (the top levels of a 100 k build otherwise serialise ~2 M same-address atomics each)
@@ -821,7 +837,7 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B)
                 s_bins[i] = b;
             }
             __syncthreads();
-            for (int i = t; i < n; i += T) sah_bin_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, s_bins);
+            for (int i = t; i < n; i += T) sah_bin_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, s_bins, act_a, nactive);
             __syncthreads();
             for (int i = threadIdx.x; i < nactive * 3 * kSahBins; i += blockDim.x) {
                 const SahBin b = s_bins[i];
@@ -833,49 +849,54 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) k_build_fused(FusedBuild B)
                 }
             }
         } else {
-            for (int i = t; i < n; i += T) sah_bin_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, B.bins);
+            for (int i = t; i < n; i += T) sah_bin_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, B.bins, act_a, nactive);
         }
         sync();
         for (int sl = t; sl < nactive; sl += T)
-            sah_split_item(sl, B.leaf_max, counters + 1, act_a, B.bins, B.nlo, B.nhi, B.left, B.right, B.first, B.count, counters, act_b, B.splits, B.cursors);
+            sah_split_item(sl, B.leaf_max, counters + 1, act_a, B.bins, B.nlo, B.nhi, B.left, B.right, B.first, B.count, counters, act_b, B.splits, B.cursors, next_count);
         sync();
         for (int i = t; i < n; i += T)
-            sah_partition_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, B.left, B.first, B.splits, B.cursors, ord_b, pn_b);
-        sync();
-        for (int i = t; i < nactive; i += T) B.slot_of[act_a[i]] = -1;
-        sync();
-        if (t == 0) { counters[1] = counters[2]; counters[2] = 0; }
+            sah_partition_item(i, n, ord_a, pn_a, B.slot_of, B.plo, B.phi, B.nlo, B.nhi, B.left, B.first, B.splits, B.cursors, ord_b, pn_b, act_a, nactive);
+        {   // next level: its bins and slots (the children named in act_b are new nodes, no item of this phase looks them up)
+            const int nnext = *next_count;
+            clear_bins(nnext);
+            for (int i = t; i < nnext; i += T) B.slot_of[act_b[i]] = i;
+        }
         sync();
         uint32_t* to = ord_a; ord_a = ord_b; ord_b = to;
         int* tp = pn_a; pn_a = pn_b; pn_b = tp;
         int* ta = act_a; act_a = act_b; act_b = ta;
     }
-    // collapse to Node4, BFS; counters[8] node4 counter, [9] next-level queue size, [10] this level's queue size, [16 + L] level table
+    // collapse to Node4, BFS, one barrier per level; counters[8] node counter, counters[4 + L % 3] queue size of level L (rotating like the
+    // open-node counts), [10] what is left in the queue at the end (0 unless the tree is too deep), [11] levels run, [16 + L] level table:
+    // every queued item allocates exactly one node, so level L + 1 begins at the first node of level L plus the size of level L's queue.
     int2 *qa = B.qa, *qb = B.qb;
-    if (t == 0) { qa[0] = make_int2(0, 0); counters[8] = 1; counters[9] = 0; counters[10] = 1; counters[12] = (int)GK_LEAF_SLACK; counters[13] = counters[14] = counters[15] = 0; }  // 13-15: unused, published with the rest
+    if (t == 0) { qa[0] = make_int2(0, 0); counters[8] = 1; counters[4] = 1; counters[5] = 0; counters[6] = 0; counters[9] = 0; counters[10] = 0; counters[11] = 0; counters[12] = (int)GK_LEAF_SLACK; counters[13] = counters[14] = counters[15] = 0; }  // 13-15: unused, published with the rest
     for (int i = t; i < 48; i += T) counters[16 + i] = 0;
     sync();
-    for (int level = 0; level < 46; ++level) {
-        const int nin = counters[10];
+    int run = 1;  // nodes allocated before this level's items run = first node of the next level
+    int level = 0;
+    for (; level < 46; ++level) {
+        const int nin = counters[4 + level % 3];
+        if (level > 0) {
+            run += nin;
+            if (t == 0) { counters[16 + level + 1] = run; counters[11] = level; }
+        }
         if (nin == 0) break;
+        int* nout = counters + 4 + (level + 1) % 3;
+        if (t == 0) counters[4 + (level + 2) % 3] = 0;
         for (int i = t; i < nin; i += T) {
             if (B.w8.fmt == 8)
-                collapse_item8(i, qa, qb, counters + 9, counters + 8, counters + 12, B.nlo, B.nhi, B.left, B.right, B.first, B.count, B.leaf_max, ord_a, B.remap,
+                collapse_item8(i, qa, qb, nout, counters + 8, counters + 12, B.nlo, B.nhi, B.left, B.right, B.first, B.count, B.leaf_max, ord_a, B.remap,
                                B.remap ? 1 : 0, B.w8.tri_base_abs, reinterpret_cast<Node8*>(B.out), B.w8.leaf_out, B.out_lo, B.out_hi);
             else
-                collapse_item(i, qa, counters + 10, qb, counters + 9, counters + 8, B.nlo, B.nhi, B.left, B.right, B.first, B.count, B.leaf_max, ord_a, B.remap,
+                collapse_item(i, qa, nullptr, qb, nout, counters + 8, B.nlo, B.nhi, B.left, B.right, B.first, B.count, B.leaf_max, ord_a, B.remap,
                               B.remap ? 1 : 0, B.out, B.out_lo, B.out_hi);
-        }
-        sync();
-        if (t == 0) {
-            counters[16 + level + 2] = counters[8];
-            counters[10] = counters[9];
-            counters[9] = 0;
-            counters[11] = level + 1;  // levels run
         }
         sync();
         int2* tq = qa; qa = qb; qb = tq;
     }
+    if (t == 0 && level == 46) { counters[10] = counters[4 + level % 3]; counters[11] = 46; counters[16 + 47] = run + counters[4 + level % 3]; }
 }
 
 // ------------------------------------------------------------------------------------------- instances

@@ -106,6 +106,9 @@ struct Context {
     int use_tma = 1;        // GKCU_TMA=0 falls back to plain-load staging of the stencil tiles (2 / 3: only reproject / only denoise)
     int shade_minb = 7;     // GKCU_SHADE_MINB: 8 compiles k_shade for 8 blocks/SM (<= 64 registers)
     int trace_carveout = -1;  // k_trace shared-memory carve-out in percent (GKCU_TRACE_CARVEOUT), -1 = sized to the resident blocks
+    int trace_rpb = 128;      // GKCU_TRACE_RPB: rays per block the k_trace grid is sized for
+    int trace_grid_mult = 16; // GKCU_TRACE_GRID: k_trace grid cap in blocks per SM
+    int match_carveout = 0;   // GKCU_MATCH_CARVEOUT=1: k_primary / k_shade / k_tail ask for k_trace's shared-memory split (see run_rt_pass)
     int carveout_applied = 0; // trace_carveout + 2 once the function attribute has been set on this context's device
     int node_format = 4;      // GKCU_NODE_FORMAT: 4 = fp32 4-wide Node4 (default: 4.5 % faster on the bench frame, profiles/r02_experiments.md), 8 = quantised 8-wide Node8 (gk_bvh.cuh)
     int sort_rays = 0;      // GKCU_SORT_RAYS = bits per axis of the origin grid the rays of a wave are sorted on before k_trace (0 = queue order)
@@ -141,7 +144,7 @@ struct Context {
     int lanes = 1;
     cudaStream_t lane_stream[4] = {};
     cudaEvent_t lane_ev[4][4] = {};  // per lane: tail begin / end, done; [0][3]: primary done
-    int tail_div = 64;         // the wavefront hands over to k_tail once the wave is narrower than pixels / tail_div (GKCU_TAIL_DIV)
+    int tail_div = 32;         // the wavefront hands over to k_tail once the wave is narrower than pixels / tail_div (GKCU_TAIL_DIV); 32 since the loop has no host waits: rt pass 28.2 -> 27.3 ms against 64, profiles/r02_experiments.md section 10
     int wave_chunk = 6;        // how many waves the launches may run ahead of the queue sizes the host has read, 1..7 (GKCU_WAVE_CHUNK)
     cudaEvent_t ev[8] = {};
     uint64_t launches = 0;

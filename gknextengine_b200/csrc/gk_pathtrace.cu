@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(128, VARIANT == 5 ? GK_TRACE_MINB : 1) k_trace
     __shared__ float s_world[VARIANT == 5 ? 16 * 128 : 1];
     typename std::conditional<VARIANT == 5, WorldSmemX<128>, WorldRegs>::type world;
     if constexpr (VARIANT == 5) world.p = s_world + threadIdx.x;
-    LocalStack stack;
+    typename std::conditional<GK_TOS_REG && VARIANT == 5 && FMT == 4, TosStack, LocalStack>::type stack;
     Trav T;
     T.done = true;
     uint32_t slot = 0;
@@ -1280,6 +1280,14 @@ __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V,
     }
 }
 
+#ifndef GK_SHADE_PREFETCH
+#define GK_SHADE_PREFETCH 0
+#endif
+template <int LEVEL>
+GK_DEV void gk_prefetch(const void* p) {
+    if (LEVEL == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 // Shade: one thread per queue slot: consume the hit, advance the path to its next ray, compact the survivors into the other queue.
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters) {
@@ -1313,6 +1321,17 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
     uint32_t pixel = 0;
     PathRegs P;
     if (slot < n && in_cap) {
+#if GK_SHADE_PREFETCH
+        {   // The per-pixel records the end of a sample touches (two of three slots end one): requested now, they arrive while the hit is
+            // being resolved instead of costing a dependent HBM round trip each at the end of the chain. 1: into L2, 2: into L1.
+            const uint32_t px = sp & 0x7FFFFFFFu, fl = __float_as_uint(raw.o.w);
+            const float4* acc = (fl & FL_HIT_REFLECT) ? V.final_refl + px : V.final_color + px;
+            gk_prefetch<GK_SHADE_PREFETCH>(acc);
+            gk_prefetch<GK_SHADE_PREFETCH>(V.prim_nrm_cnt + px);
+            gk_prefetch<GK_SHADE_PREFETCH>(V.prim_pos_mat + px);
+            if (fl & FL_HIT_METAL) gk_prefetch<GK_SHADE_PREFETCH>(V.prim_albedo + px);
+        }
+#endif
         Hit h;
         h.t = hv.x; h.u = hv.y; h.v = hv.z; h.inst = __float_as_uint(hv.w); h.prim = hprim;
         load_slot(V, S, qi, slot, (sp & 0x80000000u) != 0, P, &raw);
@@ -1554,6 +1573,14 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                     p = std::min(100, (int)((GK_TRACE_MINB * (fa.sharedSizeBytes + 1024) * 100 + smem_sm - 1) / smem_sm));
             }
             if (p >= 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, p);
+            // An SM runs one shared-memory configuration at a time: a kernel with another carve-out cannot start on an SM while blocks
+            // of k_trace are resident. The other kernels of the rt pass ask for the same split (GKCU_MATCH_CARVEOUT), so that the blocks of
+            // a following (or, with several lanes, concurrent) kernel can move in while the last k_trace blocks drain.
+            if (p >= 0 && c.match_carveout && fmt == (c.node_format == 8 ? 1 : 0)) {
+                for (const void* g : {(const void*)k_shade<1>, (const void*)k_shade<6>, (const void*)k_shade<7>, (const void*)k_shade<8>, (const void*)k_shade<10>,
+                                      (const void*)k_tail, (const void*)k_primary})
+                    cudaFuncSetAttribute(g, cudaFuncAttributePreferredSharedMemoryCarveout, p);
+            }
         }
         c.carveout_applied = c.trace_carveout + 2;
     }
@@ -1675,7 +1702,10 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                         const uint32_t pb = std::min<uint32_t>((bound[l] + GK_POOL - 1) / GK_POOL, (uint32_t)c.sm_count * GK_POOL_MINB);
                         k_trace_pool<4><<<pb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, b.pool_stack.as<uint2>() + (size_t)l * b.pool_stack_stride, thr);
                     } else {
-                        const uint32_t tb = std::min<uint32_t>((bound[l] + 127) / 128, (uint32_t)c.sm_count * 16u);
+                        // rays per block the grid is sized for: with 128 every block of a wave that fits one residency round takes one
+                        // batch and only drains it; a multiple leaves rays in the queue for the refills (GKCU_TRACE_RPB)
+                        const uint32_t rpb = (uint32_t)c.trace_rpb;
+                        const uint32_t tb = std::max<uint32_t>(1u, std::min<uint32_t>((bound[l] + rpb - 1) / rpb, (uint32_t)c.sm_count * (uint32_t)c.trace_grid_mult));
                         if (c.node_format == 8) k_trace<5, 8><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below, thr);
                         else k_trace<5, 4><<<tb, 128, 0, s2>>>(S.ts, Vt, qi[l], half, c.refill_below, thr);
                     }
