@@ -536,16 +536,23 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
         # ---- end to end through the public API with host buffers (e2e)
         nodes_ptr, nn = scene.nodes()
         node_bytes = nn * C.sizeof(GkNodeProxy)
-        pinned_nodes = torch.empty(node_bytes, dtype=torch.uint8, pin_memory=True)
+        pinned_nodes2 = [torch.empty(node_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        pinned_nodes = pinned_nodes2[0]
         pinned_out = [torch.empty(WIDTH * HEIGHT * 8, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
         e2e_rays = 0
+
+        def prepare(step):
+            # the host side of a frame - Scene::UpdateNodes (Scene.cpp:410-492) and staging NodeProxy[] in pinned memory - runs while the
+            # GPU renders the frame before it, the way the engine's CPU frame overlaps its GPU frame
+            scene.update_nodes()
+            ptr, _ = scene.nodes()
+            C.memmove(pinned_nodes2[step & 1].data_ptr(), ptr, node_bytes)
+
         sync_all()
         t0 = time.perf_counter()
+        prepare(0)
         for _step in range(args.steps):
-            scene.update_nodes()  # Scene::UpdateNodes on the host (Scene.cpp:410-492)
-            nodes_ptr, nn = scene.nodes()
-            C.memmove(pinned_nodes.data_ptr(), nodes_ptr, node_bytes)
-            r.update_nodes_ptr(pinned_nodes.data_ptr(), nn)  # H2D NodeProxy[]
+            r.update_nodes_ptr(pinned_nodes2[_step & 1].data_ptr(), nn)  # H2D NodeProxy[]
             frame(tf)  # H2D UBO inside
             tf += 1
             if rank == 0:
@@ -557,7 +564,9 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
                     r.present_async(out_buf.data_ptr(), out_buf.numel())
                 else:
                     r.readback_into(RT["DENOISED"], out_buf.data_ptr(), out_buf.numel())
-            c = r.counters()
+            if _step + 1 < args.steps:
+                prepare(_step + 1)
+            c = r.counters()  # synchronises the stream: the frame is complete
             e2e_rays += c["primary_rays"] + c["closest_hit_rays"] + c["any_hit_rays"]
         if rank == 0:
             r.present_wait()

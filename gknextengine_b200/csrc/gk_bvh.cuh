@@ -647,6 +647,40 @@ GK_DEV void trace_ray_fmt(const TraceScene& S, float3 o, float3 d, float tmin, f
     }
     best = T.best;
 }
+// The same query for a whole warp: every lane of the warp calls it together (lanes without a ray pass active = false), and each
+// iteration the warp executes only the step kind most of its rays wait for - node walk, instance entry or triangle leaf - like
+// k_trace does, instead of serialising the three code paths whenever the lanes disagree. Per ray the sequence of steps is that of
+// trace_ray_fmt, so the result is the same bits. Used by k_tail, where every thread runs a whole path and the rays of a warp
+// are traced in lockstep anyway.
+template <int FMT>
+GK_DEV void trace_ray_warp_fmt(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, bool any, bool active, Hit& best) {
+    LocalStack stack;
+    Trav T;
+    WorldRegs world;
+    trav_init<FMT>(T, world, S, o, d, tmin, tmax, any);
+    if (!active) T.done = true;
+    for (;;) {
+        const bool live = !T.done;
+        const bool leaf = (T.cur & GK_LEAF_BIT) != 0;
+        const bool wN = live && !leaf;
+        const bool wI = live && leaf && T.cur_inst == GK_NO_HIT;
+        const bool wT = live && leaf && T.cur_inst != GK_NO_HIT;
+        const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nI = __popc(__ballot_sync(0xffffffffu, wI)), nT = __popc(__ballot_sync(0xffffffffu, wT));
+        if (nN + nI + nT == 0) break;
+        if (nN >= nT && nN >= nI) {
+            if (wN) trav_node_step<FMT>(T, world, S, stack);
+        } else if (nT >= nI) {
+            if (wT) trav_leaf_step<FMT>(T, world, S, stack);
+        } else {
+            if (wI) trav_leaf_step<FMT>(T, world, S, stack);
+        }
+    }
+    best = T.best;
+}
+GK_DEV void trace_ray_warp(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, bool any, bool active, Hit& best) {
+    if (S.fmt == 8) trace_ray_warp_fmt<8>(S, o, d, tmin, tmax, any, active, best);
+    else trace_ray_warp_fmt<4>(S, o, d, tmin, tmax, any, active, best);
+}
 // The kernels off the hot path pick the format at run time (both loops are compiled in); k_trace is instantiated per format.
 template <bool ANY>
 GK_DEV void trace_ray(const TraceScene& S, float3 o, float3 d, float tmin, float tmax, Hit& best) {

@@ -1351,6 +1351,9 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
     }
 }
 
+#ifndef GK_TAIL_VOTE
+#define GK_TAIL_VOTE 0
+#endif
 // Tail / megakernel: every thread runs its pixel's program to completion with the traversal inlined.
 __global__ void __launch_bounds__(128) k_tail(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters, int after_wavefront) {
     SceneView S = S_;
@@ -1360,6 +1363,27 @@ __global__ void __launch_bounds__(128) k_tail(SceneView S_, const __grid_constan
     PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
     const size_t half = (size_t)R.w * R.h;
     uint32_t nclosest = 0, nany = 0;
+#if GK_TAIL_VOTE
+    // The rays of a warp are traced together (trace_ray_warp: the warp votes on the step kind), then the lanes that had one shade together.
+    // The trip counts are warp-uniform; a lane without a slot or with a finished path just sits the calls out.
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; __any_sync(0xffffffffu, slot < n); slot += gridDim.x * blockDim.x) {
+        const bool have = slot < n;
+        uint32_t sp = have ? V.slot_pixel[qi][slot] : 0u;
+        uint32_t pixel = sp & 0x7FFFFFFFu;
+        PathRegs P;
+        if (have) load_slot(V, S, qi, slot, (sp & 0x80000000u) != 0, P);
+        else { P.ro = f3(0, 0, 0); P.rd = f3(0, 0, 1); }
+        int req = !have ? REQ_DONE : ((sp & 0x80000000u) ? REQ_ANY : REQ_CLOSEST);
+        while (__any_sync(0xffffffffu, req != REQ_DONE)) {
+            Hit h;
+            trace_ray_warp(S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, req == REQ_ANY, req != REQ_DONE, h);
+            if (req != REQ_DONE) {
+                if (req == REQ_ANY) nany++; else nclosest++;
+                req = advance(S, O, cfg, V, pixel, P, h);
+            }
+        }
+    }
+#else
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
         uint32_t sp = V.slot_pixel[qi][slot];
         uint32_t pixel = sp & 0x7FFFFFFFu;
@@ -1373,6 +1397,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneView S_, const __grid_constan
             req = advance(S, O, cfg, V, pixel, P, h);
         }
     }
+#endif
     for (int o = 16; o > 0; o >>= 1) {
         nclosest += __shfl_xor_sync(0xffffffffu, nclosest, o);
         nany += __shfl_xor_sync(0xffffffffu, nany, o);
