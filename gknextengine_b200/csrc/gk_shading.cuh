@@ -80,6 +80,13 @@ GK_DEV VtxLite unpack_vertex(const SceneView& S, uint32_t vi) {  // UnpackVertex
 }
 GK_DEV uint32_t fetch_material_id(const GkNodeProxy* node, uint32_t slot) { return slot < 16 ? node->matId[slot] : 0; }  // :370-424
 
+// v mod n in [0, n) (repeat addressing). Coordinates within one tile of the image - every sky lookup, most uv sets - take two
+// compares instead of the integer division sequence (4 % of k_shade's instructions went into the four `%` of a bilinear fetch).
+GK_DEV int wrap_texel(int v, int n) {
+    if ((unsigned)(v + n) < 3u * (unsigned)n) return v < 0 ? v + n : (v >= n ? v - n : v);
+    const int r = v % n;
+    return r < 0 ? r + n : r;
+}
 // Sampler2D.SampleLevel(uv, 0): linear, repeat (src/Vulkan/Sampler.hpp:9-26), full-precision weights
 GK_DEV float4 sample_texture(const SceneView& S, uint32_t id, float2 uv) {
     if (id >= S.tex_count) return f4(0, 0, 0, 0);
@@ -89,10 +96,8 @@ GK_DEV float4 sample_texture(const SceneView& S, uint32_t id, float2 uv) {
     float fx = floorf(x), fy = floorf(y);
     float ax = x - fx, ay = y - fy;
     int x0 = (int)fx, y0 = (int)fy;
-    int xa = x0 % (int)tx.w; if (xa < 0) xa += tx.w;
-    int xb = (x0 + 1) % (int)tx.w; if (xb < 0) xb += tx.w;
-    int ya = y0 % (int)tx.h; if (ya < 0) ya += tx.h;
-    int yb = (y0 + 1) % (int)tx.h; if (yb < 0) yb += tx.h;
+    const int xa = wrap_texel(x0, (int)tx.w), xb = wrap_texel(x0 + 1, (int)tx.w);
+    const int ya = wrap_texel(y0, (int)tx.h), yb = wrap_texel(y0 + 1, (int)tx.h);
     float4 t00 = __ldg(tx.texels + (size_t)ya * tx.w + xa), t10 = __ldg(tx.texels + (size_t)ya * tx.w + xb);
     float4 t01 = __ldg(tx.texels + (size_t)yb * tx.w + xa), t11 = __ldg(tx.texels + (size_t)yb * tx.w + xb);
     return lerp4(lerp4(t00, t10, ax), lerp4(t01, t11, ax), ay);
