@@ -132,6 +132,8 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     if (const char* e = getenv("GKCU_TMA")) c.use_tma = atoi(e);
     if (const char* e = getenv("GKCU_FAST_STENCIL")) c.fast_stencil = atoi(e) != 0;
     if (const char* e = getenv("GKCU_SHADE_MINB")) c.shade_minb = atoi(e);
+    if (const char* e = getenv("GKCU_TLAS_REFIT")) c.tlas_refit = atoi(e) != 0;
+    if (const char* e = getenv("GKCU_TLAS_REBUILD_EVERY")) c.tlas_rebuild_every = std::max(0, atoi(e));
     if (const char* e = getenv("GKCU_TRACE_RPB")) c.trace_rpb = std::max(32, std::min(65536, atoi(e)));
     if (const char* e = getenv("GKCU_TRACE_GRID")) c.trace_grid_mult = std::max(1, std::min(64, atoi(e)));
     if (const char* e = getenv("GKCU_MATCH_CARVEOUT")) c.match_carveout = atoi(e) != 0;
@@ -180,7 +182,7 @@ int gkcu_destroy(GkcuContext* ctx) {
         if (t.texels) cudaFree(t.texels);
     DevBuf* bufs[] = {&c.vertices, &c.simple, &c.indices, &c.offsets, &c.materials, &c.nodes, &c.blas_nodes, &c.blas_node_lo, &c.blas_node_hi,
                       &c.blas_tris, &c.blas_tri_prim, &c.blas_table, &c.shade_tris, &c.shade_inst, &c.tlas_nodes, &c.tlas_node_lo, &c.tlas_node_hi, &c.blas_leaf, &c.tlas_leaf, &c.raster_indices, &c.reorders, &c.draw_cmds, &c.gpu_stats, &c.vis_keys, &c.raster_large, &c.raster_counters, &c.instances, &c.inst_lo,
-                      &c.inst_hi, &c.tlas_active_ids, &c.inst_flags, &c.select_tmp, &c.select_count, &c.node_stage, &c.node_stage_idx, &c.tex_table, &c.probes, &c.probe_meta, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
+                      &c.inst_hi, &c.tlas_active_ids, &c.inst_flags, &c.inst_flags_prev, &c.select_tmp, &c.select_count, &c.node_stage, &c.node_stage_idx, &c.tex_table, &c.probes, &c.probe_meta, &c.pages, &c.cube_snapshot, &c.lights, &c.sky_sh, &c.ubo, &c.trace_rays, &c.trace_hits,
                       &c.peer_flags};
     for (DevBuf* b : bufs) b->release();
     BuildScratch& s = c.scratch;
@@ -259,6 +261,7 @@ int gkcu_scene_upload(GkcuContext* ctx, const GkcuSceneDesc* d) {
     cudaStream_t st = c.stream;
     c.raster_index_count = c.reorder_count = 0;  // the raster-side buffers belong to the previous scene
     c.blas_built = false;  // from here on the old acceleration structures no longer describe the buffers
+    c.tlas_topo_valid = false;
     c.tlas_dirty = true;
     c.tlas.node_count = 0;
     if (!c.vertices.reserve((size_t)d->vertex_count * sizeof(GkGPUVertex)) || !c.simple.reserve((size_t)d->vertex_count * 8) ||
@@ -808,6 +811,19 @@ int gkcu_debug_info(GkcuContext* ctx, uint32_t* out, uint32_t capacity) {
     return 0;
 }
 
+int gkcu_set_tlas_refit(GkcuContext* ctx, uint32_t enabled, uint32_t rebuild_every) {
+    CTX_OR_FAIL(ctx);
+    c.tlas_refit = enabled ? 1 : 0;
+    c.tlas_rebuild_every = (int)std::min<uint32_t>(rebuild_every, 1u << 30);
+    if (!enabled) c.tlas_topo_valid = false;
+    return 0;
+}
+int gkcu_tlas_stats(GkcuContext* ctx, uint64_t* builds, uint64_t* refits) {
+    CTX_OR_FAIL(ctx);
+    if (builds) *builds = c.tlas_builds;
+    if (refits) *refits = c.tlas_refits;
+    return 0;
+}
 int gkcu_set_skip_unchanged_nodes(GkcuContext* ctx, uint32_t enabled) {
     CTX_OR_FAIL(ctx);
     c.skip_unchanged_nodes = enabled ? 1 : 0;

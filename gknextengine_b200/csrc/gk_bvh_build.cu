@@ -983,6 +983,64 @@ __global__ void k_gather_boxes(const uint32_t* __restrict__ ids, uint32_t m, con
     out_hi[i] = hi[ids[i]];
 }
 
+constexpr float kRefitCostLimit = 1.3f;  // rebuild once the refitted tree's node areas have grown by 30 %
+// ------------------------------------------------------------------------------------------- TLAS refit
+// Keeps the topology of the last full build and recomputes every box from this frame's instance boxes, bottom-up over the BFS levels in one
+// single-block launch (a few hundred to a few ten thousand nodes; __syncthreads() between the levels). The closest hit does not depend on the
+// tree (gk_bvh.cuh), so a refitted TLAS gives the same bits as a rebuilt one; what it can lose is traversal speed when instances have moved far,
+// which is why the sum of the node areas comes back with it: build_tlas_impl rebuilds when it has grown past kRefitCostLimit x the value of
+// the fresh tree, when the set of active instances has changed, or every GKCU_TLAS_REBUILD_EVERY frames.
+struct TlasRefitArgs {
+    Node4* nodes;
+    float4 *node_lo, *node_hi;
+    const float4 *inst_lo, *inst_hi;
+    float* cost;
+    int levels;
+    uint32_t level_start[49];
+};
+__global__ void __launch_bounds__(1024) k_tlas_refit(const __grid_constant__ TlasRefitArgs A) {
+    float area = 0.0f;
+    for (int L = A.levels - 1; L >= 0; --L) {
+        for (uint32_t i = A.level_start[L] + threadIdx.x; i < A.level_start[L + 1]; i += blockDim.x) {
+            const uint4 refs = *(reinterpret_cast<const uint4*>(A.nodes + i) + 6);
+            const uint32_t child[4] = {refs.x, refs.y, refs.z, refs.w};
+            const int nk = (int)A.nodes[i].n;
+            ChildBox ch[4];
+            float3 nlo = f3(FLT_MAX, FLT_MAX, FLT_MAX), nhi = f3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+            for (int k = 0; k < nk; ++k) {
+                const uint32_t ref = child[k];
+                float4 l, h;
+                if (ref & GK_LEAF_BIT) { l = A.inst_lo[ref & 0x0FFFFFFFu]; h = A.inst_hi[ref & 0x0FFFFFFFu]; }  // a TLAS leaf is one instance
+                else { l = A.node_lo[ref]; h = A.node_hi[ref]; }
+                ch[k].lo = f3(l.x, l.y, l.z); ch[k].hi = f3(h.x, h.y, h.z); ch[k].ref = ref;
+                nlo = f3(fminf(nlo.x, l.x), fminf(nlo.y, l.y), fminf(nlo.z, l.z));
+                nhi = f3(fmaxf(nhi.x, h.x), fmaxf(nhi.y, h.y), fmaxf(nhi.z, h.z));
+            }
+            write_node4(A.nodes + i, nk, ch);
+            A.node_lo[i] = f4(nlo.x, nlo.y, nlo.z, 0);
+            A.node_hi[i] = f4(nhi.x, nhi.y, nhi.z, 0);
+            area += box_area(f4(nlo.x, nlo.y, nlo.z, 0), f4(nhi.x, nhi.y, nhi.z, 0));
+        }
+        __syncthreads();
+    }
+    __shared__ float s_area[32];
+    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+    if ((threadIdx.x & 31) == 0) s_area[threadIdx.x >> 5] = area;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float a = threadIdx.x < (blockDim.x >> 5) ? s_area[threadIdx.x] : 0.0f;
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (threadIdx.x == 0) *A.cost = a;
+    }
+}
+// did the set of active instances change since the topology was built? (also keeps the new flags for the next comparison)
+__global__ void k_flags_changed(const uint8_t* __restrict__ flags, uint8_t* __restrict__ prev, uint32_t n, uint32_t* changed) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t f = flags[i];
+    if (f != prev[i]) { *changed = 1u; prev[i] = f; }
+}
+
 inline dim3 grid_for(size_t n, int block = 256) { return dim3((unsigned)((n + block - 1) / block)); }
 
 struct Bvh2 {
@@ -1355,6 +1413,7 @@ int build_tlas(Context& c) {
 static int build_tlas_impl(Context& c) {
     cudaStream_t st = c.stream;
     uint32_t n = c.node_count;
+    const uint32_t kept_nodes = c.tlas.node_count;
     c.tlas.node_count = 0;
     c.tlas_dirty = false;
     if (n == 0 || !c.blas_built) return 0;
@@ -1372,6 +1431,41 @@ static int build_tlas_impl(Context& c) {
     k_instances<<<grid_for(n, 128), 128, 0, st>>>(c.nodes.as<GkNodeProxy>(), n, c.blas_table.as<uint4>(), c.model_count, c.instances.as<InstanceRec>(),
                                              c.inst_lo.as<float4>(), c.inst_hi.as<float4>(), c.shade_inst.as<uint4>(), c.inst_flags.as<uint8_t>());
     c.launches += 1;
+    const char* tb = getenv("GKCU_TLAS_BUILDER");
+    const bool lbvh = tb && std::string(tb) == "lbvh";
+    if (!c.inst_flags_prev.reserve(n)) return 1;
+    if (c.tlas_refit && c.node_format == 4 && !lbvh && c.tlas_topo_valid && c.tlas_topo_n == n && kept_nodes > 0 && c.tlas.level_start.size() >= 2 &&
+        c.tlas.level_start.size() <= 49) {
+        // Refit first and ask afterwards: the refit and the question "is the topology still the right one" go to the device together and the
+        // host waits once. When the answer is no, the refit has only touched a tree that is rebuilt below.
+        uint32_t* words = c.select_count.as<uint32_t>();
+        GK_CUDA(cudaMemsetAsync(words + 1, 0, 8, st));
+        k_flags_changed<<<grid_for(n), 256, 0, st>>>(c.inst_flags.as<uint8_t>(), c.inst_flags_prev.as<uint8_t>(), n, words + 1);
+        TlasRefitArgs A;
+        A.nodes = c.tlas_nodes.as<Node4>(); A.node_lo = c.tlas_node_lo.as<float4>(); A.node_hi = c.tlas_node_hi.as<float4>();
+        A.inst_lo = c.inst_lo.as<float4>(); A.inst_hi = c.inst_hi.as<float4>();
+        A.cost = reinterpret_cast<float*>(words + 2);
+        A.levels = (int)c.tlas.level_start.size() - 1;
+        for (size_t k = 0; k < c.tlas.level_start.size(); ++k) A.level_start[k] = c.tlas.level_start[k];
+        k_tlas_refit<<<1, 1024, 0, st>>>(A);
+        c.launches += 2;
+        if (publish_words(c, words + 1, 1, 2, st)) return 1;
+        GK_CUDA(cudaStreamSynchronize(st));
+        GK_CUDA(cudaGetLastError());
+        const bool changed = c.pub_host[1] != 0;
+        float cost = 0.0f;
+        memcpy(&cost, c.pub_host + 2, 4);
+        if (c.tlas_built_cost < 0.0f) c.tlas_built_cost = cost;  // first refit of a fresh tree: its boxes are the builder's
+        const bool degraded = !(cost <= c.tlas_built_cost * kRefitCostLimit);
+        const bool periodic = c.tlas_rebuild_every > 0 && c.tlas_frames_since_build + 1 >= (uint32_t)c.tlas_rebuild_every;
+        if (!changed && !degraded && !periodic) {
+            c.tlas.node_count = kept_nodes;
+            c.tlas_frames_since_build++;
+            c.tlas_refits++;
+            return 0;
+        }
+    }
+    c.tlas_topo_valid = false;
     {   // the instances with a non-zero mask, in index order (stable compaction), and how many there are
         thrust::counting_iterator<uint32_t> iota(0u);
         size_t tmp = 0;
@@ -1394,9 +1488,8 @@ static int build_tlas_impl(Context& c) {
                                                s.prim_lo.as<float4>(), s.prim_hi.as<float4>());
     c.launches += 1;
     Bvh2 b2;
-    const char* tb = getenv("GKCU_TLAS_BUILDER");
     const uint32_t fused_max = getenv("GKCU_TLAS_FUSED_MAX") ? (uint32_t)atoi(getenv("GKCU_TLAS_FUSED_MAX")) : 262144u;
-    if (tb && std::string(tb) == "lbvh") {
+    if (lbvh) {
         if (build_lbvh(c, m, m, b2)) return 1;
         if (collapse(c, b2, m, 1, c.tlas_active_ids.as<uint32_t>(), c.tlas_nodes.as<Node4>(), c.tlas_node_lo.as<float4>(), c.tlas_node_hi.as<float4>(), c.tlas, w8)) return 1;
     } else if (m <= fused_max) {
@@ -1419,6 +1512,13 @@ static int build_tlas_impl(Context& c) {
         c.tlas.node_count = 0;
         return 1;
     }
+    // this topology serves the following frames for as long as the same instances are active (refit above)
+    GK_CUDA(cudaMemcpyAsync(c.inst_flags_prev.p, c.inst_flags.p, n, cudaMemcpyDeviceToDevice, st));
+    c.tlas_topo_valid = true;
+    c.tlas_topo_n = n;
+    c.tlas_built_cost = -1.0f;
+    c.tlas_frames_since_build = 0;
+    c.tlas_builds++;
     return 0;
 }
 

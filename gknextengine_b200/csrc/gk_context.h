@@ -96,6 +96,16 @@ struct Context {
     DevBuf node_stage, node_stage_idx;            // gkcu_update_nodes_sparse staging
     WideBvhInfo tlas;
     bool tlas_dirty = true;
+    // Per-frame TLAS update: refit the topology of the last full build while the same instances are active, rebuild when the set changes, when
+    // the refitted tree has degraded (node areas + 30 %) or every tlas_rebuild_every frames (0 = never by count). gkcu_set_tlas_refit /
+    // GKCU_TLAS_REFIT=0 rebuilds every frame like the reference's vkCmdBuildAccelerationStructures call (RayTraceBaseRenderer.cpp:205-218).
+    int tlas_refit = 1;
+    int tlas_rebuild_every = 0;
+    bool tlas_topo_valid = false;
+    uint32_t tlas_topo_n = 0, tlas_frames_since_build = 0;
+    float tlas_built_cost = -1.0f;
+    uint64_t tlas_builds = 0, tlas_refits = 0;
+    DevBuf inst_flags_prev;
     int skip_unchanged_nodes = 0;        // gkcu_set_skip_unchanged_nodes: gkcu_update_nodes keeps the TLAS when the proxies are byte-identical
     std::vector<uint8_t> nodes_shadow;   // host copy of the last full NodeProxy[] upload (only kept while the option is on)
     bool frame_built_tlas = false;

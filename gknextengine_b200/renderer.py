@@ -83,6 +83,8 @@ def lib():
         L.gkcu_set_kernel_timing.argtypes = [P, C.c_uint32]
         L.gkcu_set_fast_stencil.argtypes = [P, C.c_uint32]
         L.gkcu_set_skip_unchanged_nodes.argtypes = [P, C.c_uint32]
+        L.gkcu_set_tlas_refit.argtypes = [P, C.c_uint32, C.c_uint32]
+        L.gkcu_tlas_stats.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.gkcu_stream.restype = C.c_uint64
         L.gkcu_stream.argtypes = [P]
         L.gkcu_trace_rays.argtypes = [P, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
@@ -303,6 +305,14 @@ class CudaPathTracingRenderer:
         c = GkcuCounters()
         _ck(lib().gkcu_get_counters(self._ctx, C.byref(c)))
         return {n: getattr(c, n) for n, _ in GkcuCounters._fields_}
+
+    def set_tlas_refit(self, enabled, rebuild_every=0):
+        _ck(lib().gkcu_set_tlas_refit(self._ctx, int(bool(enabled)), int(rebuild_every)))
+
+    def tlas_stats(self):
+        b, r = C.c_uint64(0), C.c_uint64(0)
+        _ck(lib().gkcu_tlas_stats(self._ctx, C.byref(b), C.byref(r)))
+        return {"builds": b.value, "refits": r.value}
 
     def set_skip_unchanged_nodes(self, enabled):
         _ck(lib().gkcu_set_skip_unchanged_nodes(self._ctx, int(bool(enabled))))

@@ -1,12 +1,13 @@
-"""Renders a few frames of the bench workload (for ncu): python scripts/profile_frame.py [frames] [tracer]"""
+"""Renders a few frames of the bench workload (for ncu): python scripts/profile_frame.py [frames] [tracer] [spp]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gknextengine_b200 import CudaPathTracingRenderer, GkcuFrameParams, host
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 tracer = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+spp = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 W, H = 1920, 1080
-scene = host.Scene("RTIO.proc", samples=16, bounces=8, taa=True, temporal_frames=16, denoiser=True)
+scene = host.Scene("RTIO.proc", samples=spp, bounces=8, taa=True, temporal_frames=16, denoiser=True)
 scene.update_nodes()
 r = CudaPathTracingRenderer(0)
 r.CreateSwapChain((W, H))

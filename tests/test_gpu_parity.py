@@ -495,6 +495,66 @@ def test_blas_refit_and_dynamic_tlas(renderer):
     assert t["blas_refit_ms"] > 0 and t["tlas_update_ms"] > 0
 
 
+def test_tlas_refit_equals_rebuild_and_rebuilds_when_the_active_set_changes(renderer):
+    """gkcu_set_tlas_refit (default on): while the same instances are active the per-frame TLAS update refits the last full build; hits stay
+    bit-equal to the oracle's (which builds its own tree), the refitted tree is a valid BVH, and a change of the active set, the option being
+    switched off or the rebuild interval bring the full build back."""
+    import ctypes as C
+    from gknextengine_b200._abi import GkNodeProxy
+    scene = host.Scene("LegoBricks.synth:3000")
+    scene.update_nodes()
+    osc, _ = setup_pair(renderer, scene, 64, 64)
+    renderer.set_tlas_refit(True, 0)
+    rays = random_rays(30000, seed=11, center=(0, 1.5, 0), spread=8.0)
+    rays["dy"] = -np.abs(rays["dy"])
+
+    def check():
+        hg, hc = renderer.trace(rays), osc.trace(rays)
+        assert np.array_equal(hg["inst"], hc["inst"]) and np.array_equal(hg["prim"], hc["prim"])
+        assert np.array_equal(hg["t"].view(np.uint32), hc["t"].view(np.uint32))
+        assert validate(renderer)["tlas"]["all_instances_once"]
+
+    renderer.AfterUpdateScene(scene)
+    renderer.PreRender()  # full build of this scene
+    s0 = renderer.tlas_stats()
+    for step in range(1, 5):
+        scene.jitter_instances(step, 0.05)
+        scene.update_nodes()
+        renderer.AfterUpdateScene(scene)
+        osc.update_nodes(scene)
+        renderer.PreRender()
+        check()
+    s1 = renderer.tlas_stats()
+    assert s1["refits"] - s0["refits"] == 4 and s1["builds"] == s0["builds"]
+    # an instance leaves the TLAS: the topology no longer fits, full build
+    nodes, n = scene.nodes()
+    arr = (GkNodeProxy * n)(*[nodes[i] for i in range(n)])
+    arr[5].visible = 0
+    renderer.update_nodes_ptr(C.addressof(arr), n)
+    osc.L.gko_update_nodes(osc._h, arr, n)
+    renderer.PreRender()
+    check()
+    s2 = renderer.tlas_stats()
+    assert s2["builds"] == s1["builds"] + 1 and s2["refits"] == s1["refits"]
+    # rebuild interval
+    renderer.set_tlas_refit(True, 2)
+    for _ in range(4):
+        renderer.update_nodes_ptr(C.addressof(arr), n)
+        renderer.PreRender()
+    s3 = renderer.tlas_stats()
+    assert s3["builds"] - s2["builds"] == 2 and s3["refits"] - s2["refits"] == 2
+    check()
+    # off: every frame builds, like the reference
+    renderer.set_tlas_refit(False, 0)
+    for _ in range(2):
+        renderer.update_nodes_ptr(C.addressof(arr), n)
+        renderer.PreRender()
+    s4 = renderer.tlas_stats()
+    assert s4["builds"] - s3["builds"] == 2 and s4["refits"] == s3["refits"]
+    check()
+    renderer.set_tlas_refit(True, 0)
+
+
 def test_skip_unchanged_nodes_keeps_the_tlas_and_the_images(renderer):
     """gkcu_set_skip_unchanged_nodes: a byte-identical NodeProxy[] neither crosses the bus nor rebuilds the TLAS; a moved instance does."""
     scene = host.Scene("LegoBricks.synth:2000")
