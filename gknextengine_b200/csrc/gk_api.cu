@@ -159,6 +159,15 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
     // lane streams only when the frame is split into lanes: every stream takes one of the device's hardware queues (8 by default), and two
     // streams that share a queue serialise - fatal for kernels that wait for a kernel of another context (the multi-GPU device barrier)
     for (int l = 0; l < 4 && c.lanes > 1; ++l) cudaStreamCreateWithFlags(&c.lane_stream[l], cudaStreamNonBlocking);
+    if (const char* e = getenv("GKCU_TAIL_SEGMENTS")) {
+        c.tail_segments = 0;
+        for (const char* q = e; *q && c.tail_segments < 14;) {
+            const int v = atoi(q);
+            if (v > 0) c.tail_segment_rays[c.tail_segments++] = v;
+            while (*q && *q != ',' && *q != ':') ++q;
+            if (*q) ++q;
+        }
+    }
     if (const char* e = getenv("GKCU_TAIL_DIV")) c.tail_div = std::max(1, std::min(65536, atoi(e)));
     if (const char* e = getenv("GKCU_WAVE_CHUNK")) c.wave_chunk = std::max(1, std::min(7, atoi(e)));
     if (!c.ubo.reserve(sizeof(GkUniformBufferObject))) { delete ctx; return 1; }

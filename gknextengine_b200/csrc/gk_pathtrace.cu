@@ -1283,6 +1283,9 @@ __global__ void __launch_bounds__(128) k_trace_simple(TraceScene ts, PathView V,
 #ifndef GK_SHADE_PREFETCH
 #define GK_SHADE_PREFETCH 0
 #endif
+#ifndef GK_SHADE_GROUP
+#define GK_SHADE_GROUP 0
+#endif
 template <int LEVEL>
 GK_DEV void gk_prefetch(const void* p) {
     if (LEVEL == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -1296,7 +1299,53 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
     // The slot's records are requested BEFORE the queue size: every block used to start by waiting a full memory round trip for the 16-byte
     // header (13 % of the kernel's stall samples, profiles/r02_experiments.md) and only then issue its loads. The grid never exceeds the
     // queue's capacity, so a slot beyond the current size is allocated memory with stale contents that are simply not used.
+#if GK_SHADE_GROUP
+    // The 128 slots of the block are dealt to its threads misses first, hits after (a stable partition on the hit record's instance word):
+    // a warp then runs either the sky lookup or the hit resolve + material fetch instead of both (two thirds of the bench frame's slots are
+    // misses, so nearly every warp of the slot-ordered kernel executes both paths). The block's records are the same cache lines whichever
+    // thread reads them; they are requested (prefetch into L1) before the partition, whose key needs the hit record's round trip.
+    const uint32_t slot0 = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t slot = slot0;
+    {
+        __shared__ uint16_t s_perm[128];
+        __shared__ uint32_t s_cnt[2][4];
+        const bool cap0 = slot0 < (uint32_t)V.pixels;
+        uint32_t inst0 = GK_NO_HIT;
+        if (cap0) {
+            const size_t i0 = (size_t)qi * V.pixels + slot0;
+            gk_prefetch<2>(V.slot_pixel[qi] + slot0); gk_prefetch<2>(V.hit_prim + slot0);
+            gk_prefetch<2>(V.ray_o + i0); gk_prefetch<2>(V.ray_d + i0); gk_prefetch<2>(V.rng + i0); gk_prefetch<2>(V.ray_color + i0);
+            inst0 = __float_as_uint(V.hit_tuv[slot0].w);
+        }
+        const uint32_t n0 = V.counts[qi];
+        const bool valid0 = cap0 && slot0 < n0;
+        const bool miss0 = valid0 && inst0 == GK_NO_HIT, hit0 = valid0 && inst0 != GK_NO_HIT;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const unsigned bm = __ballot_sync(0xffffffffu, miss0), bh = __ballot_sync(0xffffffffu, hit0);
+        if (lane == 0) { s_cnt[0][w] = __popc(bm); s_cnt[1][w] = __popc(bh); }
+        __syncthreads();
+        uint32_t miss_before = 0, hit_before = 0, miss_total = 0, hit_total = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < w) { miss_before += s_cnt[0][k]; hit_before += s_cnt[1][k]; }
+            miss_total += s_cnt[0][k]; hit_total += s_cnt[1][k];
+        }
+        const unsigned below = (1u << lane) - 1u;
+        uint32_t dst;
+        if (miss0) dst = miss_before + __popc(bm & below);
+        else if (hit0) dst = miss_total + hit_before + __popc(bh & below);
+        else {  // slots beyond the queue keep the rest, in order
+            const unsigned bi = ~(bm | bh);
+            uint32_t inv_before = (uint32_t)w * 32u - miss_before - hit_before;
+            dst = miss_total + hit_total + inv_before + __popc(bi & below);
+        }
+        s_perm[dst] = (uint16_t)threadIdx.x;
+        __syncthreads();
+        slot = blockIdx.x * blockDim.x + s_perm[threadIdx.x];
+    }
+#else
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+#endif
     const bool in_cap = slot < (uint32_t)V.pixels;
     uint32_t sp = 0, hprim = 0;
     float4 hv = f4(0, 0, 0, 0);
@@ -1403,6 +1452,58 @@ __global__ void __launch_bounds__(128) k_tail(SceneView S_, const __grid_constan
         nany += __shfl_xor_sync(0xffffffffu, nany, o);
     }
     if ((threadIdx.x & 31) == 0) {
+        if (nclosest) atomicAdd(ray_counters + 1, (unsigned long long)nclosest);
+        if (nany) atomicAdd(ray_counters + 2, (unsigned long long)nany);
+    }
+}
+
+// The tail in segments: every thread advances its path by at most `max_rays` rays (0 = to the end), and the paths that are still alive are
+// compacted into the other queue for the next segment, so the warps of a segment start full again instead of thinning out to the few
+// longest paths (k_tail runs at 3.9 of 32 lanes). Segment `seg` reads queue (q0 + seg) & 1, q0 being the queue the wavefront stopped at, and
+// counts the entries it leaves behind in counts[17 + seg] (all zero at the start of the frame).
+__global__ void __launch_bounds__(128) k_tail_seg(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters,
+                                                  int seg, int max_rays) {
+    SceneView S = S_;
+    S.cam = &cam;
+    const int q0 = V.counts[3] ? (int)V.counts[3] - 1 : qi;
+    const int qin = (q0 + seg) & 1, qout = qin ^ 1;
+    const uint32_t n = seg == 0 ? V.counts[q0] : V.counts[16 + seg];
+    uint32_t* out_count = V.counts + 17 + seg;
+    PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
+    uint32_t nclosest = 0, nany = 0;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; __any_sync(0xffffffffu, slot < n); slot += gridDim.x * blockDim.x) {
+        const bool have = slot < n;
+        uint32_t pixel = 0;
+        int req = REQ_DONE;
+        PathRegs P;
+        if (have) {
+            const uint32_t sp = V.slot_pixel[qin][slot];
+            pixel = sp & 0x7FFFFFFFu;
+            load_slot(V, S, qin, slot, (sp & 0x80000000u) != 0, P);
+            req = (sp & 0x80000000u) ? REQ_ANY : REQ_CLOSEST;
+            for (int rays = 0; req != REQ_DONE && (max_rays == 0 || rays < max_rays); ++rays) {
+                Hit h;
+                if (req == REQ_ANY) { trace_ray<true>(S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h); nany++; }
+                else { trace_ray<false>(S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, h); nclosest++; }
+                req = advance(S, O, cfg, V, pixel, P, h);
+            }
+        }
+        const bool want = req != REQ_DONE;
+        const unsigned mask = __ballot_sync(0xffffffffu, want);
+        if (mask) {
+            const int leader = __ffs(mask) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(out_count, (uint32_t)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) store_slot(V, qout, base + __popc(mask & ((1u << lane) - 1u)), pixel, req, P);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nclosest += __shfl_xor_sync(0xffffffffu, nclosest, o);
+        nany += __shfl_xor_sync(0xffffffffu, nany, o);
+    }
+    if (lane == 0) {
         if (nclosest) atomicAdd(ray_counters + 1, (unsigned long long)nclosest);
         if (nany) atomicAdd(ray_counters + 2, (unsigned long long)nany);
     }
@@ -1762,7 +1863,13 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     for (int l = 0; l < lanes; ++l) {
         const uint32_t blocks = std::min<uint32_t>((pixels / lanes + 127) / 128, (uint32_t)c.sm_count * 16u);
         cudaEventRecord(c.lane_ev[l][0], ls[l]);
-        k_tail<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), p.tracer == 0 ? 1 : 0);
+        if (p.tracer == 0 && c.tail_segments > 0) {
+            for (int sg = 0; sg <= c.tail_segments; ++sg)  // the last segment runs every remaining path to its end
+                k_tail_seg<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), sg, sg < c.tail_segments ? c.tail_segment_rays[sg] : 0);
+            c.launches += c.tail_segments;
+        } else {
+            k_tail<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), p.tracer == 0 ? 1 : 0);
+        }
         cudaEventRecord(c.lane_ev[l][1], ls[l]);
         c.launches++;
         // per lane: primary / closest / any ray counters (3 x u64) and the wavefront statistics (rays, launches)
