@@ -3,7 +3,7 @@
 
 Workload (config.workload): BASELINE.json configs[1] — the RayTracingInOneWeekend procedural scene (RTIO.proc,
 src/Runtime/SceneList.cpp:117-178), 1920x1080, 16 spp, 8 bounces, sky, steady state (no node motion). A "step" is one
-frame through PathTracingRenderer::Render's pass sequence: TLAS rebuild -> rt pass -> reproject pass -> compose pass.
+frame through PathTracingRenderer::Render's pass sequence: TLAS update -> rt pass -> reproject pass -> compose pass.
 With N > 1 every rank holds a scene replica and traces 16 spp of a 16*N-spp frame (weak scaling over samples per pixel,
 SURVEY 8e); the un-normalised radiance sums are reduced to rank 0 with NCCL and rank 0 resolves + runs the post passes.
 
@@ -432,7 +432,7 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
 
     def frame(total_frames):
         ubo = scene.ubo(WIDTH, HEIGHT, total_frames)
-        r.PreRender()  # "TLAS Update": the reference rebuilds the TLAS every frame (RayTraceBaseRenderer.cpp:205-218)
+        r.PreRender()  # "TLAS Update" (RayTraceBaseRenderer.cpp:205-218): instance records + boxes from this frame's NodeProxy[], refit of the last full build (gkcu_set_tlas_refit)
         r.Render(ubo, params)
         if world > 1:
             reduce_ev[0].record(ext)
@@ -599,6 +599,7 @@ def run_ours(args, workload, steps, warmup, world, rank, local_rank, full):
             "tracer": "wavefront" if args.tracer == 0 else "megakernel",
             "rays_per_frame": {"primary": primary_rays / args.steps, "closest_hit": closest_rays / args.steps, "any_hit": any_rays / args.steps},
             "passes_ms_per_frame_rank0": {k: v / args.steps for k, v in pass_ms.items()},
+            "tlas_update": dict(r.tlas_stats(), policy="refit of the last full build while the same instances are active, full SAH build otherwise (gkcu_set_tlas_refit); counts since the context was created"),
             "without_kernel_events": {"ms_per_step": ms_plain / args.steps, "value": value * ms / ms_plain, "unit": "Mrays/s",
                                       "note": "same K frames with gkcu_set_kernel_timing(0): no per-launch event brackets inside the rt pass"},
         }

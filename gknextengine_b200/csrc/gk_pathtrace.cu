@@ -1756,7 +1756,10 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
         // things: the grids of the following waves (the queue can only shrink: every path has at most one successor, so an old size is
         // an upper bound) and to stop launching once a size at or below the threshold has come back. The GPU therefore always has
         // several waves queued (no launch gaps), and the few waves launched past the stop cost two empty kernels each.
-        tail_threshold = std::max<uint32_t>(pixels / (uint32_t)std::max(1, c.tail_div), (uint32_t)c.sm_count * 128u) / (uint32_t)lanes;
+        // hand-over once a wave is narrower than pixels / tail_div, but with no more paths than one residency round of k_tail holds
+        // (tail_cap per SM: at 4K pixels / 32 would be 3.5 rounds of it) and no fewer than a block per SM
+        tail_threshold = std::max<uint32_t>(std::min<uint32_t>(pixels / (uint32_t)std::max(1, c.tail_div), (uint32_t)c.sm_count * (uint32_t)c.tail_cap),
+                                            (uint32_t)c.sm_count * 128u) / (uint32_t)lanes;
         constexpr int kRing = 8;
         const int ahead = std::max(1, std::min(kRing - 1, c.wave_chunk));
         bool any = false;

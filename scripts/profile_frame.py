@@ -1,4 +1,4 @@
-"""Renders a few frames of the bench workload (for ncu): python scripts/profile_frame.py [frames] [tracer] [spp]"""
+"""Renders a few frames of the bench workload (for ncu): python scripts/profile_frame.py [frames] [tracer] [spp] [width] [height]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -6,7 +6,8 @@ from gknextengine_b200 import CudaPathTracingRenderer, GkcuFrameParams, host
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 tracer = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 spp = int(sys.argv[3]) if len(sys.argv) > 3 else 16
-W, H = 1920, 1080
+W = int(sys.argv[4]) if len(sys.argv) > 4 else 1920
+H = int(sys.argv[5]) if len(sys.argv) > 5 else 1080
 scene = host.Scene("RTIO.proc", samples=spp, bounces=8, taa=True, temporal_frames=16, denoiser=True)
 scene.update_nodes()
 r = CudaPathTracingRenderer(0)

@@ -126,7 +126,7 @@ def test_config3_gltf_scene_1080p_orbit_temporal_denoise(sky):
 
 def test_config4_100k_instances_tlas_rebuild_refit_and_hits(sky):
     """BASELINE configs[3]: the MagicaLego-shaped scene with 100 000 instances (~10 M instanced triangles; 32-bit instance ids, the reference
-    caps at 65 535), 1 % of the instances move per frame (full TLAS rebuild), one brick model is deformed (BLAS refit). 100 000 closest-hit and
+    caps at 65 535), 1 % of the instances move per frame (per-frame TLAS update: full build, then refits), one brick model is deformed (BLAS refit). 100 000 closest-hit and
     any-hit queries and two bands of a 1080p frame against the oracle (which rebuilds from scratch)."""
     W, H = 1920, 1080
     scene = host.Scene("LegoBricks.synth:100000", samples=1, bounces=4, taa=True, denoiser=True)

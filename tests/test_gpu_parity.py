@@ -469,8 +469,8 @@ def test_trace_rays_edge_cases(renderer):
 
 
 def test_blas_refit_and_dynamic_tlas(renderer):
-    """BASELINE config 4 shape at test size: instances move every frame (full TLAS rebuild) and one brick model is deformed
-    (BLAS refit). Hits must equal the oracle's (which rebuilds from scratch) and a refit must equal a rebuild."""
+    """BASELINE config 4 shape at test size: instances move every frame (per-frame TLAS update: refit of the last full build) and one brick
+    model is deformed (BLAS refit). Hits must equal the oracle's (which rebuilds from scratch) and a refit must equal a rebuild."""
     scene = host.Scene("LegoBricks.synth:4000")
     scene.update_nodes()
     osc, _ = setup_pair(renderer, scene, 64, 64)
@@ -586,7 +586,7 @@ def test_skip_unchanged_nodes_keeps_the_tlas_and_the_images(renderer):
     assert not np.array_equal(hg["inst"], first["inst"])
     renderer.set_skip_unchanged_nodes(False)
     renderer.PreRender()
-    assert renderer.timings()["tlas_update_ms"] > 0  # the default rebuilds every frame, like the reference
+    assert renderer.timings()["tlas_update_ms"] > 0  # the default updates the TLAS every frame (refit or rebuild)
 
 
 def test_sparse_node_updates_equal_full_uploads(renderer):
