@@ -1669,6 +1669,16 @@ int path_resize(Context& c) {
     if (!ok) return 1;
     // ranks other than 0 never write the direct-term plane; keep it defined for a host that resolves on such a context
     GK_CUDA(cudaMemsetAsync(b.direct.p, 0, n * 16, c.stream));
+    // k_shade requests its slot's records before it knows the queue size (see there): slots beyond the size are read and not used, so they
+    // only have to be defined (compute-sanitizer initcheck)
+    GK_CUDA(cudaMemsetAsync(b.rng.p, 0, 2 * m * 16, c.stream));
+    GK_CUDA(cudaMemsetAsync(b.ray_o.p, 0, 2 * m * 16, c.stream));
+    GK_CUDA(cudaMemsetAsync(b.ray_d.p, 0, 2 * m * 16, c.stream));
+    GK_CUDA(cudaMemsetAsync(b.ray_color.p, 0, 2 * m * 16, c.stream));
+    GK_CUDA(cudaMemsetAsync(b.slot_pixel[0].p, 0, m * 4, c.stream));
+    GK_CUDA(cudaMemsetAsync(b.slot_pixel[1].p, 0, m * 4, c.stream));
+    GK_CUDA(cudaMemsetAsync(b.hit_tuv.p, 0, m * 16, c.stream));
+    GK_CUDA(cudaMemsetAsync(b.hit_prim.p, 0, m * 4, c.stream));
     b.host_counts = c.pub_host + 64;
     return 0;
 }

@@ -73,3 +73,29 @@ for fmt in ("4", "8"):
         r.BeforeNextFrame()
     print("node format", fmt, r.counters())
     r.close()
+
+# ---- round 2, third session: TLAS refit / rebuild policy with moving instances, wavefront hand-over, segmented tail, variant knobs
+os.environ["GKCU_NODE_FORMAT"] = "4"
+os.environ["GKCU_TAIL_DIV"] = "4"          # the wavefront engages at this size and hands a wide tail over
+os.environ["GKCU_TAIL_SEGMENTS"] = "2:3"
+W, H = 224, 128
+scene = host.Scene("LegoBricks.synth:600", samples=2, bounces=4, taa=True, denoiser=True)
+scene.update_nodes()
+r = CudaPathTracingRenderer(0)
+r.CreateSwapChain((W, H))
+r.OnPostLoadScene(scene, host.make_sky(64, 32))
+p = GkcuFrameParams(temporal_frames=16, spp_world=1)
+for f in range(1, 6):
+    scene.jitter_instances(f, 0.05)
+    scene.update_nodes()
+    r.AfterUpdateScene(scene)
+    if f == 4: r.set_tlas_refit(True, 2)
+    r.PreRender()
+    r.Render(scene.ubo(W, H, f), p)
+    r.BeforeNextFrame()
+r.set_tlas_refit(False, 0)
+r.PreRender()
+r.trace(random_rays(2000, seed=5, center=(0, 1.5, 0), spread=8.0))
+print("tlas refit / segmented tail", r.tlas_stats(), r.counters())
+r.close()
+del os.environ["GKCU_TAIL_SEGMENTS"], os.environ["GKCU_TAIL_DIV"]
