@@ -424,7 +424,10 @@ GK_DEV void enqueue(const PathView& V, int qi, bool want, uint32_t pixel, int re
 // Primary visibility + G-buffer (FPathTracingRendererV2::Init/PrimaryHit, Shading.slang:1187-1241, with the visibility
 // buffer lookup of FVisibilityBufferRayCasterV2::TracePrimaryRay, :338-494, replaced by a closest-hit cast through the pixel
 // centre, where the raster pass samples), the buffer clear (Util.BufferClear.comp.slang:5-14), and the first ray of sample 0.
-__global__ void __launch_bounds__(128) k_primary(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, const __grid_constant__ PathLanes L, FrameCfg cfg, unsigned long long* ray_counters) {
+#ifndef GK_PRIMARY_MINB
+#define GK_PRIMARY_MINB 6  // resident blocks per SM k_primary is compiled for: 80 registers + 128 B more spill instead of 122 (4 blocks): 0.740 -> 0.673 ms at 1080p
+#endif
+__global__ void __launch_bounds__(128, GK_PRIMARY_MINB) k_primary(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, const __grid_constant__ PathLanes L, FrameCfg cfg, unsigned long long* ray_counters) {
     const PathView& V = L.v[(blockIdx.x + blockIdx.y) % L.n];  // checkerboard of tiles over the lanes
     SceneView S = S_;
     S.cam = &cam;  // the camera block is read through the constant bank (uniform loads), not through L1
@@ -1404,7 +1407,10 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
 #define GK_TAIL_VOTE 0
 #endif
 // Tail / megakernel: every thread runs its pixel's program to completion with the traversal inlined.
-__global__ void __launch_bounds__(128) k_tail(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters, int after_wavefront) {
+#ifndef GK_TAIL_MINB
+#define GK_TAIL_MINB 4  // 4 resident blocks per SM = at most 128 registers (127 used); 1 lets the compiler take 149 and the tail 3.7 ms instead of 2.7; 5 / 6 / 8 (96 / 80 / 64 registers): 2.76 / 3.22 / 3.41 ms
+#endif
+__global__ void __launch_bounds__(128, GK_TAIL_MINB) k_tail(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters, int after_wavefront) {
     SceneView S = S_;
     S.cam = &cam;
     if (after_wavefront && V.counts[3]) qi = (int)V.counts[3] - 1;  // the queue the device stopped the wavefront at (wave_stopped)
