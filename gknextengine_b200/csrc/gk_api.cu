@@ -168,6 +168,7 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
             if (*q) ++q;
         }
     }
+    if (const char* e = getenv("GKCU_TAIL_FUSED")) c.tail_fused = atoi(e) != 0;
     if (const char* e = getenv("GKCU_TAIL_CAP")) c.tail_cap = std::max(128, std::min(1 << 20, atoi(e)));
     if (const char* e = getenv("GKCU_TAIL_DIV")) c.tail_div = std::max(1, std::min(65536, atoi(e)));
     if (const char* e = getenv("GKCU_WAVE_CHUNK")) c.wave_chunk = std::max(1, std::min(7, atoi(e)));

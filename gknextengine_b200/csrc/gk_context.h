@@ -155,6 +155,7 @@ struct Context {
     cudaStream_t lane_stream[4] = {};
     cudaEvent_t lane_ev[4][4] = {};  // per lane: tail begin / end, done; [0][3]: primary done
     int tail_cap = 448;        // GKCU_TAIL_CAP: most paths per SM the wavefront hands to k_tail (k_tail: 127 registers, 512 resident threads per SM)
+    int tail_fused = 0;        // GKCU_TAIL_FUSED=1: the tail runs as persistent vote-scheduled warps (k_tail_fused) instead of one thread per path
     int tail_segments = 0;     // GKCU_TAIL_SEGMENTS=a,b,c: the tail runs as segments of at most a, b, c rays per path with a compaction between them, then to the end (k_tail_seg); 0 = one k_tail launch
     int tail_segment_rays[14] = {};
     int tail_div = 32;         // the wavefront hands over to k_tail once the wave is narrower than pixels / tail_div (GKCU_TAIL_DIV); 32 since the loop has no host waits: rt pass 28.2 -> 27.3 ms against 64, profiles/r02_experiments.md section 10

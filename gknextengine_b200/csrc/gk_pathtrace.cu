@@ -1515,6 +1515,93 @@ __global__ void __launch_bounds__(128) k_tail_seg(SceneView S_, const __grid_con
     }
 }
 
+// The tail as persistent warps that schedule by vote: every lane owns one path and is either walking its pending ray (node step /
+// instance entry / triangle leaf, as in k_trace) or waiting to shade its hit; each iteration the warp runs the one step kind most of its
+// lanes wait for, so a lane does not wait for the longest ray of its warp before it shades (k_tail), and lanes whose path has ended pull the
+// next slot of the tail queue. Same per-path sequence of rays and the same `advance`, so the same bits. counts[15] is the queue cursor
+// (zero at the start of the frame).
+#ifndef GK_FUSED_REFILL
+#define GK_FUSED_REFILL 8  // idle lanes that make the warp go back for more paths while the queue has some
+#endif
+__global__ void __launch_bounds__(128, 4) k_tail_fused(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi,
+                                                       unsigned long long* ray_counters, int after_wavefront) {
+    SceneView S = S_;
+    S.cam = &cam;
+    if (after_wavefront && V.counts[3]) qi = (int)V.counts[3] - 1;
+    const uint32_t n = V.counts[qi];
+    PixelOut O{R, V.radiance, V.direct, (size_t)R.w * R.h};
+    const int lane = threadIdx.x & 31;
+    uint32_t nclosest = 0, nany = 0;
+    LocalStack stack;
+    Trav T;
+    WorldRegs world;
+    PathRegs P;
+    uint32_t pixel = 0;
+    int req = REQ_DONE;
+    bool has_path = false, drained = false;
+    uint32_t guard = 0;
+    T.done = true; T.cur = 0; T.cur_inst = GK_NO_HIT;
+    for (;;) {
+        if (!drained) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !has_path);
+            if (idle) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(V.counts + 15, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!has_path) {
+                    const uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
+                    if (slot < n) {
+                        const uint32_t sp = V.slot_pixel[qi][slot];
+                        pixel = sp & 0x7FFFFFFFu;
+                        load_slot(V, S, qi, slot, (sp & 0x80000000u) != 0, P);
+                        req = (sp & 0x80000000u) ? REQ_ANY : REQ_CLOSEST;
+                        trav_init<4>(T, world, S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, req == REQ_ANY);
+                        has_path = true;
+                    }
+                }
+                if (base + (uint32_t)__popc(idle) >= n) drained = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, has_path)) break;
+        for (;;) {
+            const bool tracing = has_path && !T.done;
+            const bool leaf = (T.cur & GK_LEAF_BIT) != 0;
+            const bool wN = tracing && !leaf;
+            const bool wI = tracing && leaf && T.cur_inst == GK_NO_HIT;
+            const bool wT = tracing && leaf && T.cur_inst != GK_NO_HIT;
+            const bool wS = has_path && T.done;
+            const int nN = __popc(__ballot_sync(0xffffffffu, wN)), nI = __popc(__ballot_sync(0xffffffffu, wI)), nT = __popc(__ballot_sync(0xffffffffu, wT)),
+                      nS = __popc(__ballot_sync(0xffffffffu, wS));
+            const int busy = nN + nI + nT + nS;
+            if (busy == 0) break;
+            if (++guard > (1u << 27)) { if (lane == 0) V.counts[14] = 0xDEADu; return; }  // cannot happen; a scheduling bug must not hang the device
+            if (!drained && 32 - busy >= GK_FUSED_REFILL) break;  // enough idle lanes: fetch more paths
+            if (nN >= nT && nN >= nI && nN >= nS) {
+                if (wN) trav_node_step<4>(T, world, S.ts, stack);
+            } else if (nT >= nI && nT >= nS) {
+                if (wT) trav_leaf_step<4>(T, world, S.ts, stack);
+            } else if (nI >= nS) {
+                if (wI) trav_leaf_step<4>(T, world, S.ts, stack);
+            } else if (wS) {
+                const Hit h = T.best;
+                if (req == REQ_ANY) nany++; else nclosest++;
+                req = advance(S, O, cfg, V, pixel, P, h);
+                if (req == REQ_DONE) has_path = false;
+                else trav_init<4>(T, world, S.ts, P.ro, P.rd, GK_EPS, GK_PT_MAX_TRACE_DISTANCE, req == REQ_ANY);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nclosest += __shfl_xor_sync(0xffffffffu, nclosest, o);
+        nany += __shfl_xor_sync(0xffffffffu, nany, o);
+    }
+    if (lane == 0) {
+        if (nclosest) atomicAdd(ray_counters + 1, (unsigned long long)nclosest);
+        if (nany) atomicAdd(ray_counters + 2, (unsigned long long)nany);
+    }
+}
+
 // Multi-GPU resolve: SINGLE_* = sums / S + direct (Shading.slang:1175-1183) after the NCCL reduce.
 __global__ void k_resolve(RTView R, const float4* __restrict__ radiance, const float4* __restrict__ direct, const uint16_t* __restrict__ moment,
                           const GkUniformBufferObject* __restrict__ C) {
@@ -1882,7 +1969,11 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
     for (int l = 0; l < lanes; ++l) {
         const uint32_t blocks = std::min<uint32_t>((pixels / lanes + 127) / 128, (uint32_t)c.sm_count * 16u);
         cudaEventRecord(c.lane_ev[l][0], ls[l]);
-        if (p.tracer == 0 && c.tail_segments > 0) {
+        if (p.tracer == 0 && c.tail_fused && c.node_format == 4) {
+            // one warp per 32 paths up to what is resident at once; the warps refill from the queue beyond that
+            const uint32_t fb = std::min<uint32_t>((std::max<uint32_t>(tail_threshold == 0xFFFFFFFFu ? pixels / lanes : tail_threshold, 128u) + 127) / 128, (uint32_t)c.sm_count * 4u);
+            k_tail_fused<<<fb, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), 1);
+        } else if (p.tracer == 0 && c.tail_segments > 0) {
             for (int sg = 0; sg <= c.tail_segments; ++sg)  // the last segment runs every remaining path to its end
                 k_tail_seg<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), sg, sg < c.tail_segments ? c.tail_segment_rays[sg] : 0);
             c.launches += c.tail_segments;
