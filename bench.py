@@ -64,7 +64,30 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.proc = None
 
+    def run_nvml(self):
+        """NVML polled every 10 ms: the timed region of the default run is ~0.3 s, nvidia-smi's loop would see it once or twice."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), 2), (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), 3),
+                (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), 4), (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), 5)]
+        self.nvml_running = True
+        while self.nvml_running:
+            r = get_reasons(h)
+            row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", "", "", ""]
+            for mask, col in bits:
+                row[col] = "Active" if (r & mask) else "Not Active"
+            self.samples.append(row)
+            time.sleep(0.01)
+
     def run(self):
+        try:
+            self.run_nvml()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -78,6 +101,7 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self.nvml_running = False
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
