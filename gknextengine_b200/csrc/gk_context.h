@@ -147,7 +147,7 @@ struct Context {
     cudaEvent_t wev[4][24] = {};  // per lane: trace/shade brackets of the last 8 waves (ring)
     cudaEvent_t pev[4][8] = {};   // per lane: "queue size of wave k has reached the host" (ring, no timing)
     int wave_seen[4] = {}, wave_launched[4] = {};  // waves of the last frame whose events the host has read / that were launched
-    int kernel_timing = 1;        // GKCU_KERNEL_TIMING=0: no per-wave event brackets (GkcuKernelStats.trace_ms / shade_ms stay 0)
+    int kernel_timing = 0;        // per-wave event brackets for GkcuKernelStats.trace_ms / shade_ms (~4 us each, 0.45 ms per bench frame): off by default, gkcu_set_kernel_timing(ctx, 1) / GKCU_KERNEL_TIMING=1 turn them on
     // The frame's pixels can be dealt to `lanes` independent wavefronts on their own streams (checkerboard of 8 x 16 tiles), so one
     // lane's shade kernel and the thin end of its trace kernel overlap the other lanes' kernels (GKCU_LANES, 1..4). Measured: 2 lanes
     // -0.7 %, 3 lanes +2 %, 4 lanes +5 % (the kernels already fill the GPU; overlap only shares it), so the default is one lane.

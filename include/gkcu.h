@@ -466,7 +466,8 @@ int gkcu_get_timings(GkcuContext* ctx, GkcuTimings* out);
 int gkcu_get_counters(GkcuContext* ctx, GkcuCounters* out);
 int gkcu_get_kernel_stats(GkcuContext* ctx, GkcuKernelStats* out);
 /* Per-launch CUDA-event brackets around the k_trace / k_shade launches of the wavefront (GkcuKernelStats.trace_ms / shade_ms) cost about
- * 4 us per event, 0.7 ms on a 60-wave frame. On (1) by default; 0 leaves trace_ms / shade_ms at 0 and the frame without those gaps. */
+ * 4 us per event, 0.45 ms on the 43-wave bench frame. Off (0) by default: trace_ms / shade_ms then stay 0; profiling callers (bench.py's
+ * device-resident leg, the scripts under scripts/) turn them on. */
 int gkcu_set_kernel_timing(GkcuContext* ctx, uint32_t enabled);
 /* Compose pass (Process.DenoiseJBF.comp.slang) with the GPU's approximate exp / pow and a reciprocal instead of the pinned software
  * transcendentals and the IEEE division: RT_DENOISED then differs from the pinned build by at most 4 fp16 ulps per channel, relative RMSE

@@ -11,6 +11,7 @@ H = int(sys.argv[5]) if len(sys.argv) > 5 else 1080
 scene = host.Scene("RTIO.proc", samples=spp, bounces=8, taa=True, temporal_frames=16, denoiser=True)
 scene.update_nodes()
 r = CudaPathTracingRenderer(0)
+r.set_kernel_timing(True)  # per-launch event brackets: kernel_stats() needs them
 r.CreateSwapChain((W, H))
 r.OnPostLoadScene(scene, host.make_sky(1024, 512))
 p = GkcuFrameParams(temporal_frames=16, spp_world=1, tracer=tracer)

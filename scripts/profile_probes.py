@@ -8,6 +8,7 @@ scene = host.Scene("RTIO.proc", samples=16, bounces=8, taa=True, temporal_frames
 scene.update_nodes()
 sky = host.make_sky(1024, 512)
 r = CudaPathTracingRenderer(0)
+r.set_kernel_timing(True)  # per-launch event brackets: kernel_stats() needs them
 r.CreateSwapChain((W, H))
 r.OnPostLoadScene(scene, sky)
 r.set_lights(scene); r.set_sky_sh(0, host.project_sh(sky))

@@ -28,6 +28,7 @@ def config1():
     scene = host.Scene("CornellBox.proc", samples=1, bounces=4, taa=False)
     scene.update_nodes()
     r = CudaPathTracingRenderer(0)
+    r.set_kernel_timing(True)  # per-launch event brackets: kernel_stats() needs them
     r.CreateSwapChain((W, H))
     r.OnPostLoadScene(scene)
     osc, ofr = O.OracleScene(scene), O.OracleFrame(W, H)
