@@ -19,7 +19,7 @@
 #define GK_NODE_REPEAT 1
 #endif
 #ifndef GK_TRACE_MINB
-#define GK_TRACE_MINB 6  // resident blocks per SM k_trace<5> is compiled for (6 -> 80 registers; 8 -> 64 is 6% slower since the fp32 nodes)
+#define GK_TRACE_MINB 7  // resident blocks per SM k_trace<5> is compiled for and its carve-out is sized for (70 registers fit 7; compiled for 6 it ran 0.6 % slower on a carve-out one block short, 8 -> 64 registers is 2.4 % slower)
 #endif
 #include "gk_context.h"
 #include "gk_shading.cuh"
