@@ -378,11 +378,19 @@ GK_DEV void store_slot(const PathView& V, int qi, uint32_t slot, uint32_t pixel,
     }
 }
 // the four records every slot has, as loaded (k_shade issues these loads before it knows the queue size, see there)
+#ifndef GK_SHADE_LDCS
+#define GK_SHADE_LDCS 1  // slot and hit records are read once: ld.global.cs keeps them from displacing the shading records (k_shade 6.37 -> 6.33 ms)
+#endif
 struct SlotRaw { float4 o, d, ray_color; uint4 rng; };
 GK_DEV SlotRaw load_slot_raw(const PathView& V, int qi, uint32_t slot) {
     const size_t i = (size_t)qi * V.pixels + slot;
     SlotRaw r;
+#if GK_SHADE_LDCS
+    // read once: streamed past the caches the gathers of the shading records live in
+    r.o = __ldcs(V.ray_o + i); r.d = __ldcs(V.ray_d + i); r.rng = __ldcs(V.rng + i); r.ray_color = __ldcs(V.ray_color + i);
+#else
     r.o = V.ray_o[i]; r.d = V.ray_d[i]; r.rng = V.rng[i]; r.ray_color = V.ray_color[i];
+#endif
     return r;
 }
 GK_DEV void load_slot(const PathView& V, const SceneView& S, int qi, uint32_t slot, bool any, PathRegs& P, const SlotRaw* raw = nullptr) {
@@ -1354,9 +1362,15 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
     float4 hv = f4(0, 0, 0, 0);
     SlotRaw raw{};
     if (in_cap) {
+#if GK_SHADE_LDCS
+        sp = __ldcs(V.slot_pixel[qi] + slot);
+        hv = __ldcs(V.hit_tuv + slot);
+        hprim = __ldcs(V.hit_prim + slot);
+#else
         sp = V.slot_pixel[qi][slot];
         hv = V.hit_tuv[slot];
         hprim = V.hit_prim[slot];
+#endif
         raw = load_slot_raw(V, qi, slot);
     }
     const uint4 hdr = *reinterpret_cast<const uint4*>(V.counts);  // queue sizes, trace cursor, stop flag: one load
