@@ -94,6 +94,19 @@ GK_DEV float safe_rcp(float x) {
     return __frcp_rn(x);  // correctly rounded, == 1.0f / x
 }
 GK_DEV float sel3(int k, float3 v) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+// Node load: read-only path; GK_NODE_EVICT_LAST = 1 asks L1 to keep node lines over the streamed data (experiment)
+#ifndef GK_NODE_EVICT_LAST
+#define GK_NODE_EVICT_LAST 0
+#endif
+GK_DEV uint4 ld_node(const uint4* p) {
+#if GK_NODE_EVICT_LAST
+    uint4 v;
+    asm("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 // 256-bit read-only global load (sm_100: LDG.E.ENL2.256), p must be 32-byte aligned
 GK_DEV void ld256(const void* p, float (&v)[8]) {
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -395,10 +408,10 @@ GK_DEV bool trav_node_core4(Trav& T, St& stack) {
     }
     const uint4 n1 = __ldg(np + 6);
 #else
-    const uint4 nx = __ldg(np + ix), fx = __ldg(np + (ix ^ 1u));
-    const uint4 ny = __ldg(np + 2 + iy), fy = __ldg(np + 2 + (iy ^ 1u));
-    const uint4 nz = __ldg(np + 4 + iz), fz = __ldg(np + 4 + (iz ^ 1u));
-    const uint4 n1 = __ldg(np + 6);
+    const uint4 nx = ld_node(np + ix), fx = ld_node(np + (ix ^ 1u));
+    const uint4 ny = ld_node(np + 2 + iy), fy = ld_node(np + 2 + (iy ^ 1u));
+    const uint4 nz = ld_node(np + 4 + iz), fz = ld_node(np + 4 + (iz ^ 1u));
+    const uint4 n1 = ld_node(np + 6);
     const float pnx[4] = {__uint_as_float(nx.x), __uint_as_float(nx.y), __uint_as_float(nx.z), __uint_as_float(nx.w)};
     const float pfx[4] = {__uint_as_float(fx.x), __uint_as_float(fx.y), __uint_as_float(fx.z), __uint_as_float(fx.w)};
     const float pny[4] = {__uint_as_float(ny.x), __uint_as_float(ny.y), __uint_as_float(ny.z), __uint_as_float(ny.w)};
