@@ -168,6 +168,9 @@ int gkcu_create(int device_ordinal, GkcuContext** out_ctx) {
             if (*q) ++q;
         }
     }
+    if (const char* e = getenv("GKCU_TAIL_SORT")) c.tail_sort = atoi(e) != 0;
+    if (const char* e = getenv("GKCU_TAIL_SOLO")) c.tail_solo = std::max(0, std::min(1 << 20, atoi(e)));
+    if (const char* e = getenv("GKCU_TAIL_SPREAD")) c.tail_spread = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("GKCU_TAIL_FUSED")) c.tail_fused = atoi(e) != 0;
     if (const char* e = getenv("GKCU_TAIL_CAP")) c.tail_cap = std::max(128, std::min(1 << 20, atoi(e)));
     if (const char* e = getenv("GKCU_TAIL_DIV")) c.tail_div = std::max(1, std::min(65536, atoi(e)));

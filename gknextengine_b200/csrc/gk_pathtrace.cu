@@ -65,6 +65,7 @@ struct PathBuffers {
     DevBuf ray_o, ray_d, slot_pixel[2], hit_tuv, hit_prim, counts, radiance, direct;
     DevBuf sort_keys[2], sort_vals[2], sort_tmp;  // ray reordering (GKCU_SORT_RAYS)
     size_t sort_tmp_bytes = 0;
+    DevBuf tail_order, tail_hist;  // GKCU_TAIL_SORT: tail slots ordered by the samples their pixel still has to run, and the 2 x 128 bucket counters per lane
     DevBuf pool_stack;  // k_trace_pool / k_trace_wpool: traversal stacks, [lane][block (, warp)][depth][slot]
     size_t pool_stack_stride = 0;  // uint2 entries per lane
     uint32_t* host_counts = nullptr;  // Context::pub_host + 64: mapped pinned memory, 64 words per lane, written by kernels
@@ -1417,6 +1418,38 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
     }
 }
 
+// GKCU_TAIL_SORT: the tail's slots ordered by how many samples their pixel still has to run, longest first, so that the paths of a warp
+// end at about the same time and the longest ones start in the first blocks (counting sort: 128 buckets, three small kernels).
+GK_DEV uint32_t tail_key(const PathView& V, int qi, uint32_t slot) {
+    const uint32_t pixel = V.slot_pixel[qi][slot] & 0x7FFFFFFFu;
+    const uint32_t sample = __float_as_uint(V.ray_d[(size_t)qi * V.pixels + slot].w) & 0xFFFFu;
+    const uint32_t end = __float_as_uint(V.prim_nrm_cnt[pixel].w) & 0xFFFFu;
+    const uint32_t rem = end > sample ? end - sample : 0u;
+    return 127u - min(rem, 127u);
+}
+__global__ void k_tail_hist(PathView V, int qi, uint32_t* __restrict__ hist) {
+    if (V.counts[3]) qi = (int)V.counts[3] - 1;
+    const uint32_t n = V.counts[qi];
+    __shared__ uint32_t s_h[128];
+    if (threadIdx.x < 128) s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) atomicAdd(&s_h[tail_key(V, qi, slot)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 128 && s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_h[threadIdx.x]);
+}
+__global__ void k_tail_scan(uint32_t* __restrict__ hist) {  // hist[0..127] counts -> hist[128..255] first position of each bucket
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int k = 0; k < 128; ++k) { hist[128 + k] = acc; acc += hist[k]; }
+    }
+}
+__global__ void k_tail_scatter(PathView V, int qi, uint32_t* __restrict__ hist, uint32_t* __restrict__ order) {
+    if (V.counts[3]) qi = (int)V.counts[3] - 1;
+    const uint32_t n = V.counts[qi];
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x)
+        order[atomicAdd(&hist[128 + tail_key(V, qi, slot)], 1u)] = slot;
+}
+
 #ifndef GK_TAIL_VOTE
 #define GK_TAIL_VOTE 0
 #endif
@@ -1424,7 +1457,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView S_, const __grid_
 #ifndef GK_TAIL_MINB
 #define GK_TAIL_MINB 4  // 4 resident blocks per SM = at most 128 registers (127 used); 1 lets the compiler take 149 and the tail 3.7 ms instead of 2.7; 5 / 6 / 8 (96 / 80 / 64 registers): 2.76 / 3.22 / 3.41 ms
 #endif
-__global__ void __launch_bounds__(128, GK_TAIL_MINB) k_tail(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters, int after_wavefront) {
+__global__ void __launch_bounds__(128, GK_TAIL_MINB) k_tail(SceneView S_, const __grid_constant__ GkUniformBufferObject cam, RTView R, PathView V, FrameCfg cfg, int qi, unsigned long long* ray_counters, int after_wavefront, const uint32_t* __restrict__ order, int spread, int solo) {
     SceneView S = S_;
     S.cam = &cam;
     if (after_wavefront && V.counts[3]) qi = (int)V.counts[3] - 1;  // the queue the device stopped the wavefront at (wave_stopped)
@@ -1453,7 +1486,22 @@ __global__ void __launch_bounds__(128, GK_TAIL_MINB) k_tail(SceneView S_, const 
         }
     }
 #else
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+    // Ordered tail: rank r of the longest-first order goes to warp r mod W, so the W longest paths sit in W different warps (the long paths of
+    // a frame are neighbours on screen - the pixels of a glass ball - and in queue order they share warps, where every bounce of one waits
+    // for the divergent bounces of the others) and a warp holds about `spread` paths.
+    uint32_t at0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (order) {
+        const uint32_t grid_warps = gridDim.x * (blockDim.x >> 5);
+        const uint32_t K = min((uint32_t)solo, min(n, grid_warps / 2u));  // the K longest paths get a warp each
+        const uint32_t rest = n - K;
+        const uint32_t W = max(1u, min(grid_warps - K, (rest + (uint32_t)spread - 1u) / (uint32_t)spread));
+        const uint32_t w = at0 >> 5, lane = threadIdx.x & 31u;
+        if (w < K) { at0 = lane == 0 ? w : n; stride = n; }
+        else if (w - K >= W) at0 = n;  // this warp has no part in the ordered tail
+        else { at0 = K + lane * W + (w - K); stride = 32u * W; }
+    }
+    for (uint32_t at = at0; at < n; at += stride) {
+        const uint32_t slot = order ? order[at] : at;
         uint32_t sp = V.slot_pixel[qi][slot];
         uint32_t pixel = sp & 0x7FFFFFFFu;
         PathRegs P;
@@ -1764,7 +1812,7 @@ int path_resize(Context& c) {
               b.ray_color.reserve(2 * m * 16) && b.final_color.reserve(n * 16) && b.final_refl.reserve(n * 16) && b.prim_pos_mat.reserve(n * 16) &&
               b.prim_nrm_cnt.reserve(n * 16) && b.prim_albedo.reserve(n * 16) && b.ray_o.reserve(2 * m * 16) && b.ray_d.reserve(2 * m * 16) &&
               b.slot_pixel[0].reserve(m * 4) && b.slot_pixel[1].reserve(m * 4) && b.hit_tuv.reserve(m * 16) && b.hit_prim.reserve(m * 4) &&
-              b.counts.reserve(4 * 64 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16) &&
+              b.counts.reserve(4 * 64 * 4) && b.tail_order.reserve(m * 4) && b.tail_hist.reserve(4 * 256 * 4) && b.radiance.reserve(2 * n * 16) && b.direct.reserve(n * 16) &&
               b.pool_stack.reserve((size_t)b.lanes * c.sm_count * std::max<size_t>((size_t)GK_POOL_MINB * GK_POOL, (size_t)GK_WPOOL_MINB * 4 * GK_WPOOL) * GK_TRAV_STACK * sizeof(uint2));
     if (c.sort_rays) {
         size_t tmp = 0;
@@ -1794,7 +1842,7 @@ void path_release(Context& c) {
     if (!c.path) return;
     PathBuffers& b = *c.path;
     for (DevBuf* d : {&b.rng, &b.pos_mat, &b.nrm_flags, &b.dir_cnt, &b.ray_color, &b.final_color, &b.final_refl, &b.prim_pos_mat, &b.prim_nrm_cnt,
-                      &b.prim_albedo, &b.ray_o, &b.ray_d, &b.slot_pixel[0], &b.slot_pixel[1], &b.hit_tuv, &b.hit_prim, &b.counts, &b.radiance, &b.direct, &b.pool_stack, &b.sort_keys[0], &b.sort_keys[1], &b.sort_vals[0], &b.sort_vals[1], &b.sort_tmp})
+                      &b.prim_albedo, &b.ray_o, &b.ray_d, &b.slot_pixel[0], &b.slot_pixel[1], &b.hit_tuv, &b.hit_prim, &b.counts, &b.tail_order, &b.tail_hist, &b.radiance, &b.direct, &b.pool_stack, &b.sort_keys[0], &b.sort_keys[1], &b.sort_vals[0], &b.sort_vals[1], &b.sort_tmp})
         d->release();
     delete c.path;
     c.path = nullptr;
@@ -1992,7 +2040,19 @@ int run_rt_pass(Context& c, const GkUniformBufferObject& ubo, const GkcuFramePar
                 k_tail_seg<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), sg, sg < c.tail_segments ? c.tail_segment_rays[sg] : 0);
             c.launches += c.tail_segments;
         } else {
-            k_tail<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), p.tracer == 0 ? 1 : 0);
+            const uint32_t* order = nullptr;
+            if (p.tracer == 0 && c.tail_sort && ubo.NumberOfSamples > 1) {  // with one sample per pixel the paths end within a few rays of each other: nothing to order
+                uint32_t* hist = b.tail_hist.as<uint32_t>() + 256 * l;
+                uint32_t* ord = b.tail_order.as<uint32_t>() + (size_t)l * b.lane_cap;
+                const uint32_t sb = std::max<uint32_t>(1u, std::min<uint32_t>((tail_threshold == 0xFFFFFFFFu ? pixels / lanes : tail_threshold) / 256u + 1u, (uint32_t)c.sm_count * 4u));
+                GK_CUDA(cudaMemsetAsync(hist, 0, 256 * 4, ls[l]));
+                k_tail_hist<<<sb, 256, 0, ls[l]>>>(L.v[l], qi[l], hist);
+                k_tail_scan<<<1, 32, 0, ls[l]>>>(hist);
+                k_tail_scatter<<<sb, 256, 0, ls[l]>>>(L.v[l], qi[l], hist, ord);
+                c.launches += 3;
+                order = ord;
+            }
+            k_tail<<<blocks, 128, 0, ls[l]>>>(S, ubo, R, L.v[l], cfg, qi[l], ray_counters_of(l), p.tracer == 0 ? 1 : 0, order, c.tail_spread, c.tail_solo);
         }
         cudaEventRecord(c.lane_ev[l][1], ls[l]);
         c.launches++;
