@@ -18,6 +18,6 @@ done
 # roofline.achieved which is the mean over the same launches)
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k 'regex:k_trace|k_shade' -c 400 --csv \
     --log-file $O/${TAG}_frame_traffic.csv python scripts/profile_frame.py 1 > $O/${TAG}_frame_traffic.log 2>&1
-ncu --set full --clock-control none --import-source on -k 'regex:k_reproject|k_denoise|k_primary|k_tail' -c 6 -o $O/${TAG}_prof_misc -f \
+ncu --set full --clock-control none --import-source on -k 'regex:k_reproject|k_denoise|k_primary|k_tail$' -c 4 -o $O/${TAG}_prof_misc -f \
     python scripts/profile_frame.py 1 > $O/${TAG}_prof_misc.log 2>&1
 ls -la $O | tail -12
