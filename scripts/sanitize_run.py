@@ -98,4 +98,17 @@ r.PreRender()
 r.trace(random_rays(2000, seed=5, center=(0, 1.5, 0), spread=8.0))
 print("tlas refit / segmented tail", r.tlas_stats(), r.counters())
 r.close()
-del os.environ["GKCU_TAIL_SEGMENTS"], os.environ["GKCU_TAIL_DIV"]
+del os.environ["GKCU_TAIL_SEGMENTS"]
+# the default tail: slots ordered by remaining samples (k_tail_hist / scan / scatter), then the fused vote-scheduled variant
+for fused in ("0", "1"):
+    os.environ["GKCU_TAIL_FUSED"] = fused
+    r = CudaPathTracingRenderer(0)
+    r.CreateSwapChain((W, H))
+    r.OnPostLoadScene(scene, host.make_sky(64, 32))
+    for f in range(1, 3):
+        r.PreRender()
+        r.Render(scene.ubo(W, H, f), p)
+        r.BeforeNextFrame()
+    print("ordered tail, fused =", fused, r.counters())
+    r.close()
+del os.environ["GKCU_TAIL_FUSED"], os.environ["GKCU_TAIL_DIV"]
