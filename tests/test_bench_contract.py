@@ -39,6 +39,34 @@ def test_committed_round_profile_carries_the_contract():
         assert j["roofline_stencils"][k]["bound"] == "issue" and 0 < j["roofline_stencils"][k]["issue_frac"] < 1
 
 
+def test_committed_round2_profile_carries_the_contract():
+    """profiles/r02_bench_n1.json: the line of the final round-2 code. The end-to-end leg runs the library defaults (no per-launch event brackets), so it
+    may read above the device-resident value, whose timed region carries them for the roofline; both must be consistent with the frame without
+    brackets. The multi-GPU lines of the same code carry the strong-scaling block."""
+    load = lambda name: json.loads([ln for ln in open(os.path.join(ROOT, "profiles", name)).read().splitlines() if ln.strip().startswith("{")][-1])
+    j = load("r02_bench_n1.json")
+    assert BASE_KEYS <= set(j) and j["n_gpus"] == 1 and j["warmup"] >= 3 and j["gpu_launches"] > 0 and j["data"].startswith("synthetic")
+    assert j["metric"] == "Mrays/s" and j["dtype"] == "f32" and j["vs_baseline"] is None and "workload" in j["config"] and "l2" in j["config"]
+    r = j["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0 and r["kernel"] == "k_trace"
+    assert 0.5 < r["share_of_step"] < 0.75 and r["launches"] == 42 * j["steps"]
+    e, plain = j["e2e"], j["without_kernel_events"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 1920 * 1080 * 8 and "defaults" in e["note"]
+    assert plain["ms_per_step"] < j["ms_per_step"] and plain["ms_per_step"] <= e["ms_per_step"] < 1.1 * j["ms_per_step"]
+    c = j["clocks"]
+    assert c["samples"] >= 3 and c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    cb = j["cpu_baseline"]
+    assert cb["value"] > 0 and cb["cores"] >= 1 and cb["kind"] == "reference" and "tinybvh" in cb["sample"]
+    assert j["tlas_update"]["refits"] > j["tlas_update"]["builds"] >= 1
+    s1 = j["strong"]
+    assert s1["scaling"] == "strong" and s1["width"] == 3840 and s1["spp_per_gpu"] == 64
+    for n in (2, 8):
+        m = load(f"r02_bench_n{n}.json")
+        assert m["n_gpus"] == n and m["scaling"] == "weak" and 0.97 * n < m["value"] / j["value"] < 1.03 * n
+        sn = m["strong"]
+        assert sn["scaling"] == "strong" and sn["spp_per_gpu"] == 64 // n and 0.85 * n < s1["ms_per_step"] / sn["ms_per_step"] <= n
+
+
 def test_cpu_baseline_reference_and_port_trace_the_same_rays_and_threads_do_not_change_results():
     """bench.py's CPU baseline: the compiled reference shaders (kind "reference", multi-threaded over rows) and the oracle port must count the
     same rays on the same band of the bench frame, and the thread count must not change a single pixel."""
